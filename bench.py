@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- MLUPS of the D3Q27 f+g (fp64) lattice update on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--size 512] [--impl ours|reference]
+
+A "step" is one coarse time step of the single-level periodic box (BASELINE.json config 3,
+the Taylor-Green deck at SIZE^3 cells per GPU): ghost fill, pull-stream of f and g, macrodata,
+q-correction, equilibrium, BGK relax.  N > 1 is launched by torchrun, one rank per GPU, z-slabs,
+weak scaling (SIZE^3 per GPU, domain SIZE x SIZE x N*SIZE), ghost planes over NCCL/NVLink.
+Rank 0 prints ONE JSON line (contract in the task prompt / DESIGN.md "Measurement").
+
+ value      whole-job MLUPS, state resident in HBM, CUDA events, max over ranks
+ e2e        the same metric through the host-buffer call (mbl_step_host): every step uploads f,g from
+            pinned host memory and downloads the result
+ roofline   dominant kernel (collide pass): 864 algorithmic bytes per cell update / its device time,
+            against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+ cpu_baseline  the unmodified reference (oracle/_ref, OpenMP) on the host cores, bounded sample
+
+--impl reference times the reference's own CPU implementation (oracle/_ref) on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BYTES_PER_CELL = 864  # (27 f + 27 g) x 8 B x (read + write): SURVEY.md section 8(d)
+
+TG_DECK = """
+max_step = 1000000
+geometry.prob_lo = -1.0 -1.0 -1.0
+geometry.prob_hi =  1.0  1.0  1.0
+geometry.is_periodic = 1 1 1
+amr.n_cell = {nx} {ny} {nz}
+amr.max_level = 0
+amr.max_grid_size = {mgs}
+amr.plot_int = -1
+amr.chk_int = -1
+lbm.bc_lo = 0 0 0
+lbm.bc_hi = 0 0 0
+lbm.dx_outer = 1.0
+lbm.dt_outer = 1.0
+lbm.nu = 0.1733333333333333
+lbm.save_streaming = 0
+lbm.ic_type = "taylorgreen"
+ic_taylorgreen.rho0 = 1.0
+ic_taylorgreen.v0 = 0.1
+eb2.geom_type = "all_regular"
+amrex.the_arena_is_managed = 0
+"""
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_mlups(size: int, steps: int, threads: int | None = None):
+    """Run the unmodified reference (oracle/_ref, OpenMP build) on the TG deck at size^3 and return
+    (MLUPS, seconds per step, threads).  Per-step time = LBM::evolve() inclusive time of the
+    reference's own TinyProfiler table / steps."""
+    from oracle import oracle as O
+    exe = O.REF_OMP if os.path.exists(O.REF_OMP) else O.REF_SERIAL
+    if not os.path.exists(exe):
+        return None
+    threads = threads or os.cpu_count() or 1
+    work = tempfile.mkdtemp(prefix="mbl_ref_")
+    deck = os.path.join(work, "tg.inp")
+    with open(deck, "w") as fh:
+        fh.write(TG_DECK.format(nx=size, ny=size, nz=size, mgs=max(32, size // 4)))
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="false")
+    t0 = time.time()
+    res = subprocess.run([exe, deck, f"max_step={steps}"], cwd=work, env=env, capture_output=True, text=True)
+    wall = time.time() - t0
+    if res.returncode != 0:
+        return None
+    evolve = None
+    for ln in res.stdout.splitlines():
+        m = re.match(r"\s*LBM::evolve\(\)\s+\d+\s+([\d.eE+-]+)\s+([\d.eE+-]+)\s+([\d.eE+-]+)", ln)
+        if m and evolve is None and "Incl" not in ln:
+            evolve = float(m.group(3))
+    # the inclusive table comes second; take the largest figure reported for LBM::evolve()
+    vals = [float(x) for ln in res.stdout.splitlines() if ln.strip().startswith("LBM::evolve()")
+            for x in re.findall(r"[\d.]+(?:[eE][+-]?\d+)?", ln.split("LBM::evolve()")[1])[1:4]]
+    if vals:
+        evolve = max(vals)
+    sec = (evolve if evolve else wall) / steps
+    import shutil
+    shutil.rmtree(work, ignore_errors=True)
+    return size ** 3 / sec / 1e6, sec, threads, os.path.basename(exe)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    size = args.ref_size
+    vals = []
+    for _ in range(args.warmup and 1 or 0):
+        reference_mlups(size, 1)
+    for _ in range(max(1, min(args.steps, 3))):
+        r = reference_mlups(size, args.ref_steps)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref executable missing or failed"}))
+            return
+        vals.append(r)
+    mlups = statistics.median(v[0] for v in vals)
+    sec = statistics.median(v[1] for v in vals)
+    sample = f"TG deck {size}^3, {args.ref_steps} steps per run, LBM::evolve() inclusive time ({vals[0][3]})"
+    line = {
+        "impl": "reference", "metric": "MLUPS (D3Q27 f+g, fp64)", "value": mlups, "unit": "MLUPS",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"periodic Taylor-Green box, single level, CPU sample {size}^3 of the "
+                               f"{args.size}^3-per-GPU workload"},
+        "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": vals[0][2], "kind": "reference", "sample": sample},
+        "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=512, help="cells per side per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-size", type=int, default=128)
+    ap.add_argument("--ref-steps", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from marbles_b200.inputs import parse_deck
+    from marbles_b200.lbm import LBM
+    from marbles_b200.parallel import HaloComm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.size
+    deck = parse_deck(text=TG_DECK.format(nx=n, ny=n, nz=n * world, mgs=n))
+    comm = HaloComm(rank, world, True, dev) if world > 1 else None
+    stream = torch.cuda.current_stream().cuda_stream
+    lbm = LBM(deck, device=local, rank=rank, world=world, comm=comm, cuda_stream=stream)
+    lbm.init_data()
+    cells_total = lbm.ncells * world
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        lbm.step(1)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    import ctypes as C
+    lbm.lib.mbl_set_timing(lbm.ctx, 1)
+    launches0 = lbm.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    if world == 1:
+        lbm.step(args.steps)
+    else:
+        for _ in range(args.steps):
+            lbm.step(1)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    kms = (C.c_double * 3)()
+    nrec = C.c_int()
+    lbm.lib.mbl_get_timing(lbm.ctx, kms, C.byref(nrec))
+    lbm.lib.mbl_set_timing(lbm.ctx, 0)
+    launches = lbm.launches - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = cells_total / (ms_per_step * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (collide pass) -----------------------------
+    peak, peak_src = measured_peak_gbs()
+    collide_ms = kms[2] / max(nrec.value, 1)
+    achieved = BYTES_PER_CELL * lbm.ncells / (collide_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh).get("k_collide_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {
+        "bound": "hbm", "kernel": "k_collide<pull>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "bytes_per_cell": BYTES_PER_CELL, "cells_per_launch": lbm.ncells,
+        "kernel_ms": {"ghost_fill": kms[0] / max(nrec.value, 1), "qcorr": kms[1] / max(nrec.value, 1),
+                      "collide": collide_ms},
+        "step_achieved": BYTES_PER_CELL * lbm.ncells / (ms_per_step * 1e-3) / 1e9,
+        "step_frac": BYTES_PER_CELL * lbm.ncells / (ms_per_step * 1e-3) / 1e9 / peak,
+    }
+
+    # ---- end to end through the host-buffer call -------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        nx, ny, nz = lbm.n_local
+        shape = (27, nz, ny, nx)
+        try:
+            fh_t = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+            gh_t = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+            pinned = True
+        except Exception:
+            fh_t, gh_t, pinned = torch.empty(shape, dtype=torch.float64), torch.empty(shape, dtype=torch.float64), False
+        fh, gh = fh_t.numpy(), gh_t.numpy()
+        from marbles_b200.lbm import _dptr
+        from marbles_b200._lib import check
+        check(lbm.lib.mbl_download(lbm.ctx, 0, 0, _dptr(fh), 0))
+        check(lbm.lib.mbl_download(lbm.ctx, 0, 1, _dptr(gh), 0))
+        if world > 1:
+            # host-buffer stepping of a slab needs the halo exchange between upload and step:
+            # upload, exchange + step, download
+            def host_step():
+                lbm.set_state(fh, gh, ng=0)
+                lbm.step(1)
+                check(lbm.lib.mbl_download(lbm.ctx, 0, 0, _dptr(fh), 0))
+                check(lbm.lib.mbl_download(lbm.ctx, 0, 1, _dptr(gh), 0))
+        else:
+            def host_step():
+                lbm.step_host(fh, gh, 1, ng=0)
+        host_step()  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            host_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        nbytes = 2 * fh.nbytes
+        e2e = {"value": cells_total * args.e2e_steps / dt / 1e6, "unit": "MLUPS",
+               "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world,
+               "steps": args.e2e_steps, "pinned": pinned, "ms_per_step": dt / args.e2e_steps * 1e3}
+        del fh, gh, fh_t, gh_t
+
+    lbm.close()
+
+    # ---- CPU baseline: the unmodified reference on the host cores ---------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = reference_mlups(args.ref_size, args.ref_steps)
+        if r is not None:
+            cpu = {"value": r[0], "unit": "MLUPS", "cores": r[2], "kind": "reference",
+                   "sample": f"TG deck {args.ref_size}^3, {args.ref_steps} steps, LBM::evolve() inclusive time, {r[3]}"}
+
+    if rank == 0:
+        line = {
+            "metric": "MLUPS (D3Q27 f+g, fp64)", "value": value, "unit": "MLUPS", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"periodic Taylor-Green box {n}^3 per GPU, single level, D3Q27 f+g fp64 "
+                                   f"(BASELINE config 3; domain {n}x{n}x{n * world})",
+                       "decomposition": f"{world} z-slab(s)", "l2": "state (58 GB per GPU at 512^3) is far larger than L2",
+                       "variant": "two-pass (q-correction, collide)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,195 @@
+/*
+ * marbles_b200.h -- C ABI of the B200-native D3Q27 f+g lattice update.
+ *
+ * This is the drop-in boundary for ONE path of NREL/marbles: the per-timestep
+ * lattice update behind lbm::LBM (stream / collide / f_to_macrodata /
+ * FillPatchOps::fillpatch / physbc, reference Source/LBM.H:78-112,
+ * Source/FillPatchOps.H:15-42).  The reference has no FFI for this path (it calls
+ * amrex::ParallelFor lambdas in place); each entry point below names the
+ * reference member function it replaces, and INTEGRATION.md shows the patch to
+ * Source/LBM.cpp that calls them.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every function returns 0 on success, nonzero
+ *    on error (then mbl_last_error() describes it; the reference-side shim turns
+ *    that into amrex::Abort, which is how the reference reports errors);
+ *  - work is enqueued on the context's CUDA stream (mbl_set_stream; pass
+ *    amrex::Gpu::gpuStream()) and is asynchronous unless the call moves data to
+ *    or from HOST memory; mbl_sync() waits;
+ *  - "FAB layout" means the reference's array layout for one box grown by `ng`
+ *    ghost cells: x fastest, then y, z, component slowest
+ *    (Submodules/AMReX/Src/Base/AMReX_Array4.H:60-94);
+ *  - there is NO CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef MARBLES_B200_H
+#define MARBLES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBL_NQ 27        /* constants::N_MICRO_STATES, Source/Constants.H:36 */
+#define MBL_NMACRO 19    /* constants::N_MACRO_STATES, Source/Constants.H:8  */
+#define MBL_NDERIVED 7   /* constants::N_DERIVED,      Source/Constants.H:39 */
+
+/* lbm.bc_lo / lbm.bc_hi codes, Source/BC.H:13-20 */
+enum {
+    MBL_BC_PERIODIC = 0,
+    MBL_BC_NOSLIP = 1,
+    MBL_BC_VELOCITY = 2,
+    MBL_BC_PRESSURE = 3,
+    MBL_BC_OUTFLOW = 5,
+    MBL_BC_SLIP_X = 6,
+    MBL_BC_SLIP_Y = 7,
+    MBL_BC_SLIP_Z = 8
+};
+/* lbm.velocity_bc_type, Source/LBM.cpp:1382-1451 / Source/VelocityBC.H */
+enum { MBL_VBC_NOOP = 0, MBL_VBC_CONSTANT = 1, MBL_VBC_CHANNEL = 2, MBL_VBC_PARABOLIC = 3 };
+/* which lattice */
+enum { MBL_F = 0, MBL_G = 1 };
+
+/* The parsed scalars of LBM::read_parameters (Source/LBM.cpp:196-300) and of the
+ * inlet functor constructors (Source/VelocityBC.cpp:6-54) that the path needs. */
+typedef struct mbl_params {
+    double nu;          /* lbm.nu                                   */
+    double alpha;       /* lbm.alpha (defaults to nu)               */
+    double R;           /* m_R_u / m_m_bar                          */
+    double gamma;       /* lbm.adiabatic_exponent                   */
+    double mesh_speed;  /* lbm.dx_outer / lbm.dt_outer              */
+    int bc_type[6];     /* m_bc_type: idir + 3*lohi                 */
+    int periodic[3];    /* geometry.is_periodic                     */
+    int vbc_kind;       /* MBL_VBC_*                                */
+    int vbc_dir;        /* velocity_bc_constant.dir                 */
+    int vbc_normal_dir;     /* velocity_bc_parabolic.normal_dir     */
+    int vbc_tangential_dir; /* velocity_bc_parabolic.tangential_dir */
+    double vbc_u;       /* u0 / u_ref / um = Mach_ref * c_s         */
+    double vbc_rho, vbc_T, vbc_gamma, vbc_R; /* functor state       */
+} mbl_params;
+
+/* One level of the hierarchy as this rank sees it: the level domain and the ONE
+ * box (z-slab of the domain) this rank owns.  Replaces the BoxArray /
+ * DistributionMapping / Geometry triple handed to MakeNewLevelFromScratch
+ * (Source/LBM.cpp:1148-1199). */
+typedef struct mbl_level_geom {
+    int dom_lo[3], dom_hi[3]; /* geom[lev].Domain()                 */
+    int lo[3], hi[3];         /* valid box owned by this rank       */
+    double dt;                /* m_dts[lev]                          */
+    double inv_dx[3];         /* geom[lev].InvCellSizeArray()        */
+    double prob_lo[3], prob_hi[3], dx[3];
+} mbl_level_geom;
+
+/* Device layout of one level's state (structure of arrays, ghost cells
+ * included; DESIGN.md "Data layout").  element (q,k,j,i) of a lattice buffer is
+ * at  q*comp_stride + (k+gz)*plane_stride + (j+gy)*pitch + (i+ox). */
+typedef struct mbl_layout {
+    int64_t pitch, plane_stride, comp_stride; /* in doubles          */
+    int32_t nx, ny, nz;                        /* valid cells         */
+    int32_t ox, gy, gz;                        /* offsets of cell 0   */
+    int64_t lattice_doubles;                   /* 27 * comp_stride    */
+    int64_t state_bytes;                       /* all device state    */
+} mbl_layout;
+
+typedef struct mbl_ctx mbl_ctx;
+
+const char* mbl_last_error(void);
+int mbl_version(void);
+
+/* lifetime ------------------------------------------------------------- */
+int mbl_create(const mbl_params* params, int device, mbl_ctx** out);
+int mbl_destroy(mbl_ctx* ctx);
+int mbl_set_stream(mbl_ctx* ctx, void* cuda_stream);
+int mbl_sync(mbl_ctx* ctx);
+
+/* level definition: call again after every regrid (RemakeLevel /
+ * MakeNewLevelFromCoarse / ClearLevel, Source/LBM.cpp:1088-1379).
+ * `device_state` may be NULL (the library allocates) or caller-owned device
+ * memory of mbl_level_layout().state_bytes bytes (no ownership transfer). */
+int mbl_level_layout(const mbl_level_geom* geom, mbl_layout* out);
+int mbl_level_define(mbl_ctx* ctx, int lev, const mbl_level_geom* geom, void* device_state);
+int mbl_level_clear(mbl_ctx* ctx, int lev);
+/* device pointer of the CURRENT f (which=0) / g (which=1) buffer */
+int mbl_level_lattice_ptr(mbl_ctx* ctx, int lev, int which, void** out);
+
+/* EB flag field: replaces LBM::initialize_is_fluid's product m_is_fluid
+ * (Source/LBM.cpp:1213-1262).  `is_fluid` is HOST memory, FAB layout, int32,
+ * component 0 over the valid box grown by ng (ng >= 2; values beyond the
+ * domain come from the geometry).  Builds the 1-byte flag field
+ * (bit0 fluid, bit1 eb_boundary, bits2-7 gradient-neighbour usable) and the
+ * 27-bit pull mask on the device. */
+int mbl_set_is_fluid(mbl_ctx* ctx, int lev, const int32_t* is_fluid, int ng);
+int mbl_set_all_fluid(mbl_ctx* ctx, int lev);
+
+/* state transfer, HOST <-> device, FAB layout (27 comps, ghost ng; only valid
+ * cells are read on upload unless with_ghosts != 0).  These are the calls that
+ * carry m_f[lev] / m_g[lev] across the boundary (checkpoint restart, plotfiles,
+ * regrid: Source/LBM.cpp:1629-1675, 1772-1782, 1897-1915). */
+int mbl_upload(mbl_ctx* ctx, int lev, int which, const double* fab, int ng);
+int mbl_download(mbl_ctx* ctx, int lev, int which, double* fab, int ng);
+/* macrodata of the last collide/step with want_macrodata (19 comps, ghost ng<=1,
+ * valid cells written) and derived data (7 comps, ng 0) */
+int mbl_download_macrodata(mbl_ctx* ctx, int lev, double* fab, int ng);
+int mbl_download_derived(mbl_ctx* ctx, int lev, double* fab);
+
+/* initial state on the device: ic::Initializer<ICOp>::initialize + fill_f_inside_eb
+ * (Source/IC.H:474-519, Source/LBM.cpp:1287-1295).  `ic` = {kind, 16 doubles}, see
+ * marbles_b200/lbm.py. */
+int mbl_initialize(mbl_ctx* ctx, int lev, int ic_kind, const double* ic_params, int n_ic_params);
+
+/* reference-granular operators (AMR-compatible sequencing stays in the caller) */
+/* FillPatchOps::fillpatch(lev,time,mf) for lev 0 / same-level part
+ * (Source/FillPatchOps.H:75-132): K6 pre-pass, periodic fill, BCFill pass.
+ * Ghost planes owned by other ranks are filled by mbl_halo_* first. */
+int mbl_fillpatch(mbl_ctx* ctx, int lev, double time);
+/* FillPatchOps::physbc (Source/FillPatchOps.H:142-159) */
+int mbl_physbc(mbl_ctx* ctx, int lev, double time);
+/* LBM::stream(lev, m_f) and LBM::stream(lev, m_g) (Source/LBM.cpp:558-604), pull form */
+int mbl_stream(mbl_ctx* ctx, int lev);
+/* LBM::collide(lev) = f_to_macrodata + compute_q_corrections +
+ * macrodata_to_equilibrium + relax_f_to_equilibrium (Source/LBM.cpp:607-618) on the
+ * already streamed state */
+int mbl_collide(mbl_ctx* ctx, int lev, int want_macrodata);
+/* LBM::f_to_macrodata(lev) (Source/LBM.cpp:810-906) on the current state */
+int mbl_f_to_macrodata(mbl_ctx* ctx, int lev);
+/* LBM::compute_derived(lev) (Source/LBM.cpp:909-955), needs macrodata */
+int mbl_compute_derived(mbl_ctx* ctx, int lev);
+/* LBM::compute_eb_forces() for one level (Source/LBM.cpp:994-1044): local sum */
+int mbl_eb_forces(mbl_ctx* ctx, int lev, double out[3]);
+
+/* fused fast path: one coarse step of a single-level run =
+ * fillpatch(f), fillpatch(g), stream(f), stream(g), collide
+ * (Source/LBM.cpp:416-422, 523-544).  nsteps > 1 only on a single rank. */
+int mbl_step(mbl_ctx* ctx, int lev, int nsteps, double time, int want_macrodata);
+/* the same step split so a caller can exchange z-halo planes between ranks:
+ * mbl_step_begin = nothing yet (reserved); halo exchange; mbl_step_finish */
+int mbl_step_local(mbl_ctx* ctx, int lev, double time, int want_macrodata);
+
+/* z-halo planes (multi-rank slabs): side 0 = low-z, 1 = high-z.  pack copies
+ * the gz outermost VALID planes of f and g (all 27 comps) into `device_buf`
+ * (mbl_halo_doubles() doubles); unpack writes a neighbour's packed planes into
+ * the ghost planes on that side.  Transport (NCCL over NVLink) is the caller's. */
+int64_t mbl_halo_doubles(mbl_ctx* ctx, int lev);
+int mbl_halo_pack(mbl_ctx* ctx, int lev, int side, double* device_buf);
+int mbl_halo_unpack(mbl_ctx* ctx, int lev, int side, const double* device_buf);
+
+/* host-buffer convenience used for the end-to-end measurement: upload f,g
+ * (FAB layout, ghost ng), run nsteps, download f,g into the same buffers */
+int mbl_step_host(mbl_ctx* ctx, int lev, int nsteps, double time, double* f_fab, double* g_fab, int ng);
+
+/* number of kernels launched by this context so far (bench.py gpu_launches) */
+int64_t mbl_launch_count(mbl_ctx* ctx);
+/* per-kernel device timing of mbl_step / mbl_step_local with CUDA events on the context's
+ * stream: ms[0] ghost fill, ms[1] q-correction pass, ms[2] collide pass, summed over the
+ * *nsteps steps recorded since the last call (bench.py roofline) */
+int mbl_set_timing(mbl_ctx* ctx, int on);
+int mbl_get_timing(mbl_ctx* ctx, double ms[3], int* nsteps);
+/* select the collide implementation: 0 = two-pass (moments, then collide),
+ * 1 = fused z-marching kernel (when available) */
+int mbl_set_variant(mbl_ctx* ctx, int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARBLES_B200_H */

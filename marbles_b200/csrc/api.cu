@@ -1,0 +1,606 @@
+// api.cu -- C ABI (include/marbles_b200.h) over the CUDA kernels: context, levels,
+// device state ownership, host<->device transfer and the per-step sequencing that
+// replaces LBM::advance / FillPatchOps::fillpatch (Source/LBM.cpp:523-544,
+// Source/FillPatchOps.H:75-132).  No CPU fallback: every entry point needs a device.
+#include "../../include/marbles_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace mbl;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CU(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) return fail("%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+constexpr int MAX_LEVELS = 16;
+constexpr int NMACRO_ALL = MBL_NMACRO + MBL_NDERIVED;  // macro comps followed by derived comps
+
+struct Level {
+    bool defined = false;
+    Layout L;
+    Phys P;
+    BcInfo B;
+    mbl_level_geom geom;
+    char* base = nullptr;  // device state block
+    bool owned = false;
+    LevelPtrs p;
+    int cur = 0;  // index of the current lattice buffers
+    bool local_z = true;
+    double* stage = nullptr;  // one-component staging for FAB transfers
+    size_t stage_bytes = 0;
+    int32_t* flag_stage = nullptr;
+    double* d_red = nullptr;  // 3 doubles for reductions
+    double* macro = nullptr;  // lazily allocated (26 comps)
+};
+
+}  // namespace
+
+struct mbl_ctx {
+    mbl_params prm;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    Level lev[MAX_LEVELS];
+    int64_t launches = 0;
+    int variant = 0;
+    bool timing = false;
+    std::vector<cudaEvent_t> events;  // 4 per timed step: before ghost fill, q-corr, collide, after
+};
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct StateMap {
+    size_t f0, g0, f1, g1, qc, nbr, flag, total;
+};
+
+StateMap state_map(const Layout& L)
+{
+    StateMap m;
+    const size_t lat = (size_t)NQ * L.sq * sizeof(double);
+    size_t o = 0;
+    m.f0 = o, o += align_up(lat, 256);
+    m.g0 = o, o += align_up(lat, 256);
+    m.f1 = o, o += align_up(lat, 256);
+    m.g1 = o, o += align_up(lat, 256);
+    m.qc = o, o += align_up((size_t)3 * L.sq * sizeof(double), 256);
+    m.nbr = o, o += align_up((size_t)L.sq * sizeof(uint32_t), 256);
+    m.flag = o, o += align_up((size_t)L.sq, 256);
+    m.total = o;
+    return m;
+}
+
+Layout layout_of(const mbl_level_geom* g) { return make_layout(g->lo, g->hi, g->dom_lo, g->dom_hi); }
+
+int check_level(mbl_ctx* ctx, int lev)
+{
+    if (!ctx) return fail("null context");
+    if (lev < 0 || lev >= MAX_LEVELS || !ctx->lev[lev].defined) return fail("level %d is not defined", lev);
+    return 0;
+}
+
+int ensure_stage(Level& lv, size_t bytes)
+{
+    if (lv.stage_bytes >= bytes) return 0;
+    if (lv.stage) cudaFree(lv.stage);
+    lv.stage = nullptr;
+    lv.stage_bytes = 0;
+    CU(cudaMalloc(&lv.stage, bytes));
+    lv.stage_bytes = bytes;
+    return 0;
+}
+
+int ensure_macro(Level& lv, cudaStream_t st, int64_t& launches)
+{
+    if (lv.macro) return 0;
+    const size_t n = (size_t)NMACRO_ALL * lv.L.sq;
+    CU(cudaMalloc(&lv.macro, n * sizeof(double)));
+    launches += launch_fill(lv.macro, (long long)n, 0.0, st);  // m_macrodata.setVal(0), LBM.cpp:1187-1190
+    return 0;
+}
+
+double* curf(Level& lv) { return lv.p.f[lv.cur]; }
+double* curg(Level& lv) { return lv.p.g[lv.cur]; }
+
+// one fused step on the local box; z ghost planes owned by other ranks must be current
+int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
+{
+    cudaStream_t st = ctx->stream;
+    if (want_macro && ensure_macro(lv, st, ctx->launches)) return 1;
+    const int a = lv.cur, b = 1 - lv.cur;
+    auto mark = [&]() {
+        if (!ctx->timing) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ctx->events.push_back(e);
+    };
+    mark();
+    ctx->launches += launch_ghost_fill(lv.L, lv.B, lv.p.f[a], lv.p.g[a], lv.local_z, true, true, st);
+    mark();
+    ctx->launches += launch_qcorr(lv.L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st);
+    mark();
+    ctx->launches += launch_collide(lv.L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
+                                    lv.p.qc, want_macro ? lv.macro : nullptr, true, st);
+    mark();
+    lv.cur = b;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mbl_last_error(void) { return g_err.c_str(); }
+int mbl_version(void) { return 100; }
+
+int mbl_create(const mbl_params* params, int device, mbl_ctx** out)
+{
+    if (!params || !out) return fail("mbl_create: null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail("mbl_create: no CUDA device (%s); marbles_b200 has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail("mbl_create: device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    for (int d = 0; d < 3; ++d) {
+        // LBM::read_parameters consistency checks (LBM.cpp:227-252)
+        if (params->periodic[d] && (params->bc_type[d] != 0 || params->bc_type[d + 3] != 0))
+            return fail("BC is periodic in direction %d but bc_lo/bc_hi is not 0", d);
+        if (!params->periodic[d] && (params->bc_type[d] == 0 || params->bc_type[d + 3] == 0))
+            return fail("BC is interior in direction %d but not periodic", d);
+    }
+    mbl_ctx* c = new mbl_ctx();
+    c->prm = *params;
+    c->device = device;
+    init_tables();
+    CU(cudaGetLastError());
+    *out = c;
+    return 0;
+}
+
+int mbl_destroy(mbl_ctx* ctx)
+{
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    for (int l = 0; l < MAX_LEVELS; ++l) mbl_level_clear(ctx, l);
+    delete ctx;
+    return 0;
+}
+
+int mbl_set_stream(mbl_ctx* ctx, void* s)
+{
+    if (!ctx) return fail("null context");
+    ctx->stream = (cudaStream_t)s;
+    return 0;
+}
+
+int mbl_sync(mbl_ctx* ctx)
+{
+    if (!ctx) return fail("null context");
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mbl_level_layout(const mbl_level_geom* geom, mbl_layout* out)
+{
+    if (!geom || !out) return fail("null argument");
+    const Layout L = layout_of(geom);
+    out->pitch = L.px;
+    out->plane_stride = L.sz;
+    out->comp_stride = L.sq;
+    out->nx = L.nx, out->ny = L.ny, out->nz = L.nz;
+    out->ox = OX, out->gy = GY, out->gz = GZ;
+    out->lattice_doubles = (int64_t)NQ * L.sq;
+    out->state_bytes = (int64_t)state_map(L).total;
+    return 0;
+}
+
+int mbl_level_clear(mbl_ctx* ctx, int lev)
+{
+    if (!ctx || lev < 0 || lev >= MAX_LEVELS) return fail("bad level");
+    Level& lv = ctx->lev[lev];
+    if (!lv.defined) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (lv.owned && lv.base) cudaFree(lv.base);
+    if (lv.stage) cudaFree(lv.stage);
+    if (lv.flag_stage) cudaFree(lv.flag_stage);
+    if (lv.d_red) cudaFree(lv.d_red);
+    if (lv.macro) cudaFree(lv.macro);
+    lv = Level();
+    return 0;
+}
+
+int mbl_level_define(mbl_ctx* ctx, int lev, const mbl_level_geom* g, void* device_state)
+{
+    if (!ctx || !g) return fail("null argument");
+    if (lev < 0 || lev >= MAX_LEVELS) return fail("level %d out of range", lev);
+    for (int d = 0; d < 3; ++d) {
+        if (g->hi[d] < g->lo[d]) return fail("empty box in direction %d", d);
+        if (g->lo[d] < g->dom_lo[d] || g->hi[d] > g->dom_hi[d]) return fail("box leaves the domain in direction %d", d);
+    }
+    if (g->lo[0] != g->dom_lo[0] || g->hi[0] != g->dom_hi[0] || g->lo[1] != g->dom_lo[1] || g->hi[1] != g->dom_hi[1])
+        return fail("a rank's box must span the level domain in x and y (z-slab decomposition)");
+    CU(cudaSetDevice(ctx->device));
+    mbl_level_clear(ctx, lev);
+    Level& lv = ctx->lev[lev];
+    lv.geom = *g;
+    lv.L = layout_of(g);
+    lv.local_z = (g->lo[2] == g->dom_lo[2] && g->hi[2] == g->dom_hi[2]);
+    if (!lv.local_z && lv.L.nz < GZ) return fail("a z-slab needs at least %d planes", GZ);
+    const mbl_params& pr = ctx->prm;
+    lv.P.nu = pr.nu;
+    lv.P.alpha = pr.alpha;
+    lv.P.R = pr.R;
+    lv.P.gamma = pr.gamma;
+    lv.P.cv = pr.R / (pr.gamma - 1.0);  // LBM.cpp:640
+    lv.P.dt = g->dt;
+    lv.P.mesh_speed = pr.mesh_speed;
+    for (int d = 0; d < 3; ++d) {
+        lv.P.idx[d] = g->inv_dx[d];
+        lv.B.periodic[d] = pr.periodic[d];
+        lv.B.prob_lo[d] = g->prob_lo[d];
+        lv.B.prob_hi[d] = g->prob_hi[d];
+        lv.B.dx[d] = g->dx[d];
+    }
+    for (int n = 0; n < 6; ++n) lv.B.bc[n] = pr.bc_type[n];
+    lv.B.vbc_kind = pr.vbc_kind;
+    lv.B.vbc_dir = pr.vbc_dir;
+    lv.B.vbc_normal_dir = pr.vbc_normal_dir;
+    lv.B.vbc_tangential_dir = pr.vbc_tangential_dir;
+    lv.B.vbc_u = pr.vbc_u;
+    lv.B.vbc_rho = pr.vbc_rho;
+    lv.B.vbc_T = pr.vbc_T;
+    lv.B.vbc_gamma = pr.vbc_gamma;
+    lv.B.vbc_R = pr.vbc_R;
+
+    const StateMap m = state_map(lv.L);
+    if (device_state) {
+        lv.base = (char*)device_state;
+        lv.owned = false;
+    } else {
+        CU(cudaMalloc(&lv.base, m.total));
+        lv.owned = true;
+    }
+    lv.p.f[0] = (double*)(lv.base + m.f0);
+    lv.p.g[0] = (double*)(lv.base + m.g0);
+    lv.p.f[1] = (double*)(lv.base + m.f1);
+    lv.p.g[1] = (double*)(lv.base + m.g1);
+    lv.p.qc = (double*)(lv.base + m.qc);
+    lv.p.nbr = (uint32_t*)(lv.base + m.nbr);
+    lv.p.flag = (uint8_t*)(lv.base + m.flag);
+    lv.cur = 0;
+    CU(cudaMalloc(&lv.d_red, 8 * sizeof(double)));
+    // zero everything once: pad cells are never written by the kernels
+    CU(cudaMemsetAsync(lv.base, 0, m.total, ctx->stream));
+    lv.defined = true;
+    ctx->launches += launch_flags_all_fluid(lv.L, lv.B, lv.p.nbr, lv.p.flag, ctx->stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbl_level_lattice_ptr(mbl_ctx* ctx, int lev, int which, void** out)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    *out = which == MBL_G ? (void*)curg(lv) : (void*)curf(lv);
+    return 0;
+}
+
+int mbl_set_all_fluid(mbl_ctx* ctx, int lev)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches += launch_flags_all_fluid(lv.L, lv.B, lv.p.nbr, lv.p.flag, ctx->stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbl_set_is_fluid(mbl_ctx* ctx, int lev, const int32_t* is_fluid, int ng)
+{
+    if (check_level(ctx, lev)) return 1;
+    if (!is_fluid) return fail("null is_fluid");
+    if (ng < 2) return fail("is_fluid needs at least 2 ghost cells (got %d)", ng);
+    Level& lv = ctx->lev[lev];
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)(lv.L.nx + 2 * ng) * (lv.L.ny + 2 * ng) * (lv.L.nz + 2 * ng);
+    if (lv.flag_stage) cudaFree(lv.flag_stage);
+    CU(cudaMalloc(&lv.flag_stage, n * sizeof(int32_t)));
+    CU(cudaMemcpyAsync(lv.flag_stage, is_fluid, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->launches += launch_flags(lv.L, lv.B, lv.flag_stage, ng, lv.p.nbr, lv.p.flag, ctx->stream);
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(lv.flag_stage);
+    lv.flag_stage = nullptr;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbl_upload(mbl_ctx* ctx, int lev, int which, const double* fab, int ng)
+{
+    if (check_level(ctx, lev)) return 1;
+    if (!fab || ng < 0) return fail("mbl_upload: bad argument");
+    Level& lv = ctx->lev[lev];
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)(lv.L.nx + 2 * ng) * (lv.L.ny + 2 * ng) * (lv.L.nz + 2 * ng);
+    if (ensure_stage(lv, n * sizeof(double))) return 1;
+    double* dst = which == MBL_G ? curg(lv) : curf(lv);
+    for (int q = 0; q < NQ; ++q) {
+        CU(cudaMemcpyAsync(lv.stage, fab + (size_t)q * n, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->launches += launch_fab_to_soa(lv.L, lv.stage, ng, dst + (size_t)q * lv.L.sq, 1, ctx->stream);
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int download_comps(mbl_ctx* ctx, Level& lv, const double* src, int ncomp, double* fab, int ng)
+{
+    // valid cells only: compact on the device, then one strided copy into the interior of the
+    // host FAB (its ghost cells are left untouched)
+    const size_t nv = (size_t)lv.L.nx * lv.L.ny * lv.L.nz;
+    const size_t sx = lv.L.nx + 2 * ng, sy = lv.L.ny + 2 * ng, n = sx * sy * (lv.L.nz + 2 * ng);
+    if (ensure_stage(lv, nv * sizeof(double))) return 1;
+    for (int q = 0; q < ncomp; ++q) {
+        ctx->launches += launch_soa_to_fab(lv.L, src + (size_t)q * lv.L.sq, 0, lv.stage, ctx->stream);
+        cudaMemcpy3DParms p;
+        memset(&p, 0, sizeof(p));
+        p.srcPtr = make_cudaPitchedPtr(lv.stage, lv.L.nx * sizeof(double), lv.L.nx, lv.L.ny);
+        p.dstPtr = make_cudaPitchedPtr(fab + (size_t)q * n, sx * sizeof(double), sx, sy);
+        p.dstPos = make_cudaPos((size_t)ng * sizeof(double), ng, ng);
+        p.extent = make_cudaExtent(lv.L.nx * sizeof(double), lv.L.ny, lv.L.nz);
+        p.kind = cudaMemcpyDeviceToHost;
+        CU(cudaMemcpy3DAsync(&p, ctx->stream));
+        // the staging buffer is reused by the next component
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbl_download(mbl_ctx* ctx, int lev, int which, double* fab, int ng)
+{
+    if (check_level(ctx, lev)) return 1;
+    if (!fab || ng < 0) return fail("mbl_download: bad argument");
+    Level& lv = ctx->lev[lev];
+    CU(cudaSetDevice(ctx->device));
+    return download_comps(ctx, lv, which == MBL_G ? curg(lv) : curf(lv), NQ, fab, ng);
+}
+
+int mbl_download_macrodata(mbl_ctx* ctx, int lev, double* fab, int ng)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    if (!lv.macro) return fail("no macrodata yet: call mbl_collide/mbl_step with want_macrodata or mbl_f_to_macrodata");
+    CU(cudaSetDevice(ctx->device));
+    return download_comps(ctx, lv, lv.macro, MBL_NMACRO, fab, ng);
+}
+
+int mbl_download_derived(mbl_ctx* ctx, int lev, double* fab)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    if (!lv.macro) return fail("no derived data yet");
+    CU(cudaSetDevice(ctx->device));
+    return download_comps(ctx, lv, lv.macro + (size_t)MBL_NMACRO * lv.L.sq, MBL_NDERIVED, fab, 0);
+}
+
+int mbl_initialize(mbl_ctx* ctx, int lev, int ic_kind, const double* v, int nv)
+{
+    if (check_level(ctx, lev)) return 1;
+    if (nv < 16 || !v) return fail("mbl_initialize: need 16 parameters");
+    if (ic_kind < 0 || ic_kind > 4) return fail("mbl_initialize: unknown initial condition %d", ic_kind);
+    Level& lv = ctx->lev[lev];
+    CU(cudaSetDevice(ctx->device));
+    IcInfo I;
+    I.kind = ic_kind;
+    I.density = v[0];
+    I.vel[0] = v[1], I.vel[1] = v[2], I.vel[2] = v[3];
+    I.v0 = v[4];
+    I.omega[0] = v[5], I.omega[1] = v[6], I.omega[2] = v[7];
+    I.wave_length = v[8];
+    I.T0 = v[9], I.gamma = v[10], I.R = v[11], I.c_s = v[12];
+    I.density_ratio = v[13], I.temperature_ratio = v[14], I.x_disc = v[15];
+    ctx->launches += launch_initialize(lv.L, lv.B, I, lv.p.flag, curf(lv), curg(lv), ctx->stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbl_fillpatch(mbl_ctx* ctx, int lev, double /*time*/)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches += launch_ghost_fill(lv.L, lv.B, curf(lv), curg(lv), lv.local_z, true, true, ctx->stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbl_physbc(mbl_ctx* ctx, int lev, double /*time*/)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches += launch_ghost_fill(lv.L, lv.B, curf(lv), curg(lv), lv.local_z, false, false, ctx->stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbl_stream(mbl_ctx* ctx, int lev)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    CU(cudaSetDevice(ctx->device));
+    const int a = lv.cur, b = 1 - lv.cur;
+    ctx->launches += launch_stream(lv.L, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, ctx->stream);
+    lv.cur = b;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbl_collide(mbl_ctx* ctx, int lev, int want_macro)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (want_macro && ensure_macro(lv, st, ctx->launches)) return 1;
+    double *f = curf(lv), *g = curg(lv);
+    ctx->launches += launch_qcorr(lv.L, lv.P, f, g, lv.p.nbr, lv.p.qc, false, st);
+    ctx->launches += launch_collide(lv.L, lv.P, f, g, f, g, lv.p.nbr, lv.p.flag, lv.p.qc,
+                                    want_macro ? lv.macro : nullptr, false, st);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbl_f_to_macrodata(mbl_ctx* ctx, int lev)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    CU(cudaSetDevice(ctx->device));
+    if (ensure_macro(lv, ctx->stream, ctx->launches)) return 1;
+    ctx->launches += launch_macrodata(lv.L, lv.P, curf(lv), curg(lv), lv.p.flag, lv.macro, ctx->stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbl_compute_derived(mbl_ctx* ctx, int lev)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    if (!lv.macro) return fail("mbl_compute_derived needs macrodata");
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches += launch_derived(lv.L, lv.P, lv.p.flag, lv.macro, lv.macro + (size_t)MBL_NMACRO * lv.L.sq, ctx->stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbl_eb_forces(mbl_ctx* ctx, int lev, double out[3])
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    CU(cudaSetDevice(ctx->device));
+    // the reference reads f in ghost cells that FillBoundary refreshed after the collision
+    // (LBM.cpp:805); refresh the periodic images here
+    ctx->launches += launch_ghost_fill(lv.L, lv.B, curf(lv), curg(lv), lv.local_z, false, true, ctx->stream);
+    ctx->launches += launch_eb_forces(lv.L, curf(lv), lv.p.flag, lv.d_red, ctx->stream);
+    CU(cudaMemcpyAsync(out, lv.d_red, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mbl_step_local(mbl_ctx* ctx, int lev, double time, int want_macro)
+{
+    if (check_level(ctx, lev)) return 1;
+    CU(cudaSetDevice(ctx->device));
+    return step_local(ctx, ctx->lev[lev], time, want_macro);
+}
+
+int mbl_step(mbl_ctx* ctx, int lev, int nsteps, double time, int want_macro)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    if (!lv.local_z && nsteps > 1) return fail("mbl_step: nsteps > 1 needs a box that spans the domain in z");
+    CU(cudaSetDevice(ctx->device));
+    for (int s = 0; s < nsteps; ++s)
+        if (step_local(ctx, lv, time + s * lv.P.dt, want_macro && s == nsteps - 1)) return 1;
+    return 0;
+}
+
+int64_t mbl_halo_doubles(mbl_ctx* ctx, int lev)
+{
+    if (check_level(ctx, lev)) return -1;
+    return 2LL * NQ * GZ * ctx->lev[lev].L.sz;
+}
+
+int mbl_halo_pack(mbl_ctx* ctx, int lev, int side, double* buf)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches += launch_halo_pack(lv.L, curf(lv), curg(lv), side, buf, ctx->stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbl_halo_unpack(mbl_ctx* ctx, int lev, int side, const double* buf)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches += launch_halo_unpack(lv.L, curf(lv), curg(lv), side, buf, ctx->stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbl_step_host(mbl_ctx* ctx, int lev, int nsteps, double time, double* f_fab, double* g_fab, int ng)
+{
+    if (mbl_upload(ctx, lev, MBL_F, f_fab, ng)) return 1;
+    if (mbl_upload(ctx, lev, MBL_G, g_fab, ng)) return 1;
+    if (mbl_step(ctx, lev, nsteps, time, 0)) return 1;
+    if (mbl_download(ctx, lev, MBL_F, f_fab, ng)) return 1;
+    if (mbl_download(ctx, lev, MBL_G, g_fab, ng)) return 1;
+    return 0;
+}
+
+int64_t mbl_launch_count(mbl_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int mbl_set_timing(mbl_ctx* ctx, int on)
+{
+    if (!ctx) return fail("null context");
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    ctx->events.clear();
+    ctx->timing = on != 0;
+    return 0;
+}
+
+int mbl_get_timing(mbl_ctx* ctx, double ms[3], int* nsteps)
+{
+    if (!ctx || !ms || !nsteps) return fail("null argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ms[0] = ms[1] = ms[2] = 0.0;
+    *nsteps = (int)(ctx->events.size() / 4);
+    for (int s = 0; s < *nsteps; ++s)
+        for (int k = 0; k < 3; ++k) {
+            float t = 0.f;
+            CU(cudaEventElapsedTime(&t, ctx->events[4 * s + k], ctx->events[4 * s + k + 1]));
+            ms[k] += t;
+        }
+    return mbl_set_timing(ctx, ctx->timing ? 1 : 0);
+}
+
+int mbl_set_variant(mbl_ctx* ctx, int variant)
+{
+    if (!ctx) return fail("null context");
+    if (variant != 0) return fail("variant %d is not available", variant);
+    ctx->variant = variant;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,948 @@
+// kernels.cu -- CUDA kernels (sm_100a) of the D3Q27 f+g lattice update.
+//
+//   k_qcorr      pass 1: pull f,g -> rho,u,T -> QCorr_x,y,z      (LBM.cpp:810-906, pulled LBM.cpp:558-604)
+//   k_collide    pass 2: pull f,g -> moments -> grad QCorr -> feq/geq -> BGK relax -> store
+//                (LBM.cpp:558-604 + 607-618 fused; pull=false: collide only, in place)
+//   k_stream     pull-scheme stream with halfway bounce-back (LBM.cpp:558-604)
+//   ghost fill   K6 pre-pass (FillPatchOps.H:92-108), periodic wrap (FillBoundary), BCFill regions
+//                (BC.H:345-471 in the region order of AMReX_PhysBCFunct.H:593-678)
+//   flags        is_fluid (LBM.cpp:1213-1262) -> flag byte field + 27-bit pull mask
+//
+// All kernels are bandwidth-bound fp64 stencil/byte work: no tensor cores.  Thread x
+// is the fastest index so every load/store of a component plane is coalesced; stores
+// and e_x = 0 loads are 128-byte aligned, e_x = +-1 loads are shifted by one element.
+#include "kernels.cuh"
+
+#include <cstdio>
+
+namespace mbl {
+
+
+void init_tables()
+{
+    DirTables t;
+    for (int q = 0; q < NQ; ++q) {
+        t.ex[q] = ex(q);
+        t.ey[q] = ey(q);
+        t.ez[q] = ez(q);
+        t.opp[q] = opp(q);
+        t.mx[q] = mirror_x(q);
+        t.my[q] = mirror_y(q);
+        t.mz[q] = mirror_z(q);
+        t.w[q] = weight(q);
+    }
+    cudaMemcpyToSymbol(c_dir, &t, sizeof(t));
+}
+
+// ---------------------------------------------------------------------------
+// pull of one lattice (all 27 directions) for cell c
+// ---------------------------------------------------------------------------
+template <bool PULL, bool FAST, typename F>
+__device__ __forceinline__ void gather27(const double* __restrict__ in, long long c, uint32_t m, const Layout& L, F&& sink)
+{
+    static_for<0, NQ>([&](auto qc) {
+        constexpr int Q = decltype(qc)::value;
+        double v;
+        if constexpr (!PULL) {
+            v = in[(long long)Q * L.sq + c];
+        } else if constexpr (FAST) {
+            v = in[(long long)Q * L.sq + c - ((long long)ex(Q) + (long long)ey(Q) * L.px + (long long)ez(Q) * L.sz)];
+        } else {
+            // fluid source: take its population; solid source: halfway bounce-back of the
+            // cell's own opposite population (LBM.cpp:590-595 in pull form)
+            const bool fl = (m >> Q) & 1u;
+            const long long a = (long long)Q * L.sq + c - ((long long)ex(Q) + (long long)ey(Q) * L.px + (long long)ez(Q) * L.sz);
+            const long long b = (long long)opp(Q) * L.sq + c;
+            v = in[fl ? a : b];
+        }
+        sink(qc, v);
+    });
+}
+
+// ---------------------------------------------------------------------------
+// pass 1: q-corrections of the post-stream state
+// ---------------------------------------------------------------------------
+template <bool PULL>
+__global__ void __launch_bounds__(128) k_qcorr(const double* __restrict__ fin, const double* __restrict__ gin,
+                                               const uint32_t* __restrict__ nbr, double* __restrict__ qc, Layout L,
+                                               Phys P, int k0)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int k = blockIdx.z + k0;
+    if (i >= L.nx) return;
+    const long long c = L.cell(i, j, k);
+    const uint32_t m = nbr[c];
+    if (!(m & 1u)) return;
+    MomL ml = {0.0, 0.0, 0.0, 0.0};
+    double e2 = 0.0;
+    const bool fast = __all_sync(__activemask(), m == ALL_FLUID);
+    if (fast) {
+        gather27<PULL, true>(fin, c, m, L, [&](auto qc_, double v) { acc_l<decltype(qc_)::value>(ml, v); });
+        gather27<PULL, true>(gin, c, m, L, [&](auto, double v) { e2 += v; });
+    } else {
+        gather27<PULL, false>(fin, c, m, L, [&](auto qc_, double v) { acc_l<decltype(qc_)::value>(ml, v); });
+        gather27<PULL, false>(gin, c, m, L, [&](auto, double v) { e2 += v; });
+    }
+    const Prim s = primitives(ml.rho, ml.jx, ml.jy, ml.jz, e2, P);
+    const long long n = L.sq;
+    qc[c] = s.qcx;
+    qc[n + c] = s.qcy;
+    qc[2 * n + c] = s.qcz;
+}
+
+// ---------------------------------------------------------------------------
+// pass 2: (pull +) collide
+// ---------------------------------------------------------------------------
+template <bool PULL, bool MACRO>
+__global__ void __launch_bounds__(128) k_collide(const double* __restrict__ fin, const double* __restrict__ gin,
+                                                 double* __restrict__ fout, double* __restrict__ gout,
+                                                 const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ flag,
+                                                 const double* __restrict__ qc, double* __restrict__ macro, Layout L,
+                                                 Phys P)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int k = blockIdx.z;
+    if (i >= L.nx) return;
+    const long long c = L.cell(i, j, k);
+    const long long n = L.sq;
+    const uint32_t m = nbr[c];
+    if (!(m & 1u)) {
+        // solid cell: the streamed value is the -1 sentinel (LBM.cpp:565, 582); collide skips it
+        if constexpr (PULL) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                fout[q * n + c] = -1.0;
+                gout[q * n + c] = -1.0;
+            }
+        }
+        return;
+    }
+    double f[NQ], g[NQ];
+    MomF mf = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    MomG mg = {0, 0, 0, 0};
+    const bool fast = __all_sync(__activemask(), m == ALL_FLUID);
+    if (fast) {
+        gather27<PULL, true>(fin, c, m, L, [&](auto qc_, double v) {
+            constexpr int Q = decltype(qc_)::value;
+            f[Q] = v;
+            acc_f<Q>(mf, v);
+        });
+        gather27<PULL, true>(gin, c, m, L, [&](auto qc_, double v) {
+            constexpr int Q = decltype(qc_)::value;
+            g[Q] = v;
+            acc_g<Q>(mg, v);
+        });
+    } else {
+        gather27<PULL, false>(fin, c, m, L, [&](auto qc_, double v) {
+            constexpr int Q = decltype(qc_)::value;
+            f[Q] = v;
+            acc_f<Q>(mf, v);
+        });
+        gather27<PULL, false>(gin, c, m, L, [&](auto qc_, double v) {
+            constexpr int Q = decltype(qc_)::value;
+            g[Q] = v;
+            acc_g<Q>(mg, v);
+        });
+    }
+    const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
+
+    // grad of the q-correction (LBM.cpp:959-991, Utilities.H:279-312)
+    const unsigned fb = flag[c];
+    double dqx, dqy, dqz;
+    {
+        const bool okp = fb & GRAD_PX, okm = fb & GRAD_MX;
+        const double dp = okp ? qc[c + 1] : 0.0, dm = okm ? qc[c - 1] : 0.0;
+        dqx = one_sided_gradient(okp, okm, dp, s.qcx, dm, P.idx[0]);
+    }
+    {
+        const bool okp = fb & GRAD_PY, okm = fb & GRAD_MY;
+        const double dp = okp ? qc[n + c + L.px] : 0.0, dm = okm ? qc[n + c - L.px] : 0.0;
+        dqy = one_sided_gradient(okp, okm, dp, s.qcy, dm, P.idx[1]);
+    }
+    {
+        const bool okp = fb & GRAD_PZ, okm = fb & GRAD_MZ;
+        const double dp = okp ? qc[2 * n + c + L.sz] : 0.0, dm = okm ? qc[2 * n + c - L.sz] : 0.0;
+        dqz = one_sided_gradient(okp, okm, dp, s.qcz, dm, P.idx[2]);
+    }
+
+    if constexpr (MACRO) {
+        // m_macrodata of the post-stream state (Constants.H:8-31, LBM.cpp:867-901)
+        macro[0 * n + c] = s.rho;
+        macro[1 * n + c] = s.u;
+        macro[2 * n + c] = s.v;
+        macro[3 * n + c] = s.w;
+        macro[4 * n + c] = sqrt(s.u * s.u + s.v * s.v + s.w * s.w);
+        macro[5 * n + c] = mg.e2;
+        macro[6 * n + c] = s.qcx;
+        macro[7 * n + c] = s.qcy;
+        macro[8 * n + c] = s.qcz;
+        macro[9 * n + c] = mf.pxx;
+        macro[10 * n + c] = mf.pyy;
+        macro[11 * n + c] = mf.pzz;
+        macro[12 * n + c] = mf.pxy;
+        macro[13 * n + c] = mf.pxz;
+        macro[14 * n + c] = mf.pyz;
+        macro[15 * n + c] = mg.qx;
+        macro[16 * n + c] = mg.qy;
+        macro[17 * n + c] = mg.qz;
+        macro[18 * n + c] = s.T;
+        // m_derived (Constants.H:39-47) lives behind the 19 macro comps: 19..22 vorticity, 23..25 dQCorr
+        macro[23 * n + c] = dqx;
+        macro[24 * n + c] = dqy;
+        macro[25 * n + c] = dqz;
+    }
+
+    const Coll cc = collision_coefficients(s, mf, mg, dqx, dqy, dqz, P);
+    // relax_f_to_equilibrium (LBM.cpp:799-801)
+    static_for<0, NQ>([&](auto qc_) {
+        constexpr int Q = decltype(qc_)::value;
+        fout[(long long)Q * n + c] = f[Q] + cc.omega * (feq_q<Q>(cc) - f[Q]);
+    });
+    static_for<0, NQ>([&](auto qc_) {
+        constexpr int Q = decltype(qc_)::value;
+        gout[(long long)Q * n + c] = g[Q] + cc.omega * (geq_q<Q>(cc) - g[Q]);
+    });
+}
+
+// ---------------------------------------------------------------------------
+// stream only (pull form of LBM.cpp:558-604): lat = blockIdx.y selects f / g via pointer arrays
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_stream(const double* __restrict__ fin, const double* __restrict__ gin,
+                                                double* __restrict__ fout, double* __restrict__ gout,
+                                                const uint32_t* __restrict__ nbr, Layout L)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int k = blockIdx.z;
+    if (i >= L.nx) return;
+    const long long c = L.cell(i, j, k);
+    const long long n = L.sq;
+    const uint32_t m = nbr[c];
+    if (!(m & 1u)) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            fout[q * n + c] = -1.0;
+            gout[q * n + c] = -1.0;
+        }
+        return;
+    }
+    gather27<true, false>(fin, c, m, L, [&](auto qc_, double v) { fout[(long long)decltype(qc_)::value * n + c] = v; });
+    gather27<true, false>(gin, c, m, L, [&](auto qc_, double v) { gout[(long long)decltype(qc_)::value * n + c] = v; });
+}
+
+// f_to_macrodata on the current (already streamed) state, valid cells (LBM.cpp:810-906)
+__global__ void __launch_bounds__(128) k_macrodata(const double* __restrict__ f, const double* __restrict__ g,
+                                                   const uint8_t* __restrict__ flag, double* __restrict__ macro,
+                                                   Layout L, Phys P)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int k = blockIdx.z;
+    if (i >= L.nx) return;
+    const long long c = L.cell(i, j, k);
+    const long long n = L.sq;
+    if (!(flag[c] & FLAG_FLUID)) return;
+    MomF mf = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    MomG mg = {0, 0, 0, 0};
+    gather27<false, true>(f, c, 0u, L, [&](auto qc_, double v) { acc_f<decltype(qc_)::value>(mf, v); });
+    gather27<false, true>(g, c, 0u, L, [&](auto qc_, double v) { acc_g<decltype(qc_)::value>(mg, v); });
+    const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
+    macro[0 * n + c] = s.rho;
+    macro[1 * n + c] = s.u;
+    macro[2 * n + c] = s.v;
+    macro[3 * n + c] = s.w;
+    macro[4 * n + c] = sqrt(s.u * s.u + s.v * s.v + s.w * s.w);
+    macro[5 * n + c] = mg.e2;
+    macro[6 * n + c] = s.qcx;
+    macro[7 * n + c] = s.qcy;
+    macro[8 * n + c] = s.qcz;
+    macro[9 * n + c] = mf.pxx;
+    macro[10 * n + c] = mf.pyy;
+    macro[11 * n + c] = mf.pzz;
+    macro[12 * n + c] = mf.pxy;
+    macro[13 * n + c] = mf.pxz;
+    macro[14 * n + c] = mf.pyz;
+    macro[15 * n + c] = mg.qx;
+    macro[16 * n + c] = mg.qy;
+    macro[17 * n + c] = mg.qz;
+    macro[18 * n + c] = s.T;
+}
+
+// compute_derived (LBM.cpp:909-955): vorticity from the velocity macrodata of valid cells.
+// Needs macrodata of the face neighbours inside the domain (valid cells of this box; the
+// z-neighbours across a rank boundary are treated as unusable -- plot-only quantity).
+__global__ void __launch_bounds__(128) k_derived(const uint8_t* __restrict__ flag, const double* __restrict__ macro,
+                                                 double* __restrict__ derived, Layout L, Phys P)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int k = blockIdx.z;
+    if (i >= L.nx) return;
+    const long long c = L.cell(i, j, k);
+    const long long n = L.sq;
+    const unsigned fb = flag[c];
+    if (!(fb & FLAG_FLUID)) return;
+    const long long step[3] = {1, L.px, L.sz};
+    const unsigned bp[3] = {GRAD_PX, GRAD_PY, GRAD_PZ}, bm[3] = {GRAD_MX, GRAD_MY, GRAD_MZ};
+    const bool zin_p = (k + 1 < L.nz), zin_m = (k - 1 >= 0);
+    auto grad = [&](int dir, int comp) {
+        bool okp = fb & bp[dir], okm = fb & bm[dir];
+        if (dir == 2) {
+            okp = okp && zin_p;
+            okm = okm && zin_m;
+        }
+        const double* a = macro + (long long)comp * n;
+        const double dp = okp ? a[c + step[dir]] : 0.0, dm = okm ? a[c - step[dir]] : 0.0;
+        return one_sided_gradient(okp, okm, dp, a[c], dm, P.idx[dir]);
+    };
+    const double vx = grad(0, 2), wx = grad(0, 3), uy = grad(1, 1), wy = grad(1, 3), uz = grad(2, 1), vz = grad(2, 2);
+    derived[0 * n + c] = wy - vz;
+    derived[1 * n + c] = uz - wx;
+    derived[2 * n + c] = vx - uy;
+    derived[3 * n + c] = sqrt((wy - vz) * (wy - vz) + (uz - wx) * (uz - wx) + (vx - uy) * (vx - uy));
+}
+
+// compute_eb_forces (LBM.cpp:994-1044), single level: momentum exchange over solid cells that
+// touch fluid (flag bit1); one double atomicAdd per block and direction
+__global__ void __launch_bounds__(128) k_eb_forces(const double* __restrict__ f, const uint8_t* __restrict__ flag,
+                                                   double* __restrict__ out3, Layout L)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int k = blockIdx.z;
+    double fs[3] = {0.0, 0.0, 0.0};
+    if (i < L.nx) {
+        const long long c = L.cell(i, j, k);
+        if (flag[c] & FLAG_EBB) {
+            for (int q = 0; q < NQ; ++q) {
+                const int o = c_dir.opp[q];
+                const long long r = c + c_dir.ex[o] + c_dir.ey[o] * L.px + c_dir.ez[o] * L.sz;
+                if (flag[r] & FLAG_FLUID) {
+                    const double v = 2.0 * f[(long long)q * L.sq + r];
+                    fs[0] += c_dir.ex[q] * v;
+                    fs[1] += c_dir.ey[q] * v;
+                    fs[2] += c_dir.ez[q] * v;
+                }
+            }
+        }
+    }
+    __shared__ double sh[3][4];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double v = fs[d];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) sh[d][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) v += sh[threadIdx.x][w];
+        if (v != 0.0) atomicAdd(out3 + threadIdx.x, v);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// ghost shell enumeration: the padded box minus the valid box as six slabs
+// ---------------------------------------------------------------------------
+struct Shell {
+    long long off[7];
+    int nxp, nyp;  // padded extents in x (ghost only, no alignment pad) and y
+};
+static Shell make_shell(const Layout& L)
+{
+    Shell s;
+    s.nxp = L.nx + 2 * GX;
+    s.nyp = L.ny + 2 * GY;
+    const long long zslab = (long long)GZ * s.nxp * s.nyp;
+    const long long yslab = (long long)GY * s.nxp * L.nz;
+    const long long xslab = (long long)GX * L.ny * L.nz;
+    s.off[0] = 0;
+    s.off[1] = zslab;
+    s.off[2] = 2 * zslab;
+    s.off[3] = s.off[2] + yslab;
+    s.off[4] = s.off[3] + yslab;
+    s.off[5] = s.off[4] + xslab;
+    s.off[6] = s.off[5] + xslab;
+    return s;
+}
+__device__ __forceinline__ void shell_decode(const Shell& s, const Layout& L, long long t, int& i, int& j, int& k)
+{
+    if (t < s.off[2]) {  // z slabs: all i, j
+        const bool hi = t >= s.off[1];
+        t -= hi ? s.off[1] : 0;
+        i = (int)(t % s.nxp) - GX;
+        t /= s.nxp;
+        j = (int)(t % s.nyp) - GY;
+        const int kk = (int)(t / s.nyp);
+        k = hi ? L.nz + kk : kk - GZ;
+    } else if (t < s.off[4]) {  // y slabs: valid k, all i
+        const bool hi = t >= s.off[3];
+        t -= hi ? s.off[3] : s.off[2];
+        i = (int)(t % s.nxp) - GX;
+        t /= s.nxp;
+        k = (int)(t % L.nz);
+        const int jj = (int)(t / L.nz);
+        j = hi ? L.ny + jj : jj - GY;
+    } else {  // x slabs: valid j, k
+        const bool hi = t >= s.off[5];
+        t -= hi ? s.off[5] : s.off[4];
+        j = (int)(t % L.ny);
+        t /= L.ny;
+        k = (int)(t % L.nz);
+        const int ii = (int)(t / L.nz);
+        i = hi ? L.nx + ii : ii - GX;
+    }
+}
+
+__device__ __forceinline__ bool in_dom(const Layout& L, int d, int local) { return local + L.lo[d] >= L.dlo[d] && local + L.lo[d] <= L.dhi[d]; }
+__device__ __forceinline__ bool in_padded(const Layout& L, int i, int j, int k)
+{
+    return i >= -GX && i <= L.nx - 1 + GX && j >= -GY && j <= L.ny - 1 + GY && k >= -GZ && k <= L.nz - 1 + GZ;
+}
+
+// periodic wrap in z on a box that spans the domain in z (FillBoundary, local copies)
+__global__ void __launch_bounds__(128) k_zwrap(double* __restrict__ f, double* __restrict__ g, Layout L)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int kk = blockIdx.z;  // 0 .. 2*GZ-1
+    if (i >= L.nx) return;
+    const int k = kk < GZ ? kk - GZ : L.nz + (kk - GZ);
+    int ks = k % L.nz;
+    if (ks < 0) ks += L.nz;
+    const long long dst = L.cell(i, j, k), src = L.cell(i, j, ks);
+    for (int q = 0; q < NQ; ++q) {
+        f[q * L.sq + dst] = f[q * L.sq + src];
+        g[q * L.sq + dst] = g[q * L.sq + src];
+    }
+}
+
+// K6 pre-pass (FillPatchOps.H:92-108) restricted to the ghosts the periodic fill will not overwrite
+__global__ void __launch_bounds__(128) k_prepass(double* __restrict__ f, double* __restrict__ g, Layout L, Shell S,
+                                                 BcInfo B)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S.off[6]) return;
+    int i, j, k;
+    shell_decode(S, L, t, i, j, k);
+    const int iv[3] = {i, j, k};
+    bool outside_np = false;
+    for (int d = 0; d < 3; ++d) outside_np |= (!B.periodic[d] && !in_dom(L, d, iv[d]));
+    if (!outside_np) return;
+    const long long c = L.cell(i, j, k);
+    for (int q = 0; q < NQ; ++q) {
+        const int in = i + c_dir.ex[q], jn = j + c_dir.ey[q], kn = k + c_dir.ez[q];
+        if (in_dom(L, 0, in) && in_dom(L, 1, jn) && in_dom(L, 2, kn) && in_padded(L, in, jn, kn)) {
+            const long long s = L.cell(in, jn, kn) + (long long)c_dir.opp[q] * L.sq;
+            f[q * L.sq + c] = f[s];
+            g[q * L.sq + c] = g[s];
+        }
+    }
+}
+
+// periodic wrap in x and y for every ghost cell that FillBoundary would fill
+__global__ void __launch_bounds__(128) k_xywrap(double* __restrict__ f, double* __restrict__ g, Layout L, Shell S,
+                                                BcInfo B)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S.off[6]) return;
+    int i, j, k;
+    shell_decode(S, L, t, i, j, k);
+    const bool xin = i >= 0 && i < L.nx, yin = j >= 0 && j < L.ny;
+    if (xin && yin) return;  // z ghost of valid (i,j): filled by k_zwrap / halo exchange
+    if (!(xin || B.periodic[0]) || !(yin || B.periodic[1]) || !(in_dom(L, 2, k) || B.periodic[2])) return;
+    const int is = xin ? i : (i < 0 ? i + L.nx : i - L.nx);
+    const int js = yin ? j : (j < 0 ? j + L.ny : j - L.ny);
+    const long long dst = L.cell(i, j, k), src = L.cell(is, js, k);
+    for (int q = 0; q < NQ; ++q) {
+        f[q * L.sq + dst] = f[q * L.sq + src];
+        g[q * L.sq + dst] = g[q * L.sq + src];
+    }
+}
+
+// inlet functors (VelocityBC.H:44-190) at the literal (un-wrapped) global ghost index
+__device__ __forceinline__ void vel_bc_op(const BcInfo& B, const Layout& L, int gi, int gj, int gk, double& rho,
+                                          double vel[3], double& R, double& T, double& gamma)
+{
+    const int iv[3] = {gi, gj, gk};
+    if (B.vbc_kind == 1) {
+        rho = B.vbc_rho;
+        vel[B.vbc_dir] = B.vbc_u;
+    } else if (B.vbc_kind == 2) {
+        rho = B.vbc_rho;
+        const double c1 = (double)(iv[1] * (L.dhi[1] - iv[1]));
+        const double c2 = (double)(iv[2] * (L.dhi[2] - iv[2]));
+        const double d = (double)(L.dhi[1] + 1);
+        vel[0] = 16.0 * B.vbc_u * c1 * c2 / (d * d * d * d);
+    } else if (B.vbc_kind == 3) {
+        rho = B.vbc_rho;
+        const int nd = B.vbc_normal_dir;
+        const double height = B.prob_hi[nd] - B.prob_lo[nd];
+        const double x = B.prob_lo[nd] + (iv[nd] + 0.5) * B.dx[nd];
+        vel[B.vbc_tangential_dir] = 4.0 * B.vbc_u * x * (height - x) / (height * height);
+    } else {
+        return;
+    }
+    R = B.vbc_R;
+    T = B.vbc_T;
+    gamma = B.vbc_gamma;
+}
+
+struct Region {
+    int lo[3], hi[3];     // cells of the region (local indices, inclusive)
+    int in_lo[3], in_hi[3];  // the `inside` box of BC.H:374-380
+};
+
+// BCFill::operator() (BC.H:345-471) for the cells of one face / edge / corner region;
+// blockIdx.y = lattice (0: f, 1: g = energy lattice)
+__global__ void __launch_bounds__(64) k_bc_region(double* __restrict__ f, double* __restrict__ g, Layout L, BcInfo B,
+                                                  Region Rg)
+{
+    const int n0 = Rg.hi[0] - Rg.lo[0] + 1, n1 = Rg.hi[1] - Rg.lo[1] + 1, n2 = Rg.hi[2] - Rg.lo[2] + 1;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n0 * n1 * n2) return;
+    const int i = Rg.lo[0] + (int)(t % n0);
+    t /= n0;
+    const int j = Rg.lo[1] + (int)(t % n1);
+    const int k = Rg.lo[2] + (int)(t / n1);
+    const bool energy = blockIdx.y == 1;
+    double* __restrict__ data = energy ? g : f;
+    const long long c = L.cell(i, j, k);
+    const int iv[3] = {i, j, k};
+    for (int idir = 0; idir < 3; ++idir) {
+        for (int lohi = 0; lohi < 2; ++lohi) {
+            const int g_iv = iv[idir] + L.lo[idir];
+            if (!((lohi == 0 && g_iv < L.dlo[idir]) || (lohi == 1 && g_iv > L.dhi[idir]))) continue;
+            const int ndir = lohi == 0 ? 1 : -1;
+            const int bc = B.bc[idir + 3 * lohi];
+            // quantities that do not depend on q
+            double vel[3] = {0.0, 0.0, 0.0}, R = 1.0, T = 1.0 / 3.0, gamma = 5.0 / 3.0;
+            double rho_bc = (bc == 3) ? 1.0 : 0.0;
+            if (bc == 2 || bc == 3) vel_bc_op(B, L, i + L.lo[0], j + L.lo[1], k + L.lo[2], rho_bc, vel, R, T, gamma);
+            for (int q = 0; q < NQ; ++q) {
+                const int e[3] = {c_dir.ex[q], c_dir.ey[q], c_dir.ez[q]};
+                const int in = i + e[0], jn = j + e[1], kn = k + e[2];
+                const bool inside = in >= Rg.in_lo[0] && in <= Rg.in_hi[0] && jn >= Rg.in_lo[1] && jn <= Rg.in_hi[1] &&
+                                    kn >= Rg.in_lo[2] && kn <= Rg.in_hi[2];
+                double* dst = data + (long long)q * L.sq + c;
+                if (!inside) {
+                    *dst = -1.0;  // BC.H:463-466
+                    continue;
+                }
+                const long long cn = L.cell(in, jn, kn);
+                if (bc == 1) {  // NOSLIPWALL, BC.H:81
+                    *dst = data[(long long)c_dir.opp[q] * L.sq + cn];
+                } else if (bc == 2) {  // VELOCITY, BC.H:394-419
+                    *dst = energy ? geq_state(rho_bc, vel, T, R, gamma, q) : feq_std(rho_bc, vel, R * T, q);
+                } else if (bc == 3) {  // PRESSURE, BC.H:421-450, 242-268, 298-320
+                    double vb[3] = {0.0, 0.0, 0.0};
+                    if (energy) {
+                        vb[idir] = ndir * (1.0 - 1.0 / rho_bc);
+                        *dst = geq_state(rho_bc, vb, T, R, gamma, q);
+                    } else {
+                        double rho_out = 0.0, rho_tan = 0.0;
+                        for (int qq = 0; qq < NQ; ++qq) {
+                            const int bq = c_dir.opp[qq];
+                            const int ei[3] = {c_dir.ex[bq], c_dir.ey[bq], c_dir.ez[bq]};
+                            const long long cs = cn + c_dir.ex[qq] + c_dir.ey[qq] * L.px + c_dir.ez[qq] * L.sz;
+                            if (ei[idir] == -ndir) {
+                                rho_out += 2.0 * data[(long long)bq * L.sq + cs];
+                            } else if (ei[idir] == 0) {
+                                rho_tan += data[(long long)bq * L.sq + cs];
+                            }
+                        }
+                        vb[idir] = ndir * (1.0 - (rho_out + rho_tan) / rho_bc);
+                        *dst = feq_std(rho_bc, vb, R * T, q);
+                    }
+                } else if (bc == 5) {  // OUTFLOW_ZEROTH_ORDER, BC.H:339-341
+                    const long long step = idir == 0 ? 1 : idir == 1 ? L.px : L.sz;
+                    *dst = data[(long long)q * L.sq + c + ndir * step];
+                } else if (bc == 6) {  // SLIPWALLXNORMAL, BC.H:100
+                    *dst = data[(long long)c_dir.mx[q] * L.sq + cn];
+                } else if (bc == 7) {
+                    *dst = data[(long long)c_dir.my[q] * L.sq + cn];
+                } else if (bc == 8) {
+                    *dst = data[(long long)c_dir.mz[q] * L.sq + cn];
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// flags
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int fab_fluid(const int32_t* fab, const Layout& L, int ng, int i, int j, int k)
+{
+    // FAB layout over the valid box grown by ng; cells beyond it count as fluid
+    if (i < -ng || i >= L.nx + ng || j < -ng || j >= L.ny + ng || k < -ng || k >= L.nz + ng) return 1;
+    const long long sx = L.nx + 2 * ng, sy = L.ny + 2 * ng;
+    return fab[(i + ng) + (j + ng) * sx + (long long)(k + ng) * sx * sy];
+}
+
+__global__ void __launch_bounds__(128) k_flags(const int32_t* __restrict__ fab, int ng, uint32_t* __restrict__ nbr,
+                                               uint8_t* __restrict__ flag, Layout L, BcInfo B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - GX;
+    const int j = blockIdx.y - GY;
+    const int k = blockIdx.z - GZ;
+    if (i > L.nx - 1 + GX) return;
+    const long long c = L.cell(i, j, k);
+    uint32_t m = 0;
+    for (int q = 0; q < NQ; ++q) {
+        const int fl = fab ? fab_fluid(fab, L, ng, i - c_dir.ex[q], j - c_dir.ey[q], k - c_dir.ez[q]) : 1;
+        m |= (fl == 1 ? 1u : 0u) << q;
+    }
+    unsigned fb = (m & 1u) ? FLAG_FLUID : 0u;
+    const int iv[3] = {i, j, k};
+    const unsigned bp[3] = {GRAD_PX, GRAD_PY, GRAD_PZ}, bm[3] = {GRAD_MX, GRAD_MY, GRAD_MZ};
+    bool any_fluid_face = false;
+    for (int d = 0; d < 3; ++d) {
+        int p[3] = {i, j, k}, mm[3] = {i, j, k};
+        p[d] += 1;
+        mm[d] -= 1;
+        const int fp = fab ? fab_fluid(fab, L, ng, p[0], p[1], p[2]) : 1;
+        const int fm = fab ? fab_fluid(fab, L, ng, mm[0], mm[1], mm[2]) : 1;
+        // gradient(): neighbour inside the DOMAIN box (not periodic-grown) and fluid
+        // (Utilities.H:292-309 with dbox = geom.Domain(), LBM.cpp:968)
+        if (in_dom(L, d, iv[d] + 1) && in_dom(L, (d + 1) % 3, iv[(d + 1) % 3]) && in_dom(L, (d + 2) % 3, iv[(d + 2) % 3]) &&
+            fp == 1)
+            fb |= bp[d];
+        if (in_dom(L, d, iv[d] - 1) && in_dom(L, (d + 1) % 3, iv[(d + 1) % 3]) && in_dom(L, (d + 2) % 3, iv[(d + 2) % 3]) &&
+            fm == 1)
+            fb |= bm[d];
+        any_fluid_face |= (fp != 0) || (fm != 0);
+    }
+    // eb_boundary: solid cell with a fluid face neighbour (LBM.cpp:1236-1259)
+    if (!(m & 1u) && any_fluid_face) fb |= FLAG_EBB;
+    nbr[c] = m;
+    flag[c] = (uint8_t)fb;
+}
+
+// ---------------------------------------------------------------------------
+// layout conversion: one component, FAB(ng) <-> SoA
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_fab_to_soa(const double* __restrict__ fab, int ng, double* __restrict__ soa,
+                                                    Layout L, int gx, int gy, int gz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - gx;
+    const int j = blockIdx.y - gy;
+    const int k = blockIdx.z - gz;
+    if (i > L.nx - 1 + gx) return;
+    const long long sx = L.nx + 2 * ng, sy = L.ny + 2 * ng;
+    soa[L.cell(i, j, k)] = fab[(i + ng) + (j + ng) * sx + (long long)(k + ng) * sx * sy];
+}
+__global__ void __launch_bounds__(128) k_soa_to_fab(const double* __restrict__ soa, int ng, double* __restrict__ fab,
+                                                    Layout L)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int k = blockIdx.z;
+    if (i >= L.nx) return;
+    const long long sx = L.nx + 2 * ng, sy = L.ny + 2 * ng;
+    fab[(i + ng) + (j + ng) * sx + (long long)(k + ng) * sx * sy] = soa[L.cell(i, j, k)];
+}
+__global__ void k_fill(double* __restrict__ p, long long n, double v)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; t < n; t += stride) p[t] = v;
+}
+
+// ---------------------------------------------------------------------------
+// initial conditions (IC.H), valid cells + ghost cells of the padded box
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_initialize(double* __restrict__ f, double* __restrict__ g,
+                                                    const uint8_t* __restrict__ flag, Layout L, BcInfo B, IcInfo I)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - GX;
+    const int j = blockIdx.y - GY;
+    const int k = blockIdx.z - GZ;
+    if (i > L.nx - 1 + GX) return;
+    const long long c = L.cell(i, j, k);
+    const int gi = i + L.lo[0], gj = j + L.lo[1], gk = k + L.lo[2];
+    double rho = 1.0, vel[3] = {0.0, 0.0, 0.0}, T = 1.0 / 3.0, R = 1.0, gamma = 1.667;
+    const double PI = 3.14159265358979323846;
+    if (I.kind == 0) {  // IC.H:42-57
+        rho = I.density;
+        vel[0] = I.vel[0], vel[1] = I.vel[1], vel[2] = I.vel[2];
+        T = I.T0, R = I.R, gamma = I.gamma;
+    } else if (I.kind == 1) {  // IC.H:119-153
+        const double x = B.prob_lo[0] + (gi + 0.5) * B.dx[0];
+        const double y = B.prob_lo[1] + (gj + 0.5) * B.dx[1];
+        const double z = B.prob_lo[2] + (gk + 0.5) * B.dx[2];
+        const double Lc = 1.0 / PI;
+        rho = I.density + I.density * I.v0 * I.v0 / 16.0 * (cos(2.0 * I.omega[0] * x / Lc) + cos(2.0 * I.omega[1] * y / Lc)) *
+                              (cos(2.0 * I.omega[2] * z / Lc) + 2.0);
+        vel[0] = I.v0 * sin(I.omega[0] * x / Lc) * cos(I.omega[1] * y / Lc) * cos(I.omega[2] * z / Lc);
+        vel[1] = -I.v0 * cos(I.omega[0] * x / Lc) * sin(I.omega[1] * y / Lc) * cos(I.omega[2] * z / Lc);
+        vel[2] = 0.0;
+        T = I.T0, R = I.R, gamma = 5.0 / 3.0;
+    } else if (I.kind == 2) {  // IC.H:213-240
+        const double y = B.prob_lo[1] + (gj + 0.5 * 0.0) * B.dx[1];
+        rho = I.density;
+        vel[0] = I.vel[0] + 0.010 * I.c_s * sin(2.0 * PI * y / I.wave_length);
+        vel[1] = I.vel[1], vel[2] = I.vel[2];
+        T = I.T0, R = I.R, gamma = I.gamma;
+    } else if (I.kind == 3) {  // IC.H:302-333
+        const double y = B.prob_lo[1] + (gj + 0.5 * 0.0) * B.dx[1];
+        R = I.R;
+        const double pressure = I.density * R * I.T0;
+        rho = I.density + 0.0010 * I.T0 * sin(2.0 * PI * y / I.wave_length);
+        vel[0] = I.vel[0], vel[1] = I.vel[1], vel[2] = I.vel[2];
+        gamma = I.gamma;
+        T = pressure / (rho * R);
+    } else if (I.kind == 4) {  // IC.H:394-428
+        const double x = B.prob_lo[0] + (gi + 0.5 * 0.0) * B.dx[0];
+        R = I.R, gamma = I.gamma;
+        vel[0] = I.vel[0], vel[1] = I.vel[1], vel[2] = I.vel[2];
+        const double s = 0.5 * (1.0 + tanh((x - I.x_disc) * 3.0));
+        rho = I.density + s * (I.density_ratio * I.density - I.density);
+        T = I.T0 + s * (I.temperature_ratio * I.T0 - I.T0);
+    }
+    const bool solid = !(flag[c] & FLAG_FLUID);
+    for (int q = 0; q < NQ; ++q) {
+        f[(long long)q * L.sq + c] = solid ? 0.0 : feq_std(rho, vel, R * T, q);
+        g[(long long)q * L.sq + c] = solid ? 0.0 : geq_state(rho, vel, T, R, gamma, q);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// z-halo pack / unpack: GZ whole padded planes per component are contiguous
+// ---------------------------------------------------------------------------
+__global__ void k_halo_copy(double* __restrict__ f, double* __restrict__ g, double* __restrict__ buf, Layout L, int k0,
+                            int to_buf)
+{
+    const long long chunk = (long long)GZ * L.sz;
+    const long long total = 2LL * NQ * chunk;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long base = (long long)(k0 + GZ) * L.sz;
+    for (; t < total; t += stride) {
+        const long long w = t % chunk;
+        const int q = (int)((t / chunk) % NQ);
+        const int lat = (int)(t / (chunk * NQ));
+        double* p = (lat ? g : f) + (long long)q * L.sq + base + w;
+        if (to_buf)
+            buf[t] = *p;
+        else
+            *p = buf[t];
+    }
+}
+
+// ===========================================================================
+// launchers
+// ===========================================================================
+static inline dim3 grid3(const Layout& L, int bx, int ex_ = 0, int ey_ = 0, int ez_ = 0)
+{
+    return dim3((L.nx + 2 * ex_ + bx - 1) / bx, L.ny + 2 * ey_, L.nz + 2 * ez_);
+}
+static inline int block_x(const Layout& L) { return L.nx >= 128 ? 128 : L.nx > 32 ? 64 : 32; }
+
+int launch_flags(const Layout& L, const BcInfo& B, const int32_t* fab, int ng, uint32_t* nbr, uint8_t* flag,
+                 cudaStream_t st)
+{
+    const int bx = block_x(L);
+    k_flags<<<grid3(L, bx, GX, GY, GZ), bx, 0, st>>>(fab, ng, nbr, flag, L, B);
+    return 1;
+}
+int launch_flags_all_fluid(const Layout& L, const BcInfo& B, uint32_t* nbr, uint8_t* flag, cudaStream_t st)
+{
+    return launch_flags(L, B, nullptr, 0, nbr, flag, st);
+}
+
+int launch_fab_to_soa(const Layout& L, const double* fab, int ng, double* soa, int with_ghosts, cudaStream_t st)
+{
+    const int bx = block_x(L);
+    const int gx = with_ghosts ? (ng < GX ? ng : GX) : 0, gy = with_ghosts ? (ng < GY ? ng : GY) : 0,
+              gz = with_ghosts ? (ng < GZ ? ng : GZ) : 0;
+    k_fab_to_soa<<<grid3(L, bx, gx, gy, gz), bx, 0, st>>>(fab, ng, soa, L, gx, gy, gz);
+    return 1;
+}
+int launch_soa_to_fab(const Layout& L, const double* soa, int ng, double* fab, cudaStream_t st)
+{
+    const int bx = block_x(L);
+    k_soa_to_fab<<<grid3(L, bx), bx, 0, st>>>(soa, ng, fab, L);
+    return 1;
+}
+int launch_fill(double* p, long long n, double v, cudaStream_t st)
+{
+    k_fill<<<148 * 8, 256, 0, st>>>(p, n, v);
+    return 1;
+}
+
+int launch_initialize(const Layout& L, const BcInfo& B, const IcInfo& I, const uint8_t* flag, double* f, double* g,
+                      cudaStream_t st)
+{
+    const int bx = block_x(L);
+    k_initialize<<<grid3(L, bx, GX, GY, GZ), bx, 0, st>>>(f, g, flag, L, B, I);
+    return 1;
+}
+
+static bool side_range(const Layout& L, const BcInfo& B, int d, int side, int& a0, int& a1)
+{
+    const int n[3] = {L.nx, L.ny, L.nz};
+    const int gw[3] = {GX, GY, GZ};
+    const int plo = -gw[d], phi = n[d] - 1 + gw[d];
+    const int big = 1 << 28;
+    const int glo = B.periodic[d] ? -big : L.dlo[d] - L.lo[d];
+    const int ghi = B.periodic[d] ? big : L.dhi[d] - L.lo[d];
+    if (side < 0) {
+        a0 = plo;
+        a1 = glo - 1 < phi ? glo - 1 : phi;
+    } else if (side > 0) {
+        a0 = ghi + 1 > plo ? ghi + 1 : plo;
+        a1 = phi;
+    } else {
+        a0 = glo > plo ? glo : plo;
+        a1 = ghi < phi ? ghi : phi;
+    }
+    return a0 <= a1;
+}
+
+static int launch_bc_region(const Layout& L, const BcInfo& B, double* f, double* g, int sx, int sy, int sz,
+                            cudaStream_t st)
+{
+    Region R;
+    const int s[3] = {sx, sy, sz};
+    for (int d = 0; d < 3; ++d)
+        if (!side_range(L, B, d, s[d], R.lo[d], R.hi[d])) return 0;
+    const int n[3] = {L.nx, L.ny, L.nz};
+    for (int d = 0; d < 3; ++d) {
+        R.in_lo[d] = 0;
+        R.in_hi[d] = n[d] - 1;
+    }
+    // the z-ghost planes that belong to a neighbouring rank are valid cells of the level: BC values
+    // that stream into them are needed for the q-correction of the first ghost plane
+    if (L.lo[2] > L.dlo[2]) R.in_lo[2] = -GZ;
+    if (L.lo[2] + L.nz - 1 < L.dhi[2]) R.in_hi[2] = L.nz - 1 + GZ;
+    const long long cells = (long long)(R.hi[0] - R.lo[0] + 1) * (R.hi[1] - R.lo[1] + 1) * (R.hi[2] - R.lo[2] + 1);
+    dim3 grid((unsigned)((cells + 63) / 64), 2, 1);
+    k_bc_region<<<grid, 64, 0, st>>>(f, g, L, B, R);
+    return 1;
+}
+
+int launch_ghost_fill(const Layout& L, const BcInfo& B, double* f, double* g, bool local_z, bool do_prepass,
+                      bool do_periodic, cudaStream_t st)
+{
+    int nl = 0;
+    const int bx = block_x(L);
+    const Shell S = make_shell(L);
+    const bool all_periodic = B.periodic[0] && B.periodic[1] && B.periodic[2];
+    if (do_periodic && local_z && B.periodic[2]) {
+        k_zwrap<<<dim3((L.nx + bx - 1) / bx, L.ny, 2 * GZ), bx, 0, st>>>(f, g, L);
+        ++nl;
+    }
+    const unsigned sb = (unsigned)((S.off[6] + 127) / 128);
+    if (do_prepass && !all_periodic) {
+        k_prepass<<<sb, 128, 0, st>>>(f, g, L, S, B);
+        ++nl;
+    }
+    if (do_periodic && (B.periodic[0] || B.periodic[1])) {
+        k_xywrap<<<sb, 128, 0, st>>>(f, g, L, S, B);
+        ++nl;
+    }
+    if (all_periodic) return nl;  // PhysBCFunct::operator() returns early (AMReX_PhysBCFunct.H:202)
+    // faces (xlo ylo zlo xhi yhi zhi), edges, corners: AMReX_PhysBCFunct.H:593-678
+    nl += launch_bc_region(L, B, f, g, -1, 0, 0, st);
+    nl += launch_bc_region(L, B, f, g, 0, -1, 0, st);
+    nl += launch_bc_region(L, B, f, g, 0, 0, -1, st);
+    nl += launch_bc_region(L, B, f, g, +1, 0, 0, st);
+    nl += launch_bc_region(L, B, f, g, 0, +1, 0, st);
+    nl += launch_bc_region(L, B, f, g, 0, 0, +1, st);
+    for (int s1 = -1; s1 <= 1; s1 += 2)
+        for (int s0 = -1; s0 <= 1; s0 += 2) nl += launch_bc_region(L, B, f, g, s0, s1, 0, st);
+    for (int s1 = -1; s1 <= 1; s1 += 2)
+        for (int s0 = -1; s0 <= 1; s0 += 2) nl += launch_bc_region(L, B, f, g, s0, 0, s1, st);
+    for (int s1 = -1; s1 <= 1; s1 += 2)
+        for (int s0 = -1; s0 <= 1; s0 += 2) nl += launch_bc_region(L, B, f, g, 0, s0, s1, st);
+    for (int s2 = -1; s2 <= 1; s2 += 2)
+        for (int s1 = -1; s1 <= 1; s1 += 2)
+            for (int s0 = -1; s0 <= 1; s0 += 2) nl += launch_bc_region(L, B, f, g, s0, s1, s2, st);
+    return nl;
+}
+
+int launch_qcorr(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr, double* qc,
+                 bool pull, cudaStream_t st)
+{
+    const int bx = block_x(L);
+    // q-corrections are needed on the valid cells and, where the box borders another rank in z,
+    // on the first ghost plane (recomputed from the two exchanged planes instead of a second exchange)
+    const int k0 = (L.lo[2] > L.dlo[2]) ? -1 : 0;
+    const int k1 = (L.lo[2] + L.nz - 1 < L.dhi[2]) ? L.nz : L.nz - 1;
+    dim3 grid((L.nx + bx - 1) / bx, L.ny, k1 - k0 + 1);
+    if (pull)
+        k_qcorr<true><<<grid, bx, 0, st>>>(fin, gin, nbr, qc, L, P, k0);
+    else
+        k_qcorr<false><<<grid, bx, 0, st>>>(fin, gin, nbr, qc, L, P, k0);
+    return 1;
+}
+
+int launch_collide(const Layout& L, const Phys& P, const double* fin, const double* gin, double* fout, double* gout,
+                   const uint32_t* nbr, const uint8_t* flag, const double* qc, double* macro, bool pull,
+                   cudaStream_t st)
+{
+    const int bx = block_x(L);
+    const dim3 grid = grid3(L, bx);
+    if (pull) {
+        if (macro)
+            k_collide<true, true><<<grid, bx, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P);
+        else
+            k_collide<true, false><<<grid, bx, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P);
+    } else {
+        if (macro)
+            k_collide<false, true><<<grid, bx, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P);
+        else
+            k_collide<false, false><<<grid, bx, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P);
+    }
+    return 1;
+}
+
+int launch_stream(const Layout& L, const double* fin, const double* gin, double* fout, double* gout,
+                  const uint32_t* nbr, cudaStream_t st)
+{
+    const int bx = block_x(L);
+    k_stream<<<grid3(L, bx), bx, 0, st>>>(fin, gin, fout, gout, nbr, L);
+    return 1;
+}
+
+int launch_macrodata(const Layout& L, const Phys& P, const double* f, const double* g, const uint8_t* flag,
+                     double* macro, cudaStream_t st)
+{
+    const int bx = block_x(L);
+    k_macrodata<<<grid3(L, bx), bx, 0, st>>>(f, g, flag, macro, L, P);
+    return 1;
+}
+
+int launch_derived(const Layout& L, const Phys& P, const uint8_t* flag, const double* macro, double* derived,
+                   cudaStream_t st)
+{
+    const int bx = block_x(L);
+    k_derived<<<grid3(L, bx), bx, 0, st>>>(flag, macro, derived, L, P);
+    return 1;
+}
+
+int launch_eb_forces(const Layout& L, const double* f, const uint8_t* flag, double* d_out3, cudaStream_t st)
+{
+    const int bx = block_x(L);
+    cudaMemsetAsync(d_out3, 0, 3 * sizeof(double), st);
+    k_eb_forces<<<grid3(L, bx), bx, 0, st>>>(f, flag, d_out3, L);
+    return 1;
+}
+
+int launch_halo_pack(const Layout& L, const double* f, const double* g, int side, double* buf, cudaStream_t st)
+{
+    const int k0 = side == 0 ? 0 : L.nz - GZ;
+    k_halo_copy<<<148 * 4, 256, 0, st>>>(const_cast<double*>(f), const_cast<double*>(g), buf, L, k0, 1);
+    return 1;
+}
+int launch_halo_unpack(const Layout& L, double* f, double* g, int side, const double* buf, cudaStream_t st)
+{
+    const int k0 = side == 0 ? -GZ : L.nz;
+    k_halo_copy<<<148 * 4, 256, 0, st>>>(f, g, const_cast<double*>(buf), L, k0, 0);
+    return 1;
+}
+
+}  // namespace mbl

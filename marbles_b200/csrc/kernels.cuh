@@ -1,0 +1,69 @@
+// kernels.cuh -- launch interface between the C ABI (api.cu) and the CUDA kernels
+// (kernels.cu).  Every launcher enqueues on `st` and returns the number of kernels
+// it launched.
+#pragma once
+#include "lattice.cuh"
+
+namespace mbl {
+
+struct BcInfo {
+    int periodic[3];
+    int bc[6];  // idir + 3*lohi
+    int vbc_kind, vbc_dir, vbc_normal_dir, vbc_tangential_dir;
+    double vbc_u, vbc_rho, vbc_T, vbc_gamma, vbc_R;
+    double prob_lo[3], prob_hi[3], dx[3];
+};
+
+struct IcInfo {
+    int kind;
+    double density, vel[3], v0, omega[3], wave_length, T0, gamma, R, c_s, density_ratio, temperature_ratio, x_disc;
+};
+
+struct LevelPtrs {
+    double* f[2];  // ping-pong lattice buffers
+    double* g[2];
+    double* qc;     // 3 comps: QCorr_x, QCorr_y, QCorr_z of the post-stream state
+    double* macro;  // 19 comps or nullptr
+    double* derived;  // 7 comps or nullptr
+    uint32_t* nbr;  // 27-bit pull mask
+    uint8_t* flag;  // flag byte field
+};
+
+void init_tables();
+
+int launch_flags(const Layout& L, const BcInfo& B, const int32_t* d_isfluid_fab, int ng, uint32_t* nbr, uint8_t* flag,
+                 cudaStream_t st);
+int launch_flags_all_fluid(const Layout& L, const BcInfo& B, uint32_t* nbr, uint8_t* flag, cudaStream_t st);
+
+int launch_fab_to_soa(const Layout& L, const double* d_fab_comp, int ng, double* soa_comp, int with_ghosts,
+                      cudaStream_t st);
+int launch_soa_to_fab(const Layout& L, const double* soa_comp, int ng, double* d_fab_comp, cudaStream_t st);
+int launch_fill(double* p, long long n, double v, cudaStream_t st);
+
+int launch_initialize(const Layout& L, const BcInfo& B, const IcInfo& I, const uint8_t* flag, double* f, double* g,
+                      cudaStream_t st);
+
+// ghost fill of the CURRENT buffers; `local_z` = this box spans the whole domain in z
+// (periodic z is then wrapped locally, otherwise z ghost planes come from mbl_halo_*)
+int launch_ghost_fill(const Layout& L, const BcInfo& B, double* f, double* g, bool local_z, bool do_prepass,
+                      bool do_periodic, cudaStream_t st);
+
+// two-pass collide.  pull=true: stream+collide fused, reads (fin,gin) writes (fout,gout);
+// pull=false: collide in place on the streamed state.
+int launch_qcorr(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr, double* qc,
+                 bool pull, cudaStream_t st);
+int launch_collide(const Layout& L, const Phys& P, const double* fin, const double* gin, double* fout, double* gout,
+                   const uint32_t* nbr, const uint8_t* flag, const double* qc, double* macro, bool pull,
+                   cudaStream_t st);
+int launch_stream(const Layout& L, const double* fin, const double* gin, double* fout, double* gout,
+                  const uint32_t* nbr, cudaStream_t st);
+int launch_macrodata(const Layout& L, const Phys& P, const double* f, const double* g, const uint8_t* flag,
+                     double* macro, cudaStream_t st);
+int launch_derived(const Layout& L, const Phys& P, const uint8_t* flag, const double* macro, double* derived,
+                   cudaStream_t st);
+int launch_eb_forces(const Layout& L, const double* f, const uint8_t* flag, double* d_out3, cudaStream_t st);
+
+int launch_halo_pack(const Layout& L, const double* f, const double* g, int side, double* buf, cudaStream_t st);
+int launch_halo_unpack(const Layout& L, double* f, double* g, int side, const double* buf, cudaStream_t st);
+
+}  // namespace mbl

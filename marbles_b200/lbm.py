@@ -1,0 +1,294 @@
+"""Host-side mirror of the reference's `lbm::LBM` surface for the accelerated path.
+
+The reference drives the lattice update through member functions of
+`lbm::LBM : amrex::AmrCore` (Source/LBM.H:28-119).  This class keeps their names,
+argument meaning and call order for the single-level hot path and forwards each of
+them to the C ABI (include/marbles_b200.h):
+
+    LBM::init_data            Source/LBM.cpp:155-194   -> mbl_level_define, mbl_set_is_fluid, mbl_initialize
+    LBM::evolve               Source/LBM.cpp:398-448   -> fillpatch, time_step, post_time_step per step
+    FillPatchOps::fillpatch   Source/FillPatchOps.H:75-132 -> mbl_fillpatch (+ z-halo exchange between ranks)
+    LBM::advance              Source/LBM.cpp:523-544   -> stream(f), stream(g), collide
+    LBM::stream               Source/LBM.cpp:558-604   -> mbl_stream
+    LBM::collide              Source/LBM.cpp:607-618   -> mbl_collide
+    LBM::f_to_macrodata       Source/LBM.cpp:810-906   -> mbl_f_to_macrodata
+    LBM::compute_derived      Source/LBM.cpp:909-955   -> mbl_compute_derived
+    LBM::compute_eb_forces    Source/LBM.cpp:994-1044  -> mbl_eb_forces (+ all-reduce)
+
+`step()` is the fused fast path (mbl_step): same result as fillpatch + advance.
+Errors raise (the reference calls amrex::Abort).  No CPU fallback exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import LevelGeom, Layout, MarblesError, Params, check
+from .geometry import is_fluid_from_deck
+from .inputs import LbmInputs, lbm_inputs, parse_deck
+
+NQ, NMACRO, NDERIVED = 27, 19, 7
+MACRO_NAMES = ["rho", "vel_x", "vel_y", "vel_z", "vel_mag", "two_rho_e", "QCorrX", "QCorrY", "QCorrZ",
+               "pxx", "pyy", "pzz", "pxy", "pxz", "pyz", "qx", "qy", "qz", "temperature"]
+DERIVED_NAMES = ["vort_x", "vort_y", "vort_z", "vort_mag", "dQCorrX", "dQCorrY", "dQCorrZ"]
+F_NGHOST = 3  # m_f_nghost, Source/LBM.H:230
+
+
+def _dptr(a: np.ndarray):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def slab_bounds(nz: int, rank: int, world: int) -> tuple[int, int]:
+    """z-range [lo, hi] (inclusive) of `rank`'s slab: contiguous, sizes differ by at most one plane."""
+    base, rem = divmod(nz, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0) - 1
+
+
+class LBM:
+    """Single-level lattice-Boltzmann state of one rank (one z-slab of the domain) on one B200."""
+
+    def __init__(self, deck=None, overrides=None, *, inputs: LbmInputs | None = None, device: int = 0,
+                 rank: int = 0, world: int = 1, comm=None, is_fluid: np.ndarray | None = None,
+                 cuda_stream: int | None = None):
+        if inputs is None:
+            d = deck if isinstance(deck, dict) else parse_deck(deck, overrides)
+            if isinstance(deck, dict) and overrides:
+                d = dict(d)
+                d.update(parse_deck(None, overrides))
+            inputs = lbm_inputs(d)
+        self.inp = inputs
+        self.rank, self.world, self.comm = rank, world, comm
+        self.lib = _lib.load()
+        self.ctx = C.c_void_p()
+        self.lev = 0
+        self.time = 0.0
+        self.isteps = 0
+        self.dt = 1.0  # est_time_step == 1 (Source/LBM.cpp:1080-1084)
+        n = inputs.n_cell
+        zlo, zhi = slab_bounds(n[2], rank, world)
+        self.lo = (0, 0, zlo)
+        self.hi = (n[0] - 1, n[1] - 1, zhi)
+        self.n_local = (n[0], n[1], zhi - zlo + 1)
+
+        p = Params()
+        p.nu, p.alpha, p.R, p.gamma, p.mesh_speed = inputs.nu, inputs.alpha, inputs.R, inputs.gamma, inputs.mesh_speed
+        for d in range(3):
+            p.bc_type[d] = inputs.bc_lo[d]
+            p.bc_type[d + 3] = inputs.bc_hi[d]
+            p.periodic[d] = inputs.periodic[d]
+        p.vbc_kind, p.vbc_dir = inputs.vbc_kind, inputs.vbc_dir
+        p.vbc_normal_dir, p.vbc_tangential_dir = inputs.vbc_normal_dir, inputs.vbc_tangential_dir
+        p.vbc_u, p.vbc_rho, p.vbc_T = inputs.vbc_u, inputs.vbc_rho, inputs.vbc_T
+        p.vbc_gamma, p.vbc_R = inputs.vbc_gamma, inputs.vbc_R
+        self.params = p
+        check(self.lib.mbl_create(C.byref(p), device, C.byref(self.ctx)))
+        if cuda_stream is not None:
+            check(self.lib.mbl_set_stream(self.ctx, C.c_void_p(cuda_stream)))
+
+        g = LevelGeom()
+        dx = inputs.dx
+        for d in range(3):
+            g.dom_lo[d], g.dom_hi[d] = 0, n[d] - 1
+            g.lo[d], g.hi[d] = self.lo[d], self.hi[d]
+            g.inv_dx[d] = 1.0 / dx[d]
+            g.prob_lo[d], g.prob_hi[d], g.dx[d] = inputs.prob_lo[d], inputs.prob_hi[d], dx[d]
+        g.dt = self.dt
+        self.geom = g
+        self.layout = Layout()
+        check(self.lib.mbl_level_layout(C.byref(g), C.byref(self.layout)))
+        check(self.lib.mbl_level_define(self.ctx, self.lev, C.byref(g), None))
+        self._is_fluid = None
+        self._halo = None
+        self.set_is_fluid(is_fluid)
+
+    # ------------------------------------------------------------------ setup
+    def close(self):
+        if self.ctx:
+            self.lib.mbl_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_is_fluid(self, is_fluid: np.ndarray | None):
+        """LBM::initialize_is_fluid (Source/LBM.cpp:1213-1262).  `is_fluid`: component 0 on the local
+        valid box [nz,ny,nx] or on the box grown by F_NGHOST; None -> eb2.geom_type of the deck."""
+        ng = F_NGHOST
+        nx, ny, nz = self.n_local
+        full = (nz + 2 * ng, ny + 2 * ng, nx + 2 * ng)
+        if is_fluid is None:
+            a = is_fluid_from_deck(self.inp.deck, self.inp.n_cell, self.inp.prob_lo, self.inp.dx, self.lo,
+                                   self.n_local, ng)
+            if a.min() == 1:
+                self._is_fluid = a
+                check(self.lib.mbl_set_all_fluid(self.ctx, self.lev))
+                return
+            a = self._wrap_periodic(a, ng, z_local=self.world == 1)
+        else:
+            is_fluid = np.asarray(is_fluid, dtype=np.int32)
+            if is_fluid.shape == full:
+                a = np.ascontiguousarray(is_fluid)
+            elif is_fluid.shape == (nz, ny, nx):
+                a = np.ones(full, dtype=np.int32)
+                a[ng:-ng, ng:-ng, ng:-ng] = is_fluid
+                a = self._wrap_periodic(a, ng, z_local=self.world == 1)
+            else:
+                raise MarblesError(f"is_fluid has shape {is_fluid.shape}, expected {(nz, ny, nx)} or {full}")
+        self._is_fluid = a
+        check(self.lib.mbl_set_is_fluid(self.ctx, self.lev, a.ctypes.data_as(C.POINTER(C.c_int32)), ng))
+
+    def _wrap_periodic(self, a: np.ndarray, ng: int, z_local: bool) -> np.ndarray:
+        """m_is_fluid.FillBoundary(periodicity): ghost cells in periodic directions mirror the valid cells."""
+        a = a.copy()
+        nloc = self.n_local
+        for axis, d in ((2, 0), (1, 1), (0, 2)):
+            if not self.inp.periodic[d] or (d == 2 and not z_local):
+                continue
+            n = nloc[d]
+            idx = (np.arange(-ng, n + ng) % n) + ng
+            a = np.take(a, idx, axis=axis)
+        return np.ascontiguousarray(a)
+
+    def init_data(self):
+        """initialize_f of MakeNewLevelFromScratch (Source/LBM.cpp:1186-1198) on the device."""
+        v = (C.c_double * 16)(*self.inp.ic_params)
+        check(self.lib.mbl_initialize(self.ctx, self.lev, self.inp.ic_kind, v, 16))
+        self.time, self.isteps = 0.0, 0
+
+    # ---------------------------------------------------------------- operators
+    def exchange_halo(self):
+        """ghost planes owned by neighbouring ranks (the FillBoundary part that crosses ranks)."""
+        if self.world > 1:
+            if self.comm is None:
+                raise MarblesError("world > 1 needs a halo communicator (marbles_b200.parallel.HaloComm)")
+            self.comm.exchange(self)
+
+    def fillpatch(self, lev: int = 0, time: float | None = None):
+        """m_fillpatch_op->fillpatch(lev, time, m_f[lev]) and the same for m_g (Source/LBM.cpp:416-418)."""
+        self.exchange_halo()
+        check(self.lib.mbl_fillpatch(self.ctx, lev, self.time if time is None else time))
+
+    def physbc(self, lev: int = 0, time: float | None = None):
+        check(self.lib.mbl_physbc(self.ctx, lev, self.time if time is None else time))
+
+    def stream(self, lev: int = 0):
+        """stream(lev, m_f); stream(lev, m_g) (Source/LBM.cpp:535-537)."""
+        check(self.lib.mbl_stream(self.ctx, lev))
+
+    def collide(self, lev: int = 0, want_macrodata: bool = True):
+        if self.world > 1:
+            self.exchange_halo()  # post-stream state of the neighbours' edge planes (q-correction stencil)
+        check(self.lib.mbl_collide(self.ctx, lev, int(want_macrodata)))
+
+    def advance(self, lev: int = 0):
+        """LBM::advance (Source/LBM.cpp:523-544), un-fused."""
+        self.stream(lev)
+        self.collide(lev)
+
+    def f_to_macrodata(self, lev: int = 0):
+        check(self.lib.mbl_f_to_macrodata(self.ctx, lev))
+
+    def compute_derived(self, lev: int = 0):
+        check(self.lib.mbl_compute_derived(self.ctx, lev))
+
+    def compute_eb_forces(self) -> np.ndarray:
+        out = (C.c_double * 3)()
+        if self.world > 1:
+            self.exchange_halo()
+        check(self.lib.mbl_eb_forces(self.ctx, self.lev, out))
+        f = np.array(out[:])
+        if self.world > 1:
+            f = self.comm.allreduce_sum(f)
+        return f
+
+    def step(self, nsteps: int = 1, want_macrodata: bool = False):
+        """Fused fast path: nsteps x (fillpatch f, g; stream f, g; collide)."""
+        if self.world == 1:
+            check(self.lib.mbl_step(self.ctx, self.lev, nsteps, self.time, int(want_macrodata)))
+        else:
+            for s in range(nsteps):
+                self.exchange_halo()
+                check(self.lib.mbl_step_local(self.ctx, self.lev, self.time + s * self.dt,
+                                              int(want_macrodata and s == nsteps - 1)))
+        self.time += nsteps * self.dt
+        self.isteps += nsteps
+
+    def evolve(self, max_step: int | None = None, fused: bool = True, want_macrodata: bool = False):
+        """LBM::evolve (Source/LBM.cpp:398-448) without I/O."""
+        nsteps = self.inp.max_step if max_step is None else max_step
+        if fused:
+            self.step(nsteps, want_macrodata)
+            return
+        for _ in range(nsteps):
+            self.fillpatch(0)
+            self.advance(0)
+            self.time += self.dt
+            self.isteps += 1
+
+    def sync(self):
+        check(self.lib.mbl_sync(self.ctx))
+
+    def step_host(self, f_fab: np.ndarray, g_fab: np.ndarray, nsteps: int = 1, ng: int = F_NGHOST):
+        """The reference-facing call with HOST buffers (FAB layout): upload, nsteps, download in place."""
+        check(self.lib.mbl_step_host(self.ctx, self.lev, nsteps, self.time, _dptr(f_fab), _dptr(g_fab), ng))
+        self.time += nsteps * self.dt
+        self.isteps += nsteps
+
+    # ------------------------------------------------------------------ access
+    def fab_shape(self, ncomp: int, ng: int):
+        nx, ny, nz = self.n_local
+        return (ncomp, nz + 2 * ng, ny + 2 * ng, nx + 2 * ng)
+
+    def set_state(self, f: np.ndarray, g: np.ndarray, ng: int = F_NGHOST):
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        assert f.shape == self.fab_shape(NQ, ng) and g.shape == f.shape, (f.shape, self.fab_shape(NQ, ng))
+        check(self.lib.mbl_upload(self.ctx, self.lev, 0, _dptr(f), ng))
+        check(self.lib.mbl_upload(self.ctx, self.lev, 1, _dptr(g), ng))
+
+    def get_f(self, ng: int = 0) -> np.ndarray:
+        a = np.zeros(self.fab_shape(NQ, ng))
+        check(self.lib.mbl_download(self.ctx, self.lev, 0, _dptr(a), ng))
+        return a
+
+    def get_g(self, ng: int = 0) -> np.ndarray:
+        a = np.zeros(self.fab_shape(NQ, ng))
+        check(self.lib.mbl_download(self.ctx, self.lev, 1, _dptr(a), ng))
+        return a
+
+    def get_macrodata(self, ng: int = 0) -> np.ndarray:
+        a = np.zeros(self.fab_shape(NMACRO, ng))
+        check(self.lib.mbl_download_macrodata(self.ctx, self.lev, _dptr(a), ng))
+        return a
+
+    def get_derived(self) -> np.ndarray:
+        a = np.zeros(self.fab_shape(NDERIVED, 0))
+        check(self.lib.mbl_download_derived(self.ctx, self.lev, _dptr(a)))
+        return a
+
+    def fields(self) -> dict:
+        """Valid-cell fields under the reference's plotfile names (Source/LBM.cpp:302-340)."""
+        out = {}
+        m = self.get_macrodata()
+        for n, name in enumerate(MACRO_NAMES):
+            out[name] = m[n]
+        f, g = self.get_f(), self.get_g()
+        for q in range(NQ):
+            out[f"f_{q:02d}"] = f[q]
+            out[f"g_{q:02d}"] = g[q]
+        return out
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.mbl_launch_count(self.ctx))
+
+    @property
+    def ncells(self) -> int:
+        return int(np.prod(self.n_local))

@@ -1,0 +1,231 @@
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference.
+
+    python tests/golden/make_golden.py          # needs oracle/_ref/marbles3d.ex (make -C oracle ref)
+
+Each case is a small deck (written here, in the reference's deck format) run by
+the reference executable built from /root/reference by oracle/refbuild/Makefile.
+The plotfiles it writes (lbm.save_streaming=1, lbm.save_derived=1) are read back
+with oracle.read_plotfile and stored as <case>.npz:
+
+    deck        the deck text (tests re-parse it; nothing under /root/reference is read at test time)
+    steps       plotted step numbers stored
+    is_fluid    component 0 on valid cells (from plt00000)
+    s<N>_<name> every plotfile component of step N  (all 82 for the last step; f,g + macro for step 0)
+
+The reference ships no goldens of its own: these files are
+the pin for the oracle, and through it for the CUDA path.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+
+COMMON = """
+lbm.dx_outer = 1.0
+lbm.dt_outer = 1.0
+lbm.save_streaming = 1
+lbm.save_derived = 1
+amr.max_level = 0
+amr.plot_int = 1
+amr.chk_int = -1
+amr.max_grid_size = 64
+amr.blocking_factor = 2
+amrex.fpe_trap_invalid = 1
+amrex.fpe_trap_zero = 1
+amrex.fpe_trap_overflow = 1
+amrex.the_arena_is_managed = 0
+"""
+
+CASES = {
+    # config 1 of BASELINE.json at reduced size: periodic Taylor-Green vortex, uniform T0 = 1/3
+    "tg12": ("""
+max_step = 10
+geometry.prob_lo = -1.0 -1.0 -1.0
+geometry.prob_hi =  1.0  1.0  1.0
+geometry.is_periodic = 1 1 1
+amr.n_cell = 12 12 12
+lbm.bc_lo = 0 0 0
+lbm.bc_hi = 0 0 0
+lbm.nu = 0.1733333333333333
+lbm.ic_type = "taylorgreen"
+ic_taylorgreen.rho0 = 1.0
+ic_taylorgreen.v0 = 0.1
+eb2.geom_type = "all_regular"
+""", [0, 1, 10]),
+    # config 2: thermal Sod tube (gamma = 2, alpha set, zeroth-order outflow in x)
+    "sod48": ("""
+max_step = 30
+geometry.prob_lo = 0.0 -1.0 -1.0
+geometry.prob_hi = 48.0 1.0 1.0
+geometry.is_periodic = 0 1 1
+amr.n_cell = 48 2 2
+lbm.bc_lo = 5 0 0
+lbm.bc_hi = 5 0 0
+lbm.nu = 0.010
+lbm.alpha = 0.010
+lbm.ic_type = "sod"
+ic_sod.density = 0.50
+ic_sod.mach_components = 0.0 0.0 0.0
+ic_sod.x_discontinuity = 24.0
+ic_sod.initial_temperature = 0.20
+ic_sod.adiabatic_exponent = 2.0
+ic_sod.mean_molecular_mass = 28.96
+ic_sod.density_ratio = 4.00
+ic_sod.temperature_ratio = 0.1250
+lbm.initial_temperature = 0.20
+lbm.adiabatic_exponent = 2.0
+lbm.mean_molecular_mass = 28.96
+eb2.geom_type = "all_regular"
+""", [0, 1, 30]),
+    # config 4 at reduced size: channel inlet, outflow, no-slip walls, periodic z, EB cylinder
+    "chcyl": ("""
+max_step = 8
+geometry.prob_lo = 0.0 0.0 0.0
+geometry.prob_hi = 32.0 12.0 4.0
+geometry.is_periodic = 0 0 1
+amr.n_cell = 32 12 4
+lbm.bc_lo = 2 1 0
+lbm.bc_hi = 5 1 0
+lbm.nu = 0.0050
+lbm.velocity_bc_type = "channel"
+velocity_bc_channel.initial_density = 1.0
+velocity_bc_channel.Mach_ref = 0.01
+velocity_bc_channel.initial_temperature = 0.03
+lbm.ic_type = "constant"
+ic_constant.density = 1.0
+ic_constant.initial_temperature = 0.03
+ic_constant.mach_components = 0.0 0.0 0.0
+eb2.geom_type = "cylinder"
+eb2.cylinder_radius = 2.6
+eb2.cylinder_center = 9.0 6.0 8.0
+eb2.cylinder_has_fluid_inside = 0
+eb2.cylinder_height = 256.0
+eb2.cylinder_direction = 2
+""", [0, 1, 8]),
+    # Pr != 1, R != 1: exercises omega_one/omega != 1 (MRT heat flux) near the over-relaxation limit
+    "thermal": ("""
+max_step = 20
+geometry.prob_lo = 0.0 0.0 -1.0
+geometry.prob_hi = 4.0 24.0 1.0
+geometry.is_periodic = 1 1 1
+amr.n_cell = 4 24 2
+lbm.bc_lo = 0 0 0
+lbm.bc_hi = 0 0 0
+lbm.nu = 0.000008076
+lbm.alpha = 0.000010
+lbm.ic_type = "thermaldiffusivity_test"
+ic_thermaldiffusivity_test.density = 1.0
+ic_thermaldiffusivity_test.mach_components = 0.0 0.0 0.0
+ic_thermaldiffusivity_test.wave_length = 24.0
+ic_thermaldiffusivity_test.initial_temperature = 0.003333
+ic_thermaldiffusivity_test.adiabatic_exponent = 1.32
+ic_thermaldiffusivity_test.mean_molecular_mass = 17.031
+lbm.initial_temperature = 0.003333
+lbm.adiabatic_exponent = 1.32
+lbm.mean_molecular_mass = 17.031
+eb2.geom_type = "all_regular"
+""", [0, 1, 20]),
+    # pine_box boundary set on a clean geometry: constant-velocity inlet (z-lo), pressure outlet
+    # (z-hi), four no-slip walls, EB sphere; needs the K6 pre-pass at the outlet corners
+    "pressure": ("""
+max_step = 6
+geometry.prob_lo = 0.0 0.0 0.0
+geometry.prob_hi = 10.0 10.0 14.0
+geometry.is_periodic = 0 0 0
+amr.n_cell = 10 10 14
+lbm.bc_lo = 1 1 2
+lbm.bc_hi = 1 1 3
+lbm.nu = 0.01733333333333333
+lbm.velocity_bc_type = "constant"
+velocity_bc_constant.dir = 2
+velocity_bc_constant.Mach_ref = 0.01
+lbm.ic_type = "constant"
+ic_constant.density = 1.0
+ic_constant.mach_components = 0.0 0.0 0.002
+eb2.geom_type = "sphere"
+eb2.sphere_radius = 2.2
+eb2.sphere_center = 5.0 5.0 6.0
+eb2.sphere_has_fluid_inside = 0
+""", [0, 1, 6]),
+    # single_rotated_box boundary set: slip walls (x), parabolic inlet (y-lo) with prob_lo != 0,
+    # outflow (y-hi), periodic z, EB box
+    "slip": ("""
+max_step = 6
+geometry.prob_lo = -8.0 0.0 -2.0
+geometry.prob_hi = 8.0 24.0 2.0
+geometry.is_periodic = 0 0 1
+amr.n_cell = 16 24 4
+lbm.bc_lo = 6 2 0
+lbm.bc_hi = 6 5 0
+lbm.nu = 0.20
+lbm.velocity_bc_type = "parabolic"
+velocity_bc_parabolic.Mach_ref = 0.0025
+velocity_bc_parabolic.normal_dir = 0
+velocity_bc_parabolic.tangential_dir = 1
+lbm.ic_type = "constant"
+ic_constant.density = 1.0
+ic_constant.mach_components = 0.0 0.0 0.0
+eb2.geom_type = "box"
+eb2.box_lo = -2.5 8.5 -1000.0
+eb2.box_hi = 2.5 13.5 1000.0
+eb2.box_has_fluid_inside = 0
+""", [0, 1, 6]),
+    # viscosity-test shear wave (all periodic, non-default IC kind 2)
+    "shear": ("""
+max_step = 12
+geometry.prob_lo = 0.0 0.0 -1.0
+geometry.prob_hi = 4.0 20.0 1.0
+geometry.is_periodic = 1 1 1
+amr.n_cell = 4 20 2
+lbm.bc_lo = 0 0 0
+lbm.bc_hi = 0 0 0
+lbm.nu = 0.0001
+lbm.ic_type = "viscosity_test"
+ic_viscosity_test.density = 1.0
+ic_viscosity_test.mach_components = 0.0 0.0 0.0
+ic_viscosity_test.wave_length = 20.0
+ic_viscosity_test.initial_temperature = 0.03333
+lbm.initial_temperature = 0.03333
+eb2.geom_type = "all_regular"
+""", [0, 1, 12]),
+}
+
+KEEP_STEP0 = ([f"f_{q:02d}" for q in range(27)] + [f"g_{q:02d}" for q in range(27)] + O.MACRO_NAMES)
+
+
+def main():
+    out_dir = os.path.dirname(os.path.abspath(__file__))
+    only = sys.argv[1:]
+    for name, (deck, steps) in CASES.items():
+        if only and name not in only:
+            continue
+        work = tempfile.mkdtemp(prefix=f"golden_{name}_")
+        deck_text = deck.strip() + "\n" + COMMON
+        deck_path = os.path.join(work, "case.inp")
+        with open(deck_path, "w") as fh:
+            fh.write(deck_text)
+        O.run_reference(deck_path, work, [], omp=False)
+        data = {"deck": np.array(deck_text), "steps": np.array(steps)}
+        for s in steps:
+            pf = O.read_plotfile(os.path.join(work, f"plt{s:05d}"))
+            names = pf["__names__"] if s == steps[-1] else KEEP_STEP0
+            for n in names:
+                data[f"s{s}_{n}"] = pf[n]
+            if s == steps[0]:
+                data["is_fluid"] = pf["is_fluid"].astype(np.int8)
+        path = os.path.join(out_dir, f"{name}.npz")
+        np.savez_compressed(path, **data)
+        print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB, solid cells {int((data['is_fluid'] == 0).sum())}")
+        shutil.rmtree(work)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,170 @@
+"""Parity of the CUDA path (through the C ABI) with the reference: golden vectors written by the
+unmodified reference executable, and the oracle on seeded inputs.  fp64, tolerance 1e-12 of the
+field scale per step (tests/parity.py)."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, load_golden
+from parity import compare, scales
+
+pytestmark = pytest.mark.gpu
+
+
+def golden_fields(z, s):
+    pre = f"s{s}_"
+    return {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
+
+
+def new_lbm(deck_text, is_fluid=None, overrides=None):
+    from marbles_b200.inputs import parse_deck
+    from marbles_b200.lbm import LBM
+    deck = parse_deck(text=deck_text, overrides=overrides)
+    lbm = LBM(deck, is_fluid=is_fluid)
+    lbm.init_data()
+    return lbm
+
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "unfused"])
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_cuda_vs_reference_golden(case, fused):
+    z, deck_text, steps = load_golden(case)
+    lbm = new_lbm(deck_text, z["is_fluid"].astype(np.int32))
+    inp = lbm.inp
+    done = 0
+    for s in steps:
+        if s == 0:
+            ref = golden_fields(z, 0)
+            sc = scales(ref, inp.R, inp.gamma, 1.0 / inp.dx[0])
+            mine = {"f": lbm.get_f(), "g": lbm.get_g()}
+            got = {f"f_{q:02d}": mine["f"][q] for q in range(27)}
+            got.update({f"g_{q:02d}": mine["g"][q] for q in range(27)})
+            compare(got, ref, sc, 1)
+            continue
+        if fused:
+            lbm.step(s - done, want_macrodata=True)
+        else:
+            lbm.evolve(s - done, fused=False)
+        done = s
+        ref = golden_fields(z, s)
+        sc = scales(ref, inp.R, inp.gamma, 1.0 / inp.dx[0])
+        got = lbm.fields()
+        d = lbm.get_derived()
+        got.update({"dQCorrX": d[4], "dQCorrY": d[5], "dQCorrZ": d[6]})
+        worst, key = compare(got, ref, sc, s)
+        print(f"{case} step {s}: worst {worst:.2e} ({key})")
+    lbm.close()
+
+
+def test_solid_sentinel_and_macrodata_zero():
+    z, deck_text, _ = load_golden("chcyl")
+    fl = z["is_fluid"].astype(np.int32)
+    lbm = new_lbm(deck_text, fl)
+    assert (lbm.get_f()[:, fl == 0] == 0.0).all()
+    lbm.step(1, want_macrodata=True)
+    assert (lbm.get_f()[:, fl == 0] == -1.0).all() and (lbm.get_g()[:, fl == 0] == -1.0).all()
+    assert (lbm.get_macrodata()[:, fl == 0] == 0.0).all()
+    lbm.close()
+
+
+def test_geometry_matches_reference_is_fluid():
+    """host-mirror EB flags (corner rule) against the reference's is_fluid for the shipped body types"""
+    from marbles_b200.geometry import is_fluid_from_deck
+    from marbles_b200.inputs import lbm_inputs, parse_deck
+    for case in ("chcyl", "pressure", "slip"):
+        z, deck_text, _ = load_golden(case)
+        deck = parse_deck(text=deck_text)
+        inp = lbm_inputs(deck)
+        a = is_fluid_from_deck(deck, inp.n_cell, inp.prob_lo, inp.dx, ng=3)[3:-3, 3:-3, 3:-3]
+        assert np.array_equal(a, z["is_fluid"].astype(np.int32)), case
+
+
+@pytest.mark.parametrize("case", ["chcyl", "pressure", "slip", "tg12"])
+def test_random_state_vs_oracle(oracle_mod, case):
+    """seeded random perturbation of f, g and a random solid mask, 3 steps, all boundary types"""
+    O = oracle_mod
+    z, deck_text, _ = load_golden(case)
+    rng = np.random.default_rng(1234)
+    fl = z["is_fluid"].astype(np.int32).copy()
+    nzv, nyv, nxv = fl.shape
+    # sprinkle solid cells in the interior (away from the non-periodic faces)
+    mask = rng.random(fl.shape) < 0.03
+    mask[:2], mask[-2:], mask[:, :2], mask[:, -2:], mask[:, :, :2], mask[:, :, -2:] = (False,) * 6
+    fl[mask] = 0
+    o = O.Oracle(O.lbm_setup(O.parse_deck(None, deck_text.splitlines())), is_fluid=fl)
+    o.initialize()
+    noise = lambda a: a * (1.0 + 0.05 * rng.standard_normal(a.shape))
+    o.f[:] = np.where(o.f > 0, noise(o.f), o.f)
+    o.g[:] = np.where(o.g > 0, noise(o.g), o.g)
+    lbm = new_lbm(deck_text, fl)
+    lbm.set_state(o.f, o.g, ng=3)
+    nsteps = 3
+    o.step(nsteps)
+    lbm.step(nsteps, want_macrodata=True)
+    ref = o.fields()
+    sc = scales(ref, lbm.inp.R, lbm.inp.gamma, 1.0 / lbm.inp.dx[0])
+    got = lbm.fields()
+    worst, key = compare(got, ref, sc, nsteps)
+    print(f"{case}: worst {worst:.2e} ({key})")
+    lbm.close()
+
+
+def test_eb_forces_and_vorticity_vs_oracle(oracle_mod):
+    O = oracle_mod
+    z, deck_text, _ = load_golden("chcyl")
+    fl = z["is_fluid"].astype(np.int32)
+    o = O.Oracle(O.lbm_setup(O.parse_deck(None, deck_text.splitlines())), is_fluid=fl)
+    o.initialize()
+    lbm = new_lbm(deck_text, fl)
+    o.step(4)
+    lbm.step(4, want_macrodata=True)
+    lbm.compute_derived()
+    fo, fm = o.eb_forces(), lbm.compute_eb_forces()
+    assert np.abs(fo - fm).max() <= 1e-11 * max(np.abs(fo).max(), 1.0), (fo, fm)
+    d = lbm.get_derived()
+    cs = np.sqrt(lbm.inp.gamma * lbm.inp.R * 0.03)
+    for n in range(4):
+        assert np.abs(d[n] - o.derived[n]).max() <= 4e-12 * cs
+    lbm.close()
+
+
+def test_tg64_vs_oracle_and_conservation(oracle_mod):
+    """BASELINE config 1 (TG 64^3): 3 steps against the oracle, then size-independent properties"""
+    O = oracle_mod
+    z, deck_text, _ = load_golden("tg12")
+    ov = ["amr.n_cell = 64 64 64"]
+    o = O.Oracle(O.lbm_setup(O.parse_deck(None, deck_text.splitlines() + ov)))
+    o.initialize()
+    lbm = new_lbm(deck_text, overrides=ov)
+    m0, e0 = lbm.get_f().sum(), lbm.get_g().sum()
+    o.step(3)
+    lbm.step(3, want_macrodata=True)
+    ref = o.fields()
+    sc = scales(ref, 1.0, 5.0 / 3.0, 32.0)
+    worst, key = compare(lbm.fields(), ref, sc, 3)
+    print(f"tg64: worst {worst:.2e} ({key})")
+    lbm.step(20)
+    f, g = lbm.get_f(), lbm.get_g()
+    assert abs(f.sum() - m0) <= 1e-11 * m0 and abs(g.sum() - e0) <= 1e-11 * e0
+    # TG symmetry: w == 0 initially and the flow is mirror-symmetric in z -> sum of e_z f vanishes
+    from oracle.oracle import stencil
+    ev = stencil()[0]
+    jz = np.tensordot(ev[:, 2].astype(float), f, axes=1)
+    assert abs(jz.sum()) <= 1e-10 * m0
+    lbm.close()
+
+
+def test_full_size_conservation_256():
+    """periodic 256^3 (largest size the test box does in seconds): mass/energy conservation of
+    stream+collide and agreement of the fused and un-fused operator sequences"""
+    _, deck_text, _ = load_golden("tg12")
+    ov = ["amr.n_cell = 256 256 256"]
+    a = new_lbm(deck_text, overrides=ov)
+    import ctypes as C
+    s0 = a.get_f(0).sum(dtype=np.float64), a.get_g(0).sum(dtype=np.float64)
+    a.step(10)
+    f = a.get_f(0)
+    assert abs(f.sum(dtype=np.float64) - s0[0]) <= 1e-11 * s0[0]
+    assert np.isfinite(f).all() and f.min() > 0
+    g = a.get_g(0)
+    assert abs(g.sum(dtype=np.float64) - s0[1]) <= 1e-11 * s0[1]
+    a.close()

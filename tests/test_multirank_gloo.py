@@ -1,0 +1,113 @@
+"""N > 1 host logic on CPU: world_size 2 over gloo.
+
+What is under test is the product's slab decomposition and ghost-plane exchange schedule
+(marbles_b200.lbm.slab_bounds, marbles_b200.parallel.neighbours / exchange_buffers: posting order,
+periodic ring with lower == upper, non-periodic ends) and the step scheme it relies on -- ONE exchange
+of the two outermost planes per step, then a purely local step in which the q-correction of the
+first ghost plane is recomputed instead of exchanged.  The per-rank arithmetic is done by the CPU
+oracle (the checker), the assembled result must equal the single-box oracle run."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, load_golden
+
+GZ = 2  # ghost planes the product exchanges (marbles_b200/csrc/lattice.cuh)
+
+
+def _worker(rank, world, case, nsteps, initfile, outdir, nz_override):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ctypes as C
+
+    from marbles_b200.lbm import slab_bounds
+    from marbles_b200.parallel import exchange_buffers, neighbours
+    from oracle import oracle as O
+
+    dist.init_process_group("gloo", init_method=f"file://{initfile}", rank=rank, world_size=world)
+    z, deck_text, _ = load_golden(case)
+    lines = deck_text.splitlines()
+    deck = O.parse_deck(None, lines)
+    n = [int(v) for v in deck["amr.n_cell"]]
+    if nz_override:
+        n[2] = nz_override
+        deck = O.parse_deck(None, lines + [f"amr.n_cell = {n[0]} {n[1]} {n[2]}"])
+    zlo, zhi = slab_bounds(n[2], rank, world)
+    s = O.lbm_setup(deck, lo=(0, 0, zlo), hi=(n[0] - 1, n[1] - 1, zhi))
+    periodic_z = bool(s.params.periodic[2])
+    lower, upper = neighbours(rank, world, periodic_z)
+    o = O.Oracle(s)  # all-fluid geometry in these cases (is_fluid of a slab needs the caller's geometry)
+    L, p = O.lib(), C.byref(o.p)
+    ng = o.ng
+    nzl = zhi - zlo + 1
+
+    def exchange():
+        for a in (o.f, o.g):
+            send_lo = torch.from_numpy(np.ascontiguousarray(a[:, ng:ng + GZ]))
+            send_hi = torch.from_numpy(np.ascontiguousarray(a[:, ng + nzl - GZ:ng + nzl]))
+            recv_lo, recv_hi = torch.empty_like(send_lo), torch.empty_like(send_hi)
+            exchange_buffers(send_lo, send_hi, recv_lo, recv_hi, lower, upper)
+            if lower is not None:
+                a[:, ng - GZ:ng] = recv_lo.numpy()
+            if upper is not None:
+                a[:, ng + nzl:ng + nzl + GZ] = recv_hi.numpy()
+
+    # initial state: IC on the grown box (position-dependent, no communication needed)
+    L.orc_initialize(p, C.byref(s.ic), O._ptr(o.is_fluid, C.c_int), O._ptr(o.f), O._ptr(o.g))
+    for _ in range(nsteps):
+        exchange()
+        for a, en in ((o.f, 0), (o.g, 1)):
+            L.orc_prepass(p, O._ptr(a))
+            L.orc_fill_periodic(p, O._ptr(a), 27, ng)
+        exchange()  # whole padded planes: carries the neighbours' x/y periodic images too
+        for a, en in ((o.f, 0), (o.g, 1)):
+            L.orc_physbc(p, O._ptr(a), en, C.c_double(0.0))
+        L.orc_stream(p, O._ptr(o.is_fluid, C.c_int), O._ptr(o.f), 0)
+        L.orc_stream(p, O._ptr(o.is_fluid, C.c_int), O._ptr(o.g), 0)
+        L.orc_collide(p, O._ptr(o.is_fluid, C.c_int), O._ptr(o.f), O._ptr(o.g), O._ptr(o.macro),
+                      O._ptr(o.derived), O._ptr(o.eq), O._ptr(o.eq_g), 0)
+    np.savez(os.path.join(outdir, f"rank{rank}.npz"), f=o.f_valid, g=o.g_valid, zlo=zlo, zhi=zhi)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case,nz,world", [("tg12", 12, 2), ("tg12", 13, 2), ("sod48", 8, 2), ("thermal", 6, 3)])
+def test_slab_decomposition_matches_single_box(oracle_mod, case, nz, world):
+    O = oracle_mod
+    nsteps = 3
+    with tempfile.TemporaryDirectory() as tmp:
+        initfile = os.path.join(tmp, "init")
+        mp.spawn(_worker, args=(world, case, nsteps, initfile, tmp, nz), nprocs=world, join=True)
+        parts = [np.load(os.path.join(tmp, f"rank{r}.npz")) for r in range(world)]
+    _, deck_text, _ = load_golden(case)
+    deck = O.parse_deck(None, deck_text.splitlines())
+    n = [int(v) for v in deck["amr.n_cell"]]
+    deck = O.parse_deck(None, deck_text.splitlines() + [f"amr.n_cell = {n[0]} {n[1]} {nz}"])
+    o = O.Oracle(O.lbm_setup(deck))
+    o.initialize()
+    o.step(nsteps)
+    f = np.concatenate([p["f"] for p in parts], axis=1)
+    g = np.concatenate([p["g"] for p in parts], axis=1)
+    assert f.shape == o.f_valid.shape
+    assert [int(p["zlo"]) for p in parts] == sorted(int(p["zlo"]) for p in parts)
+    assert np.array_equal(f, o.f_valid), float(np.abs(f - o.f_valid).max())
+    assert np.array_equal(g, o.g_valid), float(np.abs(g - o.g_valid).max())
+
+
+def test_slab_bounds_and_neighbours():
+    from marbles_b200.lbm import slab_bounds
+    from marbles_b200.parallel import neighbours
+    for nz, world in ((512, 8), (13, 2), (7, 3), (4096, 8)):
+        b = [slab_bounds(nz, r, world) for r in range(world)]
+        assert b[0][0] == 0 and b[-1][1] == nz - 1
+        assert all(b[r + 1][0] == b[r][1] + 1 for r in range(world - 1))
+        sizes = [hi - lo + 1 for lo, hi in b]
+        assert max(sizes) - min(sizes) <= 1
+    assert neighbours(0, 2, True) == (1, 1)
+    assert neighbours(0, 4, False) == (None, 1) and neighbours(3, 4, False) == (2, None)
+    assert neighbours(0, 1, True) == (0, 0)
