@@ -2,10 +2,12 @@
 
 What is under test is the product's slab decomposition and ghost-plane exchange schedule
 (marbles_b200.lbm.slab_bounds, marbles_b200.parallel.neighbours / exchange_buffers: posting order,
-periodic ring with lower == upper, non-periodic ends) and the step scheme it relies on -- ONE exchange
-of the two outermost planes per step, then a purely local step in which the q-correction of the
-first ghost plane is recomputed instead of exchanged.  The per-rank arithmetic is done by the CPU
-oracle (the checker), the assembled result must equal the single-box oracle run."""
+periodic ring with lower == upper, non-periodic ends).  The per-rank arithmetic is done by the CPU
+oracle (the checker) in the reference's own order -- ghost planes are swapped wherever the reference
+calls FillBoundary (fillpatch, end of stream) -- and the assembled result must be bit-identical to the
+single-box oracle run.  The product's own scheme (ONE exchange of two planes per step, q-correction
+of the first ghost plane recomputed locally) has no CPU path; it is covered on the GPU by
+tests/test_gpu_parity.py::test_two_slabs_match_single_box."""
 import os
 import sys
 import tempfile
@@ -68,8 +70,9 @@ def _worker(rank, world, case, nsteps, initfile, outdir, nz_override):
         exchange()  # whole padded planes: carries the neighbours' x/y periodic images too
         for a, en in ((o.f, 0), (o.g, 1)):
             L.orc_physbc(p, O._ptr(a), en, C.c_double(0.0))
-        L.orc_stream(p, O._ptr(o.is_fluid, C.c_int), O._ptr(o.f), 0)
-        L.orc_stream(p, O._ptr(o.is_fluid, C.c_int), O._ptr(o.g), 0)
+        L.orc_stream(p, O._ptr(o.is_fluid, C.c_int), O._ptr(o.f), 1)
+        L.orc_stream(p, O._ptr(o.is_fluid, C.c_int), O._ptr(o.g), 1)
+        exchange()  # the cross-rank part of the FillBoundary that ends LBM::stream (LBM.cpp:603)
         L.orc_collide(p, O._ptr(o.is_fluid, C.c_int), O._ptr(o.f), O._ptr(o.g), O._ptr(o.macro),
                       O._ptr(o.derived), O._ptr(o.eq), O._ptr(o.eq_g), 0)
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), f=o.f_valid, g=o.g_valid, zlo=zlo, zhi=zhi)
