@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--variant", type=int, default=1, help="1 fused persistent TMA kernel, 2 same as two launches, 0 two plain kernels")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -221,7 +222,7 @@ def main():
     deck = parse_deck(text=TG_DECK.format(nx=n, ny=n, nz=n * world, mgs=n))
     comm = HaloComm(rank, world, True, dev) if world > 1 else None
     stream = torch.cuda.current_stream().cuda_stream
-    lbm = LBM(deck, device=local, rank=rank, world=world, comm=comm, cuda_stream=stream)
+    lbm = LBM(deck, device=local, rank=rank, world=world, comm=comm, cuda_stream=stream, variant=args.variant)
     lbm.init_data()
     cells_total = lbm.ncells * world
 
@@ -268,6 +269,9 @@ def main():
     # ---- roofline of the dominant kernel (collide pass) -----------------------------
     peak, peak_src = measured_peak_gbs()
     collide_ms = kms[2] / max(nrec.value, 1)
+    kname = {0: "k_collide<pull>", 1: "k_fused (q-correction + collide jobs)", 2: "k_fused (collide jobs)"}[args.variant]
+    vname = {0: "two plain kernels (q-correction, collide)", 1: "one persistent TMA-pipelined kernel per step",
+             2: "persistent TMA kernel, two launches (q-correction, collide)"}[args.variant]
     achieved = BYTES_PER_CELL * lbm.ncells / (collide_ms * 1e-3) / 1e9
     traffic = None
     try:
@@ -276,7 +280,7 @@ def main():
     except Exception:
         pass
     roofline = {
-        "bound": "hbm", "kernel": "k_collide<pull>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "bytes_per_cell": BYTES_PER_CELL, "cells_per_launch": lbm.ncells,
         "kernel_ms": {"ghost_fill": kms[0] / max(nrec.value, 1), "qcorr": kms[1] / max(nrec.value, 1),
@@ -347,7 +351,7 @@ def main():
             "config": {"workload": f"periodic Taylor-Green box {n}^3 per GPU, single level, D3Q27 f+g fp64 "
                                    f"(BASELINE config 3; domain {n}x{n}x{n * world})",
                        "decomposition": f"{world} z-slab(s)", "l2": "state (58 GB per GPU at 512^3) is far larger than L2",
-                       "variant": "two-pass (q-correction, collide)"},
+                       "variant": vname},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -185,8 +185,9 @@ int64_t mbl_launch_count(mbl_ctx* ctx);
  * *nsteps steps recorded since the last call (bench.py roofline) */
 int mbl_set_timing(mbl_ctx* ctx, int on);
 int mbl_get_timing(mbl_ctx* ctx, double ms[3], int* nsteps);
-/* select the collide implementation: 0 = two-pass (moments, then collide),
- * 1 = fused z-marching kernel (when available) */
+/* select the implementation of mbl_step: 1 (default) = ONE persistent kernel per level (bulk-TMA staged
+ * pulls; q-correction jobs and collide jobs interleaved so the second touch of a population is an L2
+ * hit); 2 = the same job types as two launches; 0 = two plain kernels (k_qcorr, k_collide) */
 int mbl_set_variant(mbl_ctx* ctx, int variant);
 
 #ifdef __cplusplus

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmarbles_b200.so")
-SOURCES = ["kernels.cu", "api.cu"]
+SOURCES = ["kernels.cu", "fused.cu", "api.cu"]
 HEADERS = ["lattice.cuh", "kernels.cuh", os.path.join("..", "..", "include", "marbles_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -49,11 +50,13 @@ struct Level {
     LevelPtrs p;
     int cur = 0;  // index of the current lattice buffers
     bool local_z = true;
+    bool images_valid = false;  // ghost cells that are periodic images of valid cells are current
     double* stage = nullptr;  // one-component staging for FAB transfers
     size_t stage_bytes = 0;
     int32_t* flag_stage = nullptr;
     double* d_red = nullptr;  // 3 doubles for reductions
     double* macro = nullptr;  // lazily allocated (26 comps)
+    int* counters = nullptr;  // fused kernel: ticket + per-slab completion counters
 };
 
 }  // namespace
@@ -64,7 +67,10 @@ struct mbl_ctx {
     cudaStream_t stream = nullptr;
     Level lev[MAX_LEVELS];
     int64_t launches = 0;
-    int variant = 0;
+    int variant = 1;   // 0: two kernels (k_qcorr, k_collide); 1: fused persistent TMA kernel; 2: its two job
+                       // types as two launches
+    int uw = 128, band_rows = 16, lag_per_cta = 3;  // fused kernel tuning (MBL_UW / MBL_BAND / MBL_LAG)
+    int sm_count = 148;
     bool timing = false;
     std::vector<cudaEvent_t> events;  // 4 per timed step: before ghost fill, q-corr, collide, after
 };
@@ -139,12 +145,28 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
         ctx->events.push_back(e);
     };
     mark();
-    ctx->launches += launch_ghost_fill(lv.L, lv.B, lv.p.f[a], lv.p.g[a], lv.local_z, true, true, st);
+    // the periodic images are kept current by the stores of the previous step; only a state that
+    // came from outside (upload, initialize) needs the copy kernels
+    ctx->launches += launch_ghost_fill(lv.L, lv.B, lv.p.f[a], lv.p.g[a], lv.local_z, true, !lv.images_valid, st);
+    lv.images_valid = true;
     mark();
-    ctx->launches += launch_qcorr(lv.L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st);
-    mark();
-    ctx->launches += launch_collide(lv.L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
-                                    lv.p.qc, want_macro ? lv.macro : nullptr, true, st);
+    double* macro = want_macro ? lv.macro : nullptr;
+    if (ctx->variant == 0) {
+        ctx->launches += launch_qcorr(lv.L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st);
+        mark();
+        ctx->launches += launch_collide(lv.L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
+                                        lv.p.qc, macro, true, st);
+    } else if (ctx->variant == 2) {
+        ctx->launches += launch_fused(lv.L, lv.P, ctx->uw, ctx->band_rows, ctx->lag_per_cta, 0, ctx->sm_count, lv.p.f[a],
+                                      lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, macro, lv.counters, st);
+        mark();
+        ctx->launches += launch_fused(lv.L, lv.P, ctx->uw, ctx->band_rows, ctx->lag_per_cta, 1, ctx->sm_count, lv.p.f[a],
+                                      lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, macro, lv.counters, st);
+    } else {
+        mark();  // no separate q-correction pass
+        ctx->launches += launch_fused(lv.L, lv.P, ctx->uw, ctx->band_rows, ctx->lag_per_cta, 2, ctx->sm_count, lv.p.f[a],
+                                      lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, macro, lv.counters, st);
+    }
     mark();
     lv.cur = b;
     CU(cudaGetLastError());
@@ -177,6 +199,11 @@ int mbl_create(const mbl_params* params, int device, mbl_ctx** out)
     mbl_ctx* c = new mbl_ctx();
     c->prm = *params;
     c->device = device;
+    CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (const char* e = getenv("MBL_VARIANT")) c->variant = atoi(e);
+    if (const char* e = getenv("MBL_UW")) c->uw = atoi(e) == 256 ? 256 : 128;
+    if (const char* e = getenv("MBL_BAND")) c->band_rows = atoi(e) > 0 ? atoi(e) : 16;
+    if (const char* e = getenv("MBL_LAG")) c->lag_per_cta = atoi(e) > 0 ? atoi(e) : 3;
     init_tables();
     CU(cudaGetLastError());
     *out = c;
@@ -232,6 +259,7 @@ int mbl_level_clear(mbl_ctx* ctx, int lev)
     if (lv.flag_stage) cudaFree(lv.flag_stage);
     if (lv.d_red) cudaFree(lv.d_red);
     if (lv.macro) cudaFree(lv.macro);
+    if (lv.counters) cudaFree(lv.counters);
     lv = Level();
     return 0;
 }
@@ -252,6 +280,9 @@ int mbl_level_define(mbl_ctx* ctx, int lev, const mbl_level_geom* g, void* devic
     lv.geom = *g;
     lv.L = layout_of(g);
     lv.local_z = (g->lo[2] == g->dom_lo[2] && g->hi[2] == g->dom_hi[2]);
+    lv.L.img[0] = ctx->prm.periodic[0];
+    lv.L.img[1] = ctx->prm.periodic[1];
+    lv.L.img[2] = ctx->prm.periodic[2] && lv.local_z;
     if (!lv.local_z && lv.L.nz < GZ) return fail("a z-slab needs at least %d planes", GZ);
     const mbl_params& pr = ctx->prm;
     lv.P.nu = pr.nu;
@@ -296,6 +327,7 @@ int mbl_level_define(mbl_ctx* ctx, int lev, const mbl_level_geom* g, void* devic
     lv.p.flag = (uint8_t*)(lv.base + m.flag);
     lv.cur = 0;
     CU(cudaMalloc(&lv.d_red, 8 * sizeof(double)));
+    CU(cudaMalloc(&lv.counters, fused_counter_ints(lv.L) * sizeof(int)));
     // zero everything once: pad cells are never written by the kernels
     CU(cudaMemsetAsync(lv.base, 0, m.total, ctx->stream));
     lv.defined = true;
@@ -350,6 +382,7 @@ int mbl_upload(mbl_ctx* ctx, int lev, int which, const double* fab, int ng)
     const size_t n = (size_t)(lv.L.nx + 2 * ng) * (lv.L.ny + 2 * ng) * (lv.L.nz + 2 * ng);
     if (ensure_stage(lv, n * sizeof(double))) return 1;
     double* dst = which == MBL_G ? curg(lv) : curf(lv);
+    lv.images_valid = false;
     for (int q = 0; q < NQ; ++q) {
         CU(cudaMemcpyAsync(lv.stage, fab + (size_t)q * n, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         ctx->launches += launch_fab_to_soa(lv.L, lv.stage, ng, dst + (size_t)q * lv.L.sq, 1, ctx->stream);
@@ -426,6 +459,7 @@ int mbl_initialize(mbl_ctx* ctx, int lev, int ic_kind, const double* v, int nv)
     I.wave_length = v[8];
     I.T0 = v[9], I.gamma = v[10], I.R = v[11], I.c_s = v[12];
     I.density_ratio = v[13], I.temperature_ratio = v[14], I.x_disc = v[15];
+    lv.images_valid = false;
     ctx->launches += launch_initialize(lv.L, lv.B, I, lv.p.flag, curf(lv), curg(lv), ctx->stream);
     CU(cudaGetLastError());
     return 0;
@@ -436,7 +470,8 @@ int mbl_fillpatch(mbl_ctx* ctx, int lev, double /*time*/)
     if (check_level(ctx, lev)) return 1;
     Level& lv = ctx->lev[lev];
     CU(cudaSetDevice(ctx->device));
-    ctx->launches += launch_ghost_fill(lv.L, lv.B, curf(lv), curg(lv), lv.local_z, true, true, ctx->stream);
+    ctx->launches += launch_ghost_fill(lv.L, lv.B, curf(lv), curg(lv), lv.local_z, true, !lv.images_valid, ctx->stream);
+    lv.images_valid = true;
     CU(cudaGetLastError());
     return 0;
 }
@@ -507,7 +542,8 @@ int mbl_eb_forces(mbl_ctx* ctx, int lev, double out[3])
     CU(cudaSetDevice(ctx->device));
     // the reference reads f in ghost cells that FillBoundary refreshed after the collision
     // (LBM.cpp:805); refresh the periodic images here
-    ctx->launches += launch_ghost_fill(lv.L, lv.B, curf(lv), curg(lv), lv.local_z, false, true, ctx->stream);
+    ctx->launches += launch_ghost_fill(lv.L, lv.B, curf(lv), curg(lv), lv.local_z, false, !lv.images_valid, ctx->stream);
+    lv.images_valid = true;
     ctx->launches += launch_eb_forces(lv.L, curf(lv), lv.p.flag, lv.d_red, ctx->stream);
     CU(cudaMemcpyAsync(out, lv.d_red, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -598,7 +634,7 @@ int mbl_get_timing(mbl_ctx* ctx, double ms[3], int* nsteps)
 int mbl_set_variant(mbl_ctx* ctx, int variant)
 {
     if (!ctx) return fail("null context");
-    if (variant != 0) return fail("variant %d is not available", variant);
+    if (variant < 0 || variant > 2) return fail("variant %d is not available", variant);
     ctx->variant = variant;
     return 0;
 }

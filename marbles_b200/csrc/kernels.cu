@@ -111,11 +111,13 @@ __global__ void __launch_bounds__(128) k_collide(const double* __restrict__ fin,
     if (!(m & 1u)) {
         // solid cell: the streamed value is the -1 sentinel (LBM.cpp:565, 582); collide skips it
         if constexpr (PULL) {
+            for_cell_and_images(L, i, j, k, [&](long long d) {
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                fout[q * n + c] = -1.0;
-                gout[q * n + c] = -1.0;
-            }
+                for (int q = 0; q < NQ; ++q) {
+                    fout[q * n + c + d] = -1.0;
+                    gout[q * n + c + d] = -1.0;
+                }
+            });
         }
         return;
     }
@@ -195,14 +197,24 @@ __global__ void __launch_bounds__(128) k_collide(const double* __restrict__ fin,
     }
 
     const Coll cc = collision_coefficients(s, mf, mg, dqx, dqy, dqz, P);
-    // relax_f_to_equilibrium (LBM.cpp:799-801)
+    // relax_f_to_equilibrium (LBM.cpp:799-801) + the FillBoundary of f, g that follows it (LBM.cpp:805-806)
     static_for<0, NQ>([&](auto qc_) {
         constexpr int Q = decltype(qc_)::value;
-        fout[(long long)Q * n + c] = f[Q] + cc.omega * (feq_q<Q>(cc) - f[Q]);
+        f[Q] += cc.omega * (feq_q<Q>(cc) - f[Q]);
     });
     static_for<0, NQ>([&](auto qc_) {
         constexpr int Q = decltype(qc_)::value;
-        gout[(long long)Q * n + c] = g[Q] + cc.omega * (geq_q<Q>(cc) - g[Q]);
+        g[Q] += cc.omega * (geq_q<Q>(cc) - g[Q]);
+    });
+    for_cell_and_images(L, i, j, k, [&](long long d) {
+        static_for<0, NQ>([&](auto qc_) {
+            constexpr int Q = decltype(qc_)::value;
+            fout[(long long)Q * n + c + d] = f[Q];
+        });
+        static_for<0, NQ>([&](auto qc_) {
+            constexpr int Q = decltype(qc_)::value;
+            gout[(long long)Q * n + c + d] = g[Q];
+        });
     });
 }
 
@@ -220,16 +232,21 @@ __global__ void __launch_bounds__(128) k_stream(const double* __restrict__ fin, 
     const long long c = L.cell(i, j, k);
     const long long n = L.sq;
     const uint32_t m = nbr[c];
-    if (!(m & 1u)) {
+    // the stores also refresh the cell's periodic images: the FillBoundary that ends LBM::stream (LBM.cpp:603)
+    for_cell_and_images(L, i, j, k, [&](long long d) {
+        if (!(m & 1u)) {
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            fout[q * n + c] = -1.0;
-            gout[q * n + c] = -1.0;
+            for (int q = 0; q < NQ; ++q) {
+                fout[q * n + c + d] = -1.0;
+                gout[q * n + c + d] = -1.0;
+            }
+        } else {
+            gather27<true, false>(fin, c, m, L,
+                                  [&](auto qc_, double v) { fout[(long long)decltype(qc_)::value * n + c + d] = v; });
+            gather27<true, false>(gin, c, m, L,
+                                  [&](auto qc_, double v) { gout[(long long)decltype(qc_)::value * n + c + d] = v; });
         }
-        return;
-    }
-    gather27<true, false>(fin, c, m, L, [&](auto qc_, double v) { fout[(long long)decltype(qc_)::value * n + c] = v; });
-    gather27<true, false>(gin, c, m, L, [&](auto qc_, double v) { gout[(long long)decltype(qc_)::value * n + c] = v; });
+    });
 }
 
 // f_to_macrodata on the current (already streamed) state, valid cells (LBM.cpp:810-906)

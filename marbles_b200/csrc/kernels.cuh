@@ -63,6 +63,23 @@ int launch_derived(const Layout& L, const Phys& P, const uint8_t* flag, const do
                    cudaStream_t st);
 int launch_eb_forces(const Layout& L, const double* f, const uint8_t* flag, double* d_out3, cudaStream_t st);
 
+// fused.cu: persistent TMA-pipelined kernel.  mode 0: q-correction jobs only (pass 1), 1: collide jobs only
+// (pass 2), 2: both interleaved in one launch (the second touch of every population is an L2 hit).
+struct FusedPlan {
+    int B, NB;       // band height (rows), number of bands
+    int kq0, NK;     // first plane with q-correction jobs, number of planes
+    int UPR, JPS;    // units per row, job indices per slab = (B + 1) * UPR
+    long long NJ;    // job indices per type
+    long long LAG;   // collide job n runs after q-correction job n + LAG was handed out
+    long long total_tickets;
+    int mode;
+};
+FusedPlan make_fused_plan(const Layout& L, int uw, int band_rows, int mode, int grid, int lag_per_cta);
+size_t fused_counter_ints(const Layout& L);
+int launch_fused(const Layout& L, const Phys& P, int uw, int band_rows, int lag_per_cta, int mode, int sm_count,
+                 const double* fin, const double* gin, double* fout, double* gout, const uint32_t* nbr,
+                 const uint8_t* flag, double* qc, double* macro, int* counters, cudaStream_t st);
+
 int launch_halo_pack(const Layout& L, const double* f, const double* g, int side, double* buf, cudaStream_t st);
 int launch_halo_unpack(const Layout& L, double* f, double* g, int side, const double* buf, cudaStream_t st);
 

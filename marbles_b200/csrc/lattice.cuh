@@ -70,6 +70,7 @@ struct Layout {
     int lo[3];        // global index of local cell (0,0,0)
     int dlo[3], dhi[3];  // level domain
     long long px, sz, sq; // row pitch, plane stride, component stride (doubles)
+    int img[3];       // direction is periodic AND the box spans it: stores keep the ghost images current
     __host__ __device__ long long cell(int i, int j, int k) const
     {
         return (long long)(i + OX) + (long long)(j + GY) * px + (long long)(k + GZ) * sz;
@@ -92,7 +93,29 @@ inline Layout make_layout(const int lo[3], const int hi[3], const int dlo[3], co
     L.px = ((long long)(L.nx + OX + GX) + 15) / 16 * 16;
     L.sz = L.px * (L.ny + 2 * GY);
     L.sq = L.sz * (L.nz + 2 * GZ);
+    L.img[0] = L.img[1] = L.img[2] = 0;
     return L;
+}
+
+// Periodic images of a valid cell inside the padded box.  The reference refreshes ghost cells with
+// FillBoundary after every stream and relax (LBM.cpp:603, 805-806); here the kernel that produces a
+// value also stores it to the cell's periodic images, so no separate ghost pass touches the state.
+// body(delta) is called for the cell itself (delta 0) and for each image (offset in doubles).
+template <typename F>
+__device__ __forceinline__ void for_cell_and_images(const Layout& L, int i, int j, int k, F&& body)
+{
+    const bool edge = (L.img[0] && (i < GX || i >= L.nx - GX)) || (L.img[1] && (j < GY || j >= L.ny - GY)) ||
+                      (L.img[2] && (k < GZ || k >= L.nz - GZ));
+    // 45 candidates (mx, my, mz) in {-1,0,1} x {-1,0,1} x {-2..2}; t = 22 is the cell itself
+    const int t0 = edge ? 0 : 22, t1 = edge ? 45 : 23;
+#pragma unroll 1
+    for (int t = t0; t < t1; ++t) {
+        const int mx = t % 3 - 1, my = (t / 3) % 3 - 1, mz = t / 9 - 2;
+        if ((mx != 0 && !L.img[0]) || (my != 0 && !L.img[1]) || (mz != 0 && !L.img[2])) continue;
+        const int ii = i + mx * L.nx, jj = j + my * L.ny, kk = k + mz * L.nz;
+        if (ii < -GX || ii > L.nx - 1 + GX || jj < -GY || jj > L.ny - 1 + GY || kk < -GZ || kk > L.nz - 1 + GZ) continue;
+        body((long long)mx * L.nx + (long long)my * L.ny * L.px + (long long)mz * L.nz * L.sz);
+    }
 }
 
 struct Phys {

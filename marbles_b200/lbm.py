@@ -53,7 +53,7 @@ class LBM:
 
     def __init__(self, deck=None, overrides=None, *, inputs: LbmInputs | None = None, device: int = 0,
                  rank: int = 0, world: int = 1, comm=None, is_fluid: np.ndarray | None = None,
-                 cuda_stream: int | None = None):
+                 cuda_stream: int | None = None, variant: int | None = None):
         if inputs is None:
             d = deck if isinstance(deck, dict) else parse_deck(deck, overrides)
             if isinstance(deck, dict) and overrides:
@@ -88,6 +88,8 @@ class LBM:
         check(self.lib.mbl_create(C.byref(p), device, C.byref(self.ctx)))
         if cuda_stream is not None:
             check(self.lib.mbl_set_stream(self.ctx, C.c_void_p(cuda_stream)))
+        if variant is not None:
+            check(self.lib.mbl_set_variant(self.ctx, variant))
 
         g = LevelGeom()
         dx = inputs.dx

@@ -76,3 +76,51 @@ class HaloComm:
         t = torch.as_tensor(a, dtype=torch.float64, device=self.device)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
+
+
+class LocalSlabs:
+    """All z-slabs of one domain held by ONE process on one device: the same pack / unpack / step_local
+    sequence as the multi-rank run, with device-to-device copies instead of NCCL.  Used by the GPU parity
+    tests to check the slab scheme (one exchange of GZ planes per step, q-correction of the first ghost
+    plane recomputed locally) against the single-box run without needing two GPUs."""
+
+    def __init__(self, make_lbm, world: int, periodic_z: bool, device: torch.device):
+        self.world, self.periodic_z, self.device = world, periodic_z, device
+        self.slabs = [make_lbm(rank, world) for rank in range(world)]
+        self.bufs = None
+
+    def exchange(self):
+        n = int(self.slabs[0].lib.mbl_halo_doubles(self.slabs[0].ctx, 0))
+        if self.bufs is None:
+            self.bufs = [[torch.empty(int(s.lib.mbl_halo_doubles(s.ctx, 0)), dtype=torch.float64, device=self.device)
+                          for _ in range(2)] for s in self.slabs]
+        for s, (lo, hi) in zip(self.slabs, self.bufs):
+            check(s.lib.mbl_halo_pack(s.ctx, 0, 0, C.c_void_p(lo.data_ptr())))
+            check(s.lib.mbl_halo_pack(s.ctx, 0, 1, C.c_void_p(hi.data_ptr())))
+            s.sync()
+        for r, s in enumerate(self.slabs):
+            lower, upper = neighbours(r, self.world, self.periodic_z)
+            if lower is not None:
+                check(s.lib.mbl_halo_unpack(s.ctx, 0, 0, C.c_void_p(self.bufs[lower][1].data_ptr())))
+            if upper is not None:
+                check(s.lib.mbl_halo_unpack(s.ctx, 0, 1, C.c_void_p(self.bufs[upper][0].data_ptr())))
+            s.sync()
+        del n
+
+    def step(self, nsteps: int = 1, want_macrodata: bool = False):
+        for it in range(nsteps):
+            self.exchange()
+            for s in self.slabs:
+                check(s.lib.mbl_step_local(s.ctx, 0, s.time, int(want_macrodata and it == nsteps - 1)))
+                s.time += s.dt
+                s.isteps += 1
+                s.sync()
+
+    def gather(self, getter):
+        """concatenate a per-slab FAB getter (e.g. LBM.get_f) along z"""
+        import numpy as np
+        return np.concatenate([getter(s) for s in self.slabs], axis=1)
+
+    def close(self):
+        for s in self.slabs:
+            s.close()

@@ -15,20 +15,22 @@ def golden_fields(z, s):
     return {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
 
 
-def new_lbm(deck_text, is_fluid=None, overrides=None):
+def new_lbm(deck_text, is_fluid=None, overrides=None, variant=None):
     from marbles_b200.inputs import parse_deck
     from marbles_b200.lbm import LBM
     deck = parse_deck(text=deck_text, overrides=overrides)
-    lbm = LBM(deck, is_fluid=is_fluid)
+    lbm = LBM(deck, is_fluid=is_fluid, variant=variant)
     lbm.init_data()
     return lbm
 
 
-@pytest.mark.parametrize("fused", [True, False], ids=["fused", "unfused"])
+# fused: mbl_step with the persistent TMA kernel (variant 1, the default), its two job types as two
+# launches (2), or the two plain kernels (0); unfused: the reference-granular operator sequence
+@pytest.mark.parametrize("fused", [1, 2, 0, None], ids=["fused-tma", "twopass-tma", "twopass-plain", "unfused"])
 @pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_cuda_vs_reference_golden(case, fused):
     z, deck_text, steps = load_golden(case)
-    lbm = new_lbm(deck_text, z["is_fluid"].astype(np.int32))
+    lbm = new_lbm(deck_text, z["is_fluid"].astype(np.int32), variant=fused)
     inp = lbm.inp
     done = 0
     for s in steps:
@@ -40,7 +42,7 @@ def test_cuda_vs_reference_golden(case, fused):
             got.update({f"g_{q:02d}": mine["g"][q] for q in range(27)})
             compare(got, ref, sc, 1)
             continue
-        if fused:
+        if fused is not None:
             lbm.step(s - done, want_macrodata=True)
         else:
             lbm.evolve(s - done, fused=False)
@@ -78,8 +80,9 @@ def test_geometry_matches_reference_is_fluid():
         assert np.array_equal(a, z["is_fluid"].astype(np.int32)), case
 
 
+@pytest.mark.parametrize("variant", [1, 0], ids=["fused-tma", "twopass-plain"])
 @pytest.mark.parametrize("case", ["chcyl", "pressure", "slip", "tg12"])
-def test_random_state_vs_oracle(oracle_mod, case):
+def test_random_state_vs_oracle(oracle_mod, case, variant):
     """seeded random perturbation of f, g and a random solid mask, 3 steps, all boundary types"""
     O = oracle_mod
     z, deck_text, _ = load_golden(case)
@@ -95,7 +98,7 @@ def test_random_state_vs_oracle(oracle_mod, case):
     noise = lambda a: a * (1.0 + 0.05 * rng.standard_normal(a.shape))
     o.f[:] = np.where(o.f > 0, noise(o.f), o.f)
     o.g[:] = np.where(o.g > 0, noise(o.g), o.g)
-    lbm = new_lbm(deck_text, fl)
+    lbm = new_lbm(deck_text, fl, variant=variant)
     lbm.set_state(o.f, o.g, ng=3)
     nsteps = 3
     o.step(nsteps)
@@ -168,3 +171,55 @@ def test_full_size_conservation_256():
     g = a.get_g(0)
     assert abs(g.sum(dtype=np.float64) - s0[1]) <= 1e-11 * s0[1]
     a.close()
+
+
+@pytest.mark.parametrize("case,nz,world", [("tg12", 12, 2), ("tg12", 13, 3), ("sod48", 8, 2), ("chcyl", None, 2),
+                                           ("pressure", None, 2)])
+def test_two_slabs_match_single_box(case, nz, world):
+    """the multi-rank scheme (z-slabs, ONE exchange of two ghost planes per step, q-correction of the first
+    ghost plane recomputed locally, BC ghosts of neighbour-owned planes) on one device: the assembled slabs
+    must reproduce the single-box run to round-off (different kernels launches, same arithmetic per cell:
+    the two are expected to be bit-identical)"""
+    import torch
+    from marbles_b200.inputs import lbm_inputs, parse_deck
+    from marbles_b200.lbm import LBM, slab_bounds
+    from marbles_b200.parallel import LocalSlabs
+    z, deck_text, _ = load_golden(case)
+    fl = z["is_fluid"].astype(np.int32)
+    ov = None
+    if nz is not None:
+        n = lbm_inputs(parse_deck(text=deck_text)).n_cell
+        ov = [f"amr.n_cell = {n[0]} {n[1]} {nz}"]
+        fl = None if fl.min() == 1 else fl
+        assert fl is None
+    deck = parse_deck(text=deck_text, overrides=ov)
+    single = LBM(deck, is_fluid=fl)
+    single.init_data()
+    nzt = single.n_local[2]
+
+    def make(rank, w):
+        lo, hi = slab_bounds(nzt, rank, w)
+        if fl is None:
+            sub = None
+        else:
+            # is_fluid of the slab grown by 3: interior neighbours from the full array, domain ends = fluid
+            ng = 3
+            full = np.ones((nzt + 2 * ng,) + tuple(d + 2 * ng for d in fl.shape[1:]), dtype=np.int32)
+            full[ng:-ng, ng:-ng, ng:-ng] = fl
+            full = single._wrap_periodic(full, ng, z_local=True)
+            sub = np.ascontiguousarray(full[lo:hi + 1 + 2 * ng])
+        s = LBM(deck, rank=rank, world=w, comm=None, is_fluid=sub)
+        s.init_data()
+        return s
+
+    slabs = LocalSlabs(make, world, bool(single.inp.periodic[2]), torch.device("cuda", 0))
+    nsteps = 4
+    single.step(nsteps, want_macrodata=True)
+    slabs.step(nsteps, want_macrodata=True)
+    for name, get in (("f", lambda s: s.get_f()), ("g", lambda s: s.get_g()), ("macro", lambda s: s.get_macrodata())):
+        a, b = get(single), slabs.gather(get)
+        assert a.shape == b.shape
+        err = float(np.abs(a - b).max())
+        assert err <= 1e-13 * max(float(np.abs(a).max()), 1.0), (case, name, err)
+    slabs.close()
+    single.close()
