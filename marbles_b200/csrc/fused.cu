@@ -61,9 +61,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// Every wait in this kernel is bounded: a protocol error must surface as a launch failure
+// (cudaErrorLaunchFailure from __trap), never as a hung GPU.
+constexpr long long SPIN_LIMIT_CYCLES = 4000000000LL;  // ~2 s
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > SPIN_LIMIT_CYCLES) {
+            printf("marbles_b200: k_fused barrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
     }
 }
 // 1-D bulk copy global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP)
@@ -114,7 +123,7 @@ struct Cfg {
     static constexpr int BAR_BYTES = 128;
     static constexpr int SMEM_BYTES = NSLOT * SLOT_BYTES + NAUX * AUX_BYTES + BAR_BYTES;
     static constexpr int NCW = UW / 32;  // consumer warps
-    static constexpr int THREADS = UW + 32;
+    static constexpr int THREADS = UW;
     static_assert(SLOT_BYTES % 16 == 0 && AUX_BYTES % 16 == 0 && NBR_BYTES % 16 == 0 && FLAG_BYTES % 16 == 0, "TMA alignment");
 };
 
@@ -170,6 +179,12 @@ __device__ __forceinline__ int slab_target(int b, const FusedPlan& F, const Layo
 
 }  // namespace
 
+// One thread (thread 0) also plays producer at two fixed points of every job: (A) when the f slot of the
+// current job has been drained it refills that slot with g of the next job, (B) at the end of the job it
+// draws the job after next (the ticket was requested one job earlier, so the atomic's latency is hidden),
+// checks its dependencies and issues its aux rows and f rows.  Loads therefore run one job ahead of the
+// arithmetic; a separate producer warp would leave the 4 SM sub-partitions unevenly loaded (5 warps per
+// CTA) and caps the kernel at 168 registers, which spills.
 template <int UW, bool MACRO>
 __global__ void __launch_bounds__(Cfg<UW>::THREADS, UW == 128 ? 2 : 1)
     k_fused(const double* __restrict__ fin, const double* __restrict__ gin, double* __restrict__ fout,
@@ -181,13 +196,13 @@ __global__ void __launch_bounds__(Cfg<UW>::THREADS, UW == 128 ? 2 : 1)
     unsigned char* pop_base = smem;
     unsigned char* aux_base = smem + C::NSLOT * C::SLOT_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(aux_base + C::NAUX * C::AUX_BYTES);
-    uint64_t* pop_full = bars;                  // [NSLOT]
-    uint64_t* pop_empty = bars + C::NSLOT;      // [NSLOT]
-    uint64_t* aux_full = bars + 2 * C::NSLOT;   // [NAUX]
-    uint64_t* aux_empty = aux_full + C::NAUX;   // [NAUX]
+    uint64_t* pop_full = bars;                 // [NSLOT]
+    uint64_t* pop_empty = bars + C::NSLOT;     // [NSLOT]
+    uint64_t* aux_full = bars + 2 * C::NSLOT;  // [NAUX]
+    uint64_t* aux_empty = aux_full + C::NAUX;  // [NAUX]
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < C::NSLOT; ++s) {
             mbar_init(pop_full + s, 1);
@@ -206,88 +221,151 @@ __global__ void __launch_bounds__(Cfg<UW>::THREADS, UW == 128 ? 2 : 1)
     int* done = counters + 1;
     const long long n = L.sq;
 
-    if (warp == C::NCW) {
-        // ------------------------------------------------------------------ producer warp
-        uint32_t ps = 0, pphase = 0, as = 0, aphase = 0;
-        // P1 reads are re-read by the P2 job a few hundred tickets later: keep them; P2 reads are the last use
-        const uint64_t pol_keep = policy_evict_last(), pol_last = policy_evict_first(), pol_norm = policy_normal();
-        for (;;) {
-            long long ticket = 0;
-            if (lane == 0) ticket = (long long)atomicAdd(tickets, 1);
-            ticket = __shfl_sync(0xffffffffu, ticket, 0);
-            const Job J = decode(ticket, F, L, UW);
-            if (J.type == JOB_EXIT) {
-                if (lane == 0) {
-                    mbar_wait(aux_empty + as, aphase ^ 1);
-                    reinterpret_cast<JobDesc*>(aux_base + as * C::AUX_BYTES)->type = JOB_EXIT;
-                    mbar_arrive(aux_full + as);
-                }
-                break;
-            }
-            if (!J.valid) continue;
-            unsigned char* aux = aux_base + as * C::AUX_BYTES;
-            const long long c0 = L.cell(J.i0 - 2, J.j, J.k);  // first staged cell of the row
-            const int avail = (int)(L.px - J.i0);              // cells left in the padded row from c0
-            const uint32_t len_d = (uint32_t)min(C::ROWD, avail) * 8u;
-            const uint32_t len_n = (uint32_t)min(C::ROWD, avail) * 4u;
-            const uint32_t len_f = (uint32_t)min(C::FLAG_BYTES, avail);
+    // A finished q-correction job is published (release-increment of its slab counter) lazily: right after
+    // its stores the fence would wait for them to drain (~1 us per job); one job later they are long
+    // complete.  Anything that might block on another job publishes first, so laziness cannot deadlock.
+    int pending_slab = -1;
+    auto publish_pending = [&]() {
+        if (pending_slab >= 0) {
             if (lane == 0) {
-                mbar_wait(aux_empty + as, aphase ^ 1);
-                JobDesc* d = reinterpret_cast<JobDesc*>(aux);
-                d->type = J.type, d->i0 = J.i0, d->j = J.j, d->k = J.k, d->slab = J.slab;
-                if (J.type == JOB_P2 && F.mode == 2) {
-                    // QCorr of this row's face neighbours must be complete (and visible to the async proxy)
-                    const int tgt = slab_target(J.b, F, L, C::NCW);
-                    for (;;) {
-                        bool ok = ld_acquire(done + J.slab) >= tgt;
-                        if (ok && J.kk > 0) ok = ld_acquire(done + J.slab - 1) >= tgt;
-                        if (ok && J.kk < F.NK - 1) ok = ld_acquire(done + J.slab + 1) >= tgt;
-                        if (ok && J.b > 0) ok = ld_acquire(done + J.slab - F.NK) >= slab_target(J.b - 1, F, L, C::NCW);
-                        if (ok) break;
-                        __nanosleep(200);
-                    }
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                }
-                mbar_expect_tx(aux_full + as, J.type == JOB_P2 ? len_n + len_f + 5 * len_d : len_n);
+                __threadfence();
+                atomicAdd(done + pending_slab, 1);
             }
-            __syncwarp();
-            {
-                unsigned char* a_nbr = aux + C::DESC_BYTES;
-                unsigned char* a_flag = a_nbr + C::NBR_BYTES;
-                unsigned char* a_qc = a_flag + C::FLAG_BYTES;
-                if (lane == 0) bulk_g2s(a_nbr, nbr + c0, len_n, aux_full + as, pol_norm);
-                if (J.type == JOB_P2) {
-                    if (lane == 1) bulk_g2s(a_flag, flag + c0, len_f, aux_full + as, pol_norm);
-                    if (lane == 2) bulk_g2s(a_qc + 0 * C::QC_BYTES, qc + c0, len_d, aux_full + as, pol_norm);
-                    if (lane == 3) bulk_g2s(a_qc + 1 * C::QC_BYTES, qc + n + c0 - L.px, len_d, aux_full + as, pol_norm);
-                    if (lane == 4) bulk_g2s(a_qc + 2 * C::QC_BYTES, qc + n + c0 + L.px, len_d, aux_full + as, pol_norm);
-                    if (lane == 5) bulk_g2s(a_qc + 3 * C::QC_BYTES, qc + 2 * n + c0 - L.sz, len_d, aux_full + as, pol_norm);
-                    if (lane == 6) bulk_g2s(a_qc + 4 * C::QC_BYTES, qc + 2 * n + c0 + L.sz, len_d, aux_full + as, pol_norm);
-                }
-            }
-            if (++as == C::NAUX) as = 0, aphase ^= 1;
-            const uint64_t pol = (F.mode == 2) ? (J.type == JOB_P1 ? pol_keep : pol_last) : pol_norm;
+            pending_slab = -1;
+        }
+    };
+    auto wait_full = [&](uint64_t* bar, uint32_t parity) {
+        if (!mbar_try_wait(bar, parity)) {
+            publish_pending();
+            mbar_wait(bar, parity);
+        }
+    };
+
+    // ------------------------------------------------------------------ producer state (thread 0 only)
+    uint32_t ps = 0, pphase = 0, pas = 0, paphase = 0;  // next population / aux slot to fill
+    int prefetched_ticket = 0;
+    bool producing = (tid == 0);  // false once the EXIT descriptor has been queued
+    Job pend;                     // job whose g rows are still to be issued
+    pend.valid = false;
+    uint64_t pol_keep = 0, pol_last = 0, pol_norm = 0;
+    if (tid == 0) {
+        // P1 reads are re-read by the P2 job a few hundred tickets later: keep them; P2 reads are the last use
+        pol_keep = policy_evict_last(), pol_last = policy_evict_first(), pol_norm = policy_normal();
+        prefetched_ticket = atomicAdd(tickets, 1);
+    }
+    auto issue_pop = [&](const Job& J, int lat) {
+        const long long c0 = L.cell(J.i0 - 2, J.j, J.k);
+        const uint32_t len_d = (uint32_t)min(C::ROWD, (int)(L.px - J.i0)) * 8u;
+        const uint64_t pol = (F.mode == 2) ? (J.type == JOB_P1 ? pol_keep : pol_last) : pol_norm;
+        const double* src = lat ? gin : fin;
+        unsigned char* slot = pop_base + ps * C::SLOT_BYTES;
+        mbar_wait(pop_empty + ps, pphase ^ 1);
+        mbar_expect_tx(pop_full + ps, NQ * len_d);
 #pragma unroll 1
-            for (int lat = 0; lat < 2; ++lat) {
-                const double* src = lat ? gin : fin;
-                unsigned char* slot = pop_base + ps * C::SLOT_BYTES;
-                if (lane == 0) {
-                    mbar_wait(pop_empty + ps, pphase ^ 1);
-                    mbar_expect_tx(pop_full + ps, NQ * len_d);
-                }
-                __syncwarp();
-                if (lane < NQ) {
-                    const int q = lane;
-                    const long long off = (long long)q * n + c0 - ((long long)ey(q) * L.px + (long long)ez(q) * L.sz);
-                    bulk_g2s(slot + q * C::ROWD * 8, src + off, len_d, pop_full + ps, pol);
-                }
-                if (++ps == C::NSLOT) ps = 0, pphase ^= 1;
+        for (int q = 0; q < NQ; ++q) {
+            const long long off = (long long)q * n + c0 - ((long long)ey(q) * L.px + (long long)ez(q) * L.sz);
+            bulk_g2s(slot + q * C::ROWD * 8, src + off, len_d, pop_full + ps, pol);
+        }
+        if (++ps == C::NSLOT) ps = 0, pphase ^= 1;
+    };
+    auto produce_g = [&]() {
+        if (pend.valid) {
+            issue_pop(pend, 1);
+            pend.valid = false;
+        }
+    };
+    auto deps_ok = [&](const Job& J) {
+        const int tgt = slab_target(J.b, F, L, C::NCW);
+        bool ok = ld_acquire(done + J.slab) >= tgt;
+        if (ok && J.kk > 0) ok = ld_acquire(done + J.slab - 1) >= tgt;
+        if (ok && J.kk < F.NK - 1) ok = ld_acquire(done + J.slab + 1) >= tgt;
+        if (ok && J.b > 0) ok = ld_acquire(done + J.slab - F.NK) >= slab_target(J.b - 1, F, L, C::NCW);
+        return ok;
+    };
+    // Draw tickets until a real job (or the end) and queue its descriptor + aux rows + f rows.  A collide job
+    // whose q-corrections are not complete yet is only waited for when this CTA has nothing else queued
+    // (may_block): otherwise it is parked and retried after the next job, because the jobs this CTA has
+    // queued may be exactly what another CTA's parked job is waiting for.
+    int queued = 0;
+    bool has_parked = false;
+    Job parked;
+    parked.valid = false;
+    auto try_produce = [&](bool may_block) -> bool {
+        produce_g();
+        Job J;
+        if (has_parked) {
+            J = parked;
+        } else {
+            for (;;) {
+                const long long ticket = prefetched_ticket;
+                prefetched_ticket = atomicAdd(tickets, 1);  // consumed one job later
+                J = decode(ticket, F, L, UW);
+                if (J.valid || J.type == JOB_EXIT) break;
             }
         }
-        return;
-    }
+        if (J.type == JOB_P2 && F.mode == 2) {
+            // QCorr of this row's face neighbours must be complete (and visible to the async proxy)
+            if (!deps_ok(J)) {
+                if (!may_block) {
+                    parked = J;
+                    has_parked = true;
+                    return false;
+                }
+                const long long t0 = clock64();
+                do {
+                    publish_pending();  // the awaited q-correction job may be this warp's own
+                    __nanosleep(100);
+                    if (clock64() - t0 > SPIN_LIMIT_CYCLES) {
+                        printf("marbles_b200: k_fused dependency wait timed out (block %d slab %d)\n", blockIdx.x, J.slab);
+                        __trap();
+                    }
+                } while (!deps_ok(J));
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        has_parked = false;
+        unsigned char* aux = aux_base + pas * C::AUX_BYTES;
+        mbar_wait(aux_empty + pas, paphase ^ 1);
+        JobDesc* d = reinterpret_cast<JobDesc*>(aux);
+        d->type = J.type;
+        if (J.type == JOB_EXIT) {
+            mbar_arrive(aux_full + pas);
+            producing = false;
+            return false;
+        }
+        d->i0 = J.i0, d->j = J.j, d->k = J.k, d->slab = J.slab;
+        const long long c0 = L.cell(J.i0 - 2, J.j, J.k);  // first staged cell of the row
+        const int avail = (int)(L.px - J.i0);              // cells left in the padded row from c0
+        const uint32_t len_d = (uint32_t)min(C::ROWD, avail) * 8u;
+        const uint32_t len_n = (uint32_t)min(C::ROWD, avail) * 4u;
+        const uint32_t len_f = (uint32_t)min(C::FLAG_BYTES, avail);
+        unsigned char* a_nbr = aux + C::DESC_BYTES;
+        unsigned char* a_flag = a_nbr + C::NBR_BYTES;
+        unsigned char* a_qc = a_flag + C::FLAG_BYTES;
+        mbar_expect_tx(aux_full + pas, J.type == JOB_P2 ? len_n + len_f + 5 * len_d : len_n);
+        bulk_g2s(a_nbr, nbr + c0, len_n, aux_full + pas, pol_norm);
+        if (J.type == JOB_P2) {
+            bulk_g2s(a_flag, flag + c0, len_f, aux_full + pas, pol_norm);
+            bulk_g2s(a_qc + 0 * C::QC_BYTES, qc + c0, len_d, aux_full + pas, pol_norm);
+            bulk_g2s(a_qc + 1 * C::QC_BYTES, qc + n + c0 - L.px, len_d, aux_full + pas, pol_norm);
+            bulk_g2s(a_qc + 2 * C::QC_BYTES, qc + n + c0 + L.px, len_d, aux_full + pas, pol_norm);
+            bulk_g2s(a_qc + 3 * C::QC_BYTES, qc + 2 * n + c0 - L.sz, len_d, aux_full + pas, pol_norm);
+            bulk_g2s(a_qc + 4 * C::QC_BYTES, qc + 2 * n + c0 + L.sz, len_d, aux_full + pas, pol_norm);
+        }
+        if (++pas == C::NAUX) pas = 0, paphase ^= 1;
+        issue_pop(J, 0);
+        pend = J;
+        ++queued;
+        return true;
+    };
+    // keep two jobs queued: the one being computed and the one whose rows are in flight
+    auto top_up = [&]() {
+        while (producing && queued < 2)
+            if (!try_produce(queued == 0)) break;
+    };
+    if (tid == 0) top_up();
 
-    // ---------------------------------------------------------------------- consumer warps
+    // ---------------------------------------------------------------------- all warps consume
     uint32_t cs = 0, cphase = 0, as = 0, aphase = 0;
     auto next_slot = [&]() {
         if (++cs == C::NSLOT) cs = 0, cphase ^= 1;
@@ -298,7 +376,7 @@ __global__ void __launch_bounds__(Cfg<UW>::THREADS, UW == 128 ? 2 : 1)
     };
     for (;;) {
         unsigned char* aux = aux_base + as * C::AUX_BYTES;
-        mbar_wait(aux_full + as, aphase);
+        wait_full(aux_full + as, aphase);
         const JobDesc* d = reinterpret_cast<const JobDesc*>(aux);
         const int type = d->type;
         if (type == JOB_EXIT) break;
@@ -321,39 +399,40 @@ __global__ void __launch_bounds__(Cfg<UW>::THREADS, UW == 128 ? 2 : 1)
         };
 
         if (type == JOB_P1) {
+            release_slot(aux_empty + as);  // only the pull mask was needed
             MomL ml = {0.0, 0.0, 0.0, 0.0};
             double e2 = 0.0;
             {
                 const double* slot = reinterpret_cast<const double*>(pop_base + cs * C::SLOT_BYTES);
-                mbar_wait(pop_full + cs, cphase);
+                wait_full(pop_full + cs, cphase);
                 if (fluid) static_for<0, NQ>([&](auto qc_) { acc_l<decltype(qc_)::value>(ml, pulled(slot, fin, qc_)); });
                 release_slot(pop_empty + cs);
                 next_slot();
+                if (tid == 0) produce_g();
             }
             {
                 const double* slot = reinterpret_cast<const double*>(pop_base + cs * C::SLOT_BYTES);
-                mbar_wait(pop_full + cs, cphase);
+                wait_full(pop_full + cs, cphase);
                 if (fluid) static_for<0, NQ>([&](auto qc_) { e2 += pulled(slot, gin, qc_); });
                 release_slot(pop_empty + cs);
                 next_slot();
             }
+            publish_pending();
             if (fluid) {
                 const Prim s = primitives(ml.rho, ml.jx, ml.jy, ml.jz, e2, P);
                 qc[c] = s.qcx;
                 qc[n + c] = s.qcy;
                 qc[2 * n + c] = s.qcz;
             }
-            // publish: this warp's QCorr stores happen-before the counter increment
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) atomicAdd(done + slab, 1);
+            __syncwarp();  // orders every lane's stores before lane 0's later fence + increment
+            pending_slab = slab;
         } else {
             double f[NQ];
             MomF mf = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
             MomG mg = {0, 0, 0, 0};
             {
                 const double* slot = reinterpret_cast<const double*>(pop_base + cs * C::SLOT_BYTES);
-                mbar_wait(pop_full + cs, cphase);
+                wait_full(pop_full + cs, cphase);
                 static_for<0, NQ>([&](auto qc_) {
                     constexpr int Q = decltype(qc_)::value;
                     f[Q] = fluid ? pulled(slot, fin, qc_) : 0.0;
@@ -361,12 +440,35 @@ __global__ void __launch_bounds__(Cfg<UW>::THREADS, UW == 128 ? 2 : 1)
                 });
                 release_slot(pop_empty + cs);  // f lives in registers from here on
                 next_slot();
+                if (tid == 0) produce_g();
             }
             const double* gslot = reinterpret_cast<const double*>(pop_base + cs * C::SLOT_BYTES);
             uint64_t* gbar = pop_empty + cs;
-            mbar_wait(pop_full + cs, cphase);
+            wait_full(pop_full + cs, cphase);
             next_slot();
             if (fluid) static_for<0, NQ>([&](auto qc_) { acc_g<decltype(qc_)::value>(mg, pulled(gslot, gin, qc_)); });
+            const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
+            // grad of the q-correction (LBM.cpp:959-991, Utilities.H:279-312) from the staged rows
+            const unsigned fb = s_flag[tid + 2];
+            double dqx, dqy, dqz;
+            {
+                const bool okp = fb & GRAD_PX, okm = fb & GRAD_MX;
+                const double dp = okp ? s_qc[tid + 3] : 0.0, dm = okm ? s_qc[tid + 1] : 0.0;
+                dqx = one_sided_gradient(okp, okm, dp, s.qcx, dm, P.idx[0]);
+            }
+            {
+                const bool okp = fb & GRAD_PY, okm = fb & GRAD_MY;
+                const double dp = okp ? s_qc[2 * C::ROWD + tid + 2] : 0.0, dm = okm ? s_qc[1 * C::ROWD + tid + 2] : 0.0;
+                dqy = one_sided_gradient(okp, okm, dp, s.qcy, dm, P.idx[1]);
+            }
+            {
+                const bool okp = fb & GRAD_PZ, okm = fb & GRAD_MZ;
+                const double dp = okp ? s_qc[4 * C::ROWD + tid + 2] : 0.0, dm = okm ? s_qc[3 * C::ROWD + tid + 2] : 0.0;
+                dqz = one_sided_gradient(okp, okm, dp, s.qcz, dm, P.idx[2]);
+            }
+            release_slot(aux_empty + as);
+            publish_pending();
+            const bool edge = in_row && is_image_edge(L, i, j, k);
             if (in_row && !fluid) {
                 // solid cell: the streamed value is the -1 sentinel (LBM.cpp:565, 582); collide skips it
                 for_cell_and_images(L, i, j, k, [&](long long dd) {
@@ -378,25 +480,6 @@ __global__ void __launch_bounds__(Cfg<UW>::THREADS, UW == 128 ? 2 : 1)
                 });
             }
             if (fluid) {
-                const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
-                // grad of the q-correction (LBM.cpp:959-991, Utilities.H:279-312) from the staged rows
-                const unsigned fb = s_flag[tid + 2];
-                double dqx, dqy, dqz;
-                {
-                    const bool okp = fb & GRAD_PX, okm = fb & GRAD_MX;
-                    const double dp = okp ? s_qc[tid + 3] : 0.0, dm = okm ? s_qc[tid + 1] : 0.0;
-                    dqx = one_sided_gradient(okp, okm, dp, s.qcx, dm, P.idx[0]);
-                }
-                {
-                    const bool okp = fb & GRAD_PY, okm = fb & GRAD_MY;
-                    const double dp = okp ? s_qc[2 * C::ROWD + tid + 2] : 0.0, dm = okm ? s_qc[1 * C::ROWD + tid + 2] : 0.0;
-                    dqy = one_sided_gradient(okp, okm, dp, s.qcy, dm, P.idx[1]);
-                }
-                {
-                    const bool okp = fb & GRAD_PZ, okm = fb & GRAD_MZ;
-                    const double dp = okp ? s_qc[4 * C::ROWD + tid + 2] : 0.0, dm = okm ? s_qc[3 * C::ROWD + tid + 2] : 0.0;
-                    dqz = one_sided_gradient(okp, okm, dp, s.qcz, dm, P.idx[2]);
-                }
                 if constexpr (MACRO) {
                     // m_macrodata of the post-stream state (Constants.H:8-31, LBM.cpp:867-901)
                     macro[0 * n + c] = s.rho;
@@ -426,25 +509,36 @@ __global__ void __launch_bounds__(Cfg<UW>::THREADS, UW == 128 ? 2 : 1)
                 // relax_f_to_equilibrium (LBM.cpp:799-801) + the FillBoundary of f, g that follows it
                 static_for<0, NQ>([&](auto qc_) {
                     constexpr int Q = decltype(qc_)::value;
-                    f[Q] += cc.omega * (feq_q<Q>(cc) - f[Q]);
+                    fout[(long long)Q * n + c] = f[Q] = f[Q] + cc.omega * (feq_q<Q>(cc) - f[Q]);
                 });
-                for_cell_and_images(L, i, j, k, [&](long long dd) {
-                    static_for<0, NQ>([&](auto qc_) {
-                        constexpr int Q = decltype(qc_)::value;
-                        fout[(long long)Q * n + c + dd] = f[Q];
-                    });
-                    static_for<0, NQ>([&](auto qc_) {
-                        constexpr int Q = decltype(qc_)::value;
-                        const double gq = pulled(gslot, gin, qc_);
-                        gout[(long long)Q * n + c + dd] = gq + cc.omega * (geq_q<Q>(cc) - gq);
-                    });
+                static_for<0, NQ>([&](auto qc_) {
+                    constexpr int Q = decltype(qc_)::value;
+                    const double gq = pulled(gslot, gin, qc_);
+                    gout[(long long)Q * n + c] = gq + cc.omega * (geq_q<Q>(cc) - gq);
                 });
+                if (edge) {
+                    for_images(L, i, j, k, [&](long long dd) {
+                        static_for<0, NQ>([&](auto qc_) {
+                            constexpr int Q = decltype(qc_)::value;
+                            fout[(long long)Q * n + c + dd] = f[Q];
+                        });
+                        static_for<0, NQ>([&](auto qc_) {
+                            constexpr int Q = decltype(qc_)::value;
+                            const double gq = pulled(gslot, gin, qc_);
+                            gout[(long long)Q * n + c + dd] = gq + cc.omega * (geq_q<Q>(cc) - gq);
+                        });
+                    });
+                }
             }
             release_slot(gbar);
         }
-        release_slot(aux_empty + as);
         if (++as == C::NAUX) as = 0, aphase ^= 1;
+        if (tid == 0) {
+            --queued;
+            top_up();
+        }
     }
+    publish_pending();
 }
 
 // ===========================================================================

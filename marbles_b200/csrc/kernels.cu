@@ -200,22 +200,24 @@ __global__ void __launch_bounds__(128) k_collide(const double* __restrict__ fin,
     // relax_f_to_equilibrium (LBM.cpp:799-801) + the FillBoundary of f, g that follows it (LBM.cpp:805-806)
     static_for<0, NQ>([&](auto qc_) {
         constexpr int Q = decltype(qc_)::value;
-        f[Q] += cc.omega * (feq_q<Q>(cc) - f[Q]);
+        fout[(long long)Q * n + c] = f[Q] = f[Q] + cc.omega * (feq_q<Q>(cc) - f[Q]);
     });
     static_for<0, NQ>([&](auto qc_) {
         constexpr int Q = decltype(qc_)::value;
-        g[Q] += cc.omega * (geq_q<Q>(cc) - g[Q]);
+        gout[(long long)Q * n + c] = g[Q] = g[Q] + cc.omega * (geq_q<Q>(cc) - g[Q]);
     });
-    for_cell_and_images(L, i, j, k, [&](long long d) {
-        static_for<0, NQ>([&](auto qc_) {
-            constexpr int Q = decltype(qc_)::value;
-            fout[(long long)Q * n + c + d] = f[Q];
+    if (is_image_edge(L, i, j, k)) {
+        for_images(L, i, j, k, [&](long long d) {
+            static_for<0, NQ>([&](auto qc_) {
+                constexpr int Q = decltype(qc_)::value;
+                fout[(long long)Q * n + c + d] = f[Q];
+            });
+            static_for<0, NQ>([&](auto qc_) {
+                constexpr int Q = decltype(qc_)::value;
+                gout[(long long)Q * n + c + d] = g[Q];
+            });
         });
-        static_for<0, NQ>([&](auto qc_) {
-            constexpr int Q = decltype(qc_)::value;
-            gout[(long long)Q * n + c + d] = g[Q];
-        });
-    });
+    }
 }
 
 // ---------------------------------------------------------------------------

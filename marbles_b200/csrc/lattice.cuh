@@ -101,21 +101,37 @@ inline Layout make_layout(const int lo[3], const int hi[3], const int dlo[3], co
 // FillBoundary after every stream and relax (LBM.cpp:603, 805-806); here the kernel that produces a
 // value also stores it to the cell's periodic images, so no separate ghost pass touches the state.
 // body(delta) is called for the cell itself (delta 0) and for each image (offset in doubles).
-template <typename F>
-__device__ __forceinline__ void for_cell_and_images(const Layout& L, int i, int j, int k, F&& body)
+__device__ __forceinline__ bool is_image_edge(const Layout& L, int i, int j, int k)
 {
-    const bool edge = (L.img[0] && (i < GX || i >= L.nx - GX)) || (L.img[1] && (j < GY || j >= L.ny - GY)) ||
-                      (L.img[2] && (k < GZ || k >= L.nz - GZ));
-    // 45 candidates (mx, my, mz) in {-1,0,1} x {-1,0,1} x {-2..2}; t = 22 is the cell itself
-    const int t0 = edge ? 0 : 22, t1 = edge ? 45 : 23;
+    return (L.img[0] && (i < GX || i >= L.nx - GX)) || (L.img[1] && (j < GY || j >= L.ny - GY)) ||
+           (L.img[2] && (k < GZ || k >= L.nz - GZ));
+}
+// 45 candidates (mx, my, mz) in {-1,0,1} x {-1,0,1} x {-2..2}; t = 22 is the cell itself
+template <typename F>
+__device__ __forceinline__ void for_image_range(const Layout& L, int i, int j, int k, int t0, int t1, bool skip_self, F&& body)
+{
 #pragma unroll 1
     for (int t = t0; t < t1; ++t) {
+        if (skip_self && t == 22) continue;
         const int mx = t % 3 - 1, my = (t / 3) % 3 - 1, mz = t / 9 - 2;
         if ((mx != 0 && !L.img[0]) || (my != 0 && !L.img[1]) || (mz != 0 && !L.img[2])) continue;
         const int ii = i + mx * L.nx, jj = j + my * L.ny, kk = k + mz * L.nz;
         if (ii < -GX || ii > L.nx - 1 + GX || jj < -GY || jj > L.ny - 1 + GY || kk < -GZ || kk > L.nz - 1 + GZ) continue;
         body((long long)mx * L.nx + (long long)my * L.ny * L.px + (long long)mz * L.nz * L.sz);
     }
+}
+// the cell itself (delta 0) and its images
+template <typename F>
+__device__ __forceinline__ void for_cell_and_images(const Layout& L, int i, int j, int k, F&& body)
+{
+    const bool edge = is_image_edge(L, i, j, k);
+    for_image_range(L, i, j, k, edge ? 0 : 22, edge ? 45 : 23, false, body);
+}
+// the images only (call for edge cells)
+template <typename F>
+__device__ __forceinline__ void for_images(const Layout& L, int i, int j, int k, F&& body)
+{
+    for_image_range(L, i, j, k, 0, 45, true, body);
 }
 
 struct Phys {
