@@ -269,9 +269,11 @@ def main():
     # ---- roofline of the dominant kernel (collide pass) -----------------------------
     peak, peak_src = measured_peak_gbs()
     collide_ms = kms[2] / max(nrec.value, 1)
-    kname = {0: "k_collide<pull>", 1: "k_fused (q-correction + collide jobs)", 2: "k_fused (collide jobs)"}[args.variant]
+    kname = {0: "k_collide<pull>", 1: "k_fused (q-correction + collide jobs)", 2: "k_fused (collide jobs)",
+             3: "k_fused_plain (q-correction + collide jobs)"}[args.variant]
     vname = {0: "two plain kernels (q-correction, collide)", 1: "one persistent TMA-pipelined kernel per step",
-             2: "persistent TMA kernel, two launches (q-correction, collide)"}[args.variant]
+             2: "persistent TMA kernel, two launches (q-correction, collide)",
+             3: "one persistent kernel per step, plain loads"}[args.variant]
     achieved = BYTES_PER_CELL * lbm.ncells / (collide_ms * 1e-3) / 1e9
     traffic = None
     try:

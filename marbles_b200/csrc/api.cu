@@ -50,7 +50,6 @@ struct Level {
     LevelPtrs p;
     int cur = 0;  // index of the current lattice buffers
     bool local_z = true;
-    bool images_valid = false;  // ghost cells that are periodic images of valid cells are current
     double* stage = nullptr;  // one-component staging for FAB transfers
     size_t stage_bytes = 0;
     int32_t* flag_stage = nullptr;
@@ -145,26 +144,34 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
         ctx->events.push_back(e);
     };
     mark();
-    // the periodic images are kept current by the stores of the previous step; only a state that
-    // came from outside (upload, initialize) needs the copy kernels
-    ctx->launches += launch_ghost_fill(lv.L, lv.B, lv.p.f[a], lv.p.g[a], lv.local_z, true, !lv.images_valid, st);
-    lv.images_valid = true;
+    // all-periodic level: the plain kernels wrap source indices themselves and no ghost cell is read;
+    // otherwise (and for the TMA kernels, which stage un-wrapped rows) fill every ghost cell first
+    const bool tma = ctx->variant == 1 || ctx->variant == 2;
+    Layout Lk = lv.L;
+    if (tma) Lk.wrap[0] = Lk.wrap[1] = Lk.wrap[2] = 0;
+    const bool need_ghosts = !(Lk.wrap[0] && Lk.wrap[1]);
+    if (need_ghosts) ctx->launches += launch_ghost_fill(lv.L, lv.B, lv.p.f[a], lv.p.g[a], lv.local_z, true, true, st);
     mark();
     double* macro = want_macro ? lv.macro : nullptr;
     if (ctx->variant == 0) {
-        ctx->launches += launch_qcorr(lv.L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st);
+        ctx->launches += launch_qcorr(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st);
         mark();
-        ctx->launches += launch_collide(lv.L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
+        ctx->launches += launch_collide(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
                                         lv.p.qc, macro, true, st);
     } else if (ctx->variant == 2) {
-        ctx->launches += launch_fused(lv.L, lv.P, ctx->uw, ctx->band_rows, ctx->lag_per_cta, 0, ctx->sm_count, lv.p.f[a],
+        ctx->launches += launch_fused(Lk, lv.P, ctx->uw, ctx->band_rows, ctx->lag_per_cta, 0, ctx->sm_count, lv.p.f[a],
                                       lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, macro, lv.counters, st);
         mark();
-        ctx->launches += launch_fused(lv.L, lv.P, ctx->uw, ctx->band_rows, ctx->lag_per_cta, 1, ctx->sm_count, lv.p.f[a],
+        ctx->launches += launch_fused(Lk, lv.P, ctx->uw, ctx->band_rows, ctx->lag_per_cta, 1, ctx->sm_count, lv.p.f[a],
                                       lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, macro, lv.counters, st);
+    } else if (ctx->variant == 3) {
+        mark();  // no separate q-correction pass
+        ctx->launches += launch_fused_plain(Lk, lv.P, ctx->band_rows, ctx->lag_per_cta, 2, ctx->sm_count, lv.p.f[a],
+                                            lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, macro,
+                                            lv.counters, st);
     } else {
         mark();  // no separate q-correction pass
-        ctx->launches += launch_fused(lv.L, lv.P, ctx->uw, ctx->band_rows, ctx->lag_per_cta, 2, ctx->sm_count, lv.p.f[a],
+        ctx->launches += launch_fused(Lk, lv.P, ctx->uw, ctx->band_rows, ctx->lag_per_cta, 2, ctx->sm_count, lv.p.f[a],
                                       lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, macro, lv.counters, st);
     }
     mark();
@@ -280,9 +287,9 @@ int mbl_level_define(mbl_ctx* ctx, int lev, const mbl_level_geom* g, void* devic
     lv.geom = *g;
     lv.L = layout_of(g);
     lv.local_z = (g->lo[2] == g->dom_lo[2] && g->hi[2] == g->dom_hi[2]);
-    lv.L.img[0] = ctx->prm.periodic[0];
-    lv.L.img[1] = ctx->prm.periodic[1];
-    lv.L.img[2] = ctx->prm.periodic[2] && lv.local_z;
+    const bool all_periodic = ctx->prm.periodic[0] && ctx->prm.periodic[1] && ctx->prm.periodic[2];
+    lv.L.wrap[0] = lv.L.wrap[1] = all_periodic;
+    lv.L.wrap[2] = all_periodic && lv.local_z;
     if (!lv.local_z && lv.L.nz < GZ) return fail("a z-slab needs at least %d planes", GZ);
     const mbl_params& pr = ctx->prm;
     lv.P.nu = pr.nu;
@@ -382,7 +389,6 @@ int mbl_upload(mbl_ctx* ctx, int lev, int which, const double* fab, int ng)
     const size_t n = (size_t)(lv.L.nx + 2 * ng) * (lv.L.ny + 2 * ng) * (lv.L.nz + 2 * ng);
     if (ensure_stage(lv, n * sizeof(double))) return 1;
     double* dst = which == MBL_G ? curg(lv) : curf(lv);
-    lv.images_valid = false;
     for (int q = 0; q < NQ; ++q) {
         CU(cudaMemcpyAsync(lv.stage, fab + (size_t)q * n, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         ctx->launches += launch_fab_to_soa(lv.L, lv.stage, ng, dst + (size_t)q * lv.L.sq, 1, ctx->stream);
@@ -459,7 +465,6 @@ int mbl_initialize(mbl_ctx* ctx, int lev, int ic_kind, const double* v, int nv)
     I.wave_length = v[8];
     I.T0 = v[9], I.gamma = v[10], I.R = v[11], I.c_s = v[12];
     I.density_ratio = v[13], I.temperature_ratio = v[14], I.x_disc = v[15];
-    lv.images_valid = false;
     ctx->launches += launch_initialize(lv.L, lv.B, I, lv.p.flag, curf(lv), curg(lv), ctx->stream);
     CU(cudaGetLastError());
     return 0;
@@ -470,8 +475,7 @@ int mbl_fillpatch(mbl_ctx* ctx, int lev, double /*time*/)
     if (check_level(ctx, lev)) return 1;
     Level& lv = ctx->lev[lev];
     CU(cudaSetDevice(ctx->device));
-    ctx->launches += launch_ghost_fill(lv.L, lv.B, curf(lv), curg(lv), lv.local_z, true, !lv.images_valid, ctx->stream);
-    lv.images_valid = true;
+    ctx->launches += launch_ghost_fill(lv.L, lv.B, curf(lv), curg(lv), lv.local_z, true, true, ctx->stream);
     CU(cudaGetLastError());
     return 0;
 }
@@ -542,8 +546,7 @@ int mbl_eb_forces(mbl_ctx* ctx, int lev, double out[3])
     CU(cudaSetDevice(ctx->device));
     // the reference reads f in ghost cells that FillBoundary refreshed after the collision
     // (LBM.cpp:805); refresh the periodic images here
-    ctx->launches += launch_ghost_fill(lv.L, lv.B, curf(lv), curg(lv), lv.local_z, false, !lv.images_valid, ctx->stream);
-    lv.images_valid = true;
+    ctx->launches += launch_ghost_fill(lv.L, lv.B, curf(lv), curg(lv), lv.local_z, false, true, ctx->stream);
     ctx->launches += launch_eb_forces(lv.L, curf(lv), lv.p.flag, lv.d_red, ctx->stream);
     CU(cudaMemcpyAsync(out, lv.d_red, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -634,7 +637,7 @@ int mbl_get_timing(mbl_ctx* ctx, double ms[3], int* nsteps)
 int mbl_set_variant(mbl_ctx* ctx, int variant)
 {
     if (!ctx) return fail("null context");
-    if (variant < 0 || variant > 2) return fail("variant %d is not available", variant);
+    if (variant < 0 || variant > 3) return fail("variant %d is not available", variant);
     ctx->variant = variant;
     return 0;
 }

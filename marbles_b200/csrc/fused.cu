@@ -20,11 +20,12 @@
 //     full/empty mbarriers; loads of the next job are in flight while the consumers compute.
 //   * consumers: thread t owns cell i0+t.  P1: sum the staged rows -> QCorr -> global, then
 //     release-increment the slab's completion counter.  P2: f to registers (slot released at once),
-//     g read in place, collide, store (plus the periodic images, lattice.cuh).
+//     g read in place, collide, store.
 //   * the producer checks the completion counters of the slabs a P2 job reads QCorr from (acquire) before
 //     it issues that job's QCorr copies.
 // Bounce-back (source cell solid) falls back to a direct global load of the cell's own opposite
-// population; ghost cells of non-periodic faces are filled by the BC kernels (kernels.cu) beforehand.
+// population.  The staged rows are read un-wrapped, so this kernel needs every ghost cell (periodic images
+// included) filled by the ghost kernels (kernels.cu) beforehand.
 #include "kernels.cuh"
 
 #include <cstdio>
@@ -201,9 +202,16 @@ __global__ void __launch_bounds__(Cfg<UW>::THREADS, UW == 128 ? 2 : 1)
     uint64_t* aux_full = bars + 2 * C::NSLOT;  // [NAUX]
     uint64_t* aux_empty = aux_full + C::NAUX;  // [NAUX]
 
+    // element offset of the row a direction pulls from, relative to the job's own row (the x shift is
+    // applied when the staged row is read)
+    __shared__ long long s_rowoff[NQ];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     if (tid == 0) {
+        static_for<0, NQ>([&](auto qc_) {
+            constexpr int Q = decltype(qc_)::value;
+            s_rowoff[Q] = (long long)Q * L.sq - ((long long)ey(Q) * L.px + (long long)ez(Q) * L.sz);
+        });
         for (int s = 0; s < C::NSLOT; ++s) {
             mbar_init(pop_full + s, 1);
             mbar_init(pop_empty + s, C::NCW);
@@ -261,11 +269,8 @@ __global__ void __launch_bounds__(Cfg<UW>::THREADS, UW == 128 ? 2 : 1)
         unsigned char* slot = pop_base + ps * C::SLOT_BYTES;
         mbar_wait(pop_empty + ps, pphase ^ 1);
         mbar_expect_tx(pop_full + ps, NQ * len_d);
-#pragma unroll 1
-        for (int q = 0; q < NQ; ++q) {
-            const long long off = (long long)q * n + c0 - ((long long)ey(q) * L.px + (long long)ez(q) * L.sz);
-            bulk_g2s(slot + q * C::ROWD * 8, src + off, len_d, pop_full + ps, pol);
-        }
+#pragma unroll 9
+        for (int q = 0; q < NQ; ++q) bulk_g2s(slot + q * C::ROWD * 8, src + c0 + s_rowoff[q], len_d, pop_full + ps, pol);
         if (++ps == C::NSLOT) ps = 0, pphase ^= 1;
     };
     auto produce_g = [&]() {
@@ -468,16 +473,13 @@ __global__ void __launch_bounds__(Cfg<UW>::THREADS, UW == 128 ? 2 : 1)
             }
             release_slot(aux_empty + as);
             publish_pending();
-            const bool edge = in_row && is_image_edge(L, i, j, k);
             if (in_row && !fluid) {
                 // solid cell: the streamed value is the -1 sentinel (LBM.cpp:565, 582); collide skips it
-                for_cell_and_images(L, i, j, k, [&](long long dd) {
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        fout[q * n + c + dd] = -1.0;
-                        gout[q * n + c + dd] = -1.0;
-                    }
-                });
+                for (int q = 0; q < NQ; ++q) {
+                    fout[q * n + c] = -1.0;
+                    gout[q * n + c] = -1.0;
+                }
             }
             if (fluid) {
                 if constexpr (MACRO) {
@@ -509,26 +511,13 @@ __global__ void __launch_bounds__(Cfg<UW>::THREADS, UW == 128 ? 2 : 1)
                 // relax_f_to_equilibrium (LBM.cpp:799-801) + the FillBoundary of f, g that follows it
                 static_for<0, NQ>([&](auto qc_) {
                     constexpr int Q = decltype(qc_)::value;
-                    fout[(long long)Q * n + c] = f[Q] = f[Q] + cc.omega * (feq_q<Q>(cc) - f[Q]);
+                    fout[(long long)Q * n + c] = f[Q] + cc.omega * (feq_q<Q>(cc) - f[Q]);
                 });
                 static_for<0, NQ>([&](auto qc_) {
                     constexpr int Q = decltype(qc_)::value;
                     const double gq = pulled(gslot, gin, qc_);
                     gout[(long long)Q * n + c] = gq + cc.omega * (geq_q<Q>(cc) - gq);
                 });
-                if (edge) {
-                    for_images(L, i, j, k, [&](long long dd) {
-                        static_for<0, NQ>([&](auto qc_) {
-                            constexpr int Q = decltype(qc_)::value;
-                            fout[(long long)Q * n + c + dd] = f[Q];
-                        });
-                        static_for<0, NQ>([&](auto qc_) {
-                            constexpr int Q = decltype(qc_)::value;
-                            const double gq = pulled(gslot, gin, qc_);
-                            gout[(long long)Q * n + c + dd] = gq + cc.omega * (geq_q<Q>(cc) - gq);
-                        });
-                    });
-                }
             }
             release_slot(gbar);
         }

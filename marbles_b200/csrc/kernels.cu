@@ -38,7 +38,8 @@ void init_tables()
 // pull of one lattice (all 27 directions) for cell c
 // ---------------------------------------------------------------------------
 template <bool PULL, bool FAST, typename F>
-__device__ __forceinline__ void gather27(const double* __restrict__ in, long long c, uint32_t m, const Layout& L, F&& sink)
+__device__ __forceinline__ void gather27(const double* __restrict__ in, long long c, uint32_t m, const Layout& L,
+                                         const PullOffsets& o, F&& sink)
 {
     static_for<0, NQ>([&](auto qc) {
         constexpr int Q = decltype(qc)::value;
@@ -46,12 +47,12 @@ __device__ __forceinline__ void gather27(const double* __restrict__ in, long lon
         if constexpr (!PULL) {
             v = in[(long long)Q * L.sq + c];
         } else if constexpr (FAST) {
-            v = in[(long long)Q * L.sq + c - ((long long)ex(Q) + (long long)ey(Q) * L.px + (long long)ez(Q) * L.sz)];
+            v = in[(long long)Q * L.sq + c + (o.xo[ex(Q) + 1] + o.yo[ey(Q) + 1] + o.zo[ez(Q) + 1])];
         } else {
             // fluid source: take its population; solid source: halfway bounce-back of the
             // cell's own opposite population (LBM.cpp:590-595 in pull form)
             const bool fl = (m >> Q) & 1u;
-            const long long a = (long long)Q * L.sq + c - ((long long)ex(Q) + (long long)ey(Q) * L.px + (long long)ez(Q) * L.sz);
+            const long long a = (long long)Q * L.sq + c + (o.xo[ex(Q) + 1] + o.yo[ey(Q) + 1] + o.zo[ez(Q) + 1]);
             const long long b = (long long)opp(Q) * L.sq + c;
             v = in[fl ? a : b];
         }
@@ -60,29 +61,26 @@ __device__ __forceinline__ void gather27(const double* __restrict__ in, long lon
 }
 
 // ---------------------------------------------------------------------------
-// pass 1: q-corrections of the post-stream state
+// pass 1: q-corrections of the post-stream state of one cell
 // ---------------------------------------------------------------------------
 template <bool PULL>
-__global__ void __launch_bounds__(128) k_qcorr(const double* __restrict__ fin, const double* __restrict__ gin,
-                                               const uint32_t* __restrict__ nbr, double* __restrict__ qc, Layout L,
-                                               Phys P, int k0)
+__device__ __forceinline__ void qcorr_cell(const double* __restrict__ fin, const double* __restrict__ gin,
+                                           const uint32_t* __restrict__ nbr, double* __restrict__ qc, const Layout& L,
+                                           const Phys& P, int i, int j, int k)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    const int k = blockIdx.z + k0;
-    if (i >= L.nx) return;
     const long long c = L.cell(i, j, k);
     const uint32_t m = nbr[c];
     if (!(m & 1u)) return;
     MomL ml = {0.0, 0.0, 0.0, 0.0};
     double e2 = 0.0;
+    const PullOffsets o = pull_offsets(L, i, j, k);
     const bool fast = __all_sync(__activemask(), m == ALL_FLUID);
     if (fast) {
-        gather27<PULL, true>(fin, c, m, L, [&](auto qc_, double v) { acc_l<decltype(qc_)::value>(ml, v); });
-        gather27<PULL, true>(gin, c, m, L, [&](auto, double v) { e2 += v; });
+        gather27<PULL, true>(fin, c, m, L, o, [&](auto qc_, double v) { acc_l<decltype(qc_)::value>(ml, v); });
+        gather27<PULL, true>(gin, c, m, L, o, [&](auto, double v) { e2 += v; });
     } else {
-        gather27<PULL, false>(fin, c, m, L, [&](auto qc_, double v) { acc_l<decltype(qc_)::value>(ml, v); });
-        gather27<PULL, false>(gin, c, m, L, [&](auto, double v) { e2 += v; });
+        gather27<PULL, false>(fin, c, m, L, o, [&](auto qc_, double v) { acc_l<decltype(qc_)::value>(ml, v); });
+        gather27<PULL, false>(gin, c, m, L, o, [&](auto, double v) { e2 += v; });
     }
     const Prim s = primitives(ml.rho, ml.jx, ml.jy, ml.jz, e2, P);
     const long long n = L.sq;
@@ -91,58 +89,63 @@ __global__ void __launch_bounds__(128) k_qcorr(const double* __restrict__ fin, c
     qc[2 * n + c] = s.qcz;
 }
 
-// ---------------------------------------------------------------------------
-// pass 2: (pull +) collide
-// ---------------------------------------------------------------------------
-template <bool PULL, bool MACRO>
-__global__ void __launch_bounds__(128) k_collide(const double* __restrict__ fin, const double* __restrict__ gin,
-                                                 double* __restrict__ fout, double* __restrict__ gout,
-                                                 const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ flag,
-                                                 const double* __restrict__ qc, double* __restrict__ macro, Layout L,
-                                                 Phys P)
+template <bool PULL>
+__global__ void __launch_bounds__(128) k_qcorr(const double* __restrict__ fin, const double* __restrict__ gin,
+                                               const uint32_t* __restrict__ nbr, double* __restrict__ qc,
+                                               const __grid_constant__ Layout L, const __grid_constant__ Phys P, int k0)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    const int k = blockIdx.z;
     if (i >= L.nx) return;
+    qcorr_cell<PULL>(fin, gin, nbr, qc, L, P, i, blockIdx.y, blockIdx.z + k0);
+}
+
+// ---------------------------------------------------------------------------
+// pass 2: (pull +) collide of one cell
+// ---------------------------------------------------------------------------
+template <bool PULL, bool MACRO>
+__device__ __forceinline__ void collide_cell(const double* __restrict__ fin, const double* __restrict__ gin,
+                                             double* __restrict__ fout, double* __restrict__ gout,
+                                             const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ flag,
+                                             const double* __restrict__ qc, double* __restrict__ macro, const Layout& L,
+                                             const Phys& P, int i, int j, int k)
+{
     const long long c = L.cell(i, j, k);
     const long long n = L.sq;
     const uint32_t m = nbr[c];
     if (!(m & 1u)) {
         // solid cell: the streamed value is the -1 sentinel (LBM.cpp:565, 582); collide skips it
         if constexpr (PULL) {
-            for_cell_and_images(L, i, j, k, [&](long long d) {
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    fout[q * n + c + d] = -1.0;
-                    gout[q * n + c + d] = -1.0;
-                }
-            });
+            for (int q = 0; q < NQ; ++q) {
+                fout[q * n + c] = -1.0;
+                gout[q * n + c] = -1.0;
+            }
         }
         return;
     }
     double f[NQ], g[NQ];
     MomF mf = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     MomG mg = {0, 0, 0, 0};
+    const PullOffsets o = pull_offsets(L, i, j, k);
     const bool fast = __all_sync(__activemask(), m == ALL_FLUID);
     if (fast) {
-        gather27<PULL, true>(fin, c, m, L, [&](auto qc_, double v) {
+        gather27<PULL, true>(fin, c, m, L, o, [&](auto qc_, double v) {
             constexpr int Q = decltype(qc_)::value;
             f[Q] = v;
             acc_f<Q>(mf, v);
         });
-        gather27<PULL, true>(gin, c, m, L, [&](auto qc_, double v) {
+        gather27<PULL, true>(gin, c, m, L, o, [&](auto qc_, double v) {
             constexpr int Q = decltype(qc_)::value;
             g[Q] = v;
             acc_g<Q>(mg, v);
         });
     } else {
-        gather27<PULL, false>(fin, c, m, L, [&](auto qc_, double v) {
+        gather27<PULL, false>(fin, c, m, L, o, [&](auto qc_, double v) {
             constexpr int Q = decltype(qc_)::value;
             f[Q] = v;
             acc_f<Q>(mf, v);
         });
-        gather27<PULL, false>(gin, c, m, L, [&](auto qc_, double v) {
+        gather27<PULL, false>(gin, c, m, L, o, [&](auto qc_, double v) {
             constexpr int Q = decltype(qc_)::value;
             g[Q] = v;
             acc_g<Q>(mg, v);
@@ -197,27 +200,118 @@ __global__ void __launch_bounds__(128) k_collide(const double* __restrict__ fin,
     }
 
     const Coll cc = collision_coefficients(s, mf, mg, dqx, dqy, dqz, P);
-    // relax_f_to_equilibrium (LBM.cpp:799-801) + the FillBoundary of f, g that follows it (LBM.cpp:805-806)
+    // relax_f_to_equilibrium (LBM.cpp:799-801)
     static_for<0, NQ>([&](auto qc_) {
         constexpr int Q = decltype(qc_)::value;
-        fout[(long long)Q * n + c] = f[Q] = f[Q] + cc.omega * (feq_q<Q>(cc) - f[Q]);
+        fout[(long long)Q * n + c] = f[Q] + cc.omega * (feq_q<Q>(cc) - f[Q]);
     });
     static_for<0, NQ>([&](auto qc_) {
         constexpr int Q = decltype(qc_)::value;
-        gout[(long long)Q * n + c] = g[Q] = g[Q] + cc.omega * (geq_q<Q>(cc) - g[Q]);
+        gout[(long long)Q * n + c] = g[Q] + cc.omega * (geq_q<Q>(cc) - g[Q]);
     });
-    if (is_image_edge(L, i, j, k)) {
-        for_images(L, i, j, k, [&](long long d) {
-            static_for<0, NQ>([&](auto qc_) {
-                constexpr int Q = decltype(qc_)::value;
-                fout[(long long)Q * n + c + d] = f[Q];
-            });
-            static_for<0, NQ>([&](auto qc_) {
-                constexpr int Q = decltype(qc_)::value;
-                gout[(long long)Q * n + c + d] = g[Q];
-            });
-        });
+}
+
+template <bool PULL, bool MACRO>
+__global__ void __launch_bounds__(128) k_collide(const double* __restrict__ fin, const double* __restrict__ gin,
+                                                 double* __restrict__ fout, double* __restrict__ gout,
+                                                 const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ flag,
+                                                 const double* __restrict__ qc, double* __restrict__ macro,
+                                                 const __grid_constant__ Layout L, const __grid_constant__ Phys P)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.nx) return;
+    collide_cell<PULL, MACRO>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P, i, blockIdx.y, blockIdx.z);
+}
+
+// ---------------------------------------------------------------------------
+// both passes in ONE persistent launch (plain loads): a global ticket counter hands out 128-cell row
+// jobs, ticket 2n = q-correction job n, ticket 2n+1 = collide job n - LAG, slab-major order (fused.cu
+// explains the order and the completion counters).  The collide job re-reads from L2 what the
+// q-correction job of the same row pulled from HBM a few hundred tickets earlier.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_i32(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <bool MACRO>
+__global__ void __launch_bounds__(128, 2)
+    k_fused_plain(const double* __restrict__ fin, const double* __restrict__ gin, double* __restrict__ fout,
+                  double* __restrict__ gout, const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ flag,
+                  double* __restrict__ qc, double* __restrict__ macro, const __grid_constant__ Layout L,
+                  const __grid_constant__ Phys P, const __grid_constant__ FusedPlan F, int* __restrict__ counters)
+{
+    constexpr int UW = 128, NCW = 4;
+    __shared__ int s_ticket[2];
+    int* tickets = counters;
+    int* done = counters + 1;
+    const int tid = threadIdx.x;
+    int next = 0, pending = -1, it = 0;
+    if (tid == 0) next = atomicAdd(tickets, 1);
+    auto publish = [&]() {  // thread 0 only; the stores of the pending job were ordered by a __syncthreads
+        if (pending >= 0) {
+            __threadfence();
+            atomicAdd(done + pending, NCW);
+            pending = -1;
+        }
+    };
+    for (;; it ^= 1) {
+        if (tid == 0) s_ticket[it] = next;
+        __syncthreads();
+        const long long ticket = s_ticket[it];
+        if (tid == 0) next = atomicAdd(tickets, 1);  // used one job later: its latency is hidden
+        // decode (same enumeration as fused.cu)
+        int type;
+        long long jn;
+        if (F.mode == 2) {
+            type = (int)(ticket & 1);
+            jn = (ticket >> 1) - (type == 1 ? F.LAG : 0);
+        } else {
+            type = F.mode;
+            jn = ticket;
+        }
+        if (ticket >= F.total_tickets) break;
+        if (jn < 0 || jn >= F.NJ) continue;
+        const int slab = (int)(jn / F.JPS), r = (int)(jn % F.JPS);
+        const int b = slab / F.NK, kk = slab % F.NK, k = F.kq0 + kk;
+        const int row = r / F.UPR, i = (r % F.UPR) * UW + tid, j = b * F.B + row;
+        if (j >= L.ny) continue;
+        if (type == 1 && (row >= F.B || k < 0 || k >= L.nz)) continue;
+        if (type == 0) {
+            if (i < L.nx) qcorr_cell<true>(fin, gin, nbr, qc, L, P, i, j, k);
+            if (tid == 0) publish();  // an older job; this one is published one job later (its stores are
+            __syncthreads();          // still draining now, a fence here would wait for them)
+            pending = slab;
+        } else {
+            if (F.mode == 2 && tid == 0) {
+                auto target = [&](int bb) { return min(F.B + 1, L.ny - bb * F.B) * F.UPR * NCW; };
+                auto ok = [&]() {
+                    bool o = ld_acquire_i32(done + slab) >= target(b);
+                    if (o && kk > 0) o = ld_acquire_i32(done + slab - 1) >= target(b);
+                    if (o && kk < F.NK - 1) o = ld_acquire_i32(done + slab + 1) >= target(b);
+                    if (o && b > 0) o = ld_acquire_i32(done + slab - F.NK) >= target(b - 1);
+                    return o;
+                };
+                if (!ok()) {
+                    publish();
+                    const long long t0 = clock64();
+                    while (!ok()) {
+                        __nanosleep(100);
+                        if (clock64() - t0 > 4000000000LL) {
+                            printf("marbles_b200: k_fused_plain dependency wait timed out (block %d slab %d)\n", blockIdx.x, slab);
+                            __trap();
+                        }
+                    }
+                }
+            }
+            if (F.mode == 2) __syncthreads();
+            if (i < L.nx) collide_cell<true, MACRO>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P, i, j, k);
+            if (tid == 0) publish();
+        }
     }
+    if (tid == 0) publish();
 }
 
 // ---------------------------------------------------------------------------
@@ -234,21 +328,17 @@ __global__ void __launch_bounds__(128) k_stream(const double* __restrict__ fin, 
     const long long c = L.cell(i, j, k);
     const long long n = L.sq;
     const uint32_t m = nbr[c];
-    // the stores also refresh the cell's periodic images: the FillBoundary that ends LBM::stream (LBM.cpp:603)
-    for_cell_and_images(L, i, j, k, [&](long long d) {
-        if (!(m & 1u)) {
+    if (!(m & 1u)) {
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                fout[q * n + c + d] = -1.0;
-                gout[q * n + c + d] = -1.0;
-            }
-        } else {
-            gather27<true, false>(fin, c, m, L,
-                                  [&](auto qc_, double v) { fout[(long long)decltype(qc_)::value * n + c + d] = v; });
-            gather27<true, false>(gin, c, m, L,
-                                  [&](auto qc_, double v) { gout[(long long)decltype(qc_)::value * n + c + d] = v; });
+        for (int q = 0; q < NQ; ++q) {
+            fout[q * n + c] = -1.0;
+            gout[q * n + c] = -1.0;
         }
-    });
+        return;
+    }
+    const PullOffsets o = pull_offsets(L, i, j, k);
+    gather27<true, false>(fin, c, m, L, o, [&](auto qc_, double v) { fout[(long long)decltype(qc_)::value * n + c] = v; });
+    gather27<true, false>(gin, c, m, L, o, [&](auto qc_, double v) { gout[(long long)decltype(qc_)::value * n + c] = v; });
 }
 
 // f_to_macrodata on the current (already streamed) state, valid cells (LBM.cpp:810-906)
@@ -265,8 +355,9 @@ __global__ void __launch_bounds__(128) k_macrodata(const double* __restrict__ f,
     if (!(flag[c] & FLAG_FLUID)) return;
     MomF mf = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     MomG mg = {0, 0, 0, 0};
-    gather27<false, true>(f, c, 0u, L, [&](auto qc_, double v) { acc_f<decltype(qc_)::value>(mf, v); });
-    gather27<false, true>(g, c, 0u, L, [&](auto qc_, double v) { acc_g<decltype(qc_)::value>(mg, v); });
+    const PullOffsets o = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    gather27<false, true>(f, c, 0u, L, o, [&](auto qc_, double v) { acc_f<decltype(qc_)::value>(mf, v); });
+    gather27<false, true>(g, c, 0u, L, o, [&](auto qc_, double v) { acc_g<decltype(qc_)::value>(mg, v); });
     const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
     macro[0 * n + c] = s.rho;
     macro[1 * n + c] = s.u;
@@ -916,6 +1007,21 @@ int launch_collide(const Layout& L, const Phys& P, const double* fin, const doub
         else
             k_collide<false, false><<<grid, bx, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P);
     }
+    return 1;
+}
+
+int launch_fused_plain(const Layout& L, const Phys& P, int band_rows, int lag_per_cta, int mode, int sm_count,
+                       const double* fin, const double* gin, double* fout, double* gout, const uint32_t* nbr,
+                       const uint8_t* flag, double* qc, double* macro, int* counters, cudaStream_t st)
+{
+    const int grid = 2 * sm_count;
+    const FusedPlan F = make_fused_plan(L, 128, band_rows, mode, grid, lag_per_cta);
+    const size_t ints = mode == 1 ? 1 : 1 + (size_t)F.NB * F.NK;
+    cudaMemsetAsync(counters, 0, ints * sizeof(int), st);
+    if (macro)
+        k_fused_plain<true><<<grid, 128, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P, F, counters);
+    else
+        k_fused_plain<false><<<grid, 128, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P, F, counters);
     return 1;
 }
 

@@ -80,6 +80,10 @@ int launch_fused(const Layout& L, const Phys& P, int uw, int band_rows, int lag_
                  const double* fin, const double* gin, double* fout, double* gout, const uint32_t* nbr,
                  const uint8_t* flag, double* qc, double* macro, int* counters, cudaStream_t st);
 
+int launch_fused_plain(const Layout& L, const Phys& P, int band_rows, int lag_per_cta, int mode, int sm_count,
+                       const double* fin, const double* gin, double* fout, double* gout, const uint32_t* nbr,
+                       const uint8_t* flag, double* qc, double* macro, int* counters, cudaStream_t st);
+
 int launch_halo_pack(const Layout& L, const double* f, const double* g, int side, double* buf, cudaStream_t st);
 int launch_halo_unpack(const Layout& L, double* f, double* g, int side, const double* buf, cudaStream_t st);
 

@@ -70,7 +70,8 @@ struct Layout {
     int lo[3];        // global index of local cell (0,0,0)
     int dlo[3], dhi[3];  // level domain
     long long px, sz, sq; // row pitch, plane stride, component stride (doubles)
-    int img[3];       // direction is periodic AND the box spans it: stores keep the ghost images current
+    int wrap[3];      // the kernels wrap source indices in this direction themselves (set only when every
+                      // direction is periodic: then no ghost cell of the box is ever read)
     __host__ __device__ long long cell(int i, int j, int k) const
     {
         return (long long)(i + OX) + (long long)(j + GY) * px + (long long)(k + GZ) * sz;
@@ -93,45 +94,29 @@ inline Layout make_layout(const int lo[3], const int hi[3], const int dlo[3], co
     L.px = ((long long)(L.nx + OX + GX) + 15) / 16 * 16;
     L.sz = L.px * (L.ny + 2 * GY);
     L.sq = L.sz * (L.nz + 2 * GZ);
-    L.img[0] = L.img[1] = L.img[2] = 0;
+    L.wrap[0] = L.wrap[1] = L.wrap[2] = 0;
     return L;
 }
 
-// Periodic images of a valid cell inside the padded box.  The reference refreshes ghost cells with
-// FillBoundary after every stream and relax (LBM.cpp:603, 805-806); here the kernel that produces a
-// value also stores it to the cell's periodic images, so no separate ghost pass touches the state.
-// body(delta) is called for the cell itself (delta 0) and for each image (offset in doubles).
-__device__ __forceinline__ bool is_image_edge(const Layout& L, int i, int j, int k)
+// Offsets (in doubles) from a cell to the cell one step back along each axis, for e = -1, 0, +1
+// (index e + 1): the pull source of direction q is  c + xo[ex+1] + yo[ey+1] + zo[ez+1].  Without wrap
+// these are -e, -e*px, -e*sz (the neighbour may be a ghost cell filled by the ghost kernels); with wrap
+// the first / last cell of a periodic direction reads the opposite end of the box instead, which is what
+// the reference's FillBoundary would have copied into that ghost cell (LBM.cpp:603, 805-806).
+struct PullOffsets {
+    long long xo[3], yo[3], zo[3];
+};
+__device__ __forceinline__ PullOffsets pull_offsets(const Layout& L, int i, int j, int k)
 {
-    return (L.img[0] && (i < GX || i >= L.nx - GX)) || (L.img[1] && (j < GY || j >= L.ny - GY)) ||
-           (L.img[2] && (k < GZ || k >= L.nz - GZ));
-}
-// 45 candidates (mx, my, mz) in {-1,0,1} x {-1,0,1} x {-2..2}; t = 22 is the cell itself
-template <typename F>
-__device__ __forceinline__ void for_image_range(const Layout& L, int i, int j, int k, int t0, int t1, bool skip_self, F&& body)
-{
-#pragma unroll 1
-    for (int t = t0; t < t1; ++t) {
-        if (skip_self && t == 22) continue;
-        const int mx = t % 3 - 1, my = (t / 3) % 3 - 1, mz = t / 9 - 2;
-        if ((mx != 0 && !L.img[0]) || (my != 0 && !L.img[1]) || (mz != 0 && !L.img[2])) continue;
-        const int ii = i + mx * L.nx, jj = j + my * L.ny, kk = k + mz * L.nz;
-        if (ii < -GX || ii > L.nx - 1 + GX || jj < -GY || jj > L.ny - 1 + GY || kk < -GZ || kk > L.nz - 1 + GZ) continue;
-        body((long long)mx * L.nx + (long long)my * L.ny * L.px + (long long)mz * L.nz * L.sz);
-    }
-}
-// the cell itself (delta 0) and its images
-template <typename F>
-__device__ __forceinline__ void for_cell_and_images(const Layout& L, int i, int j, int k, F&& body)
-{
-    const bool edge = is_image_edge(L, i, j, k);
-    for_image_range(L, i, j, k, edge ? 0 : 22, edge ? 45 : 23, false, body);
-}
-// the images only (call for edge cells)
-template <typename F>
-__device__ __forceinline__ void for_images(const Layout& L, int i, int j, int k, F&& body)
-{
-    for_image_range(L, i, j, k, 0, 45, true, body);
+    PullOffsets o;
+    o.xo[1] = o.yo[1] = o.zo[1] = 0;
+    o.xo[2] = (L.wrap[0] && i == 0) ? (long long)(L.nx - 1) : -1LL;           // e = +1: source i - 1
+    o.xo[0] = (L.wrap[0] && i == L.nx - 1) ? -(long long)(L.nx - 1) : 1LL;    // e = -1: source i + 1
+    o.yo[2] = ((L.wrap[1] && j == 0) ? (long long)(L.ny - 1) : -1LL) * L.px;
+    o.yo[0] = ((L.wrap[1] && j == L.ny - 1) ? -(long long)(L.ny - 1) : 1LL) * L.px;
+    o.zo[2] = ((L.wrap[2] && k == 0) ? (long long)(L.nz - 1) : -1LL) * L.sz;
+    o.zo[0] = ((L.wrap[2] && k == L.nz - 1) ? -(long long)(L.nz - 1) : 1LL) * L.sz;
+    return o;
 }
 
 struct Phys {

@@ -26,7 +26,7 @@ def new_lbm(deck_text, is_fluid=None, overrides=None, variant=None):
 
 # fused: mbl_step with the persistent TMA kernel (variant 1, the default), its two job types as two
 # launches (2), or the two plain kernels (0); unfused: the reference-granular operator sequence
-@pytest.mark.parametrize("fused", [1, 2, 0, None], ids=["fused-tma", "twopass-tma", "twopass-plain", "unfused"])
+@pytest.mark.parametrize("fused", [1, 2, 3, 0, None], ids=["fused-tma", "twopass-tma", "fused-plain", "twopass-plain", "unfused"])
 @pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_cuda_vs_reference_golden(case, fused):
     z, deck_text, steps = load_golden(case)
