@@ -270,10 +270,11 @@ def main():
     peak, peak_src = measured_peak_gbs()
     collide_ms = kms[2] / max(nrec.value, 1)
     kname = {0: "k_collide<pull>", 1: "k_fused (q-correction + collide jobs)", 2: "k_fused (collide jobs)",
-             3: "k_fused_plain (q-correction + collide jobs)"}[args.variant]
+             3: "k_fused_plain (q-correction + collide jobs)", 4: "k_collide_pipe"}[args.variant]
     vname = {0: "two plain kernels (q-correction, collide)", 1: "one persistent TMA-pipelined kernel per step",
              2: "persistent TMA kernel, two launches (q-correction, collide)",
-             3: "one persistent kernel per step, plain loads"}[args.variant]
+             3: "one persistent kernel per step, plain loads",
+             4: "k_qcorr + software-pipelined persistent collide (cp.async double buffer)"}[args.variant]
     achieved = BYTES_PER_CELL * lbm.ncells / (collide_ms * 1e-3) / 1e9
     traffic = None
     try:

@@ -164,6 +164,11 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
         mark();
         ctx->launches += launch_fused(Lk, lv.P, ctx->uw, ctx->band_rows, ctx->lag_per_cta, 1, ctx->sm_count, lv.p.f[a],
                                       lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, macro, lv.counters, st);
+    } else if (ctx->variant == 4) {
+        ctx->launches += launch_qcorr(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st);
+        mark();
+        ctx->launches += launch_collide_pipe(Lk, lv.P, ctx->sm_count, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr,
+                                             lv.p.flag, lv.p.qc, macro, st);
     } else if (ctx->variant == 3) {
         mark();  // no separate q-correction pass
         ctx->launches += launch_fused_plain(Lk, lv.P, ctx->band_rows, ctx->lag_per_cta, 2, ctx->sm_count, lv.p.f[a],
@@ -637,7 +642,7 @@ int mbl_get_timing(mbl_ctx* ctx, double ms[3], int* nsteps)
 int mbl_set_variant(mbl_ctx* ctx, int variant)
 {
     if (!ctx) return fail("null context");
-    if (variant < 0 || variant > 3) return fail("variant %d is not available", variant);
+    if (variant < 0 || variant > 4) return fail("variant %d is not available", variant);
     ctx->variant = variant;
     return 0;
 }

@@ -14,6 +14,7 @@
 #include "kernels.cuh"
 
 #include <cstdio>
+#include <cuda_pipeline.h>
 
 namespace mbl {
 
@@ -69,13 +70,14 @@ __device__ __forceinline__ void qcorr_cell(const double* __restrict__ fin, const
                                            const Phys& P, int i, int j, int k)
 {
     const long long c = L.cell(i, j, k);
+    const long long n = L.sq;
+    // 40 registers -> 12 CTAs per SM: here occupancy hides the mask -> pull dependency (ncu: 6.5 TB/s)
     const uint32_t m = nbr[c];
     if (!(m & 1u)) return;
+    const PullOffsets o = pull_offsets(L, i, j, k);
     MomL ml = {0.0, 0.0, 0.0, 0.0};
     double e2 = 0.0;
-    const PullOffsets o = pull_offsets(L, i, j, k);
-    const bool fast = __all_sync(__activemask(), m == ALL_FLUID);
-    if (fast) {
+    if (__all_sync(__activemask(), m == ALL_FLUID)) {
         gather27<PULL, true>(fin, c, m, L, o, [&](auto qc_, double v) { acc_l<decltype(qc_)::value>(ml, v); });
         gather27<PULL, true>(gin, c, m, L, o, [&](auto, double v) { e2 += v; });
     } else {
@@ -83,7 +85,6 @@ __device__ __forceinline__ void qcorr_cell(const double* __restrict__ fin, const
         gather27<PULL, false>(gin, c, m, L, o, [&](auto, double v) { e2 += v; });
     }
     const Prim s = primitives(ml.rho, ml.jx, ml.jy, ml.jz, e2, P);
-    const long long n = L.sq;
     qc[c] = s.qcx;
     qc[n + c] = s.qcy;
     qc[2 * n + c] = s.qcz;
@@ -111,7 +112,20 @@ __device__ __forceinline__ void collide_cell(const double* __restrict__ fin, con
 {
     const long long c = L.cell(i, j, k);
     const long long n = L.sq;
+    // Every load of the cell is issued before anything is waited for (ncu showed four dependent global
+    // latencies per cell -- mask, populations, flag byte, neighbour q-corrections -- costing 64 % of the
+    // kernel): the mask, the flag byte, the six neighbour q-corrections (always inside the padded box;
+    // unusable ones are discarded by the flag bits afterwards) and, speculatively, the 54 all-fluid pulls;
+    // directions whose source turns out to be solid are patched.
     const uint32_t m = nbr[c];
+    const unsigned fb = flag[c];
+    const double qxp = qc[c + 1], qxm = qc[c - 1];
+    const double qyp = qc[n + c + L.px], qym = qc[n + c - L.px];
+    const double qzp = qc[2 * n + c + L.sz], qzm = qc[2 * n + c - L.sz];
+    const PullOffsets o = pull_offsets(L, i, j, k);
+    double f[NQ], g[NQ];
+    gather27<PULL, true>(fin, c, ALL_FLUID, L, o, [&](auto qc_, double v) { f[decltype(qc_)::value] = v; });
+    gather27<PULL, true>(gin, c, ALL_FLUID, L, o, [&](auto qc_, double v) { g[decltype(qc_)::value] = v; });
     if (!(m & 1u)) {
         // solid cell: the streamed value is the -1 sentinel (LBM.cpp:565, 582); collide skips it
         if constexpr (PULL) {
@@ -123,54 +137,37 @@ __device__ __forceinline__ void collide_cell(const double* __restrict__ fin, con
         }
         return;
     }
-    double f[NQ], g[NQ];
+    if constexpr (PULL) {
+        if (m != ALL_FLUID) {
+            // halfway bounce-back: the cell's own opposite population (LBM.cpp:590-595 in pull form)
+            static_for<1, NQ>([&](auto qc_) {
+                constexpr int Q = decltype(qc_)::value;
+                if (!((m >> Q) & 1u)) {
+                    f[Q] = fin[(long long)opp(Q) * n + c];
+                    g[Q] = gin[(long long)opp(Q) * n + c];
+                }
+            });
+        }
+    }
     MomF mf = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     MomG mg = {0, 0, 0, 0};
-    const PullOffsets o = pull_offsets(L, i, j, k);
-    const bool fast = __all_sync(__activemask(), m == ALL_FLUID);
-    if (fast) {
-        gather27<PULL, true>(fin, c, m, L, o, [&](auto qc_, double v) {
-            constexpr int Q = decltype(qc_)::value;
-            f[Q] = v;
-            acc_f<Q>(mf, v);
-        });
-        gather27<PULL, true>(gin, c, m, L, o, [&](auto qc_, double v) {
-            constexpr int Q = decltype(qc_)::value;
-            g[Q] = v;
-            acc_g<Q>(mg, v);
-        });
-    } else {
-        gather27<PULL, false>(fin, c, m, L, o, [&](auto qc_, double v) {
-            constexpr int Q = decltype(qc_)::value;
-            f[Q] = v;
-            acc_f<Q>(mf, v);
-        });
-        gather27<PULL, false>(gin, c, m, L, o, [&](auto qc_, double v) {
-            constexpr int Q = decltype(qc_)::value;
-            g[Q] = v;
-            acc_g<Q>(mg, v);
-        });
-    }
+    static_for<0, NQ>([&](auto qc_) {
+        constexpr int Q = decltype(qc_)::value;
+        acc_f<Q>(mf, f[Q]);
+    });
+    static_for<0, NQ>([&](auto qc_) {
+        constexpr int Q = decltype(qc_)::value;
+        acc_g<Q>(mg, g[Q]);
+    });
     const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
 
     // grad of the q-correction (LBM.cpp:959-991, Utilities.H:279-312)
-    const unsigned fb = flag[c];
-    double dqx, dqy, dqz;
-    {
-        const bool okp = fb & GRAD_PX, okm = fb & GRAD_MX;
-        const double dp = okp ? qc[c + 1] : 0.0, dm = okm ? qc[c - 1] : 0.0;
-        dqx = one_sided_gradient(okp, okm, dp, s.qcx, dm, P.idx[0]);
-    }
-    {
-        const bool okp = fb & GRAD_PY, okm = fb & GRAD_MY;
-        const double dp = okp ? qc[n + c + L.px] : 0.0, dm = okm ? qc[n + c - L.px] : 0.0;
-        dqy = one_sided_gradient(okp, okm, dp, s.qcy, dm, P.idx[1]);
-    }
-    {
-        const bool okp = fb & GRAD_PZ, okm = fb & GRAD_MZ;
-        const double dp = okp ? qc[2 * n + c + L.sz] : 0.0, dm = okm ? qc[2 * n + c - L.sz] : 0.0;
-        dqz = one_sided_gradient(okp, okm, dp, s.qcz, dm, P.idx[2]);
-    }
+    const double dqx = one_sided_gradient(fb & GRAD_PX, fb & GRAD_MX, (fb & GRAD_PX) ? qxp : 0.0, s.qcx,
+                                          (fb & GRAD_MX) ? qxm : 0.0, P.idx[0]);
+    const double dqy = one_sided_gradient(fb & GRAD_PY, fb & GRAD_MY, (fb & GRAD_PY) ? qyp : 0.0, s.qcy,
+                                          (fb & GRAD_MY) ? qym : 0.0, P.idx[1]);
+    const double dqz = one_sided_gradient(fb & GRAD_PZ, fb & GRAD_MZ, (fb & GRAD_PZ) ? qzp : 0.0, s.qcz,
+                                          (fb & GRAD_MZ) ? qzm : 0.0, P.idx[2]);
 
     if constexpr (MACRO) {
         // m_macrodata of the post-stream state (Constants.H:8-31, LBM.cpp:867-901)
@@ -212,7 +209,7 @@ __device__ __forceinline__ void collide_cell(const double* __restrict__ fin, con
 }
 
 template <bool PULL, bool MACRO>
-__global__ void __launch_bounds__(128) k_collide(const double* __restrict__ fin, const double* __restrict__ gin,
+__global__ void __launch_bounds__(128, 3) k_collide(const double* __restrict__ fin, const double* __restrict__ gin,
                                                  double* __restrict__ fout, double* __restrict__ gout,
                                                  const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ flag,
                                                  const double* __restrict__ qc, double* __restrict__ macro,
@@ -221,6 +218,151 @@ __global__ void __launch_bounds__(128) k_collide(const double* __restrict__ fin,
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= L.nx) return;
     collide_cell<PULL, MACRO>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P, i, blockIdx.y, blockIdx.z);
+}
+
+// ---------------------------------------------------------------------------
+// pass 2 as a software-pipelined persistent kernel.  k_collide keeps the 54 populations of a cell in
+// registers (180 registers -> 8 warps per SM) and alternates load / compute / store phases, so HBM sees
+// loads in flight only part of the time (ncu: 4.4 TB/s, long-scoreboard bound).  Here every thread owns a
+// private column of shared memory per buffer; while it collides job n out of buffer n&1 the 54 pulls of
+// job n+1 are already in flight into the other buffer (cp.async, no destination registers).  No barrier
+// is needed anywhere: columns are thread-private, completion is the thread's own cp.async group.
+// ---------------------------------------------------------------------------
+constexpr int PIPE_THREADS = 128;
+constexpr int PIPE_ROWS = 2 * NQ;                                          // f then g
+constexpr size_t PIPE_SMEM = 2 * PIPE_ROWS * PIPE_THREADS * sizeof(double);  // two buffers
+
+struct PipeJob {
+    int i, j, k;
+    long long c;
+    bool in_row;
+};
+
+template <bool MACRO>
+__global__ void __launch_bounds__(PIPE_THREADS, 2)
+    k_collide_pipe(const double* __restrict__ fin, const double* __restrict__ gin, double* __restrict__ fout,
+                   double* __restrict__ gout, const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ flag,
+                   const double* __restrict__ qc, double* __restrict__ macro, const __grid_constant__ Layout L,
+                   const __grid_constant__ Phys P, long long njobs, int upr)
+{
+    extern __shared__ double s_cols[];
+    const int tid = threadIdx.x;
+    const long long n = L.sq;
+    auto job_of = [&](long long id) {
+        PipeJob J;
+        const int seg = (int)(id % upr);
+        const long long row = id / upr;
+        J.j = (int)(row % L.ny);
+        J.k = (int)(row / L.ny);
+        J.i = seg * PIPE_THREADS + tid;
+        J.in_row = id < njobs && J.i < L.nx;
+        J.c = L.cell(J.in_row ? J.i : 0, J.j, J.k);
+        return J;
+    };
+    // start the 54 pulls of a job into buffer `buf`
+    auto issue = [&](const PipeJob& J, uint32_t m, int buf) {
+        double* col = s_cols + (size_t)buf * PIPE_ROWS * PIPE_THREADS + tid;
+        if (J.in_row && (m & 1u)) {
+            const PullOffsets o = pull_offsets(L, J.i, J.j, J.k);
+            static_for<0, NQ>([&](auto qc_) {
+                constexpr int Q = decltype(qc_)::value;
+                long long a = (long long)Q * n + J.c + (o.xo[ex(Q) + 1] + o.yo[ey(Q) + 1] + o.zo[ez(Q) + 1]);
+                if (!((m >> Q) & 1u)) a = (long long)opp(Q) * n + J.c;  // halfway bounce-back (LBM.cpp:590-595)
+                __pipeline_memcpy_async(col + Q * PIPE_THREADS, fin + a, sizeof(double));
+                __pipeline_memcpy_async(col + (NQ + Q) * PIPE_THREADS, gin + a, sizeof(double));
+            });
+        }
+        __pipeline_commit();
+    };
+    const long long stride = gridDim.x;
+    long long id = blockIdx.x;
+    PipeJob cur = job_of(id), nxt = job_of(id + stride);
+    uint32_t m_cur = cur.in_row ? nbr[cur.c] : 0u;
+    uint32_t m_nxt = nxt.in_row ? nbr[nxt.c] : 0u;
+    issue(cur, m_cur, 0);
+    for (int buf = 0; id < njobs; id += stride, buf ^= 1) {
+        // next job's pulls go out before this job's arithmetic starts; the mask of the job after next is
+        // fetched now so that it is in a register when that job is issued
+        issue(nxt, m_nxt, buf ^ 1);
+        const PipeJob nn = job_of(id + 2 * stride);
+        const uint32_t m_nn = nn.in_row ? nbr[nn.c] : 0u;
+        if (cur.in_row) {
+            const long long c = cur.c;
+            if (!(m_cur & 1u)) {
+                // solid cell: the streamed value is the -1 sentinel (LBM.cpp:565, 582); collide skips it
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    fout[q * n + c] = -1.0;
+                    gout[q * n + c] = -1.0;
+                }
+            } else {
+                // neighbours' q-corrections (LBM.cpp:959-991): loads overlap the moment sums below
+                const unsigned fb = flag[c];
+                const bool xp = fb & GRAD_PX, xm = fb & GRAD_MX, yp = fb & GRAD_PY, ym = fb & GRAD_MY, zp = fb & GRAD_PZ,
+                           zm = fb & GRAD_MZ;
+                const double qxp = xp ? qc[c + 1] : 0.0, qxm = xm ? qc[c - 1] : 0.0;
+                const double qyp = yp ? qc[n + c + L.px] : 0.0, qym = ym ? qc[n + c - L.px] : 0.0;
+                const double qzp = zp ? qc[2 * n + c + L.sz] : 0.0, qzm = zm ? qc[2 * n + c - L.sz] : 0.0;
+                __pipeline_wait_prior(1);  // this job's group; the next job's stays in flight
+                const double* col = s_cols + (size_t)buf * PIPE_ROWS * PIPE_THREADS + tid;
+                MomF mf = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                MomG mg = {0, 0, 0, 0};
+                static_for<0, NQ>([&](auto qc_) {
+                    constexpr int Q = decltype(qc_)::value;
+                    acc_f<Q>(mf, col[Q * PIPE_THREADS]);
+                });
+                static_for<0, NQ>([&](auto qc_) {
+                    constexpr int Q = decltype(qc_)::value;
+                    acc_g<Q>(mg, col[(NQ + Q) * PIPE_THREADS]);
+                });
+                const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
+                const double dqx = one_sided_gradient(xp, xm, qxp, s.qcx, qxm, P.idx[0]);
+                const double dqy = one_sided_gradient(yp, ym, qyp, s.qcy, qym, P.idx[1]);
+                const double dqz = one_sided_gradient(zp, zm, qzp, s.qcz, qzm, P.idx[2]);
+                if constexpr (MACRO) {
+                    // m_macrodata of the post-stream state (Constants.H:8-31, LBM.cpp:867-901)
+                    macro[0 * n + c] = s.rho;
+                    macro[1 * n + c] = s.u;
+                    macro[2 * n + c] = s.v;
+                    macro[3 * n + c] = s.w;
+                    macro[4 * n + c] = sqrt(s.u * s.u + s.v * s.v + s.w * s.w);
+                    macro[5 * n + c] = mg.e2;
+                    macro[6 * n + c] = s.qcx;
+                    macro[7 * n + c] = s.qcy;
+                    macro[8 * n + c] = s.qcz;
+                    macro[9 * n + c] = mf.pxx;
+                    macro[10 * n + c] = mf.pyy;
+                    macro[11 * n + c] = mf.pzz;
+                    macro[12 * n + c] = mf.pxy;
+                    macro[13 * n + c] = mf.pxz;
+                    macro[14 * n + c] = mf.pyz;
+                    macro[15 * n + c] = mg.qx;
+                    macro[16 * n + c] = mg.qy;
+                    macro[17 * n + c] = mg.qz;
+                    macro[18 * n + c] = s.T;
+                    macro[23 * n + c] = dqx;
+                    macro[24 * n + c] = dqy;
+                    macro[25 * n + c] = dqz;
+                }
+                const Coll cc = collision_coefficients(s, mf, mg, dqx, dqy, dqz, P);
+                // relax_f_to_equilibrium (LBM.cpp:799-801)
+                static_for<0, NQ>([&](auto qc_) {
+                    constexpr int Q = decltype(qc_)::value;
+                    const double fq = col[Q * PIPE_THREADS];
+                    fout[(long long)Q * n + c] = fq + cc.omega * (feq_q<Q>(cc) - fq);
+                });
+                static_for<0, NQ>([&](auto qc_) {
+                    constexpr int Q = decltype(qc_)::value;
+                    const double gq = col[(NQ + Q) * PIPE_THREADS];
+                    gout[(long long)Q * n + c] = gq + cc.omega * (geq_q<Q>(cc) - gq);
+                });
+            }
+        }
+        __pipeline_wait_prior(1);  // threads that skipped the arithmetic still retire this job's group
+        cur = nxt, m_cur = m_nxt;
+        nxt = nn, m_nxt = m_nn;
+    }
+    __pipeline_wait_prior(0);
 }
 
 // ---------------------------------------------------------------------------
@@ -1007,6 +1149,26 @@ int launch_collide(const Layout& L, const Phys& P, const double* fin, const doub
         else
             k_collide<false, false><<<grid, bx, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P);
     }
+    return 1;
+}
+
+int launch_collide_pipe(const Layout& L, const Phys& P, int sm_count, const double* fin, const double* gin, double* fout,
+                        double* gout, const uint32_t* nbr, const uint8_t* flag, const double* qc, double* macro,
+                        cudaStream_t st)
+{
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_collide_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM);
+        cudaFuncSetAttribute(k_collide_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM);
+        attr = true;
+    }
+    const int upr = (L.nx + PIPE_THREADS - 1) / PIPE_THREADS;
+    const long long njobs = (long long)upr * L.ny * L.nz;
+    const int grid = (int)(njobs < 2LL * sm_count ? njobs : 2LL * sm_count);
+    if (macro)
+        k_collide_pipe<true><<<grid, PIPE_THREADS, PIPE_SMEM, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P, njobs, upr);
+    else
+        k_collide_pipe<false><<<grid, PIPE_THREADS, PIPE_SMEM, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P, njobs, upr);
     return 1;
 }
 
