@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--variant", type=int, default=1, help="1 fused persistent TMA kernel, 2 same as two launches, 0 two plain kernels")
+    ap.add_argument("--variant", type=int, default=0, help="0 two kernels (default), 1 fused persistent TMA kernel, 2 same as two launches, 3 fused persistent plain-load kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -185,9 +185,11 @@ int64_t mbl_launch_count(mbl_ctx* ctx);
  * *nsteps steps recorded since the last call (bench.py roofline) */
 int mbl_set_timing(mbl_ctx* ctx, int on);
 int mbl_get_timing(mbl_ctx* ctx, double ms[3], int* nsteps);
-/* select the implementation of mbl_step: 1 (default) = ONE persistent kernel per level (bulk-TMA staged
- * pulls; q-correction jobs and collide jobs interleaved so the second touch of a population is an L2
- * hit); 2 = the same job types as two launches; 0 = two plain kernels (k_qcorr, k_collide) */
+/* select the implementation of mbl_step: 0 (default) = two kernels, k_qcorr (q-corrections of the
+ * post-stream state) then k_collide (pull + collide); 1 = ONE persistent kernel per level with bulk-TMA
+ * staged pulls, q-correction jobs and collide jobs interleaved; 2 = the same kernel launched once per job
+ * type; 3 = one persistent warp-autonomous kernel with plain loads.  All give the same results; 0 is the
+ * fastest measured on B200. */
 int mbl_set_variant(mbl_ctx* ctx, int variant);
 
 #ifdef __cplusplus

@@ -66,9 +66,11 @@ struct mbl_ctx {
     cudaStream_t stream = nullptr;
     Level lev[MAX_LEVELS];
     int64_t launches = 0;
-    int variant = 1;   // 0: two kernels (k_qcorr, k_collide); 1: fused persistent TMA kernel; 2: its two job
-                       // types as two launches
-    int uw = 128, band_rows = 16, lag_per_cta = 3;  // fused kernel tuning (MBL_UW / MBL_BAND / MBL_LAG)
+    // implementation of mbl_step: 0 (default, fastest measured): two kernels, k_qcorr + k_collide;
+    // 1: persistent TMA-pipelined kernel with both job types; 2: the same kernel, one launch per job type;
+    // 3: persistent warp-autonomous kernel (plain loads) with both job types.  DESIGN.md has the numbers.
+    int variant = 0;
+    int uw = 128, band_rows = 16, lag_per_cta = 4;  // variants 1-3 tuning (MBL_UW / MBL_BAND / MBL_LAG)
     int sm_count = 148;
     bool timing = false;
     std::vector<cudaEvent_t> events;  // 4 per timed step: before ghost fill, q-corr, collide, after
@@ -164,11 +166,6 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
         mark();
         ctx->launches += launch_fused(Lk, lv.P, ctx->uw, ctx->band_rows, ctx->lag_per_cta, 1, ctx->sm_count, lv.p.f[a],
                                       lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, macro, lv.counters, st);
-    } else if (ctx->variant == 4) {
-        ctx->launches += launch_qcorr(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st);
-        mark();
-        ctx->launches += launch_collide_pipe(Lk, lv.P, ctx->sm_count, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr,
-                                             lv.p.flag, lv.p.qc, macro, st);
     } else if (ctx->variant == 3) {
         mark();  // no separate q-correction pass
         ctx->launches += launch_fused_plain(Lk, lv.P, ctx->band_rows, ctx->lag_per_cta, 2, ctx->sm_count, lv.p.f[a],
@@ -215,7 +212,7 @@ int mbl_create(const mbl_params* params, int device, mbl_ctx** out)
     if (const char* e = getenv("MBL_VARIANT")) c->variant = atoi(e);
     if (const char* e = getenv("MBL_UW")) c->uw = atoi(e) == 256 ? 256 : 128;
     if (const char* e = getenv("MBL_BAND")) c->band_rows = atoi(e) > 0 ? atoi(e) : 16;
-    if (const char* e = getenv("MBL_LAG")) c->lag_per_cta = atoi(e) > 0 ? atoi(e) : 3;
+    if (const char* e = getenv("MBL_LAG")) c->lag_per_cta = atoi(e) > 0 ? atoi(e) : 4;
     init_tables();
     CU(cudaGetLastError());
     *out = c;
@@ -642,7 +639,7 @@ int mbl_get_timing(mbl_ctx* ctx, double ms[3], int* nsteps)
 int mbl_set_variant(mbl_ctx* ctx, int variant)
 {
     if (!ctx) return fail("null context");
-    if (variant < 0 || variant > 4) return fail("variant %d is not available", variant);
+    if (variant < 0 || variant > 3) return fail("variant %d is not available", variant);
     ctx->variant = variant;
     return 0;
 }

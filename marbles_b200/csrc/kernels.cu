@@ -14,7 +14,6 @@
 #include "kernels.cuh"
 
 #include <cstdio>
-#include <cuda_pipeline.h>
 
 namespace mbl {
 
@@ -38,24 +37,56 @@ void init_tables()
 // ---------------------------------------------------------------------------
 // pull of one lattice (all 27 directions) for cell c
 // ---------------------------------------------------------------------------
-template <bool PULL, bool FAST, typename F>
+// L2 eviction-priority hints (createpolicy + ld/st .L2::cache_hint).  The fused kernel touches every
+// population twice: the q-correction job's pull should stay in L2 (HINT_KEEP) until the collide job of the
+// same row re-reads it (HINT_LAST: last use) and the collide job's stores must not push it out.
+constexpr int HINT_NONE = 0, HINT_KEEP = 1, HINT_LAST = 2;
+__device__ __forceinline__ uint64_t make_policy(int hint)
+{
+    uint64_t p = 0;
+    if (hint == HINT_KEEP) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    if (hint == HINT_LAST) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+template <int HINT>
+__device__ __forceinline__ double ld_hint(const double* p, uint64_t pol)
+{
+    if constexpr (HINT == HINT_NONE) {
+        return *p;
+    } else {
+        double v;
+        asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+        return v;
+    }
+}
+template <int HINT>
+__device__ __forceinline__ void st_hint(double* p, double v, uint64_t pol)
+{
+    if constexpr (HINT == HINT_NONE) {
+        *p = v;
+    } else {
+        asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+    }
+}
+
+template <bool PULL, bool FAST, int HINT = HINT_NONE, typename F>
 __device__ __forceinline__ void gather27(const double* __restrict__ in, long long c, uint32_t m, const Layout& L,
-                                         const PullOffsets& o, F&& sink)
+                                         const PullOffsets& o, F&& sink, uint64_t pol = 0)
 {
     static_for<0, NQ>([&](auto qc) {
         constexpr int Q = decltype(qc)::value;
         double v;
         if constexpr (!PULL) {
-            v = in[(long long)Q * L.sq + c];
+            v = ld_hint<HINT>(in + (long long)Q * L.sq + c, pol);
         } else if constexpr (FAST) {
-            v = in[(long long)Q * L.sq + c + (o.xo[ex(Q) + 1] + o.yo[ey(Q) + 1] + o.zo[ez(Q) + 1])];
+            v = ld_hint<HINT>(in + (long long)Q * L.sq + c + (o.xo[ex(Q) + 1] + o.yo[ey(Q) + 1] + o.zo[ez(Q) + 1]), pol);
         } else {
             // fluid source: take its population; solid source: halfway bounce-back of the
             // cell's own opposite population (LBM.cpp:590-595 in pull form)
             const bool fl = (m >> Q) & 1u;
             const long long a = (long long)Q * L.sq + c + (o.xo[ex(Q) + 1] + o.yo[ey(Q) + 1] + o.zo[ez(Q) + 1]);
             const long long b = (long long)opp(Q) * L.sq + c;
-            v = in[fl ? a : b];
+            v = ld_hint<HINT>(in + (fl ? a : b), pol);
         }
         sink(qc, v);
     });
@@ -64,10 +95,10 @@ __device__ __forceinline__ void gather27(const double* __restrict__ in, long lon
 // ---------------------------------------------------------------------------
 // pass 1: q-corrections of the post-stream state of one cell
 // ---------------------------------------------------------------------------
-template <bool PULL>
+template <bool PULL, int HINT = HINT_NONE>
 __device__ __forceinline__ void qcorr_cell(const double* __restrict__ fin, const double* __restrict__ gin,
                                            const uint32_t* __restrict__ nbr, double* __restrict__ qc, const Layout& L,
-                                           const Phys& P, int i, int j, int k)
+                                           const Phys& P, int i, int j, int k, uint64_t pol = 0)
 {
     const long long c = L.cell(i, j, k);
     const long long n = L.sq;
@@ -78,11 +109,11 @@ __device__ __forceinline__ void qcorr_cell(const double* __restrict__ fin, const
     MomL ml = {0.0, 0.0, 0.0, 0.0};
     double e2 = 0.0;
     if (__all_sync(__activemask(), m == ALL_FLUID)) {
-        gather27<PULL, true>(fin, c, m, L, o, [&](auto qc_, double v) { acc_l<decltype(qc_)::value>(ml, v); });
-        gather27<PULL, true>(gin, c, m, L, o, [&](auto, double v) { e2 += v; });
+        gather27<PULL, true, HINT>(fin, c, m, L, o, [&](auto qc_, double v) { acc_l<decltype(qc_)::value>(ml, v); }, pol);
+        gather27<PULL, true, HINT>(gin, c, m, L, o, [&](auto, double v) { e2 += v; }, pol);
     } else {
-        gather27<PULL, false>(fin, c, m, L, o, [&](auto qc_, double v) { acc_l<decltype(qc_)::value>(ml, v); });
-        gather27<PULL, false>(gin, c, m, L, o, [&](auto, double v) { e2 += v; });
+        gather27<PULL, false, HINT>(fin, c, m, L, o, [&](auto qc_, double v) { acc_l<decltype(qc_)::value>(ml, v); }, pol);
+        gather27<PULL, false, HINT>(gin, c, m, L, o, [&](auto, double v) { e2 += v; }, pol);
     }
     const Prim s = primitives(ml.rho, ml.jx, ml.jy, ml.jz, e2, P);
     qc[c] = s.qcx;
@@ -103,12 +134,12 @@ __global__ void __launch_bounds__(128) k_qcorr(const double* __restrict__ fin, c
 // ---------------------------------------------------------------------------
 // pass 2: (pull +) collide of one cell
 // ---------------------------------------------------------------------------
-template <bool PULL, bool MACRO>
+template <bool PULL, bool MACRO, int HINT = HINT_NONE>
 __device__ __forceinline__ void collide_cell(const double* __restrict__ fin, const double* __restrict__ gin,
                                              double* __restrict__ fout, double* __restrict__ gout,
                                              const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ flag,
                                              const double* __restrict__ qc, double* __restrict__ macro, const Layout& L,
-                                             const Phys& P, int i, int j, int k)
+                                             const Phys& P, int i, int j, int k, uint64_t pol = 0)
 {
     const long long c = L.cell(i, j, k);
     const long long n = L.sq;
@@ -124,8 +155,8 @@ __device__ __forceinline__ void collide_cell(const double* __restrict__ fin, con
     const double qzp = qc[2 * n + c + L.sz], qzm = qc[2 * n + c - L.sz];
     const PullOffsets o = pull_offsets(L, i, j, k);
     double f[NQ], g[NQ];
-    gather27<PULL, true>(fin, c, ALL_FLUID, L, o, [&](auto qc_, double v) { f[decltype(qc_)::value] = v; });
-    gather27<PULL, true>(gin, c, ALL_FLUID, L, o, [&](auto qc_, double v) { g[decltype(qc_)::value] = v; });
+    gather27<PULL, true, HINT>(fin, c, ALL_FLUID, L, o, [&](auto qc_, double v) { f[decltype(qc_)::value] = v; }, pol);
+    gather27<PULL, true, HINT>(gin, c, ALL_FLUID, L, o, [&](auto qc_, double v) { g[decltype(qc_)::value] = v; }, pol);
     if (!(m & 1u)) {
         // solid cell: the streamed value is the -1 sentinel (LBM.cpp:565, 582); collide skips it
         if constexpr (PULL) {
@@ -200,11 +231,11 @@ __device__ __forceinline__ void collide_cell(const double* __restrict__ fin, con
     // relax_f_to_equilibrium (LBM.cpp:799-801)
     static_for<0, NQ>([&](auto qc_) {
         constexpr int Q = decltype(qc_)::value;
-        fout[(long long)Q * n + c] = f[Q] + cc.omega * (feq_q<Q>(cc) - f[Q]);
+        st_hint<HINT>(fout + (long long)Q * n + c, f[Q] + cc.omega * (feq_q<Q>(cc) - f[Q]), pol);
     });
     static_for<0, NQ>([&](auto qc_) {
         constexpr int Q = decltype(qc_)::value;
-        gout[(long long)Q * n + c] = g[Q] + cc.omega * (geq_q<Q>(cc) - g[Q]);
+        st_hint<HINT>(gout + (long long)Q * n + c, g[Q] + cc.omega * (geq_q<Q>(cc) - g[Q]), pol);
     });
 }
 
@@ -221,151 +252,6 @@ __global__ void __launch_bounds__(128, 3) k_collide(const double* __restrict__ f
 }
 
 // ---------------------------------------------------------------------------
-// pass 2 as a software-pipelined persistent kernel.  k_collide keeps the 54 populations of a cell in
-// registers (180 registers -> 8 warps per SM) and alternates load / compute / store phases, so HBM sees
-// loads in flight only part of the time (ncu: 4.4 TB/s, long-scoreboard bound).  Here every thread owns a
-// private column of shared memory per buffer; while it collides job n out of buffer n&1 the 54 pulls of
-// job n+1 are already in flight into the other buffer (cp.async, no destination registers).  No barrier
-// is needed anywhere: columns are thread-private, completion is the thread's own cp.async group.
-// ---------------------------------------------------------------------------
-constexpr int PIPE_THREADS = 128;
-constexpr int PIPE_ROWS = 2 * NQ;                                          // f then g
-constexpr size_t PIPE_SMEM = 2 * PIPE_ROWS * PIPE_THREADS * sizeof(double);  // two buffers
-
-struct PipeJob {
-    int i, j, k;
-    long long c;
-    bool in_row;
-};
-
-template <bool MACRO>
-__global__ void __launch_bounds__(PIPE_THREADS, 2)
-    k_collide_pipe(const double* __restrict__ fin, const double* __restrict__ gin, double* __restrict__ fout,
-                   double* __restrict__ gout, const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ flag,
-                   const double* __restrict__ qc, double* __restrict__ macro, const __grid_constant__ Layout L,
-                   const __grid_constant__ Phys P, long long njobs, int upr)
-{
-    extern __shared__ double s_cols[];
-    const int tid = threadIdx.x;
-    const long long n = L.sq;
-    auto job_of = [&](long long id) {
-        PipeJob J;
-        const int seg = (int)(id % upr);
-        const long long row = id / upr;
-        J.j = (int)(row % L.ny);
-        J.k = (int)(row / L.ny);
-        J.i = seg * PIPE_THREADS + tid;
-        J.in_row = id < njobs && J.i < L.nx;
-        J.c = L.cell(J.in_row ? J.i : 0, J.j, J.k);
-        return J;
-    };
-    // start the 54 pulls of a job into buffer `buf`
-    auto issue = [&](const PipeJob& J, uint32_t m, int buf) {
-        double* col = s_cols + (size_t)buf * PIPE_ROWS * PIPE_THREADS + tid;
-        if (J.in_row && (m & 1u)) {
-            const PullOffsets o = pull_offsets(L, J.i, J.j, J.k);
-            static_for<0, NQ>([&](auto qc_) {
-                constexpr int Q = decltype(qc_)::value;
-                long long a = (long long)Q * n + J.c + (o.xo[ex(Q) + 1] + o.yo[ey(Q) + 1] + o.zo[ez(Q) + 1]);
-                if (!((m >> Q) & 1u)) a = (long long)opp(Q) * n + J.c;  // halfway bounce-back (LBM.cpp:590-595)
-                __pipeline_memcpy_async(col + Q * PIPE_THREADS, fin + a, sizeof(double));
-                __pipeline_memcpy_async(col + (NQ + Q) * PIPE_THREADS, gin + a, sizeof(double));
-            });
-        }
-        __pipeline_commit();
-    };
-    const long long stride = gridDim.x;
-    long long id = blockIdx.x;
-    PipeJob cur = job_of(id), nxt = job_of(id + stride);
-    uint32_t m_cur = cur.in_row ? nbr[cur.c] : 0u;
-    uint32_t m_nxt = nxt.in_row ? nbr[nxt.c] : 0u;
-    issue(cur, m_cur, 0);
-    for (int buf = 0; id < njobs; id += stride, buf ^= 1) {
-        // next job's pulls go out before this job's arithmetic starts; the mask of the job after next is
-        // fetched now so that it is in a register when that job is issued
-        issue(nxt, m_nxt, buf ^ 1);
-        const PipeJob nn = job_of(id + 2 * stride);
-        const uint32_t m_nn = nn.in_row ? nbr[nn.c] : 0u;
-        if (cur.in_row) {
-            const long long c = cur.c;
-            if (!(m_cur & 1u)) {
-                // solid cell: the streamed value is the -1 sentinel (LBM.cpp:565, 582); collide skips it
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    fout[q * n + c] = -1.0;
-                    gout[q * n + c] = -1.0;
-                }
-            } else {
-                // neighbours' q-corrections (LBM.cpp:959-991): loads overlap the moment sums below
-                const unsigned fb = flag[c];
-                const bool xp = fb & GRAD_PX, xm = fb & GRAD_MX, yp = fb & GRAD_PY, ym = fb & GRAD_MY, zp = fb & GRAD_PZ,
-                           zm = fb & GRAD_MZ;
-                const double qxp = xp ? qc[c + 1] : 0.0, qxm = xm ? qc[c - 1] : 0.0;
-                const double qyp = yp ? qc[n + c + L.px] : 0.0, qym = ym ? qc[n + c - L.px] : 0.0;
-                const double qzp = zp ? qc[2 * n + c + L.sz] : 0.0, qzm = zm ? qc[2 * n + c - L.sz] : 0.0;
-                __pipeline_wait_prior(1);  // this job's group; the next job's stays in flight
-                const double* col = s_cols + (size_t)buf * PIPE_ROWS * PIPE_THREADS + tid;
-                MomF mf = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-                MomG mg = {0, 0, 0, 0};
-                static_for<0, NQ>([&](auto qc_) {
-                    constexpr int Q = decltype(qc_)::value;
-                    acc_f<Q>(mf, col[Q * PIPE_THREADS]);
-                });
-                static_for<0, NQ>([&](auto qc_) {
-                    constexpr int Q = decltype(qc_)::value;
-                    acc_g<Q>(mg, col[(NQ + Q) * PIPE_THREADS]);
-                });
-                const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
-                const double dqx = one_sided_gradient(xp, xm, qxp, s.qcx, qxm, P.idx[0]);
-                const double dqy = one_sided_gradient(yp, ym, qyp, s.qcy, qym, P.idx[1]);
-                const double dqz = one_sided_gradient(zp, zm, qzp, s.qcz, qzm, P.idx[2]);
-                if constexpr (MACRO) {
-                    // m_macrodata of the post-stream state (Constants.H:8-31, LBM.cpp:867-901)
-                    macro[0 * n + c] = s.rho;
-                    macro[1 * n + c] = s.u;
-                    macro[2 * n + c] = s.v;
-                    macro[3 * n + c] = s.w;
-                    macro[4 * n + c] = sqrt(s.u * s.u + s.v * s.v + s.w * s.w);
-                    macro[5 * n + c] = mg.e2;
-                    macro[6 * n + c] = s.qcx;
-                    macro[7 * n + c] = s.qcy;
-                    macro[8 * n + c] = s.qcz;
-                    macro[9 * n + c] = mf.pxx;
-                    macro[10 * n + c] = mf.pyy;
-                    macro[11 * n + c] = mf.pzz;
-                    macro[12 * n + c] = mf.pxy;
-                    macro[13 * n + c] = mf.pxz;
-                    macro[14 * n + c] = mf.pyz;
-                    macro[15 * n + c] = mg.qx;
-                    macro[16 * n + c] = mg.qy;
-                    macro[17 * n + c] = mg.qz;
-                    macro[18 * n + c] = s.T;
-                    macro[23 * n + c] = dqx;
-                    macro[24 * n + c] = dqy;
-                    macro[25 * n + c] = dqz;
-                }
-                const Coll cc = collision_coefficients(s, mf, mg, dqx, dqy, dqz, P);
-                // relax_f_to_equilibrium (LBM.cpp:799-801)
-                static_for<0, NQ>([&](auto qc_) {
-                    constexpr int Q = decltype(qc_)::value;
-                    const double fq = col[Q * PIPE_THREADS];
-                    fout[(long long)Q * n + c] = fq + cc.omega * (feq_q<Q>(cc) - fq);
-                });
-                static_for<0, NQ>([&](auto qc_) {
-                    constexpr int Q = decltype(qc_)::value;
-                    const double gq = col[(NQ + Q) * PIPE_THREADS];
-                    gout[(long long)Q * n + c] = gq + cc.omega * (geq_q<Q>(cc) - gq);
-                });
-            }
-        }
-        __pipeline_wait_prior(1);  // threads that skipped the arithmetic still retire this job's group
-        cur = nxt, m_cur = m_nxt;
-        nxt = nn, m_nxt = m_nn;
-    }
-    __pipeline_wait_prior(0);
-}
-
-// ---------------------------------------------------------------------------
 // both passes in ONE persistent launch (plain loads): a global ticket counter hands out 128-cell row
 // jobs, ticket 2n = q-correction job n, ticket 2n+1 = collide job n - LAG, slab-major order (fused.cu
 // explains the order and the completion counters).  The collide job re-reads from L2 what the
@@ -378,32 +264,36 @@ __device__ __forceinline__ int ld_acquire_i32(const int* p)
     return v;
 }
 
+constexpr int FP_UW = 32;  // a job is one warp wide: every warp is an autonomous worker, no CTA barrier anywhere
 template <bool MACRO>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, 3)
     k_fused_plain(const double* __restrict__ fin, const double* __restrict__ gin, double* __restrict__ fout,
                   double* __restrict__ gout, const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ flag,
                   double* __restrict__ qc, double* __restrict__ macro, const __grid_constant__ Layout L,
                   const __grid_constant__ Phys P, const __grid_constant__ FusedPlan F, int* __restrict__ counters)
 {
-    constexpr int UW = 128, NCW = 4;
-    __shared__ int s_ticket[2];
     int* tickets = counters;
     int* done = counters + 1;
-    const int tid = threadIdx.x;
-    int next = 0, pending = -1, it = 0;
-    if (tid == 0) next = atomicAdd(tickets, 1);
-    auto publish = [&]() {  // thread 0 only; the stores of the pending job were ordered by a __syncthreads
+    const int lane = threadIdx.x & 31;
+    const uint64_t pol_keep = make_policy(HINT_KEEP), pol_last = make_policy(HINT_LAST);
+    int next = 0, pending = -1;
+    if (lane == 0) next = atomicAdd(tickets, 1);
+    // A finished q-correction job is published (release-increment of its slab counter) one job later, when
+    // its stores have long drained and the fence is cheap; a warp that is about to wait publishes first.
+    auto publish = [&]() {
         if (pending >= 0) {
-            __threadfence();
-            atomicAdd(done + pending, NCW);
+            if (lane == 0) {
+                __threadfence();
+                atomicAdd(done + pending, 1);
+            }
             pending = -1;
         }
     };
-    for (;; it ^= 1) {
-        if (tid == 0) s_ticket[it] = next;
-        __syncthreads();
-        const long long ticket = s_ticket[it];
-        if (tid == 0) next = atomicAdd(tickets, 1);  // used one job later: its latency is hidden
+    auto target = [&](int bb) { return min(F.B + 1, L.ny - bb * F.B) * F.UPR; };
+    for (;;) {
+        const long long ticket = __shfl_sync(0xffffffffu, next, 0);
+        if (ticket >= F.total_tickets) break;
+        if (lane == 0) next = atomicAdd(tickets, 1);  // used one job later: its latency is hidden
         // decode (same enumeration as fused.cu)
         int type;
         long long jn;
@@ -414,46 +304,50 @@ __global__ void __launch_bounds__(128, 2)
             type = F.mode;
             jn = ticket;
         }
-        if (ticket >= F.total_tickets) break;
         if (jn < 0 || jn >= F.NJ) continue;
         const int slab = (int)(jn / F.JPS), r = (int)(jn % F.JPS);
         const int b = slab / F.NK, kk = slab % F.NK, k = F.kq0 + kk;
-        const int row = r / F.UPR, i = (r % F.UPR) * UW + tid, j = b * F.B + row;
+        const int row = r / F.UPR, i = (r % F.UPR) * FP_UW + lane, j = b * F.B + row;
         if (j >= L.ny) continue;
         if (type == 1 && (row >= F.B || k < 0 || k >= L.nz)) continue;
         if (type == 0) {
-            if (i < L.nx) qcorr_cell<true>(fin, gin, nbr, qc, L, P, i, j, k);
-            if (tid == 0) publish();  // an older job; this one is published one job later (its stores are
-            __syncthreads();          // still draining now, a fence here would wait for them)
+            if (i < L.nx) qcorr_cell<true, HINT_KEEP>(fin, gin, nbr, qc, L, P, i, j, k, pol_keep);
+            publish();     // the previous q-correction job of this warp
+            __syncwarp();  // orders every lane's QCorr stores before lane 0's later fence + increment
             pending = slab;
         } else {
-            if (F.mode == 2 && tid == 0) {
-                auto target = [&](int bb) { return min(F.B + 1, L.ny - bb * F.B) * F.UPR * NCW; };
-                auto ok = [&]() {
-                    bool o = ld_acquire_i32(done + slab) >= target(b);
-                    if (o && kk > 0) o = ld_acquire_i32(done + slab - 1) >= target(b);
-                    if (o && kk < F.NK - 1) o = ld_acquire_i32(done + slab + 1) >= target(b);
-                    if (o && b > 0) o = ld_acquire_i32(done + slab - F.NK) >= target(b - 1);
-                    return o;
-                };
-                if (!ok()) {
-                    publish();
-                    const long long t0 = clock64();
-                    while (!ok()) {
-                        __nanosleep(100);
-                        if (clock64() - t0 > 4000000000LL) {
-                            printf("marbles_b200: k_fused_plain dependency wait timed out (block %d slab %d)\n", blockIdx.x, slab);
-                            __trap();
+            if (F.mode == 2) {
+                if (lane == 0) {
+                    auto ok = [&]() {
+                        bool o = ld_acquire_i32(done + slab) >= target(b);
+                        if (o && kk > 0) o = ld_acquire_i32(done + slab - 1) >= target(b);
+                        if (o && kk < F.NK - 1) o = ld_acquire_i32(done + slab + 1) >= target(b);
+                        if (o && b > 0) o = ld_acquire_i32(done + slab - F.NK) >= target(b - 1);
+                        return o;
+                    };
+                    if (!ok()) {
+                        if (pending >= 0) {
+                            __threadfence();
+                            atomicAdd(done + pending, 1);
                         }
+                        const long long t0 = clock64();
+                        while (!ok()) {
+                            __nanosleep(100);
+                            if (clock64() - t0 > 4000000000LL) {
+                                printf("marbles_b200: k_fused_plain dependency wait timed out (block %d slab %d)\n", blockIdx.x, slab);
+                                __trap();
+                            }
+                        }
+                        pending = -2;  // published above
                     }
                 }
+                if (__shfl_sync(0xffffffffu, pending, 0) == -2) pending = -1;
             }
-            if (F.mode == 2) __syncthreads();
-            if (i < L.nx) collide_cell<true, MACRO>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P, i, j, k);
-            if (tid == 0) publish();
+            if (i < L.nx) collide_cell<true, MACRO, HINT_LAST>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P, i, j, k, pol_last);
+            publish();
         }
     }
-    if (tid == 0) publish();
+    publish();
 }
 
 // ---------------------------------------------------------------------------
@@ -1152,32 +1046,16 @@ int launch_collide(const Layout& L, const Phys& P, const double* fin, const doub
     return 1;
 }
 
-int launch_collide_pipe(const Layout& L, const Phys& P, int sm_count, const double* fin, const double* gin, double* fout,
-                        double* gout, const uint32_t* nbr, const uint8_t* flag, const double* qc, double* macro,
-                        cudaStream_t st)
-{
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_collide_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM);
-        cudaFuncSetAttribute(k_collide_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM);
-        attr = true;
-    }
-    const int upr = (L.nx + PIPE_THREADS - 1) / PIPE_THREADS;
-    const long long njobs = (long long)upr * L.ny * L.nz;
-    const int grid = (int)(njobs < 2LL * sm_count ? njobs : 2LL * sm_count);
-    if (macro)
-        k_collide_pipe<true><<<grid, PIPE_THREADS, PIPE_SMEM, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P, njobs, upr);
-    else
-        k_collide_pipe<false><<<grid, PIPE_THREADS, PIPE_SMEM, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P, njobs, upr);
-    return 1;
-}
-
-int launch_fused_plain(const Layout& L, const Phys& P, int band_rows, int lag_per_cta, int mode, int sm_count,
+int launch_fused_plain(const Layout& L, const Phys& P, int band_rows, int lag_quarters, int mode, int sm_count,
                        const double* fin, const double* gin, double* fout, double* gout, const uint32_t* nbr,
                        const uint8_t* flag, double* qc, double* macro, int* counters, cudaStream_t st)
 {
-    const int grid = 2 * sm_count;
-    const FusedPlan F = make_fused_plan(L, 128, band_rows, mode, grid, lag_per_cta);
+    const int grid = 3 * sm_count, workers = grid * 4;
+    // collide job n follows q-correction job n + LAG: two slabs (the z+1 neighbour's q-correction must be
+    // complete) plus lag_quarters/4 of the jobs the grid has in flight
+    FusedPlan F = make_fused_plan(L, FP_UW, band_rows, mode, 0, 0);
+    F.LAG = 2LL * F.JPS + (long long)lag_quarters * workers / 4;
+    F.total_tickets = mode == 2 ? 2 * (F.NJ + F.LAG) : F.NJ;
     const size_t ints = mode == 1 ? 1 : 1 + (size_t)F.NB * F.NK;
     cudaMemsetAsync(counters, 0, ints * sizeof(int), st);
     if (macro)

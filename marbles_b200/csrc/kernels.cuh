@@ -80,9 +80,6 @@ int launch_fused(const Layout& L, const Phys& P, int uw, int band_rows, int lag_
                  const double* fin, const double* gin, double* fout, double* gout, const uint32_t* nbr,
                  const uint8_t* flag, double* qc, double* macro, int* counters, cudaStream_t st);
 
-int launch_collide_pipe(const Layout& L, const Phys& P, int sm_count, const double* fin, const double* gin, double* fout,
-                        double* gout, const uint32_t* nbr, const uint8_t* flag, const double* qc, double* macro,
-                        cudaStream_t st);
 int launch_fused_plain(const Layout& L, const Phys& P, int band_rows, int lag_per_cta, int mode, int sm_count,
                        const double* fin, const double* gin, double* fout, double* gout, const uint32_t* nbr,
                        const uint8_t* flag, double* qc, double* macro, int* counters, cudaStream_t st);
