@@ -5,7 +5,7 @@
  * (NREL/marbles @ b1b50272) on ONE box with ghost cells, written so that the
  * order of floating-point operations follows the reference and results can be
  * compared bit for bit with the reference executable built by
- * oracle/refbuild/Makefile (parity is PINNED: see tests/test_oracle_vs_reference.py
+ * oracle/refbuild/Makefile (parity is PINNED: see tests/test_oracle_golden.py
  * and tests/golden/).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /

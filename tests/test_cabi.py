@@ -1,0 +1,81 @@
+"""The C-ABI shared library loads on a machine without a GPU and exports exactly the entry points
+include/marbles_b200.h declares; the ctypes stub (marbles_b200/_lib.py) lists the same set.  No compute
+calls here: without a CUDA device every entry point must fail loudly (there is no CPU path)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "marbles_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mbl_[a-z_0-9]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from marbles_b200 import _lib, build
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build()
+    return _lib.load()
+
+
+def test_header_symbols_are_exported(lib):
+    from marbles_b200 import _lib
+    names = declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in marbles_b200.h but not exported"
+    assert sorted(_lib.SYMBOLS) == names, "marbles_b200/_lib.py:SYMBOLS and the header disagree"
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (mbl_[a-z_0-9]+)", out))
+    assert exported == set(names), exported ^ set(names)
+
+
+def test_struct_sizes_match_header(lib):
+    """the ctypes mirrors have the C layout (checked against a tiny C program compiled with gcc)"""
+    from marbles_b200 import _lib
+    src = ('#include <stdio.h>\n#include "marbles_b200.h"\nint main(){printf("%zu %zu %zu\\n",'
+           "sizeof(mbl_params),sizeof(mbl_level_geom),sizeof(mbl_layout));return 0;}\n")
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        c = os.path.join(tmp, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(tmp, "s")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        sizes = [int(v) for v in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
+    assert sizes == [C.sizeof(_lib.Params), C.sizeof(_lib.LevelGeom), C.sizeof(_lib.Layout)]
+
+
+def test_no_device_fails_loudly(lib):
+    """on the CPU-only build box mbl_create must return an error, never fall back"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from marbles_b200 import _lib
+    p = _lib.Params()
+    p.nu = p.alpha = 0.1
+    p.R, p.gamma, p.mesh_speed = 1.0, 5.0 / 3.0, 1.0
+    for d in range(3):
+        p.periodic[d] = 1
+    ctx = C.c_void_p()
+    assert lib.mbl_create(C.byref(p), 0, C.byref(ctx)) != 0
+    assert b"no CUDA device" in lib.mbl_last_error()
+    with pytest.raises(_lib.MarblesError):
+        _lib.check(lib.mbl_create(C.byref(p), 0, C.byref(ctx)))
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "marbles_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "liboracle" not in text and "marbles_oracle" not in text, f
