@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--variant", type=int, default=0, help="0 two kernels (default), 1 fused persistent TMA kernel, 2 same as two launches, 3 fused persistent plain-load kernel")
+    ap.add_argument("--variant", type=int, default=0, help="0 two kernels (default), 1 fused persistent TMA kernel, 2 same as two launches, 3 fused persistent plain-load kernel, 4 carry step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -270,11 +270,12 @@ def main():
     peak, peak_src = measured_peak_gbs()
     collide_ms = kms[2] / max(nrec.value, 1)
     kname = {0: "k_collide<pull>", 1: "k_fused (q-correction + collide jobs)", 2: "k_fused (collide jobs)",
-             3: "k_fused_plain (q-correction + collide jobs)", 4: "k_collide_pipe"}[args.variant]
+             3: "k_fused_plain (q-correction + collide jobs)", 4: "k_collide_carry"}[args.variant]
     vname = {0: "two plain kernels (q-correction, collide)", 1: "one persistent TMA-pipelined kernel per step",
              2: "persistent TMA kernel, two launches (q-correction, collide)",
              3: "one persistent kernel per step, plain loads",
-             4: "k_qcorr + software-pipelined persistent collide (cp.async double buffer)"}[args.variant]
+             4: "carry step: k_qcorr_combine (row sums -> q-corrections) + k_collide_carry (collide, emits the next "
+                "step's moment row sums)"}[args.variant]
     achieved = BYTES_PER_CELL * lbm.ncells / (collide_ms * 1e-3) / 1e9
     traffic = None
     try:

@@ -56,6 +56,8 @@ struct Level {
     double* d_red = nullptr;  // 3 doubles for reductions
     double* macro = nullptr;  // lazily allocated (26 comps)
     int* counters = nullptr;  // fused kernel: ticket + per-slab completion counters
+    double* part = nullptr;   // carry step: 12 row-sum words per cell (lazily allocated)
+    bool carry_valid = false; // `part` holds the row sums of the current lattice buffers' next post-stream state
 };
 
 }  // namespace
@@ -71,6 +73,7 @@ struct mbl_ctx {
     // 3: persistent warp-autonomous kernel (plain loads) with both job types.  DESIGN.md has the numbers.
     int variant = 0;
     int uw = 128, band_rows = 16, lag_per_cta = 4;  // variants 1-3 tuning (MBL_UW / MBL_BAND / MBL_LAG)
+    int carry_own = 30, carry_kz = 64, carry_minb = 2;  // variant 4 tuning (MBL_OWN / MBL_KZ / MBL_MINB)
     int sm_count = 148;
     bool timing = false;
     std::vector<cudaEvent_t> events;  // 4 per timed step: before ghost fill, q-corr, collide, after
@@ -155,7 +158,26 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
     if (need_ghosts) ctx->launches += launch_ghost_fill(lv.L, lv.B, lv.p.f[a], lv.p.g[a], lv.local_z, true, true, st);
     mark();
     double* macro = want_macro ? lv.macro : nullptr;
-    if (ctx->variant == 0) {
+    if (ctx->variant == 4) {
+        // carry step: q-corrections from the row sums the previous collide left behind (first step, or after
+        // anything else wrote the lattice: the full q-correction pass)
+        if (!lv.part) CU(cudaMalloc(&lv.part, (size_t)CARRY_WORDS * lv.L.sq * sizeof(double)));
+        if (lv.carry_valid)
+            ctx->launches += launch_qcorr_combine(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.part, lv.p.qc, st);
+        else
+            ctx->launches += launch_qcorr(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st);
+        mark();
+        if (macro) {
+            ctx->launches += launch_collide(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
+                                            lv.p.qc, macro, true, st);
+            lv.carry_valid = false;
+        } else {
+            const CarryPlan C = make_carry_plan(Lk, ctx->carry_own, ctx->carry_kz);
+            ctx->launches += launch_collide_carry(Lk, lv.P, C, ctx->carry_minb, lv.p.f[a], lv.p.g[a], lv.p.f[b],
+                                                  lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, lv.part, st);
+            lv.carry_valid = true;
+        }
+    } else if (ctx->variant == 0) {
         ctx->launches += launch_qcorr(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st);
         mark();
         ctx->launches += launch_collide(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
@@ -213,6 +235,9 @@ int mbl_create(const mbl_params* params, int device, mbl_ctx** out)
     if (const char* e = getenv("MBL_UW")) c->uw = atoi(e) == 256 ? 256 : 128;
     if (const char* e = getenv("MBL_BAND")) c->band_rows = atoi(e) > 0 ? atoi(e) : 16;
     if (const char* e = getenv("MBL_LAG")) c->lag_per_cta = atoi(e) > 0 ? atoi(e) : 4;
+    if (const char* e = getenv("MBL_OWN")) c->carry_own = atoi(e) == 28 ? 28 : 30;
+    if (const char* e = getenv("MBL_KZ")) c->carry_kz = atoi(e) > 0 ? atoi(e) : 64;
+    if (const char* e = getenv("MBL_MINB")) c->carry_minb = atoi(e) == 3 ? 3 : 2;
     init_tables();
     CU(cudaGetLastError());
     *out = c;
@@ -269,6 +294,7 @@ int mbl_level_clear(mbl_ctx* ctx, int lev)
     if (lv.d_red) cudaFree(lv.d_red);
     if (lv.macro) cudaFree(lv.macro);
     if (lv.counters) cudaFree(lv.counters);
+    if (lv.part) cudaFree(lv.part);
     lv = Level();
     return 0;
 }
@@ -357,6 +383,7 @@ int mbl_set_all_fluid(mbl_ctx* ctx, int lev)
 {
     if (check_level(ctx, lev)) return 1;
     Level& lv = ctx->lev[lev];
+    lv.carry_valid = false;
     CU(cudaSetDevice(ctx->device));
     ctx->launches += launch_flags_all_fluid(lv.L, lv.B, lv.p.nbr, lv.p.flag, ctx->stream);
     CU(cudaGetLastError());
@@ -369,6 +396,7 @@ int mbl_set_is_fluid(mbl_ctx* ctx, int lev, const int32_t* is_fluid, int ng)
     if (!is_fluid) return fail("null is_fluid");
     if (ng < 2) return fail("is_fluid needs at least 2 ghost cells (got %d)", ng);
     Level& lv = ctx->lev[lev];
+    lv.carry_valid = false;
     CU(cudaSetDevice(ctx->device));
     const size_t n = (size_t)(lv.L.nx + 2 * ng) * (lv.L.ny + 2 * ng) * (lv.L.nz + 2 * ng);
     if (lv.flag_stage) cudaFree(lv.flag_stage);
@@ -387,6 +415,7 @@ int mbl_upload(mbl_ctx* ctx, int lev, int which, const double* fab, int ng)
     if (check_level(ctx, lev)) return 1;
     if (!fab || ng < 0) return fail("mbl_upload: bad argument");
     Level& lv = ctx->lev[lev];
+    lv.carry_valid = false;
     CU(cudaSetDevice(ctx->device));
     const size_t n = (size_t)(lv.L.nx + 2 * ng) * (lv.L.ny + 2 * ng) * (lv.L.nz + 2 * ng);
     if (ensure_stage(lv, n * sizeof(double))) return 1;
@@ -457,6 +486,7 @@ int mbl_initialize(mbl_ctx* ctx, int lev, int ic_kind, const double* v, int nv)
     if (nv < 16 || !v) return fail("mbl_initialize: need 16 parameters");
     if (ic_kind < 0 || ic_kind > 4) return fail("mbl_initialize: unknown initial condition %d", ic_kind);
     Level& lv = ctx->lev[lev];
+    lv.carry_valid = false;
     CU(cudaSetDevice(ctx->device));
     IcInfo I;
     I.kind = ic_kind;
@@ -496,6 +526,7 @@ int mbl_stream(mbl_ctx* ctx, int lev)
 {
     if (check_level(ctx, lev)) return 1;
     Level& lv = ctx->lev[lev];
+    lv.carry_valid = false;
     CU(cudaSetDevice(ctx->device));
     const int a = lv.cur, b = 1 - lv.cur;
     ctx->launches += launch_stream(lv.L, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, ctx->stream);
@@ -508,6 +539,7 @@ int mbl_collide(mbl_ctx* ctx, int lev, int want_macro)
 {
     if (check_level(ctx, lev)) return 1;
     Level& lv = ctx->lev[lev];
+    lv.carry_valid = false;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     if (want_macro && ensure_macro(lv, st, ctx->launches)) return 1;
@@ -639,8 +671,9 @@ int mbl_get_timing(mbl_ctx* ctx, double ms[3], int* nsteps)
 int mbl_set_variant(mbl_ctx* ctx, int variant)
 {
     if (!ctx) return fail("null context");
-    if (variant < 0 || variant > 3) return fail("variant %d is not available", variant);
+    if (variant < 0 || variant > 4) return fail("variant %d is not available", variant);
     ctx->variant = variant;
+    for (int l = 0; l < MAX_LEVELS; ++l) ctx->lev[l].carry_valid = false;
     return 0;
 }
 

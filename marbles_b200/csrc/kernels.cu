@@ -252,6 +252,204 @@ __global__ void __launch_bounds__(128, 3) k_collide(const double* __restrict__ f
 }
 
 // ---------------------------------------------------------------------------
+// "carry" step: the collide kernel of step n also emits the conserved moments of the POST-STREAM state of
+// step n+1, so that the q-correction pass (the second touch of all 54 populations) disappears.
+//
+// rho, rho*u and 2rhoE of the next post-stream state at cell d are sums over the 27 cells d - e_q of this
+// step's post-collision populations: M(d) = sum_q phi_q f*_q(d - e_q).  The sum is separable on the
+// tensor-product lattice, so it is reduced in three stages without ever re-reading a population:
+//   x  inside the warp: lane l holds cell i0 + l of a row, the e_x = +-1 populations are shifted one lane
+//      by shuffles.  Warps overlap by CARRY_HALO cells on each side (those lanes collide redundantly and
+//      store nothing), so no partial sums cross a warp edge.
+//   z  by marching: a thread walks its column through KZ planes (plus one redundant plane at either end)
+//      and keeps the sums destined for planes k-1 and k in registers; plane k-1 is complete once plane k
+//      has been collided.
+//   y  through memory: the thread of source row j writes, per destination row j+b (b = -1,0,1), the four
+//      words (rho, jx, jz, 2rhoE) -- jy is b * rho.  k_qcorr_combine adds the three rows of a cell.
+// Cells whose 27 pull sources are not all collided cells of this box (EB neighbours, non-wrapped box
+// faces, ghost planes owned by another rank) are not served by the carried sums: k_qcorr_combine pulls
+// their populations itself, exactly as k_qcorr does.
+// Real traffic per cell: collide 54 + 54 + 12 words, combine 12 + 3 words (+ masks) = 1085 B against
+// 1360 B of the two-pass step.
+// ---------------------------------------------------------------------------
+static_assert(CARRY_WORDS == 12, "part layout: [b = -1,0,1][rho, jx, jz, e2]");
+
+struct RowSums {
+    double rho[3], jx[3], e2[3];  // index b + 1
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
+    k_collide_carry(const double* __restrict__ fin, const double* __restrict__ gin, double* __restrict__ fout,
+                    double* __restrict__ gout, const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ flag,
+                    const double* __restrict__ qc, double* __restrict__ part, const __grid_constant__ Layout L,
+                    const __grid_constant__ Phys P, const __grid_constant__ CarryPlan C)
+{
+    const int lane = threadIdx.x & 31;
+    const int xc = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (xc >= C.nxc) return;  // whole warp
+    const int j = blockIdx.y;
+    const int z0 = blockIdx.z * C.kz;
+    const int kz = min(C.kz, L.nz - z0);
+    const int i = xc * C.own - C.halo + lane;
+    const bool own_lane = lane >= C.halo && lane < C.halo + C.own && i < L.nx;
+    // column this lane collides: its own cell, the periodic image for a halo lane that hangs over a wrapped
+    // edge, otherwise clamped (the lane then only keeps the shuffles uniform; whatever it contributes lands
+    // in cells k_qcorr_combine does not take from the carried sums)
+    int is = i;
+    if (is < 0) is = L.wrap[0] ? is + L.nx : 0;
+    if (is >= L.nx) is = (L.wrap[0] && is - L.nx < L.nx) ? is - L.nx : L.nx - 1;
+    const long long n = L.sq;
+    const unsigned FULL = 0xffffffffu;
+
+    // sums destined for plane k-1 (A: complete after this plane) and plane k (B)
+    double Arho[3] = {0, 0, 0}, Ajx[3] = {0, 0, 0}, Ajz[3] = {0, 0, 0}, Ae2[3] = {0, 0, 0};
+    RowSums B = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+
+    for (int kk = -1; kk <= kz; ++kk) {
+        int k = z0 + kk;
+        bool plane_ok = true;
+        if (k < 0) {
+            plane_ok = L.wrap[2];
+            k += L.nz;
+        } else if (k >= L.nz) {
+            plane_ok = L.wrap[2];
+            k -= L.nz;
+        }
+        RowSums Cn = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // sums destined for plane k+1
+        const double Bjz0 = B.rho[0], Bjz1 = B.rho[1], Bjz2 = B.rho[2];  // B holds only e_z = +1 terms so far
+        if (plane_ok) {
+            const long long c = L.cell(is, j, k);
+            const uint32_t m = nbr[c];
+            const unsigned fb = flag[c];
+            const double qxp = qc[c + 1], qxm = qc[c - 1];
+            const double qyp = qc[n + c + L.px], qym = qc[n + c - L.px];
+            const double qzp = qc[2 * n + c + L.sz], qzm = qc[2 * n + c - L.sz];
+            const PullOffsets o = pull_offsets(L, is, j, k);
+            double f[NQ], g[NQ];
+            gather27<true, true>(fin, c, ALL_FLUID, L, o, [&](auto qc_, double v) { f[decltype(qc_)::value] = v; });
+            gather27<true, true>(gin, c, ALL_FLUID, L, o, [&](auto qc_, double v) { g[decltype(qc_)::value] = v; });
+            const bool fluid = m & 1u;
+            if (fluid && m != ALL_FLUID) {
+                static_for<1, NQ>([&](auto qc_) {
+                    constexpr int Q = decltype(qc_)::value;
+                    if (!((m >> Q) & 1u)) {
+                        f[Q] = fin[(long long)opp(Q) * n + c];
+                        g[Q] = gin[(long long)opp(Q) * n + c];
+                    }
+                });
+            }
+            MomF mf = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            MomG mg = {0, 0, 0, 0};
+            static_for<0, NQ>([&](auto qc_) { acc_f<decltype(qc_)::value>(mf, f[decltype(qc_)::value]); });
+            static_for<0, NQ>([&](auto qc_) { acc_g<decltype(qc_)::value>(mg, g[decltype(qc_)::value]); });
+            const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
+            const double dqx = one_sided_gradient(fb & GRAD_PX, fb & GRAD_MX, (fb & GRAD_PX) ? qxp : 0.0, s.qcx,
+                                                  (fb & GRAD_MX) ? qxm : 0.0, P.idx[0]);
+            const double dqy = one_sided_gradient(fb & GRAD_PY, fb & GRAD_MY, (fb & GRAD_PY) ? qyp : 0.0, s.qcy,
+                                                  (fb & GRAD_MY) ? qym : 0.0, P.idx[1]);
+            const double dqz = one_sided_gradient(fb & GRAD_PZ, fb & GRAD_MZ, (fb & GRAD_PZ) ? qzp : 0.0, s.qcz,
+                                                  (fb & GRAD_MZ) ? qzm : 0.0, P.idx[2]);
+            const Coll cc = collision_coefficients(s, mf, mg, dqx, dqy, dqz, P);
+            const bool st = own_lane && kk >= 0 && kk < kz;
+            // relax, store, and hand the new population to the cell it will be pulled by
+            static_for<0, NQ>([&](auto qc_) {
+                constexpr int Q = decltype(qc_)::value;
+                constexpr int b = ey(Q) + 1;
+                const double v = fluid ? f[Q] + cc.omega * (feq_q<Q>(cc) - f[Q]) : -1.0;
+                if (st) fout[(long long)Q * n + c] = v;
+                double t = v;
+                if constexpr (ex(Q) == 1) t = __shfl_up_sync(FULL, v, 1);
+                if constexpr (ex(Q) == -1) t = __shfl_down_sync(FULL, v, 1);
+                if constexpr (ez(Q) == -1) {
+                    Arho[b] += t;
+                    Ajz[b] -= t;
+                    if constexpr (ex(Q) == 1) Ajx[b] += t;
+                    if constexpr (ex(Q) == -1) Ajx[b] -= t;
+                } else if constexpr (ez(Q) == 0) {
+                    B.rho[b] += t;
+                    if constexpr (ex(Q) == 1) B.jx[b] += t;
+                    if constexpr (ex(Q) == -1) B.jx[b] -= t;
+                } else {
+                    Cn.rho[b] += t;
+                    if constexpr (ex(Q) == 1) Cn.jx[b] += t;
+                    if constexpr (ex(Q) == -1) Cn.jx[b] -= t;
+                }
+            });
+            static_for<0, NQ>([&](auto qc_) {
+                constexpr int Q = decltype(qc_)::value;
+                constexpr int b = ey(Q) + 1;
+                const double v = fluid ? g[Q] + cc.omega * (geq_q<Q>(cc) - g[Q]) : -1.0;
+                if (st) gout[(long long)Q * n + c] = v;
+                double t = v;
+                if constexpr (ex(Q) == 1) t = __shfl_up_sync(FULL, v, 1);
+                if constexpr (ex(Q) == -1) t = __shfl_down_sync(FULL, v, 1);
+                if constexpr (ez(Q) == -1)
+                    Ae2[b] += t;
+                else if constexpr (ez(Q) == 0)
+                    B.e2[b] += t;
+                else
+                    Cn.e2[b] += t;
+            });
+        }
+        // plane k-1 of this chunk is complete: every row sum goes out once
+        if (own_lane && kk >= 1) {
+            const long long cd = L.cell(i, j, z0 + kk - 1);
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                part[(long long)(4 * b + 0) * n + cd] = Arho[b];
+                part[(long long)(4 * b + 1) * n + cd] = Ajx[b];
+                part[(long long)(4 * b + 2) * n + cd] = Ajz[b];
+                part[(long long)(4 * b + 3) * n + cd] = Ae2[b];
+            }
+        }
+        // rotate: B becomes the plane whose last contribution comes with the next source plane
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            Arho[b] = B.rho[b];
+            Ajx[b] = B.jx[b];
+            Ae2[b] = B.e2[b];
+        }
+        Ajz[0] = Bjz0, Ajz[1] = Bjz1, Ajz[2] = Bjz2;
+        B = Cn;
+    }
+}
+
+// q-corrections of the post-stream state from the carried row sums (interior cells) or by pulling the
+// populations (everything k_collide_carry could not serve)
+__global__ void __launch_bounds__(128, 6) k_qcorr_combine(const double* __restrict__ fin, const double* __restrict__ gin,
+                                                       const uint32_t* __restrict__ nbr, const double* __restrict__ part,
+                                                       double* __restrict__ qc, const __grid_constant__ Layout L,
+                                                       const __grid_constant__ Phys P, int k0)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.nx) return;
+    const int j = blockIdx.y, k = blockIdx.z + k0;
+    const long long c = L.cell(i, j, k);
+    const long long n = L.sq;
+    const uint32_t m = nbr[c];
+    if (!(m & 1u)) return;
+    const bool inner = (L.wrap[0] || (i > 0 && i < L.nx - 1)) && (L.wrap[1] || (j > 0 && j < L.ny - 1)) &&
+                       (L.wrap[2] || (k > 0 && k < L.nz - 1)) && k >= 0 && k < L.nz;
+    if (!(inner && m == ALL_FLUID)) {
+        qcorr_cell<true>(fin, gin, nbr, qc, L, P, i, j, k);
+        return;
+    }
+    const long long cm = L.cell(i, j == 0 ? L.ny - 1 : j - 1, k);      // source row j-1 sends with b = +1
+    const long long cp = L.cell(i, j == L.ny - 1 ? 0 : j + 1, k);      // source row j+1 sends with b = -1
+    const double rm = part[8 * n + cm], r0 = part[4 * n + c], rp = part[0 * n + cp];
+    const double rho = rm + r0 + rp;
+    const double jy = rm - rp;
+    const double jx = part[9 * n + cm] + part[5 * n + c] + part[1 * n + cp];
+    const double jz = part[10 * n + cm] + part[6 * n + c] + part[2 * n + cp];
+    const double e2 = part[11 * n + cm] + part[7 * n + c] + part[3 * n + cp];
+    const Prim s = primitives(rho, jx, jy, jz, e2, P);
+    qc[c] = s.qcx;
+    qc[n + c] = s.qcy;
+    qc[2 * n + c] = s.qcz;
+}
+
+// ---------------------------------------------------------------------------
 // both passes in ONE persistent launch (plain loads): a global ticket counter hands out 128-cell row
 // jobs, ticket 2n = q-correction job n, ticket 2n+1 = collide job n - LAG, slab-major order (fused.cu
 // explains the order and the completion counters).  The collide job re-reads from L2 what the
@@ -1043,6 +1241,39 @@ int launch_collide(const Layout& L, const Phys& P, const double* fin, const doub
         else
             k_collide<false, false><<<grid, bx, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P);
     }
+    return 1;
+}
+
+CarryPlan make_carry_plan(const Layout& L, int own, int kz)
+{
+    CarryPlan C;
+    C.own = (own == 28) ? 28 : 30;
+    C.halo = (32 - C.own) / 2;
+    C.kz = kz < 1 ? 1 : (kz > L.nz ? L.nz : kz);
+    C.nxc = (L.nx + C.own - 1) / C.own;
+    return C;
+}
+
+int launch_collide_carry(const Layout& L, const Phys& P, const CarryPlan& C, int min_blocks, const double* fin,
+                         const double* gin, double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag,
+                         const double* qc, double* part, cudaStream_t st)
+{
+    const dim3 grid((C.nxc + 3) / 4, L.ny, (L.nz + C.kz - 1) / C.kz);
+    if (min_blocks >= 3)
+        k_collide_carry<3><<<grid, 128, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, part, L, P, C);
+    else
+        k_collide_carry<2><<<grid, 128, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, part, L, P, C);
+    return 1;
+}
+
+int launch_qcorr_combine(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr,
+                         const double* part, double* qc, cudaStream_t st)
+{
+    const int bx = block_x(L);
+    const int k0 = (L.lo[2] > L.dlo[2]) ? -1 : 0;
+    const int k1 = (L.lo[2] + L.nz - 1 < L.dhi[2]) ? L.nz : L.nz - 1;
+    dim3 grid((L.nx + bx - 1) / bx, L.ny, k1 - k0 + 1);
+    k_qcorr_combine<<<grid, bx, 0, st>>>(fin, gin, nbr, part, qc, L, P, k0);
     return 1;
 }
 

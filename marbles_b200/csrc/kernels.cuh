@@ -55,6 +55,22 @@ int launch_qcorr(const Layout& L, const Phys& P, const double* fin, const double
 int launch_collide(const Layout& L, const Phys& P, const double* fin, const double* gin, double* fout, double* gout,
                    const uint32_t* nbr, const uint8_t* flag, const double* qc, double* macro, bool pull,
                    cudaStream_t st);
+// "carry" step (kernels.cu: k_collide_carry / k_qcorr_combine): the collide kernel also emits the row sums of
+// the next post-stream state's conserved moments (12 words per cell, `part`), from which the next step's
+// q-corrections are assembled without touching the populations a second time.
+struct CarryPlan {
+    int own, halo;  // cells a warp owns (own + 2 * halo = 32 lanes) and redundant cells on each side
+    int kz;         // planes a thread marches through
+    int nxc;        // warps per row
+};
+CarryPlan make_carry_plan(const Layout& L, int own, int kz);
+int launch_collide_carry(const Layout& L, const Phys& P, const CarryPlan& C, int min_blocks, const double* fin,
+                         const double* gin, double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag,
+                         const double* qc, double* part, cudaStream_t st);
+int launch_qcorr_combine(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr,
+                         const double* part, double* qc, cudaStream_t st);
+constexpr int CARRY_WORDS = 12;
+
 int launch_stream(const Layout& L, const double* fin, const double* gin, double* fout, double* gout,
                   const uint32_t* nbr, cudaStream_t st);
 int launch_macrodata(const Layout& L, const Phys& P, const double* f, const double* g, const uint8_t* flag,

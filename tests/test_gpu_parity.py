@@ -15,10 +15,31 @@ def golden_fields(z, s):
     return {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
 
 
+# step variants (mbl_set_variant).  "carry*" = variant 4 with different marching / warp-overlap tunings so
+# that small boxes still exercise several z-chunks, ragged chunks, several warps per row and both launch bounds
+CARRY_ENV = {
+    "carry": {},
+    "carry-kz5-own28": {"MBL_KZ": "5", "MBL_OWN": "28", "MBL_MINB": "3"},
+    "carry-kz1": {"MBL_KZ": "1"},
+}
+
+
+def variant_of(v):
+    """-> (variant number, environment overrides)"""
+    if isinstance(v, str):
+        return 4, CARRY_ENV[v]
+    return v, {}
+
+
 def new_lbm(deck_text, is_fluid=None, overrides=None, variant=None):
+    import os
     from marbles_b200.inputs import parse_deck
     from marbles_b200.lbm import LBM
     deck = parse_deck(text=deck_text, overrides=overrides)
+    variant, env = variant_of(variant)
+    for k in ("MBL_KZ", "MBL_OWN", "MBL_MINB"):
+        os.environ.pop(k, None)
+    os.environ.update(env)  # read by mbl_create
     lbm = LBM(deck, is_fluid=is_fluid, variant=variant)
     lbm.init_data()
     return lbm
@@ -26,7 +47,8 @@ def new_lbm(deck_text, is_fluid=None, overrides=None, variant=None):
 
 # fused: mbl_step with the persistent TMA kernel (variant 1, the default), its two job types as two
 # launches (2), or the two plain kernels (0); unfused: the reference-granular operator sequence
-@pytest.mark.parametrize("fused", [1, 2, 3, 0, None], ids=["fused-tma", "twopass-tma", "fused-plain", "twopass-plain", "unfused"])
+@pytest.mark.parametrize("fused", [1, 2, 3, 0, "carry", "carry-kz5-own28", None],
+                         ids=["fused-tma", "twopass-tma", "fused-plain", "twopass-plain", "carry", "carry-kz5-own28", "unfused"])
 @pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_cuda_vs_reference_golden(case, fused):
     z, deck_text, steps = load_golden(case)
@@ -80,7 +102,8 @@ def test_geometry_matches_reference_is_fluid():
         assert np.array_equal(a, z["is_fluid"].astype(np.int32)), case
 
 
-@pytest.mark.parametrize("variant", [1, 3, 0], ids=["fused-tma", "fused-plain", "twopass-plain"])
+@pytest.mark.parametrize("variant", [1, 3, 0, "carry", "carry-kz5-own28", "carry-kz1"],
+                         ids=["fused-tma", "fused-plain", "twopass-plain", "carry", "carry-kz5-own28", "carry-kz1"])
 @pytest.mark.parametrize("case", ["chcyl", "pressure", "slip", "tg12"])
 def test_random_state_vs_oracle(oracle_mod, case, variant):
     """seeded random perturbation of f, g and a random solid mask, 3 steps, all boundary types"""
@@ -100,7 +123,7 @@ def test_random_state_vs_oracle(oracle_mod, case, variant):
     o.g[:] = np.where(o.g > 0, noise(o.g), o.g)
     lbm = new_lbm(deck_text, fl, variant=variant)
     lbm.set_state(o.f, o.g, ng=3)
-    nsteps = 3
+    nsteps = 4
     o.step(nsteps)
     lbm.step(nsteps, want_macrodata=True)
     ref = o.fields()
@@ -130,14 +153,15 @@ def test_eb_forces_and_vorticity_vs_oracle(oracle_mod):
     lbm.close()
 
 
-def test_tg64_vs_oracle_and_conservation(oracle_mod):
+@pytest.mark.parametrize("variant", [0, "carry"], ids=["twopass-plain", "carry"])
+def test_tg64_vs_oracle_and_conservation(oracle_mod, variant):
     """BASELINE config 1 (TG 64^3): 3 steps against the oracle, then size-independent properties"""
     O = oracle_mod
     z, deck_text, _ = load_golden("tg12")
     ov = ["amr.n_cell = 64 64 64"]
     o = O.Oracle(O.lbm_setup(O.parse_deck(None, deck_text.splitlines() + ov)))
     o.initialize()
-    lbm = new_lbm(deck_text, overrides=ov)
+    lbm = new_lbm(deck_text, overrides=ov, variant=variant)
     m0, e0 = lbm.get_f().sum(), lbm.get_g().sum()
     o.step(3)
     lbm.step(3, want_macrodata=True)
@@ -156,13 +180,13 @@ def test_tg64_vs_oracle_and_conservation(oracle_mod):
     lbm.close()
 
 
-def test_full_size_conservation_256():
+@pytest.mark.parametrize("variant", [0, "carry"], ids=["twopass-plain", "carry"])
+def test_full_size_conservation_256(variant):
     """periodic 256^3 (largest size the test box does in seconds): mass/energy conservation of
     stream+collide and agreement of the fused and un-fused operator sequences"""
     _, deck_text, _ = load_golden("tg12")
     ov = ["amr.n_cell = 256 256 256"]
-    a = new_lbm(deck_text, overrides=ov)
-    import ctypes as C
+    a = new_lbm(deck_text, overrides=ov, variant=variant)
     s0 = a.get_f(0).sum(dtype=np.float64), a.get_g(0).sum(dtype=np.float64)
     a.step(10)
     f = a.get_f(0)
@@ -175,15 +199,21 @@ def test_full_size_conservation_256():
 
 @pytest.mark.parametrize("case,nz,world", [("tg12", 12, 2), ("tg12", 13, 3), ("sod48", 8, 2), ("chcyl", None, 2),
                                            ("pressure", None, 2)])
-def test_two_slabs_match_single_box(case, nz, world):
+@pytest.mark.parametrize("variant", [0, "carry-kz5-own28"], ids=["twopass-plain", "carry-kz5-own28"])
+def test_two_slabs_match_single_box(case, nz, world, variant):
     """the multi-rank scheme (z-slabs, ONE exchange of two ghost planes per step, q-correction of the first
     ghost plane recomputed locally, BC ghosts of neighbour-owned planes) on one device: the assembled slabs
     must reproduce the single-box run to round-off (different kernels launches, same arithmetic per cell:
     the two are expected to be bit-identical)"""
+    import os
     import torch
     from marbles_b200.inputs import lbm_inputs, parse_deck
     from marbles_b200.lbm import LBM, slab_bounds
     from marbles_b200.parallel import LocalSlabs
+    variant, env = variant_of(variant)
+    for k in ("MBL_KZ", "MBL_OWN", "MBL_MINB"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
     z, deck_text, _ = load_golden(case)
     fl = z["is_fluid"].astype(np.int32)
     ov = None
@@ -193,7 +223,7 @@ def test_two_slabs_match_single_box(case, nz, world):
         fl = None if fl.min() == 1 else fl
         assert fl is None
     deck = parse_deck(text=deck_text, overrides=ov)
-    single = LBM(deck, is_fluid=fl)
+    single = LBM(deck, is_fluid=fl, variant=0)
     single.init_data()
     nzt = single.n_local[2]
 
@@ -208,7 +238,7 @@ def test_two_slabs_match_single_box(case, nz, world):
             full[ng:-ng, ng:-ng, ng:-ng] = fl
             full = single._wrap_periodic(full, ng, z_local=True)
             sub = np.ascontiguousarray(full[lo:hi + 1 + 2 * ng])
-        s = LBM(deck, rank=rank, world=w, comm=None, is_fluid=sub)
+        s = LBM(deck, rank=rank, world=w, comm=None, is_fluid=sub, variant=variant)
         s.init_data()
         return s
 
@@ -220,6 +250,7 @@ def test_two_slabs_match_single_box(case, nz, world):
         a, b = get(single), slabs.gather(get)
         assert a.shape == b.shape
         err = float(np.abs(a - b).max())
-        assert err <= 1e-13 * max(float(np.abs(a).max()), 1.0), (case, name, err)
+        # carry: the moments behind the q-corrections are summed in another order -> round-off, not bit-identical
+        assert err <= (1e-13 if variant == 0 else 1e-12 * nsteps) * max(float(np.abs(a).max()), 1.0), (case, name, err)
     slabs.close()
     single.close()
