@@ -75,6 +75,8 @@ struct mbl_ctx {
     int uw = 128, band_rows = 16, lag_per_cta = 4;  // variants 1-3 tuning (MBL_UW / MBL_BAND / MBL_LAG)
     int carry_own = 30, carry_kz = 64, carry_minb = 2;  // variant 4 tuning (MBL_OWN / MBL_KZ / MBL_MINB)
     int sm_count = 148;
+    cudaStream_t s_up = nullptr, s_down = nullptr;  // copy streams of the pipelined mbl_step_host
+    int host_chunk = 16;  // planes per upload chunk (MBL_HOST_CHUNK; negative: no pipelining)
     bool timing = false;
     std::vector<cudaEvent_t> events;  // 4 per timed step: before ghost fill, q-corr, collide, after
 };
@@ -235,6 +237,7 @@ int mbl_create(const mbl_params* params, int device, mbl_ctx** out)
     if (const char* e = getenv("MBL_UW")) c->uw = atoi(e) == 256 ? 256 : 128;
     if (const char* e = getenv("MBL_BAND")) c->band_rows = atoi(e) > 0 ? atoi(e) : 16;
     if (const char* e = getenv("MBL_LAG")) c->lag_per_cta = atoi(e) > 0 ? atoi(e) : 4;
+    if (const char* e = getenv("MBL_HOST_CHUNK")) c->host_chunk = atoi(e);
     if (const char* e = getenv("MBL_OWN")) c->carry_own = atoi(e) == 28 ? 28 : 30;
     if (const char* e = getenv("MBL_KZ")) c->carry_kz = atoi(e) > 0 ? atoi(e) : 64;
     if (const char* e = getenv("MBL_MINB")) c->carry_minb = atoi(e) == 3 ? 3 : 2;
@@ -631,13 +634,114 @@ int mbl_halo_unpack(mbl_ctx* ctx, int lev, int side, const double* buf)
     return 0;
 }
 
+// planes [ka, kb) of all 27 components of one lattice between a host FAB (ghost width ng, interior only)
+// and the padded SoA buffer: one pitched DMA per component, no staging kernel
+static int copy_planes(Level& lv, double* soa, double* fab, int ng, int ka, int kb, bool to_device, cudaStream_t st)
+{
+    const Layout& L = lv.L;
+    const size_t sx = L.nx + 2 * ng, sy = L.ny + 2 * ng, n = sx * sy * (L.nz + 2 * ng);
+    for (int q = 0; q < NQ; ++q) {
+        cudaMemcpy3DParms p;
+        memset(&p, 0, sizeof(p));
+        cudaPitchedPtr host = make_cudaPitchedPtr(fab + (size_t)q * n, sx * sizeof(double), sx, sy);
+        cudaPitchedPtr dev = make_cudaPitchedPtr(soa + (size_t)q * L.sq, L.px * sizeof(double), L.px, L.ny + 2 * GY);
+        const cudaPos hpos = make_cudaPos((size_t)ng * sizeof(double), ng, ng + ka);
+        const cudaPos dpos = make_cudaPos((size_t)OX * sizeof(double), GY, GZ + ka);
+        p.srcPtr = to_device ? host : dev;
+        p.srcPos = to_device ? hpos : dpos;
+        p.dstPtr = to_device ? dev : host;
+        p.dstPos = to_device ? dpos : hpos;
+        p.extent = make_cudaExtent(L.nx * sizeof(double), L.ny, kb - ka);
+        p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+        CU(cudaMemcpy3DAsync(&p, st));
+    }
+    return 0;
+}
+
+// One step of an all-periodic box that spans the domain, with the host<->device copies of the step's input and
+// result overlapped with the kernels: the box is cut into z-chunks; chunk c+1 is uploaded (copy stream) while
+// the q-correction and collide kernels run on the planes whose three-plane neighbourhoods are already on the
+// device (compute stream) and finished planes of the result go back to the host (second copy stream).  The
+// two planes at the top are uploaded first, because the periodic wrap makes plane 0 depend on them.
+static int step_host_pipelined(mbl_ctx* ctx, Level& lv, double* f_fab, double* g_fab, int ng)
+{
+    const Layout& L = lv.L;
+    const int nz = L.nz;
+    if (!ctx->s_up) {
+        CU(cudaStreamCreateWithFlags(&ctx->s_up, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ctx->s_down, cudaStreamNonBlocking));
+    }
+    cudaStream_t sc = ctx->stream, su = ctx->s_up, sd = ctx->s_down;
+    const int a = lv.cur, b = 1 - lv.cur;
+    const int top = nz - 2;  // planes [top, nz) go first
+    const int cz = ctx->host_chunk > 0 ? ctx->host_chunk : 16;
+    std::vector<cudaEvent_t> evs;
+    auto event = [&](cudaStream_t st) {
+        cudaEvent_t e;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        cudaEventRecord(e, st);
+        evs.push_back(e);
+        return e;
+    };
+    // the copy streams start after whatever the caller queued on the compute stream
+    cudaEvent_t e0 = event(sc);
+    CU(cudaStreamWaitEvent(su, e0, 0));
+    CU(cudaStreamWaitEvent(sd, e0, 0));
+    if (copy_planes(lv, lv.p.f[a], f_fab, ng, top, nz, true, su)) return 1;
+    if (copy_planes(lv, lv.p.g[a], g_fab, ng, top, nz, true, su)) return 1;
+    int qdone = 0, cdone = 0;
+    bool first = true;
+    for (int u0 = 0; u0 < top; u0 += cz) {
+        const int u = std::min(top, u0 + cz);  // planes [0, u) and [top, nz) are on the device after this upload
+        if (copy_planes(lv, lv.p.f[a], f_fab, ng, u0, u, true, su)) return 1;
+        if (copy_planes(lv, lv.p.g[a], g_fab, ng, u0, u, true, su)) return 1;
+        CU(cudaStreamWaitEvent(sc, event(su), 0));
+        if (first) {  // plane nz-1 pulls from nz-2, nz-1 and 0
+            ctx->launches += launch_qcorr(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, sc, nz - 1, nz);
+            first = false;
+        }
+        const int qhi = (u == top) ? nz - 1 : u - 1;  // q-correction of plane k pulls from plane k+1
+        if (qhi > qdone) {
+            ctx->launches += launch_qcorr(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, sc, qdone, qhi);
+            qdone = qhi;
+        }
+        const int chi = (qdone == nz - 1) ? nz : qdone - 1;  // collide of plane k differences the q-correction of k+1
+        if (chi > cdone) {
+            ctx->launches += launch_collide(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
+                                            lv.p.qc, nullptr, true, sc, cdone, chi);
+            CU(cudaStreamWaitEvent(sd, event(sc), 0));
+            if (copy_planes(lv, lv.p.f[b], f_fab, ng, cdone, chi, false, sd)) return 1;
+            if (copy_planes(lv, lv.p.g[b], g_fab, ng, cdone, chi, false, sd)) return 1;
+            cdone = chi;
+        }
+    }
+    lv.cur = b;
+    lv.carry_valid = false;
+    CU(cudaStreamWaitEvent(sc, event(sd), 0));  // later work on the caller's stream sees the finished step
+    CU(cudaStreamSynchronize(sd));              // the host buffers are valid on return
+    CU(cudaStreamSynchronize(sc));
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int mbl_step_host(mbl_ctx* ctx, int lev, int nsteps, double time, double* f_fab, double* g_fab, int ng)
 {
-    if (mbl_upload(ctx, lev, MBL_F, f_fab, ng)) return 1;
-    if (mbl_upload(ctx, lev, MBL_G, g_fab, ng)) return 1;
+    if (check_level(ctx, lev)) return 1;
+    if (!f_fab || !g_fab || ng < 0 || nsteps < 1) return fail("mbl_step_host: bad argument");
+    Level& lv = ctx->lev[lev];
+    CU(cudaSetDevice(ctx->device));
+    const Layout& L = lv.L;
+    if (nsteps == 1 && ctx->host_chunk >= 0 && L.wrap[0] && L.wrap[1] && L.wrap[2] && L.nz >= 8)
+        return step_host_pipelined(ctx, lv, f_fab, g_fab, ng);
+    // general boxes: upload everything (the step refills every ghost cell), step, download
+    lv.carry_valid = false;
+    if (copy_planes(lv, curf(lv), f_fab, ng, 0, L.nz, true, ctx->stream)) return 1;
+    if (copy_planes(lv, curg(lv), g_fab, ng, 0, L.nz, true, ctx->stream)) return 1;
     if (mbl_step(ctx, lev, nsteps, time, 0)) return 1;
-    if (mbl_download(ctx, lev, MBL_F, f_fab, ng)) return 1;
-    if (mbl_download(ctx, lev, MBL_G, g_fab, ng)) return 1;
+    if (copy_planes(lv, curf(lv), f_fab, ng, 0, L.nz, false, ctx->stream)) return 1;
+    if (copy_planes(lv, curg(lv), g_fab, ng, 0, L.nz, false, ctx->stream)) return 1;
+    CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 

@@ -244,11 +244,11 @@ __global__ void __launch_bounds__(128, 3) k_collide(const double* __restrict__ f
                                                  double* __restrict__ fout, double* __restrict__ gout,
                                                  const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ flag,
                                                  const double* __restrict__ qc, double* __restrict__ macro,
-                                                 const __grid_constant__ Layout L, const __grid_constant__ Phys P)
+                                                 const __grid_constant__ Layout L, const __grid_constant__ Phys P, int k0)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= L.nx) return;
-    collide_cell<PULL, MACRO>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P, i, blockIdx.y, blockIdx.z);
+    collide_cell<PULL, MACRO>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P, i, blockIdx.y, blockIdx.z + k0);
 }
 
 // ---------------------------------------------------------------------------
@@ -1209,13 +1209,14 @@ int launch_ghost_fill(const Layout& L, const BcInfo& B, double* f, double* g, bo
 }
 
 int launch_qcorr(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr, double* qc,
-                 bool pull, cudaStream_t st)
+                 bool pull, cudaStream_t st, int ka, int kb)
 {
     const int bx = block_x(L);
     // q-corrections are needed on the valid cells and, where the box borders another rank in z,
     // on the first ghost plane (recomputed from the two exchanged planes instead of a second exchange)
-    const int k0 = (L.lo[2] > L.dlo[2]) ? -1 : 0;
-    const int k1 = (L.lo[2] + L.nz - 1 < L.dhi[2]) ? L.nz : L.nz - 1;
+    int k0 = (L.lo[2] > L.dlo[2]) ? -1 : 0;
+    int k1 = (L.lo[2] + L.nz - 1 < L.dhi[2]) ? L.nz : L.nz - 1;
+    if (kb > ka) k0 = ka, k1 = kb - 1;  // explicit plane range [ka, kb)
     dim3 grid((L.nx + bx - 1) / bx, L.ny, k1 - k0 + 1);
     if (pull)
         k_qcorr<true><<<grid, bx, 0, st>>>(fin, gin, nbr, qc, L, P, k0);
@@ -1226,20 +1227,22 @@ int launch_qcorr(const Layout& L, const Phys& P, const double* fin, const double
 
 int launch_collide(const Layout& L, const Phys& P, const double* fin, const double* gin, double* fout, double* gout,
                    const uint32_t* nbr, const uint8_t* flag, const double* qc, double* macro, bool pull,
-                   cudaStream_t st)
+                   cudaStream_t st, int ka, int kb)
 {
     const int bx = block_x(L);
-    const dim3 grid = grid3(L, bx);
+    dim3 grid = grid3(L, bx);
+    int k0 = 0;
+    if (kb > ka) k0 = ka, grid.z = kb - ka;  // explicit plane range [ka, kb)
     if (pull) {
         if (macro)
-            k_collide<true, true><<<grid, bx, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P);
+            k_collide<true, true><<<grid, bx, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P, k0);
         else
-            k_collide<true, false><<<grid, bx, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P);
+            k_collide<true, false><<<grid, bx, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P, k0);
     } else {
         if (macro)
-            k_collide<false, true><<<grid, bx, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P);
+            k_collide<false, true><<<grid, bx, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P, k0);
         else
-            k_collide<false, false><<<grid, bx, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P);
+            k_collide<false, false><<<grid, bx, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, macro, L, P, k0);
     }
     return 1;
 }

@@ -49,12 +49,13 @@ int launch_ghost_fill(const Layout& L, const BcInfo& B, double* f, double* g, bo
                       bool do_periodic, cudaStream_t st);
 
 // two-pass collide.  pull=true: stream+collide fused, reads (fin,gin) writes (fout,gout);
-// pull=false: collide in place on the streamed state.
+// pull=false: collide in place on the streamed state.  [ka, kb) restricts the launch to those planes
+// (default: every plane the step needs).
 int launch_qcorr(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr, double* qc,
-                 bool pull, cudaStream_t st);
+                 bool pull, cudaStream_t st, int ka = 0, int kb = 0);
 int launch_collide(const Layout& L, const Phys& P, const double* fin, const double* gin, double* fout, double* gout,
                    const uint32_t* nbr, const uint8_t* flag, const double* qc, double* macro, bool pull,
-                   cudaStream_t st);
+                   cudaStream_t st, int ka = 0, int kb = 0);
 // "carry" step (kernels.cu: k_collide_carry / k_qcorr_combine): the collide kernel also emits the row sums of
 // the next post-stream state's conserved moments (12 words per cell, `part`), from which the next step's
 // q-corrections are assembled without touching the populations a second time.
