@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -636,22 +637,27 @@ int mbl_halo_unpack(mbl_ctx* ctx, int lev, int side, const double* buf)
 
 // planes [ka, kb) of all 27 components of one lattice between a host FAB (ghost width ng, interior only)
 // and the padded SoA buffer: one pitched DMA per component, no staging kernel
-static int copy_planes(Level& lv, double* soa, double* fab, int ng, int ka, int kb, bool to_device, cudaStream_t st)
+// (with_ghosts: also the FAB's ghost cells the device layout has room for, as mbl_upload does)
+static int copy_planes(Level& lv, double* soa, double* fab, int ng, int ka, int kb, bool to_device, cudaStream_t st,
+                       bool with_ghosts = false)
 {
     const Layout& L = lv.L;
     const size_t sx = L.nx + 2 * ng, sy = L.ny + 2 * ng, n = sx * sy * (L.nz + 2 * ng);
+    const int gx = with_ghosts ? std::min(ng, GX) : 0, gy = with_ghosts ? std::min(ng, GY) : 0,
+              gz = with_ghosts ? std::min(ng, GZ) : 0;
+    ka -= gz, kb += gz;
     for (int q = 0; q < NQ; ++q) {
         cudaMemcpy3DParms p;
         memset(&p, 0, sizeof(p));
         cudaPitchedPtr host = make_cudaPitchedPtr(fab + (size_t)q * n, sx * sizeof(double), sx, sy);
         cudaPitchedPtr dev = make_cudaPitchedPtr(soa + (size_t)q * L.sq, L.px * sizeof(double), L.px, L.ny + 2 * GY);
-        const cudaPos hpos = make_cudaPos((size_t)ng * sizeof(double), ng, ng + ka);
-        const cudaPos dpos = make_cudaPos((size_t)OX * sizeof(double), GY, GZ + ka);
+        const cudaPos hpos = make_cudaPos((size_t)(ng - gx) * sizeof(double), ng - gy, ng + ka);
+        const cudaPos dpos = make_cudaPos((size_t)(OX - gx) * sizeof(double), GY - gy, GZ + ka);
         p.srcPtr = to_device ? host : dev;
         p.srcPos = to_device ? hpos : dpos;
         p.dstPtr = to_device ? dev : host;
         p.dstPos = to_device ? dpos : hpos;
-        p.extent = make_cudaExtent(L.nx * sizeof(double), L.ny, kb - ka);
+        p.extent = make_cudaExtent((L.nx + 2 * gx) * sizeof(double), L.ny + 2 * gy, kb - ka);
         p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
         CU(cudaMemcpy3DAsync(&p, st));
     }
@@ -736,8 +742,8 @@ int mbl_step_host(mbl_ctx* ctx, int lev, int nsteps, double time, double* f_fab,
         return step_host_pipelined(ctx, lv, f_fab, g_fab, ng);
     // general boxes: upload everything (the step refills every ghost cell), step, download
     lv.carry_valid = false;
-    if (copy_planes(lv, curf(lv), f_fab, ng, 0, L.nz, true, ctx->stream)) return 1;
-    if (copy_planes(lv, curg(lv), g_fab, ng, 0, L.nz, true, ctx->stream)) return 1;
+    if (copy_planes(lv, curf(lv), f_fab, ng, 0, L.nz, true, ctx->stream, true)) return 1;
+    if (copy_planes(lv, curg(lv), g_fab, ng, 0, L.nz, true, ctx->stream, true)) return 1;
     if (mbl_step(ctx, lev, nsteps, time, 0)) return 1;
     if (copy_planes(lv, curf(lv), f_fab, ng, 0, L.nz, false, ctx->stream)) return 1;
     if (copy_planes(lv, curg(lv), g_fab, ng, 0, L.nz, false, ctx->stream)) return 1;

@@ -280,10 +280,9 @@ struct RowSums {
 
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB)
-    k_collide_carry(const double* __restrict__ fin, const double* __restrict__ gin, double* __restrict__ fout,
-                    double* __restrict__ gout, const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ flag,
-                    const double* __restrict__ qc, double* __restrict__ part, const __grid_constant__ Layout L,
-                    const __grid_constant__ Phys P, const __grid_constant__ CarryPlan C)
+    k_collide_carry(const __grid_constant__ CarryPtrs A, const uint32_t* __restrict__ nbr,
+                    const uint8_t* __restrict__ flag, const __grid_constant__ Layout L, const __grid_constant__ Phys P,
+                    const __grid_constant__ CarryPlan C)
 {
     const int lane = threadIdx.x & 31;
     const int xc = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -299,10 +298,23 @@ __global__ void __launch_bounds__(128, MINB)
     int is = i;
     if (is < 0) is = L.wrap[0] ? is + L.nx : 0;
     if (is >= L.nx) is = (L.wrap[0] && is - L.nx < L.nx) ? is - L.nx : L.nx - 1;
-    const long long n = L.sq;
     const unsigned FULL = 0xffffffffu;
+    // All addressing is a per-component base pointer (kernel parameter space, uniform) plus an UNSIGNED 32-bit
+    // byte offset: unsigned arithmetic keeps the compiler from widening the index sums to 64 bits, so an
+    // access costs one 32-bit add and one 64-bit base add instead of a 64-bit multiply-add chain.  Pull
+    // offsets as in pull_offsets(); the x and y ones do not change along the march.
+    const unsigned px8 = (unsigned)L.px * 8u, sz8 = (unsigned)L.sz * 8u;
+    unsigned xo[3], yo[3];
+    xo[1] = yo[1] = 0u;
+    xo[2] = (L.wrap[0] && is == 0) ? (unsigned)(L.nx - 1) * 8u : 0u - 8u;
+    xo[0] = (L.wrap[0] && is == L.nx - 1) ? 0u - (unsigned)(L.nx - 1) * 8u : 8u;
+    yo[2] = (L.wrap[1] && j == 0) ? (unsigned)(L.ny - 1) * px8 : 0u - px8;
+    yo[0] = (L.wrap[1] && j == L.ny - 1) ? 0u - (unsigned)(L.ny - 1) * px8 : px8;
+    const unsigned crow = (unsigned)(is + OX) * 8u + (unsigned)(j + GY) * px8;
+    auto ldb = [](const double* base, unsigned off) { return *(const double*)((const char*)base + off); };
+    auto stb = [](double* base, unsigned off, double v) { *(double*)((char*)base + off) = v; };
 
-    // sums destined for plane k-1 (A: complete after this plane) and plane k (B)
+    // sums destined for plane k-1 (A*: complete after this plane) and plane k (B)
     double Arho[3] = {0, 0, 0}, Ajx[3] = {0, 0, 0}, Ajz[3] = {0, 0, 0}, Ae2[3] = {0, 0, 0};
     RowSums B = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
 
@@ -319,25 +331,47 @@ __global__ void __launch_bounds__(128, MINB)
         RowSums Cn = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // sums destined for plane k+1
         const double Bjz0 = B.rho[0], Bjz1 = B.rho[1], Bjz2 = B.rho[2];  // B holds only e_z = +1 terms so far
         if (plane_ok) {
-            const long long c = L.cell(is, j, k);
-            const uint32_t m = nbr[c];
-            const unsigned fb = flag[c];
-            const double qxp = qc[c + 1], qxm = qc[c - 1];
-            const double qyp = qc[n + c + L.px], qym = qc[n + c - L.px];
-            const double qzp = qc[2 * n + c + L.sz], qzm = qc[2 * n + c - L.sz];
-            const PullOffsets o = pull_offsets(L, is, j, k);
+            const unsigned c = crow + (unsigned)(k + GZ) * sz8;
+            const uint32_t m = *(const uint32_t*)((const char*)nbr + (c >> 1));
+            const unsigned fb = flag[c >> 3];
+            const double qxp = ldb(A.qc[0], c + 8u), qxm = ldb(A.qc[0], c - 8u);
+            const double qyp = ldb(A.qc[1], c + px8), qym = ldb(A.qc[1], c - px8);
+            const double qzp = ldb(A.qc[2], c + sz8), qzm = ldb(A.qc[2], c - sz8);
+            unsigned zo[3];
+            zo[1] = 0u;
+            zo[2] = (L.wrap[2] && k == 0) ? (unsigned)(L.nz - 1) * sz8 : 0u - sz8;
+            zo[0] = (L.wrap[2] && k == L.nz - 1) ? 0u - (unsigned)(L.nz - 1) * sz8 : sz8;
+            unsigned cyz[3][3];
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) cyz[b][d] = c + yo[b] + zo[d];
             double f[NQ], g[NQ];
-            gather27<true, true>(fin, c, ALL_FLUID, L, o, [&](auto qc_, double v) { f[decltype(qc_)::value] = v; });
-            gather27<true, true>(gin, c, ALL_FLUID, L, o, [&](auto qc_, double v) { g[decltype(qc_)::value] = v; });
+            static_for<0, NQ>([&](auto qc_) {
+                constexpr int Q = decltype(qc_)::value;
+                f[Q] = ldb(A.fin[Q], cyz[ey(Q) + 1][ez(Q) + 1] + xo[ex(Q) + 1]);
+            });
+            static_for<0, NQ>([&](auto qc_) {
+                constexpr int Q = decltype(qc_)::value;
+                g[Q] = ldb(A.gin[Q], cyz[ey(Q) + 1][ez(Q) + 1] + xo[ex(Q) + 1]);
+            });
             const bool fluid = m & 1u;
-            if (fluid && m != ALL_FLUID) {
-                static_for<1, NQ>([&](auto qc_) {
-                    constexpr int Q = decltype(qc_)::value;
-                    if (!((m >> Q) & 1u)) {
-                        f[Q] = fin[(long long)opp(Q) * n + c];
-                        g[Q] = gin[(long long)opp(Q) * n + c];
-                    }
-                });
+            if (m != ALL_FLUID) {
+                if (fluid) {
+                    // halfway bounce-back: the cell's own opposite population (LBM.cpp:590-595 in pull form)
+                    static_for<1, NQ>([&](auto qc_) {
+                        constexpr int Q = decltype(qc_)::value;
+                        if (!((m >> Q) & 1u)) {
+                            f[Q] = ldb(A.fin[opp(Q)], c);
+                            g[Q] = ldb(A.gin[opp(Q)], c);
+                        }
+                    });
+                } else {
+                    // solid cell: the streamed value is the -1 sentinel (LBM.cpp:565, 582) and collide skips it;
+                    // with omega = 0 below the "relaxed" value is exactly -1 again
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) f[q] = g[q] = -1.0;
+                }
             }
             MomF mf = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
             MomG mg = {0, 0, 0, 0};
@@ -351,13 +385,14 @@ __global__ void __launch_bounds__(128, MINB)
             const double dqz = one_sided_gradient(fb & GRAD_PZ, fb & GRAD_MZ, (fb & GRAD_PZ) ? qzp : 0.0, s.qcz,
                                                   (fb & GRAD_MZ) ? qzm : 0.0, P.idx[2]);
             const Coll cc = collision_coefficients(s, mf, mg, dqx, dqy, dqz, P);
+            const double omega = fluid ? cc.omega : 0.0;
             const bool st = own_lane && kk >= 0 && kk < kz;
             // relax, store, and hand the new population to the cell it will be pulled by
             static_for<0, NQ>([&](auto qc_) {
                 constexpr int Q = decltype(qc_)::value;
                 constexpr int b = ey(Q) + 1;
-                const double v = fluid ? f[Q] + cc.omega * (feq_q<Q>(cc) - f[Q]) : -1.0;
-                if (st) fout[(long long)Q * n + c] = v;
+                const double v = f[Q] + omega * (feq_q<Q>(cc) - f[Q]);
+                if (st) stb(A.fout[Q], c, v);
                 double t = v;
                 if constexpr (ex(Q) == 1) t = __shfl_up_sync(FULL, v, 1);
                 if constexpr (ex(Q) == -1) t = __shfl_down_sync(FULL, v, 1);
@@ -379,8 +414,8 @@ __global__ void __launch_bounds__(128, MINB)
             static_for<0, NQ>([&](auto qc_) {
                 constexpr int Q = decltype(qc_)::value;
                 constexpr int b = ey(Q) + 1;
-                const double v = fluid ? g[Q] + cc.omega * (geq_q<Q>(cc) - g[Q]) : -1.0;
-                if (st) gout[(long long)Q * n + c] = v;
+                const double v = g[Q] + omega * (geq_q<Q>(cc) - g[Q]);
+                if (st) stb(A.gout[Q], c, v);
                 double t = v;
                 if constexpr (ex(Q) == 1) t = __shfl_up_sync(FULL, v, 1);
                 if constexpr (ex(Q) == -1) t = __shfl_down_sync(FULL, v, 1);
@@ -394,13 +429,13 @@ __global__ void __launch_bounds__(128, MINB)
         }
         // plane k-1 of this chunk is complete: every row sum goes out once
         if (own_lane && kk >= 1) {
-            const long long cd = L.cell(i, j, z0 + kk - 1);
+            const unsigned cd = (unsigned)(i + OX) * 8u + (unsigned)(j + GY) * px8 + (unsigned)(z0 + kk - 1 + GZ) * sz8;
 #pragma unroll
             for (int b = 0; b < 3; ++b) {
-                part[(long long)(4 * b + 0) * n + cd] = Arho[b];
-                part[(long long)(4 * b + 1) * n + cd] = Ajx[b];
-                part[(long long)(4 * b + 2) * n + cd] = Ajz[b];
-                part[(long long)(4 * b + 3) * n + cd] = Ae2[b];
+                stb(A.part[4 * b + 0], cd, Arho[b]);
+                stb(A.part[4 * b + 1], cd, Ajx[b]);
+                stb(A.part[4 * b + 2], cd, Ajz[b]);
+                stb(A.part[4 * b + 3], cd, Ae2[b]);
             }
         }
         // rotate: B becomes the plane whose last contribution comes with the next source plane
@@ -1261,11 +1296,21 @@ int launch_collide_carry(const Layout& L, const Phys& P, const CarryPlan& C, int
                          const double* gin, double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag,
                          const double* qc, double* part, cudaStream_t st)
 {
+    if (L.sq * 8 >= (1LL << 32)) return -1;  // 32-bit byte offsets inside a component
+    CarryPtrs A;
+    for (int q = 0; q < NQ; ++q) {
+        A.fin[q] = fin + (long long)q * L.sq;
+        A.gin[q] = gin + (long long)q * L.sq;
+        A.fout[q] = fout + (long long)q * L.sq;
+        A.gout[q] = gout + (long long)q * L.sq;
+    }
+    for (int d = 0; d < 3; ++d) A.qc[d] = qc + (long long)d * L.sq;
+    for (int w = 0; w < CARRY_WORDS; ++w) A.part[w] = part + (long long)w * L.sq;
     const dim3 grid((C.nxc + 3) / 4, L.ny, (L.nz + C.kz - 1) / C.kz);
     if (min_blocks >= 3)
-        k_collide_carry<3><<<grid, 128, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, part, L, P, C);
+        k_collide_carry<3><<<grid, 128, 0, st>>>(A, nbr, flag, L, P, C);
     else
-        k_collide_carry<2><<<grid, 128, 0, st>>>(fin, gin, fout, gout, nbr, flag, qc, part, L, P, C);
+        k_collide_carry<2><<<grid, 128, 0, st>>>(A, nbr, flag, L, P, C);
     return 1;
 }
 

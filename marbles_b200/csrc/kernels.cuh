@@ -64,13 +64,22 @@ struct CarryPlan {
     int kz;         // planes a thread marches through
     int nxc;        // warps per row
 };
+constexpr int CARRY_WORDS = 12;
+// per-component base pointers, passed by value in kernel parameter space
+struct CarryPtrs {
+    const double* fin[NQ];
+    const double* gin[NQ];
+    double* fout[NQ];
+    double* gout[NQ];
+    const double* qc[3];
+    double* part[CARRY_WORDS];
+};
 CarryPlan make_carry_plan(const Layout& L, int own, int kz);
 int launch_collide_carry(const Layout& L, const Phys& P, const CarryPlan& C, int min_blocks, const double* fin,
                          const double* gin, double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag,
                          const double* qc, double* part, cudaStream_t st);
 int launch_qcorr_combine(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr,
                          const double* part, double* qc, cudaStream_t st);
-constexpr int CARRY_WORDS = 12;
 
 int launch_stream(const Layout& L, const double* fin, const double* gin, double* fout, double* gout,
                   const uint32_t* nbr, cudaStream_t st);
