@@ -57,8 +57,8 @@ struct Level {
     double* d_red = nullptr;  // 3 doubles for reductions
     double* macro = nullptr;  // lazily allocated (26 comps)
     int* counters = nullptr;  // fused kernel: ticket + per-slab completion counters
-    double* part = nullptr;   // carry step: 12 row-sum words per cell (lazily allocated)
-    bool carry_valid = false; // `part` holds the row sums of the current lattice buffers' next post-stream state
+    double* part = nullptr;   // carry step: 12 partial-sum words per cell (lazily allocated)
+    bool carry_valid = false; // `part` holds the partial sums of the current lattice buffers' next post-stream state
 };
 
 }  // namespace
@@ -74,7 +74,7 @@ struct mbl_ctx {
     // 3: persistent warp-autonomous kernel (plain loads) with both job types.  DESIGN.md has the numbers.
     int variant = 0;
     int uw = 128, band_rows = 16, lag_per_cta = 4;  // variants 1-3 tuning (MBL_UW / MBL_BAND / MBL_LAG)
-    int carry_own = 30, carry_kz = 64, carry_minb = 2;  // variant 4 tuning (MBL_OWN / MBL_KZ / MBL_MINB)
+    int carry_own = 30, carry_ky = 32, carry_minb = 3;  // variant 4 tuning (MBL_OWN / MBL_KY / MBL_MINB)
     int sm_count = 148;
     cudaStream_t s_up = nullptr, s_down = nullptr;  // copy streams of the pipelined mbl_step_host
     int host_chunk = 16;  // planes per upload chunk (MBL_HOST_CHUNK; negative: no pipelining)
@@ -162,7 +162,7 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
     mark();
     double* macro = want_macro ? lv.macro : nullptr;
     if (ctx->variant == 4) {
-        // carry step: q-corrections from the row sums the previous collide left behind (first step, or after
+        // carry step: q-corrections from the partial sums the previous collide left behind (first step, or after
         // anything else wrote the lattice: the full q-correction pass)
         if (!lv.part) CU(cudaMalloc(&lv.part, (size_t)CARRY_WORDS * lv.L.sq * sizeof(double)));
         if (lv.carry_valid)
@@ -175,7 +175,7 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
                                             lv.p.qc, macro, true, st);
             lv.carry_valid = false;
         } else {
-            const CarryPlan C = make_carry_plan(Lk, ctx->carry_own, ctx->carry_kz);
+            const CarryPlan C = make_carry_plan(Lk, ctx->carry_own, ctx->carry_ky);
             ctx->launches += launch_collide_carry(Lk, lv.P, C, ctx->carry_minb, lv.p.f[a], lv.p.g[a], lv.p.f[b],
                                                   lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, lv.part, st);
             lv.carry_valid = true;
@@ -240,8 +240,8 @@ int mbl_create(const mbl_params* params, int device, mbl_ctx** out)
     if (const char* e = getenv("MBL_LAG")) c->lag_per_cta = atoi(e) > 0 ? atoi(e) : 4;
     if (const char* e = getenv("MBL_HOST_CHUNK")) c->host_chunk = atoi(e);
     if (const char* e = getenv("MBL_OWN")) c->carry_own = atoi(e) == 28 ? 28 : 30;
-    if (const char* e = getenv("MBL_KZ")) c->carry_kz = atoi(e) > 0 ? atoi(e) : 64;
-    if (const char* e = getenv("MBL_MINB")) c->carry_minb = atoi(e) == 3 ? 3 : 2;
+    if (const char* e = getenv("MBL_KY")) c->carry_ky = atoi(e) > 0 ? atoi(e) : 32;
+    if (const char* e = getenv("MBL_MINB")) c->carry_minb = atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 3;
     init_tables();
     CU(cudaGetLastError());
     *out = c;

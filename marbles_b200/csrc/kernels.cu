@@ -14,6 +14,7 @@
 #include "kernels.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace mbl {
 
@@ -259,24 +260,40 @@ __global__ void __launch_bounds__(128, 3) k_collide(const double* __restrict__ f
 // step's post-collision populations: M(d) = sum_q phi_q f*_q(d - e_q).  The sum is separable on the
 // tensor-product lattice, so it is reduced in three stages without ever re-reading a population:
 //   x  inside the warp: lane l holds cell i0 + l of a row, the e_x = +-1 populations are shifted one lane
-//      by shuffles.  Warps overlap by CARRY_HALO cells on each side (those lanes collide redundantly and
+//      by shuffles.  Warps overlap by `halo` cells on each side (those lanes collide redundantly and
 //      store nothing), so no partial sums cross a warp edge.
-//   z  by marching: a thread walks its column through KZ planes (plus one redundant plane at either end)
-//      and keeps the sums destined for planes k-1 and k in registers; plane k-1 is complete once plane k
-//      has been collided.
-//   y  through memory: the thread of source row j writes, per destination row j+b (b = -1,0,1), the four
-//      words (rho, jx, jz, 2rhoE) -- jy is b * rho.  k_qcorr_combine adds the three rows of a cell.
+//   y  by marching: a thread walks its column through KY rows of one plane (plus one redundant row at
+//      either end) and keeps the sums destined for rows j-1 and j in a private shared-memory ring; row j-1
+//      is complete once row j has been collided.  Rows, not planes, are marched so that the CTAs resident at
+//      any time cover a few whole planes: marching through planes spreads them over every plane of a chunk
+//      (thousands of 2 MB pages and DRAM rows in flight; measured 40 % slower).
+//   z  through memory: the thread of source plane k writes, per destination plane k+c (c = -1,0,1), the four
+//      words (rho, jx, jy, 2rhoE) -- jz is c * rho.  k_qcorr_combine adds the three planes of a cell.
 // Cells whose 27 pull sources are not all collided cells of this box (EB neighbours, non-wrapped box
 // faces, ghost planes owned by another rank) are not served by the carried sums: k_qcorr_combine pulls
 // their populations itself, exactly as k_qcorr does.
 // Real traffic per cell: collide 54 + 54 + 12 words, combine 12 + 3 words (+ masks) = 1085 B against
 // 1360 B of the two-pass step.
 // ---------------------------------------------------------------------------
-static_assert(CARRY_WORDS == 12, "part layout: [b = -1,0,1][rho, jx, jz, e2]");
+static_assert(CARRY_WORDS == 12, "part layout: [c = -1,0,1][rho, jx, jy, e2]");
 
-struct RowSums {
-    double rho[3], jx[3], e2[3];  // index b + 1
-};
+// Shared memory of k_collide_carry, private per thread (slot-major, so a warp's access to one slot is one
+// conflict-free 256-byte row): the 27 pulled g populations of the current cell (they arrive by cp.async
+// and never occupy registers: the register file holds f, the collision coefficients and this cell's
+// partial sums, which is what lets three or four CTAs share an SM) and the two ring rows of sums.
+constexpr int CARRY_G_SLOTS = NQ;       // g[q]
+constexpr int CARRY_RING_SLOTS = 21;    // A: rho,jx,jy,e2 x 3 planes;  B: rho,jx,e2 x 3 planes
+constexpr int CARRY_SMEM_BYTES = (CARRY_G_SLOTS + CARRY_RING_SLOTS) * 128 * 8;
+
+__device__ __forceinline__ void cp_async8(unsigned smem_addr, const void* gptr)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB)
@@ -284,12 +301,16 @@ __global__ void __launch_bounds__(128, MINB)
                     const uint8_t* __restrict__ flag, const __grid_constant__ Layout L, const __grid_constant__ Phys P,
                     const __grid_constant__ CarryPlan C)
 {
+    extern __shared__ double smem[];
+    double* const sg = smem + threadIdx.x;                          // sg[q * 128]
+    double* const ring = smem + CARRY_G_SLOTS * 128 + threadIdx.x;  // ring[slot * 128]
+    const unsigned sg_addr = (unsigned)__cvta_generic_to_shared(sg);
     const int lane = threadIdx.x & 31;
     const int xc = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (xc >= C.nxc) return;  // whole warp
-    const int j = blockIdx.y;
-    const int z0 = blockIdx.z * C.kz;
-    const int kz = min(C.kz, L.nz - z0);
+    const int y0 = blockIdx.y * C.ky;
+    const int ky = min(C.ky, L.ny - y0);
+    const int k = blockIdx.z;
     const int i = xc * C.own - C.halo + lane;
     const bool own_lane = lane >= C.halo && lane < C.halo + C.own && i < L.nx;
     // column this lane collides: its own cell, the periodic image for a halo lane that hangs over a wrapped
@@ -302,60 +323,64 @@ __global__ void __launch_bounds__(128, MINB)
     // All addressing is a per-component base pointer (kernel parameter space, uniform) plus an UNSIGNED 32-bit
     // byte offset: unsigned arithmetic keeps the compiler from widening the index sums to 64 bits, so an
     // access costs one 32-bit add and one 64-bit base add instead of a 64-bit multiply-add chain.  Pull
-    // offsets as in pull_offsets(); the x and y ones do not change along the march.
+    // offsets as in pull_offsets(); the x and z ones do not change along the march.
     const unsigned px8 = (unsigned)L.px * 8u, sz8 = (unsigned)L.sz * 8u;
-    unsigned xo[3], yo[3];
-    xo[1] = yo[1] = 0u;
+    unsigned xo[3], zo[3];
+    xo[1] = zo[1] = 0u;
     xo[2] = (L.wrap[0] && is == 0) ? (unsigned)(L.nx - 1) * 8u : 0u - 8u;
     xo[0] = (L.wrap[0] && is == L.nx - 1) ? 0u - (unsigned)(L.nx - 1) * 8u : 8u;
-    yo[2] = (L.wrap[1] && j == 0) ? (unsigned)(L.ny - 1) * px8 : 0u - px8;
-    yo[0] = (L.wrap[1] && j == L.ny - 1) ? 0u - (unsigned)(L.ny - 1) * px8 : px8;
-    const unsigned crow = (unsigned)(is + OX) * 8u + (unsigned)(j + GY) * px8;
+    zo[2] = (L.wrap[2] && k == 0) ? (unsigned)(L.nz - 1) * sz8 : 0u - sz8;
+    zo[0] = (L.wrap[2] && k == L.nz - 1) ? 0u - (unsigned)(L.nz - 1) * sz8 : sz8;
+    const unsigned ccol = (unsigned)(is + OX) * 8u + (unsigned)(k + GZ) * sz8;
     auto ldb = [](const double* base, unsigned off) { return *(const double*)((const char*)base + off); };
     auto stb = [](double* base, unsigned off, double v) { *(double*)((char*)base + off) = v; };
 
-    // sums destined for plane k-1 (A*: complete after this plane) and plane k (B)
-    double Arho[3] = {0, 0, 0}, Ajx[3] = {0, 0, 0}, Ajz[3] = {0, 0, 0}, Ae2[3] = {0, 0, 0};
-    RowSums B = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    // ring: sums destined for row j-1 (A, complete after this row: slots 0..11 = [plane c][rho,jx,jy,e2]) and
+    // for row j (B, slots 12..20 = [plane c][rho,jx,e2]; its jy is its rho as long as it holds e_y = +1 terms only)
+#pragma unroll
+    for (int t = 0; t < CARRY_RING_SLOTS; ++t) ring[t * 128] = 0.0;
 
-    for (int kk = -1; kk <= kz; ++kk) {
-        int k = z0 + kk;
-        bool plane_ok = true;
-        if (k < 0) {
-            plane_ok = L.wrap[2];
-            k += L.nz;
-        } else if (k >= L.nz) {
-            plane_ok = L.wrap[2];
-            k -= L.nz;
+    for (int jj = -1; jj <= ky; ++jj) {
+        int j = y0 + jj;
+        bool row_ok = true;
+        if (j < 0) {
+            row_ok = L.wrap[1];
+            j += L.ny;
+        } else if (j >= L.ny) {
+            row_ok = L.wrap[1];
+            j -= L.ny;
         }
-        RowSums Cn = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // sums destined for plane k+1
-        const double Bjz0 = B.rho[0], Bjz1 = B.rho[1], Bjz2 = B.rho[2];  // B holds only e_z = +1 terms so far
-        if (plane_ok) {
-            const unsigned c = crow + (unsigned)(k + GZ) * sz8;
-            const uint32_t m = *(const uint32_t*)((const char*)nbr + (c >> 1));
-            const unsigned fb = flag[c >> 3];
-            const double qxp = ldb(A.qc[0], c + 8u), qxm = ldb(A.qc[0], c - 8u);
-            const double qyp = ldb(A.qc[1], c + px8), qym = ldb(A.qc[1], c - px8);
-            const double qzp = ldb(A.qc[2], c + sz8), qzm = ldb(A.qc[2], c - sz8);
-            unsigned zo[3];
-            zo[1] = 0u;
-            zo[2] = (L.wrap[2] && k == 0) ? (unsigned)(L.nz - 1) * sz8 : 0u - sz8;
-            zo[0] = (L.wrap[2] && k == L.nz - 1) ? 0u - (unsigned)(L.nz - 1) * sz8 : sz8;
+        // this row's contributions to rows j-1 (TA), j (TB), j+1 (TC): [plane c][rho, jx] now, e2 in the g phase
+        double TA[3][2] = {}, TB[3][2] = {}, TC[3][2] = {};
+        double EA[3] = {}, EB[3] = {}, EC[3] = {};
+        if (row_ok) {
+            const unsigned c = ccol + (unsigned)(j + GY) * px8;
+            unsigned yo[3];
+            yo[1] = 0u;
+            yo[2] = (L.wrap[1] && j == 0) ? (unsigned)(L.ny - 1) * px8 : 0u - px8;
+            yo[0] = (L.wrap[1] && j == L.ny - 1) ? 0u - (unsigned)(L.ny - 1) * px8 : px8;
             unsigned cyz[3][3];
 #pragma unroll
             for (int b = 0; b < 3; ++b)
 #pragma unroll
                 for (int d = 0; d < 3; ++d) cyz[b][d] = c + yo[b] + zo[d];
-            double f[NQ], g[NQ];
+            // g: global -> shared, asynchronously, no registers
+            static_for<0, NQ>([&](auto qc_) {
+                constexpr int Q = decltype(qc_)::value;
+                cp_async8(sg_addr + Q * 128 * 8, (const char*)A.gin[Q] + (cyz[ey(Q) + 1][ez(Q) + 1] + xo[ex(Q) + 1]));
+            });
+            const uint32_t m = *(const uint32_t*)((const char*)nbr + (c >> 1));
+            const unsigned fb = flag[c >> 3];
+            const double qxp = ldb(A.qc[0], c + 8u), qxm = ldb(A.qc[0], c - 8u);
+            const double qyp = ldb(A.qc[1], c + px8), qym = ldb(A.qc[1], c - px8);
+            const double qzp = ldb(A.qc[2], c + sz8), qzm = ldb(A.qc[2], c - sz8);
+            double f[NQ];
             static_for<0, NQ>([&](auto qc_) {
                 constexpr int Q = decltype(qc_)::value;
                 f[Q] = ldb(A.fin[Q], cyz[ey(Q) + 1][ez(Q) + 1] + xo[ex(Q) + 1]);
             });
-            static_for<0, NQ>([&](auto qc_) {
-                constexpr int Q = decltype(qc_)::value;
-                g[Q] = ldb(A.gin[Q], cyz[ey(Q) + 1][ez(Q) + 1] + xo[ex(Q) + 1]);
-            });
             const bool fluid = m & 1u;
+            cp_async_wait_all();
             if (m != ALL_FLUID) {
                 if (fluid) {
                     // halfway bounce-back: the cell's own opposite population (LBM.cpp:590-595 in pull form)
@@ -363,20 +388,23 @@ __global__ void __launch_bounds__(128, MINB)
                         constexpr int Q = decltype(qc_)::value;
                         if (!((m >> Q) & 1u)) {
                             f[Q] = ldb(A.fin[opp(Q)], c);
-                            g[Q] = ldb(A.gin[opp(Q)], c);
+                            sg[Q * 128] = ldb(A.gin[opp(Q)], c);
                         }
                     });
                 } else {
                     // solid cell: the streamed value is the -1 sentinel (LBM.cpp:565, 582) and collide skips it;
                     // with omega = 0 below the "relaxed" value is exactly -1 again
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) f[q] = g[q] = -1.0;
+                    for (int q = 0; q < NQ; ++q) {
+                        f[q] = -1.0;
+                        sg[q * 128] = -1.0;
+                    }
                 }
             }
             MomF mf = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
             MomG mg = {0, 0, 0, 0};
             static_for<0, NQ>([&](auto qc_) { acc_f<decltype(qc_)::value>(mf, f[decltype(qc_)::value]); });
-            static_for<0, NQ>([&](auto qc_) { acc_g<decltype(qc_)::value>(mg, g[decltype(qc_)::value]); });
+            static_for<0, NQ>([&](auto qc_) { acc_g<decltype(qc_)::value>(mg, sg[decltype(qc_)::value * 128]); });
             const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
             const double dqx = one_sided_gradient(fb & GRAD_PX, fb & GRAD_MX, (fb & GRAD_PX) ? qxp : 0.0, s.qcx,
                                                   (fb & GRAD_MX) ? qxm : 0.0, P.idx[0]);
@@ -386,76 +414,82 @@ __global__ void __launch_bounds__(128, MINB)
                                                   (fb & GRAD_MZ) ? qzm : 0.0, P.idx[2]);
             const Coll cc = collision_coefficients(s, mf, mg, dqx, dqy, dqz, P);
             const double omega = fluid ? cc.omega : 0.0;
-            const bool st = own_lane && kk >= 0 && kk < kz;
+            const bool st = own_lane && jj >= 0 && jj < ky;
             // relax, store, and hand the new population to the cell it will be pulled by
             static_for<0, NQ>([&](auto qc_) {
                 constexpr int Q = decltype(qc_)::value;
-                constexpr int b = ey(Q) + 1;
+                constexpr int d = ez(Q) + 1;
                 const double v = f[Q] + omega * (feq_q<Q>(cc) - f[Q]);
                 if (st) stb(A.fout[Q], c, v);
                 double t = v;
                 if constexpr (ex(Q) == 1) t = __shfl_up_sync(FULL, v, 1);
                 if constexpr (ex(Q) == -1) t = __shfl_down_sync(FULL, v, 1);
-                if constexpr (ez(Q) == -1) {
-                    Arho[b] += t;
-                    Ajz[b] -= t;
-                    if constexpr (ex(Q) == 1) Ajx[b] += t;
-                    if constexpr (ex(Q) == -1) Ajx[b] -= t;
-                } else if constexpr (ez(Q) == 0) {
-                    B.rho[b] += t;
-                    if constexpr (ex(Q) == 1) B.jx[b] += t;
-                    if constexpr (ex(Q) == -1) B.jx[b] -= t;
-                } else {
-                    Cn.rho[b] += t;
-                    if constexpr (ex(Q) == 1) Cn.jx[b] += t;
-                    if constexpr (ex(Q) == -1) Cn.jx[b] -= t;
-                }
+                double(&T)[3][2] = ey(Q) == -1 ? TA : ey(Q) == 0 ? TB : TC;
+                T[d][0] += t;
+                if constexpr (ex(Q) == 1) T[d][1] += t;
+                if constexpr (ex(Q) == -1) T[d][1] -= t;
             });
+            // a later row of this column: into L2 while this one is finished (one bulk prefetch per component
+            // row segment, issued by lane 0 for the warp's 32 cells; the y offsets of the current row are close
+            // enough at a wrapped edge)
+            if (C.prefetch > 0 && jj + C.prefetch <= ky && lane == 0) {
+                int jp = j + C.prefetch;
+                if (jp >= L.ny) jp -= L.ny;
+                const unsigned dp = (unsigned)(jp - j) * px8;
+                static_for<0, NQ>([&](auto qc_) {
+                    constexpr int Q = decltype(qc_)::value;
+                    const unsigned off = (cyz[ey(Q) + 1][ez(Q) + 1] + dp - 8u) & ~15u;
+                    prefetch_l2_bulk((const char*)A.fin[Q] + off, 288u);
+                    prefetch_l2_bulk((const char*)A.gin[Q] + off, 288u);
+                });
+            }
             static_for<0, NQ>([&](auto qc_) {
                 constexpr int Q = decltype(qc_)::value;
-                constexpr int b = ey(Q) + 1;
-                const double v = g[Q] + omega * (geq_q<Q>(cc) - g[Q]);
+                constexpr int d = ez(Q) + 1;
+                const double gq = sg[Q * 128];
+                const double v = gq + omega * (geq_q<Q>(cc) - gq);
                 if (st) stb(A.gout[Q], c, v);
                 double t = v;
                 if constexpr (ex(Q) == 1) t = __shfl_up_sync(FULL, v, 1);
                 if constexpr (ex(Q) == -1) t = __shfl_down_sync(FULL, v, 1);
-                if constexpr (ez(Q) == -1)
-                    Ae2[b] += t;
-                else if constexpr (ez(Q) == 0)
-                    B.e2[b] += t;
-                else
-                    Cn.e2[b] += t;
+                double(&E)[3] = ey(Q) == -1 ? EA : ey(Q) == 0 ? EB : EC;
+                E[d] += t;
             });
         }
-        // plane k-1 of this chunk is complete: every row sum goes out once
-        if (own_lane && kk >= 1) {
-            const unsigned cd = (unsigned)(i + OX) * 8u + (unsigned)(j + GY) * px8 + (unsigned)(z0 + kk - 1 + GZ) * sz8;
+        // merge with the ring.  Row j-1 of this chunk is complete: every plane sum goes out once.
+        const bool out = own_lane && jj >= 1;
+        const unsigned cd = (unsigned)(i + OX) * 8u + (unsigned)(y0 + jj - 1 + GY) * px8 + (unsigned)(k + GZ) * sz8;
 #pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                stb(A.part[4 * b + 0], cd, Arho[b]);
-                stb(A.part[4 * b + 1], cd, Ajx[b]);
-                stb(A.part[4 * b + 2], cd, Ajz[b]);
-                stb(A.part[4 * b + 3], cd, Ae2[b]);
+        for (int d = 0; d < 3; ++d) {
+            const double a_rho = ring[(4 * d + 0) * 128] + TA[d][0];
+            const double a_jx = ring[(4 * d + 1) * 128] + TA[d][1];
+            const double a_jy = ring[(4 * d + 2) * 128] - TA[d][0];  // e_y = -1 terms
+            const double a_e2 = ring[(4 * d + 3) * 128] + EA[d];
+            if (out) {
+                stb(A.part[4 * d + 0], cd, a_rho);
+                stb(A.part[4 * d + 1], cd, a_jx);
+                stb(A.part[4 * d + 2], cd, a_jy);
+                stb(A.part[4 * d + 3], cd, a_e2);
             }
+            // rotate: B (+ this row's e_y = 0 terms) becomes A, this row's e_y = +1 terms become B
+            const double b_rho = ring[(12 + 3 * d + 0) * 128];
+            ring[(4 * d + 0) * 128] = b_rho + TB[d][0];
+            ring[(4 * d + 1) * 128] = ring[(12 + 3 * d + 1) * 128] + TB[d][1];
+            ring[(4 * d + 2) * 128] = b_rho;  // B held e_y = +1 terms only
+            ring[(4 * d + 3) * 128] = ring[(12 + 3 * d + 2) * 128] + EB[d];
+            ring[(12 + 3 * d + 0) * 128] = TC[d][0];
+            ring[(12 + 3 * d + 1) * 128] = TC[d][1];
+            ring[(12 + 3 * d + 2) * 128] = EC[d];
         }
-        // rotate: B becomes the plane whose last contribution comes with the next source plane
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-            Arho[b] = B.rho[b];
-            Ajx[b] = B.jx[b];
-            Ae2[b] = B.e2[b];
-        }
-        Ajz[0] = Bjz0, Ajz[1] = Bjz1, Ajz[2] = Bjz2;
-        B = Cn;
     }
 }
 
-// q-corrections of the post-stream state from the carried row sums (interior cells) or by pulling the
+// q-corrections of the post-stream state from the carried plane sums (interior cells) or by pulling the
 // populations (everything k_collide_carry could not serve)
 __global__ void __launch_bounds__(128, 6) k_qcorr_combine(const double* __restrict__ fin, const double* __restrict__ gin,
-                                                       const uint32_t* __restrict__ nbr, const double* __restrict__ part,
-                                                       double* __restrict__ qc, const __grid_constant__ Layout L,
-                                                       const __grid_constant__ Phys P, int k0)
+                                                          const uint32_t* __restrict__ nbr, const double* __restrict__ part,
+                                                          double* __restrict__ qc, const __grid_constant__ Layout L,
+                                                          const __grid_constant__ Phys P, int k0)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= L.nx) return;
@@ -470,13 +504,13 @@ __global__ void __launch_bounds__(128, 6) k_qcorr_combine(const double* __restri
         qcorr_cell<true>(fin, gin, nbr, qc, L, P, i, j, k);
         return;
     }
-    const long long cm = L.cell(i, j == 0 ? L.ny - 1 : j - 1, k);      // source row j-1 sends with b = +1
-    const long long cp = L.cell(i, j == L.ny - 1 ? 0 : j + 1, k);      // source row j+1 sends with b = -1
+    const long long cm = L.cell(i, j, k == 0 ? L.nz - 1 : k - 1);      // source plane k-1 sends with c = +1
+    const long long cp = L.cell(i, j, k == L.nz - 1 ? 0 : k + 1);      // source plane k+1 sends with c = -1
     const double rm = part[8 * n + cm], r0 = part[4 * n + c], rp = part[0 * n + cp];
     const double rho = rm + r0 + rp;
-    const double jy = rm - rp;
+    const double jz = rm - rp;
     const double jx = part[9 * n + cm] + part[5 * n + c] + part[1 * n + cp];
-    const double jz = part[10 * n + cm] + part[6 * n + c] + part[2 * n + cp];
+    const double jy = part[10 * n + cm] + part[6 * n + c] + part[2 * n + cp];
     const double e2 = part[11 * n + cm] + part[7 * n + c] + part[3 * n + cp];
     const Prim s = primitives(rho, jx, jy, jz, e2, P);
     qc[c] = s.qcx;
@@ -1282,13 +1316,15 @@ int launch_collide(const Layout& L, const Phys& P, const double* fin, const doub
     return 1;
 }
 
-CarryPlan make_carry_plan(const Layout& L, int own, int kz)
+CarryPlan make_carry_plan(const Layout& L, int own, int ky)
 {
     CarryPlan C;
     C.own = (own == 28) ? 28 : 30;
     C.halo = (32 - C.own) / 2;
-    C.kz = kz < 1 ? 1 : (kz > L.nz ? L.nz : kz);
+    C.ky = ky < 1 ? 1 : (ky > L.ny ? L.ny : ky);
     C.nxc = (L.nx + C.own - 1) / C.own;
+    C.prefetch = 0;
+    if (const char* e = getenv("MBL_PREFETCH")) C.prefetch = atoi(e);
     return C;
 }
 
@@ -1306,11 +1342,20 @@ int launch_collide_carry(const Layout& L, const Phys& P, const CarryPlan& C, int
     }
     for (int d = 0; d < 3; ++d) A.qc[d] = qc + (long long)d * L.sq;
     for (int w = 0; w < CARRY_WORDS; ++w) A.part[w] = part + (long long)w * L.sq;
-    const dim3 grid((C.nxc + 3) / 4, L.ny, (L.nz + C.kz - 1) / C.kz);
-    if (min_blocks >= 3)
-        k_collide_carry<3><<<grid, 128, 0, st>>>(A, nbr, flag, L, P, C);
+    const dim3 grid((C.nxc + 3) / 4, (L.ny + C.ky - 1) / C.ky, L.nz);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_collide_carry<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CARRY_SMEM_BYTES);
+        cudaFuncSetAttribute(k_collide_carry<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CARRY_SMEM_BYTES);
+        cudaFuncSetAttribute(k_collide_carry<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, CARRY_SMEM_BYTES);
+        attr_done = true;
+    }
+    if (min_blocks >= 4)
+        k_collide_carry<4><<<grid, 128, CARRY_SMEM_BYTES, st>>>(A, nbr, flag, L, P, C);
+    else if (min_blocks == 3)
+        k_collide_carry<3><<<grid, 128, CARRY_SMEM_BYTES, st>>>(A, nbr, flag, L, P, C);
     else
-        k_collide_carry<2><<<grid, 128, 0, st>>>(A, nbr, flag, L, P, C);
+        k_collide_carry<2><<<grid, 128, CARRY_SMEM_BYTES, st>>>(A, nbr, flag, L, P, C);
     return 1;
 }
 

@@ -56,13 +56,14 @@ int launch_qcorr(const Layout& L, const Phys& P, const double* fin, const double
 int launch_collide(const Layout& L, const Phys& P, const double* fin, const double* gin, double* fout, double* gout,
                    const uint32_t* nbr, const uint8_t* flag, const double* qc, double* macro, bool pull,
                    cudaStream_t st, int ka = 0, int kb = 0);
-// "carry" step (kernels.cu: k_collide_carry / k_qcorr_combine): the collide kernel also emits the row sums of
+// "carry" step (kernels.cu: k_collide_carry / k_qcorr_combine): the collide kernel also emits partial sums of
 // the next post-stream state's conserved moments (12 words per cell, `part`), from which the next step's
 // q-corrections are assembled without touching the populations a second time.
 struct CarryPlan {
     int own, halo;  // cells a warp owns (own + 2 * halo = 32 lanes) and redundant cells on each side
-    int kz;         // planes a thread marches through
+    int ky;         // rows a thread marches through
     int nxc;        // warps per row
+    int prefetch;   // rows of L2 bulk-prefetch distance (0: off)
 };
 constexpr int CARRY_WORDS = 12;
 // per-component base pointers, passed by value in kernel parameter space
@@ -74,7 +75,7 @@ struct CarryPtrs {
     const double* qc[3];
     double* part[CARRY_WORDS];
 };
-CarryPlan make_carry_plan(const Layout& L, int own, int kz);
+CarryPlan make_carry_plan(const Layout& L, int own, int ky);
 int launch_collide_carry(const Layout& L, const Phys& P, const CarryPlan& C, int min_blocks, const double* fin,
                          const double* gin, double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag,
                          const double* qc, double* part, cudaStream_t st);

@@ -19,9 +19,10 @@ except Exception as e:
 PY
 }
 run v0 0 X=1
-for cfg in ${CONFIGS:-"64 30 2" "32 30 2" "128 30 2" "64 28 2" "64 30 3" "512 30 2"}; do
-  set -- $cfg
-  run v4_kz$1_own$2_b$3 4 MBL_KZ=$1 MBL_OWN=$2 MBL_MINB=$3
+# each config: comma-separated environment assignments (MBL_KY rows per march, MBL_OWN cells per warp, MBL_MINB CTAs/SM,
+# MBL_SYNC CTA barrier per row, MBL_PREFETCH rows of L2 prefetch distance)
+for cfg in ${CONFIGS:-"MBL_MINB=3" "MBL_MINB=2"}; do
+  run v4_$(echo $cfg | tr -d 'MBL_' | tr ',=' '__') 4 $(echo $cfg | tr ',' ' ')
 done
 if [ -z "$SKIP_NCU" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,lts__t_sector_hit_rate.pct,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum \

@@ -19,8 +19,8 @@ def golden_fields(z, s):
 # that small boxes still exercise several z-chunks, ragged chunks, several warps per row and both launch bounds
 CARRY_ENV = {
     "carry": {},
-    "carry-kz5-own28": {"MBL_KZ": "5", "MBL_OWN": "28", "MBL_MINB": "3"},
-    "carry-kz1": {"MBL_KZ": "1"},
+    "carry-ky5-own28": {"MBL_KY": "5", "MBL_OWN": "28", "MBL_MINB": "3"},
+    "carry-ky1": {"MBL_KY": "1"},
 }
 
 
@@ -37,7 +37,7 @@ def new_lbm(deck_text, is_fluid=None, overrides=None, variant=None):
     from marbles_b200.lbm import LBM
     deck = parse_deck(text=deck_text, overrides=overrides)
     variant, env = variant_of(variant)
-    for k in ("MBL_KZ", "MBL_OWN", "MBL_MINB"):
+    for k in ("MBL_KY", "MBL_OWN", "MBL_MINB"):
         os.environ.pop(k, None)
     os.environ.update(env)  # read by mbl_create
     lbm = LBM(deck, is_fluid=is_fluid, variant=variant)
@@ -47,8 +47,8 @@ def new_lbm(deck_text, is_fluid=None, overrides=None, variant=None):
 
 # fused: mbl_step with the persistent TMA kernel (variant 1, the default), its two job types as two
 # launches (2), or the two plain kernels (0); unfused: the reference-granular operator sequence
-@pytest.mark.parametrize("fused", [1, 2, 3, 0, "carry", "carry-kz5-own28", None],
-                         ids=["fused-tma", "twopass-tma", "fused-plain", "twopass-plain", "carry", "carry-kz5-own28", "unfused"])
+@pytest.mark.parametrize("fused", [1, 2, 3, 0, "carry", "carry-ky5-own28", None],
+                         ids=["fused-tma", "twopass-tma", "fused-plain", "twopass-plain", "carry", "carry-ky5-own28", "unfused"])
 @pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_cuda_vs_reference_golden(case, fused):
     z, deck_text, steps = load_golden(case)
@@ -102,8 +102,8 @@ def test_geometry_matches_reference_is_fluid():
         assert np.array_equal(a, z["is_fluid"].astype(np.int32)), case
 
 
-@pytest.mark.parametrize("variant", [1, 3, 0, "carry", "carry-kz5-own28", "carry-kz1"],
-                         ids=["fused-tma", "fused-plain", "twopass-plain", "carry", "carry-kz5-own28", "carry-kz1"])
+@pytest.mark.parametrize("variant", [1, 3, 0, "carry", "carry-ky5-own28", "carry-ky1"],
+                         ids=["fused-tma", "fused-plain", "twopass-plain", "carry", "carry-ky5-own28", "carry-ky1"])
 @pytest.mark.parametrize("case", ["chcyl", "pressure", "slip", "tg12"])
 def test_random_state_vs_oracle(oracle_mod, case, variant):
     """seeded random perturbation of f, g and a random solid mask, 3 steps, all boundary types"""
@@ -199,7 +199,7 @@ def test_full_size_conservation_256(variant):
 
 @pytest.mark.parametrize("case,nz,world", [("tg12", 12, 2), ("tg12", 13, 3), ("sod48", 8, 2), ("chcyl", None, 2),
                                            ("pressure", None, 2)])
-@pytest.mark.parametrize("variant", [0, "carry-kz5-own28"], ids=["twopass-plain", "carry-kz5-own28"])
+@pytest.mark.parametrize("variant", [0, "carry-ky5-own28"], ids=["twopass-plain", "carry-ky5-own28"])
 def test_two_slabs_match_single_box(case, nz, world, variant):
     """the multi-rank scheme (z-slabs, ONE exchange of two ghost planes per step, q-correction of the first
     ghost plane recomputed locally, BC ghosts of neighbour-owned planes) on one device: the assembled slabs
@@ -211,7 +211,7 @@ def test_two_slabs_match_single_box(case, nz, world, variant):
     from marbles_b200.lbm import LBM, slab_bounds
     from marbles_b200.parallel import LocalSlabs
     variant, env = variant_of(variant)
-    for k in ("MBL_KZ", "MBL_OWN", "MBL_MINB"):
+    for k in ("MBL_KY", "MBL_OWN", "MBL_MINB"):
         os.environ.pop(k, None)
     os.environ.update(env)
     z, deck_text, _ = load_golden(case)
