@@ -217,7 +217,15 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keeps NCCL's version banner out of stdout (one JSON line)
+        # NCCL's own stream at high priority: the halo send/recv kernels run beside the interior collide
+        # kernel instead of queueing behind its pending CTAs
+        opts = None
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            pass
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     n = args.size
     deck = parse_deck(text=TG_DECK.format(nx=n, ny=n, nz=n * world, mgs=n))
     comm = HaloComm(rank, world, True, dev) if world > 1 else None
@@ -270,12 +278,13 @@ def main():
     peak, peak_src = measured_peak_gbs()
     collide_ms = kms[2] / max(nrec.value, 1)
     kname = {0: "k_collide<pull>", 1: "k_fused (q-correction + collide jobs)", 2: "k_fused (collide jobs)",
-             3: "k_fused_plain (q-correction + collide jobs)", 4: "k_collide_carry"}[args.variant]
+             3: "k_fused_plain (q-correction + collide jobs)", 4: "k_collide_carry", 5: "k_collide_tile"}[args.variant]
     vname = {0: "two plain kernels (q-correction, collide)", 1: "one persistent TMA-pipelined kernel per step",
              2: "persistent TMA kernel, two launches (q-correction, collide)",
              3: "one persistent kernel per step, plain loads",
              4: "carry step: k_qcorr_combine (row sums -> q-corrections) + k_collide_carry (collide, emits the next "
-                "step's moment row sums)"}[args.variant]
+                "step's moment row sums)",
+             5: "carry step without marching: k_qcorr_combine + k_collide_tile"}[args.variant]
     achieved = BYTES_PER_CELL * lbm.ncells / (collide_ms * 1e-3) / 1e9
     traffic = None
     try:

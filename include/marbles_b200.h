@@ -174,6 +174,18 @@ int64_t mbl_halo_doubles(mbl_ctx* ctx, int lev);
 int mbl_halo_pack(mbl_ctx* ctx, int lev, int side, double* device_buf);
 int mbl_halo_unpack(mbl_ctx* ctx, int lev, int side, const double* device_buf);
 
+/* The slab step with the halo exchange overlapped with the interior planes (all-periodic levels: the
+ * cross-rank part of FillBoundary, AMReX_FabArrayCommI.H:8-253, hidden behind the kernels).  Output plane k
+ * depends on input planes k-2..k+2, so:
+ *   mbl_step_split(part 0): the 2 outermost planes at each z-end (needs the current ghost planes)
+ *   mbl_halo_pack_next / exchange / mbl_halo_unpack_next on ANOTHER stream (mbl_set_stream): the boundary
+ *     planes just written travel to the neighbours' ghost planes of the buffers being written
+ *   mbl_step_split(part 1): the interior planes; the written buffers become current.
+ * The caller orders the streams with events (marbles_b200/lbm.py: LBM._step_overlapped). */
+int mbl_step_split(mbl_ctx* ctx, int lev, int part);
+int mbl_halo_pack_next(mbl_ctx* ctx, int lev, int side, double* device_buf);
+int mbl_halo_unpack_next(mbl_ctx* ctx, int lev, int side, const double* device_buf);
+
 /* host-buffer convenience used for the end-to-end measurement: upload f,g
  * (FAB layout, ghost ng), run nsteps, download f,g into the same buffers */
 int mbl_step_host(mbl_ctx* ctx, int lev, int nsteps, double time, double* f_fab, double* g_fab, int ng);
@@ -188,8 +200,11 @@ int mbl_get_timing(mbl_ctx* ctx, double ms[3], int* nsteps);
 /* select the implementation of mbl_step: 0 (default) = two kernels, k_qcorr (q-corrections of the
  * post-stream state) then k_collide (pull + collide); 1 = ONE persistent kernel per level with bulk-TMA
  * staged pulls, q-correction jobs and collide jobs interleaved; 2 = the same kernel launched once per job
- * type; 3 = one persistent warp-autonomous kernel with plain loads.  All give the same results; 0 is the
- * fastest measured on B200. */
+ * type; 3 = one persistent warp-autonomous kernel with plain loads; 4, 5 = "carry" steps whose collide kernel
+ * also emits partial sums of the next step's conserved moments, so the q-correction pass does not read the
+ * populations again (4: threads march through rows, 5: one cell per thread, rows exchanged inside the CTA).
+ * 0-3 give identical results, 4-5 agree to round-off (the moments are summed in another order); DESIGN.md
+ * has the measurements. */
 int mbl_set_variant(mbl_ctx* ctx, int variant);
 
 #ifdef __cplusplus

@@ -77,6 +77,9 @@ SYMBOLS = {
     "mbl_halo_doubles": (C.c_int64, [_P, C.c_int]),
     "mbl_halo_pack": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "mbl_halo_unpack": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "mbl_step_split": (C.c_int, [_P, C.c_int, C.c_int]),
+    "mbl_halo_pack_next": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "mbl_halo_unpack_next": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "mbl_step_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D, _D, C.c_int]),
     "mbl_launch_count": (C.c_int64, [_P]),
     "mbl_set_variant": (C.c_int, [_P, C.c_int]),

@@ -74,12 +74,13 @@ struct mbl_ctx {
     // 3: persistent warp-autonomous kernel (plain loads) with both job types.  DESIGN.md has the numbers.
     int variant = 0;
     int uw = 128, band_rows = 16, lag_per_cta = 4;  // variants 1-3 tuning (MBL_UW / MBL_BAND / MBL_LAG)
-    int carry_own = 30, carry_ky = 32, carry_minb = 3;  // variant 4 tuning (MBL_OWN / MBL_KY / MBL_MINB)
+    int carry_own = 30, carry_ky = 32, carry_minb = 2, carry_rows = 8;  // variant 4 tuning (MBL_OWN / MBL_KY / MBL_MINB)
     int sm_count = 148;
     cudaStream_t s_up = nullptr, s_down = nullptr;  // copy streams of the pipelined mbl_step_host
     int host_chunk = 16;  // planes per upload chunk (MBL_HOST_CHUNK; negative: no pipelining)
     bool timing = false;
-    std::vector<cudaEvent_t> events;  // 4 per timed step: before ghost fill, q-corr, collide, after
+    std::vector<cudaEvent_t> events;  // 4 per timed record: before ghost fill, q-corr, collide, after
+    int timed_steps = 0;              // steps covered by the records (a split step makes two records)
 };
 
 namespace {
@@ -161,7 +162,7 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
     if (need_ghosts) ctx->launches += launch_ghost_fill(lv.L, lv.B, lv.p.f[a], lv.p.g[a], lv.local_z, true, true, st);
     mark();
     double* macro = want_macro ? lv.macro : nullptr;
-    if (ctx->variant == 4) {
+    if (ctx->variant == 4 || ctx->variant == 5) {
         // carry step: q-corrections from the partial sums the previous collide left behind (first step, or after
         // anything else wrote the lattice: the full q-correction pass)
         if (!lv.part) CU(cudaMalloc(&lv.part, (size_t)CARRY_WORDS * lv.L.sq * sizeof(double)));
@@ -176,8 +177,13 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
             lv.carry_valid = false;
         } else {
             const CarryPlan C = make_carry_plan(Lk, ctx->carry_own, ctx->carry_ky);
-            ctx->launches += launch_collide_carry(Lk, lv.P, C, ctx->carry_minb, lv.p.f[a], lv.p.g[a], lv.p.f[b],
-                                                  lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, lv.part, st);
+            const int nl = ctx->variant == 4
+                               ? launch_collide_carry(Lk, lv.P, C, ctx->carry_minb, lv.p.f[a], lv.p.g[a], lv.p.f[b],
+                                                      lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, lv.part, st)
+                               : launch_collide_tile(Lk, lv.P, C, ctx->carry_rows, lv.p.f[a], lv.p.g[a], lv.p.f[b],
+                                                     lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, lv.part, st);
+            if (nl < 0) return fail("carry step: a lattice component exceeds 4 GB (32-bit byte offsets)");
+            ctx->launches += nl;
             lv.carry_valid = true;
         }
     } else if (ctx->variant == 0) {
@@ -202,6 +208,7 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
                                       lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, macro, lv.counters, st);
     }
     mark();
+    if (ctx->timing) ctx->timed_steps++;
     lv.cur = b;
     CU(cudaGetLastError());
     return 0;
@@ -238,10 +245,11 @@ int mbl_create(const mbl_params* params, int device, mbl_ctx** out)
     if (const char* e = getenv("MBL_UW")) c->uw = atoi(e) == 256 ? 256 : 128;
     if (const char* e = getenv("MBL_BAND")) c->band_rows = atoi(e) > 0 ? atoi(e) : 16;
     if (const char* e = getenv("MBL_LAG")) c->lag_per_cta = atoi(e) > 0 ? atoi(e) : 4;
+    if (const char* e = getenv("MBL_ROWS")) c->carry_rows = atoi(e);
     if (const char* e = getenv("MBL_HOST_CHUNK")) c->host_chunk = atoi(e);
     if (const char* e = getenv("MBL_OWN")) c->carry_own = atoi(e) == 28 ? 28 : 30;
     if (const char* e = getenv("MBL_KY")) c->carry_ky = atoi(e) > 0 ? atoi(e) : 32;
-    if (const char* e = getenv("MBL_MINB")) c->carry_minb = atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 3;
+    if (const char* e = getenv("MBL_MINB")) c->carry_minb = atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 2;
     init_tables();
     CU(cudaGetLastError());
     *out = c;
@@ -414,6 +422,35 @@ int mbl_set_is_fluid(mbl_ctx* ctx, int lev, const int32_t* is_fluid, int ng)
     return 0;
 }
 
+// planes [ka, kb) of the components of one lattice (or of the macrodata) between a host FAB (ghost width ng, interior only)
+// and the padded SoA buffer: one pitched DMA per component, no staging kernel
+// (with_ghosts: also the FAB's ghost cells the device layout has room for, as mbl_upload does)
+static int copy_planes(Level& lv, double* soa, double* fab, int ng, int ka, int kb, bool to_device, cudaStream_t st,
+                       bool with_ghosts = false, int ncomp = NQ)
+{
+    const Layout& L = lv.L;
+    const size_t sx = L.nx + 2 * ng, sy = L.ny + 2 * ng, n = sx * sy * (L.nz + 2 * ng);
+    const int gx = with_ghosts ? std::min(ng, GX) : 0, gy = with_ghosts ? std::min(ng, GY) : 0,
+              gz = with_ghosts ? std::min(ng, GZ) : 0;
+    ka -= gz, kb += gz;
+    for (int q = 0; q < ncomp; ++q) {
+        cudaMemcpy3DParms p;
+        memset(&p, 0, sizeof(p));
+        cudaPitchedPtr host = make_cudaPitchedPtr(fab + (size_t)q * n, sx * sizeof(double), sx, sy);
+        cudaPitchedPtr dev = make_cudaPitchedPtr(soa + (size_t)q * L.sq, L.px * sizeof(double), L.px, L.ny + 2 * GY);
+        const cudaPos hpos = make_cudaPos((size_t)(ng - gx) * sizeof(double), ng - gy, ng + ka);
+        const cudaPos dpos = make_cudaPos((size_t)(OX - gx) * sizeof(double), GY - gy, GZ + ka);
+        p.srcPtr = to_device ? host : dev;
+        p.srcPos = to_device ? hpos : dpos;
+        p.dstPtr = to_device ? dev : host;
+        p.dstPos = to_device ? dpos : hpos;
+        p.extent = make_cudaExtent((L.nx + 2 * gx) * sizeof(double), L.ny + 2 * gy, kb - ka);
+        p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+        CU(cudaMemcpy3DAsync(&p, st));
+    }
+    return 0;
+}
+
 int mbl_upload(mbl_ctx* ctx, int lev, int which, const double* fab, int ng)
 {
     if (check_level(ctx, lev)) return 1;
@@ -421,39 +458,19 @@ int mbl_upload(mbl_ctx* ctx, int lev, int which, const double* fab, int ng)
     Level& lv = ctx->lev[lev];
     lv.carry_valid = false;
     CU(cudaSetDevice(ctx->device));
-    const size_t n = (size_t)(lv.L.nx + 2 * ng) * (lv.L.ny + 2 * ng) * (lv.L.nz + 2 * ng);
-    if (ensure_stage(lv, n * sizeof(double))) return 1;
-    double* dst = which == MBL_G ? curg(lv) : curf(lv);
-    for (int q = 0; q < NQ; ++q) {
-        CU(cudaMemcpyAsync(lv.stage, fab + (size_t)q * n, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        ctx->launches += launch_fab_to_soa(lv.L, lv.stage, ng, dst + (size_t)q * lv.L.sq, 1, ctx->stream);
-    }
+    // valid cells plus the FAB ghost cells the device layout has room for, one pitched DMA per component
+    if (copy_planes(lv, which == MBL_G ? curg(lv) : curf(lv), const_cast<double*>(fab), ng, 0, lv.L.nz, true, ctx->stream,
+                    true))
+        return 1;
     CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaGetLastError());
     return 0;
 }
 
 static int download_comps(mbl_ctx* ctx, Level& lv, const double* src, int ncomp, double* fab, int ng)
 {
-    // valid cells only: compact on the device, then one strided copy into the interior of the
-    // host FAB (its ghost cells are left untouched)
-    const size_t nv = (size_t)lv.L.nx * lv.L.ny * lv.L.nz;
-    const size_t sx = lv.L.nx + 2 * ng, sy = lv.L.ny + 2 * ng, n = sx * sy * (lv.L.nz + 2 * ng);
-    if (ensure_stage(lv, nv * sizeof(double))) return 1;
-    for (int q = 0; q < ncomp; ++q) {
-        ctx->launches += launch_soa_to_fab(lv.L, src + (size_t)q * lv.L.sq, 0, lv.stage, ctx->stream);
-        cudaMemcpy3DParms p;
-        memset(&p, 0, sizeof(p));
-        p.srcPtr = make_cudaPitchedPtr(lv.stage, lv.L.nx * sizeof(double), lv.L.nx, lv.L.ny);
-        p.dstPtr = make_cudaPitchedPtr(fab + (size_t)q * n, sx * sizeof(double), sx, sy);
-        p.dstPos = make_cudaPos((size_t)ng * sizeof(double), ng, ng);
-        p.extent = make_cudaExtent(lv.L.nx * sizeof(double), lv.L.ny, lv.L.nz);
-        p.kind = cudaMemcpyDeviceToHost;
-        CU(cudaMemcpy3DAsync(&p, ctx->stream));
-        // the staging buffer is reused by the next component
-        CU(cudaStreamSynchronize(ctx->stream));
-    }
-    CU(cudaGetLastError());
+    // valid cells only, straight into the interior of the host FAB (its ghost cells are left untouched)
+    if (copy_planes(lv, const_cast<double*>(src), fab, ng, 0, lv.L.nz, false, ctx->stream, false, ncomp)) return 1;
+    CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -609,6 +626,82 @@ int mbl_step(mbl_ctx* ctx, int lev, int nsteps, double time, int want_macro)
     return 0;
 }
 
+// Overlapped slab step.  Output plane k needs input planes k-2 .. k+2 (the q-correction of k+-1 pulls from
+// k+-2), so only the GZ = 2 outermost planes at each z-end depend on the neighbours' ghost planes.
+//   part 0: q-corrections of planes [-1, 3) and [nz-3, nz+1), collide of planes [0, 2) and [nz-2, nz)
+//   part 1: q-corrections of planes [3, nz-3), collide of planes [2, nz-2); the written buffers become current
+// Between the two the caller packs the freshly written boundary planes (mbl_halo_pack_next), exchanges them
+// and unpacks them into the ghost planes of the written buffers (mbl_halo_unpack_next) on another stream.
+int mbl_step_split(mbl_ctx* ctx, int lev, int part)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    const Layout& L = lv.L;
+    if (!(L.wrap[0] && L.wrap[1])) return fail("mbl_step_split: only for all-periodic levels (no ghost fill between the parts)");
+    if (L.nz < 8) return fail("mbl_step_split: a slab needs at least 8 planes");
+    if (part != 0 && part != 1) return fail("mbl_step_split: part must be 0 or 1");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int a = lv.cur, b = 1 - lv.cur, nz = L.nz;
+    auto mark = [&]() {
+        if (!ctx->timing) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ctx->events.push_back(e);
+    };
+    auto q = [&](int ka, int kb) {
+        ctx->launches += launch_qcorr(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st, ka, kb);
+    };
+    auto c = [&](int ka, int kb) {
+        ctx->launches += launch_collide(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
+                                        lv.p.qc, nullptr, true, st, ka, kb);
+    };
+    if (part == 0) {
+        // a z-end that is a periodic image of the box itself (single rank in z) has no ghost planes to wait for,
+        // but the split is still valid: the kernels wrap
+        const int klo = L.wrap[2] ? 0 : -1, khi = L.wrap[2] ? nz : nz + 1;
+        mark(), mark();
+        q(klo, 3);
+        q(nz - 3, khi);
+        mark();
+        c(0, 2);
+        c(nz - 2, nz);
+        mark();
+    } else {
+        mark(), mark();
+        if (nz > 6) q(3, nz - 3);
+        mark();
+        c(2, nz - 2);
+        mark();
+        if (ctx->timing) ctx->timed_steps++;
+        lv.cur = b;
+        lv.carry_valid = false;
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbl_halo_pack_next(mbl_ctx* ctx, int lev, int side, double* buf)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches += launch_halo_pack(lv.L, lv.p.f[1 - lv.cur], lv.p.g[1 - lv.cur], side, buf, ctx->stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbl_halo_unpack_next(mbl_ctx* ctx, int lev, int side, const double* buf)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches += launch_halo_unpack(lv.L, lv.p.f[1 - lv.cur], lv.p.g[1 - lv.cur], side, buf, ctx->stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int64_t mbl_halo_doubles(mbl_ctx* ctx, int lev)
 {
     if (check_level(ctx, lev)) return -1;
@@ -632,35 +725,6 @@ int mbl_halo_unpack(mbl_ctx* ctx, int lev, int side, const double* buf)
     CU(cudaSetDevice(ctx->device));
     ctx->launches += launch_halo_unpack(lv.L, curf(lv), curg(lv), side, buf, ctx->stream);
     CU(cudaGetLastError());
-    return 0;
-}
-
-// planes [ka, kb) of all 27 components of one lattice between a host FAB (ghost width ng, interior only)
-// and the padded SoA buffer: one pitched DMA per component, no staging kernel
-// (with_ghosts: also the FAB's ghost cells the device layout has room for, as mbl_upload does)
-static int copy_planes(Level& lv, double* soa, double* fab, int ng, int ka, int kb, bool to_device, cudaStream_t st,
-                       bool with_ghosts = false)
-{
-    const Layout& L = lv.L;
-    const size_t sx = L.nx + 2 * ng, sy = L.ny + 2 * ng, n = sx * sy * (L.nz + 2 * ng);
-    const int gx = with_ghosts ? std::min(ng, GX) : 0, gy = with_ghosts ? std::min(ng, GY) : 0,
-              gz = with_ghosts ? std::min(ng, GZ) : 0;
-    ka -= gz, kb += gz;
-    for (int q = 0; q < NQ; ++q) {
-        cudaMemcpy3DParms p;
-        memset(&p, 0, sizeof(p));
-        cudaPitchedPtr host = make_cudaPitchedPtr(fab + (size_t)q * n, sx * sizeof(double), sx, sy);
-        cudaPitchedPtr dev = make_cudaPitchedPtr(soa + (size_t)q * L.sq, L.px * sizeof(double), L.px, L.ny + 2 * GY);
-        const cudaPos hpos = make_cudaPos((size_t)(ng - gx) * sizeof(double), ng - gy, ng + ka);
-        const cudaPos dpos = make_cudaPos((size_t)(OX - gx) * sizeof(double), GY - gy, GZ + ka);
-        p.srcPtr = to_device ? host : dev;
-        p.srcPos = to_device ? hpos : dpos;
-        p.dstPtr = to_device ? dev : host;
-        p.dstPos = to_device ? dpos : hpos;
-        p.extent = make_cudaExtent((L.nx + 2 * gx) * sizeof(double), L.ny + 2 * gy, kb - ka);
-        p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
-        CU(cudaMemcpy3DAsync(&p, st));
-    }
     return 0;
 }
 
@@ -758,6 +822,7 @@ int mbl_set_timing(mbl_ctx* ctx, int on)
     if (!ctx) return fail("null context");
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     ctx->events.clear();
+    ctx->timed_steps = 0;
     ctx->timing = on != 0;
     return 0;
 }
@@ -768,8 +833,9 @@ int mbl_get_timing(mbl_ctx* ctx, double ms[3], int* nsteps)
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     ms[0] = ms[1] = ms[2] = 0.0;
-    *nsteps = (int)(ctx->events.size() / 4);
-    for (int s = 0; s < *nsteps; ++s)
+    *nsteps = ctx->timed_steps;
+    const int nrec = (int)(ctx->events.size() / 4);
+    for (int s = 0; s < nrec; ++s)
         for (int k = 0; k < 3; ++k) {
             float t = 0.f;
             CU(cudaEventElapsedTime(&t, ctx->events[4 * s + k], ctx->events[4 * s + k + 1]));
@@ -781,7 +847,7 @@ int mbl_get_timing(mbl_ctx* ctx, double ms[3], int* nsteps)
 int mbl_set_variant(mbl_ctx* ctx, int variant)
 {
     if (!ctx) return fail("null context");
-    if (variant < 0 || variant > 4) return fail("variant %d is not available", variant);
+    if (variant < 0 || variant > 5) return fail("variant %d is not available", variant);
     ctx->variant = variant;
     for (int l = 0; l < MAX_LEVELS; ++l) ctx->lev[l].carry_valid = false;
     return 0;

@@ -293,6 +293,7 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes)
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all_after(double& dep) { asm volatile("cp.async.wait_all;" : "+d"(dep)::"memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int MINB>
@@ -480,6 +481,167 @@ __global__ void __launch_bounds__(128, MINB)
             ring[(12 + 3 * d + 0) * 128] = TC[d][0];
             ring[(12 + 3 * d + 1) * 128] = TC[d][1];
             ring[(12 + 3 * d + 2) * 128] = EC[d];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// The same carried sums without marching: a CTA is W warps = W consecutive rows of one warp-wide column strip,
+// one cell per thread, so CTAs sweep the box in launch order exactly like k_collide (the DRAM streams stay
+// compact; marching spreads the resident CTAs over rows that are KY rows apart).  x is reduced by shuffles as
+// above, y by one exchange through shared memory between the warps of the CTA; the first and the last row of a
+// CTA are halo rows that are collided redundantly (their populations come out of L2: the neighbouring CTA is
+// resident at the same time) and store nothing.  g again travels global -> shared by cp.async, and the exchange
+// reuses those slots.
+// ---------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(32 * W, (W <= 8 ? 2 : 1))
+    k_collide_tile(const __grid_constant__ CarryPtrs A, const uint32_t* __restrict__ nbr,
+                   const uint8_t* __restrict__ flag, const __grid_constant__ Layout L, const __grid_constant__ Phys P,
+                   const __grid_constant__ CarryPlan C)
+{
+    constexpr int T = 32 * W;
+    extern __shared__ double smem[];
+    double* const sg = smem + threadIdx.x;  // sg[slot * T]
+    const unsigned sg_addr = (unsigned)__cvta_generic_to_shared(sg);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int xc = blockIdx.x;
+    const int y0 = blockIdx.y * (W - 2);
+    const int k = blockIdx.z;
+    const int i = xc * C.own - C.halo + lane;
+    const int jr = y0 - 1 + w;  // row of this warp; w = 0 and w = W-1 are the halo rows
+    const bool own = lane >= C.halo && lane < C.halo + C.own && i < L.nx && w >= 1 && w <= W - 2 && jr < L.ny;
+    // cell this thread collides: its own, the periodic image for halo lanes / rows over a wrapped edge, otherwise
+    // clamped (what such a thread contributes lands in cells k_qcorr_combine does not take from the carried sums)
+    int is = i, j = jr;
+    if (is < 0) is = L.wrap[0] ? is + L.nx : 0;
+    if (is >= L.nx) is = (L.wrap[0] && is - L.nx < L.nx) ? is - L.nx : L.nx - 1;
+    if (j < 0) j = L.wrap[1] ? j + L.ny : 0;
+    if (j >= L.ny) j = (L.wrap[1] && j - L.ny < L.ny) ? j - L.ny : L.ny - 1;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned px8 = (unsigned)L.px * 8u, sz8 = (unsigned)L.sz * 8u;
+    unsigned xo[3], yo[3], zo[3];
+    xo[1] = yo[1] = zo[1] = 0u;
+    xo[2] = (L.wrap[0] && is == 0) ? (unsigned)(L.nx - 1) * 8u : 0u - 8u;
+    xo[0] = (L.wrap[0] && is == L.nx - 1) ? 0u - (unsigned)(L.nx - 1) * 8u : 8u;
+    yo[2] = (L.wrap[1] && j == 0) ? (unsigned)(L.ny - 1) * px8 : 0u - px8;
+    yo[0] = (L.wrap[1] && j == L.ny - 1) ? 0u - (unsigned)(L.ny - 1) * px8 : px8;
+    zo[2] = (L.wrap[2] && k == 0) ? (unsigned)(L.nz - 1) * sz8 : 0u - sz8;
+    zo[0] = (L.wrap[2] && k == L.nz - 1) ? 0u - (unsigned)(L.nz - 1) * sz8 : sz8;
+    const unsigned c = (unsigned)(is + OX) * 8u + (unsigned)(j + GY) * px8 + (unsigned)(k + GZ) * sz8;
+    auto ldb = [](const double* base, unsigned off) { return *(const double*)((const char*)base + off); };
+    auto stb = [](double* base, unsigned off, double v) { *(double*)((char*)base + off) = v; };
+    unsigned cyz[3][3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) cyz[b][d] = c + yo[b] + zo[d];
+    // g: global -> shared, asynchronously, no registers
+    static_for<0, NQ>([&](auto qc_) {
+        constexpr int Q = decltype(qc_)::value;
+        cp_async8(sg_addr + Q * T * 8, (const char*)A.gin[Q] + (cyz[ey(Q) + 1][ez(Q) + 1] + xo[ex(Q) + 1]));
+    });
+    const uint32_t m = *(const uint32_t*)((const char*)nbr + (c >> 1));
+    const unsigned fb = flag[c >> 3];
+    const double qxp = ldb(A.qc[0], c + 8u), qxm = ldb(A.qc[0], c - 8u);
+    const double qyp = ldb(A.qc[1], c + px8), qym = ldb(A.qc[1], c - px8);
+    const double qzp = ldb(A.qc[2], c + sz8), qzm = ldb(A.qc[2], c - sz8);
+    double f[NQ];
+    static_for<0, NQ>([&](auto qc_) {
+        constexpr int Q = decltype(qc_)::value;
+        f[Q] = ldb(A.fin[Q], cyz[ey(Q) + 1][ez(Q) + 1] + xo[ex(Q) + 1]);
+    });
+    const bool fluid = m & 1u;
+    if (m != ALL_FLUID) {
+        if (fluid) {
+            // halfway bounce-back: the cell's own opposite population (LBM.cpp:590-595 in pull form)
+            static_for<1, NQ>([&](auto qc_) {
+                constexpr int Q = decltype(qc_)::value;
+                if (!((m >> Q) & 1u)) f[Q] = ldb(A.fin[opp(Q)], c);
+            });
+        } else {
+            // solid cell: the streamed value is the -1 sentinel (LBM.cpp:565, 582) and collide skips it;
+            // with omega = 0 below the "relaxed" value is exactly -1 again
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) f[q] = -1.0;
+        }
+    }
+    MomF mf = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    static_for<0, NQ>([&](auto qc_) { acc_f<decltype(qc_)::value>(mf, f[decltype(qc_)::value]); });
+    // wait for g only now, and tied to a value that needs every f: placed right after the cp.async issue, ptxas
+    // schedules the f loads behind the wait and the cell pays two DRAM latencies in series
+    cp_async_wait_all_after(mf.rho);
+    if (m != ALL_FLUID) {
+        if (fluid) {
+            static_for<1, NQ>([&](auto qc_) {
+                constexpr int Q = decltype(qc_)::value;
+                if (!((m >> Q) & 1u)) sg[Q * T] = ldb(A.gin[opp(Q)], c);
+            });
+        } else {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) sg[q * T] = -1.0;
+        }
+    }
+    MomG mg = {0, 0, 0, 0};
+    static_for<0, NQ>([&](auto qc_) { acc_g<decltype(qc_)::value>(mg, sg[decltype(qc_)::value * T]); });
+    const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
+    const double dqx = one_sided_gradient(fb & GRAD_PX, fb & GRAD_MX, (fb & GRAD_PX) ? qxp : 0.0, s.qcx,
+                                          (fb & GRAD_MX) ? qxm : 0.0, P.idx[0]);
+    const double dqy = one_sided_gradient(fb & GRAD_PY, fb & GRAD_MY, (fb & GRAD_PY) ? qyp : 0.0, s.qcy,
+                                          (fb & GRAD_MY) ? qym : 0.0, P.idx[1]);
+    const double dqz = one_sided_gradient(fb & GRAD_PZ, fb & GRAD_MZ, (fb & GRAD_PZ) ? qzp : 0.0, s.qcz,
+                                          (fb & GRAD_MZ) ? qzm : 0.0, P.idx[2]);
+    const Coll cc = collision_coefficients(s, mf, mg, dqx, dqy, dqz, P);
+    const double omega = fluid ? cc.omega : 0.0;
+    // this cell's contributions to rows j-1 (TA), j (TB), j+1 (TC): [plane c][rho, jx], then e2
+    double TA[3][2] = {}, TB[3][2] = {}, TC[3][2] = {};
+    double EA[3] = {}, EB[3] = {}, EC[3] = {};
+    static_for<0, NQ>([&](auto qc_) {
+        constexpr int Q = decltype(qc_)::value;
+        constexpr int d = ez(Q) + 1;
+        const double v = f[Q] + omega * (feq_q<Q>(cc) - f[Q]);
+        if (own) stb(A.fout[Q], c, v);
+        double t = v;
+        if constexpr (ex(Q) == 1) t = __shfl_up_sync(FULL, v, 1);
+        if constexpr (ex(Q) == -1) t = __shfl_down_sync(FULL, v, 1);
+        double(&Tt)[3][2] = ey(Q) == -1 ? TA : ey(Q) == 0 ? TB : TC;
+        Tt[d][0] += t;
+        if constexpr (ex(Q) == 1) Tt[d][1] += t;
+        if constexpr (ex(Q) == -1) Tt[d][1] -= t;
+    });
+    static_for<0, NQ>([&](auto qc_) {
+        constexpr int Q = decltype(qc_)::value;
+        constexpr int d = ez(Q) + 1;
+        const double gq = sg[Q * T];
+        const double v = gq + omega * (geq_q<Q>(cc) - gq);
+        if (own) stb(A.gout[Q], c, v);
+        double t = v;
+        if constexpr (ex(Q) == 1) t = __shfl_up_sync(FULL, v, 1);
+        if constexpr (ex(Q) == -1) t = __shfl_down_sync(FULL, v, 1);
+        double(&E)[3] = ey(Q) == -1 ? EA : ey(Q) == 0 ? EB : EC;
+        E[d] += t;
+    });
+    // y exchange: what this row sends down (TA, EA: slots 0..8) and up (TC, EC: slots 9..17), in the g slots
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        sg[(3 * d + 0) * T] = TA[d][0];
+        sg[(3 * d + 1) * T] = TA[d][1];
+        sg[(3 * d + 2) * T] = EA[d];
+        sg[(9 + 3 * d + 0) * T] = TC[d][0];
+        sg[(9 + 3 * d + 1) * T] = TC[d][1];
+        sg[(9 + 3 * d + 2) * T] = EC[d];
+    }
+    __syncthreads();
+    if (own) {
+        const double* up = sg + 32;   // row j+1: its e_y = -1 terms arrive here
+        const double* dn = sg - 32;   // row j-1: its e_y = +1 terms
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const double ua = up[(3 * d + 0) * T], dc = dn[(9 + 3 * d + 0) * T];
+            stb(A.part[4 * d + 0], c, TB[d][0] + ua + dc);
+            stb(A.part[4 * d + 1], c, TB[d][1] + up[(3 * d + 1) * T] + dn[(9 + 3 * d + 1) * T]);
+            stb(A.part[4 * d + 2], c, dc - ua);
+            stb(A.part[4 * d + 3], c, EB[d] + up[(3 * d + 2) * T] + dn[(9 + 3 * d + 2) * T]);
         }
     }
 }
@@ -1356,6 +1518,39 @@ int launch_collide_carry(const Layout& L, const Phys& P, const CarryPlan& C, int
         k_collide_carry<3><<<grid, 128, CARRY_SMEM_BYTES, st>>>(A, nbr, flag, L, P, C);
     else
         k_collide_carry<2><<<grid, 128, CARRY_SMEM_BYTES, st>>>(A, nbr, flag, L, P, C);
+    return 1;
+}
+
+int launch_collide_tile(const Layout& L, const Phys& P, const CarryPlan& C, int rows, const double* fin,
+                        const double* gin, double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag,
+                        const double* qc, double* part, cudaStream_t st)
+{
+    if (L.sq * 8 >= (1LL << 32)) return -1;  // 32-bit byte offsets inside a component
+    CarryPtrs A;
+    for (int q = 0; q < NQ; ++q) {
+        A.fin[q] = fin + (long long)q * L.sq;
+        A.gin[q] = gin + (long long)q * L.sq;
+        A.fout[q] = fout + (long long)q * L.sq;
+        A.gout[q] = gout + (long long)q * L.sq;
+    }
+    for (int d = 0; d < 3; ++d) A.qc[d] = qc + (long long)d * L.sq;
+    for (int w = 0; w < CARRY_WORDS; ++w) A.part[w] = part + (long long)w * L.sq;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_collide_tile<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ * 32 * 6 * 8);
+        cudaFuncSetAttribute(k_collide_tile<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ * 32 * 8 * 8);
+        cudaFuncSetAttribute(k_collide_tile<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ * 32 * 12 * 8);
+        attr_done = true;
+    }
+    const int W = rows == 6 ? 6 : rows == 12 ? 12 : 8;
+    const dim3 grid(C.nxc, (L.ny + W - 3) / (W - 2), L.nz);
+    const size_t sm = (size_t)NQ * 32 * W * 8;
+    if (W == 6)
+        k_collide_tile<6><<<grid, 32 * 6, sm, st>>>(A, nbr, flag, L, P, C);
+    else if (W == 12)
+        k_collide_tile<12><<<grid, 32 * 12, sm, st>>>(A, nbr, flag, L, P, C);
+    else
+        k_collide_tile<8><<<grid, 32 * 8, sm, st>>>(A, nbr, flag, L, P, C);
     return 1;
 }
 

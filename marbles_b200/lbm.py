@@ -21,6 +21,7 @@ Errors raise (the reference calls amrex::Abort).  No CPU fallback exists.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -62,6 +63,10 @@ class LBM:
             inputs = lbm_inputs(d)
         self.inp = inputs
         self.rank, self.world, self.comm = rank, world, comm
+        self.variant = 0 if variant is None else variant
+        self.cuda_stream = cuda_stream
+        self.overlap = os.environ.get("MBL_OVERLAP", "1") != "0"
+        self._ghosts_fresh = False  # the ghost planes of the current buffers hold the neighbours' planes
         self.lib = _lib.load()
         self.ctx = C.c_void_p()
         self.lev = 0
@@ -163,6 +168,7 @@ class LBM:
         v = (C.c_double * 16)(*self.inp.ic_params)
         check(self.lib.mbl_initialize(self.ctx, self.lev, self.inp.ic_kind, v, 16))
         self.time, self.isteps = 0.0, 0
+        self._ghosts_fresh = False
 
     # ---------------------------------------------------------------- operators
     def exchange_halo(self):
@@ -183,11 +189,13 @@ class LBM:
     def stream(self, lev: int = 0):
         """stream(lev, m_f); stream(lev, m_g) (Source/LBM.cpp:535-537)."""
         check(self.lib.mbl_stream(self.ctx, lev))
+        self._ghosts_fresh = False
 
     def collide(self, lev: int = 0, want_macrodata: bool = True):
         if self.world > 1:
             self.exchange_halo()  # post-stream state of the neighbours' edge planes (q-correction stencil)
         check(self.lib.mbl_collide(self.ctx, lev, int(want_macrodata)))
+        self._ghosts_fresh = False
 
     def advance(self, lev: int = 0):
         """LBM::advance (Source/LBM.cpp:523-544), un-fused."""
@@ -210,17 +218,43 @@ class LBM:
             f = self.comm.allreduce_sum(f)
         return f
 
+    def can_overlap(self) -> bool:
+        """The overlapped slab step (mbl_step_split) applies to all-periodic decks (no ghost fill between its
+        parts), the two-kernel variant and slabs of at least 8 planes."""
+        return (self.world > 1 and all(self.inp.periodic) and self.variant == 0 and self.n_local[2] >= 8
+                and self.comm is not None and hasattr(self.comm, "exchange_next") and self.overlap)
+
     def step(self, nsteps: int = 1, want_macrodata: bool = False):
         """Fused fast path: nsteps x (fillpatch f, g; stream f, g; collide)."""
         if self.world == 1:
             check(self.lib.mbl_step(self.ctx, self.lev, nsteps, self.time, int(want_macrodata)))
+        elif self.can_overlap() and nsteps > (1 if want_macrodata else 0):
+            self._step_overlapped(nsteps - (1 if want_macrodata else 0))
+            if want_macrodata:  # the last step stores all 19 fields: the plain slab step
+                self._ghosts_fresh = False
+                check(self.lib.mbl_step_local(self.ctx, self.lev, self.time + (nsteps - 1) * self.dt, 1))
         else:
             for s in range(nsteps):
                 self.exchange_halo()
                 check(self.lib.mbl_step_local(self.ctx, self.lev, self.time + s * self.dt,
                                               int(want_macrodata and s == nsteps - 1)))
+            self._ghosts_fresh = False
         self.time += nsteps * self.dt
         self.isteps += nsteps
+
+    def _step_overlapped(self, nsteps: int):
+        """Slab steps with the ghost-plane exchange hidden behind the interior planes: the two boundary planes
+        at each z-end are collided first (part 0), travel to the neighbours on the communicator's stream while
+        the interior planes are collided (part 1), and are awaited only by the next step's part 0."""
+        if not self._ghosts_fresh:
+            self.exchange_halo()  # blocking exchange of the current buffers' ghost planes
+            self._ghosts_fresh = True
+        for _ in range(nsteps):
+            self.comm.wait_exchange(self)                        # ghost planes of the current buffers are in
+            check(self.lib.mbl_step_split(self.ctx, self.lev, 0))
+            self.comm.exchange_next(self)                        # async: boundary planes of the written buffers
+            check(self.lib.mbl_step_split(self.ctx, self.lev, 1))
+        self.comm.wait_exchange(self)
 
     def evolve(self, max_step: int | None = None, fused: bool = True, want_macrodata: bool = False):
         """LBM::evolve (Source/LBM.cpp:398-448) without I/O."""
@@ -240,6 +274,7 @@ class LBM:
     def step_host(self, f_fab: np.ndarray, g_fab: np.ndarray, nsteps: int = 1, ng: int = F_NGHOST):
         """The reference-facing call with HOST buffers (FAB layout): upload, nsteps, download in place."""
         check(self.lib.mbl_step_host(self.ctx, self.lev, nsteps, self.time, _dptr(f_fab), _dptr(g_fab), ng))
+        self._ghosts_fresh = False
         self.time += nsteps * self.dt
         self.isteps += nsteps
 
@@ -254,6 +289,7 @@ class LBM:
         assert f.shape == self.fab_shape(NQ, ng) and g.shape == f.shape, (f.shape, self.fab_shape(NQ, ng))
         check(self.lib.mbl_upload(self.ctx, self.lev, 0, _dptr(f), ng))
         check(self.lib.mbl_upload(self.ctx, self.lev, 1, _dptr(g), ng))
+        self._ghosts_fresh = False
 
     def get_f(self, ng: int = 0) -> np.ndarray:
         a = np.zeros(self.fab_shape(NQ, ng))

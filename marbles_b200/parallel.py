@@ -72,6 +72,50 @@ class HaloComm:
         if self.upper is not None:
             check(lbm.lib.mbl_halo_unpack(lbm.ctx, lbm.lev, 1, C.c_void_p(recv_hi.data_ptr())))
 
+    # ---- overlapped exchange (LBM._step_overlapped) --------------------------------------------
+    def _side_stream(self, lbm):
+        if getattr(self, "xstream", None) is None:
+            # high priority: its small kernels must not queue behind the interior collide's pending CTAs
+            self.xstream = torch.cuda.Stream(device=self.device, priority=-1)
+            self.ev_boundary = torch.cuda.Event()
+            self.ev_exchanged = None
+            self.compute = torch.cuda.ExternalStream(lbm.cuda_stream, device=self.device) if lbm.cuda_stream \
+                else torch.cuda.default_stream(self.device)
+        return self.xstream
+
+    def exchange_next(self, lbm):
+        """Asynchronous: once part 0 of the step has written the boundary planes of the buffers being written,
+        pack them, swap them with the z-neighbours and unpack them into those buffers' ghost planes -- all on
+        the communicator's own stream, so part 1 (interior planes) runs at the same time."""
+        xs = self._side_stream(lbm)
+        n = int(lbm.lib.mbl_halo_doubles(lbm.ctx, lbm.lev))
+        send_lo, send_hi, recv_lo, recv_hi = self._buffers(n)
+        self.ev_boundary.record(self.compute)
+        xs.wait_event(self.ev_boundary)
+        check(lbm.lib.mbl_set_stream(lbm.ctx, C.c_void_p(xs.cuda_stream)))
+        try:
+            with torch.cuda.stream(xs):
+                if self.lower is not None:
+                    check(lbm.lib.mbl_halo_pack_next(lbm.ctx, lbm.lev, 0, C.c_void_p(send_lo.data_ptr())))
+                if self.upper is not None:
+                    check(lbm.lib.mbl_halo_pack_next(lbm.ctx, lbm.lev, 1, C.c_void_p(send_hi.data_ptr())))
+                exchange_buffers(send_lo, send_hi, recv_lo, recv_hi, self.lower, self.upper, self.group)
+                if self.lower is not None:
+                    check(lbm.lib.mbl_halo_unpack_next(lbm.ctx, lbm.lev, 0, C.c_void_p(recv_lo.data_ptr())))
+                if self.upper is not None:
+                    check(lbm.lib.mbl_halo_unpack_next(lbm.ctx, lbm.lev, 1, C.c_void_p(recv_hi.data_ptr())))
+                self.ev_exchanged = torch.cuda.Event()
+                self.ev_exchanged.record(xs)
+        finally:
+            check(lbm.lib.mbl_set_stream(lbm.ctx, C.c_void_p(self.compute.cuda_stream)))
+
+    def wait_exchange(self, lbm):
+        """the compute stream waits (on the device) for the last exchange_next"""
+        self._side_stream(lbm)
+        if self.ev_exchanged is not None:
+            self.compute.wait_event(self.ev_exchanged)
+            self.ev_exchanged = None
+
     def allreduce_sum(self, a):
         t = torch.as_tensor(a, dtype=torch.float64, device=self.device)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
@@ -112,6 +156,32 @@ class LocalSlabs:
             self.exchange()
             for s in self.slabs:
                 check(s.lib.mbl_step_local(s.ctx, 0, s.time, int(want_macrodata and it == nsteps - 1)))
+                s.time += s.dt
+                s.isteps += 1
+                s.sync()
+
+    def step_overlapped(self, nsteps: int = 1):
+        """the split step of LBM._step_overlapped, in its order: part 0 of every slab, the exchange of the
+        freshly written boundary planes into the written buffers' ghost planes, part 1"""
+        self.exchange()
+        for _ in range(nsteps):
+            for s in self.slabs:
+                check(s.lib.mbl_step_split(s.ctx, 0, 0))
+            if self.bufs is None:
+                self.exchange()
+            for s, (lo, hi) in zip(self.slabs, self.bufs):
+                check(s.lib.mbl_halo_pack_next(s.ctx, 0, 0, C.c_void_p(lo.data_ptr())))
+                check(s.lib.mbl_halo_pack_next(s.ctx, 0, 1, C.c_void_p(hi.data_ptr())))
+                s.sync()
+            for r, s in enumerate(self.slabs):
+                lower, upper = neighbours(r, self.world, self.periodic_z)
+                if lower is not None:
+                    check(s.lib.mbl_halo_unpack_next(s.ctx, 0, 0, C.c_void_p(self.bufs[lower][1].data_ptr())))
+                if upper is not None:
+                    check(s.lib.mbl_halo_unpack_next(s.ctx, 0, 1, C.c_void_p(self.bufs[upper][0].data_ptr())))
+                s.sync()
+            for s in self.slabs:
+                check(s.lib.mbl_step_split(s.ctx, 0, 1))
                 s.time += s.dt
                 s.isteps += 1
                 s.sync()

@@ -4,7 +4,7 @@
 OUT=gpurun_out/${1:-carry}
 mkdir -p $OUT
 if [ -z "$SKIP_TESTS" ]; then
-  timeout 900 python -m pytest tests -m gpu -x -q -k "carry" > $OUT/pytest_carry.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_carry.log
+  timeout 900 python -m pytest tests -m gpu -x -q -k "carry or tile" > $OUT/pytest_carry.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_carry.log
   tail -5 $OUT/pytest_carry.log
 fi
 run() { # name, variant, env...
@@ -22,11 +22,12 @@ run v0 0 X=1
 # each config: comma-separated environment assignments (MBL_KY rows per march, MBL_OWN cells per warp, MBL_MINB CTAs/SM,
 # MBL_SYNC CTA barrier per row, MBL_PREFETCH rows of L2 prefetch distance)
 for cfg in ${CONFIGS:-"MBL_MINB=3" "MBL_MINB=2"}; do
-  run v4_$(echo $cfg | tr -d 'MBL_' | tr ',=' '__') 4 $(echo $cfg | tr ',' ' ')
+  v=${VARIANT:-4}
+  run v${v}_$(echo $cfg | sed 's/MBL_//g' | tr ',=' '__') $v $(echo $cfg | tr ',' ' ')
 done
 if [ -z "$SKIP_NCU" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,lts__t_sector_hit_rate.pct,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum \
-     --clock-control none -k regex:'k_collide_carry|k_qcorr_combine' -s 4 -c 2 --csv --log-file $OUT/ncu_carry_256.csv \
-     python bench.py --variant 4 --size 256 --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_carry_256.log 2>&1
+     --clock-control none -k regex:'k_collide_carry|k_collide_tile|k_qcorr_combine' -s 4 -c 2 --csv --log-file $OUT/ncu_carry_256.csv \
+     python bench.py --variant ${VARIANT:-4} --size 256 --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_carry_256.log 2>&1
   tail -4 $OUT/ncu_carry_256.csv | cut -c1-400
 fi

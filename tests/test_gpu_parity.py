@@ -18,16 +18,20 @@ def golden_fields(z, s):
 # step variants (mbl_set_variant).  "carry*" = variant 4 with different marching / warp-overlap tunings so
 # that small boxes still exercise several z-chunks, ragged chunks, several warps per row and both launch bounds
 CARRY_ENV = {
-    "carry": {},
-    "carry-ky5-own28": {"MBL_KY": "5", "MBL_OWN": "28", "MBL_MINB": "3"},
-    "carry-ky1": {"MBL_KY": "1"},
+    "carry": (4, {}),
+    "carry-ky5-own28": (4, {"MBL_KY": "5", "MBL_OWN": "28", "MBL_MINB": "3"}),
+    "carry-ky1": (4, {"MBL_KY": "1"}),
+    "tile": (5, {}),
+    "tile-6rows-own28": (5, {"MBL_ROWS": "6", "MBL_OWN": "28"}),
+    "tile-12rows": (5, {"MBL_ROWS": "12"}),
 }
+TUNING_VARS = ("MBL_KY", "MBL_OWN", "MBL_MINB", "MBL_ROWS")
 
 
 def variant_of(v):
     """-> (variant number, environment overrides)"""
     if isinstance(v, str):
-        return 4, CARRY_ENV[v]
+        return CARRY_ENV[v]
     return v, {}
 
 
@@ -37,7 +41,7 @@ def new_lbm(deck_text, is_fluid=None, overrides=None, variant=None):
     from marbles_b200.lbm import LBM
     deck = parse_deck(text=deck_text, overrides=overrides)
     variant, env = variant_of(variant)
-    for k in ("MBL_KY", "MBL_OWN", "MBL_MINB"):
+    for k in TUNING_VARS:
         os.environ.pop(k, None)
     os.environ.update(env)  # read by mbl_create
     lbm = LBM(deck, is_fluid=is_fluid, variant=variant)
@@ -47,8 +51,9 @@ def new_lbm(deck_text, is_fluid=None, overrides=None, variant=None):
 
 # fused: mbl_step with the persistent TMA kernel (variant 1, the default), its two job types as two
 # launches (2), or the two plain kernels (0); unfused: the reference-granular operator sequence
-@pytest.mark.parametrize("fused", [1, 2, 3, 0, "carry", "carry-ky5-own28", None],
-                         ids=["fused-tma", "twopass-tma", "fused-plain", "twopass-plain", "carry", "carry-ky5-own28", "unfused"])
+@pytest.mark.parametrize("fused", [1, 2, 3, 0, "carry", "carry-ky5-own28", "tile", "tile-6rows-own28", None],
+                         ids=["fused-tma", "twopass-tma", "fused-plain", "twopass-plain", "carry", "carry-ky5-own28", "tile",
+                              "tile-6rows-own28", "unfused"])
 @pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_cuda_vs_reference_golden(case, fused):
     z, deck_text, steps = load_golden(case)
@@ -102,8 +107,9 @@ def test_geometry_matches_reference_is_fluid():
         assert np.array_equal(a, z["is_fluid"].astype(np.int32)), case
 
 
-@pytest.mark.parametrize("variant", [1, 3, 0, "carry", "carry-ky5-own28", "carry-ky1"],
-                         ids=["fused-tma", "fused-plain", "twopass-plain", "carry", "carry-ky5-own28", "carry-ky1"])
+@pytest.mark.parametrize("variant", [1, 3, 0, "carry", "carry-ky5-own28", "carry-ky1", "tile", "tile-6rows-own28", "tile-12rows"],
+                         ids=["fused-tma", "fused-plain", "twopass-plain", "carry", "carry-ky5-own28", "carry-ky1", "tile",
+                              "tile-6rows-own28", "tile-12rows"])
 @pytest.mark.parametrize("case", ["chcyl", "pressure", "slip", "tg12"])
 def test_random_state_vs_oracle(oracle_mod, case, variant):
     """seeded random perturbation of f, g and a random solid mask, 3 steps, all boundary types"""
@@ -153,7 +159,7 @@ def test_eb_forces_and_vorticity_vs_oracle(oracle_mod):
     lbm.close()
 
 
-@pytest.mark.parametrize("variant", [0, "carry"], ids=["twopass-plain", "carry"])
+@pytest.mark.parametrize("variant", [0, "carry", "tile"], ids=["twopass-plain", "carry", "tile"])
 def test_tg64_vs_oracle_and_conservation(oracle_mod, variant):
     """BASELINE config 1 (TG 64^3): 3 steps against the oracle, then size-independent properties"""
     O = oracle_mod
@@ -180,7 +186,7 @@ def test_tg64_vs_oracle_and_conservation(oracle_mod, variant):
     lbm.close()
 
 
-@pytest.mark.parametrize("variant", [0, "carry"], ids=["twopass-plain", "carry"])
+@pytest.mark.parametrize("variant", [0, "carry", "tile"], ids=["twopass-plain", "carry", "tile"])
 def test_full_size_conservation_256(variant):
     """periodic 256^3 (largest size the test box does in seconds): mass/energy conservation of
     stream+collide and agreement of the fused and un-fused operator sequences"""
@@ -199,7 +205,7 @@ def test_full_size_conservation_256(variant):
 
 @pytest.mark.parametrize("case,nz,world", [("tg12", 12, 2), ("tg12", 13, 3), ("sod48", 8, 2), ("chcyl", None, 2),
                                            ("pressure", None, 2)])
-@pytest.mark.parametrize("variant", [0, "carry-ky5-own28"], ids=["twopass-plain", "carry-ky5-own28"])
+@pytest.mark.parametrize("variant", [0, "carry-ky5-own28", "tile-6rows-own28"], ids=["twopass-plain", "carry-ky5-own28", "tile-6rows-own28"])
 def test_two_slabs_match_single_box(case, nz, world, variant):
     """the multi-rank scheme (z-slabs, ONE exchange of two ghost planes per step, q-correction of the first
     ghost plane recomputed locally, BC ghosts of neighbour-owned planes) on one device: the assembled slabs
@@ -211,7 +217,7 @@ def test_two_slabs_match_single_box(case, nz, world, variant):
     from marbles_b200.lbm import LBM, slab_bounds
     from marbles_b200.parallel import LocalSlabs
     variant, env = variant_of(variant)
-    for k in ("MBL_KY", "MBL_OWN", "MBL_MINB"):
+    for k in TUNING_VARS:
         os.environ.pop(k, None)
     os.environ.update(env)
     z, deck_text, _ = load_golden(case)
@@ -286,3 +292,31 @@ def test_step_host_matches_device_step(case, ov, chunk, ng):
     assert np.array_equal(b.get_f(), a.get_f())
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("nz,world", [(16, 2), (27, 3)])
+def test_overlapped_slab_step_matches_single_box(nz, world):
+    """mbl_step_split (boundary planes first, exchange of the written buffers' boundary planes, interior planes)
+    in the order LBM._step_overlapped issues it, on one device: bit-identical to the single box"""
+    import torch
+    from marbles_b200.inputs import parse_deck
+    from marbles_b200.lbm import LBM, slab_bounds
+    from marbles_b200.parallel import LocalSlabs
+    z, deck_text, _ = load_golden("tg12")
+    deck = parse_deck(text=deck_text, overrides=[f"amr.n_cell = 12 12 {nz}"])
+    single = LBM(deck, variant=0)
+    single.init_data()
+
+    def make(rank, w):
+        s = LBM(deck, rank=rank, world=w, comm=None, variant=0)
+        s.init_data()
+        return s
+
+    slabs = LocalSlabs(make, world, True, torch.device("cuda", 0))
+    single.step(5)
+    slabs.step_overlapped(3)
+    slabs.step(2)  # and back to the plain slab step
+    for get in (lambda s: s.get_f(), lambda s: s.get_g()):
+        assert np.array_equal(get(single), slabs.gather(get))
+    slabs.close()
+    single.close()
