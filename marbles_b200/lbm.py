@@ -323,6 +323,12 @@ class LBM:
             out[f"g_{q:02d}"] = g[q]
         return out
 
+    def write_plot_file(self, directory: str = ".", prefix: str = "plt") -> str:
+        """LBM::write_plot_file (Source/LBM.cpp:1677-1690): the current state as an AMReX plotfile
+        `<prefix><step:05d>`; the last step must have been taken with want_macrodata=True."""
+        from .plotfile import write_lbm_plotfile
+        return write_lbm_plotfile(self, directory, prefix)
+
     @property
     def launches(self) -> int:
         return int(self.lib.mbl_launch_count(self.ctx))

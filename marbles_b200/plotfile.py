@@ -1,0 +1,175 @@
+"""AMReX plotfile emission for the device-resident state.
+
+`LBM::write_plot_file` (Source/LBM.cpp:1677-1690) hands `plot_file_mf()` (Source/LBM.cpp:1629-1675: macrodata,
+then f and g if lbm.save_streaming, then the derived fields if lbm.save_derived, then the two is_fluid
+components) to `amrex::WriteMultiLevelPlotfile`.  This module writes the same on-disk format -- `Header`,
+`Level_0/Cell_H`, `Level_0/Cell_D_00000` with native little-endian doubles -- byte for byte for a single level
+(checked against files written by the unmodified reference, tests/test_plotfile.py), so post-processing
+(fcompare, yt, the reference's Tools/) keeps working when the step runs on the GPU.
+
+Host side only: the fields come from `LBM.fields()` / `get_derived()` (device -> host copies of the C ABI).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+MACRO_NAMES = ["rho", "vel_x", "vel_y", "vel_z", "vel_mag", "two_rho_e", "QCorrX", "QCorrY", "QCorrZ", "pxx", "pyy", "pzz",
+               "pxy", "pxz", "pyz", "qx", "qy", "qz", "temperature"]  # Source/LBM.cpp:302-340, Constants.H:8-31
+DERIVED_NAMES = ["vort_x", "vort_y", "vort_z", "vort_mag", "dQCorrX", "dQCorrY", "dQCorrZ"]  # Constants.H:39-47
+IS_FLUID_NAMES = ["is_fluid", "eb_boundary"]
+FAB_HEADER = "FAB ((8, (64 11 52 0 1 12 0 1023)),(8, (8 7 6 5 4 3 2 1)))"  # IEEE double, little endian
+
+
+def plot_file_var_names(save_streaming: bool = True, save_derived: bool = True) -> list[str]:
+    """LBM::plot_file_var_names (the order plot_file_mf copies the components in)"""
+    names = list(MACRO_NAMES)
+    if save_streaming:
+        names += [f"f_{q:02d}" for q in range(27)] + [f"g_{q:02d}" for q in range(27)]
+    if save_derived:
+        names += DERIVED_NAMES
+    return names + IS_FLUID_NAMES
+
+
+def chop_boxes(n_cell, max_grid_size: int):
+    """The level's BoxArray as AmrMesh::MakeNewGrids builds it for a single level: the domain chopped into
+    boxes of max_grid_size cells per side (a shorter last box where it does not divide), x fastest -- what
+    BoxArray::maxSize gives for the sizes the reference decks use (n a multiple of the blocking factor)."""
+    cuts = []
+    for d in range(3):
+        n = int(n_cell[d])
+        edges = list(range(0, n, max_grid_size)) + [n]
+        cuts.append([(edges[i], edges[i + 1] - 1) for i in range(len(edges) - 1)])
+    boxes = []
+    for kz in cuts[2]:
+        for jy in cuts[1]:
+            for ix in cuts[0]:
+                boxes.append(((ix[0], jy[0], kz[0]), (ix[1], jy[1], kz[1])))
+    return boxes
+
+
+def _g17(v: float) -> str:
+    """AMReX writes the reals of the Header with setprecision(17), default float format"""
+    return "%.17g" % float(v)
+
+
+def _box(lo, hi) -> str:
+    return f"(({lo[0]},{lo[1]},{lo[2]}) ({hi[0]},{hi[1]},{hi[2]}) (0,0,0))"
+
+
+def write_plotfile(path: str, names: list[str], data: np.ndarray, *, time: float, step: int, prob_lo, prob_hi,
+                   max_grid_size: int = 32) -> None:
+    """Write a single-level cell-centred plotfile.  data: [ncomp, nz, ny, nx] float64."""
+    data = np.asarray(data, dtype=np.float64)
+    ncomp, nz, ny, nx = data.shape
+    assert ncomp == len(names)
+    n = (nx, ny, nz)
+    dx = [(float(prob_hi[d]) - float(prob_lo[d])) / n[d] for d in range(3)]
+    boxes = chop_boxes(n, max_grid_size)
+    lev_dir = os.path.join(path, "Level_0")
+    os.makedirs(lev_dir, exist_ok=True)
+
+    # ---- Cell_D_00000 + per-box offsets, minima, maxima --------------------------------------------------
+    offsets, mins, maxs = [], [], []
+    with open(os.path.join(lev_dir, "Cell_D_00000"), "wb") as fh:
+        for lo, hi in boxes:
+            offsets.append(fh.tell())
+            sub = np.ascontiguousarray(data[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1])
+            fh.write(f"{FAB_HEADER}{_box(lo, hi)} {ncomp}\n".encode())
+            fh.write(sub.astype("<f8").tobytes())
+            flat = sub.reshape(ncomp, -1)
+            mins.append(flat.min(axis=1))
+            maxs.append(flat.max(axis=1))
+
+    # ---- Cell_H (VisMF header, version 1 = with min/max tables) -------------------------------------------
+    with open(os.path.join(lev_dir, "Cell_H"), "w") as fh:
+        fh.write(f"1\n1\n{ncomp}\n0\n")
+        fh.write(f"({len(boxes)} 0\n")
+        for lo, hi in boxes:
+            fh.write(_box(lo, hi) + "\n")
+        fh.write(")\n")
+        fh.write(f"{len(boxes)}\n")
+        for off in offsets:
+            fh.write(f"FabOnDisk: Cell_D_00000 {off}\n")
+        fh.write("\n")
+        for table in (mins, maxs):
+            fh.write(f"{len(boxes)},{ncomp}\n")
+            for row in table:
+                fh.write("".join("%.17e," % v for v in row) + "\n")
+            fh.write("\n")
+
+    # ---- Header (amrex::WriteGenericPlotfileHeader, AMReX_PlotFileUtil.cpp) --------------------------------
+    with open(os.path.join(path, "Header"), "w") as fh:
+        fh.write("HyperCLaw-V1.1\n")
+        fh.write(f"{ncomp}\n")
+        for nm in names:
+            fh.write(nm + "\n")
+        fh.write("3\n")
+        fh.write(_g17(time) + "\n")
+        fh.write("0\n")  # finest level
+        fh.write(" ".join(_g17(v) for v in prob_lo) + " \n")
+        fh.write(" ".join(_g17(v) for v in prob_hi) + " \n")
+        fh.write("\n")  # refinement ratios: none for a single level
+        fh.write(_box((0, 0, 0), (nx - 1, ny - 1, nz - 1)) + " \n")
+        fh.write(f"{step} \n")
+        fh.write(" ".join(_g17(v) for v in dx) + " \n")
+        fh.write("0\n0\n")  # coordinate system, boundary width
+        fh.write(f"0 {len(boxes)} {_g17(time)}\n")
+        fh.write(f"{step}\n")
+        for lo, hi in boxes:
+            for d in range(3):
+                fh.write(f"{_g17(prob_lo[d] + lo[d] * dx[d])} {_g17(prob_lo[d] + (hi[d] + 1) * dx[d])}\n")
+        fh.write("Level_0/Cell\n")
+
+
+def plot_file_name(prefix: str, step: int) -> str:
+    """amrex::Concatenate(plot_file, step, 5) (Source/LBM.cpp:1617-1621)"""
+    return f"{prefix}{step:05d}"
+
+
+def write_lbm_plotfile(lbm, directory: str = ".", prefix: str = "plt", max_grid_size: int | None = None,
+                       save_streaming: bool | None = None, save_derived: bool | None = None) -> str:
+    """LBM::write_plot_file for a single-rank `marbles_b200.lbm.LBM`: the macrodata must be current (last step
+    taken with want_macrodata=True, as the reference's post_time_step leaves it)."""
+    deck = lbm.inp.deck
+    if save_streaming is None:
+        save_streaming = bool(int(str(deck.get("lbm.save_streaming", "1")).split()[0]))
+    if save_derived is None:
+        save_derived = bool(int(str(deck.get("lbm.save_derived", "1")).split()[0]))
+    if max_grid_size is None:
+        max_grid_size = int(str(deck.get("amr.max_grid_size", "32")).split()[0])
+    if lbm.world != 1:
+        raise ValueError("write_lbm_plotfile writes the whole level from one rank")
+    names = plot_file_var_names(save_streaming, save_derived)
+    parts = [lbm.get_macrodata()]
+    if save_streaming:
+        parts += [lbm.get_f(), lbm.get_g()]
+    if save_derived:
+        lbm.compute_derived()
+        parts.append(lbm.get_derived())
+    ng = (lbm._is_fluid.shape[0] - lbm.n_local[2]) // 2
+    fl = lbm._is_fluid[ng:-ng, ng:-ng, ng:-ng] if ng else lbm._is_fluid
+    parts.append(np.stack([fl.astype(np.float64), eb_boundary(lbm._is_fluid, ng).astype(np.float64)]))
+    data = np.concatenate(parts, axis=0)
+    path = os.path.join(directory, plot_file_name(prefix, lbm.isteps))
+    write_plotfile(path, names, data, time=lbm.time, step=lbm.isteps, prob_lo=lbm.inp.prob_lo, prob_hi=lbm.inp.prob_hi,
+                   max_grid_size=max_grid_size)
+    return path
+
+
+def eb_boundary(is_fluid_grown: np.ndarray, ng: int) -> np.ndarray:
+    """component 1 of m_is_fluid (Source/LBM.cpp:1244-1259): a solid cell with at least one fluid face neighbour"""
+    a = is_fluid_grown
+    if ng == 0:
+        a = np.pad(a, 1, mode="edge")
+        ng = 1
+    c = a[ng:-ng, ng:-ng, ng:-ng]
+    out = np.zeros_like(c)
+    sl = lambda o, n: slice(ng + o, n + ng + o)
+    nz, ny, nx = c.shape
+    any_fluid = np.zeros(c.shape, dtype=bool)
+    for dz, dy, dxx in ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)):
+        any_fluid |= a[sl(dz, nz), sl(dy, ny), sl(dxx, nx)] == 1
+    out[(c == 0) & any_fluid] = 1
+    return out

@@ -1,0 +1,78 @@
+"""Plotfile emission: marbles_b200.plotfile against a plotfile written by the unmodified
+reference (tests/golden/plt_tg8.npz, made by tests/golden/make_plotfile_golden.py) -- byte for byte -- and a
+round trip through the oracle's plotfile reader."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from marbles_b200 import plotfile as P
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "plt_tg8.npz")
+
+
+def test_var_names_match_reference_order():
+    z = np.load(GOLD)
+    assert P.plot_file_var_names(True, True) == [str(n) for n in z["names"]]
+    assert len(P.plot_file_var_names(False, False)) == 19 + 2
+
+
+def test_plotfile_bytes_match_reference(tmp_path):
+    z = np.load(GOLD)
+    names = [str(n) for n in z["names"]]
+    out = str(tmp_path / "plt00001")
+    P.write_plotfile(out, names, z["data"], time=float(z["time"]), step=1, prob_lo=[-1, -1, -1], prob_hi=[1, 1, 1],
+                     max_grid_size=4)
+    assert open(os.path.join(out, "Header")).read() == str(z["header"])
+    assert open(os.path.join(out, "Level_0", "Cell_H")).read() == str(z["cell_h"])
+    digest = hashlib.sha256(open(os.path.join(out, "Level_0", "Cell_D_00000"), "rb").read()).hexdigest()
+    assert digest == str(z["cell_d_sha256"])
+
+
+@pytest.mark.parametrize("shape,mgs", [((5, 6, 7), 4), ((8, 8, 8), 8), ((3, 16, 4), 32)])
+def test_plotfile_round_trip_through_oracle_reader(tmp_path, shape, mgs):
+    from oracle import oracle as O
+    rng = np.random.default_rng(7)
+    names = ["a", "b", "c"]
+    nz, ny, nx = shape
+    data = rng.standard_normal((3, nz, ny, nx))
+    out = str(tmp_path / "plt00042")
+    P.write_plotfile(out, names, data, time=1.5, step=42, prob_lo=[0, 0, 0], prob_hi=[nx, ny, nz], max_grid_size=mgs)
+    pf = O.read_plotfile(out)
+    assert pf["__names__"] == names and pf["__time__"] == 1.5
+    for c, n in enumerate(names):
+        assert np.array_equal(pf[n], data[c])
+
+
+def test_eb_boundary_flag():
+    a = np.ones((5, 5, 5), dtype=np.int32)
+    a[2, 2, 2] = 0
+    a[2, 2, 3] = 0
+    eb = P.eb_boundary(np.pad(a, 1, mode="edge"), 1)
+    assert eb.sum() == 2 and eb[2, 2, 2] == 1 and eb[2, 2, 3] == 1
+
+
+@pytest.mark.gpu
+def test_lbm_write_plot_file_matches_golden(tmp_path):
+    """the device state written as a plotfile, read back, against the reference's fields of the same step"""
+    from conftest import load_golden
+    from oracle import oracle as O
+    from parity import compare, scales
+    from marbles_b200.inputs import parse_deck
+    from marbles_b200.lbm import LBM
+    z, deck_text, steps = load_golden("chcyl")
+    lbm = LBM(parse_deck(text=deck_text), is_fluid=z["is_fluid"].astype(np.int32))
+    lbm.init_data()
+    n = steps[-1]
+    lbm.step(n, want_macrodata=True)
+    path = P.write_lbm_plotfile(lbm, str(tmp_path))
+    assert os.path.basename(path) == f"plt{n:05d}"
+    pf = O.read_plotfile(path)
+    ref = {k[len(f"s{n}_"):]: z[k] for k in z.files if k.startswith(f"s{n}_")}
+    assert np.array_equal(pf["is_fluid"], ref["is_fluid"]) and np.array_equal(pf["eb_boundary"], ref["eb_boundary"])
+    got = {k: pf[k] for k in ref if k in pf and k not in ("is_fluid", "eb_boundary")}
+    sc = scales(ref, lbm.inp.R, lbm.inp.gamma, 1.0 / lbm.inp.dx[0])
+    worst, key = compare(got, {k: ref[k] for k in got}, sc, n)
+    print(f"plotfile fields: worst {worst:.2e} ({key}), {len(got)} components")
+    lbm.close()
