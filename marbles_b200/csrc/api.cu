@@ -186,7 +186,15 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
             ctx->launches += nl;
             lv.carry_valid = true;
         }
-    } else if (ctx->variant == 0) {
+    } else if (ctx->variant == 6 && !macro) {
+        // the lean collide with a chosen number of CTAs per SM (MBL_MINB); variant 0 uses it with 3
+        ctx->launches += launch_qcorr(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st);
+        mark();
+        const int nl = launch_collide_lean(Lk, lv.P, ctx->carry_minb, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b],
+                                           lv.p.nbr, lv.p.flag, lv.p.qc, st);
+        if (nl < 0) return fail("lean collide: a lattice component exceeds 4 GB (32-bit byte offsets)");
+        ctx->launches += nl;
+    } else if (ctx->variant == 0 || ctx->variant == 6) {
         ctx->launches += launch_qcorr(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st);
         mark();
         ctx->launches += launch_collide(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
@@ -249,7 +257,7 @@ int mbl_create(const mbl_params* params, int device, mbl_ctx** out)
     if (const char* e = getenv("MBL_HOST_CHUNK")) c->host_chunk = atoi(e);
     if (const char* e = getenv("MBL_OWN")) c->carry_own = atoi(e) == 28 ? 28 : 30;
     if (const char* e = getenv("MBL_KY")) c->carry_ky = atoi(e) > 0 ? atoi(e) : 32;
-    if (const char* e = getenv("MBL_MINB")) c->carry_minb = atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 2;
+    if (const char* e = getenv("MBL_MINB")) c->carry_minb = atoi(e) >= 2 && atoi(e) <= 5 ? atoi(e) : 2;
     init_tables();
     CU(cudaGetLastError());
     *out = c;
@@ -847,7 +855,7 @@ int mbl_get_timing(mbl_ctx* ctx, double ms[3], int* nsteps)
 int mbl_set_variant(mbl_ctx* ctx, int variant)
 {
     if (!ctx) return fail("null context");
-    if (variant < 0 || variant > 5) return fail("variant %d is not available", variant);
+    if (variant < 0 || variant > 6) return fail("variant %d is not available", variant);
     ctx->variant = variant;
     for (int l = 0; l < MAX_LEVELS; ++l) ctx->lev[l].carry_valid = false;
     return 0;

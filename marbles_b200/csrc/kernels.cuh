@@ -79,6 +79,10 @@ CarryPlan make_carry_plan(const Layout& L, int own, int ky);
 int launch_collide_carry(const Layout& L, const Phys& P, const CarryPlan& C, int min_blocks, const double* fin,
                          const double* gin, double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag,
                          const double* qc, double* part, cudaStream_t st);
+// k_collide<pull> with g staged through shared memory and 32-bit addressing (bit-identical results)
+int launch_collide_lean(const Layout& L, const Phys& P, int min_blocks, const double* fin, const double* gin,
+                        double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag, const double* qc,
+                        cudaStream_t st, int ka = 0, int kb = 0);
 // the same without marching: CTA = `rows` warps = rows - 2 owned rows + 2 halo rows of one column strip
 int launch_collide_tile(const Layout& L, const Phys& P, const CarryPlan& C, int rows, const double* fin,
                         const double* gin, double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag,

@@ -133,12 +133,19 @@ def write_lbm_plotfile(lbm, directory: str = ".", prefix: str = "plt", max_grid_
     """LBM::write_plot_file for a single-rank `marbles_b200.lbm.LBM`: the macrodata must be current (last step
     taken with want_macrodata=True, as the reference's post_time_step leaves it)."""
     deck = lbm.inp.deck
+
+    def deck_int(key: str, default: int) -> int:
+        v = deck.get(key, default)  # parse_deck keeps a list of tokens per key
+        if isinstance(v, (list, tuple)):
+            v = v[0]
+        return int(str(v).split()[0])
+
     if save_streaming is None:
-        save_streaming = bool(int(str(deck.get("lbm.save_streaming", "1")).split()[0]))
+        save_streaming = bool(deck_int("lbm.save_streaming", 1))
     if save_derived is None:
-        save_derived = bool(int(str(deck.get("lbm.save_derived", "1")).split()[0]))
+        save_derived = bool(deck_int("lbm.save_derived", 1))
     if max_grid_size is None:
-        max_grid_size = int(str(deck.get("amr.max_grid_size", "32")).split()[0])
+        max_grid_size = deck_int("amr.max_grid_size", 32)
     if lbm.world != 1:
         raise ValueError("write_lbm_plotfile writes the whole level from one rank")
     names = plot_file_var_names(save_streaming, save_derived)

@@ -24,6 +24,7 @@ CARRY_ENV = {
     "tile": (5, {}),
     "tile-6rows-own28": (5, {"MBL_ROWS": "6", "MBL_OWN": "28"}),
     "tile-12rows": (5, {"MBL_ROWS": "12"}),
+    "lean": (6, {"MBL_MINB": "4"}),
 }
 TUNING_VARS = ("MBL_KY", "MBL_OWN", "MBL_MINB", "MBL_ROWS")
 
@@ -51,9 +52,9 @@ def new_lbm(deck_text, is_fluid=None, overrides=None, variant=None):
 
 # fused: mbl_step with the persistent TMA kernel (variant 1, the default), its two job types as two
 # launches (2), or the two plain kernels (0); unfused: the reference-granular operator sequence
-@pytest.mark.parametrize("fused", [1, 2, 3, 0, "carry", "carry-ky5-own28", "tile", "tile-6rows-own28", None],
+@pytest.mark.parametrize("fused", [1, 2, 3, 0, "carry", "carry-ky5-own28", "tile", "tile-6rows-own28", "lean", None],
                          ids=["fused-tma", "twopass-tma", "fused-plain", "twopass-plain", "carry", "carry-ky5-own28", "tile",
-                              "tile-6rows-own28", "unfused"])
+                              "tile-6rows-own28", "lean", "unfused"])
 @pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_cuda_vs_reference_golden(case, fused):
     z, deck_text, steps = load_golden(case)
@@ -320,3 +321,22 @@ def test_overlapped_slab_step_matches_single_box(nz, world):
         assert np.array_equal(get(single), slabs.gather(get))
     slabs.close()
     single.close()
+
+
+@pytest.mark.parametrize("case", ["chcyl", "tg12", "pressure"])
+def test_lean_collide_is_bit_identical_to_collide(case):
+    """k_collide_lean (g through shared memory, 32-bit offsets) does the arithmetic of k_collide in the same order"""
+    import os
+    z, deck_text, _ = load_golden(case)
+    fl = z["is_fluid"].astype(np.int32)
+    a = new_lbm(deck_text, fl, variant=0)
+    b = new_lbm(deck_text, fl, variant="lean")
+    os.environ["MBL_PLAIN_COLLIDE"] = "1"  # variant 0 with the original k_collide
+    try:
+        a.step(6)
+    finally:
+        os.environ.pop("MBL_PLAIN_COLLIDE", None)
+    b.step(6)
+    assert np.array_equal(a.get_f(), b.get_f()) and np.array_equal(a.get_g(), b.get_g())
+    a.close()
+    b.close()
