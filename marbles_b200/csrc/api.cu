@@ -58,6 +58,8 @@ struct Level {
     double* macro = nullptr;  // lazily allocated (26 comps)
     int* counters = nullptr;  // fused kernel: ticket + per-slab completion counters
     double* part = nullptr;   // carry step: 12 partial-sum words per cell (lazily allocated)
+    double* edge = nullptr;   // tile carry step: 18 words per CTA row
+    int edge_rows = 0;        // rows per CTA the edge arrays were written with (0: written by the marching kernel)
     bool carry_valid = false; // `part` holds the partial sums of the current lattice buffers' next post-stream state
 };
 
@@ -166,8 +168,12 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
         // carry step: q-corrections from the partial sums the previous collide left behind (first step, or after
         // anything else wrote the lattice: the full q-correction pass)
         if (!lv.part) CU(cudaMalloc(&lv.part, (size_t)CARRY_WORDS * lv.L.sq * sizeof(double)));
+        const int W = ctx->carry_rows == 6 ? 6 : ctx->carry_rows == 12 ? 12 : 8;
+        if (ctx->variant == 5 && !lv.edge)
+            CU(cudaMalloc(&lv.edge, (size_t)CARRY_EDGE_WORDS * carry_edge_plane(lv.L, 6) * (lv.L.nz + 2 * GZ) * sizeof(double)));
         if (lv.carry_valid)
-            ctx->launches += launch_qcorr_combine(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.part, lv.p.qc, st);
+            ctx->launches += launch_qcorr_combine(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.part,
+                                                  lv.edge_rows ? lv.edge : nullptr, lv.edge_rows, lv.p.qc, st);
         else
             ctx->launches += launch_qcorr(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st);
         mark();
@@ -180,8 +186,9 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
             const int nl = ctx->variant == 4
                                ? launch_collide_carry(Lk, lv.P, C, ctx->carry_minb, lv.p.f[a], lv.p.g[a], lv.p.f[b],
                                                       lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, lv.part, st)
-                               : launch_collide_tile(Lk, lv.P, C, ctx->carry_rows, lv.p.f[a], lv.p.g[a], lv.p.f[b],
-                                                     lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, lv.part, st);
+                               : launch_collide_tile(Lk, lv.P, C, W, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b],
+                                                     lv.p.nbr, lv.p.flag, lv.p.qc, lv.part, lv.edge, st);
+            lv.edge_rows = ctx->variant == 5 ? W : 0;
             if (nl < 0) return fail("carry step: a lattice component exceeds 4 GB (32-bit byte offsets)");
             ctx->launches += nl;
             lv.carry_valid = true;
@@ -315,6 +322,7 @@ int mbl_level_clear(mbl_ctx* ctx, int lev)
     if (lv.macro) cudaFree(lv.macro);
     if (lv.counters) cudaFree(lv.counters);
     if (lv.part) cudaFree(lv.part);
+    if (lv.edge) cudaFree(lv.edge);
     lv = Level();
     return 0;
 }

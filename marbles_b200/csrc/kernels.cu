@@ -181,16 +181,8 @@ __device__ __forceinline__ void collide_cell(const double* __restrict__ fin, con
             });
         }
     }
-    MomF mf = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    MomG mg = {0, 0, 0, 0};
-    static_for<0, NQ>([&](auto qc_) {
-        constexpr int Q = decltype(qc_)::value;
-        acc_f<Q>(mf, f[Q]);
-    });
-    static_for<0, NQ>([&](auto qc_) {
-        constexpr int Q = decltype(qc_)::value;
-        acc_g<Q>(mg, g[Q]);
-    });
+    const MomF mf = moments_f([&](int q) { return f[q]; });
+    const MomG mg = moments_g([&](int q) { return g[q]; });
     const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
 
     // grad of the q-correction (LBM.cpp:959-991, Utilities.H:279-312)
@@ -402,10 +394,8 @@ __global__ void __launch_bounds__(128, MINB)
                     }
                 }
             }
-            MomF mf = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-            MomG mg = {0, 0, 0, 0};
-            static_for<0, NQ>([&](auto qc_) { acc_f<decltype(qc_)::value>(mf, f[decltype(qc_)::value]); });
-            static_for<0, NQ>([&](auto qc_) { acc_g<decltype(qc_)::value>(mg, sg[decltype(qc_)::value * 128]); });
+            const MomF mf = moments_f([&](int q) { return f[q]; });
+            const MomG mg = moments_g([&](int q) { return sg[q * 128]; });
             const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
             const double dqx = one_sided_gradient(fb & GRAD_PX, fb & GRAD_MX, (fb & GRAD_PX) ? qxp : 0.0, s.qcx,
                                                   (fb & GRAD_MX) ? qxm : 0.0, P.idx[0]);
@@ -557,10 +547,8 @@ __global__ void __launch_bounds__(128, MINB)
             }
         }
     }
-    MomF mf = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    MomG mg = {0, 0, 0, 0};
-    static_for<0, NQ>([&](auto qc_) { acc_f<decltype(qc_)::value>(mf, f[decltype(qc_)::value]); });
-    static_for<0, NQ>([&](auto qc_) { acc_g<decltype(qc_)::value>(mg, sg[decltype(qc_)::value * T]); });
+    const MomF mf = moments_f([&](int q) { return f[q]; });
+    const MomG mg = moments_g([&](int q) { return sg[q * T]; });
     const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
     const double dqx = one_sided_gradient(fb & GRAD_PX, fb & GRAD_MX, (fb & GRAD_PX) ? qxp : 0.0, s.qcx,
                                           (fb & GRAD_MX) ? qxm : 0.0, P.idx[0]);
@@ -587,10 +575,10 @@ __global__ void __launch_bounds__(128, MINB)
 // The same carried sums without marching: a CTA is W warps = W consecutive rows of one warp-wide column strip,
 // one cell per thread, so CTAs sweep the box in launch order exactly like k_collide (the DRAM streams stay
 // compact; marching spreads the resident CTAs over rows that are KY rows apart).  x is reduced by shuffles as
-// above, y by one exchange through shared memory between the warps of the CTA; the first and the last row of a
-// CTA are halo rows that are collided redundantly (their populations come out of L2: the neighbouring CTA is
-// resident at the same time) and store nothing.  g again travels global -> shared by cp.async, and the exchange
-// reuses those slots.
+// above, y by one exchange through shared memory between the warps of the CTA.  What the first row of a CTA
+// sends down and its last row sends up leaves the CTA: those 2 x 9 words go to the compact `edge` arrays
+// (one entry per CTA row, 18 / W words per cell) and k_qcorr_combine adds them to the two rows concerned, so no
+// row is collided twice.  g again travels global -> shared by cp.async, and the exchange reuses those slots.
 // ---------------------------------------------------------------------------
 template <int W>
 __global__ void __launch_bounds__(32 * W, (W <= 8 ? 2 : 1))
@@ -604,18 +592,16 @@ __global__ void __launch_bounds__(32 * W, (W <= 8 ? 2 : 1))
     const unsigned sg_addr = (unsigned)__cvta_generic_to_shared(sg);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int xc = blockIdx.x;
-    const int y0 = blockIdx.y * (W - 2);
+    const int y0 = blockIdx.y * W;
+    const int rows = min(W, L.ny - y0);  // rows of this CTA inside the box
     const int k = blockIdx.z;
     const int i = xc * C.own - C.halo + lane;
-    const int jr = y0 - 1 + w;  // row of this warp; w = 0 and w = W-1 are the halo rows
-    const bool own = lane >= C.halo && lane < C.halo + C.own && i < L.nx && w >= 1 && w <= W - 2 && jr < L.ny;
-    // cell this thread collides: its own, the periodic image for halo lanes / rows over a wrapped edge, otherwise
+    const bool own = lane >= C.halo && lane < C.halo + C.own && i < L.nx && w < rows;
+    // cell this thread collides: its own, the periodic image for halo lanes over a wrapped edge, otherwise
     // clamped (what such a thread contributes lands in cells k_qcorr_combine does not take from the carried sums)
-    int is = i, j = jr;
+    int is = i, j = min(y0 + w, L.ny - 1);
     if (is < 0) is = L.wrap[0] ? is + L.nx : 0;
     if (is >= L.nx) is = (L.wrap[0] && is - L.nx < L.nx) ? is - L.nx : L.nx - 1;
-    if (j < 0) j = L.wrap[1] ? j + L.ny : 0;
-    if (j >= L.ny) j = (L.wrap[1] && j - L.ny < L.ny) ? j - L.ny : L.ny - 1;
     const unsigned FULL = 0xffffffffu;
     const unsigned px8 = (unsigned)L.px * 8u, sz8 = (unsigned)L.sz * 8u;
     unsigned xo[3], yo[3], zo[3];
@@ -664,8 +650,7 @@ __global__ void __launch_bounds__(32 * W, (W <= 8 ? 2 : 1))
             for (int q = 0; q < NQ; ++q) f[q] = -1.0;
         }
     }
-    MomF mf = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    static_for<0, NQ>([&](auto qc_) { acc_f<decltype(qc_)::value>(mf, f[decltype(qc_)::value]); });
+    MomF mf = moments_f([&](int q) { return f[q]; });
     // wait for g only now, and tied to a value that needs every f: placed right after the cp.async issue, ptxas
     // schedules the f loads behind the wait and the cell pays two DRAM latencies in series
     cp_async_wait_all_after(mf.rho);
@@ -680,8 +665,7 @@ __global__ void __launch_bounds__(32 * W, (W <= 8 ? 2 : 1))
             for (int q = 0; q < NQ; ++q) sg[q * T] = -1.0;
         }
     }
-    MomG mg = {0, 0, 0, 0};
-    static_for<0, NQ>([&](auto qc_) { acc_g<decltype(qc_)::value>(mg, sg[decltype(qc_)::value * T]); });
+    const MomG mg = moments_g([&](int q) { return sg[q * T]; });
     const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
     const double dqx = one_sided_gradient(fb & GRAD_PX, fb & GRAD_MX, (fb & GRAD_PX) ? qxp : 0.0, s.qcx,
                                           (fb & GRAD_MX) ? qxm : 0.0, P.idx[0]);
@@ -719,15 +703,34 @@ __global__ void __launch_bounds__(32 * W, (W <= 8 ? 2 : 1))
         double(&E)[3] = ey(Q) == -1 ? EA : ey(Q) == 0 ? EB : EC;
         E[d] += t;
     });
-    // y exchange: what this row sends down (TA, EA: slots 0..8) and up (TC, EC: slots 9..17), in the g slots
+    // y exchange: what this row sends down (TA, EA: slots 0..8) and up (TC, EC: slots 9..17), in the g slots;
+    // the first row's "down" and the last row's "up" leave the CTA through the edge arrays
+    const unsigned ce = (unsigned)(i + OX) * 8u + (unsigned)blockIdx.y * px8 + (unsigned)(k + GZ) * (unsigned)C.esz8;
+    const bool first = w == 0, last = w == rows - 1;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        sg[(3 * d + 0) * T] = TA[d][0];
-        sg[(3 * d + 1) * T] = TA[d][1];
-        sg[(3 * d + 2) * T] = EA[d];
-        sg[(9 + 3 * d + 0) * T] = TC[d][0];
-        sg[(9 + 3 * d + 1) * T] = TC[d][1];
-        sg[(9 + 3 * d + 2) * T] = EC[d];
+        if (first) {
+            if (own) {
+                stb(A.edge[3 * d + 0], ce, TA[d][0]);
+                stb(A.edge[3 * d + 1], ce, TA[d][1]);
+                stb(A.edge[3 * d + 2], ce, EA[d]);
+            }
+        } else {
+            sg[(3 * d + 0) * T] = TA[d][0];
+            sg[(3 * d + 1) * T] = TA[d][1];
+            sg[(3 * d + 2) * T] = EA[d];
+        }
+        if (last) {
+            if (own) {
+                stb(A.edge[9 + 3 * d + 0], ce, TC[d][0]);
+                stb(A.edge[9 + 3 * d + 1], ce, TC[d][1]);
+                stb(A.edge[9 + 3 * d + 2], ce, EC[d]);
+            }
+        } else {
+            sg[(9 + 3 * d + 0) * T] = TC[d][0];
+            sg[(9 + 3 * d + 1) * T] = TC[d][1];
+            sg[(9 + 3 * d + 2) * T] = EC[d];
+        }
     }
     __syncthreads();
     if (own) {
@@ -735,11 +738,13 @@ __global__ void __launch_bounds__(32 * W, (W <= 8 ? 2 : 1))
         const double* dn = sg - 32;   // row j-1: its e_y = +1 terms
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            const double ua = up[(3 * d + 0) * T], dc = dn[(9 + 3 * d + 0) * T];
+            const double ua = last ? 0.0 : up[(3 * d + 0) * T], dc = first ? 0.0 : dn[(9 + 3 * d + 0) * T];
+            const double ux = last ? 0.0 : up[(3 * d + 1) * T], dx = first ? 0.0 : dn[(9 + 3 * d + 1) * T];
+            const double ue = last ? 0.0 : up[(3 * d + 2) * T], de = first ? 0.0 : dn[(9 + 3 * d + 2) * T];
             stb(A.part[4 * d + 0], c, TB[d][0] + ua + dc);
-            stb(A.part[4 * d + 1], c, TB[d][1] + up[(3 * d + 1) * T] + dn[(9 + 3 * d + 1) * T]);
+            stb(A.part[4 * d + 1], c, TB[d][1] + ux + dx);
             stb(A.part[4 * d + 2], c, dc - ua);
-            stb(A.part[4 * d + 3], c, EB[d] + up[(3 * d + 2) * T] + dn[(9 + 3 * d + 2) * T]);
+            stb(A.part[4 * d + 3], c, EB[d] + ue + de);
         }
     }
 }
@@ -748,6 +753,7 @@ __global__ void __launch_bounds__(32 * W, (W <= 8 ? 2 : 1))
 // populations (everything k_collide_carry could not serve)
 __global__ void __launch_bounds__(128, 6) k_qcorr_combine(const double* __restrict__ fin, const double* __restrict__ gin,
                                                           const uint32_t* __restrict__ nbr, const double* __restrict__ part,
+                                                          const double* __restrict__ edge, int W, long long esz,
                                                           double* __restrict__ qc, const __grid_constant__ Layout L,
                                                           const __grid_constant__ Phys P, int k0)
 {
@@ -764,14 +770,39 @@ __global__ void __launch_bounds__(128, 6) k_qcorr_combine(const double* __restri
         qcorr_cell<true>(fin, gin, nbr, qc, L, P, i, j, k);
         return;
     }
-    const long long cm = L.cell(i, j, k == 0 ? L.nz - 1 : k - 1);      // source plane k-1 sends with c = +1
-    const long long cp = L.cell(i, j, k == L.nz - 1 ? 0 : k + 1);      // source plane k+1 sends with c = -1
+    const int km = k == 0 ? L.nz - 1 : k - 1, kp = k == L.nz - 1 ? 0 : k + 1;
+    const long long cm = L.cell(i, j, km);      // source plane k-1 sends with c = +1
+    const long long cp = L.cell(i, j, kp);      // source plane k+1 sends with c = -1
     const double rm = part[8 * n + cm], r0 = part[4 * n + c], rp = part[0 * n + cp];
-    const double rho = rm + r0 + rp;
-    const double jz = rm - rp;
-    const double jx = part[9 * n + cm] + part[5 * n + c] + part[1 * n + cp];
-    const double jy = part[10 * n + cm] + part[6 * n + c] + part[2 * n + cp];
-    const double e2 = part[11 * n + cm] + part[7 * n + c] + part[3 * n + cp];
+    double rho = rm + r0 + rp;
+    double jz = rm - rp;
+    double jx = part[9 * n + cm] + part[5 * n + c] + part[1 * n + cp];
+    double jy = part[10 * n + cm] + part[6 * n + c] + part[2 * n + cp];
+    double e2 = part[11 * n + cm] + part[7 * n + c] + part[3 * n + cp];
+    if (W > 0) {
+        // k_collide_tile: the rows at the edges of a CTA lack what the neighbouring CTA's adjacent row sent
+        // (edge arrays: [side 0 = first row's e_y = -1 sums | side 1 = last row's e_y = +1 sums][c][rho, jx, e2])
+        const int jr = j / W, w = j - jr * W, nyr = (L.ny + W - 1) / W;
+        const int rows = min(W, L.ny - jr * W);
+        const long long en = esz * (L.nz + 2 * GZ);
+        auto add_edge = [&](int side, int jrs, double sgn) {
+            const long long e0 = (long long)(i + OX) + (long long)jrs * L.px;
+            const double am = edge[(side * 9 + 6) * en + e0 + (long long)(km + GZ) * esz];
+            const double a0 = edge[(side * 9 + 3) * en + e0 + (long long)(k + GZ) * esz];
+            const double ap = edge[(side * 9 + 0) * en + e0 + (long long)(kp + GZ) * esz];
+            rho += am + a0 + ap;
+            jz += am - ap;
+            jy += sgn * (am + a0 + ap);
+            jx += edge[(side * 9 + 7) * en + e0 + (long long)(km + GZ) * esz] +
+                  edge[(side * 9 + 4) * en + e0 + (long long)(k + GZ) * esz] +
+                  edge[(side * 9 + 1) * en + e0 + (long long)(kp + GZ) * esz];
+            e2 += edge[(side * 9 + 8) * en + e0 + (long long)(km + GZ) * esz] +
+                  edge[(side * 9 + 5) * en + e0 + (long long)(k + GZ) * esz] +
+                  edge[(side * 9 + 2) * en + e0 + (long long)(kp + GZ) * esz];
+        };
+        if (w == 0) add_edge(1, jr == 0 ? nyr - 1 : jr - 1, 1.0);          // row j-1 is another CTA's last row
+        if (w == rows - 1) add_edge(0, jr == nyr - 1 ? 0 : jr + 1, -1.0);  // row j+1 is another CTA's first row
+    }
     const Prim s = primitives(rho, jx, jy, jz, e2, P);
     qc[c] = s.qcx;
     qc[n + c] = s.qcy;
@@ -1590,6 +1621,7 @@ CarryPlan make_carry_plan(const Layout& L, int own, int ky)
     C.ky = ky < 1 ? 1 : (ky > L.ny ? L.ny : ky);
     C.nxc = (L.nx + C.own - 1) / C.own;
     C.prefetch = 0;
+    C.esz8 = 0;
     if (const char* e = getenv("MBL_PREFETCH")) C.prefetch = atoi(e);
     return C;
 }
@@ -1608,6 +1640,7 @@ int launch_collide_carry(const Layout& L, const Phys& P, const CarryPlan& C, int
     }
     for (int d = 0; d < 3; ++d) A.qc[d] = qc + (long long)d * L.sq;
     for (int w = 0; w < CARRY_WORDS; ++w) A.part[w] = part + (long long)w * L.sq;
+    for (int e = 0; e < CARRY_EDGE_WORDS; ++e) A.edge[e] = nullptr;
     const dim3 grid((C.nxc + 3) / 4, (L.ny + C.ky - 1) / C.ky, L.nz);
     static bool attr_done = false;
     if (!attr_done) {
@@ -1639,6 +1672,7 @@ int launch_collide_lean(const Layout& L, const Phys& P, int min_blocks, const do
     }
     for (int d = 0; d < 3; ++d) A.qc[d] = qc + (long long)d * L.sq;
     for (int w = 0; w < CARRY_WORDS; ++w) A.part[w] = nullptr;
+    for (int e = 0; e < CARRY_EDGE_WORDS; ++e) A.edge[e] = nullptr;
     dim3 grid((L.nx + 127) / 128, L.ny, L.nz);
     int k0 = 0;
     if (kb > ka) k0 = ka, grid.z = kb - ka;
@@ -1652,9 +1686,11 @@ int launch_collide_lean(const Layout& L, const Phys& P, int min_blocks, const do
     return 1;
 }
 
+long long carry_edge_plane(const Layout& L, int W) { return L.px * (long long)((L.ny + W - 1) / W); }
+
 int launch_collide_tile(const Layout& L, const Phys& P, const CarryPlan& C, int rows, const double* fin,
                         const double* gin, double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag,
-                        const double* qc, double* part, cudaStream_t st)
+                        const double* qc, double* part, double* edge, cudaStream_t st)
 {
     if (L.sq * 8 >= (1LL << 32)) return -1;  // 32-bit byte offsets inside a component
     CarryPtrs A;
@@ -1666,6 +1702,11 @@ int launch_collide_tile(const Layout& L, const Phys& P, const CarryPlan& C, int 
     }
     for (int d = 0; d < 3; ++d) A.qc[d] = qc + (long long)d * L.sq;
     for (int w = 0; w < CARRY_WORDS; ++w) A.part[w] = part + (long long)w * L.sq;
+    const int W = rows == 6 ? 6 : rows == 12 ? 12 : 8;
+    CarryPlan Ce = C;
+    const long long esz = carry_edge_plane(L, W);
+    Ce.esz8 = (unsigned)(esz * 8);
+    for (int e = 0; e < CARRY_EDGE_WORDS; ++e) A.edge[e] = edge + (long long)e * esz * (L.nz + 2 * GZ);
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(k_collide_tile<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ * 32 * 6 * 8);
@@ -1673,26 +1714,26 @@ int launch_collide_tile(const Layout& L, const Phys& P, const CarryPlan& C, int 
         cudaFuncSetAttribute(k_collide_tile<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ * 32 * 12 * 8);
         attr_done = true;
     }
-    const int W = rows == 6 ? 6 : rows == 12 ? 12 : 8;
-    const dim3 grid(C.nxc, (L.ny + W - 3) / (W - 2), L.nz);
+    const dim3 grid(C.nxc, (L.ny + W - 1) / W, L.nz);
     const size_t sm = (size_t)NQ * 32 * W * 8;
     if (W == 6)
-        k_collide_tile<6><<<grid, 32 * 6, sm, st>>>(A, nbr, flag, L, P, C);
+        k_collide_tile<6><<<grid, 32 * 6, sm, st>>>(A, nbr, flag, L, P, Ce);
     else if (W == 12)
-        k_collide_tile<12><<<grid, 32 * 12, sm, st>>>(A, nbr, flag, L, P, C);
+        k_collide_tile<12><<<grid, 32 * 12, sm, st>>>(A, nbr, flag, L, P, Ce);
     else
-        k_collide_tile<8><<<grid, 32 * 8, sm, st>>>(A, nbr, flag, L, P, C);
+        k_collide_tile<8><<<grid, 32 * 8, sm, st>>>(A, nbr, flag, L, P, Ce);
     return 1;
 }
 
 int launch_qcorr_combine(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr,
-                         const double* part, double* qc, cudaStream_t st)
+                         const double* part, const double* edge, int edge_rows, double* qc, cudaStream_t st)
 {
     const int bx = block_x(L);
     const int k0 = (L.lo[2] > L.dlo[2]) ? -1 : 0;
     const int k1 = (L.lo[2] + L.nz - 1 < L.dhi[2]) ? L.nz : L.nz - 1;
     dim3 grid((L.nx + bx - 1) / bx, L.ny, k1 - k0 + 1);
-    k_qcorr_combine<<<grid, bx, 0, st>>>(fin, gin, nbr, part, qc, L, P, k0);
+    const int W = edge ? (edge_rows == 6 ? 6 : edge_rows == 12 ? 12 : 8) : 0;
+    k_qcorr_combine<<<grid, bx, 0, st>>>(fin, gin, nbr, part, edge, W, W ? carry_edge_plane(L, W) : 0, qc, L, P, k0);
     return 1;
 }
 

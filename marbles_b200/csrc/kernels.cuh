@@ -64,8 +64,10 @@ struct CarryPlan {
     int ky;         // rows a thread marches through
     int nxc;        // warps per row
     int prefetch;   // rows of L2 bulk-prefetch distance (0: off)
+    unsigned esz8;  // k_collide_tile: bytes per plane of an edge array
 };
 constexpr int CARRY_WORDS = 12;
+constexpr int CARRY_EDGE_WORDS = 18;  // k_collide_tile: [first row down | last row up][c][rho, jx, e2]
 // per-component base pointers, passed by value in kernel parameter space
 struct CarryPtrs {
     const double* fin[NQ];
@@ -74,6 +76,7 @@ struct CarryPtrs {
     double* gout[NQ];
     const double* qc[3];
     double* part[CARRY_WORDS];
+    double* edge[CARRY_EDGE_WORDS];
 };
 CarryPlan make_carry_plan(const Layout& L, int own, int ky);
 int launch_collide_carry(const Layout& L, const Phys& P, const CarryPlan& C, int min_blocks, const double* fin,
@@ -86,9 +89,12 @@ int launch_collide_lean(const Layout& L, const Phys& P, int min_blocks, const do
 // the same without marching: CTA = `rows` warps = rows - 2 owned rows + 2 halo rows of one column strip
 int launch_collide_tile(const Layout& L, const Phys& P, const CarryPlan& C, int rows, const double* fin,
                         const double* gin, double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag,
-                        const double* qc, double* part, cudaStream_t st);
+                        const double* qc, double* part, double* edge, cudaStream_t st);
+// doubles per plane of one edge array for `rows` rows per CTA (the array spans nz + 2 GZ planes)
+long long carry_edge_plane(const Layout& L, int rows);
+// edge / edge_rows: the edge arrays k_collide_tile wrote (nullptr after k_collide_carry)
 int launch_qcorr_combine(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr,
-                         const double* part, double* qc, cudaStream_t st);
+                         const double* part, const double* edge, int edge_rows, double* qc, cudaStream_t st);
 
 int launch_stream(const Layout& L, const double* fin, const double* gin, double* fout, double* gout,
                   const uint32_t* nbr, cudaStream_t st);
