@@ -197,15 +197,17 @@ int64_t mbl_launch_count(mbl_ctx* ctx);
  * *nsteps steps recorded since the last call (bench.py roofline) */
 int mbl_set_timing(mbl_ctx* ctx, int on);
 int mbl_get_timing(mbl_ctx* ctx, double ms[3], int* nsteps);
-/* select the implementation of mbl_step: 0 (default) = two kernels, k_qcorr (q-corrections of the
- * post-stream state) then k_collide (pull + collide); 1 = ONE persistent kernel per level with bulk-TMA
+/* select the implementation of mbl_step: 0 = two kernels, k_qcorr (q-corrections of the
+ * post-stream state) then k_collide_lean (pull + collide); 1 = ONE persistent kernel per level with bulk-TMA
  * staged pulls, q-correction jobs and collide jobs interleaved; 2 = the same kernel launched once per job
  * type; 3 = one persistent warp-autonomous kernel with plain loads; 4, 5 = "carry" steps whose collide kernel
  * also emits partial sums of the next step's conserved moments, so the q-correction pass does not read the
  * populations again (4: threads march through rows, 5: one cell per thread, rows exchanged inside the CTA).
- * 0-3 give identical results, 4-5 agree to round-off (the moments are summed in another order); DESIGN.md
- * has the measurements. */
+ * 5 is the default (fastest measured; boxes whose components exceed 4 GB fall back to 0); 6 = 0 with a chosen
+ * number of CTAs per SM.  All variants agree to round-off (the carried moments are summed in another order);
+ * DESIGN.md has the measurements. */
 int mbl_set_variant(mbl_ctx* ctx, int variant);
+int mbl_get_variant(mbl_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -83,6 +83,7 @@ SYMBOLS = {
     "mbl_step_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D, _D, C.c_int]),
     "mbl_launch_count": (C.c_int64, [_P]),
     "mbl_set_variant": (C.c_int, [_P, C.c_int]),
+    "mbl_get_variant": (C.c_int, [_P]),
     "mbl_set_timing": (C.c_int, [_P, C.c_int]),
     "mbl_get_timing": (C.c_int, [_P, _D, C.POINTER(C.c_int)]),
 }

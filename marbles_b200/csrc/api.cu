@@ -74,9 +74,9 @@ struct mbl_ctx {
     // implementation of mbl_step: 0 (default, fastest measured): two kernels, k_qcorr + k_collide;
     // 1: persistent TMA-pipelined kernel with both job types; 2: the same kernel, one launch per job type;
     // 3: persistent warp-autonomous kernel (plain loads) with both job types.  DESIGN.md has the numbers.
-    int variant = 0;
+    int variant = 5;
     int uw = 128, band_rows = 16, lag_per_cta = 4;  // variants 1-3 tuning (MBL_UW / MBL_BAND / MBL_LAG)
-    int carry_own = 30, carry_ky = 32, carry_minb = 2, carry_rows = 8;  // variant 4 tuning (MBL_OWN / MBL_KY / MBL_MINB)
+    int carry_own = 30, carry_ky = 32, carry_minb = 2, carry_rows = 6;  // variant 4 tuning (MBL_OWN / MBL_KY / MBL_MINB)
     int sm_count = 148;
     cudaStream_t s_up = nullptr, s_down = nullptr;  // copy streams of the pipelined mbl_step_host
     int host_chunk = 16;  // planes per upload chunk (MBL_HOST_CHUNK; negative: no pipelining)
@@ -164,12 +164,15 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
     if (need_ghosts) ctx->launches += launch_ghost_fill(lv.L, lv.B, lv.p.f[a], lv.p.g[a], lv.local_z, true, true, st);
     mark();
     double* macro = want_macro ? lv.macro : nullptr;
-    if (ctx->variant == 4 || ctx->variant == 5) {
+    // the carry kernels address a component with 32-bit byte offsets: larger boxes take the two-kernel step
+    int variant = ctx->variant;
+    if ((variant == 4 || variant == 5) && lv.L.sq * 8 >= (1LL << 32)) variant = 0;
+    if (variant == 4 || variant == 5) {
         // carry step: q-corrections from the partial sums the previous collide left behind (first step, or after
         // anything else wrote the lattice: the full q-correction pass)
         if (!lv.part) CU(cudaMalloc(&lv.part, (size_t)CARRY_WORDS * lv.L.sq * sizeof(double)));
-        const int W = ctx->carry_rows == 6 ? 6 : ctx->carry_rows == 12 ? 12 : 8;
-        if (ctx->variant == 5 && !lv.edge)
+        const int W = ctx->carry_rows == 8 ? 8 : ctx->carry_rows == 12 ? 12 : 6;
+        if (variant == 5 && !lv.edge)
             CU(cudaMalloc(&lv.edge, (size_t)CARRY_EDGE_WORDS * carry_edge_plane(lv.L, 6) * (lv.L.nz + 2 * GZ) * sizeof(double)));
         if (lv.carry_valid)
             ctx->launches += launch_qcorr_combine(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.part,
@@ -183,17 +186,17 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
             lv.carry_valid = false;
         } else {
             const CarryPlan C = make_carry_plan(Lk, ctx->carry_own, ctx->carry_ky);
-            const int nl = ctx->variant == 4
+            const int nl = variant == 4
                                ? launch_collide_carry(Lk, lv.P, C, ctx->carry_minb, lv.p.f[a], lv.p.g[a], lv.p.f[b],
                                                       lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, lv.part, st)
                                : launch_collide_tile(Lk, lv.P, C, W, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b],
                                                      lv.p.nbr, lv.p.flag, lv.p.qc, lv.part, lv.edge, st);
-            lv.edge_rows = ctx->variant == 5 ? W : 0;
+            lv.edge_rows = variant == 5 ? W : 0;
             if (nl < 0) return fail("carry step: a lattice component exceeds 4 GB (32-bit byte offsets)");
             ctx->launches += nl;
             lv.carry_valid = true;
         }
-    } else if (ctx->variant == 6 && !macro) {
+    } else if (variant == 6 && !macro) {
         // the lean collide with a chosen number of CTAs per SM (MBL_MINB); variant 0 uses it with 3
         ctx->launches += launch_qcorr(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st);
         mark();
@@ -201,18 +204,18 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
                                            lv.p.nbr, lv.p.flag, lv.p.qc, st);
         if (nl < 0) return fail("lean collide: a lattice component exceeds 4 GB (32-bit byte offsets)");
         ctx->launches += nl;
-    } else if (ctx->variant == 0 || ctx->variant == 6) {
+    } else if (variant == 0 || variant == 6) {
         ctx->launches += launch_qcorr(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st);
         mark();
         ctx->launches += launch_collide(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
                                         lv.p.qc, macro, true, st);
-    } else if (ctx->variant == 2) {
+    } else if (variant == 2) {
         ctx->launches += launch_fused(Lk, lv.P, ctx->uw, ctx->band_rows, ctx->lag_per_cta, 0, ctx->sm_count, lv.p.f[a],
                                       lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, macro, lv.counters, st);
         mark();
         ctx->launches += launch_fused(Lk, lv.P, ctx->uw, ctx->band_rows, ctx->lag_per_cta, 1, ctx->sm_count, lv.p.f[a],
                                       lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, macro, lv.counters, st);
-    } else if (ctx->variant == 3) {
+    } else if (variant == 3) {
         mark();  // no separate q-correction pass
         ctx->launches += launch_fused_plain(Lk, lv.P, ctx->band_rows, ctx->lag_per_cta, 2, ctx->sm_count, lv.p.f[a],
                                             lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, macro,
@@ -666,12 +669,31 @@ int mbl_step_split(mbl_ctx* ctx, int lev, int part)
         cudaEventRecord(e, st);
         ctx->events.push_back(e);
     };
+    // variant 5 keeps carrying through the split: q-corrections from the previous step's partial sums
+    // (k_qcorr_combine; planes next to a ghost plane are pulled as before), collide by k_collide_tile
+    const bool tile = ctx->variant == 5 && L.sq * 8 < (1LL << 32);
+    const int W = ctx->carry_rows == 8 ? 8 : ctx->carry_rows == 12 ? 12 : 6;
+    if (tile) {
+        if (!lv.part) CU(cudaMalloc(&lv.part, (size_t)CARRY_WORDS * L.sq * sizeof(double)));
+        if (!lv.edge)
+            CU(cudaMalloc(&lv.edge, (size_t)CARRY_EDGE_WORDS * carry_edge_plane(L, 6) * (L.nz + 2 * GZ) * sizeof(double)));
+    }
+    const bool from_sums = tile && lv.carry_valid && lv.edge_rows == W;
+    const CarryPlan C = make_carry_plan(L, ctx->carry_own, ctx->carry_ky);
     auto q = [&](int ka, int kb) {
-        ctx->launches += launch_qcorr(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st, ka, kb);
+        if (from_sums)
+            ctx->launches += launch_qcorr_combine(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.part, lv.edge, W, lv.p.qc, st,
+                                                  ka, kb);
+        else
+            ctx->launches += launch_qcorr(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st, ka, kb);
     };
     auto c = [&](int ka, int kb) {
-        ctx->launches += launch_collide(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
-                                        lv.p.qc, nullptr, true, st, ka, kb);
+        if (tile)
+            ctx->launches += launch_collide_tile(L, lv.P, C, W, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr,
+                                                 lv.p.flag, lv.p.qc, lv.part, lv.edge, st, ka, kb);
+        else
+            ctx->launches += launch_collide(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
+                                            lv.p.qc, nullptr, true, st, ka, kb);
     };
     if (part == 0) {
         // a z-end that is a periodic image of the box itself (single rank in z) has no ghost planes to wait for,
@@ -692,7 +714,8 @@ int mbl_step_split(mbl_ctx* ctx, int lev, int part)
         mark();
         if (ctx->timing) ctx->timed_steps++;
         lv.cur = b;
-        lv.carry_valid = false;
+        lv.carry_valid = tile;
+        lv.edge_rows = tile ? W : 0;
     }
     CU(cudaGetLastError());
     return 0;
@@ -859,6 +882,8 @@ int mbl_get_timing(mbl_ctx* ctx, double ms[3], int* nsteps)
         }
     return mbl_set_timing(ctx, ctx->timing ? 1 : 0);
 }
+
+int mbl_get_variant(mbl_ctx* ctx) { return ctx ? ctx->variant : -1; }
 
 int mbl_set_variant(mbl_ctx* ctx, int variant)
 {

@@ -584,7 +584,7 @@ template <int W>
 __global__ void __launch_bounds__(32 * W, (W <= 8 ? 2 : 1))
     k_collide_tile(const __grid_constant__ CarryPtrs A, const uint32_t* __restrict__ nbr,
                    const uint8_t* __restrict__ flag, const __grid_constant__ Layout L, const __grid_constant__ Phys P,
-                   const __grid_constant__ CarryPlan C)
+                   const __grid_constant__ CarryPlan C, int k0)
 {
     constexpr int T = 32 * W;
     extern __shared__ double smem[];
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(32 * W, (W <= 8 ? 2 : 1))
     const int xc = blockIdx.x;
     const int y0 = blockIdx.y * W;
     const int rows = min(W, L.ny - y0);  // rows of this CTA inside the box
-    const int k = blockIdx.z;
+    const int k = blockIdx.z + k0;
     const int i = xc * C.own - C.halo + lane;
     const bool own = lane >= C.halo && lane < C.halo + C.own && i < L.nx && w < rows;
     // cell this thread collides: its own, the periodic image for halo lanes over a wrapped edge, otherwise
@@ -1690,7 +1690,7 @@ long long carry_edge_plane(const Layout& L, int W) { return L.px * (long long)((
 
 int launch_collide_tile(const Layout& L, const Phys& P, const CarryPlan& C, int rows, const double* fin,
                         const double* gin, double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag,
-                        const double* qc, double* part, double* edge, cudaStream_t st)
+                        const double* qc, double* part, double* edge, cudaStream_t st, int ka, int kb)
 {
     if (L.sq * 8 >= (1LL << 32)) return -1;  // 32-bit byte offsets inside a component
     CarryPtrs A;
@@ -1702,7 +1702,7 @@ int launch_collide_tile(const Layout& L, const Phys& P, const CarryPlan& C, int 
     }
     for (int d = 0; d < 3; ++d) A.qc[d] = qc + (long long)d * L.sq;
     for (int w = 0; w < CARRY_WORDS; ++w) A.part[w] = part + (long long)w * L.sq;
-    const int W = rows == 6 ? 6 : rows == 12 ? 12 : 8;
+    const int W = rows == 8 ? 8 : rows == 12 ? 12 : 6;
     CarryPlan Ce = C;
     const long long esz = carry_edge_plane(L, W);
     Ce.esz8 = (unsigned)(esz * 8);
@@ -1714,25 +1714,29 @@ int launch_collide_tile(const Layout& L, const Phys& P, const CarryPlan& C, int 
         cudaFuncSetAttribute(k_collide_tile<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ * 32 * 12 * 8);
         attr_done = true;
     }
-    const dim3 grid(C.nxc, (L.ny + W - 1) / W, L.nz);
+    dim3 grid(C.nxc, (L.ny + W - 1) / W, L.nz);
+    int k0 = 0;
+    if (kb > ka) k0 = ka, grid.z = kb - ka;  // explicit plane range [ka, kb)
     const size_t sm = (size_t)NQ * 32 * W * 8;
     if (W == 6)
-        k_collide_tile<6><<<grid, 32 * 6, sm, st>>>(A, nbr, flag, L, P, Ce);
+        k_collide_tile<6><<<grid, 32 * 6, sm, st>>>(A, nbr, flag, L, P, Ce, k0);
     else if (W == 12)
-        k_collide_tile<12><<<grid, 32 * 12, sm, st>>>(A, nbr, flag, L, P, Ce);
+        k_collide_tile<12><<<grid, 32 * 12, sm, st>>>(A, nbr, flag, L, P, Ce, k0);
     else
-        k_collide_tile<8><<<grid, 32 * 8, sm, st>>>(A, nbr, flag, L, P, Ce);
+        k_collide_tile<8><<<grid, 32 * 8, sm, st>>>(A, nbr, flag, L, P, Ce, k0);
     return 1;
 }
 
 int launch_qcorr_combine(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr,
-                         const double* part, const double* edge, int edge_rows, double* qc, cudaStream_t st)
+                         const double* part, const double* edge, int edge_rows, double* qc, cudaStream_t st, int ka,
+                         int kb)
 {
     const int bx = block_x(L);
-    const int k0 = (L.lo[2] > L.dlo[2]) ? -1 : 0;
-    const int k1 = (L.lo[2] + L.nz - 1 < L.dhi[2]) ? L.nz : L.nz - 1;
+    int k0 = (L.lo[2] > L.dlo[2]) ? -1 : 0;
+    int k1 = (L.lo[2] + L.nz - 1 < L.dhi[2]) ? L.nz : L.nz - 1;
+    if (kb > ka) k0 = ka, k1 = kb - 1;  // explicit plane range [ka, kb)
     dim3 grid((L.nx + bx - 1) / bx, L.ny, k1 - k0 + 1);
-    const int W = edge ? (edge_rows == 6 ? 6 : edge_rows == 12 ? 12 : 8) : 0;
+    const int W = edge ? (edge_rows == 8 ? 8 : edge_rows == 12 ? 12 : 6) : 0;
     k_qcorr_combine<<<grid, bx, 0, st>>>(fin, gin, nbr, part, edge, W, W ? carry_edge_plane(L, W) : 0, qc, L, P, k0);
     return 1;
 }

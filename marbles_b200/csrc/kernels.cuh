@@ -89,12 +89,13 @@ int launch_collide_lean(const Layout& L, const Phys& P, int min_blocks, const do
 // the same without marching: CTA = `rows` warps = rows - 2 owned rows + 2 halo rows of one column strip
 int launch_collide_tile(const Layout& L, const Phys& P, const CarryPlan& C, int rows, const double* fin,
                         const double* gin, double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag,
-                        const double* qc, double* part, double* edge, cudaStream_t st);
+                        const double* qc, double* part, double* edge, cudaStream_t st, int ka = 0, int kb = 0);
 // doubles per plane of one edge array for `rows` rows per CTA (the array spans nz + 2 GZ planes)
 long long carry_edge_plane(const Layout& L, int rows);
 // edge / edge_rows: the edge arrays k_collide_tile wrote (nullptr after k_collide_carry)
 int launch_qcorr_combine(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr,
-                         const double* part, const double* edge, int edge_rows, double* qc, cudaStream_t st);
+                         const double* part, const double* edge, int edge_rows, double* qc, cudaStream_t st, int ka = 0,
+                         int kb = 0);
 
 int launch_stream(const Layout& L, const double* fin, const double* gin, double* fout, double* gout,
                   const uint32_t* nbr, cudaStream_t st);

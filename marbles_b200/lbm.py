@@ -63,7 +63,6 @@ class LBM:
             inputs = lbm_inputs(d)
         self.inp = inputs
         self.rank, self.world, self.comm = rank, world, comm
-        self.variant = 0 if variant is None else variant
         self.cuda_stream = cuda_stream
         self.overlap = os.environ.get("MBL_OVERLAP", "1") != "0"
         self._ghosts_fresh = False  # the ghost planes of the current buffers hold the neighbours' planes
@@ -95,6 +94,7 @@ class LBM:
             check(self.lib.mbl_set_stream(self.ctx, C.c_void_p(cuda_stream)))
         if variant is not None:
             check(self.lib.mbl_set_variant(self.ctx, variant))
+        self.variant = int(self.lib.mbl_get_variant(self.ctx))  # library default (MBL_VARIANT) unless given
 
         g = LevelGeom()
         dx = inputs.dx
@@ -220,8 +220,8 @@ class LBM:
 
     def can_overlap(self) -> bool:
         """The overlapped slab step (mbl_step_split) applies to all-periodic decks (no ghost fill between its
-        parts), the two-kernel variant and slabs of at least 8 planes."""
-        return (self.world > 1 and all(self.inp.periodic) and self.variant == 0 and self.n_local[2] >= 8
+        parts), the two-kernel and the tile-carry variants and slabs of at least 8 planes."""
+        return (self.world > 1 and all(self.inp.periodic) and self.variant in (0, 5) and self.n_local[2] >= 8
                 and self.comm is not None and hasattr(self.comm, "exchange_next") and self.overlap)
 
     def step(self, nsteps: int = 1, want_macrodata: bool = False):

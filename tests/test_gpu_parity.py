@@ -295,8 +295,9 @@ def test_step_host_matches_device_step(case, ov, chunk, ng):
     b.close()
 
 
+@pytest.mark.parametrize("variant", [0, 5], ids=["twopass", "tile"])
 @pytest.mark.parametrize("nz,world", [(16, 2), (27, 3)])
-def test_overlapped_slab_step_matches_single_box(nz, world):
+def test_overlapped_slab_step_matches_single_box(nz, world, variant):
     """mbl_step_split (boundary planes first, exchange of the written buffers' boundary planes, interior planes)
     in the order LBM._step_overlapped issues it, on one device: bit-identical to the single box"""
     import torch
@@ -309,16 +310,21 @@ def test_overlapped_slab_step_matches_single_box(nz, world):
     single.init_data()
 
     def make(rank, w):
-        s = LBM(deck, rank=rank, world=w, comm=None, variant=0)
+        s = LBM(deck, rank=rank, world=w, comm=None, variant=variant)
         s.init_data()
         return s
 
     slabs = LocalSlabs(make, world, True, torch.device("cuda", 0))
-    single.step(5)
+    single.step(7)
     slabs.step_overlapped(3)
     slabs.step(2)  # and back to the plain slab step
+    slabs.step_overlapped(2)
     for get in (lambda s: s.get_f(), lambda s: s.get_g()):
-        assert np.array_equal(get(single), slabs.gather(get))
+        a, b = get(single), slabs.gather(get)
+        if variant == 0:
+            assert np.array_equal(a, b)
+        else:  # carried moments are summed in another order
+            assert np.abs(a - b).max() <= 7e-12 * np.abs(a).max()
     slabs.close()
     single.close()
 
