@@ -190,6 +190,12 @@ int mbl_halo_unpack_next(mbl_ctx* ctx, int lev, int side, const double* device_b
  * (FAB layout, ghost ng), run nsteps, download f,g into the same buffers */
 int mbl_step_host(mbl_ctx* ctx, int lev, int nsteps, double time, double* f_fab, double* g_fab, int ng);
 
+/* the same for a z-slab of a multi-rank run (all-periodic level): begin uploads the two outermost planes at each
+ * z-end, the caller exchanges them (mbl_halo_pack / transport / mbl_halo_unpack on the context's stream), finish
+ * uploads the interior in chunks with the kernels following the upload frontier and the result going back down */
+int mbl_step_host_begin(mbl_ctx* ctx, int lev, double* f_fab, double* g_fab, int ng);
+int mbl_step_host_finish(mbl_ctx* ctx, int lev, double* f_fab, double* g_fab, int ng);
+
 /* number of kernels launched by this context so far (bench.py gpu_launches) */
 int64_t mbl_launch_count(mbl_ctx* ctx);
 /* per-kernel device timing of mbl_step / mbl_step_local with CUDA events on the context's

@@ -81,6 +81,8 @@ SYMBOLS = {
     "mbl_halo_pack_next": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "mbl_halo_unpack_next": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "mbl_step_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D, _D, C.c_int]),
+    "mbl_step_host_begin": (C.c_int, [_P, C.c_int, _D, _D, C.c_int]),
+    "mbl_step_host_finish": (C.c_int, [_P, C.c_int, _D, _D, C.c_int]),
     "mbl_launch_count": (C.c_int64, [_P]),
     "mbl_set_variant": (C.c_int, [_P, C.c_int]),
     "mbl_get_variant": (C.c_int, [_P]),

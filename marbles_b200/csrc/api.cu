@@ -834,6 +834,97 @@ static int step_host_pipelined(mbl_ctx* ctx, Level& lv, double* f_fab, double* g
     return 0;
 }
 
+// The same for a z-slab of a multi-rank run (all-periodic level, not wrapped in z): the two outermost planes at
+// each z-end go up first (begin), the caller exchanges them with the neighbours (mbl_halo_pack / transport /
+// mbl_halo_unpack on the context's stream), then finish() uploads the interior planes in chunks while the kernels
+// follow the upload frontier and finished planes go back down.
+int mbl_step_host_begin(mbl_ctx* ctx, int lev, double* f_fab, double* g_fab, int ng)
+{
+    if (check_level(ctx, lev)) return 1;
+    if (!f_fab || !g_fab || ng < 0) return fail("mbl_step_host_begin: bad argument");
+    Level& lv = ctx->lev[lev];
+    const Layout& L = lv.L;
+    if (!(L.wrap[0] && L.wrap[1]) || L.wrap[2] || L.nz < 8)
+        return fail("mbl_step_host_begin: for z-slabs (at least 8 planes) of all-periodic levels");
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->s_up) {
+        CU(cudaStreamCreateWithFlags(&ctx->s_up, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ctx->s_down, cudaStreamNonBlocking));
+    }
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaEventRecord(e, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->s_up, e, 0));
+    const int a = lv.cur, nz = L.nz;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int ka = pass ? nz - GZ : 0, kb = pass ? nz : GZ;
+        if (copy_planes(lv, lv.p.f[a], f_fab, ng, ka, kb, true, ctx->s_up)) return 1;
+        if (copy_planes(lv, lv.p.g[a], g_fab, ng, ka, kb, true, ctx->s_up)) return 1;
+    }
+    CU(cudaEventRecord(e, ctx->s_up));
+    CU(cudaStreamWaitEvent(ctx->stream, e, 0));  // the halo pack that follows reads these planes
+    CU(cudaEventDestroy(e));
+    lv.carry_valid = false;
+    return 0;
+}
+
+int mbl_step_host_finish(mbl_ctx* ctx, int lev, double* f_fab, double* g_fab, int ng)
+{
+    if (check_level(ctx, lev)) return 1;
+    if (!f_fab || !g_fab || ng < 0) return fail("mbl_step_host_finish: bad argument");
+    Level& lv = ctx->lev[lev];
+    const Layout& L = lv.L;
+    if (!(L.wrap[0] && L.wrap[1]) || L.wrap[2] || L.nz < 8 || !ctx->s_up)
+        return fail("mbl_step_host_finish without mbl_step_host_begin");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t sc = ctx->stream, su = ctx->s_up, sd = ctx->s_down;
+    const int a = lv.cur, b = 1 - lv.cur, nz = L.nz;
+    const int cz = ctx->host_chunk > 0 ? ctx->host_chunk : 16;
+    std::vector<cudaEvent_t> evs;
+    auto event = [&](cudaStream_t st) {
+        cudaEvent_t e;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        cudaEventRecord(e, st);
+        evs.push_back(e);
+        return e;
+    };
+    cudaEvent_t e0 = event(sc);  // the ghost planes are in (halo unpack on the compute stream)
+    CU(cudaStreamWaitEvent(sd, e0, 0));
+    // planes [-2, 2) and [nz-2, nz+2) are on the device: q-corrections that need nothing else
+    ctx->launches += launch_qcorr(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, sc, -1, 1);
+    ctx->launches += launch_qcorr(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, sc, nz - 1, nz + 1);
+    int qdone = 1, cdone = 0;
+    const int top = nz - GZ;
+    for (int u0 = GZ; u0 < top; u0 += cz) {
+        const int u = std::min(top, u0 + cz);  // planes [-2, u) and [top, nz+2) are on the device after this upload
+        if (copy_planes(lv, lv.p.f[a], f_fab, ng, u0, u, true, su)) return 1;
+        if (copy_planes(lv, lv.p.g[a], g_fab, ng, u0, u, true, su)) return 1;
+        CU(cudaStreamWaitEvent(sc, event(su), 0));
+        const int qhi = (u == top) ? nz - 1 : u - 1;
+        if (qhi > qdone) {
+            ctx->launches += launch_qcorr(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, sc, qdone, qhi);
+            qdone = qhi;
+        }
+        const int chi = (qdone == nz - 1) ? nz : qdone - 1;
+        if (chi > cdone) {
+            ctx->launches += launch_collide(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
+                                            lv.p.qc, nullptr, true, sc, cdone, chi);
+            CU(cudaStreamWaitEvent(sd, event(sc), 0));
+            if (copy_planes(lv, lv.p.f[b], f_fab, ng, cdone, chi, false, sd)) return 1;
+            if (copy_planes(lv, lv.p.g[b], g_fab, ng, cdone, chi, false, sd)) return 1;
+            cdone = chi;
+        }
+    }
+    lv.cur = b;
+    lv.carry_valid = false;
+    CU(cudaStreamWaitEvent(sc, event(sd), 0));
+    CU(cudaStreamSynchronize(sd));
+    CU(cudaStreamSynchronize(sc));
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int mbl_step_host(mbl_ctx* ctx, int lev, int nsteps, double time, double* f_fab, double* g_fab, int ng)
 {
     if (check_level(ctx, lev)) return 1;

@@ -272,7 +272,23 @@ class LBM:
         check(self.lib.mbl_sync(self.ctx))
 
     def step_host(self, f_fab: np.ndarray, g_fab: np.ndarray, nsteps: int = 1, ng: int = F_NGHOST):
-        """The reference-facing call with HOST buffers (FAB layout): upload, nsteps, download in place."""
+        """The reference-facing call with HOST buffers (FAB layout): upload, nsteps, download in place.  On a
+        z-slab of an all-periodic multi-rank run the boundary planes go up first, are exchanged with the
+        neighbours, and the rest of the slab is pipelined (mbl_step_host_begin / _finish)."""
+        if self.world > 1:
+            if nsteps != 1 or not all(self.inp.periodic) or self.n_local[2] < 8:
+                self.set_state(f_fab, g_fab, ng)
+                self.step(nsteps)
+                check(self.lib.mbl_download(self.ctx, self.lev, 0, _dptr(f_fab), ng))
+                check(self.lib.mbl_download(self.ctx, self.lev, 1, _dptr(g_fab), ng))
+                return
+            check(self.lib.mbl_step_host_begin(self.ctx, self.lev, _dptr(f_fab), _dptr(g_fab), ng))
+            self.exchange_halo()
+            check(self.lib.mbl_step_host_finish(self.ctx, self.lev, _dptr(f_fab), _dptr(g_fab), ng))
+            self._ghosts_fresh = False
+            self.time += self.dt
+            self.isteps += 1
+            return
         check(self.lib.mbl_step_host(self.ctx, self.lev, nsteps, self.time, _dptr(f_fab), _dptr(g_fab), ng))
         self._ghosts_fresh = False
         self.time += nsteps * self.dt

@@ -186,6 +186,18 @@ class LocalSlabs:
                 s.isteps += 1
                 s.sync()
 
+    def step_host(self, fabs, ng: int = 0):
+        """LBM.step_host of every slab in the multi-rank order: boundary planes up, exchange, pipelined rest.
+        fabs: one (f, g) pair of host FAB arrays per slab, updated in place."""
+        from .lbm import _dptr
+        for s, (f, g) in zip(self.slabs, fabs):
+            check(s.lib.mbl_step_host_begin(s.ctx, 0, _dptr(f), _dptr(g), ng))
+        self.exchange()
+        for s, (f, g) in zip(self.slabs, fabs):
+            check(s.lib.mbl_step_host_finish(s.ctx, 0, _dptr(f), _dptr(g), ng))
+            s.time += s.dt
+            s.isteps += 1
+
     def gather(self, getter):
         """concatenate a per-slab FAB getter (e.g. LBM.get_f) along z"""
         import numpy as np
