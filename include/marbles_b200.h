@@ -122,10 +122,13 @@ int mbl_level_lattice_ptr(mbl_ctx* ctx, int lev, int which, void** out);
 int mbl_set_is_fluid(mbl_ctx* ctx, int lev, const int32_t* is_fluid, int ng);
 int mbl_set_all_fluid(mbl_ctx* ctx, int lev);
 
-/* state transfer, HOST <-> device, FAB layout (27 comps, ghost ng; only valid
- * cells are read on upload unless with_ghosts != 0).  These are the calls that
- * carry m_f[lev] / m_g[lev] across the boundary (checkpoint restart, plotfiles,
- * regrid: Source/LBM.cpp:1629-1675, 1772-1782, 1897-1915). */
+/* state transfer between a FAB (27 comps, ghost width ng, x fastest, component slowest:
+ * AMReX_Array4.H:60-94) and the library's padded SoA buffers: one pitched DMA per component.
+ * `fab` may point to HOST memory or to DEVICE memory (an AMReX device-arena MultiFab: pass
+ * mf[mfi].dataPtr()); upload also takes the FAB's ghost cells the device layout has room for,
+ * download writes valid cells only.  These are the calls that carry m_f[lev] / m_g[lev] across
+ * the boundary (checkpoint restart, plotfiles, regrid: Source/LBM.cpp:1629-1675, 1772-1782,
+ * 1897-1915). */
 int mbl_upload(mbl_ctx* ctx, int lev, int which, const double* fab, int ng);
 int mbl_download(mbl_ctx* ctx, int lev, int which, double* fab, int ng);
 /* macrodata of the last collide/step with want_macrodata (19 comps, ghost ng<=1,

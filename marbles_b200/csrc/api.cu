@@ -51,8 +51,6 @@ struct Level {
     LevelPtrs p;
     int cur = 0;  // index of the current lattice buffers
     bool local_z = true;
-    double* stage = nullptr;  // one-component staging for FAB transfers
-    size_t stage_bytes = 0;
     int32_t* flag_stage = nullptr;
     double* d_red = nullptr;  // 3 doubles for reductions
     double* macro = nullptr;  // lazily allocated (26 comps)
@@ -115,17 +113,6 @@ int check_level(mbl_ctx* ctx, int lev)
 {
     if (!ctx) return fail("null context");
     if (lev < 0 || lev >= MAX_LEVELS || !ctx->lev[lev].defined) return fail("level %d is not defined", lev);
-    return 0;
-}
-
-int ensure_stage(Level& lv, size_t bytes)
-{
-    if (lv.stage_bytes >= bytes) return 0;
-    if (lv.stage) cudaFree(lv.stage);
-    lv.stage = nullptr;
-    lv.stage_bytes = 0;
-    CU(cudaMalloc(&lv.stage, bytes));
-    lv.stage_bytes = bytes;
     return 0;
 }
 
@@ -319,7 +306,6 @@ int mbl_level_clear(mbl_ctx* ctx, int lev)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (lv.owned && lv.base) cudaFree(lv.base);
-    if (lv.stage) cudaFree(lv.stage);
     if (lv.flag_stage) cudaFree(lv.flag_stage);
     if (lv.d_red) cudaFree(lv.d_red);
     if (lv.macro) cudaFree(lv.macro);
@@ -432,7 +418,7 @@ int mbl_set_is_fluid(mbl_ctx* ctx, int lev, const int32_t* is_fluid, int ng)
     const size_t n = (size_t)(lv.L.nx + 2 * ng) * (lv.L.ny + 2 * ng) * (lv.L.nz + 2 * ng);
     if (lv.flag_stage) cudaFree(lv.flag_stage);
     CU(cudaMalloc(&lv.flag_stage, n * sizeof(int32_t)));
-    CU(cudaMemcpyAsync(lv.flag_stage, is_fluid, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(lv.flag_stage, is_fluid, n * sizeof(int32_t), cudaMemcpyDefault, ctx->stream));
     ctx->launches += launch_flags(lv.L, lv.B, lv.flag_stage, ng, lv.p.nbr, lv.p.flag, ctx->stream);
     CU(cudaStreamSynchronize(ctx->stream));
     cudaFree(lv.flag_stage);
@@ -464,7 +450,7 @@ static int copy_planes(Level& lv, double* soa, double* fab, int ng, int ka, int 
         p.dstPtr = to_device ? dev : host;
         p.dstPos = to_device ? dpos : hpos;
         p.extent = make_cudaExtent((L.nx + 2 * gx) * sizeof(double), L.ny + 2 * gy, kb - ka);
-        p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+        p.kind = cudaMemcpyDefault;  // the FAB may live in host memory or in device memory (AMReX device arena)
         CU(cudaMemcpy3DAsync(&p, st));
     }
     return 0;

@@ -1325,29 +1325,6 @@ __global__ void __launch_bounds__(128) k_flags(const int32_t* __restrict__ fab, 
     flag[c] = (uint8_t)fb;
 }
 
-// ---------------------------------------------------------------------------
-// layout conversion: one component, FAB(ng) <-> SoA
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_fab_to_soa(const double* __restrict__ fab, int ng, double* __restrict__ soa,
-                                                    Layout L, int gx, int gy, int gz)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x - gx;
-    const int j = blockIdx.y - gy;
-    const int k = blockIdx.z - gz;
-    if (i > L.nx - 1 + gx) return;
-    const long long sx = L.nx + 2 * ng, sy = L.ny + 2 * ng;
-    soa[L.cell(i, j, k)] = fab[(i + ng) + (j + ng) * sx + (long long)(k + ng) * sx * sy];
-}
-__global__ void __launch_bounds__(128) k_soa_to_fab(const double* __restrict__ soa, int ng, double* __restrict__ fab,
-                                                    Layout L)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    const int k = blockIdx.z;
-    if (i >= L.nx) return;
-    const long long sx = L.nx + 2 * ng, sy = L.ny + 2 * ng;
-    fab[(i + ng) + (j + ng) * sx + (long long)(k + ng) * sx * sy] = soa[L.cell(i, j, k)];
-}
 __global__ void k_fill(double* __restrict__ p, long long n, double v)
 {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1457,20 +1434,6 @@ int launch_flags_all_fluid(const Layout& L, const BcInfo& B, uint32_t* nbr, uint
     return launch_flags(L, B, nullptr, 0, nbr, flag, st);
 }
 
-int launch_fab_to_soa(const Layout& L, const double* fab, int ng, double* soa, int with_ghosts, cudaStream_t st)
-{
-    const int bx = block_x(L);
-    const int gx = with_ghosts ? (ng < GX ? ng : GX) : 0, gy = with_ghosts ? (ng < GY ? ng : GY) : 0,
-              gz = with_ghosts ? (ng < GZ ? ng : GZ) : 0;
-    k_fab_to_soa<<<grid3(L, bx, gx, gy, gz), bx, 0, st>>>(fab, ng, soa, L, gx, gy, gz);
-    return 1;
-}
-int launch_soa_to_fab(const Layout& L, const double* soa, int ng, double* fab, cudaStream_t st)
-{
-    const int bx = block_x(L);
-    k_soa_to_fab<<<grid3(L, bx), bx, 0, st>>>(soa, ng, fab, L);
-    return 1;
-}
 int launch_fill(double* p, long long n, double v, cudaStream_t st)
 {
     k_fill<<<148 * 8, 256, 0, st>>>(p, n, v);

@@ -35,9 +35,6 @@ int launch_flags(const Layout& L, const BcInfo& B, const int32_t* d_isfluid_fab,
                  cudaStream_t st);
 int launch_flags_all_fluid(const Layout& L, const BcInfo& B, uint32_t* nbr, uint8_t* flag, cudaStream_t st);
 
-int launch_fab_to_soa(const Layout& L, const double* d_fab_comp, int ng, double* soa_comp, int with_ghosts,
-                      cudaStream_t st);
-int launch_soa_to_fab(const Layout& L, const double* soa_comp, int ng, double* d_fab_comp, cudaStream_t st);
 int launch_fill(double* p, long long n, double v, cudaStream_t st);
 
 int launch_initialize(const Layout& L, const BcInfo& B, const IcInfo& I, const uint8_t* flag, double* f, double* g,
