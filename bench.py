@@ -118,12 +118,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def reference_mlups(size: int, steps: int, threads: int | None = None):
+def reference_mlups(size: int, steps: int, threads: int | None = None, exe: str | None = None):
     """Run the unmodified reference (oracle/_ref, OpenMP build) on the TG deck at size^3 and return
     (MLUPS, seconds per step, threads).  Per-step time = LBM::evolve() inclusive time of the
     reference's own TinyProfiler table / steps."""
     from oracle import oracle as O
-    exe = O.REF_OMP if os.path.exists(O.REF_OMP) else O.REF_SERIAL
+    if exe is None:
+        exe = O.REF_OMP if os.path.exists(O.REF_OMP) else O.REF_SERIAL
     if not os.path.exists(exe):
         return None
     threads = threads or os.cpu_count() or 1
@@ -192,6 +193,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-size", type=int, default=128)
     ap.add_argument("--ref-steps", type=int, default=4)
+    ap.add_argument("--ref-gpu-size", type=int, default=384, help="box of the reference-CUDA-build sample")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -370,6 +372,17 @@ def main():
             cpu = {"value": r[0], "unit": "MLUPS", "cores": r[2], "kind": "reference",
                    "sample": f"TG deck {args.ref_size}^3, {args.ref_steps} steps, LBM::evolve() inclusive time, {r[3]}"}
 
+    # ---- the reference's own GPU path (unmodified sources, nvcc build of oracle/refbuild) on this GPU ------------
+    ref_gpu = None
+    cuda_exe = os.path.join(ROOT, "oracle", "_ref", "marbles3d.cuda.ex")
+    if rank == 0 and world == 1 and not args.no_cpu and os.path.exists(cuda_exe):
+        torch.cuda.empty_cache()
+        r = reference_mlups(args.ref_gpu_size, 10, threads=1, exe=cuda_exe)
+        if r is not None:
+            ref_gpu = {"value": r[0], "unit": "MLUPS", "kind": "reference CUDA build (AMReX ParallelFor kernels, sm_100a)",
+                       "sample": f"TG deck {args.ref_gpu_size}^3 (its ~190 words per cell do not fit 512^3 in 180 GB), "
+                                 f"10 steps, LBM::evolve() inclusive time, {r[3]}"}
+
     if rank == 0:
         line = {
             "metric": "MLUPS (D3Q27 f+g, fp64)", "value": value, "unit": "MLUPS", "n_gpus": world,
@@ -379,7 +392,8 @@ def main():
                                    f"(BASELINE config 3; domain {n}x{n}x{n * world})",
                        "decomposition": f"{world} z-slab(s)", "l2": "state (58 GB per GPU at 512^3) is far larger than L2",
                        "variant": vname},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "e2e": e2e,
+            "gpu_launches": int(launches),
             "clocks": clocks,
         }
         print(json.dumps(line))
