@@ -383,3 +383,28 @@ def test_step_host_on_slabs_matches_device_slab_step(nz, world, chunk, ng):
     assert np.array_equal(a.gather(lambda s: s.get_f()), b.gather(lambda s: s.get_f()))
     a.close()
     b.close()
+
+
+def test_full_size_conservation_512():
+    """BASELINE config 3 at its full size (periodic 512^3, the default step): mass and energy are conserved by
+    stream + collide, every population stays finite and positive"""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 150e9:
+        pytest.skip("needs the 180 GB of a B200")
+    _, deck_text, _ = load_golden("tg12")
+    a = new_lbm(deck_text, overrides=["amr.n_cell = 512 512 512"])
+    sums = []
+    for it in range(2):
+        if it == 1:
+            a.step(4)
+        tot = []
+        for get in (a.get_f, a.get_g):
+            x = get(0)
+            if it == 1:
+                assert np.isfinite(x).all() and x.min() > 0
+            tot.append(x.sum(dtype=np.float64))
+            del x
+        sums.append(tot)
+    assert abs(sums[1][0] - sums[0][0]) <= 1e-11 * sums[0][0]
+    assert abs(sums[1][1] - sums[0][1]) <= 1e-11 * sums[0][1]
+    a.close()
