@@ -158,9 +158,9 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
         // carry step: q-corrections from the partial sums the previous collide left behind (first step, or after
         // anything else wrote the lattice: the full q-correction pass)
         if (!lv.part) CU(cudaMalloc(&lv.part, (size_t)CARRY_WORDS * lv.L.sq * sizeof(double)));
-        const int W = ctx->carry_rows == 8 ? 8 : ctx->carry_rows == 12 ? 12 : 6;
+        const int W = carry_tile_rows(ctx->carry_rows);
         if (variant == 5 && !lv.edge)
-            CU(cudaMalloc(&lv.edge, (size_t)CARRY_EDGE_WORDS * carry_edge_plane(lv.L, 6) * (lv.L.nz + 2 * GZ) * sizeof(double)));
+            CU(cudaMalloc(&lv.edge, (size_t)CARRY_EDGE_WORDS * carry_edge_plane(lv.L, 4) * (lv.L.nz + 2 * GZ) * sizeof(double)));
         if (lv.carry_valid)
             ctx->launches += launch_qcorr_combine(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.part,
                                                   lv.edge_rows ? lv.edge : nullptr, lv.edge_rows, lv.p.qc, st);
@@ -658,11 +658,11 @@ int mbl_step_split(mbl_ctx* ctx, int lev, int part)
     // variant 5 keeps carrying through the split: q-corrections from the previous step's partial sums
     // (k_qcorr_combine; planes next to a ghost plane are pulled as before), collide by k_collide_tile
     const bool tile = ctx->variant == 5 && L.sq * 8 < (1LL << 32);
-    const int W = ctx->carry_rows == 8 ? 8 : ctx->carry_rows == 12 ? 12 : 6;
+    const int W = carry_tile_rows(ctx->carry_rows);
     if (tile) {
         if (!lv.part) CU(cudaMalloc(&lv.part, (size_t)CARRY_WORDS * L.sq * sizeof(double)));
         if (!lv.edge)
-            CU(cudaMalloc(&lv.edge, (size_t)CARRY_EDGE_WORDS * carry_edge_plane(L, 6) * (L.nz + 2 * GZ) * sizeof(double)));
+            CU(cudaMalloc(&lv.edge, (size_t)CARRY_EDGE_WORDS * carry_edge_plane(L, 4) * (L.nz + 2 * GZ) * sizeof(double)));
     }
     const bool from_sums = tile && lv.carry_valid && lv.edge_rows == W;
     const CarryPlan C = make_carry_plan(L, ctx->carry_own, ctx->carry_ky);

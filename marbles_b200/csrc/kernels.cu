@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(128, MINB)
 // row is collided twice.  g again travels global -> shared by cp.async, and the exchange reuses those slots.
 // ---------------------------------------------------------------------------
 template <int W>
-__global__ void __launch_bounds__(32 * W, (W <= 8 ? 2 : 1))
+__global__ void __launch_bounds__(32 * W, (W <= 4 ? 3 : W <= 8 ? 2 : 1))
     k_collide_tile(const __grid_constant__ CarryPtrs A, const uint32_t* __restrict__ nbr,
                    const uint8_t* __restrict__ flag, const __grid_constant__ Layout L, const __grid_constant__ Phys P,
                    const __grid_constant__ CarryPlan C, int k0)
@@ -1650,6 +1650,7 @@ int launch_collide_lean(const Layout& L, const Phys& P, int min_blocks, const do
 }
 
 long long carry_edge_plane(const Layout& L, int W) { return L.px * (long long)((L.ny + W - 1) / W); }
+int carry_tile_rows(int rows) { return rows == 4 ? 4 : rows == 8 ? 8 : rows == 12 ? 12 : 6; }
 
 int launch_collide_tile(const Layout& L, const Phys& P, const CarryPlan& C, int rows, const double* fin,
                         const double* gin, double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag,
@@ -1665,13 +1666,14 @@ int launch_collide_tile(const Layout& L, const Phys& P, const CarryPlan& C, int 
     }
     for (int d = 0; d < 3; ++d) A.qc[d] = qc + (long long)d * L.sq;
     for (int w = 0; w < CARRY_WORDS; ++w) A.part[w] = part + (long long)w * L.sq;
-    const int W = rows == 8 ? 8 : rows == 12 ? 12 : 6;
+    const int W = carry_tile_rows(rows);
     CarryPlan Ce = C;
     const long long esz = carry_edge_plane(L, W);
     Ce.esz8 = (unsigned)(esz * 8);
     for (int e = 0; e < CARRY_EDGE_WORDS; ++e) A.edge[e] = edge + (long long)e * esz * (L.nz + 2 * GZ);
     static bool attr_done = false;
     if (!attr_done) {
+        cudaFuncSetAttribute(k_collide_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ * 32 * 4 * 8);
         cudaFuncSetAttribute(k_collide_tile<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ * 32 * 6 * 8);
         cudaFuncSetAttribute(k_collide_tile<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ * 32 * 8 * 8);
         cudaFuncSetAttribute(k_collide_tile<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ * 32 * 12 * 8);
@@ -1681,7 +1683,9 @@ int launch_collide_tile(const Layout& L, const Phys& P, const CarryPlan& C, int 
     int k0 = 0;
     if (kb > ka) k0 = ka, grid.z = kb - ka;  // explicit plane range [ka, kb)
     const size_t sm = (size_t)NQ * 32 * W * 8;
-    if (W == 6)
+    if (W == 4)
+        k_collide_tile<4><<<grid, 32 * 4, sm, st>>>(A, nbr, flag, L, P, Ce, k0);
+    else if (W == 6)
         k_collide_tile<6><<<grid, 32 * 6, sm, st>>>(A, nbr, flag, L, P, Ce, k0);
     else if (W == 12)
         k_collide_tile<12><<<grid, 32 * 12, sm, st>>>(A, nbr, flag, L, P, Ce, k0);
@@ -1699,7 +1703,7 @@ int launch_qcorr_combine(const Layout& L, const Phys& P, const double* fin, cons
     int k1 = (L.lo[2] + L.nz - 1 < L.dhi[2]) ? L.nz : L.nz - 1;
     if (kb > ka) k0 = ka, k1 = kb - 1;  // explicit plane range [ka, kb)
     dim3 grid((L.nx + bx - 1) / bx, L.ny, k1 - k0 + 1);
-    const int W = edge ? (edge_rows == 8 ? 8 : edge_rows == 12 ? 12 : 6) : 0;
+    const int W = edge ? carry_tile_rows(edge_rows) : 0;
     k_qcorr_combine<<<grid, bx, 0, st>>>(fin, gin, nbr, part, edge, W, W ? carry_edge_plane(L, W) : 0, qc, L, P, k0);
     return 1;
 }

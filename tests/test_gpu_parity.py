@@ -24,6 +24,7 @@ CARRY_ENV = {
     "tile": (5, {}),
     "tile-6rows-own28": (5, {"MBL_ROWS": "6", "MBL_OWN": "28"}),
     "tile-12rows": (5, {"MBL_ROWS": "12"}),
+    "tile-4rows": (5, {"MBL_ROWS": "4"}),
     "lean": (6, {"MBL_MINB": "4"}),
 }
 TUNING_VARS = ("MBL_KY", "MBL_OWN", "MBL_MINB", "MBL_ROWS")
@@ -108,9 +109,10 @@ def test_geometry_matches_reference_is_fluid():
         assert np.array_equal(a, z["is_fluid"].astype(np.int32)), case
 
 
-@pytest.mark.parametrize("variant", [1, 3, 0, "carry", "carry-ky5-own28", "carry-ky1", "tile", "tile-6rows-own28", "tile-12rows"],
+@pytest.mark.parametrize("variant", [1, 3, 0, "carry", "carry-ky5-own28", "carry-ky1", "tile", "tile-6rows-own28", "tile-12rows",
+                                     "tile-4rows"],
                          ids=["fused-tma", "fused-plain", "twopass-plain", "carry", "carry-ky5-own28", "carry-ky1", "tile",
-                              "tile-6rows-own28", "tile-12rows"])
+                              "tile-6rows-own28", "tile-12rows", "tile-4rows"])
 @pytest.mark.parametrize("case", ["chcyl", "pressure", "slip", "tg12"])
 def test_random_state_vs_oracle(oracle_mod, case, variant):
     """seeded random perturbation of f, g and a random solid mask, 3 steps, all boundary types"""
@@ -398,10 +400,10 @@ def test_full_size_conservation_512():
         if it == 1:
             a.step(4)
         tot = []
-        for get in (a.get_f, a.get_g):
+        for name, get in (("f", a.get_f), ("g", a.get_g)):
             x = get(0)
             if it == 1:  # the energy lattice g may be negative (its rest population is close to zero)
-                assert np.isfinite(x).all() and (get is a.get_g or x.min() > 0)
+                assert np.isfinite(x).all() and (name == "g" or x.min() > 0)
             tot.append(x.sum(dtype=np.float64))
             del x
         sums.append(tot)
