@@ -32,15 +32,35 @@ def plot_file_var_names(save_streaming: bool = True, save_derived: bool = True) 
     return names + IS_FLUID_NAMES
 
 
+def _max_size_cuts(n: int, chunk: int):
+    """BoxList::maxSize for one direction (AMReX_BoxList.cpp:765-818): halve block size and length together while
+    both are even, cut the remaining length into ceil(len / block) pieces whose sizes differ by at most one
+    (the longer ones first), scale back.  Returns inclusive (lo, hi) pairs."""
+    if n <= chunk:
+        return [(0, n - 1)]
+    ratio, bs, nlen = 1, chunk, n
+    while bs % 2 == 0 and nlen % 2 == 0:
+        ratio, bs, nlen = ratio * 2, bs // 2, nlen // 2
+    numblk = (nlen + bs - 1) // bs
+    sz = nlen // numblk
+    extra = nlen - sz * numblk
+    cuts, lo = [], 0
+    for b in range(numblk):
+        ln = (sz + 1 if b < extra else sz) * ratio
+        cuts.append((lo, lo + ln - 1))
+        lo += ln
+    return cuts
+
+
 def chop_boxes(n_cell, max_grid_size: int):
-    """The level's BoxArray as AmrMesh::MakeNewGrids builds it for a single level: the domain chopped into
-    boxes of max_grid_size cells per side (a shorter last box where it does not divide), x fastest -- what
-    BoxArray::maxSize gives for the sizes the reference decks use (n a multiple of the blocking factor)."""
+    """The level-0 BoxArray as AmrMesh::MakeBaseGrids builds it on one process (AMReX_AmrMesh.cpp): the domain is
+    coarsened by 2 in every direction with an even number of cells, chopped with BoxList::maxSize(max_grid_size / 2)
+    and refined again; boxes are listed x fastest."""
     cuts = []
     for d in range(3):
         n = int(n_cell[d])
-        edges = list(range(0, n, max_grid_size)) + [n]
-        cuts.append([(edges[i], edges[i + 1] - 1) for i in range(len(edges) - 1)])
+        fac = 2 if n % 2 == 0 else 1
+        cuts.append([(lo * fac, (hi + 1) * fac - 1) for lo, hi in _max_size_cuts(n // fac, max(1, max_grid_size // fac))])
     boxes = []
     for kz in cuts[2]:
         for jy in cuts[1]:

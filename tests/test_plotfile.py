@@ -76,3 +76,14 @@ def test_lbm_write_plot_file_matches_golden(tmp_path):
     worst, key = compare(got, {k: ref[k] for k in got}, sc, n)
     print(f"plotfile fields: worst {worst:.2e} ({key}), {len(got)} components")
     lbm.close()
+
+
+def test_box_lists_match_reference():
+    """chop_boxes against the level-0 BoxArrays of the unmodified reference (tests/golden/boxes.json, made by
+    tests/golden/make_boxes_golden.py): sizes that do and do not divide by max_grid_size, odd half-lengths"""
+    import json
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "boxes.json")))
+    assert len(cases) >= 6
+    for c in cases:
+        mine = [[list(lo), list(hi)] for lo, hi in P.chop_boxes(c["n_cell"], c["max_grid_size"])]
+        assert mine == c["boxes"], (c["n_cell"], c["max_grid_size"])
