@@ -58,6 +58,11 @@ struct Level {
     double* part = nullptr;   // carry step: 12 partial-sum words per cell (lazily allocated)
     double* edge = nullptr;   // tile carry step: 18 words per CTA row
     int edge_rows = 0;        // rows per CTA the edge arrays were written with (0: written by the marching kernel)
+    // two consecutive steps (buffers a -> b -> a) captured as one CUDA graph: small boxes are launch-bound
+    // (a non-periodic level issues ~30 ghost-fill launches per step)
+    cudaGraphExec_t graph = nullptr;
+    int graph_cur = -1, graph_variant = -1;  // buffer parity and step variant the graph was captured for
+    int64_t graph_launches = 0;              // kernels per replay
     bool carry_valid = false; // `part` holds the partial sums of the current lattice buffers' next post-stream state
 };
 
@@ -77,7 +82,9 @@ struct mbl_ctx {
     int carry_own = 30, carry_ky = 32, carry_minb = 2, carry_rows = 6;  // variant 4 tuning (MBL_OWN / MBL_KY / MBL_MINB)
     int sm_count = 148;
     cudaStream_t s_up = nullptr, s_down = nullptr;  // copy streams of the pipelined mbl_step_host
+    cudaStream_t s_capture = nullptr;               // CUDA graph capture of step pairs
     int host_chunk = 16;  // planes per upload chunk (MBL_HOST_CHUNK; negative: no pipelining)
+    bool use_graphs = true;  // MBL_GRAPH=0 disables
     bool timing = false;
     std::vector<cudaEvent_t> events;  // 4 per timed record: before ghost fill, q-corr, collide, after
     int timed_steps = 0;              // steps covered by the records (a split step makes two records)
@@ -252,6 +259,7 @@ int mbl_create(const mbl_params* params, int device, mbl_ctx** out)
     if (const char* e = getenv("MBL_LAG")) c->lag_per_cta = atoi(e) > 0 ? atoi(e) : 4;
     if (const char* e = getenv("MBL_ROWS")) c->carry_rows = atoi(e);
     if (const char* e = getenv("MBL_HOST_CHUNK")) c->host_chunk = atoi(e);
+    if (const char* e = getenv("MBL_GRAPH")) c->use_graphs = atoi(e) != 0;
     if (const char* e = getenv("MBL_OWN")) c->carry_own = atoi(e) == 28 ? 28 : 30;
     if (const char* e = getenv("MBL_KY")) c->carry_ky = atoi(e) > 0 ? atoi(e) : 32;
     if (const char* e = getenv("MBL_MINB")) c->carry_minb = atoi(e) >= 2 && atoi(e) <= 5 ? atoi(e) : 2;
@@ -310,6 +318,7 @@ int mbl_level_clear(mbl_ctx* ctx, int lev)
     if (lv.d_red) cudaFree(lv.d_red);
     if (lv.macro) cudaFree(lv.macro);
     if (lv.counters) cudaFree(lv.counters);
+    if (lv.graph) cudaGraphExecDestroy(lv.graph);
     if (lv.part) cudaFree(lv.part);
     if (lv.edge) cudaFree(lv.edge);
     lv = Level();
@@ -626,7 +635,57 @@ int mbl_step(mbl_ctx* ctx, int lev, int nsteps, double time, int want_macro)
     Level& lv = ctx->lev[lev];
     if (!lv.local_z && nsteps > 1) return fail("mbl_step: nsteps > 1 needs a box that spans the domain in z");
     CU(cudaSetDevice(ctx->device));
-    for (int s = 0; s < nsteps; ++s)
+    int s = 0;
+    // Launch-bound boxes: replay pairs of steps as one CUDA graph.  The first step runs eagerly (it allocates
+    // the carry arrays and brings the level into its steady kernel sequence), the last one too if macrodata
+    // is wanted; variants 1-3 (persistent kernels with host-side plans) and timed runs are not captured.
+    const bool graphable = ctx->use_graphs && !ctx->timing && (ctx->variant == 0 || ctx->variant >= 4) &&
+                           lv.L.sq < (1LL << 24);  // ~16 M cells: beyond that launches are noise
+    const int tail = want_macro ? 1 : 0;
+    if (graphable && nsteps - tail >= 5) {
+        if (step_local(ctx, lv, time, 0)) return 1;
+        s = 1;
+        if (lv.graph && (lv.graph_cur != lv.cur || lv.graph_variant != ctx->variant)) {
+            cudaGraphExecDestroy(lv.graph);
+            lv.graph = nullptr;
+        }
+        if (!lv.graph) {
+            // capture on a stream of our own (the caller's may be the legacy default stream, which cannot be
+            // captured); the instantiated graph is launched on the caller's stream
+            if (!ctx->s_capture) CU(cudaStreamCreateWithFlags(&ctx->s_capture, cudaStreamNonBlocking));
+            cudaGraph_t g = nullptr;
+            const int64_t l0 = ctx->launches;
+            cudaStream_t user = ctx->stream;
+            ctx->stream = ctx->s_capture;
+            cudaError_t ce = cudaStreamBeginCapture(ctx->s_capture, cudaStreamCaptureModeThreadLocal);
+            int rc = 0;
+            if (ce == cudaSuccess) {
+                rc = step_local(ctx, lv, time, 0) || step_local(ctx, lv, time, 0);
+                ce = cudaStreamEndCapture(ctx->s_capture, &g);
+            }
+            ctx->stream = user;
+            const int64_t captured = ctx->launches - l0;
+            ctx->launches = l0;  // nothing ran
+            if (!rc && ce == cudaSuccess && cudaGraphInstantiate(&lv.graph, g, 0) == cudaSuccess)
+                lv.graph_launches = captured;
+            if (g) cudaGraphDestroy(g);
+            if (rc || ce != cudaSuccess || !lv.graph) {
+                // not capturable here (driver, lazy loading, ...): run eagerly from now on
+                cudaGetLastError();
+                lv.graph = nullptr;
+                ctx->use_graphs = false;
+                if (rc) return 1;
+            } else {
+                lv.graph_cur = lv.cur;  // two steps: the parity is back where the capture started
+                lv.graph_variant = ctx->variant;
+            }
+        }
+        for (; lv.graph && s + 2 <= nsteps - tail; s += 2) {
+            CU(cudaGraphLaunch(lv.graph, ctx->stream));
+            ctx->launches += lv.graph_launches;
+        }
+    }
+    for (; s < nsteps; ++s)
         if (step_local(ctx, lv, time + s * lv.P.dt, want_macro && s == nsteps - 1)) return 1;
     return 0;
 }

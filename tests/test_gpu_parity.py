@@ -410,3 +410,29 @@ def test_full_size_conservation_512():
     assert abs(sums[1][0] - sums[0][0]) <= 1e-11 * sums[0][0]
     assert abs(sums[1][1] - sums[0][1]) <= 1e-11 * sums[0][1]
     a.close()
+
+
+@pytest.mark.parametrize("case", ["chcyl", "tg12", "sod48"])
+@pytest.mark.parametrize("variant", [None, 0], ids=["default", "twopass"])
+def test_graph_replay_is_bit_identical(case, variant):
+    """mbl_step replays pairs of steps as one CUDA graph on small boxes: same kernels, same order"""
+    import os
+    z, deck_text, _ = load_golden(case)
+    fl = z["is_fluid"].astype(np.int32)
+    os.environ["MBL_GRAPH"] = "0"
+    try:
+        a = new_lbm(deck_text, fl, variant=variant)
+    finally:
+        os.environ.pop("MBL_GRAPH", None)
+    b = new_lbm(deck_text, fl, variant=variant)
+    for n in (8, 5, 1, 7):
+        a.step(n)
+        b.step(n)
+    a.step(6, want_macrodata=True)
+    b.step(6, want_macrodata=True)
+    assert np.isfinite(a.get_f()).all()
+    assert np.array_equal(a.get_f(), b.get_f()) and np.array_equal(a.get_g(), b.get_g())
+    assert np.array_equal(a.get_macrodata(), b.get_macrodata())
+    assert a.launches == b.launches
+    a.close()
+    b.close()
