@@ -175,8 +175,10 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "MLUPS (D3Q27 f+g, fp64)", "value": mlups, "unit": "MLUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"periodic Taylor-Green box, single level, CPU sample {size}^3 of the "
-                               f"{args.size}^3-per-GPU workload"},
+        "config": {"workload": f"periodic Taylor-Green box {args.size}^3 per GPU, single level, D3Q27 f+g fp64 "
+                               f"(BASELINE config 3; domain {args.size}x{args.size}x{args.size * args.gpus})",
+                   "sample": f"each step = the same deck at {size}^3 on the host cores (the reference's CPU build "
+                             f"needs ~190 words per cell; CPU MLUPS is size-independent to first order)"},
         "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": vals[0][2], "kind": "reference", "sample": sample},
         "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
