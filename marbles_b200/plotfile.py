@@ -200,3 +200,131 @@ def eb_boundary(is_fluid_grown: np.ndarray, ng: int) -> np.ndarray:
         any_fluid |= a[sl(dz, nz), sl(dy, ny), sl(dxx, nx)] == 1
     out[(c == 0) & any_fluid] = 1
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Checkpoints (LBM::write_checkpoint_file / read_checkpoint_file, Source/LBM.cpp:1692-1915): a text Header and
+# the two lattices as VisMF files WITH their ghost cells, `chkNNNNN/Level_0/f_00_{H,D_00000}` and `g_00_...`.
+# A checkpoint written here restarts the unmodified reference (amr.restart=...), and the reference's checkpoints
+# load into `LBM` (tests/test_checkpoint.py runs both directions against the reference executable).
+# ---------------------------------------------------------------------------------------------------------
+def _grown(lo, hi, ng):
+    return tuple(v - ng for v in lo), tuple(v + ng for v in hi)
+
+
+def write_vismf(lev_dir: str, prefix: str, data: np.ndarray, ng: int, boxes) -> None:
+    """VisMF::Write of one MultiFab: data is [ncomp, nz+2ng, ny+2ng, nx+2ng] over the domain grown by ng; every
+    FAB goes out with its own ghost cells (taken from the grown array), minima / maxima over the valid box."""
+    ncomp = data.shape[0]
+    os.makedirs(lev_dir, exist_ok=True)
+    dname = f"{prefix}_D_00000"
+    offsets, mins, maxs = [], [], []
+    with open(os.path.join(lev_dir, dname), "wb") as fh:
+        for lo, hi in boxes:
+            offsets.append(fh.tell())
+            glo, ghi = _grown(lo, hi, ng)
+            sub = np.ascontiguousarray(data[:, lo[2]:hi[2] + 1 + 2 * ng, lo[1]:hi[1] + 1 + 2 * ng, lo[0]:hi[0] + 1 + 2 * ng])
+            fh.write(f"{FAB_HEADER}{_box(glo, ghi)} {ncomp}\n".encode())
+            fh.write(sub.astype("<f8").tobytes())
+            val = sub[:, ng:sub.shape[1] - ng, ng:sub.shape[2] - ng, ng:sub.shape[3] - ng] if ng else sub
+            flat = val.reshape(ncomp, -1)
+            mins.append(flat.min(axis=1))
+            maxs.append(flat.max(axis=1))
+    with open(os.path.join(lev_dir, f"{prefix}_H"), "w") as fh:
+        fh.write(f"1\n1\n{ncomp}\n{ng}\n")
+        fh.write(f"({len(boxes)} 0\n")
+        for lo, hi in boxes:
+            fh.write(_box(lo, hi) + "\n")
+        fh.write(")\n")
+        fh.write(f"{len(boxes)}\n")
+        for off in offsets:
+            fh.write(f"FabOnDisk: {dname} {off}\n")
+        fh.write("\n")
+        for table in (mins, maxs):
+            fh.write(f"{len(boxes)},{ncomp}\n")
+            for row in table:
+                fh.write("".join("%.17e," % v for v in row) + "\n")
+            fh.write("\n")
+
+
+def read_vismf(lev_dir: str, prefix: str):
+    """-> (data [ncomp, nz+2ng, ny+2ng, nx+2ng] over the bounding box of all FABs grown by ng, ng, boxes).
+    Cells covered by several FABs (ghost overlap) take the VALID cell's value."""
+    import re
+    with open(os.path.join(lev_dir, f"{prefix}_H")) as fh:
+        ch = fh.read().split("\n")
+    ncomp, ng = int(ch[2]), int(ch[3].split()[0].strip("(),"))
+    i = next(k for k, l in enumerate(ch) if l.startswith("(") and k >= 4)
+    nbox = int(ch[i].strip("(").split()[0])
+    boxes = []
+    for b in range(nbox):
+        m = [int(v) for v in re.findall(r"-?\d+", ch[i + 1 + b])]
+        boxes.append((tuple(m[0:3]), tuple(m[3:6])))
+    j = next(k for k, l in enumerate(ch) if l.startswith("FabOnDisk"))
+    dlo = [min(b[0][d] for b in boxes) for d in range(3)]
+    dhi = [max(b[1][d] for b in boxes) for d in range(3)]
+    n = [dhi[d] - dlo[d] + 1 for d in range(3)]
+    data = np.zeros((ncomp, n[2] + 2 * ng, n[1] + 2 * ng, n[0] + 2 * ng))
+    fabs = []
+    for b, (lo, hi) in enumerate(boxes):
+        _, fname, off = ch[j + b].split()
+        bn = [hi[d] - lo[d] + 1 + 2 * ng for d in range(3)]
+        with open(os.path.join(lev_dir, fname), "rb") as fh:
+            fh.seek(int(off))
+            fh.readline()
+            arr = np.frombuffer(fh.read(8 * ncomp * bn[0] * bn[1] * bn[2]), dtype="<f8").reshape(ncomp, bn[2], bn[1], bn[0])
+        fabs.append(arr)
+        o = [lo[d] - dlo[d] for d in range(3)]
+        data[:, o[2]:o[2] + bn[2], o[1]:o[1] + bn[1], o[0]:o[0] + bn[0]] = arr
+    for (lo, hi), arr in zip(boxes, fabs):  # valid cells win over other FABs' ghost copies
+        o = [lo[d] - dlo[d] + ng for d in range(3)]
+        bn = [hi[d] - lo[d] + 1 for d in range(3)]
+        data[:, o[2]:o[2] + bn[2], o[1]:o[1] + bn[1], o[0]:o[0] + bn[0]] = \
+            arr[:, ng:ng + bn[2], ng:ng + bn[1], ng:ng + bn[0]]
+    return data, ng, boxes
+
+
+def chk_file_name(prefix: str, step: int) -> str:
+    return f"{prefix}{step:05d}"
+
+
+def write_checkpoint(path: str, f: np.ndarray, g: np.ndarray, *, step: int, dt: float, time: float, periodic,
+                     max_grid_size: int = 32, ng: int = 3) -> None:
+    """f, g: [27, nz, ny, nx] valid cells.  Ghost cells of the files hold the periodic images in periodic
+    directions and the nearest valid cell elsewhere; the reference refills every ghost cell after a restart
+    (FillBoundary in read_checkpoint_file, fillpatch at the start of each step)."""
+    n = (f.shape[3], f.shape[2], f.shape[1])
+    boxes = chop_boxes(n, max_grid_size)
+
+    def grow(a):
+        for axis, d in ((3, 0), (2, 1), (1, 2)):
+            pad = [(0, 0)] * 4
+            pad[axis] = (ng, ng)
+            a = np.pad(a, pad, mode="wrap" if periodic[d] else "edge")
+        return a
+
+    os.makedirs(path, exist_ok=True)
+    with open(os.path.join(path, "Header"), "w") as fh:
+        fh.write("Checkpoint file for LBM\n0\n")
+        fh.write(f"{step} \n{_g17(dt)} \n{_g17(time)} \n")
+        fh.write(f"({len(boxes)} 0\n")
+        for lo, hi in boxes:
+            fh.write(_box(lo, hi) + "\n")
+        fh.write(")\n")
+    lev_dir = os.path.join(path, "Level_0")
+    write_vismf(lev_dir, "f_00", grow(np.asarray(f, dtype=np.float64)), ng, boxes)
+    write_vismf(lev_dir, "g_00", grow(np.asarray(g, dtype=np.float64)), ng, boxes)
+
+
+def read_checkpoint(path: str) -> dict:
+    """-> {"step", "dt", "time", "f", "g"} with f, g the valid cells [27, nz, ny, nx] of level 0"""
+    with open(os.path.join(path, "Header")) as fh:
+        lines = fh.read().split("\n")
+    if int(lines[1]) != 0:
+        raise ValueError("only single-level checkpoints are supported")
+    out = {"step": int(lines[2].split()[0]), "dt": float(lines[3].split()[0]), "time": float(lines[4].split()[0])}
+    for name in ("f", "g"):
+        data, ng, _ = read_vismf(os.path.join(path, "Level_0"), f"{name}_00")
+        out[name] = np.ascontiguousarray(data[:, ng:data.shape[1] - ng, ng:data.shape[2] - ng, ng:data.shape[3] - ng]
+                                         if ng else data)
+    return out
