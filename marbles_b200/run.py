@@ -1,0 +1,96 @@
+"""`python -m marbles_b200.run deck.inp [key=value ...]` -- the reference's `main` / `LBM::evolve` loop
+(Source/main.cpp:10-25, Source/LBM.cpp:155-195, 398-448) for single-level decks, with the lattice update on the
+GPU: same input deck format, same plotfile / checkpoint names, formats and cadence (amr.plot_int, amr.chk_int,
+amr.restart, max_step, stop_time), so a deck that runs under the reference executable runs here unchanged.
+
+This is the thin caller either side of the hot path, not a re-implementation of the
+reference's AMR driver: amr.max_level > 0 is refused."""
+from __future__ import annotations
+
+import os
+import sys
+
+from .inputs import parse_deck
+from .lbm import LBM, MarblesError
+from .plotfile import write_lbm_plotfile
+
+
+def _get(deck: dict, key: str, default, cast=str):
+    v = deck.get(key, None)
+    if v is None:
+        return default
+    if isinstance(v, (list, tuple)):
+        v = v[0]
+    return cast(str(v).strip('"'))
+
+
+def evolve(lbm: LBM, out_dir: str = ".", log=print) -> list[str]:
+    """LBM::init_data's output + LBM::evolve.  Returns the paths written."""
+    deck = lbm.inp.deck
+    max_step = _get(deck, "max_step", 2 ** 31 - 1, int)
+    stop_time = _get(deck, "stop_time", float("inf"), float)
+    plot_file, plot_int = _get(deck, "amr.plot_file", "plt"), _get(deck, "amr.plot_int", -1, int)
+    chk_file, chk_int = _get(deck, "amr.chk_file", "chk"), _get(deck, "amr.chk_int", -1, int)
+    restart = _get(deck, "amr.restart", "")
+    if _get(deck, "amr.max_level", 0, int) > 0:
+        raise MarblesError("marbles_b200.run drives single-level decks (amr.max_level = 0)")
+    written = []
+
+    def plot():
+        written.append(write_lbm_plotfile(lbm, out_dir, plot_file))
+        log(f"Writing plot file {written[-1]} at time {lbm.time}")
+
+    def chk():
+        written.append(lbm.write_checkpoint_file(out_dir, chk_file))
+        log(f"Writing checkpoint file {written[-1]} at time {lbm.time}")
+
+    if restart:
+        lbm.read_checkpoint_file(restart if os.path.isabs(restart) else os.path.join(out_dir, restart))
+        log(f"Restarting from checkpoint file {restart}")
+    else:
+        lbm.init_data()
+        if chk_int > 0:
+            chk()
+    if plot_int > 0:
+        lbm.f_to_macrodata()  # the state as initialised / read: macrodata without a step
+        plot()
+    last_plot = 0
+    while lbm.isteps < max_step and lbm.time < stop_time:
+        # run to the next step at which something is written
+        nxt = max_step
+        for every in (plot_int, chk_int):
+            if every > 0:
+                nxt = min(nxt, (lbm.isteps // every + 1) * every)
+        if stop_time < float("inf"):
+            nxt = min(nxt, lbm.isteps + max(1, int((stop_time - lbm.time) / lbm.dt + 1e-6)))
+        n = nxt - lbm.isteps
+        want_plot = plot_int > 0 and nxt % plot_int == 0
+        lbm.step(n, want_macrodata=want_plot or nxt >= max_step)
+        if want_plot:
+            last_plot = lbm.isteps
+            plot()
+        if chk_int > 0 and lbm.isteps % chk_int == 0:
+            chk()
+        if lbm.time >= stop_time - 1.0e-6 * lbm.dt:
+            break
+    if plot_int > 0 and lbm.isteps > last_plot:
+        plot()
+    return written
+
+
+def main(argv=None) -> int:
+    argv = sys.argv[1:] if argv is None else argv
+    if not argv:
+        print(__doc__)
+        return 2
+    deck = parse_deck(argv[0], overrides=argv[1:])
+    lbm = LBM(deck)
+    try:
+        evolve(lbm)
+    finally:
+        lbm.close()
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
