@@ -57,6 +57,7 @@ struct Level {
     int* counters = nullptr;  // fused kernel: ticket + per-slab completion counters
     double* part = nullptr;   // carry step: 12 partial-sum words per cell (lazily allocated)
     double* edge = nullptr;   // tile carry step: 18 words per CTA row
+    bool dq_from_macro = false;  // macrodata came from mbl_f_to_macrodata: compute_derived also differences QCorr
     int edge_rows = 0;        // rows per CTA the edge arrays were written with (0: written by the marching kernel)
     // two consecutive steps (buffers a -> b -> a) captured as one CUDA graph: small boxes are launch-bound
     // (a non-periodic level issues ~30 ghost-fill launches per step)
@@ -140,6 +141,7 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
 {
     cudaStream_t st = ctx->stream;
     if (want_macro && ensure_macro(lv, st, ctx->launches)) return 1;
+    if (want_macro) lv.dq_from_macro = false;  // the collide kernel stores the differenced q-corrections itself
     const int a = lv.cur, b = 1 - lv.cur;
     auto mark = [&]() {
         if (!ctx->timing) return;
@@ -578,6 +580,7 @@ int mbl_collide(mbl_ctx* ctx, int lev, int want_macro)
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     if (want_macro && ensure_macro(lv, st, ctx->launches)) return 1;
+    if (want_macro) lv.dq_from_macro = false;
     double *f = curf(lv), *g = curg(lv);
     ctx->launches += launch_qcorr(lv.L, lv.P, f, g, lv.p.nbr, lv.p.qc, false, st);
     ctx->launches += launch_collide(lv.L, lv.P, f, g, f, g, lv.p.nbr, lv.p.flag, lv.p.qc,
@@ -593,6 +596,7 @@ int mbl_f_to_macrodata(mbl_ctx* ctx, int lev)
     CU(cudaSetDevice(ctx->device));
     if (ensure_macro(lv, ctx->stream, ctx->launches)) return 1;
     ctx->launches += launch_macrodata(lv.L, lv.P, curf(lv), curg(lv), lv.p.flag, lv.macro, ctx->stream);
+    lv.dq_from_macro = true;
     CU(cudaGetLastError());
     return 0;
 }
@@ -603,7 +607,8 @@ int mbl_compute_derived(mbl_ctx* ctx, int lev)
     Level& lv = ctx->lev[lev];
     if (!lv.macro) return fail("mbl_compute_derived needs macrodata");
     CU(cudaSetDevice(ctx->device));
-    ctx->launches += launch_derived(lv.L, lv.P, lv.p.flag, lv.macro, lv.macro + (size_t)MBL_NMACRO * lv.L.sq, ctx->stream);
+    ctx->launches += launch_derived(lv.L, lv.P, lv.p.flag, lv.macro, lv.macro + (size_t)MBL_NMACRO * lv.L.sq, ctx->stream,
+                                    lv.dq_from_macro ? 1 : 0);
     CU(cudaGetLastError());
     return 0;
 }

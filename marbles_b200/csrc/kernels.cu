@@ -978,7 +978,7 @@ __global__ void __launch_bounds__(128) k_macrodata(const double* __restrict__ f,
 // Needs macrodata of the face neighbours inside the domain (valid cells of this box; the
 // z-neighbours across a rank boundary are treated as unusable -- plot-only quantity).
 __global__ void __launch_bounds__(128) k_derived(const uint8_t* __restrict__ flag, const double* __restrict__ macro,
-                                                 double* __restrict__ derived, Layout L, Phys P)
+                                                 double* __restrict__ derived, Layout L, Phys P, int with_dq)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
@@ -1006,6 +1006,13 @@ __global__ void __launch_bounds__(128) k_derived(const uint8_t* __restrict__ fla
     derived[1 * n + c] = uz - wx;
     derived[2 * n + c] = vx - uy;
     derived[3 * n + c] = sqrt((wy - vz) * (wy - vz) + (uz - wx) * (uz - wx) + (vx - uy) * (vx - uy));
+    if (with_dq) {
+        // compute_q_corrections (LBM.cpp:959-991) from the stored QCorr: only when no collide has produced them
+        // (macrodata of an initial or restarted state, LBM.cpp:1196-1198, 1903-1914)
+        derived[4 * n + c] = grad(0, 6);
+        derived[5 * n + c] = grad(1, 7);
+        derived[6 * n + c] = grad(2, 8);
+    }
 }
 
 // compute_eb_forces (LBM.cpp:994-1044), single level: momentum exchange over solid cells that
@@ -1744,10 +1751,10 @@ int launch_macrodata(const Layout& L, const Phys& P, const double* f, const doub
 }
 
 int launch_derived(const Layout& L, const Phys& P, const uint8_t* flag, const double* macro, double* derived,
-                   cudaStream_t st)
+                   cudaStream_t st, int with_dq)
 {
     const int bx = block_x(L);
-    k_derived<<<grid3(L, bx), bx, 0, st>>>(flag, macro, derived, L, P);
+    k_derived<<<grid3(L, bx), bx, 0, st>>>(flag, macro, derived, L, P, with_dq);
     return 1;
 }
 

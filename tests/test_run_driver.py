@@ -33,7 +33,7 @@ def test_deck_runs_like_the_reference(tmp_path, case, extra):
     names = sorted(os.path.basename(p) for p in written)
     ref_names = sorted(d for d in os.listdir(ref_dir) if d.startswith(("plt", "chk")))
     assert names == ref_names == ["chk00000", "chk00004", "chk00008", "plt00000", "plt00004", "plt00008"]
-    for step in (4, 8):
+    for step in (0, 4, 8):
         ref = O.read_plotfile(os.path.join(ref_dir, f"plt{step:05d}"))
         got = O.read_plotfile(os.path.join(my_dir, f"plt{step:05d}"))
         assert got["__names__"] == ref["__names__"] and got["__time__"] == ref["__time__"]
