@@ -35,6 +35,18 @@ def evolve(lbm: LBM, out_dir: str = ".", log=print) -> list[str]:
     if _get(deck, "amr.max_level", 0, int) > 0:
         raise MarblesError("marbles_b200.run drives single-level decks (amr.max_level = 0)")
     written = []
+    # lbm.compute_forces: one line of EB forces per step (open_forces_file / output_forces_file,
+    # Source/LBM.cpp:1925-1969: width 24, 16 significant digits); forces every step means stepping one at a time
+    forces_path = None
+    if _get(deck, "lbm.compute_forces", 0, int):
+        forces_path = os.path.join(out_dir, _get(deck, "lbm.forces_file", "forces.txt"))
+
+    def forces_line():
+        if forces_path is None:
+            return
+        f3 = lbm.compute_eb_forces()
+        with open(forces_path, "a") as fh:
+            fh.write("".join("%24s" % ("%.16g" % v) for v in (lbm.time, f3[0], f3[1], f3[2])) + "\n")
 
     def plot():
         written.append(write_lbm_plotfile(lbm, out_dir, plot_file))
@@ -47,10 +59,15 @@ def evolve(lbm: LBM, out_dir: str = ".", log=print) -> list[str]:
     if restart:
         lbm.read_checkpoint_file(restart if os.path.isabs(restart) else os.path.join(out_dir, restart))
         log(f"Restarting from checkpoint file {restart}")
+        if forces_path is not None and not os.path.exists(forces_path):
+            open(forces_path, "w").write("".join("%24s" % h for h in ("time", "fx", "fy", "fz")) + "\n")
     else:
         lbm.init_data()
         if chk_int > 0:
             chk()
+        if forces_path is not None:
+            open(forces_path, "w").write("".join("%24s" % h for h in ("time", "fx", "fy", "fz")) + "\n")
+            forces_line()
     if plot_int > 0:
         lbm.f_to_macrodata()  # the state as initialised / read: macrodata without a step
         plot()
@@ -65,7 +82,12 @@ def evolve(lbm: LBM, out_dir: str = ".", log=print) -> list[str]:
             nxt = min(nxt, lbm.isteps + max(1, int((stop_time - lbm.time) / lbm.dt + 1e-6)))
         n = nxt - lbm.isteps
         want_plot = plot_int > 0 and nxt % plot_int == 0
-        lbm.step(n, want_macrodata=want_plot or nxt >= max_step)
+        if forces_path is None:
+            lbm.step(n, want_macrodata=want_plot or nxt >= max_step)
+        else:
+            for s in range(n):
+                lbm.step(1, want_macrodata=(s == n - 1) and (want_plot or nxt >= max_step))
+                forces_line()
         if want_plot:
             last_plot = lbm.isteps
             plot()

@@ -53,3 +53,33 @@ def test_deck_runs_like_the_reference(tmp_path, case, extra):
         mb = open(os.path.join(my_dir, "plt00008", name)).read().split("\n")
         assert len(ra) == len(mb)
     lbm.close()
+
+
+def test_forces_file_matches_reference(tmp_path):
+    """lbm.compute_forces = 1: one line of EB forces per step, same layout as the reference's forces file"""
+    from oracle import oracle as O
+    from marbles_b200.inputs import parse_deck
+    from marbles_b200.lbm import LBM
+    from marbles_b200.run import evolve
+    if not os.path.exists(O.REF_SERIAL):
+        pytest.skip("reference executable not built")
+    z = np.load(os.path.join(HERE, "golden", "chcyl.npz"))
+    ov = ["max_step=6", "amr.plot_int=-1", "amr.chk_int=-1", "lbm.compute_forces=1", "lbm.forces_file=forces.txt"]
+    ref_dir, my_dir = str(tmp_path / "ref"), str(tmp_path / "mine")
+    os.makedirs(ref_dir), os.makedirs(my_dir)
+    deck_path = os.path.join(ref_dir, "deck.inp")
+    with open(deck_path, "w") as fh:
+        fh.write(str(z["deck"]))
+    subprocess.run([O.REF_SERIAL, "deck.inp"] + ov, cwd=ref_dir, check=True, capture_output=True)
+    lbm = LBM(parse_deck(deck_path, overrides=ov))
+    evolve(lbm, my_dir, log=lambda s: None)
+    lbm.close()
+    ref = open(os.path.join(ref_dir, "forces.txt")).read().split("\n")
+    got = open(os.path.join(my_dir, "forces.txt")).read().split("\n")
+    assert got[0] == ref[0] and len(got) == len(ref) == 9  # header, step 0 .. 6, trailing newline
+    a = np.array([[float(v) for v in l.split()] for l in ref[1:-1]])
+    b = np.array([[float(v) for v in l.split()] for l in got[1:-1]])
+    assert all(len(l) == 96 for l in got[1:-1])
+    assert np.array_equal(a[:, 0], b[:, 0])
+    assert np.abs(a[:, 1:] - b[:, 1:]).max() <= 1e-11 * max(np.abs(a[:, 1:]).max(), 1e-300)
+    print("forces: worst relative difference", np.abs(a[:, 1:] - b[:, 1:]).max() / np.abs(a[:, 1:]).max())
