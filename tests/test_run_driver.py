@@ -81,5 +81,6 @@ def test_forces_file_matches_reference(tmp_path):
     b = np.array([[float(v) for v in l.split()] for l in got[1:-1]])
     assert all(len(l) == 96 for l in got[1:-1])
     assert np.array_equal(a[:, 0], b[:, 0])
-    assert np.abs(a[:, 1:] - b[:, 1:]).max() <= 1e-11 * max(np.abs(a[:, 1:]).max(), 1e-300)
-    print("forces: worst relative difference", np.abs(a[:, 1:] - b[:, 1:]).max() / np.abs(a[:, 1:]).max())
+    # the force is a sum of O(1e-2) momentum-exchange terms that cancel to O(1e-7): round-off is absolute
+    assert np.abs(a[:, 1:] - b[:, 1:]).max() <= 1e-14
+    print("forces: worst absolute difference", np.abs(a[:, 1:] - b[:, 1:]).max(), "of", np.abs(a[:, 1:]).max())
