@@ -436,3 +436,22 @@ def test_graph_replay_is_bit_identical(case, variant):
     assert a.launches == b.launches
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("case,n_cell", [("tg12", "67 45 13"), ("tg12", "31 7 9"), ("sod48", "75 3 5"), ("sod48", "130 2 2")])
+@pytest.mark.parametrize("variant", [None, 0, "carry"], ids=["default-tile", "twopass", "carry"])
+def test_odd_box_sizes_vs_oracle(oracle_mod, case, n_cell, variant):
+    """box sizes that are no multiple of the warp strip (30 cells), the CTA height (6 rows) or the march length"""
+    O = oracle_mod
+    z, deck_text, _ = load_golden(case)
+    ov = [f"amr.n_cell = {n_cell}"]
+    o = O.Oracle(O.lbm_setup(O.parse_deck(None, deck_text.splitlines() + ov)))
+    o.initialize()
+    lbm = new_lbm(deck_text, overrides=ov, variant=variant)
+    o.step(5)
+    lbm.step(5, want_macrodata=True)
+    ref = o.fields()
+    sc = scales(ref, lbm.inp.R, lbm.inp.gamma, 1.0 / lbm.inp.dx[0])
+    worst, key = compare(lbm.fields(), ref, sc, 5)
+    print(f"{case} {n_cell}: worst {worst:.2e} ({key})")
+    lbm.close()
