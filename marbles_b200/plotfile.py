@@ -150,8 +150,10 @@ def plot_file_name(prefix: str, step: int) -> str:
 
 def write_lbm_plotfile(lbm, directory: str = ".", prefix: str = "plt", max_grid_size: int | None = None,
                        save_streaming: bool | None = None, save_derived: bool | None = None) -> str:
-    """LBM::write_plot_file for a single-rank `marbles_b200.lbm.LBM`: the macrodata must be current (last step
-    taken with want_macrodata=True, as the reference's post_time_step leaves it)."""
+    """LBM::write_plot_file: the macrodata must be current (last step taken with want_macrodata=True, as the
+    reference's post_time_step leaves it).  On several ranks every rank writes the FABs of its z-slab and rank 0 the
+    headers (collective call); the vorticity of the two planes next to another rank's slab is then differenced
+    one-sided in z."""
     deck = lbm.inp.deck
 
     def deck_int(key: str, default: int) -> int:
@@ -166,8 +168,6 @@ def write_lbm_plotfile(lbm, directory: str = ".", prefix: str = "plt", max_grid_
         save_derived = bool(deck_int("lbm.save_derived", 1))
     if max_grid_size is None:
         max_grid_size = deck_int("amr.max_grid_size", 32)
-    if lbm.world != 1:
-        raise ValueError("write_lbm_plotfile writes the whole level from one rank")
     names = plot_file_var_names(save_streaming, save_derived)
     parts = [lbm.get_macrodata()]
     if save_streaming:
@@ -180,8 +180,20 @@ def write_lbm_plotfile(lbm, directory: str = ".", prefix: str = "plt", max_grid_
     parts.append(np.stack([fl.astype(np.float64), eb_boundary(lbm._is_fluid, ng).astype(np.float64)]))
     data = np.concatenate(parts, axis=0)
     path = os.path.join(directory, plot_file_name(prefix, lbm.isteps))
-    write_plotfile(path, names, data, time=lbm.time, step=lbm.isteps, prob_lo=lbm.inp.prob_lo, prob_hi=lbm.inp.prob_hi,
-                   max_grid_size=max_grid_size)
+    if lbm.world == 1:
+        write_plotfile(path, names, data, time=lbm.time, step=lbm.isteps, prob_lo=lbm.inp.prob_lo,
+                       prob_hi=lbm.inp.prob_hi, max_grid_size=max_grid_size)
+    else:  # one z-slab per rank: every rank writes its own FABs, rank 0 the two headers
+        import torch.distributed as dist
+
+        def gather(obj):
+            out = [None] * lbm.world
+            dist.all_gather_object(out, obj)
+            return out
+
+        write_plotfile_slabs(path, names, data, zlo=lbm.lo[2], nz_total=lbm.inp.n_cell[2], rank=lbm.rank, gather=gather,
+                             time=lbm.time, step=lbm.isteps, prob_lo=lbm.inp.prob_lo, prob_hi=lbm.inp.prob_hi,
+                             max_grid_size=max_grid_size)
     return path
 
 
@@ -328,3 +340,75 @@ def read_checkpoint(path: str) -> dict:
         out[name] = np.ascontiguousarray(data[:, ng:data.shape[1] - ng, ng:data.shape[2] - ng, ng:data.shape[3] - ng]
                                          if ng else data)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Multi-rank plotfiles: every rank writes the FABs of its own z-slab into Level_0/Cell_D_<rank>, rank 0 writes
+# Header and Cell_H from the gathered box lists, offsets and extrema -- the layout VisMF uses when every rank
+# owns a file (AMReX_VisMF.cpp).  `gather(obj) -> [obj of rank 0, obj of rank 1, ...]` is the only communication
+# (torch.distributed.all_gather_object in marbles_b200.lbm; any callable in tests).
+# ---------------------------------------------------------------------------------------------------------
+def write_plotfile_slabs(path: str, names: list[str], data_local: np.ndarray, *, zlo: int, nz_total: int, rank: int,
+                         gather, time: float, step: int, prob_lo, prob_hi, max_grid_size: int = 32) -> None:
+    """data_local: [ncomp, nz_local, ny, nx] of this rank's slab, whose first plane is global plane zlo."""
+    data_local = np.asarray(data_local, dtype=np.float64)
+    ncomp, nzl, ny, nx = data_local.shape
+    lev_dir = os.path.join(path, "Level_0")
+    os.makedirs(lev_dir, exist_ok=True)
+    dname = f"Cell_D_{rank:05d}"
+    boxes, offsets, mins, maxs = [], [], [], []
+    with open(os.path.join(lev_dir, dname), "wb") as fh:
+        for lo, hi in chop_boxes((nx, ny, nzl), max_grid_size):
+            glo, ghi = (lo[0], lo[1], lo[2] + zlo), (hi[0], hi[1], hi[2] + zlo)
+            offsets.append(fh.tell())
+            sub = np.ascontiguousarray(data_local[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1])
+            fh.write(f"{FAB_HEADER}{_box(glo, ghi)} {ncomp}\n".encode())
+            fh.write(sub.astype("<f8").tobytes())
+            flat = sub.reshape(ncomp, -1)
+            boxes.append((glo, ghi))
+            mins.append(flat.min(axis=1).tolist())
+            maxs.append(flat.max(axis=1).tolist())
+    parts = gather({"file": dname, "boxes": boxes, "offsets": offsets, "mins": mins, "maxs": maxs})
+    if rank != 0:
+        return
+    all_boxes = [b for p in parts for b in p["boxes"]]
+    n = (nx, ny, nz_total)
+    dx = [(float(prob_hi[d]) - float(prob_lo[d])) / n[d] for d in range(3)]
+    with open(os.path.join(lev_dir, "Cell_H"), "w") as fh:
+        fh.write(f"1\n1\n{ncomp}\n0\n")
+        fh.write(f"({len(all_boxes)} 0\n")
+        for lo, hi in all_boxes:
+            fh.write(_box(lo, hi) + "\n")
+        fh.write(")\n")
+        fh.write(f"{len(all_boxes)}\n")
+        for p in parts:
+            for off in p["offsets"]:
+                fh.write(f"FabOnDisk: {p['file']} {off}\n")
+        fh.write("\n")
+        for key in ("mins", "maxs"):
+            fh.write(f"{len(all_boxes)},{ncomp}\n")
+            for p in parts:
+                for row in p[key]:
+                    fh.write("".join("%.17e," % v for v in row) + "\n")
+            fh.write("\n")
+    with open(os.path.join(path, "Header"), "w") as fh:
+        fh.write("HyperCLaw-V1.1\n")
+        fh.write(f"{ncomp}\n")
+        for nm in names:
+            fh.write(nm + "\n")
+        fh.write("3\n")
+        fh.write(_g17(time) + "\n")
+        fh.write("0\n")
+        fh.write(" ".join(_g17(v) for v in prob_lo) + " \n")
+        fh.write(" ".join(_g17(v) for v in prob_hi) + " \n")
+        fh.write("\n")
+        fh.write(_box((0, 0, 0), (nx - 1, ny - 1, nz_total - 1)) + " \n")
+        fh.write(f"{step} \n")
+        fh.write(" ".join(_g17(v) for v in dx) + " \n")
+        fh.write("0\n0\n")
+        fh.write(f"0 {len(all_boxes)} {_g17(time)}\n")
+        fh.write(f"{step}\n")
+        for lo, hi in all_boxes:
+            for d in range(3):
+                fh.write(f"{_g17(prob_lo[d] + lo[d] * dx[d])} {_g17(prob_lo[d] + (hi[d] + 1) * dx[d])}\n")
+        fh.write("Level_0/Cell\n")

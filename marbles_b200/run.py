@@ -34,6 +34,8 @@ def evolve(lbm: LBM, out_dir: str = ".", log=print) -> list[str]:
     restart = _get(deck, "amr.restart", "")
     if _get(deck, "amr.max_level", 0, int) > 0:
         raise MarblesError("marbles_b200.run drives single-level decks (amr.max_level = 0)")
+    if lbm.world > 1 and (chk_int > 0 or restart):
+        raise MarblesError("checkpoints are written and read by single-rank runs (amr.chk_int = -1 on several GPUs)")
     written = []
     # lbm.compute_forces: one line of EB forces per step (open_forces_file / output_forces_file,
     # Source/LBM.cpp:1925-1969: width 24, 16 significant digits); forces every step means stepping one at a time
@@ -106,11 +108,29 @@ def main(argv=None) -> int:
         print(__doc__)
         return 2
     deck = parse_deck(argv[0], overrides=argv[1:])
-    lbm = LBM(deck)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # one process per GPU (torchrun): z-slabs, ghost planes over NCCL; every rank writes its part of a plotfile
+        import torch
+        import torch.distributed as dist
+
+        from .inputs import lbm_inputs
+        from .parallel import HaloComm
+        rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        dist.init_process_group("nccl", device_id=dev)
+        comm = HaloComm(rank, world, bool(lbm_inputs(deck).periodic[2]), dev)
+        lbm = LBM(deck, device=local, rank=rank, world=world, comm=comm)
+        log = print if rank == 0 else (lambda s: None)
+    else:
+        lbm, log = LBM(deck), print
     try:
-        evolve(lbm)
+        evolve(lbm, log=log)
     finally:
         lbm.close()
+        if world > 1:
+            dist.destroy_process_group()
     return 0
 
 

@@ -114,3 +114,41 @@ def test_slab_bounds_and_neighbours():
     assert neighbours(0, 2, True) == (1, 1)
     assert neighbours(0, 4, False) == (None, 1) and neighbours(3, 4, False) == (2, None)
     assert neighbours(0, 1, True) == (0, 0)
+
+
+def _plot_worker(rank, world, initfile, outdir):
+    sys.path.insert(0, ROOT)
+    from marbles_b200.lbm import slab_bounds
+    from marbles_b200.plotfile import write_plotfile_slabs
+    dist.init_process_group("gloo", init_method=f"file://{initfile}", rank=rank, world_size=world)
+    full = np.load(os.path.join(outdir, "full.npy"))
+    nz = full.shape[1]
+    zlo, zhi = slab_bounds(nz, rank, world)
+
+    def gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    write_plotfile_slabs(os.path.join(outdir, "plt00007"), ["a", "b", "c"], full[:, zlo:zhi + 1], zlo=zlo, nz_total=nz,
+                         rank=rank, gather=gather, time=7.0, step=7, prob_lo=[0, 0, 0], prob_hi=[1, 1, 1], max_grid_size=8)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape,world", [((3, 20, 12, 10), 2), ((3, 13, 6, 18), 3)])
+def test_multirank_plotfile_round_trip(oracle_mod, shape, world):
+    """every rank writes the FABs of its slab (Cell_D_<rank>), rank 0 the headers: the oracle's plotfile reader
+    must see the full array"""
+    rng = np.random.default_rng(3)
+    full = rng.standard_normal(shape)
+    with tempfile.TemporaryDirectory() as tmp:
+        np.save(os.path.join(tmp, "full.npy"), full)
+        initfile = os.path.join(tmp, "init")
+        mp.spawn(_plot_worker, args=(world, initfile, tmp), nprocs=world, join=True)
+        pf = oracle_mod.read_plotfile(os.path.join(tmp, "plt00007"))
+        assert sorted(os.listdir(os.path.join(tmp, "plt00007", "Level_0"))) == \
+            sorted(["Cell_H"] + [f"Cell_D_{r:05d}" for r in range(world)])
+        assert pf["__names__"] == ["a", "b", "c"] and pf["__time__"] == 7.0
+        for c, name in enumerate(pf["__names__"]):
+            assert np.array_equal(pf[name], full[c])
