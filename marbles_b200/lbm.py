@@ -349,21 +349,31 @@ class LBM:
         """LBM::write_checkpoint_file (Source/LBM.cpp:1692-1783): `<prefix><step:05d>` with Header, f_00 and g_00
         VisMF files (3 ghost cells); the unmodified reference restarts from it (amr.restart)."""
         from . import plotfile as P
-        if self.world != 1:
-            raise MarblesError("write_checkpoint_file writes the whole level from one rank")
         path = os.path.join(directory, P.chk_file_name(prefix, self.isteps))
         deck = self.inp.deck
         mgs = deck.get("amr.max_grid_size", 32)
         mgs = int(str(mgs[0] if isinstance(mgs, (list, tuple)) else mgs).split()[0])
-        P.write_checkpoint(path, self.get_f(), self.get_g(), step=self.isteps, dt=self.dt, time=self.time,
-                           periodic=self.inp.periodic, max_grid_size=mgs, ng=F_NGHOST)
+        if self.world == 1:
+            P.write_checkpoint(path, self.get_f(), self.get_g(), step=self.isteps, dt=self.dt, time=self.time,
+                               periodic=self.inp.periodic, max_grid_size=mgs, ng=F_NGHOST)
+        else:  # collective: every rank writes its slab's FABs, rank 0 the headers
+            import torch.distributed as dist
+
+            def gather(obj):
+                out = [None] * self.world
+                dist.all_gather_object(out, obj)
+                return out
+
+            P.write_checkpoint_slabs(path, self.get_f(), self.get_g(), zlo=self.lo[2], nz_total=self.inp.n_cell[2],
+                                     rank=self.rank, gather=gather, step=self.isteps, dt=self.dt, time=self.time,
+                                     periodic=self.inp.periodic, max_grid_size=mgs, ng=F_NGHOST)
         return path
 
     def read_checkpoint_file(self, path: str):
         """LBM::read_checkpoint_file (Source/LBM.cpp:1785-1915): load f, g, step and time of a single-level
         checkpoint written by the reference or by write_checkpoint_file."""
         from . import plotfile as P
-        c = P.read_checkpoint(path)
+        c = P.read_checkpoint(path) if self.world == 1 else P.read_checkpoint_slab(path, self.lo[2], self.hi[2])
         if c["f"].shape != self.fab_shape(NQ, 0):
             raise MarblesError(f"checkpoint holds {c['f'].shape[1:]} cells, this level {self.fab_shape(NQ, 0)[1:]}")
         self.set_state(c["f"], c["g"], ng=0)

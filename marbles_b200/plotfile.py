@@ -224,24 +224,30 @@ def _grown(lo, hi, ng):
     return tuple(v - ng for v in lo), tuple(v + ng for v in hi)
 
 
-def write_vismf(lev_dir: str, prefix: str, data: np.ndarray, ng: int, boxes) -> None:
-    """VisMF::Write of one MultiFab: data is [ncomp, nz+2ng, ny+2ng, nx+2ng] over the domain grown by ng; every
-    FAB goes out with its own ghost cells (taken from the grown array), minima / maxima over the valid box."""
+def _write_vismf_data(lev_dir: str, dname: str, data: np.ndarray, ng: int, boxes, zoff: int = 0) -> dict:
+    """the FABs of `boxes` (global index space; data starts at global plane zoff, grown by ng) into one data file;
+    returns what the VisMF header needs"""
     ncomp = data.shape[0]
     os.makedirs(lev_dir, exist_ok=True)
-    dname = f"{prefix}_D_00000"
     offsets, mins, maxs = [], [], []
     with open(os.path.join(lev_dir, dname), "wb") as fh:
         for lo, hi in boxes:
             offsets.append(fh.tell())
             glo, ghi = _grown(lo, hi, ng)
-            sub = np.ascontiguousarray(data[:, lo[2]:hi[2] + 1 + 2 * ng, lo[1]:hi[1] + 1 + 2 * ng, lo[0]:hi[0] + 1 + 2 * ng])
+            z0, z1 = lo[2] - zoff, hi[2] - zoff
+            sub = np.ascontiguousarray(data[:, z0:z1 + 1 + 2 * ng, lo[1]:hi[1] + 1 + 2 * ng, lo[0]:hi[0] + 1 + 2 * ng])
             fh.write(f"{FAB_HEADER}{_box(glo, ghi)} {ncomp}\n".encode())
             fh.write(sub.astype("<f8").tobytes())
             val = sub[:, ng:sub.shape[1] - ng, ng:sub.shape[2] - ng, ng:sub.shape[3] - ng] if ng else sub
             flat = val.reshape(ncomp, -1)
-            mins.append(flat.min(axis=1))
-            maxs.append(flat.max(axis=1))
+            mins.append(flat.min(axis=1).tolist())
+            maxs.append(flat.max(axis=1).tolist())
+    return {"file": dname, "boxes": [(tuple(lo), tuple(hi)) for lo, hi in boxes], "offsets": offsets, "mins": mins,
+            "maxs": maxs}
+
+
+def _write_vismf_header(lev_dir: str, prefix: str, ncomp: int, ng: int, parts) -> None:
+    boxes = [b for p in parts for b in p["boxes"]]
     with open(os.path.join(lev_dir, f"{prefix}_H"), "w") as fh:
         fh.write(f"1\n1\n{ncomp}\n{ng}\n")
         fh.write(f"({len(boxes)} 0\n")
@@ -249,19 +255,29 @@ def write_vismf(lev_dir: str, prefix: str, data: np.ndarray, ng: int, boxes) -> 
             fh.write(_box(lo, hi) + "\n")
         fh.write(")\n")
         fh.write(f"{len(boxes)}\n")
-        for off in offsets:
-            fh.write(f"FabOnDisk: {dname} {off}\n")
+        for p in parts:
+            for off in p["offsets"]:
+                fh.write(f"FabOnDisk: {p['file']} {off}\n")
         fh.write("\n")
-        for table in (mins, maxs):
+        for key in ("mins", "maxs"):
             fh.write(f"{len(boxes)},{ncomp}\n")
-            for row in table:
-                fh.write("".join("%.17e," % v for v in row) + "\n")
+            for p in parts:
+                for row in p[key]:
+                    fh.write("".join("%.17e," % v for v in row) + "\n")
             fh.write("\n")
 
 
-def read_vismf(lev_dir: str, prefix: str):
-    """-> (data [ncomp, nz+2ng, ny+2ng, nx+2ng] over the bounding box of all FABs grown by ng, ng, boxes).
-    Cells covered by several FABs (ghost overlap) take the VALID cell's value."""
+def write_vismf(lev_dir: str, prefix: str, data: np.ndarray, ng: int, boxes) -> None:
+    """VisMF::Write of one MultiFab: data is [ncomp, nz+2ng, ny+2ng, nx+2ng] over the domain grown by ng; every
+    FAB goes out with its own ghost cells (taken from the grown array), minima / maxima over the valid box."""
+    part = _write_vismf_data(lev_dir, f"{prefix}_D_00000", data, ng, boxes)
+    _write_vismf_header(lev_dir, prefix, data.shape[0], ng, [part])
+
+
+def read_vismf(lev_dir: str, prefix: str, zrange=None):
+    """-> (data [ncomp, nz+2ng, ny+2ng, nx+2ng] over the bounding box of the FABs read, grown by ng, ng, boxes).
+    Cells covered by several FABs (ghost overlap) take the VALID cell's value.  zrange = (zlo, zhi): only the FABs
+    whose valid box lies inside those planes (a rank reading its own slab of a checkpoint)."""
     import re
     with open(os.path.join(lev_dir, f"{prefix}_H")) as fh:
         ch = fh.read().split("\n")
@@ -273,13 +289,17 @@ def read_vismf(lev_dir: str, prefix: str):
         m = [int(v) for v in re.findall(r"-?\d+", ch[i + 1 + b])]
         boxes.append((tuple(m[0:3]), tuple(m[3:6])))
     j = next(k for k, l in enumerate(ch) if l.startswith("FabOnDisk"))
+    fod = [ch[j + b] for b in range(nbox)]
+    if zrange is not None:
+        keep = [b for b in range(nbox) if boxes[b][1][2] >= zrange[0] and boxes[b][0][2] <= zrange[1]]
+        boxes, fod = [boxes[b] for b in keep], [fod[b] for b in keep]
     dlo = [min(b[0][d] for b in boxes) for d in range(3)]
     dhi = [max(b[1][d] for b in boxes) for d in range(3)]
     n = [dhi[d] - dlo[d] + 1 for d in range(3)]
     data = np.zeros((ncomp, n[2] + 2 * ng, n[1] + 2 * ng, n[0] + 2 * ng))
     fabs = []
     for b, (lo, hi) in enumerate(boxes):
-        _, fname, off = ch[j + b].split()
+        _, fname, off = fod[b].split()
         bn = [hi[d] - lo[d] + 1 + 2 * ng for d in range(3)]
         with open(os.path.join(lev_dir, fname), "rb") as fh:
             fh.seek(int(off))
@@ -412,3 +432,54 @@ def write_plotfile_slabs(path: str, names: list[str], data_local: np.ndarray, *,
             for d in range(3):
                 fh.write(f"{_g17(prob_lo[d] + lo[d] * dx[d])} {_g17(prob_lo[d] + (hi[d] + 1) * dx[d])}\n")
         fh.write("Level_0/Cell\n")
+
+
+def write_checkpoint_slabs(path: str, f_local: np.ndarray, g_local: np.ndarray, *, zlo: int, nz_total: int, rank: int,
+                           gather, step: int, dt: float, time: float, periodic, max_grid_size: int = 32, ng: int = 3):
+    """Checkpoint of a z-slab run: every rank writes the FABs of its slab (f_00_D_<rank>, g_00_D_<rank>), rank 0 the
+    Header and the two VisMF headers.  Ghost cells hold periodic images in x and y and the slab's own nearest
+    planes in z (the reference refills every ghost cell after a restart)."""
+    nzl, ny, nx = f_local.shape[1:]
+    boxes = [((lo[0], lo[1], lo[2] + zlo), (hi[0], hi[1], hi[2] + zlo)) for lo, hi in chop_boxes((nx, ny, nzl), max_grid_size)]
+
+    def grow(a):
+        for axis, d in ((3, 0), (2, 1), (1, 2)):
+            pad = [(0, 0)] * 4
+            pad[axis] = (ng, ng)
+            a = np.pad(a, pad, mode="wrap" if (periodic[d] and d != 2) else "edge")
+        return a
+
+    lev_dir = os.path.join(path, "Level_0")
+    os.makedirs(lev_dir, exist_ok=True)
+    parts = {}
+    for name, a in (("f_00", f_local), ("g_00", g_local)):
+        mine = _write_vismf_data(lev_dir, f"{name}_D_{rank:05d}", grow(np.asarray(a, dtype=np.float64)), ng, boxes, zoff=zlo)
+        parts[name] = gather(mine)
+    if rank != 0:
+        return
+    all_boxes = [b for p in parts["f_00"] for b in p["boxes"]]
+    with open(os.path.join(path, "Header"), "w") as fh:
+        fh.write("Checkpoint file for LBM\n0\n")
+        fh.write(f"{step} \n{_g17(dt)} \n{_g17(time)} \n")
+        fh.write(f"({len(all_boxes)} 0\n")
+        for lo, hi in all_boxes:
+            fh.write(_box(lo, hi) + "\n")
+        fh.write(")\n")
+    for name in ("f_00", "g_00"):
+        _write_vismf_header(lev_dir, name, f_local.shape[0], ng, parts[name])
+    _ = nz_total
+
+
+def read_checkpoint_slab(path: str, zlo: int, zhi: int) -> dict:
+    """the planes [zlo, zhi] of a single-level checkpoint (whoever wrote it, with whatever boxes)"""
+    with open(os.path.join(path, "Header")) as fh:
+        lines = fh.read().split("\n")
+    if int(lines[1]) != 0:
+        raise ValueError("only single-level checkpoints are supported")
+    out = {"step": int(lines[2].split()[0]), "dt": float(lines[3].split()[0]), "time": float(lines[4].split()[0])}
+    for name in ("f", "g"):
+        data, ng, boxes = read_vismf(os.path.join(path, "Level_0"), f"{name}_00", zrange=(zlo, zhi))
+        z0 = min(b[0][2] for b in boxes)
+        a = data[:, ng:data.shape[1] - ng, ng:data.shape[2] - ng, ng:data.shape[3] - ng] if ng else data
+        out[name] = np.ascontiguousarray(a[:, zlo - z0:zhi - z0 + 1])
+    return out

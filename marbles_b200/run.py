@@ -34,8 +34,6 @@ def evolve(lbm: LBM, out_dir: str = ".", log=print) -> list[str]:
     restart = _get(deck, "amr.restart", "")
     if _get(deck, "amr.max_level", 0, int) > 0:
         raise MarblesError("marbles_b200.run drives single-level decks (amr.max_level = 0)")
-    if lbm.world > 1 and (chk_int > 0 or restart):
-        raise MarblesError("checkpoints are written and read by single-rank runs (amr.chk_int = -1 on several GPUs)")
     written = []
     # lbm.compute_forces: one line of EB forces per step (open_forces_file / output_forces_file,
     # Source/LBM.cpp:1925-1969: width 24, 16 significant digits); forces every step means stepping one at a time

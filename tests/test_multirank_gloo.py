@@ -152,3 +152,56 @@ def test_multirank_plotfile_round_trip(oracle_mod, shape, world):
         assert pf["__names__"] == ["a", "b", "c"] and pf["__time__"] == 7.0
         for c, name in enumerate(pf["__names__"]):
             assert np.array_equal(pf[name], full[c])
+
+
+def _chk_worker(rank, world, initfile, outdir):
+    sys.path.insert(0, ROOT)
+    from marbles_b200.lbm import slab_bounds
+    from marbles_b200 import plotfile as P
+    dist.init_process_group("gloo", init_method=f"file://{initfile}", rank=rank, world_size=world)
+    full = np.load(os.path.join(outdir, "full.npz"))
+    nz = full["f"].shape[1]
+    zlo, zhi = slab_bounds(nz, rank, world)
+
+    def gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    P.write_checkpoint_slabs(os.path.join(outdir, "chk00004"), full["f"][:, zlo:zhi + 1], full["g"][:, zlo:zhi + 1], zlo=zlo,
+                             nz_total=nz, rank=rank, gather=gather, step=4, dt=1.0, time=4.0, periodic=[1, 1, 1],
+                             max_grid_size=8)
+    dist.barrier()
+    mine = P.read_checkpoint_slab(os.path.join(outdir, "chk00004"), zlo, zhi)  # and back, slab by slab
+    assert np.array_equal(mine["f"], full["f"][:, zlo:zhi + 1]) and np.array_equal(mine["g"], full["g"][:, zlo:zhi + 1])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_multirank_checkpoint_restarts_the_reference(oracle_mod, world):
+    """a checkpoint written by several ranks (one data file per rank): readable as a whole and slab by slab, and
+    the unmodified reference restarts from it and reproduces its uninterrupted run"""
+    import subprocess
+    from marbles_b200 import plotfile as P
+    O = oracle_mod
+    z, deck_text, _ = load_golden("tg12")
+    o = O.Oracle(O.lbm_setup(O.parse_deck(None, deck_text.splitlines())))
+    o.initialize()
+    o.step(4)
+    fl = o.fields()
+    f = np.stack([fl[f"f_{q:02d}"] for q in range(27)])
+    g = np.stack([fl[f"g_{q:02d}"] for q in range(27)])
+    with tempfile.TemporaryDirectory() as tmp:
+        np.savez(os.path.join(tmp, "full.npz"), f=f, g=g)
+        mp.spawn(_chk_worker, args=(world, os.path.join(tmp, "init"), tmp), nprocs=world, join=True)
+        c = P.read_checkpoint(os.path.join(tmp, "chk00004"))
+        assert c["step"] == 4 and np.array_equal(c["f"], f) and np.array_equal(c["g"], g)
+        if not os.path.exists(O.REF_SERIAL):
+            pytest.skip("reference executable not built")
+        with open(os.path.join(tmp, "tg.inp"), "w") as fh:
+            fh.write(deck_text)
+        subprocess.run([O.REF_SERIAL, "tg.inp", "max_step=10", "amr.plot_int=10", "amr.chk_int=-1", "amr.restart=chk00004",
+                        "lbm.save_streaming=1"], cwd=tmp, check=True, capture_output=True)
+        got = O.read_plotfile(os.path.join(tmp, "plt00010"))
+        for q in range(27):
+            assert np.array_equal(got[f"f_{q:02d}"], z[f"s10_f_{q:02d}"]) and np.array_equal(got[f"g_{q:02d}"], z[f"s10_g_{q:02d}"])
