@@ -763,22 +763,29 @@ __global__ void __launch_bounds__(128, 6) k_qcorr_combine(const double* __restri
     const long long c = L.cell(i, j, k);
     const long long n = L.sq;
     const uint32_t m = nbr[c];
-    if (!(m & 1u)) return;
     const bool inner = (L.wrap[0] || (i > 0 && i < L.nx - 1)) && (L.wrap[1] || (j > 0 && j < L.ny - 1)) &&
                        (L.wrap[2] || (k > 0 && k < L.nz - 1)) && k >= 0 && k < L.nz;
+    // the twelve part words are loaded before the mask is looked at (they are always inside the padded box):
+    // one memory latency per cell instead of two
+    const int kc = min(max(k, 0), L.nz - 1);
+    const int km = kc == 0 ? L.nz - 1 : kc - 1, kp = kc == L.nz - 1 ? 0 : kc + 1;
+    const long long c0 = L.cell(i, j, kc);
+    const long long cm = L.cell(i, j, km);      // source plane k-1 sends with c = +1
+    const long long cp = L.cell(i, j, kp);      // source plane k+1 sends with c = -1
+    const double rm = part[8 * n + cm], r0 = part[4 * n + c0], rp = part[0 * n + cp];
+    const double xm = part[9 * n + cm], x0 = part[5 * n + c0], xp = part[1 * n + cp];
+    const double ym = part[10 * n + cm], y0 = part[6 * n + c0], yp = part[2 * n + cp];
+    const double em = part[11 * n + cm], e0 = part[7 * n + c0], ep = part[3 * n + cp];
+    if (!(m & 1u)) return;
     if (!(inner && m == ALL_FLUID)) {
         qcorr_cell<true>(fin, gin, nbr, qc, L, P, i, j, k);
         return;
     }
-    const int km = k == 0 ? L.nz - 1 : k - 1, kp = k == L.nz - 1 ? 0 : k + 1;
-    const long long cm = L.cell(i, j, km);      // source plane k-1 sends with c = +1
-    const long long cp = L.cell(i, j, kp);      // source plane k+1 sends with c = -1
-    const double rm = part[8 * n + cm], r0 = part[4 * n + c], rp = part[0 * n + cp];
     double rho = rm + r0 + rp;
     double jz = rm - rp;
-    double jx = part[9 * n + cm] + part[5 * n + c] + part[1 * n + cp];
-    double jy = part[10 * n + cm] + part[6 * n + c] + part[2 * n + cp];
-    double e2 = part[11 * n + cm] + part[7 * n + c] + part[3 * n + cp];
+    double jx = xm + x0 + xp;
+    double jy = ym + y0 + yp;
+    double e2 = em + e0 + ep;
     if (W > 0) {
         // k_collide_tile: the rows at the edges of a CTA lack what the neighbouring CTA's adjacent row sent
         // (edge arrays: [side 0 = first row's e_y = -1 sums | side 1 = last row's e_y = +1 sums][c][rho, jx, e2])
