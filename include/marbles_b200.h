@@ -158,6 +158,14 @@ int mbl_collide(mbl_ctx* ctx, int lev, int want_macrodata);
 int mbl_f_to_macrodata(mbl_ctx* ctx, int lev);
 /* LBM::compute_derived(lev) (Source/LBM.cpp:909-955), needs macrodata */
 int mbl_compute_derived(mbl_ctx* ctx, int lev);
+/* compute_derived on a z-slab: the vorticity (and, for an initial state, the differenced q-corrections) of the
+ * planes next to another rank needs that rank's adjacent macrodata plane.  mbl_macro_halo(pack=1) copies the
+ * outermost valid plane of velocity and QCorr (6 comps, mbl_macro_halo_doubles() doubles) on `side` into
+ * device_buf, (pack=0) writes a neighbour's buffer into the ghost plane; mbl_compute_derived_slab then
+ * differences across the sides that have one. */
+int64_t mbl_macro_halo_doubles(mbl_ctx* ctx, int lev);
+int mbl_macro_halo(mbl_ctx* ctx, int lev, int side, double* device_buf, int pack);
+int mbl_compute_derived_slab(mbl_ctx* ctx, int lev, int has_lo, int has_hi);
 /* LBM::compute_eb_forces() for one level (Source/LBM.cpp:994-1044): local sum */
 int mbl_eb_forces(mbl_ctx* ctx, int lev, double out[3]);
 

@@ -72,6 +72,9 @@ SYMBOLS = {
     "mbl_f_to_macrodata": (C.c_int, [_P, C.c_int]),
     "mbl_compute_derived": (C.c_int, [_P, C.c_int]),
     "mbl_eb_forces": (C.c_int, [_P, C.c_int, _D]),
+    "mbl_macro_halo_doubles": (C.c_int64, [_P, C.c_int]),
+    "mbl_macro_halo": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int]),
+    "mbl_compute_derived_slab": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "mbl_step": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_int]),
     "mbl_step_local": (C.c_int, [_P, C.c_int, C.c_double, C.c_int]),
     "mbl_halo_doubles": (C.c_int64, [_P, C.c_int]),

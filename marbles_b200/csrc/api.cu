@@ -613,6 +613,46 @@ int mbl_compute_derived(mbl_ctx* ctx, int lev)
     return 0;
 }
 
+// macrodata planes a z-neighbour needs for compute_derived on a slab: velocity (vorticity) and QCorr (their
+// differences), one valid plane per side.  side 0 = low z, 1 = high z; pack copies the outermost valid plane into
+// buf, unpack copies a neighbour's plane into the ghost plane on that side.  Whole padded planes, plain copies.
+static const int MACRO_HALO_COMPS[6] = {1, 2, 3, 6, 7, 8};
+
+int64_t mbl_macro_halo_doubles(mbl_ctx* ctx, int lev)
+{
+    if (check_level(ctx, lev)) return -1;
+    return 6LL * ctx->lev[lev].L.sz;
+}
+
+int mbl_macro_halo(mbl_ctx* ctx, int lev, int side, double* buf, int pack)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    if (!lv.macro) return fail("mbl_macro_halo needs macrodata");
+    if (!buf || side < 0 || side > 1) return fail("mbl_macro_halo: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    const Layout& L = lv.L;
+    const int plane = pack ? (side == 0 ? 0 : L.nz - 1) : (side == 0 ? -1 : L.nz);
+    for (int n = 0; n < 6; ++n) {
+        double* p = lv.macro + (size_t)MACRO_HALO_COMPS[n] * L.sq + (size_t)(plane + GZ) * L.sz;
+        double* b = buf + (size_t)n * L.sz;
+        CU(cudaMemcpyAsync(pack ? b : p, pack ? p : b, (size_t)L.sz * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return 0;
+}
+
+int mbl_compute_derived_slab(mbl_ctx* ctx, int lev, int has_lo, int has_hi)
+{
+    if (check_level(ctx, lev)) return 1;
+    Level& lv = ctx->lev[lev];
+    if (!lv.macro) return fail("mbl_compute_derived needs macrodata");
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches += launch_derived(lv.L, lv.P, lv.p.flag, lv.macro, lv.macro + (size_t)MBL_NMACRO * lv.L.sq, ctx->stream,
+                                    lv.dq_from_macro ? 1 : 0, (has_lo ? 1 : 0) | (has_hi ? 2 : 0));
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int mbl_eb_forces(mbl_ctx* ctx, int lev, double out[3])
 {
     if (check_level(ctx, lev)) return 1;

@@ -985,7 +985,7 @@ __global__ void __launch_bounds__(128) k_macrodata(const double* __restrict__ f,
 // Needs macrodata of the face neighbours inside the domain (valid cells of this box; the
 // z-neighbours across a rank boundary are treated as unusable -- plot-only quantity).
 __global__ void __launch_bounds__(128) k_derived(const uint8_t* __restrict__ flag, const double* __restrict__ macro,
-                                                 double* __restrict__ derived, Layout L, Phys P, int with_dq)
+                                                 double* __restrict__ derived, Layout L, Phys P, int with_dq, int zghost)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
@@ -997,7 +997,8 @@ __global__ void __launch_bounds__(128) k_derived(const uint8_t* __restrict__ fla
     if (!(fb & FLAG_FLUID)) return;
     const long long step[3] = {1, L.px, L.sz};
     const unsigned bp[3] = {GRAD_PX, GRAD_PY, GRAD_PZ}, bm[3] = {GRAD_MX, GRAD_MY, GRAD_MZ};
-    const bool zin_p = (k + 1 < L.nz), zin_m = (k - 1 >= 0);
+    // zghost bit 0 / 1: the macrodata ghost plane below / above holds the neighbouring rank's plane
+    const bool zin_p = (k + 1 < L.nz) || (zghost & 2), zin_m = (k - 1 >= 0) || (zghost & 1);
     auto grad = [&](int dir, int comp) {
         bool okp = fb & bp[dir], okm = fb & bm[dir];
         if (dir == 2) {
@@ -1758,10 +1759,10 @@ int launch_macrodata(const Layout& L, const Phys& P, const double* f, const doub
 }
 
 int launch_derived(const Layout& L, const Phys& P, const uint8_t* flag, const double* macro, double* derived,
-                   cudaStream_t st, int with_dq)
+                   cudaStream_t st, int with_dq, int zghost)
 {
     const int bx = block_x(L);
-    k_derived<<<grid3(L, bx), bx, 0, st>>>(flag, macro, derived, L, P, with_dq);
+    k_derived<<<grid3(L, bx), bx, 0, st>>>(flag, macro, derived, L, P, with_dq, zghost);
     return 1;
 }
 

@@ -100,7 +100,7 @@ int launch_stream(const Layout& L, const double* fin, const double* gin, double*
 int launch_macrodata(const Layout& L, const Phys& P, const double* f, const double* g, const uint8_t* flag,
                      double* macro, cudaStream_t st);
 int launch_derived(const Layout& L, const Phys& P, const uint8_t* flag, const double* macro, double* derived,
-                   cudaStream_t st, int with_dq = 0);
+                   cudaStream_t st, int with_dq = 0, int zghost = 0);
 int launch_eb_forces(const Layout& L, const double* f, const uint8_t* flag, double* d_out3, cudaStream_t st);
 
 // fused.cu: persistent TMA-pipelined kernel.  mode 0: q-correction jobs only (pass 1), 1: collide jobs only

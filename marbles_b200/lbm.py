@@ -206,7 +206,14 @@ class LBM:
         check(self.lib.mbl_f_to_macrodata(self.ctx, lev))
 
     def compute_derived(self, lev: int = 0):
-        check(self.lib.mbl_compute_derived(self.ctx, lev))
+        """LBM::compute_derived.  On a slab the planes next to another rank difference across the rank boundary:
+        the neighbours' adjacent macrodata planes are exchanged first (collective call)."""
+        if self.world > 1 and self.comm is not None and hasattr(self.comm, "exchange_macro"):
+            self.comm.exchange_macro(self)
+            check(self.lib.mbl_compute_derived_slab(self.ctx, lev, int(self.comm.lower is not None),
+                                                    int(self.comm.upper is not None)))
+        else:
+            check(self.lib.mbl_compute_derived(self.ctx, lev))
 
     def compute_eb_forces(self) -> np.ndarray:
         out = (C.c_double * 3)()

@@ -72,6 +72,22 @@ class HaloComm:
         if self.upper is not None:
             check(lbm.lib.mbl_halo_unpack(lbm.ctx, lbm.lev, 1, C.c_void_p(recv_hi.data_ptr())))
 
+    def exchange_macro(self, lbm):
+        """the neighbours' adjacent planes of velocity and QCorr into the macrodata ghost planes (compute_derived)"""
+        n = int(lbm.lib.mbl_macro_halo_doubles(lbm.ctx, lbm.lev))
+        if getattr(self, "mbuf", None) is None or self.mbuf[0].numel() != n:
+            self.mbuf = [torch.empty(n, dtype=torch.float64, device=self.device) for _ in range(4)]
+        send_lo, send_hi, recv_lo, recv_hi = self.mbuf
+        if self.lower is not None:
+            check(lbm.lib.mbl_macro_halo(lbm.ctx, lbm.lev, 0, C.c_void_p(send_lo.data_ptr()), 1))
+        if self.upper is not None:
+            check(lbm.lib.mbl_macro_halo(lbm.ctx, lbm.lev, 1, C.c_void_p(send_hi.data_ptr()), 1))
+        exchange_buffers(send_lo, send_hi, recv_lo, recv_hi, self.lower, self.upper, self.group)
+        if self.lower is not None:
+            check(lbm.lib.mbl_macro_halo(lbm.ctx, lbm.lev, 0, C.c_void_p(recv_lo.data_ptr()), 0))
+        if self.upper is not None:
+            check(lbm.lib.mbl_macro_halo(lbm.ctx, lbm.lev, 1, C.c_void_p(recv_hi.data_ptr()), 0))
+
     # ---- overlapped exchange (LBM._step_overlapped) --------------------------------------------
     def _side_stream(self, lbm):
         if getattr(self, "xstream", None) is None:
@@ -185,6 +201,23 @@ class LocalSlabs:
                 s.time += s.dt
                 s.isteps += 1
                 s.sync()
+
+    def compute_derived(self):
+        """compute_derived of every slab with the neighbours' macrodata planes exchanged first"""
+        n = int(self.slabs[0].lib.mbl_macro_halo_doubles(self.slabs[0].ctx, 0))
+        bufs = [[torch.empty(n, dtype=torch.float64, device=self.device) for _ in range(2)] for _ in self.slabs]
+        for s, (lo, hi) in zip(self.slabs, bufs):
+            check(s.lib.mbl_macro_halo(s.ctx, 0, 0, C.c_void_p(lo.data_ptr()), 1))
+            check(s.lib.mbl_macro_halo(s.ctx, 0, 1, C.c_void_p(hi.data_ptr()), 1))
+            s.sync()
+        for r, s in enumerate(self.slabs):
+            lower, upper = neighbours(r, self.world, self.periodic_z)
+            if lower is not None:
+                check(s.lib.mbl_macro_halo(s.ctx, 0, 0, C.c_void_p(bufs[lower][1].data_ptr()), 0))
+            if upper is not None:
+                check(s.lib.mbl_macro_halo(s.ctx, 0, 1, C.c_void_p(bufs[upper][0].data_ptr()), 0))
+            check(s.lib.mbl_compute_derived_slab(s.ctx, 0, int(lower is not None), int(upper is not None)))
+            s.sync()
 
     def step_host(self, fabs, ng: int = 0):
         """LBM.step_host of every slab in the multi-rank order: boundary planes up, exchange, pipelined rest.

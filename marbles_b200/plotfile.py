@@ -152,8 +152,7 @@ def write_lbm_plotfile(lbm, directory: str = ".", prefix: str = "plt", max_grid_
                        save_streaming: bool | None = None, save_derived: bool | None = None) -> str:
     """LBM::write_plot_file: the macrodata must be current (last step taken with want_macrodata=True, as the
     reference's post_time_step leaves it).  On several ranks every rank writes the FABs of its z-slab and rank 0 the
-    headers (collective call); the vorticity of the two planes next to another rank's slab is then differenced
-    one-sided in z."""
+    headers (collective call; compute_derived exchanges the neighbours' macrodata planes first)."""
     deck = lbm.inp.deck
 
     def deck_int(key: str, default: int) -> int:
