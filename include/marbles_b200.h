@@ -171,10 +171,12 @@ int mbl_eb_forces(mbl_ctx* ctx, int lev, double out[3]);
 
 /* fused fast path: one coarse step of a single-level run =
  * fillpatch(f), fillpatch(g), stream(f), stream(g), collide
- * (Source/LBM.cpp:416-422, 523-544).  nsteps > 1 only on a single rank. */
+ * (Source/LBM.cpp:416-422, 523-544).  nsteps > 1 only on a single rank; macrodata (all 19
+ * fields + differenced q-corrections) is stored for the last step if want_macrodata.  On boxes
+ * below ~16 M cells, nsteps >= 5 replays pairs of steps as one CUDA graph (MBL_GRAPH=0 disables). */
 int mbl_step(mbl_ctx* ctx, int lev, int nsteps, double time, int want_macrodata);
-/* the same step split so a caller can exchange z-halo planes between ranks:
- * mbl_step_begin = nothing yet (reserved); halo exchange; mbl_step_finish */
+/* one step of a z-slab whose ghost planes are current: the caller exchanges the halo planes
+ * (mbl_halo_pack / transport / mbl_halo_unpack) before every call */
 int mbl_step_local(mbl_ctx* ctx, int lev, double time, int want_macrodata);
 
 /* z-halo planes (multi-rank slabs): side 0 = low-z, 1 = high-z.  pack copies
