@@ -482,3 +482,25 @@ def read_checkpoint_slab(path: str, zlo: int, zhi: int) -> dict:
         a = data[:, ng:data.shape[1] - ng, ng:data.shape[2] - ng, ng:data.shape[3] - ng] if ng else data
         out[name] = np.ascontiguousarray(a[:, zlo - z0:zhi - z0 + 1])
     return out
+
+
+def read_plotfile(path: str) -> dict:
+    """A single-level plotfile as {variable name: [nz, ny, nx] array} plus "__names__", "__time__", "__step__";
+    any number of data files (one per rank) and boxes."""
+    import re
+    with open(os.path.join(path, "Header")) as fh:
+        lines = fh.read().split("\n")
+    ncomp = int(lines[1])
+    names = lines[2:2 + ncomp]
+    pos = 2 + ncomp
+    time = float(lines[pos + 1])
+    if int(lines[pos + 2]) != 0:
+        raise ValueError("only single-level plotfiles are supported")
+    m = [int(v) for v in re.findall(r"-?\d+", lines[pos + 6])]
+    lo, hi = m[0:3], m[3:6]
+    step = int(lines[pos + 7].split()[0])
+    data, ng, _ = read_vismf(os.path.join(path, "Level_0"), "Cell")
+    assert ng == 0 and list(data.shape[1:]) == [hi[2] - lo[2] + 1, hi[1] - lo[1] + 1, hi[0] - lo[0] + 1]
+    out = {name: data[c] for c, name in enumerate(names)}
+    out.update({"__names__": names, "__time__": time, "__step__": step})
+    return out

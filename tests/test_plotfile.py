@@ -87,3 +87,25 @@ def test_box_lists_match_reference():
     for c in cases:
         mine = [[list(lo), list(hi)] for lo, hi in P.chop_boxes(c["n_cell"], c["max_grid_size"])]
         assert mine == c["boxes"], (c["n_cell"], c["max_grid_size"])
+
+
+def test_fcompare_and_product_reader(tmp_path, capsys):
+    """marbles_b200.fcompare on two plotfiles (one written as a single file, one as two rank files)"""
+    from marbles_b200 import fcompare as F
+    rng = np.random.default_rng(11)
+    names = ["rho", "vel_x"]
+    data = rng.standard_normal((2, 12, 6, 10))
+    a, b, c = str(tmp_path / "plt00001"), str(tmp_path / "two" / "plt00001"), str(tmp_path / "off" / "plt00001")
+    P.write_plotfile(a, names, data, time=1.0, step=1, prob_lo=[0, 0, 0], prob_hi=[1, 1, 1], max_grid_size=4)
+    # two-file version through the real collective path is covered by test_multirank_gloo; here: same data, other boxes
+    P.write_plotfile(b, names, data, time=1.0, step=1, prob_lo=[0, 0, 0], prob_hi=[1, 1, 1], max_grid_size=8)
+    pert = data.copy()
+    pert[1, 3, 2, 1] += 1e-9
+    P.write_plotfile(c, names, pert, time=1.0, step=1, prob_lo=[0, 0, 0], prob_hi=[1, 1, 1], max_grid_size=4)
+    pf = P.read_plotfile(b)
+    assert pf["__names__"] == names and pf["__step__"] == 1 and np.array_equal(pf["vel_x"], data[1])
+    assert F.main([a, b]) == 0 and "PLOTFILES AGREE" in capsys.readouterr().out
+    assert F.main([a, c]) == 1
+    assert F.main([a, c, "--abs-tol", "1e-8"]) == 0
+    rows, _ = F.compare(a, c)
+    assert rows[0][1] == 0.0 and rows[1][1] == pytest.approx(1e-9, rel=1e-3)
