@@ -282,19 +282,20 @@ def main():
     peak, peak_src = measured_peak_gbs()
     collide_ms = kms[2] / max(nrec.value, 1)
     kname = {0: "k_collide_lean (pull + collide)", 1: "k_fused (q-correction + collide jobs)", 2: "k_fused (collide jobs)",
-             3: "k_fused_plain (q-correction + collide jobs)", 4: "k_collide_carry", 5: "k_collide_tile", 6: "k_collide_lean"}[lbm.variant]
+             3: "k_fused_plain (q-correction + collide jobs)", 4: "k_collide_carry", 5: "k_collide_tile", 6: "k_collide_lean", 7: "k_collide_tile_pair"}[lbm.variant]
     vname = {0: "two kernels (k_qcorr, k_collide_lean)", 1: "one persistent TMA-pipelined kernel per step",
              2: "persistent TMA kernel, two launches (q-correction, collide)",
              3: "one persistent kernel per step, plain loads",
              4: "carry step: k_qcorr_combine (row sums -> q-corrections) + k_collide_carry (collide, emits the next "
                 "step's moment row sums)",
              5: "carry step without marching: k_qcorr_combine + k_collide_tile",
-             6: "two kernels, collide with g staged through shared memory (k_qcorr, k_collide_lean)"}[lbm.variant]
+             6: "two kernels, collide with g staged through shared memory (k_qcorr, k_collide_lean)",
+             7: "tile carry step with plane pairs: k_qcorr_combine_pair + k_collide_tile_pair"}[lbm.variant]
     achieved = BYTES_PER_CELL * lbm.ncells / (collide_ms * 1e-3) / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            tkey = {0: "k_collide_lean", 6: "k_collide_lean", 5: "k_collide_tile", 4: "k_collide_carry"}.get(lbm.variant)
+            tkey = {0: "k_collide_lean", 6: "k_collide_lean", 5: "k_collide_tile", 4: "k_collide_carry", 7: "k_collide_tile_pair"}.get(lbm.variant)
             traffic = json.load(fh).get("dram_bytes_per_launch_512", {}).get(tkey) if n == 512 else None
     except Exception:
         pass

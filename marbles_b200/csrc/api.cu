@@ -58,6 +58,7 @@ struct Level {
     double* part = nullptr;   // carry step: 12 partial-sum words per cell (lazily allocated)
     double* edge = nullptr;   // tile carry step: 18 words per CTA row
     bool dq_from_macro = false;  // macrodata came from mbl_f_to_macrodata: compute_derived also differences QCorr
+    int part_pair = 0;        // `part` holds the 9-word plane-pair layout (variant 7)
     int edge_rows = 0;        // rows per CTA the edge arrays were written with (0: written by the marching kernel)
     // two consecutive steps (buffers a -> b -> a) captured as one CUDA graph: small boxes are launch-bound
     // (a non-periodic level issues ~30 ghost-fill launches per step)
@@ -162,15 +163,18 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
     double* macro = want_macro ? lv.macro : nullptr;
     // the carry kernels address a component with 32-bit byte offsets: larger boxes take the two-kernel step
     int variant = ctx->variant;
-    if ((variant == 4 || variant == 5) && lv.L.sq * 8 >= (1LL << 32)) variant = 0;
-    if (variant == 4 || variant == 5) {
+    if (variant == 7 && ((lv.L.nz & 1) || carry_tile_rows(ctx->carry_rows) != 6)) variant = 5;  // pairs need an even nz
+    if ((variant == 4 || variant == 5 || variant == 7) && lv.L.sq * 8 >= (1LL << 32)) variant = 0;
+    if (variant == 4 || variant == 5 || variant == 7) {
         // carry step: q-corrections from the partial sums the previous collide left behind (first step, or after
         // anything else wrote the lattice: the full q-correction pass)
         if (!lv.part) CU(cudaMalloc(&lv.part, (size_t)CARRY_WORDS * lv.L.sq * sizeof(double)));
         const int W = carry_tile_rows(ctx->carry_rows);
-        if (variant == 5 && !lv.edge)
+        if (variant != 4 && !lv.edge)
             CU(cudaMalloc(&lv.edge, (size_t)CARRY_EDGE_WORDS * carry_edge_plane(lv.L, 4) * (lv.L.nz + 2 * GZ) * sizeof(double)));
-        if (lv.carry_valid)
+        if (lv.carry_valid && lv.part_pair)
+            ctx->launches += launch_qcorr_combine_pair(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.part, lv.edge, lv.p.qc, st);
+        else if (lv.carry_valid)
             ctx->launches += launch_qcorr_combine(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.part,
                                                   lv.edge_rows ? lv.edge : nullptr, lv.edge_rows, lv.p.qc, st);
         else
@@ -182,12 +186,16 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
             lv.carry_valid = false;
         } else {
             const CarryPlan C = make_carry_plan(Lk, ctx->carry_own, ctx->carry_ky);
-            const int nl = variant == 4
+            const int nl = variant == 7
+                               ? launch_collide_tile_pair(Lk, lv.P, C, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr,
+                                                          lv.p.flag, lv.p.qc, lv.part, lv.edge, st)
+                           : variant == 4
                                ? launch_collide_carry(Lk, lv.P, C, ctx->carry_minb, lv.p.f[a], lv.p.g[a], lv.p.f[b],
                                                       lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, lv.part, st)
                                : launch_collide_tile(Lk, lv.P, C, W, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b],
                                                      lv.p.nbr, lv.p.flag, lv.p.qc, lv.part, lv.edge, st);
-            lv.edge_rows = variant == 5 ? W : 0;
+            lv.edge_rows = variant == 4 ? 0 : W;
+            lv.part_pair = variant == 7;
             if (nl < 0) return fail("carry step: a lattice component exceeds 4 GB (32-bit byte offsets)");
             ctx->launches += nl;
             lv.carry_valid = true;
@@ -761,14 +769,14 @@ int mbl_step_split(mbl_ctx* ctx, int lev, int part)
     };
     // variant 5 keeps carrying through the split: q-corrections from the previous step's partial sums
     // (k_qcorr_combine; planes next to a ghost plane are pulled as before), collide by k_collide_tile
-    const bool tile = ctx->variant == 5 && L.sq * 8 < (1LL << 32);
+    const bool tile = (ctx->variant == 5 || ctx->variant == 7) && L.sq * 8 < (1LL << 32);
     const int W = carry_tile_rows(ctx->carry_rows);
     if (tile) {
         if (!lv.part) CU(cudaMalloc(&lv.part, (size_t)CARRY_WORDS * L.sq * sizeof(double)));
         if (!lv.edge)
             CU(cudaMalloc(&lv.edge, (size_t)CARRY_EDGE_WORDS * carry_edge_plane(L, 4) * (L.nz + 2 * GZ) * sizeof(double)));
     }
-    const bool from_sums = tile && lv.carry_valid && lv.edge_rows == W;
+    const bool from_sums = tile && lv.carry_valid && lv.edge_rows == W && !lv.part_pair;
     const CarryPlan C = make_carry_plan(L, ctx->carry_own, ctx->carry_ky);
     auto q = [&](int ka, int kb) {
         if (from_sums)
@@ -806,6 +814,7 @@ int mbl_step_split(mbl_ctx* ctx, int lev, int part)
         lv.cur = b;
         lv.carry_valid = tile;
         lv.edge_rows = tile ? W : 0;
+        lv.part_pair = 0;
     }
     CU(cudaGetLastError());
     return 0;
@@ -1069,7 +1078,7 @@ int mbl_get_variant(mbl_ctx* ctx) { return ctx ? ctx->variant : -1; }
 int mbl_set_variant(mbl_ctx* ctx, int variant)
 {
     if (!ctx) return fail("null context");
-    if (variant < 0 || variant > 6) return fail("variant %d is not available", variant);
+    if (variant < 0 || variant > 7) return fail("variant %d is not available", variant);
     ctx->variant = variant;
     for (int l = 0; l < MAX_LEVELS; ++l) ctx->lev[l].carry_valid = false;
     return 0;

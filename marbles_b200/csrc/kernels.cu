@@ -749,6 +749,275 @@ __global__ void __launch_bounds__(32 * W, (W <= 4 ? 3 : W <= 8 ? 2 : 1))
     }
 }
 
+// ---------------------------------------------------------------------------
+// k_collide_tile with the z sum of a PAIR of planes (2b, 2b+1) completed on chip: a thread collides its cell in
+// plane 2b, then in plane 2b+1, and keeps what the first sends up / receives from the second in shared memory.
+// Per cell 9 words leave instead of 12: own[rho, jx, jy, jz, e2] (its own and its partner's contributions) and
+// out[rho, jx, jy, e2] (even plane: what it sends down; odd plane: what it sends up).  Needs an even number of
+// planes; k_qcorr_combine_pair adds own(k) and out(k -+ 1).
+// ---------------------------------------------------------------------------
+constexpr int PAIR_KEEP_SLOTS = 8;
+template <int W>
+__global__ void __launch_bounds__(32 * W, (W <= 4 ? 3 : W <= 8 ? 2 : 1))
+    k_collide_tile_pair(const __grid_constant__ CarryPtrs A, const uint32_t* __restrict__ nbr,
+                   const uint8_t* __restrict__ flag, const __grid_constant__ Layout L, const __grid_constant__ Phys P,
+                   const __grid_constant__ CarryPlan C, int k0)
+{
+    constexpr int T = 32 * W;
+    extern __shared__ double smem[];
+    double* const sg = smem + threadIdx.x;  // sg[slot * T]
+    const unsigned sg_addr = (unsigned)__cvta_generic_to_shared(sg);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int xc = blockIdx.x;
+    const int y0 = blockIdx.y * W;
+    const int rows = min(W, L.ny - y0);  // rows of this CTA inside the box
+    double* const sk = smem + NQ * T + threadIdx.x;  // sk[slot * T]: own and up sums of the first plane
+    const int i = xc * C.own - C.halo + lane;
+    const bool own = lane >= C.halo && lane < C.halo + C.own && i < L.nx && w < rows;
+    // cell this thread collides: its own, the periodic image for halo lanes over a wrapped edge, otherwise
+    // clamped (what such a thread contributes lands in cells k_qcorr_combine does not take from the carried sums)
+    int is = i, j = min(y0 + w, L.ny - 1);
+    if (is < 0) is = L.wrap[0] ? is + L.nx : 0;
+    if (is >= L.nx) is = (L.wrap[0] && is - L.nx < L.nx) ? is - L.nx : L.nx - 1;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned px8 = (unsigned)L.px * 8u, sz8 = (unsigned)L.sz * 8u;
+    unsigned xo[3], yo[3], zo[3];
+    xo[1] = yo[1] = zo[1] = 0u;
+    xo[2] = (L.wrap[0] && is == 0) ? (unsigned)(L.nx - 1) * 8u : 0u - 8u;
+    xo[0] = (L.wrap[0] && is == L.nx - 1) ? 0u - (unsigned)(L.nx - 1) * 8u : 8u;
+    yo[2] = (L.wrap[1] && j == 0) ? (unsigned)(L.ny - 1) * px8 : 0u - px8;
+    yo[0] = (L.wrap[1] && j == L.ny - 1) ? 0u - (unsigned)(L.ny - 1) * px8 : px8;
+    unsigned c_first = 0u;
+#pragma unroll 1
+    for (int kk = 0; kk < 2; ++kk) {
+    const int k = 2 * (int)blockIdx.z + kk + k0;
+    zo[2] = (L.wrap[2] && k == 0) ? (unsigned)(L.nz - 1) * sz8 : 0u - sz8;
+    zo[0] = (L.wrap[2] && k == L.nz - 1) ? 0u - (unsigned)(L.nz - 1) * sz8 : sz8;
+    const unsigned c = (unsigned)(is + OX) * 8u + (unsigned)(j + GY) * px8 + (unsigned)(k + GZ) * sz8;
+    auto ldb = [](const double* base, unsigned off) { return *(const double*)((const char*)base + off); };
+    auto stb = [](double* base, unsigned off, double v) { *(double*)((char*)base + off) = v; };
+    unsigned cyz[3][3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) cyz[b][d] = c + yo[b] + zo[d];
+    // g: global -> shared, asynchronously, no registers
+    static_for<0, NQ>([&](auto qc_) {
+        constexpr int Q = decltype(qc_)::value;
+        cp_async8(sg_addr + Q * T * 8, (const char*)A.gin[Q] + (cyz[ey(Q) + 1][ez(Q) + 1] + xo[ex(Q) + 1]));
+    });
+    const uint32_t m = *(const uint32_t*)((const char*)nbr + (c >> 1));
+    const unsigned fb = flag[c >> 3];
+    const double qxp = ldb(A.qc[0], c + 8u), qxm = ldb(A.qc[0], c - 8u);
+    const double qyp = ldb(A.qc[1], c + px8), qym = ldb(A.qc[1], c - px8);
+    const double qzp = ldb(A.qc[2], c + sz8), qzm = ldb(A.qc[2], c - sz8);
+    double f[NQ];
+    static_for<0, NQ>([&](auto qc_) {
+        constexpr int Q = decltype(qc_)::value;
+        f[Q] = ldb(A.fin[Q], cyz[ey(Q) + 1][ez(Q) + 1] + xo[ex(Q) + 1]);
+    });
+    const bool fluid = m & 1u;
+    if (m != ALL_FLUID) {
+        if (fluid) {
+            // halfway bounce-back: the cell's own opposite population (LBM.cpp:590-595 in pull form)
+            static_for<1, NQ>([&](auto qc_) {
+                constexpr int Q = decltype(qc_)::value;
+                if (!((m >> Q) & 1u)) f[Q] = ldb(A.fin[opp(Q)], c);
+            });
+        } else {
+            // solid cell: the streamed value is the -1 sentinel (LBM.cpp:565, 582) and collide skips it;
+            // with omega = 0 below the "relaxed" value is exactly -1 again
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) f[q] = -1.0;
+        }
+    }
+    MomF mf = moments_f([&](int q) { return f[q]; });
+    // wait for g only now, and tied to a value that needs every f: placed right after the cp.async issue, ptxas
+    // schedules the f loads behind the wait and the cell pays two DRAM latencies in series
+    cp_async_wait_all_after(mf.rho);
+    if (m != ALL_FLUID) {
+        if (fluid) {
+            static_for<1, NQ>([&](auto qc_) {
+                constexpr int Q = decltype(qc_)::value;
+                if (!((m >> Q) & 1u)) sg[Q * T] = ldb(A.gin[opp(Q)], c);
+            });
+        } else {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) sg[q * T] = -1.0;
+        }
+    }
+    const MomG mg = moments_g([&](int q) { return sg[q * T]; });
+    const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
+    const double dqx = one_sided_gradient(fb & GRAD_PX, fb & GRAD_MX, (fb & GRAD_PX) ? qxp : 0.0, s.qcx,
+                                          (fb & GRAD_MX) ? qxm : 0.0, P.idx[0]);
+    const double dqy = one_sided_gradient(fb & GRAD_PY, fb & GRAD_MY, (fb & GRAD_PY) ? qyp : 0.0, s.qcy,
+                                          (fb & GRAD_MY) ? qym : 0.0, P.idx[1]);
+    const double dqz = one_sided_gradient(fb & GRAD_PZ, fb & GRAD_MZ, (fb & GRAD_PZ) ? qzp : 0.0, s.qcz,
+                                          (fb & GRAD_MZ) ? qzm : 0.0, P.idx[2]);
+    const Coll cc = collision_coefficients(s, mf, mg, dqx, dqy, dqz, P);
+    const double omega = fluid ? cc.omega : 0.0;
+    // this cell's contributions to rows j-1 (TA), j (TB), j+1 (TC): [plane c][rho, jx], then e2
+    double TA[3][2] = {}, TB[3][2] = {}, TC[3][2] = {};
+    double EA[3] = {}, EB[3] = {}, EC[3] = {};
+    static_for<0, NQ>([&](auto qc_) {
+        constexpr int Q = decltype(qc_)::value;
+        constexpr int d = ez(Q) + 1;
+        const double v = f[Q] + omega * (feq_q<Q>(cc) - f[Q]);
+        if (own) stb(A.fout[Q], c, v);
+        double t = v;
+        if constexpr (ex(Q) == 1) t = __shfl_up_sync(FULL, v, 1);
+        if constexpr (ex(Q) == -1) t = __shfl_down_sync(FULL, v, 1);
+        double(&Tt)[3][2] = ey(Q) == -1 ? TA : ey(Q) == 0 ? TB : TC;
+        Tt[d][0] += t;
+        if constexpr (ex(Q) == 1) Tt[d][1] += t;
+        if constexpr (ex(Q) == -1) Tt[d][1] -= t;
+    });
+    static_for<0, NQ>([&](auto qc_) {
+        constexpr int Q = decltype(qc_)::value;
+        constexpr int d = ez(Q) + 1;
+        const double gq = sg[Q * T];
+        const double v = gq + omega * (geq_q<Q>(cc) - gq);
+        if (own) stb(A.gout[Q], c, v);
+        double t = v;
+        if constexpr (ex(Q) == 1) t = __shfl_up_sync(FULL, v, 1);
+        if constexpr (ex(Q) == -1) t = __shfl_down_sync(FULL, v, 1);
+        double(&E)[3] = ey(Q) == -1 ? EA : ey(Q) == 0 ? EB : EC;
+        E[d] += t;
+    });
+    // y exchange: what this row sends down (TA, EA: slots 0..8) and up (TC, EC: slots 9..17), in the g slots;
+    // the first row's "down" and the last row's "up" leave the CTA through the edge arrays
+    const unsigned ce = (unsigned)(i + OX) * 8u + (unsigned)blockIdx.y * px8 + (unsigned)(k + GZ) * (unsigned)C.esz8;
+    const bool first = w == 0, last = w == rows - 1;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (first) {
+            if (own) {
+                stb(A.edge[3 * d + 0], ce, TA[d][0]);
+                stb(A.edge[3 * d + 1], ce, TA[d][1]);
+                stb(A.edge[3 * d + 2], ce, EA[d]);
+            }
+        } else {
+            sg[(3 * d + 0) * T] = TA[d][0];
+            sg[(3 * d + 1) * T] = TA[d][1];
+            sg[(3 * d + 2) * T] = EA[d];
+        }
+        if (last) {
+            if (own) {
+                stb(A.edge[9 + 3 * d + 0], ce, TC[d][0]);
+                stb(A.edge[9 + 3 * d + 1], ce, TC[d][1]);
+                stb(A.edge[9 + 3 * d + 2], ce, EC[d]);
+            }
+        } else {
+            sg[(9 + 3 * d + 0) * T] = TC[d][0];
+            sg[(9 + 3 * d + 1) * T] = TC[d][1];
+            sg[(9 + 3 * d + 2) * T] = EC[d];
+        }
+    }
+    __syncthreads();
+    if (own) {
+        const double* up = sg + 32;   // row j+1: its e_y = -1 terms arrive here
+        const double* dn = sg - 32;   // row j-1: its e_y = +1 terms
+        double r[3], x[3], y[3], e[3];  // per destination plane k-1, k, k+1: rho, jx, jy, e2 (y-complete up to the edges)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const double ua = last ? 0.0 : up[(3 * d + 0) * T], dc = first ? 0.0 : dn[(9 + 3 * d + 0) * T];
+            const double ux = last ? 0.0 : up[(3 * d + 1) * T], dx = first ? 0.0 : dn[(9 + 3 * d + 1) * T];
+            const double ue = last ? 0.0 : up[(3 * d + 2) * T], de = first ? 0.0 : dn[(9 + 3 * d + 2) * T];
+            r[d] = TB[d][0] + ua + dc;
+            x[d] = TB[d][1] + ux + dx;
+            y[d] = dc - ua;
+            e[d] = EB[d] + ue + de;
+        }
+        if (kk == 0) {
+            // even plane: what goes down leaves now; its own sums and what goes up wait for the partner plane
+            stb(A.part[5], c, r[0]);
+            stb(A.part[6], c, x[0]);
+            stb(A.part[7], c, y[0]);
+            stb(A.part[8], c, e[0]);
+            sk[0 * T] = r[1], sk[1 * T] = x[1], sk[2 * T] = y[1], sk[3 * T] = e[1];
+            sk[4 * T] = r[2], sk[5 * T] = x[2], sk[6 * T] = y[2], sk[7 * T] = e[2];
+            c_first = c;
+        } else {
+            // odd plane: own = its e_z = 0 sums + the even plane's e_z = +1 sums; what it sends up leaves
+            stb(A.part[0], c, r[1] + sk[4 * T]);
+            stb(A.part[1], c, x[1] + sk[5 * T]);
+            stb(A.part[2], c, y[1] + sk[6 * T]);
+            stb(A.part[3], c, sk[4 * T]);            // jz: e_z = +1 terms
+            stb(A.part[4], c, e[1] + sk[7 * T]);
+            stb(A.part[5], c, r[2]);
+            stb(A.part[6], c, x[2]);
+            stb(A.part[7], c, y[2]);
+            stb(A.part[8], c, e[2]);
+            // the even plane: its own e_z = 0 sums + this plane's e_z = -1 sums
+            stb(A.part[0], c_first, sk[0 * T] + r[0]);
+            stb(A.part[1], c_first, sk[1 * T] + x[0]);
+            stb(A.part[2], c_first, sk[2 * T] + y[0]);
+            stb(A.part[3], c_first, -r[0]);          // jz: e_z = -1 terms
+            stb(A.part[4], c_first, sk[3 * T] + e[0]);
+        }
+    }
+    __syncthreads();  // the exchange slots are the next plane's g slots
+    }
+}
+
+// q-corrections from the 9-word layout of k_collide_tile_pair
+__global__ void __launch_bounds__(128, 6) k_qcorr_combine_pair(const double* __restrict__ fin, const double* __restrict__ gin,
+                                                               const uint32_t* __restrict__ nbr, const double* __restrict__ part,
+                                                               const double* __restrict__ edge, int W, long long esz,
+                                                               double* __restrict__ qc, const __grid_constant__ Layout L,
+                                                               const __grid_constant__ Phys P, int k0)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.nx) return;
+    const int j = blockIdx.y, k = blockIdx.z + k0;
+    const long long c = L.cell(i, j, k);
+    const long long n = L.sq;
+    const uint32_t m = nbr[c];
+    if (!(m & 1u)) return;
+    const bool inner = (L.wrap[0] || (i > 0 && i < L.nx - 1)) && (L.wrap[1] || (j > 0 && j < L.ny - 1)) &&
+                       (L.wrap[2] || (k > 0 && k < L.nz - 1)) && k >= 0 && k < L.nz;
+    if (!(inner && m == ALL_FLUID)) {
+        qcorr_cell<true>(fin, gin, nbr, qc, L, P, i, j, k);
+        return;
+    }
+    const int km = k == 0 ? L.nz - 1 : k - 1, kp = k == L.nz - 1 ? 0 : k + 1;
+    // even plane: the plane below (odd) sent up; odd plane: the plane above (even) sent down
+    const bool even = (k & 1) == 0;
+    const long long co = L.cell(i, j, even ? km : kp);
+    const double ro = part[5 * n + co];
+    double rho = part[0 * n + c] + ro;
+    double jx = part[1 * n + c] + part[6 * n + co];
+    double jy = part[2 * n + c] + part[7 * n + co];
+    double jz = part[3 * n + c] + (even ? ro : -ro);
+    double e2 = part[4 * n + c] + part[8 * n + co];
+    {
+        const int jr = j / W, w = j - jr * W, nyr = (L.ny + W - 1) / W;
+        const int rows = min(W, L.ny - jr * W);
+        const long long en = esz * (L.nz + 2 * GZ);
+        auto add_edge = [&](int side, int jrs, double sgn) {
+            const long long e0 = (long long)(i + OX) + (long long)jrs * L.px;
+            const double am = edge[(side * 9 + 6) * en + e0 + (long long)(km + GZ) * esz];
+            const double a0 = edge[(side * 9 + 3) * en + e0 + (long long)(k + GZ) * esz];
+            const double ap = edge[(side * 9 + 0) * en + e0 + (long long)(kp + GZ) * esz];
+            rho += am + a0 + ap;
+            jz += am - ap;
+            jy += sgn * (am + a0 + ap);
+            jx += edge[(side * 9 + 7) * en + e0 + (long long)(km + GZ) * esz] +
+                  edge[(side * 9 + 4) * en + e0 + (long long)(k + GZ) * esz] +
+                  edge[(side * 9 + 1) * en + e0 + (long long)(kp + GZ) * esz];
+            e2 += edge[(side * 9 + 8) * en + e0 + (long long)(km + GZ) * esz] +
+                  edge[(side * 9 + 5) * en + e0 + (long long)(k + GZ) * esz] +
+                  edge[(side * 9 + 2) * en + e0 + (long long)(kp + GZ) * esz];
+        };
+        if (w == 0) add_edge(1, jr == 0 ? nyr - 1 : jr - 1, 1.0);
+        if (w == rows - 1) add_edge(0, jr == nyr - 1 ? 0 : jr + 1, -1.0);
+    }
+    const Prim s = primitives(rho, jx, jy, jz, e2, P);
+    qc[c] = s.qcx;
+    qc[n + c] = s.qcy;
+    qc[2 * n + c] = s.qcz;
+}
+
 // q-corrections of the post-stream state from the carried plane sums (interior cells) or by pulling the
 // populations (everything k_collide_carry could not serve)
 __global__ void __launch_bounds__(128, 6) k_qcorr_combine(const double* __restrict__ fin, const double* __restrict__ gin,
@@ -1706,6 +1975,50 @@ int launch_collide_tile(const Layout& L, const Phys& P, const CarryPlan& C, int 
         k_collide_tile<12><<<grid, 32 * 12, sm, st>>>(A, nbr, flag, L, P, Ce, k0);
     else
         k_collide_tile<8><<<grid, 32 * 8, sm, st>>>(A, nbr, flag, L, P, Ce, k0);
+    return 1;
+}
+
+int launch_collide_tile_pair(const Layout& L, const Phys& P, const CarryPlan& C, const double* fin, const double* gin,
+                             double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag, const double* qc,
+                             double* part, double* edge, cudaStream_t st, int ka, int kb)
+{
+    if (L.sq * 8 >= (1LL << 32)) return -1;
+    constexpr int W = 6;
+    if (kb <= ka) ka = 0, kb = L.nz;
+    if ((ka & 1) || ((kb - ka) & 1)) return -2;  // pairs (2b, 2b+1)
+    CarryPtrs A;
+    for (int q = 0; q < NQ; ++q) {
+        A.fin[q] = fin + (long long)q * L.sq;
+        A.gin[q] = gin + (long long)q * L.sq;
+        A.fout[q] = fout + (long long)q * L.sq;
+        A.gout[q] = gout + (long long)q * L.sq;
+    }
+    for (int d = 0; d < 3; ++d) A.qc[d] = qc + (long long)d * L.sq;
+    for (int w = 0; w < CARRY_WORDS; ++w) A.part[w] = part + (long long)w * L.sq;
+    CarryPlan Ce = C;
+    const long long esz = carry_edge_plane(L, W);
+    Ce.esz8 = (unsigned)(esz * 8);
+    for (int e = 0; e < CARRY_EDGE_WORDS; ++e) A.edge[e] = edge + (long long)e * esz * (L.nz + 2 * GZ);
+    const size_t sm = (size_t)(NQ + PAIR_KEEP_SLOTS) * 32 * W * 8;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_collide_tile_pair<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        attr_done = true;
+    }
+    const dim3 grid(C.nxc, (L.ny + W - 1) / W, (kb - ka) / 2);
+    k_collide_tile_pair<6><<<grid, 32 * W, sm, st>>>(A, nbr, flag, L, P, Ce, ka);
+    return 1;
+}
+
+int launch_qcorr_combine_pair(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr,
+                              const double* part, const double* edge, double* qc, cudaStream_t st, int ka, int kb)
+{
+    const int bx = block_x(L);
+    int k0 = (L.lo[2] > L.dlo[2]) ? -1 : 0;
+    int k1 = (L.lo[2] + L.nz - 1 < L.dhi[2]) ? L.nz : L.nz - 1;
+    if (kb > ka) k0 = ka, k1 = kb - 1;
+    dim3 grid((L.nx + bx - 1) / bx, L.ny, k1 - k0 + 1);
+    k_qcorr_combine_pair<<<grid, bx, 0, st>>>(fin, gin, nbr, part, edge, 6, carry_edge_plane(L, 6), qc, L, P, k0);
     return 1;
 }
 

@@ -88,6 +88,12 @@ int launch_collide_tile(const Layout& L, const Phys& P, const CarryPlan& C, int 
                         const double* gin, double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag,
                         const double* qc, double* part, double* edge, cudaStream_t st, int ka = 0, int kb = 0);
 // doubles per plane of one edge array for `rows` rows per CTA (the array spans nz + 2 GZ planes)
+// the tile carry step with the z sum of plane pairs completed on chip (9 part words instead of 12; even nz)
+int launch_collide_tile_pair(const Layout& L, const Phys& P, const CarryPlan& C, const double* fin, const double* gin,
+                             double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag, const double* qc,
+                             double* part, double* edge, cudaStream_t st, int ka = 0, int kb = 0);
+int launch_qcorr_combine_pair(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr,
+                              const double* part, const double* edge, double* qc, cudaStream_t st, int ka = 0, int kb = 0);
 long long carry_edge_plane(const Layout& L, int rows);
 int carry_tile_rows(int rows);  // supported rows per CTA: 4, 6 (default), 8, 12
 // edge / edge_rows: the edge arrays k_collide_tile wrote (nullptr after k_collide_carry)

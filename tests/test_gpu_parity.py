@@ -26,6 +26,7 @@ CARRY_ENV = {
     "tile-12rows": (5, {"MBL_ROWS": "12"}),
     "tile-4rows": (5, {"MBL_ROWS": "4"}),
     "lean": (6, {"MBL_MINB": "4"}),
+    "pair": (7, {}),
 }
 TUNING_VARS = ("MBL_KY", "MBL_OWN", "MBL_MINB", "MBL_ROWS")
 
@@ -53,9 +54,9 @@ def new_lbm(deck_text, is_fluid=None, overrides=None, variant=None):
 
 # fused: mbl_step with the persistent TMA kernel (variant 1, the default), its two job types as two
 # launches (2), or the two plain kernels (0); unfused: the reference-granular operator sequence
-@pytest.mark.parametrize("fused", [1, 2, 3, 0, "carry", "carry-ky5-own28", "tile", "tile-6rows-own28", "lean", None],
+@pytest.mark.parametrize("fused", [1, 2, 3, 0, "carry", "carry-ky5-own28", "tile", "tile-6rows-own28", "lean", "pair", None],
                          ids=["fused-tma", "twopass-tma", "fused-plain", "twopass-plain", "carry", "carry-ky5-own28", "tile",
-                              "tile-6rows-own28", "lean", "unfused"])
+                              "tile-6rows-own28", "lean", "pair", "unfused"])
 @pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_cuda_vs_reference_golden(case, fused):
     z, deck_text, steps = load_golden(case)
@@ -110,9 +111,9 @@ def test_geometry_matches_reference_is_fluid():
 
 
 @pytest.mark.parametrize("variant", [1, 3, 0, "carry", "carry-ky5-own28", "carry-ky1", "tile", "tile-6rows-own28", "tile-12rows",
-                                     "tile-4rows"],
+                                     "tile-4rows", "pair"],
                          ids=["fused-tma", "fused-plain", "twopass-plain", "carry", "carry-ky5-own28", "carry-ky1", "tile",
-                              "tile-6rows-own28", "tile-12rows", "tile-4rows"])
+                              "tile-6rows-own28", "tile-12rows", "tile-4rows", "pair"])
 @pytest.mark.parametrize("case", ["chcyl", "pressure", "slip", "tg12"])
 def test_random_state_vs_oracle(oracle_mod, case, variant):
     """seeded random perturbation of f, g and a random solid mask, 3 steps, all boundary types"""
@@ -162,7 +163,7 @@ def test_eb_forces_and_vorticity_vs_oracle(oracle_mod):
     lbm.close()
 
 
-@pytest.mark.parametrize("variant", [0, "carry", "tile"], ids=["twopass-plain", "carry", "tile"])
+@pytest.mark.parametrize("variant", [0, "carry", "tile", "pair"], ids=["twopass-plain", "carry", "tile", "pair"])
 def test_tg64_vs_oracle_and_conservation(oracle_mod, variant):
     """BASELINE config 1 (TG 64^3): 3 steps against the oracle, then size-independent properties"""
     O = oracle_mod
@@ -439,7 +440,7 @@ def test_graph_replay_is_bit_identical(case, variant):
 
 
 @pytest.mark.parametrize("case,n_cell", [("tg12", "67 45 13"), ("tg12", "31 7 9"), ("sod48", "75 3 5"), ("sod48", "130 2 2")])
-@pytest.mark.parametrize("variant", [None, 0, "carry"], ids=["default-tile", "twopass", "carry"])
+@pytest.mark.parametrize("variant", [None, 0, "carry", "pair"], ids=["default-tile", "twopass", "carry", "pair"])
 def test_odd_box_sizes_vs_oracle(oracle_mod, case, n_cell, variant):
     """box sizes that are no multiple of the warp strip (30 cells), the CTA height (6 rows) or the march length"""
     O = oracle_mod
