@@ -79,3 +79,24 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "liboracle" not in text and "marbles_oracle" not in text, f
+
+
+def test_plain_c_caller(tmp_path):
+    """tests/c/cabi_smoke.c: a C program that includes include/marbles_b200.h and links the library (no Python,
+    no torch in the process).  Without a GPU mbl_create must fail loudly ("no CPU path"); with one the program
+    steps a small periodic box and checks mass conservation."""
+    import shutil
+    import subprocess
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    libdir = os.path.join(root, "marbles_b200")
+    exe = str(tmp_path / "cabi_smoke")
+    subprocess.run([gcc, "-O1", "-I", os.path.join(root, "include"), os.path.join(here, "c", "cabi_smoke.c"), "-o", exe,
+                    "-L", libdir, "-lmarbles_b200", f"-Wl,-rpath,{libdir}", "-lm"], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.startswith(("NO_DEVICE", "DEVICE")), res.stdout
+    print(res.stdout.strip())
