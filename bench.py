@@ -282,7 +282,8 @@ def main():
     peak, peak_src = measured_peak_gbs()
     collide_ms = kms[2] / max(nrec.value, 1)
     kname = {0: "k_collide_lean (pull + collide)", 1: "k_fused (q-correction + collide jobs)", 2: "k_fused (collide jobs)",
-             3: "k_fused_plain (q-correction + collide jobs)", 4: "k_collide_carry", 5: "k_collide_tile", 6: "k_collide_lean", 7: "k_collide_tile_pair"}[lbm.variant]
+             3: "k_fused_plain (q-correction + collide jobs)", 4: "k_collide_carry", 5: "k_collide_tile", 6: "k_collide_lean", 7: "k_collide_tile_pair",
+             8: "k_march (pull + q-correction + collide, one kernel)"}[lbm.variant]
     vname = {0: "two kernels (k_qcorr, k_collide_lean)", 1: "one persistent TMA-pipelined kernel per step",
              2: "persistent TMA kernel, two launches (q-correction, collide)",
              3: "one persistent kernel per step, plain loads",
@@ -290,12 +291,13 @@ def main():
                 "step's moment row sums)",
              5: "carry step without marching: k_qcorr_combine + k_collide_tile",
              6: "two kernels, collide with g staged through shared memory (k_qcorr, k_collide_lean)",
-             7: "tile carry step with plane pairs: k_qcorr_combine_pair + k_collide_tile_pair"}[lbm.variant]
+             7: "tile carry step with plane pairs: k_qcorr_combine_pair + k_collide_tile_pair",
+             8: "march step: one kernel per step, z-marching CTAs, q-corrections recomputed on a one-cell halo"}[lbm.variant]
     achieved = BYTES_PER_CELL * lbm.ncells / (collide_ms * 1e-3) / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            tkey = {0: "k_collide_lean", 6: "k_collide_lean", 5: "k_collide_tile", 4: "k_collide_carry", 7: "k_collide_tile_pair"}.get(lbm.variant)
+            tkey = {0: "k_collide_lean", 6: "k_collide_lean", 5: "k_collide_tile", 4: "k_collide_carry", 7: "k_collide_tile_pair", 8: "k_march"}.get(lbm.variant)
             traffic = json.load(fh).get("dram_bytes_per_launch_512", {}).get(tkey) if n == 512 else None
     except Exception:
         pass

@@ -13,7 +13,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmarbles_b200.so")
-SOURCES = ["kernels.cu", "fused.cu", "api.cu"]
+SOURCES = ["kernels.cu", "march.cu", "api.cu"]
+# negative-result kernels of round 1 (step variants 1-4): only with MBL_EXPERIMENTS=1
+EXPERIMENT_SOURCES = [os.path.join("experiments", "fused.cu")]
+EXPERIMENT_HEADERS = [os.path.join("experiments", "experiments.cuh")]
 HEADERS = ["lattice.cuh", "kernels.cuh", os.path.join("..", "..", "include", "marbles_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -32,24 +35,42 @@ def stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS + EXPERIMENT_SOURCES + EXPERIMENT_HEADERS]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> str:
+    """One nvcc per source file, in parallel, then one link step."""
     if not force and not stale():
         return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + (extra or []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    if os.path.exists("/usr/bin/g++"):
-        cmd += ["-ccbin", "/usr/bin/g++"]
-    if verbose:
-        print(" ".join(cmd))
+    from concurrent.futures import ThreadPoolExecutor
+    experiments = os.environ.get("MBL_EXPERIMENTS") == "1"
+    sources = SOURCES + (EXPERIMENT_SOURCES if experiments else [])
+    flags = NVCC_FLAGS + (["-DMBL_EXPERIMENTS"] if experiments else []) + (extra or [])
+    ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src: str):
+        obj = os.path.join(objdir, os.path.basename(src).replace(".cu", ".o"))
+        cmd = [nvcc()] + [f for f in flags if f != "-shared"] + ccbin + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        if verbose:
+            print(" ".join(cmd))
+        return obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=len(sources)) as ex:
+        results = list(ex.map(compile_one, sources))
+    for obj, res in results:
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("nvcc failed")
+        if verbose:
+            print(res.stdout + res.stderr)
+    cmd = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + ccbin + ["-o", LIB] + [o for o, _ in results]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed")
-    if verbose:
-        print(res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed")
     return LIB
 
 

@@ -82,6 +82,7 @@ struct mbl_ctx {
     int variant = 5;
     int uw = 128, band_rows = 16, lag_per_cta = 4;  // variants 1-3 tuning (MBL_UW / MBL_BAND / MBL_LAG)
     int carry_own = 30, carry_ky = 32, carry_minb = 2, carry_rows = 6;  // variant 4 tuning (MBL_OWN / MBL_KY / MBL_MINB)
+    int march_rows = 6, march_zm = 64, march_pipe = 1;  // variant 8 tuning (MBL_MROWS / MBL_ZM / MBL_PIPE)
     int sm_count = 148;
     cudaStream_t s_up = nullptr, s_down = nullptr;  // copy streams of the pipelined mbl_step_host
     cudaStream_t s_capture = nullptr;               // CUDA graph capture of step pairs
@@ -154,7 +155,7 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
     mark();
     // all-periodic level: the plain kernels wrap source indices themselves and no ghost cell is read;
     // otherwise (and for the TMA kernels, which stage un-wrapped rows) fill every ghost cell first
-    const bool tma = ctx->variant == 1 || ctx->variant == 2;
+    const bool tma = ctx->variant == 1 || ctx->variant == 2;  // experiments only
     Layout Lk = lv.L;
     if (tma) Lk.wrap[0] = Lk.wrap[1] = Lk.wrap[2] = 0;
     const bool need_ghosts = !(Lk.wrap[0] && Lk.wrap[1]);
@@ -164,8 +165,16 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
     // the carry kernels address a component with 32-bit byte offsets: larger boxes take the two-kernel step
     int variant = ctx->variant;
     if (variant == 7 && ((lv.L.nz & 1) || carry_tile_rows(ctx->carry_rows) != 6)) variant = 5;  // pairs need an even nz
-    if ((variant == 4 || variant == 5 || variant == 7) && lv.L.sq * 8 >= (1LL << 32)) variant = 0;
-    if (variant == 4 || variant == 5 || variant == 7) {
+    if ((variant == 4 || variant == 5 || variant == 7 || variant == 8) && lv.L.sq * 8 >= (1LL << 32)) variant = 0;
+    if (variant == 8 && !macro) {
+        // march step: ONE kernel, no q-correction pass and no carried sums (march.cu)
+        mark();
+        const int nl = launch_march(Lk, lv.P, ctx->march_rows, ctx->march_zm, ctx->march_pipe, lv.p.f[a], lv.p.g[a],
+                                    lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, st);
+        if (nl < 0) return fail("march step: launch failed (%d)", nl);
+        ctx->launches += nl;
+        lv.carry_valid = false;
+    } else if (variant == 5 || variant == 7 || variant == 4) {
         // carry step: q-corrections from the partial sums the previous collide left behind (first step, or after
         // anything else wrote the lattice: the full q-correction pass)
         if (!lv.part) CU(cudaMalloc(&lv.part, (size_t)CARRY_WORDS * lv.L.sq * sizeof(double)));
@@ -186,14 +195,21 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
             lv.carry_valid = false;
         } else {
             const CarryPlan C = make_carry_plan(Lk, ctx->carry_own, ctx->carry_ky);
-            const int nl = variant == 7
-                               ? launch_collide_tile_pair(Lk, lv.P, C, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr,
-                                                          lv.p.flag, lv.p.qc, lv.part, lv.edge, st)
-                           : variant == 4
-                               ? launch_collide_carry(Lk, lv.P, C, ctx->carry_minb, lv.p.f[a], lv.p.g[a], lv.p.f[b],
-                                                      lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, lv.part, st)
-                               : launch_collide_tile(Lk, lv.P, C, W, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b],
-                                                     lv.p.nbr, lv.p.flag, lv.p.qc, lv.part, lv.edge, st);
+            int nl;
+            if (variant == 7) {
+                nl = launch_collide_tile_pair(Lk, lv.P, C, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
+                                              lv.p.qc, lv.part, lv.edge, st);
+            } else if (variant == 4) {
+#ifdef MBL_EXPERIMENTS
+                nl = launch_collide_carry(Lk, lv.P, C, ctx->carry_minb, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b],
+                                          lv.p.nbr, lv.p.flag, lv.p.qc, lv.part, st);
+#else
+                nl = -1;
+#endif
+            } else {
+                nl = launch_collide_tile(Lk, lv.P, C, W, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
+                                         lv.p.qc, lv.part, lv.edge, st);
+            }
             lv.edge_rows = variant == 4 ? 0 : W;
             lv.part_pair = variant == 7;
             if (nl < 0) return fail("carry step: a lattice component exceeds 4 GB (32-bit byte offsets)");
@@ -208,12 +224,15 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
                                            lv.p.nbr, lv.p.flag, lv.p.qc, st);
         if (nl < 0) return fail("lean collide: a lattice component exceeds 4 GB (32-bit byte offsets)");
         ctx->launches += nl;
-    } else if (variant == 0 || variant == 6) {
+    } else if (variant == 0 || variant == 6 || variant == 8) {
         ctx->launches += launch_qcorr(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st);
         mark();
         ctx->launches += launch_collide(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
                                         lv.p.qc, macro, true, st);
-    } else if (variant == 2) {
+        lv.carry_valid = false;
+    }
+#ifdef MBL_EXPERIMENTS
+    else if (variant == 2) {
         ctx->launches += launch_fused(Lk, lv.P, ctx->uw, ctx->band_rows, ctx->lag_per_cta, 0, ctx->sm_count, lv.p.f[a],
                                       lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, macro, lv.counters, st);
         mark();
@@ -229,6 +248,11 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
         ctx->launches += launch_fused(Lk, lv.P, ctx->uw, ctx->band_rows, ctx->lag_per_cta, 2, ctx->sm_count, lv.p.f[a],
                                       lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, lv.p.qc, macro, lv.counters, st);
     }
+#else
+    else {
+        return fail("step variant %d is an experiment: rebuild the library with MBL_EXPERIMENTS=1", variant);
+    }
+#endif
     mark();
     if (ctx->timing) ctx->timed_steps++;
     lv.cur = b;
@@ -269,6 +293,9 @@ int mbl_create(const mbl_params* params, int device, mbl_ctx** out)
     if (const char* e = getenv("MBL_LAG")) c->lag_per_cta = atoi(e) > 0 ? atoi(e) : 4;
     if (const char* e = getenv("MBL_ROWS")) c->carry_rows = atoi(e);
     if (const char* e = getenv("MBL_HOST_CHUNK")) c->host_chunk = atoi(e);
+    if (const char* e = getenv("MBL_MROWS")) c->march_rows = atoi(e) == 4 ? 4 : 6;
+    if (const char* e = getenv("MBL_ZM")) c->march_zm = atoi(e) > 0 ? atoi(e) : 64;
+    if (const char* e = getenv("MBL_PIPE")) c->march_pipe = atoi(e) != 0;
     if (const char* e = getenv("MBL_GRAPH")) c->use_graphs = atoi(e) != 0;
     if (const char* e = getenv("MBL_OWN")) c->carry_own = atoi(e) == 28 ? 28 : 30;
     if (const char* e = getenv("MBL_KY")) c->carry_ky = atoi(e) > 0 ? atoi(e) : 32;
@@ -398,7 +425,9 @@ int mbl_level_define(mbl_ctx* ctx, int lev, const mbl_level_geom* g, void* devic
     lv.p.flag = (uint8_t*)(lv.base + m.flag);
     lv.cur = 0;
     CU(cudaMalloc(&lv.d_red, 8 * sizeof(double)));
+#ifdef MBL_EXPERIMENTS
     CU(cudaMalloc(&lv.counters, fused_counter_ints(lv.L) * sizeof(int)));
+#endif
     // zero everything once: pad cells are never written by the kernels
     CU(cudaMemsetAsync(lv.base, 0, m.total, ctx->stream));
     lv.defined = true;
@@ -778,7 +807,9 @@ int mbl_step_split(mbl_ctx* ctx, int lev, int part)
     }
     const bool from_sums = tile && lv.carry_valid && lv.edge_rows == W && !lv.part_pair;
     const CarryPlan C = make_carry_plan(L, ctx->carry_own, ctx->carry_ky);
+    const bool march = ctx->variant == 8 && L.sq * 8 < (1LL << 32);  // one kernel: the q-correction ranges are empty
     auto q = [&](int ka, int kb) {
+        if (march) return;
         if (from_sums)
             ctx->launches += launch_qcorr_combine(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.part, lv.edge, W, lv.p.qc, st,
                                                   ka, kb);
@@ -786,7 +817,10 @@ int mbl_step_split(mbl_ctx* ctx, int lev, int part)
             ctx->launches += launch_qcorr(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st, ka, kb);
     };
     auto c = [&](int ka, int kb) {
-        if (tile)
+        if (march)
+            ctx->launches += launch_march(L, lv.P, ctx->march_rows, ctx->march_zm, ctx->march_pipe, lv.p.f[a], lv.p.g[a],
+                                          lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, st, ka, kb);
+        else if (tile)
             ctx->launches += launch_collide_tile(L, lv.P, C, W, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr,
                                                  lv.p.flag, lv.p.qc, lv.part, lv.edge, st, ka, kb);
         else
@@ -1078,7 +1112,11 @@ int mbl_get_variant(mbl_ctx* ctx) { return ctx ? ctx->variant : -1; }
 int mbl_set_variant(mbl_ctx* ctx, int variant)
 {
     if (!ctx) return fail("null context");
-    if (variant < 0 || variant > 7) return fail("variant %d is not available", variant);
+    if (variant < 0 || variant > 8) return fail("variant %d is not available", variant);
+#ifndef MBL_EXPERIMENTS
+    if (variant >= 1 && variant <= 4)
+        return fail("step variant %d is an experiment: rebuild the library with MBL_EXPERIMENTS=1", variant);
+#endif
     ctx->variant = variant;
     for (int l = 0; l < MAX_LEVELS; ++l) ctx->lev[l].carry_valid = false;
     return 0;

@@ -26,7 +26,7 @@
 // Bounce-back (source cell solid) falls back to a direct global load of the cell's own opposite
 // population.  The staged rows are read un-wrapped, so this kernel needs every ghost cell (periodic images
 // included) filled by the ghost kernels (kernels.cu) beforehand.
-#include "kernels.cuh"
+#include "../kernels.cuh"
 
 #include <cstdio>
 

@@ -101,6 +101,28 @@ int launch_qcorr_combine(const Layout& L, const Phys& P, const double* fin, cons
                          const double* part, const double* edge, int edge_rows, double* qc, cudaStream_t st, int ka = 0,
                          int kb = 0);
 
+// march.cu: the whole step as ONE kernel.  A CTA marches through the planes of a z-chunk, every population is
+// pulled once (cp.async into shared memory, where it stays for one iteration), the q-corrections of the face
+// neighbours are recomputed on a one-cell halo (two extra rows, two extra lanes) instead of being stored.
+struct MarchPtrs {
+    const double* fin[NQ];
+    const double* gin[NQ];
+    double* fout[NQ];
+    double* gout[NQ];
+};
+struct MarchPlan {
+    int own, halo;  // cells a warp owns and halo lanes on each side (own + 2 halo = 32)
+    int nxc;        // column strips per row
+    int zm;         // planes per march
+    int ka, kb;     // plane range [ka, kb) of the launch
+};
+MarchPlan make_march_plan(const Layout& L, int zm, int ka, int kb);
+size_t march_smem_bytes(int rows);
+// rows: productive rows per CTA (4, 6 or 7); zm: planes per march; pipe: pull plane k+2 behind the arithmetic of plane k
+int launch_march(const Layout& L, const Phys& P, int rows, int zm, int pipe, const double* fin, const double* gin,
+                 double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag, cudaStream_t st, int ka = 0,
+                 int kb = 0);
+
 int launch_stream(const Layout& L, const double* fin, const double* gin, double* fout, double* gout,
                   const uint32_t* nbr, cudaStream_t st);
 int launch_macrodata(const Layout& L, const Phys& P, const double* f, const double* g, const uint8_t* flag,

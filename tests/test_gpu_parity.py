@@ -27,8 +27,20 @@ CARRY_ENV = {
     "tile-4rows": (5, {"MBL_ROWS": "4"}),
     "lean": (6, {"MBL_MINB": "4"}),
     "pair": (7, {}),
+    # variant 8: the one-kernel march step (march.cu): default tuning, small CTAs with short ragged marches, and
+    # without the early pull of the next plane
+    "march": (8, {}),
+    "march-4rows-zm3": (8, {"MBL_MROWS": "4", "MBL_ZM": "3"}),
+    "march-nopipe-zm5": (8, {"MBL_PIPE": "0", "MBL_ZM": "5"}),
 }
-TUNING_VARS = ("MBL_KY", "MBL_OWN", "MBL_MINB", "MBL_ROWS")
+TUNING_VARS = ("MBL_KY", "MBL_OWN", "MBL_MINB", "MBL_ROWS", "MBL_MROWS", "MBL_ZM", "MBL_PIPE")
+# variants 1-4 are round-1 experiments, compiled only with MBL_EXPERIMENTS=1
+import os as _os
+EXPERIMENTS = _os.environ.get("MBL_EXPERIMENTS") == "1"
+
+
+def with_experiments(default, extra):
+    return list(default) + (list(extra) if EXPERIMENTS else [])
 
 
 def variant_of(v):
@@ -54,9 +66,10 @@ def new_lbm(deck_text, is_fluid=None, overrides=None, variant=None):
 
 # fused: mbl_step with the persistent TMA kernel (variant 1, the default), its two job types as two
 # launches (2), or the two plain kernels (0); unfused: the reference-granular operator sequence
-@pytest.mark.parametrize("fused", [1, 2, 3, 0, "carry", "carry-ky5-own28", "tile", "tile-6rows-own28", "lean", "pair", None],
-                         ids=["fused-tma", "twopass-tma", "fused-plain", "twopass-plain", "carry", "carry-ky5-own28", "tile",
-                              "tile-6rows-own28", "lean", "pair", "unfused"])
+@pytest.mark.parametrize("fused", with_experiments([0, "tile", "tile-6rows-own28", "lean", "pair", "march", "march-4rows-zm3",
+                                                    "march-nopipe-zm5", None], [1, 2, 3, "carry", "carry-ky5-own28"]),
+                         ids=lambda v: {0: "twopass-plain", 1: "fused-tma", 2: "twopass-tma", 3: "fused-plain",
+                                        None: "unfused"}.get(v, str(v)))
 @pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_cuda_vs_reference_golden(case, fused):
     z, deck_text, steps = load_golden(case)
@@ -110,10 +123,10 @@ def test_geometry_matches_reference_is_fluid():
         assert np.array_equal(a, z["is_fluid"].astype(np.int32)), case
 
 
-@pytest.mark.parametrize("variant", [1, 3, 0, "carry", "carry-ky5-own28", "carry-ky1", "tile", "tile-6rows-own28", "tile-12rows",
-                                     "tile-4rows", "pair"],
-                         ids=["fused-tma", "fused-plain", "twopass-plain", "carry", "carry-ky5-own28", "carry-ky1", "tile",
-                              "tile-6rows-own28", "tile-12rows", "tile-4rows", "pair"])
+@pytest.mark.parametrize("variant", with_experiments([0, "tile", "tile-6rows-own28", "tile-12rows", "tile-4rows", "pair", "march",
+                                                      "march-4rows-zm3", "march-nopipe-zm5"],
+                                                     [1, 3, "carry", "carry-ky5-own28", "carry-ky1"]),
+                         ids=lambda v: {0: "twopass-plain", 1: "fused-tma", 3: "fused-plain"}.get(v, str(v)))
 @pytest.mark.parametrize("case", ["chcyl", "pressure", "slip", "tg12"])
 def test_random_state_vs_oracle(oracle_mod, case, variant):
     """seeded random perturbation of f, g and a random solid mask, 3 steps, all boundary types"""
@@ -163,7 +176,8 @@ def test_eb_forces_and_vorticity_vs_oracle(oracle_mod):
     lbm.close()
 
 
-@pytest.mark.parametrize("variant", [0, "carry", "tile", "pair"], ids=["twopass-plain", "carry", "tile", "pair"])
+@pytest.mark.parametrize("variant", with_experiments([0, "tile", "pair", "march"], ["carry"]),
+                         ids=lambda v: "twopass-plain" if v == 0 else str(v))
 def test_tg64_vs_oracle_and_conservation(oracle_mod, variant):
     """BASELINE config 1 (TG 64^3): 3 steps against the oracle, then size-independent properties"""
     O = oracle_mod
@@ -190,7 +204,8 @@ def test_tg64_vs_oracle_and_conservation(oracle_mod, variant):
     lbm.close()
 
 
-@pytest.mark.parametrize("variant", [0, "carry", "tile"], ids=["twopass-plain", "carry", "tile"])
+@pytest.mark.parametrize("variant", with_experiments([0, "tile", "march"], ["carry"]),
+                         ids=lambda v: "twopass-plain" if v == 0 else str(v))
 def test_full_size_conservation_256(variant):
     """periodic 256^3 (largest size the test box does in seconds): mass/energy conservation of
     stream+collide and agreement of the fused and un-fused operator sequences"""
@@ -209,7 +224,8 @@ def test_full_size_conservation_256(variant):
 
 @pytest.mark.parametrize("case,nz,world", [("tg12", 12, 2), ("tg12", 13, 3), ("sod48", 8, 2), ("chcyl", None, 2),
                                            ("pressure", None, 2)])
-@pytest.mark.parametrize("variant", [0, "carry-ky5-own28", "tile-6rows-own28"], ids=["twopass-plain", "carry-ky5-own28", "tile-6rows-own28"])
+@pytest.mark.parametrize("variant", with_experiments([0, "tile-6rows-own28", "march-4rows-zm3"], ["carry-ky5-own28"]),
+                         ids=lambda v: "twopass-plain" if v == 0 else str(v))
 def test_two_slabs_match_single_box(case, nz, world, variant):
     """the multi-rank scheme (z-slabs, ONE exchange of two ghost planes per step, q-correction of the first
     ghost plane recomputed locally, BC ghosts of neighbour-owned planes) on one device: the assembled slabs
@@ -298,7 +314,7 @@ def test_step_host_matches_device_step(case, ov, chunk, ng):
     b.close()
 
 
-@pytest.mark.parametrize("variant", [0, 5], ids=["twopass", "tile"])
+@pytest.mark.parametrize("variant", [0, 5, 8], ids=["twopass", "tile", "march"])
 @pytest.mark.parametrize("nz,world", [(16, 2), (27, 3)])
 def test_overlapped_slab_step_matches_single_box(nz, world, variant):
     """mbl_step_split (boundary planes first, exchange of the written buffers' boundary planes, interior planes)
@@ -440,7 +456,8 @@ def test_graph_replay_is_bit_identical(case, variant):
 
 
 @pytest.mark.parametrize("case,n_cell", [("tg12", "67 45 13"), ("tg12", "31 7 9"), ("sod48", "75 3 5"), ("sod48", "130 2 2")])
-@pytest.mark.parametrize("variant", [None, 0, "carry", "pair"], ids=["default-tile", "twopass", "carry", "pair"])
+@pytest.mark.parametrize("variant", with_experiments([None, 0, "pair", "march", "march-4rows-zm3"], ["carry"]),
+                         ids=lambda v: {None: "default", 0: "twopass"}.get(v, str(v)))
 def test_odd_box_sizes_vs_oracle(oracle_mod, case, n_cell, variant):
     """box sizes that are no multiple of the warp strip (30 cells), the CTA height (6 rows) or the march length"""
     O = oracle_mod
@@ -499,3 +516,44 @@ def test_slab_vorticity_matches_single_box(case, nz, world):
     assert np.abs(a[:4] - b[:4]).max() <= 1e-13 * max(np.abs(a[:4]).max(), 1e-30)
     slabs.close()
     single.close()
+
+
+@pytest.mark.parametrize("variant", [None, "march"], ids=["default", "march"])
+@pytest.mark.parametrize("n", [256, 512])
+def test_full_size_values_tiled_tg_vs_oracle(oracle_mod, n, variant):
+    """Value-level pin of the benchmarked size (BASELINE config 3, 512^3; and 256^3): the box is initialised with a
+    Taylor-Green state of wavelength 64 cells (omega = n/64), i.e. an (n/64)^3 tiling of one 64^3 period.  After 3
+    steps every 64^3 tile must equal the 64^3 oracle run of one period (same dx, same coordinates) on the cells
+    further than 4 cells from a tile face: the oracle's 64^3 DOMAIN differences QCorr one-sidedly at its edges
+    (Utilities.H:292-309) where the big box differences centrally, and that difference travels one cell per
+    stream plus one per gradient.  Covers the 32-bit byte offsets of the default kernels over the whole box."""
+    import torch
+    O = oracle_mod
+    need = 2.6 * 54 * 8 * n ** 3
+    if torch.cuda.get_device_properties(0).total_memory < need:
+        pytest.skip("not enough device memory")
+    _, deck_text, _ = load_golden("tg12")
+    t = n // 64
+    ov_small = ["amr.n_cell = 64 64 64", "geometry.prob_lo = -1.0 -1.0 -1.0",
+                f"geometry.prob_hi = {-1.0 + 2.0 / t!r} {-1.0 + 2.0 / t!r} {-1.0 + 2.0 / t!r}",
+                f"ic_taylorgreen.omega = {t}.0 {t}.0 {t}.0"]
+    ov_big = [f"amr.n_cell = {n} {n} {n}", f"ic_taylorgreen.omega = {t}.0 {t}.0 {t}.0"]
+    o = O.Oracle(O.lbm_setup(O.parse_deck(None, deck_text.splitlines() + ov_small)))
+    o.initialize()
+    nsteps, m = 3, 5
+    o.step(nsteps)
+    lbm = new_lbm(deck_text, overrides=ov_big, variant=variant)
+    assert abs(lbm.inp.dx[0] - o.p.dx[0]) == 0.0
+    lbm.step(nsteps)
+    worst = 0.0
+    for name, get, ref in (("f", lbm.get_f, o.f_valid), ("g", lbm.get_g, o.g_valid)):
+        a = get(0)
+        scale = float(np.abs(ref).max())
+        for q in range(27):
+            tiles = a[q].reshape(t, 64, t, 64, t, 64)[:, m:-m, :, m:-m, :, m:-m]
+            r = ref[q][m:-m, m:-m, m:-m][None, :, None, :, None, :]
+            worst = max(worst, float(np.abs(tiles - r).max()) / scale)
+        del a
+    print(f"tiled TG {n}^3: worst {worst:.2e} of scale over {t ** 3} tiles")
+    assert worst <= 1e-12 * nsteps, worst
+    lbm.close()
