@@ -13,9 +13,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmarbles_b200.so")
-SOURCES = ["kernels.cu", "march.cu", "api.cu"]
-# negative-result kernels of round 1 (step variants 1-4): only with MBL_EXPERIMENTS=1
-EXPERIMENT_SOURCES = [os.path.join("experiments", "fused.cu")]
+SOURCES = ["kernels.cu", "api.cu"]
+# negative-result kernels (step variants 1-4 of round 1, the march step 8 of round 2): only with MBL_EXPERIMENTS=1
+EXPERIMENT_SOURCES = [os.path.join("experiments", "fused.cu"), os.path.join("experiments", "march.cu")]
 EXPERIMENT_HEADERS = [os.path.join("experiments", "experiments.cuh")]
 HEADERS = ["lattice.cuh", "kernels.cuh", os.path.join("..", "..", "include", "marbles_b200.h")]
 NVCC_FLAGS = [

@@ -166,15 +166,18 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
     int variant = ctx->variant;
     if (variant == 7 && ((lv.L.nz & 1) || carry_tile_rows(ctx->carry_rows) != 6)) variant = 5;  // pairs need an even nz
     if ((variant == 4 || variant == 5 || variant == 7 || variant == 8) && lv.L.sq * 8 >= (1LL << 32)) variant = 0;
+#ifdef MBL_EXPERIMENTS
     if (variant == 8 && !macro) {
-        // march step: ONE kernel, no q-correction pass and no carried sums (march.cu)
+        // march step: ONE kernel, no q-correction pass and no carried sums (experiments/march.cu)
         mark();
         const int nl = launch_march(Lk, lv.P, ctx->march_rows, ctx->march_zm, ctx->march_pipe, lv.p.f[a], lv.p.g[a],
                                     lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, st);
         if (nl < 0) return fail("march step: launch failed (%d)", nl);
         ctx->launches += nl;
         lv.carry_valid = false;
-    } else if (variant == 5 || variant == 7 || variant == 4) {
+    } else
+#endif
+    if (variant == 5 || variant == 7 || variant == 4) {
         // carry step: q-corrections from the partial sums the previous collide left behind (first step, or after
         // anything else wrote the lattice: the full q-correction pass)
         if (!lv.part) CU(cudaMalloc(&lv.part, (size_t)CARRY_WORDS * lv.L.sq * sizeof(double)));
@@ -807,7 +810,11 @@ int mbl_step_split(mbl_ctx* ctx, int lev, int part)
     }
     const bool from_sums = tile && lv.carry_valid && lv.edge_rows == W && !lv.part_pair;
     const CarryPlan C = make_carry_plan(L, ctx->carry_own, ctx->carry_ky);
+#ifdef MBL_EXPERIMENTS
     const bool march = ctx->variant == 8 && L.sq * 8 < (1LL << 32);  // one kernel: the q-correction ranges are empty
+#else
+    const bool march = false;
+#endif
     auto q = [&](int ka, int kb) {
         if (march) return;
         if (from_sums)
@@ -817,10 +824,14 @@ int mbl_step_split(mbl_ctx* ctx, int lev, int part)
             ctx->launches += launch_qcorr(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.p.qc, true, st, ka, kb);
     };
     auto c = [&](int ka, int kb) {
-        if (march)
+#ifdef MBL_EXPERIMENTS
+        if (march) {
             ctx->launches += launch_march(L, lv.P, ctx->march_rows, ctx->march_zm, ctx->march_pipe, lv.p.f[a], lv.p.g[a],
                                           lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag, st, ka, kb);
-        else if (tile)
+            return;
+        }
+#endif
+        if (tile)
             ctx->launches += launch_collide_tile(L, lv.P, C, W, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr,
                                                  lv.p.flag, lv.p.qc, lv.part, lv.edge, st, ka, kb);
         else
@@ -1114,7 +1125,7 @@ int mbl_set_variant(mbl_ctx* ctx, int variant)
     if (!ctx) return fail("null context");
     if (variant < 0 || variant > 8) return fail("variant %d is not available", variant);
 #ifndef MBL_EXPERIMENTS
-    if (variant >= 1 && variant <= 4)
+    if ((variant >= 1 && variant <= 4) || variant == 8)
         return fail("step variant %d is an experiment: rebuild the library with MBL_EXPERIMENTS=1", variant);
 #endif
     ctx->variant = variant;

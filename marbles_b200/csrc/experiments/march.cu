@@ -1,4 +1,4 @@
-// march.cu -- ONE kernel per step: pull-stream + q-correction + collide with every population touched once.
+// march.cu -- (round-2 experiment, variant 8; built only with MBL_EXPERIMENTS=1) ONE kernel per step: pull-stream + q-correction + collide with every population touched once.
 //
 // The collision of a cell needs the gradient of QCorr, a function of the POST-STREAM moments of its six face
 // neighbours (LBM.cpp:893-901, 959-991).  The two-kernel step reads every population twice for that, the carry
@@ -17,9 +17,16 @@
 // pulls at the same time (L2 hits); DRAM sees 54 reads + 54 writes per cell, plus two priming planes per chunk.
 // Nothing else is stored: no QCorr array, no partial sums, no second kernel.
 //
+// MEASURED (profiles/r02/march_variants_512.json, traffic_512_march.csv): parity-green, DRAM traffic 147 GB per
+// 512^3 step instead of 161 GB, but 49.7 ms per step against 28.8 ms for the tile carry step: two planes of
+// populations per cell in shared memory leave room for 8 warps per SM (202 KB per CTA), the collide arithmetic of
+// 1.5 productive warps per scheduler is latency-bound (issue slots 19 % busy, DRAM 33 %), and the halo re-reads miss
+// L2 (CTAs of one wave drift apart by more planes than L2 holds).  Kept as the record of why the populations
+// cannot simply stay on chip between the two touches.
+//
 // Every cell's QCorr comes from the exact pull (bounce-back through the 27-bit mask, ghost cells filled by the
 // ghost kernels on non-periodic levels), so walls, EB cells and slab edges take the same path as the interior.
-#include "kernels.cuh"
+#include "../kernels.cuh"
 
 namespace mbl {
 

@@ -66,8 +66,8 @@ def new_lbm(deck_text, is_fluid=None, overrides=None, variant=None):
 
 # fused: mbl_step with the persistent TMA kernel (variant 1, the default), its two job types as two
 # launches (2), or the two plain kernels (0); unfused: the reference-granular operator sequence
-@pytest.mark.parametrize("fused", with_experiments([0, "tile", "tile-6rows-own28", "lean", "pair", "march", "march-4rows-zm3",
-                                                    "march-nopipe-zm5", None], [1, 2, 3, "carry", "carry-ky5-own28"]),
+@pytest.mark.parametrize("fused", with_experiments([0, "tile", "tile-6rows-own28", "lean", "pair", None],
+                                                   [1, 2, 3, "carry", "carry-ky5-own28", "march", "march-4rows-zm3", "march-nopipe-zm5"]),
                          ids=lambda v: {0: "twopass-plain", 1: "fused-tma", 2: "twopass-tma", 3: "fused-plain",
                                         None: "unfused"}.get(v, str(v)))
 @pytest.mark.parametrize("case", GOLDEN_CASES)
@@ -123,9 +123,9 @@ def test_geometry_matches_reference_is_fluid():
         assert np.array_equal(a, z["is_fluid"].astype(np.int32)), case
 
 
-@pytest.mark.parametrize("variant", with_experiments([0, "tile", "tile-6rows-own28", "tile-12rows", "tile-4rows", "pair", "march",
-                                                      "march-4rows-zm3", "march-nopipe-zm5"],
-                                                     [1, 3, "carry", "carry-ky5-own28", "carry-ky1"]),
+@pytest.mark.parametrize("variant", with_experiments([0, "tile", "tile-6rows-own28", "tile-12rows", "tile-4rows", "pair"],
+                                                     [1, 3, "carry", "carry-ky5-own28", "carry-ky1", "march", "march-4rows-zm3",
+                                                      "march-nopipe-zm5"]),
                          ids=lambda v: {0: "twopass-plain", 1: "fused-tma", 3: "fused-plain"}.get(v, str(v)))
 @pytest.mark.parametrize("case", ["chcyl", "pressure", "slip", "tg12"])
 def test_random_state_vs_oracle(oracle_mod, case, variant):
@@ -176,7 +176,7 @@ def test_eb_forces_and_vorticity_vs_oracle(oracle_mod):
     lbm.close()
 
 
-@pytest.mark.parametrize("variant", with_experiments([0, "tile", "pair", "march"], ["carry"]),
+@pytest.mark.parametrize("variant", with_experiments([0, "tile", "pair"], ["carry", "march"]),
                          ids=lambda v: "twopass-plain" if v == 0 else str(v))
 def test_tg64_vs_oracle_and_conservation(oracle_mod, variant):
     """BASELINE config 1 (TG 64^3): 3 steps against the oracle, then size-independent properties"""
@@ -204,7 +204,7 @@ def test_tg64_vs_oracle_and_conservation(oracle_mod, variant):
     lbm.close()
 
 
-@pytest.mark.parametrize("variant", with_experiments([0, "tile", "march"], ["carry"]),
+@pytest.mark.parametrize("variant", with_experiments([0, "tile"], ["carry", "march"]),
                          ids=lambda v: "twopass-plain" if v == 0 else str(v))
 def test_full_size_conservation_256(variant):
     """periodic 256^3 (largest size the test box does in seconds): mass/energy conservation of
@@ -224,7 +224,7 @@ def test_full_size_conservation_256(variant):
 
 @pytest.mark.parametrize("case,nz,world", [("tg12", 12, 2), ("tg12", 13, 3), ("sod48", 8, 2), ("chcyl", None, 2),
                                            ("pressure", None, 2)])
-@pytest.mark.parametrize("variant", with_experiments([0, "tile-6rows-own28", "march-4rows-zm3"], ["carry-ky5-own28"]),
+@pytest.mark.parametrize("variant", with_experiments([0, "tile-6rows-own28"], ["carry-ky5-own28", "march-4rows-zm3"]),
                          ids=lambda v: "twopass-plain" if v == 0 else str(v))
 def test_two_slabs_match_single_box(case, nz, world, variant):
     """the multi-rank scheme (z-slabs, ONE exchange of two ghost planes per step, q-correction of the first
@@ -314,7 +314,7 @@ def test_step_host_matches_device_step(case, ov, chunk, ng):
     b.close()
 
 
-@pytest.mark.parametrize("variant", [0, 5, 8], ids=["twopass", "tile", "march"])
+@pytest.mark.parametrize("variant", with_experiments([0, 5], [8]), ids=lambda v: {0: "twopass", 5: "tile", 8: "march"}[v])
 @pytest.mark.parametrize("nz,world", [(16, 2), (27, 3)])
 def test_overlapped_slab_step_matches_single_box(nz, world, variant):
     """mbl_step_split (boundary planes first, exchange of the written buffers' boundary planes, interior planes)
@@ -456,7 +456,7 @@ def test_graph_replay_is_bit_identical(case, variant):
 
 
 @pytest.mark.parametrize("case,n_cell", [("tg12", "67 45 13"), ("tg12", "31 7 9"), ("sod48", "75 3 5"), ("sod48", "130 2 2")])
-@pytest.mark.parametrize("variant", with_experiments([None, 0, "pair", "march", "march-4rows-zm3"], ["carry"]),
+@pytest.mark.parametrize("variant", with_experiments([None, 0, "pair"], ["carry", "march", "march-4rows-zm3"]),
                          ids=lambda v: {None: "default", 0: "twopass"}.get(v, str(v)))
 def test_odd_box_sizes_vs_oracle(oracle_mod, case, n_cell, variant):
     """box sizes that are no multiple of the warp strip (30 cells), the CTA height (6 rows) or the march length"""
@@ -518,7 +518,7 @@ def test_slab_vorticity_matches_single_box(case, nz, world):
     single.close()
 
 
-@pytest.mark.parametrize("variant", [None, "march"], ids=["default", "march"])
+@pytest.mark.parametrize("variant", with_experiments([None], ["march"]), ids=lambda v: "default" if v is None else str(v))
 @pytest.mark.parametrize("n", [256, 512])
 def test_full_size_values_tiled_tg_vs_oracle(oracle_mod, n, variant):
     """Value-level pin of the benchmarked size (BASELINE config 3, 512^3; and 256^3): the box is initialised with a
