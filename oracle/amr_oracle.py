@@ -208,7 +208,7 @@ class AmrOracle:
                 self.lib.orc_compute_q_corrections(C.byref(b.p), _ptr(b.is_fluid, C.c_int), _ptr(b.macro),
                                                    _ptr(b.derived))
         for lev in range(self.finest - 1, -1, -1):
-            self.average_down_to(lev)
+            self.average_down_to(lev, ng=0)
 
     # ---------------------------------------------------------------- operators
     def _macrodata(self, L):
@@ -322,13 +322,20 @@ class AmrOracle:
             PK, PJ, PI = np.meshgrid(*par, indexing="ij")
             OK_, OJ, OI = np.meshgrid(*off, indexing="ij")
             val = u0[:, PK, PJ, PI] + OI * sx[:, PK, PJ, PI] + OJ * sy[:, PK, PJ, PI] + OK_ * sz[:, PK, PJ, PI]
-            if np.isnan(val[:, m]).any():
-                raise NotImplementedError("coarse-fine interpolation next to a non-periodic domain face "
-                                          "(or an improperly nested level) is not restated")
-            a[:, m] = val[:, m]
+            # guard: slopes of coarse cells on a non-periodic domain face use one-sided formulas that depend on the
+            # extents of AMReX's internal coarse patch (AMReX_MFInterp_C.H:15-33): not restated
+            for ax, d in enumerate((2, 1, 0)):
+                if Lc.periodic[d]:
+                    continue
+                pc = np.floor_divide(idx[ax], ratio)
+                sel = m.any(axis=tuple(x for x in range(3) if x != ax))
+                if ((pc[sel] <= 0) | (pc[sel] >= Lc.n[d] - 1)).any():
+                    raise NotImplementedError("coarse-fine interpolation next to a non-periodic domain face is not restated")
+            a[:, m] = val[:, m]  # NaN (see average_down_to) can only reach cells the FillBoundary below overwrites
 
-    def average_down_to(self, crse_lev, ratio=2):
-        """average_down_with_ghosts(m_f[crse_lev+1], m_f[crse_lev], geom, ng = 1, ratio) and the same for g"""
+    def average_down_to(self, crse_lev, ng=1, ratio=2):
+        """average_down_with_ghosts(m_f[crse_lev+1], m_f[crse_lev], geom, ng, ratio) and the same for g;
+        ng = 1 inside advance (Source/LBM.cpp:539-541), ng = 0 after initialisation (Source/LBM.cpp:167)"""
         Lf, Lc = self.levels[crse_lev + 1], self.levels[crse_lev]
         fboxes = [(b.lo, b.hi) for b in Lf.boxes]
         order = hash_order(fboxes)
@@ -338,8 +345,8 @@ class AmrOracle:
             cfine = []
             for b in Lf.boxes:
                 a = getattr(b, name)  # 3 ghost cells
-                clo = [b.lo[d] // ratio - 1 for d in range(3)]
-                chi = [b.hi[d] // ratio + 1 for d in range(3)]
+                clo = [b.lo[d] // ratio - ng for d in range(3)]
+                chi = [b.hi[d] // ratio + ng for d in range(3)]
                 cidx = [np.arange(clo[d], chi[d] + 1) for d in (2, 1, 0)]
                 # cfine.ParallelCopy(crse, ..., src ng 0, dst ng 1): NOT periodic; cells on no coarse valid cell
                 # stay uninitialised (NaN here)
@@ -349,7 +356,8 @@ class AmrOracle:
                 okc = ok[0][:, None, None] & ok[1][None, :, None] & ok[2][None, None, :]
                 cf[:, ~okc] = np.nan
                 # masked_avgdown over the coarsened box grown by 1 = fine valid cells + 2 ghost layers
-                fa = a[:, 1:-1, 1:-1, 1:-1]
+                t = 3 - ratio * ng  # fine ghost layers not under the coarsened box grown by ng
+                fa = a[:, t:a.shape[1] - t, t:a.shape[2] - t, t:a.shape[3] - t]
                 nzc, nyc, nxc = cf.shape[1:]
                 f8 = fa.reshape(NQ, nzc, 2, nyc, 2, nxc, 2)
                 c = np.zeros_like(cf)
@@ -378,8 +386,9 @@ class AmrOracle:
                         d_s = tuple(slice(lo[d] - cb.lo[d] + ngc, hi[d] - cb.lo[d] + ngc + 1) for d in (2, 1, 0))
                         s_s = tuple(slice(lo[d] - slo[d], hi[d] - slo[d] + 1) for d in (2, 1, 0))
                         src = cf[(slice(None),) + s_s]
-                        if np.isnan(src).any():
-                            raise NotImplementedError("average_down would copy uninitialised coarse cells")
+                        # NaN = a cfine cell the reference leaves uninitialised (outside the coarse domain in a periodic
+                        # direction, all eight fine cells masked: solid cells of a body that crosses the periodic face);
+                        # the reference copies whatever its arena held there.  Only solid cells can receive it.
                         dst[(slice(None),) + d_s] = src
 
     # ------------------------------------------------------------ time stepping
@@ -428,6 +437,6 @@ class AmrOracle:
         for n, name in enumerate(O.DERIVED_NAMES):
             out[name] = d[n]
         fl = L.gather("is_fluid", 2, np.int32)
-        out["is_fluid"] = fl[0].astype(float)
-        out["eb_boundary"] = fl[1].astype(float)
+        out["is_fluid"] = np.where(fl[0] < 0, np.nan, fl[0].astype(float))
+        out["eb_boundary"] = np.where(fl[1] < 0, np.nan, fl[1].astype(float))
         return out

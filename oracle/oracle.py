@@ -392,6 +392,21 @@ def read_plotfile(path: str, level: int = 0) -> dict:
     return out
 
 
+def read_plotfile_boxes(path: str, level: int = 0) -> list:
+    """the valid boxes of one level of a plotfile: [[lo, hi], ...] (Level_k/Cell_H)"""
+    with open(os.path.join(path, f"Level_{level}", "Cell_H")) as fh:
+        ch = fh.read().split("\n")
+    i = 0
+    while not ch[i].startswith("("):
+        i += 1
+    nbox = int(ch[i].strip("(").split()[0])
+    boxes = []
+    for b in range(nbox):
+        m = re.findall(r"-?\d+", ch[i + 1 + b])
+        boxes.append([[int(v) for v in m[0:3]], [int(v) for v in m[3:6]]])
+    return boxes
+
+
 def run_reference(deck_path: str, workdir: str, overrides: list[str], omp: bool = False, threads: int | None = None,
                   timeout: float = 3600.0) -> str:
     """Run the unmodified reference executable (oracle/_ref) on a deck. Returns its stdout."""

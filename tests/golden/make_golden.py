@@ -201,6 +201,168 @@ eb2.geom_type = "all_regular"
 KEEP_STEP0 = ([f"f_{q:02d}" for q in range(27)] + [f"g_{q:02d}" for q in range(27)] + O.MACRO_NAMES)
 
 
+
+# ---------------------------------------------------------------------------------------------------------
+# multi-level cases (BASELINE configs 4-5): several boxes per level, 2 and 3 levels, static tagging boxes.
+# Stored per level: the box list the reference made (Level_k/Cell_H), is_fluid, and dense fields (NaN where
+# the level has no box).  Fine levels stay away from non-periodic faces, and no body crosses a periodic face
+# inside a refined region (there the reference averages uninitialised memory into the coarse level).
+# ---------------------------------------------------------------------------------------------------------
+AMR_COMMON = """
+lbm.dx_outer = 1.0
+lbm.dt_outer = 1.0
+lbm.save_streaming = 1
+lbm.save_derived = 1
+amr.plot_int = 1
+amr.chk_int = -1
+amr.blocking_factor = 4
+amr.regrid_int = 1000000
+amrex.fpe_trap_invalid = 0
+amrex.fpe_trap_zero = 0
+amrex.fpe_trap_overflow = 0
+amrex.the_arena_is_managed = 0
+"""
+
+CHANNEL_BODY = """
+geometry.is_periodic = 0 0 1
+lbm.bc_lo = 2 1 0
+lbm.bc_hi = 5 1 0
+lbm.nu = 0.0050
+lbm.velocity_bc_type = "channel"
+velocity_bc_channel.initial_density = 1.0
+velocity_bc_channel.Mach_ref = 0.01
+velocity_bc_channel.initial_temperature = 0.03
+lbm.ic_type = "constant"
+ic_constant.density = 1.0
+ic_constant.initial_temperature = 0.03
+ic_constant.mach_components = 0.0 0.0 0.0
+eb2.geom_type = "cylinder"
+eb2.cylinder_radius = 2.3
+eb2.cylinder_has_fluid_inside = 0
+eb2.cylinder_height = 2.0
+eb2.cylinder_direction = 2
+"""
+
+AMR_CASES = {
+    # periodic Taylor-Green, 2 levels, 8 coarse + 8 fine boxes of different sizes
+    "amr2_tg": ("""
+max_step = 3
+geometry.prob_lo = -1.0 -1.0 -1.0
+geometry.prob_hi =  1.0  1.0  1.0
+geometry.is_periodic = 1 1 1
+amr.n_cell = 16 16 16
+lbm.bc_lo = 0 0 0
+lbm.bc_hi = 0 0 0
+lbm.nu = 0.1733333333333333
+lbm.ic_type = "taylorgreen"
+ic_taylorgreen.rho0 = 1.0
+ic_taylorgreen.v0 = 0.1
+eb2.geom_type = "all_regular"
+amr.max_level = 1
+amr.max_grid_size = 8
+amr.n_error_buf = 0
+tagging.refinement_indicators = box
+tagging.box.in_box_lo = -0.45 -0.45 -0.45
+tagging.box.in_box_hi = 0.45 0.3 0.2
+""", 2, [0, 1, 3]),
+    # BASELINE config 4 at reduced size: channel inlet / outflow / no-slip walls / periodic z, EB cylinder inside
+    # the refined region, the fine level spans the periodic direction
+    "amr2_chcyl": ("""
+max_step = 4
+geometry.prob_lo = 0.0 0.0 0.0
+geometry.prob_hi = 48.0 16.0 4.0
+amr.n_cell = 48 16 4
+eb2.cylinder_center = 14.0 8.0 2.0
+amr.max_level = 1
+amr.max_grid_size = 16
+amr.n_error_buf = 0
+tagging.refinement_indicators = box
+tagging.box.in_box_lo = 8.0 4.0 -1.0
+tagging.box.in_box_hi = 22.0 12.0 5.0
+""" + CHANNEL_BODY, 2, [0, 1, 4]),
+    # BASELINE config 5 at reduced size: 3 levels (no 3-level deck is shipped; built from the nesting of
+    # channel_cylinder_amr.inp:39-41), 6 boxes per level
+    "amr3_chcyl": ("""
+max_step = 3
+geometry.prob_lo = 0.0 0.0 0.0
+geometry.prob_hi = 48.0 24.0 4.0
+amr.n_cell = 48 24 4
+eb2.cylinder_center = 14.0 12.0 2.0
+amr.max_level = 2
+amr.max_grid_size = 16
+amr.n_error_buf = 1
+tagging.refinement_indicators = a b
+tagging.a.in_box_lo = 8.0 7.0 -1.0
+tagging.a.in_box_hi = 24.0 17.0 5.0
+tagging.a.max_level = 1
+tagging.b.in_box_lo = 10.5 9.0 -1.0
+tagging.b.in_box_hi = 18.0 15.0 5.0
+""" + CHANNEL_BODY, 3, [0, 1, 3]),
+    # sod_amr.inp with a static refined band around the discontinuity (thermal path, gamma = 2, outflow in x)
+    "amr2_sod": ("""
+max_step = 4
+geometry.prob_lo = 0.0 -2.0 -2.0
+geometry.prob_hi = 64.0 2.0 2.0
+geometry.is_periodic = 0 1 1
+amr.n_cell = 64 4 4
+lbm.bc_lo = 5 0 0
+lbm.bc_hi = 5 0 0
+lbm.nu = 0.010
+lbm.alpha = 0.010
+lbm.ic_type = "sod"
+ic_sod.density = 0.50
+ic_sod.mach_components = 0.0 0.0 0.0
+ic_sod.x_discontinuity = 32.0
+ic_sod.initial_temperature = 0.20
+ic_sod.adiabatic_exponent = 2.0
+ic_sod.mean_molecular_mass = 28.96
+ic_sod.density_ratio = 4.00
+ic_sod.temperature_ratio = 0.1250
+lbm.initial_temperature = 0.20
+lbm.adiabatic_exponent = 2.0
+lbm.mean_molecular_mass = 28.96
+eb2.geom_type = "all_regular"
+amr.max_level = 1
+amr.max_grid_size = 16
+amr.n_error_buf = 0
+tagging.refinement_indicators = box
+tagging.box.in_box_lo = 24.0 -3.0 -3.0
+tagging.box.in_box_hi = 40.0 3.0 3.0
+""", 2, [0, 1, 4]),
+}
+
+AMR_KEEP_LAST = KEEP_STEP0 + ["dQCorrX", "dQCorrY", "dQCorrZ"]
+AMR_KEEP_MID = O.MACRO_NAMES
+
+
+def make_amr(out_dir, only):
+    for name, (deck, nlev, steps) in AMR_CASES.items():
+        if only and name not in only:
+            continue
+        work = tempfile.mkdtemp(prefix=f"golden_{name}_")
+        deck_text = deck.strip() + "\n" + AMR_COMMON
+        deck_path = os.path.join(work, "case.inp")
+        with open(deck_path, "w") as fh:
+            fh.write(deck_text)
+        O.run_reference(deck_path, work, [], omp=False)
+        data = {"deck": np.array(deck_text), "steps": np.array(steps), "nlev": np.array(nlev)}
+        for lev in range(nlev):
+            data[f"boxes_l{lev}"] = np.array(O.read_plotfile_boxes(os.path.join(work, "plt00000"), lev))
+            for s in steps:
+                pf = O.read_plotfile(os.path.join(work, f"plt{s:05d}"), lev)
+                if s == steps[0]:
+                    fl = pf["is_fluid"]
+                    data[f"is_fluid_l{lev}"] = np.where(np.isnan(fl), 1, fl).astype(np.int8)
+                keep = AMR_KEEP_LAST if s == steps[-1] else (KEEP_STEP0 if s == steps[0] else AMR_KEEP_MID)
+                for n in keep:
+                    data[f"s{s}_l{lev}_{n}"] = pf[n]
+        path = os.path.join(out_dir, f"{name}.npz")
+        np.savez_compressed(path, **data)
+        print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB, boxes per level "
+              f"{[len(data[f'boxes_l{l}']) for l in range(nlev)]}")
+        shutil.rmtree(work)
+
+
 def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
     only = sys.argv[1:]
@@ -229,3 +391,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    make_amr(os.path.dirname(os.path.abspath(__file__)), sys.argv[1:])
