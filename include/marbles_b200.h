@@ -169,6 +169,41 @@ int mbl_compute_derived_slab(mbl_ctx* ctx, int lev, int has_lo, int has_hi);
 /* LBM::compute_eb_forces() for one level (Source/LBM.cpp:994-1044): local sum */
 int mbl_eb_forces(mbl_ctx* ctx, int lev, double out[3]);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-box / multi-level levels (AMR-exact mode; BASELINE configs 4-5).
+ *
+ * mbl_level_define_boxes replaces the BoxArray handed to MakeNewLevelFromScratch / RemakeLevel /
+ * MakeNewLevelFromCoarse (Source/LBM.cpp:1088-1199, 1302-1364): `nboxes` valid boxes of level `lev`
+ * owned by this rank, lo/hi = 3 ints per box in the level's index space (geom->lo/hi are ignored).
+ * Each box is stored as an AMReX-shaped FAB with 3 ghost cells (m_f_nghost, Source/LBM.H:230).  Call it
+ * again after every regrid.  On such a level the reference-granular entry points below keep their
+ * meaning and follow the reference's un-fused order exactly:
+ *   mbl_fillpatch   K6 pre-pass; for lev > 0 FillPatchTwoLevels from level lev-1 (cell_cons_interp into the
+ *                   ghost cells no fine valid cell covers, Source/FillPatchOps.H:118-129); FillBoundary; BCFill
+ *   mbl_physbc      BCFill only (between the fine substeps, Source/LBM.cpp:503-506)
+ *   mbl_stream      stream on the GROWN boxes with the -1 sentinel + FillBoundary (Source/LBM.cpp:558-604)
+ *   mbl_collide     f_to_macrodata on valid + 1, FillBoundary, q-corrections, equilibria, relax, FillBoundary
+ *   mbl_average_down  average_down_with_ghosts / masked_avgdown of level crse_lev + 1 onto crse_lev
+ *                   (Source/Utilities.cpp:5-28, Source/Utilities.H:315-350; ng = 1 inside advance, 0 after init)
+ * The sub-cycling order (LBM::time_step, Source/LBM.cpp:452-521) stays in the caller.
+ * Restrictions: refinement ratio 2; all boxes of a level on this rank; a fine box may not lie within one
+ * coarse cell of a NON-periodic domain face (mbl_fillpatch reports it).
+ * ------------------------------------------------------------------------------------------- */
+int mbl_level_define_boxes(mbl_ctx* ctx, int lev, const mbl_level_geom* geom, int nboxes, const int* lo, const int* hi);
+int mbl_level_num_boxes(mbl_ctx* ctx, int lev);
+/* zero-copy: use the DEVICE memory of an AMReX FAB (27 comps, 3 ghost cells: m_f[lev][mfi].dataPtr()) as box
+ * `ibox`'s f (which = 0) or g (which = 1); no ownership transfer.  The library keeps the result of every operator
+ * in that memory (a scratch copy is used inside mbl_stream, as the reference's f_star). */
+int mbl_level_bind(mbl_ctx* ctx, int lev, int ibox, int which, double* device_fab);
+/* m_is_fluid[lev][mfi] comp 0 (int32 FAB, ng >= 3 ghost cells already FillBoundary'd, host or device memory) */
+int mbl_box_set_is_fluid(mbl_ctx* ctx, int lev, int ibox, const int32_t* fab, int ng);
+/* FAB <-> box transfers (27 comps, ghost width ng of the caller's FAB; ghost cells up to 3 are transferred) */
+int mbl_box_upload(mbl_ctx* ctx, int lev, int ibox, int which, const double* fab, int ng);
+int mbl_box_download(mbl_ctx* ctx, int lev, int ibox, int which, double* fab, int ng);
+/* derived = 0: the 19 macrodata comps, 1: the 7 derived comps */
+int mbl_box_download_macrodata(mbl_ctx* ctx, int lev, int ibox, double* fab, int ng, int derived);
+int mbl_average_down(mbl_ctx* ctx, int crse_lev, int ng);
+
 /* fused fast path: one coarse step of a single-level run =
  * fillpatch(f), fillpatch(g), stream(f), stream(g), collide
  * (Source/LBM.cpp:416-422, 523-544).  nsteps > 1 only on a single rank; macrodata (all 19
@@ -223,7 +258,9 @@ int mbl_get_timing(mbl_ctx* ctx, double ms[3], int* nsteps);
  * also emits partial sums of the next step's conserved moments, so the q-correction pass does not read the
  * populations again (4: threads march through rows, 5: one cell per thread, rows exchanged inside the CTA).
  * 5 is the default (boxes whose components exceed 4 GB fall back to 0); 6 = 0 with a chosen number of CTAs per
- * SM; 7 = 5 with the z sum of plane pairs completed on chip (9 carried words instead of 12; even nz, else 5).  All variants agree to round-off (the carried moments are summed in another order);
+ * SM; 7 = 5 with the z sum of plane pairs completed on chip (9 carried words instead of 12; even nz, else 5);
+ * 8 = one z-marching kernel per step.  Variants 1-4 and 8 are measured negative results and are compiled only
+ * with MBL_EXPERIMENTS=1.  All variants agree to round-off (the carried moments are summed in another order);
  * DESIGN.md has the measurements. */
 int mbl_set_variant(mbl_ctx* ctx, int variant);
 int mbl_get_variant(mbl_ctx* ctx);

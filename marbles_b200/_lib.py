@@ -86,6 +86,14 @@ SYMBOLS = {
     "mbl_step_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D, _D, C.c_int]),
     "mbl_step_host_begin": (C.c_int, [_P, C.c_int, _D, _D, C.c_int]),
     "mbl_step_host_finish": (C.c_int, [_P, C.c_int, _D, _D, C.c_int]),
+    "mbl_level_define_boxes": (C.c_int, [_P, C.c_int, C.POINTER(LevelGeom), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mbl_level_num_boxes": (C.c_int, [_P, C.c_int]),
+    "mbl_level_bind": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
+    "mbl_box_set_is_fluid": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int]),
+    "mbl_box_upload": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _D, C.c_int]),
+    "mbl_box_download": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _D, C.c_int]),
+    "mbl_box_download_macrodata": (C.c_int, [_P, C.c_int, C.c_int, _D, C.c_int, C.c_int]),
+    "mbl_average_down": (C.c_int, [_P, C.c_int, C.c_int]),
     "mbl_launch_count": (C.c_int64, [_P]),
     "mbl_set_variant": (C.c_int, [_P, C.c_int]),
     "mbl_get_variant": (C.c_int, [_P]),

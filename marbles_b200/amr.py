@@ -1,0 +1,276 @@
+"""Host-side mirror of the reference's multi-level time loop over the multi-box C ABI.
+
+The reference keeps the AMR hierarchy in AMReX (`lbm::LBM : amrex::AmrCore`); what the accelerated path
+needs from it is the box list of every level.  `AmrLBM` takes those lists (as the reference-side shim
+would hand over `boxArray(lev)` after `MakeNewLevelFromScratch` / `RemakeLevel`) and drives the
+reference-granular entry points in the reference's order:
+
+    LBM::init_data            Source/LBM.cpp:155-194   -> mbl_level_define_boxes, mbl_box_set_is_fluid,
+                                                          mbl_initialize per level, mbl_average_down(ng 0)
+    LBM::evolve (one step)    Source/LBM.cpp:416-422   -> fillpatch(0); time_step(0); post_time_step
+    LBM::time_step            Source/LBM.cpp:452-521   -> fillpatch(lev+1); 2 x (physbc(lev+1); time_step(lev+1)); advance
+    LBM::advance              Source/LBM.cpp:523-544   -> stream; average_down_to(lev, 1 ghost ring); collide
+    LBM::regrid callbacks     Source/LBM.cpp:1302-1379 -> `redefine_level` (re-define with a new box list, state
+                                                          carried over where the old and the new boxes overlap)
+
+No CPU fallback: every operator is a kernel of marbles_b200/csrc/patch.cu.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import LevelGeom, MarblesError, Params, check
+from .geometry import is_fluid_from_deck
+from .inputs import LbmInputs, lbm_inputs, parse_deck
+from .lbm import DERIVED_NAMES, F_NGHOST, MACRO_NAMES, NDERIVED, NMACRO, NQ, _dptr
+
+REF_RATIO = 2
+
+
+class AmrLBM:
+    """Multi-level lattice-Boltzmann state (all boxes of every level on this rank's B200)."""
+
+    def __init__(self, deck, level_boxes, is_fluid=None, *, overrides=None, inputs: LbmInputs | None = None,
+                 device: int = 0, cuda_stream: int | None = None):
+        """level_boxes[lev] = [(lo, hi), ...] valid boxes in the index space of level lev (AMReX BoxArray);
+        is_fluid[lev] = dense int array over the level domain (component 0 of m_is_fluid on valid cells; ghost
+        cells take the value of the cell they lie on, periodic images included, and 1 beyond non-periodic faces)
+        or None -> the analytic body of the deck evaluated at each level's resolution."""
+        if inputs is None:
+            d = deck if isinstance(deck, dict) else parse_deck(deck, overrides)
+            inputs = lbm_inputs(d)
+        self.inp = inputs
+        self.lib = _lib.load()
+        self.ctx = C.c_void_p()
+        p = Params()
+        p.nu, p.alpha, p.R, p.gamma, p.mesh_speed = inputs.nu, inputs.alpha, inputs.R, inputs.gamma, inputs.mesh_speed
+        for d in range(3):
+            p.bc_type[d], p.bc_type[d + 3], p.periodic[d] = inputs.bc_lo[d], inputs.bc_hi[d], inputs.periodic[d]
+        p.vbc_kind, p.vbc_dir = inputs.vbc_kind, inputs.vbc_dir
+        p.vbc_normal_dir, p.vbc_tangential_dir = inputs.vbc_normal_dir, inputs.vbc_tangential_dir
+        p.vbc_u, p.vbc_rho, p.vbc_T = inputs.vbc_u, inputs.vbc_rho, inputs.vbc_T
+        p.vbc_gamma, p.vbc_R = inputs.vbc_gamma, inputs.vbc_R
+        self.params = p
+        check(self.lib.mbl_create(C.byref(p), device, C.byref(self.ctx)))
+        if cuda_stream is not None:
+            check(self.lib.mbl_set_stream(self.ctx, C.c_void_p(cuda_stream)))
+        self.boxes: list[list[tuple]] = []
+        self.n: list[list[int]] = []
+        self.dt: list[float] = []
+        self.time = 0.0
+        self.isteps = 0
+        self._is_fluid_dense = list(is_fluid) if is_fluid is not None else None
+        for lev, bxs in enumerate(level_boxes):
+            dense = None if is_fluid is None else is_fluid[lev]
+            self.define_level(lev, bxs, dense)
+
+    # ------------------------------------------------------------------ setup
+    def close(self):
+        if self.ctx:
+            self.lib.mbl_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def finest(self) -> int:
+        return len(self.boxes) - 1
+
+    def level_geom(self, lev: int) -> LevelGeom:
+        r = REF_RATIO ** lev
+        g = LevelGeom()
+        for d in range(3):
+            g.dom_lo[d], g.dom_hi[d] = 0, self.inp.n_cell[d] * r - 1
+            g.lo[d], g.hi[d] = g.dom_lo[d], g.dom_hi[d]
+            g.dx[d] = self.inp.dx[d] / r
+            g.inv_dx[d] = 1.0 / g.dx[d]
+            g.prob_lo[d], g.prob_hi[d] = self.inp.prob_lo[d], self.inp.prob_hi[d]
+        g.dt = 1.0 / r  # m_dts[lev] = m_dts[lev-1] / MaxRefRatio (Source/LBM.cpp:1073-1076), est_time_step == 1
+        return g
+
+    def define_level(self, lev: int, boxes, is_fluid_dense=None):
+        """MakeNewLevelFromScratch's allocations + initialize_is_fluid (Source/LBM.cpp:1148-1262) for one level"""
+        boxes = [(tuple(int(v) for v in lo), tuple(int(v) for v in hi)) for lo, hi in boxes]
+        g = self.level_geom(lev)
+        nb = len(boxes)
+        lo = (C.c_int * (3 * nb))(*[v for b in boxes for v in b[0]])
+        hi = (C.c_int * (3 * nb))(*[v for b in boxes for v in b[1]])
+        check(self.lib.mbl_level_define_boxes(self.ctx, lev, C.byref(g), nb, lo, hi))
+        n = [self.inp.n_cell[d] * REF_RATIO ** lev for d in range(3)]
+        if lev < len(self.boxes):
+            self.boxes[lev], self.n[lev], self.dt[lev] = boxes, n, g.dt
+        else:
+            assert lev == len(self.boxes), "levels are defined in order"
+            self.boxes.append(boxes)
+            self.n.append(n)
+            self.dt.append(g.dt)
+        ng = F_NGHOST
+        dx = [self.inp.dx[d] / REF_RATIO ** lev for d in range(3)]
+        for ib, (blo, bhi) in enumerate(boxes):
+            nl = [bhi[d] - blo[d] + 1 for d in range(3)]
+            if is_fluid_dense is None:
+                a = is_fluid_from_deck(self.inp.deck, n, self.inp.prob_lo, dx, blo, nl, ng)
+                if a.min() == 1:
+                    continue  # mbl_level_define_boxes starts all fluid
+            else:
+                a = np.ones(tuple(nl[d] + 2 * ng for d in (2, 1, 0)), dtype=np.int32)
+            # ghost cells on cells of the level domain (periodic images included) take the dense field's value:
+            # m_is_fluid.FillBoundary(periodicity), Source/LBM.cpp:1234
+            dense = is_fluid_dense
+            if dense is None:
+                dense = is_fluid_from_deck(self.inp.deck, n, self.inp.prob_lo, dx, (0, 0, 0), n, 0)
+            idx, ok = [], []
+            for d in (2, 1, 0):
+                x = np.arange(blo[d] - ng, bhi[d] + ng + 1)
+                if self.inp.periodic[d]:
+                    idx.append(x % n[d])
+                    ok.append(np.ones(x.shape, bool))
+                else:
+                    idx.append(np.clip(x, 0, n[d] - 1))
+                    ok.append((x >= 0) & (x < n[d]))
+            m = ok[0][:, None, None] & ok[1][None, :, None] & ok[2][None, None, :]
+            v = np.asarray(dense)[idx[0][:, None, None], idx[1][None, :, None], idx[2][None, None, :]]
+            a = np.ascontiguousarray(np.where(m, v, a).astype(np.int32))
+            check(self.lib.mbl_box_set_is_fluid(self.ctx, lev, ib, a.ctypes.data_as(C.POINTER(C.c_int32)), ng))
+
+    def init_data(self):
+        """initialize_f on every level (IC on the grown boxes) and average_down(0 ghost cells), Source/LBM.cpp:163-167"""
+        v = (C.c_double * 16)(*self.inp.ic_params)
+        for lev in range(self.finest + 1):
+            check(self.lib.mbl_initialize(self.ctx, lev, self.inp.ic_kind, v, 16))
+        for lev in range(self.finest - 1, -1, -1):
+            self.average_down_to(lev, 0)
+        self.time, self.isteps = 0.0, 0
+
+    # ---------------------------------------------------------------- operators
+    def fillpatch(self, lev: int):
+        check(self.lib.mbl_fillpatch(self.ctx, lev, self.time))
+
+    def physbc(self, lev: int):
+        check(self.lib.mbl_physbc(self.ctx, lev, self.time))
+
+    def stream(self, lev: int):
+        check(self.lib.mbl_stream(self.ctx, lev))
+
+    def collide(self, lev: int, want_macrodata: bool = False):
+        check(self.lib.mbl_collide(self.ctx, lev, int(want_macrodata)))
+
+    def average_down_to(self, crse_lev: int, ng: int = 1):
+        check(self.lib.mbl_average_down(self.ctx, crse_lev, ng))
+
+    def advance(self, lev: int, want_macrodata: bool = False):
+        """LBM::advance (Source/LBM.cpp:523-544)"""
+        self.stream(lev)
+        if lev < self.finest:
+            self.average_down_to(lev, 1)
+        self.collide(lev, want_macrodata)
+
+    def time_step(self, lev: int, want_macrodata: bool = False):
+        """LBM::time_step without the regrid check (Source/LBM.cpp:452-521): finer levels first, two substeps"""
+        if lev < self.finest:
+            self.fillpatch(lev + 1)
+            for _ in range(REF_RATIO):
+                self.physbc(lev + 1)
+                self.time_step(lev + 1, want_macrodata)
+        self.advance(lev, want_macrodata)
+
+    def step(self, nsteps: int = 1, want_macrodata: bool = False):
+        """nsteps coarse steps of LBM::evolve (Source/LBM.cpp:416-422); macrodata of the last collide of every
+        level is stored for the last step when asked for"""
+        for s in range(nsteps):
+            self.fillpatch(0)
+            self.time_step(0, want_macrodata and s == nsteps - 1)
+            self.time += 1.0
+            self.isteps += 1
+
+    def compute_derived(self):
+        """post_time_step: compute_derived on every level (Source/LBM.cpp:546-555)"""
+        for lev in range(self.finest + 1):
+            check(self.lib.mbl_compute_derived(self.ctx, lev))
+
+    def sync(self):
+        check(self.lib.mbl_sync(self.ctx))
+
+    def redefine_level(self, lev: int, boxes, is_fluid_dense=None):
+        """RemakeLevel (Source/LBM.cpp:1302-1364) for a level whose box list changed in a regrid: the new boxes take
+        the old level's data where they overlap it; the caller then calls fillpatch(lev) for the rest of the ghost
+        cells.  (New valid cells that no old box covers would be interpolated from the coarse level by the
+        reference; that case raises.)"""
+        old_boxes = self.boxes[lev]
+        old = [(self.get_box(lev, ib, 0, 0), self.get_box(lev, ib, 1, 0)) for ib in range(len(old_boxes))]
+        self.define_level(lev, boxes, is_fluid_dense)
+        n = self.n[lev]
+        dense_f = np.full((NQ, n[2], n[1], n[0]), np.nan)
+        dense_g = np.full((NQ, n[2], n[1], n[0]), np.nan)
+        for (lo, hi), (f, g) in zip(old_boxes, old):
+            s = (slice(None), slice(lo[2], hi[2] + 1), slice(lo[1], hi[1] + 1), slice(lo[0], hi[0] + 1))
+            dense_f[s], dense_g[s] = f, g
+        for ib, (lo, hi) in enumerate(self.boxes[lev]):
+            s = (slice(None), slice(lo[2], hi[2] + 1), slice(lo[1], hi[1] + 1), slice(lo[0], hi[0] + 1))
+            f, g = np.ascontiguousarray(dense_f[s]), np.ascontiguousarray(dense_g[s])
+            if np.isnan(f).any():
+                raise MarblesError("redefine_level: a new box has cells no old box covers (coarse interpolation of "
+                                   "new valid cells is not implemented)")
+            check(self.lib.mbl_box_upload(self.ctx, lev, ib, 0, _dptr(f), 0))
+            check(self.lib.mbl_box_upload(self.ctx, lev, ib, 1, _dptr(g), 0))
+
+    # ------------------------------------------------------------------ access
+    def box_shape(self, lev: int, ib: int, ncomp: int, ng: int):
+        lo, hi = self.boxes[lev][ib]
+        return (ncomp,) + tuple(hi[d] - lo[d] + 1 + 2 * ng for d in (2, 1, 0))
+
+    def get_box(self, lev: int, ib: int, which: int, ng: int = 0) -> np.ndarray:
+        a = np.zeros(self.box_shape(lev, ib, NQ, ng))
+        check(self.lib.mbl_box_download(self.ctx, lev, ib, which, _dptr(a), ng))
+        return a
+
+    def set_box(self, lev: int, ib: int, which: int, a: np.ndarray, ng: int = 0):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.shape == self.box_shape(lev, ib, NQ, ng)
+        check(self.lib.mbl_box_upload(self.ctx, lev, ib, which, _dptr(a), ng))
+
+    def dense(self, lev: int, which: str) -> np.ndarray:
+        """valid cells of every box of a level gathered over the level domain (NaN where the level has no box);
+        which = 'f' | 'g' | 'macro' | 'derived'"""
+        ncomp = {"f": NQ, "g": NQ, "macro": NMACRO, "derived": NDERIVED}[which]
+        n = self.n[lev]
+        out = np.full((ncomp, n[2], n[1], n[0]), np.nan)
+        for ib, (lo, hi) in enumerate(self.boxes[lev]):
+            a = np.zeros(self.box_shape(lev, ib, ncomp, 0))
+            if which in ("f", "g"):
+                check(self.lib.mbl_box_download(self.ctx, lev, ib, 0 if which == "f" else 1, _dptr(a), 0))
+            else:
+                check(self.lib.mbl_box_download_macrodata(self.ctx, lev, ib, _dptr(a), 0, int(which == "derived")))
+            out[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1] = a
+        return out
+
+    def fields(self, lev: int, macro: bool = True) -> dict:
+        """dense valid-cell fields of one level under the reference's plotfile names"""
+        out = {}
+        f, g = self.dense(lev, "f"), self.dense(lev, "g")
+        for q in range(NQ):
+            out[f"f_{q:02d}"] = f[q]
+            out[f"g_{q:02d}"] = g[q]
+        if macro:
+            m = self.dense(lev, "macro")
+            for n, name in enumerate(MACRO_NAMES):
+                out[name] = m[n]
+            d = self.dense(lev, "derived")
+            for n, name in enumerate(DERIVED_NAMES):
+                out[name] = d[n]
+        return out
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.mbl_launch_count(self.ctx))
+
+    def ncells(self, lev: int | None = None) -> int:
+        levs = range(self.finest + 1) if lev is None else [lev]
+        return sum(int(np.prod([hi[d] - lo[d] + 1 for d in range(3)])) for l in levs for lo, hi in self.boxes[l])

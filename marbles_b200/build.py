@@ -13,11 +13,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmarbles_b200.so")
-SOURCES = ["kernels.cu", "api.cu"]
+SOURCES = ["kernels.cu", "patch.cu", "amr.cu", "api.cu"]
 # negative-result kernels (step variants 1-4 of round 1, the march step 8 of round 2): only with MBL_EXPERIMENTS=1
 EXPERIMENT_SOURCES = [os.path.join("experiments", "fused.cu"), os.path.join("experiments", "march.cu")]
 EXPERIMENT_HEADERS = [os.path.join("experiments", "experiments.cuh")]
-HEADERS = ["lattice.cuh", "kernels.cuh", os.path.join("..", "..", "include", "marbles_b200.h")]
+HEADERS = ["lattice.cuh", "kernels.cuh", "patch.cuh", "bcic.cuh", "internal.cuh", os.path.join("..", "..", "include", "marbles_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",

@@ -1,0 +1,794 @@
+// amr.cu -- multi-box / multi-level ("AMR-exact") levels behind the C ABI.
+//
+// The reference keeps its AMR hierarchy in AMReX (BoxArray, DistributionMapping, regrid); what crosses the C ABI
+// is the box list of a level.  This file owns the device state of such a level (one AMReX-shaped FAB per box,
+// library memory or bound AMReX memory), turns the box lists into device copy-tag lists on the host --
+//   FabArray::FillBoundary(periodicity)                 AMReX_FabArrayCommI.H:8-253
+//   average_down_with_ghosts' two ParallelCopy calls    Source/Utilities.cpp:17, 26 (order of overlapping tags:
+//                                                        FabArrayBase::CPC::define, AMReX_FabArrayBase.cpp:328-472)
+//   FillPatchTwoLevels' coarse patch + fine ghost regions  AMReX_FillPatchUtil_I.H:564-609, FPinfo
+//                                                        (AMReX_FabArrayBase.cpp:1797-1851)
+// -- and sequences the kernels of patch.cu in the reference's order.  Box calculus is plain host C++.
+#include <algorithm>
+#include <array>
+#include <cstring>
+
+#include "internal.cuh"
+#include "patch.cuh"
+
+using namespace mbl;
+
+namespace mbl {
+
+namespace {
+
+struct HBox {
+    int lo[3], hi[3];
+    bool ok() const { return lo[0] <= hi[0] && lo[1] <= hi[1] && lo[2] <= hi[2]; }
+    long long pts() const { return ok() ? (long long)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1) : 0; }
+};
+HBox isect(const HBox& a, const HBox& b)
+{
+    HBox r;
+    for (int d = 0; d < 3; ++d) {
+        r.lo[d] = std::max(a.lo[d], b.lo[d]);
+        r.hi[d] = std::min(a.hi[d], b.hi[d]);
+    }
+    return r;
+}
+HBox grow(HBox b, int n)
+{
+    for (int d = 0; d < 3; ++d) b.lo[d] -= n, b.hi[d] += n;
+    return b;
+}
+HBox shifted(HBox b, const int s[3])
+{
+    for (int d = 0; d < 3; ++d) b.lo[d] += s[d], b.hi[d] += s[d];
+    return b;
+}
+int floor_div2(int a) { return a >> 1; }
+HBox coarsen2(HBox b)
+{
+    for (int d = 0; d < 3; ++d) b.lo[d] = floor_div2(b.lo[d]), b.hi[d] = floor_div2(b.hi[d]);
+    return b;
+}
+// a minus b as at most six disjoint boxes
+void box_diff(const HBox& a, const HBox& b, std::vector<HBox>& out)
+{
+    const HBox c = isect(a, b);
+    if (!c.ok()) {
+        out.push_back(a);
+        return;
+    }
+    HBox rest = a;
+    for (int d = 2; d >= 0; --d) {
+        if (rest.lo[d] < c.lo[d]) {
+            HBox p = rest;
+            p.hi[d] = c.lo[d] - 1;
+            out.push_back(p);
+            rest.lo[d] = c.lo[d];
+        }
+        if (rest.hi[d] > c.hi[d]) {
+            HBox p = rest;
+            p.lo[d] = c.hi[d] + 1;
+            out.push_back(p);
+            rest.hi[d] = c.hi[d];
+        }
+    }
+}
+
+// Periodicity::shiftIntVect (AMReX_Periodicity.cpp:8-33): x outermost, z innermost
+std::vector<std::array<int, 3>> periodic_shifts(const PGeom& G, int nghost)
+{
+    int per[3] = {0, 0, 0}, jmp[3] = {1, 1, 1};
+    for (int d = 0; d < 3; ++d)
+        if (G.periodic[d]) {
+            const int len = G.dhi[d] - G.dlo[d] + 1;
+            per[d] = jmp[d] = len;
+            while (per[d] < nghost) per[d] += len;
+        }
+    std::vector<std::array<int, 3>> r;
+    for (int i = -per[0]; i <= per[0]; i += jmp[0])
+        for (int j = -per[1]; j <= per[1]; j += jmp[1])
+            for (int k = -per[2]; k <= per[2]; k += jmp[2]) r.push_back(std::array<int, 3>{{i, j, k}});
+    return r;
+}
+
+// order in which BoxArray::intersections visits boxes (AMReX_BoxArray.cpp:1219-1310, hash bins of getHashMap :1547-1598)
+std::vector<int> hash_order(const std::vector<HBox>& b)
+{
+    int maxext[3] = {1, 1, 1};
+    for (const HBox& x : b)
+        for (int d = 0; d < 3; ++d) maxext[d] = std::max(maxext[d], x.hi[d] - x.lo[d] + 1);
+    auto fdiv = [](int a, int m) { return a >= 0 ? a / m : -((-a + m - 1) / m); };
+    std::vector<int> idx(b.size());
+    for (size_t n = 0; n < b.size(); ++n) idx[n] = (int)n;
+    std::stable_sort(idx.begin(), idx.end(), [&](int p, int q) {
+        for (int d = 2; d >= 0; --d) {
+            const int kp = fdiv(b[p].lo[d], maxext[d]), kq = fdiv(b[q].lo[d], maxext[d]);
+            if (kp != kq) return kp < kq;
+        }
+        return p < q;
+    });
+    return idx;
+}
+
+struct BoxSet {  // a table of FABs with its own memory (a level, or the auxiliary coarse boxes between two levels)
+    std::vector<PBox> h;
+    PBox* d = nullptr;
+    double* pool_f = nullptr;  // aux sets: one f and one g buffer per box
+    double* pool_g = nullptr;
+    long long max_cells = 0;
+    void free_all()
+    {
+        if (d) cudaFree(d);
+        if (pool_f) cudaFree(pool_f);
+        if (pool_g) cudaFree(pool_g);
+        d = nullptr, pool_f = pool_g = nullptr;
+        h.clear();
+    }
+};
+
+struct Tags {
+    CopyTag* d = nullptr;
+    int n = 0;
+    long long max_cells = 0;
+    void free_all()
+    {
+        if (d) cudaFree(d);
+        d = nullptr, n = 0;
+    }
+};
+
+PBox make_pbox(const HBox& valid, int ng)
+{
+    PBox b;
+    memset(&b, 0, sizeof(b));
+    for (int d = 0; d < 3; ++d) {
+        b.lo[d] = valid.lo[d], b.hi[d] = valid.hi[d];
+        b.glo[d] = valid.lo[d] - ng;
+        b.n[d] = valid.hi[d] - valid.lo[d] + 1 + 2 * ng;
+    }
+    b.sy = b.n[0];
+    b.sz = (long long)b.n[0] * b.n[1];
+    b.sq = b.sz * b.n[2];
+    return b;
+}
+
+int upload_tags(const std::vector<CopyTag>& v, Tags& t)
+{
+    t.free_all();
+    t.n = (int)v.size();
+    t.max_cells = 0;
+    for (const CopyTag& c : v) t.max_cells = std::max(t.max_cells, (long long)c.n[0] * c.n[1] * c.n[2]);
+    if (t.n == 0) return 0;
+    CU(cudaMalloc(&t.d, v.size() * sizeof(CopyTag)));
+    CU(cudaMemcpy(t.d, v.data(), v.size() * sizeof(CopyTag), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+CopyTag make_tag(int dbox, int sbox, const HBox& dst_region, const int shift[3])
+{
+    CopyTag t;
+    t.dbox = dbox, t.sbox = sbox;
+    for (int d = 0; d < 3; ++d) {
+        t.d[d] = dst_region.lo[d];
+        t.s[d] = dst_region.lo[d] - shift[d];
+        t.n[d] = dst_region.hi[d] - dst_region.lo[d] + 1;
+    }
+    return t;
+}
+
+// auxiliary coarse boxes between a fine level and the next coarser one
+struct Inter {
+    bool valid = false;
+    BoxSet avg[2];        // [ng]: coarsened fine boxes grown by ng (masked average-down, ng = 0 and 1)
+    Tags c2a[2], a2c[2];  // coarse valid -> aux; aux (grown) -> coarse valid, overlaps resolved to "last tag wins"
+    BoxSet cpatch;        // coarsen(grown fine box) grown by 1 (coarse-fine interpolation)
+    Tags c2p;
+    RegionTag* d_regs = nullptr;
+    int nregs = 0;
+    long long reg_max = 0;
+    void free_all()
+    {
+        for (int n = 0; n < 2; ++n) avg[n].free_all(), c2a[n].free_all(), a2c[n].free_all();
+        cpatch.free_all();
+        c2p.free_all();
+        if (d_regs) cudaFree(d_regs);
+        d_regs = nullptr, nregs = 0, valid = false;
+    }
+};
+
+}  // namespace
+
+struct PatchLevel {
+    int lev = 0;
+    PGeom G;
+    Phys P;
+    BcInfo B;
+    mbl_level_geom geom;
+    std::vector<HBox> boxes;
+    BoxSet set;          // the level's FABs (set.pool_* unused: separate pools below)
+    int cur = 0;
+    double* pool_f[2] = {nullptr, nullptr};
+    double* pool_g[2] = {nullptr, nullptr};
+    double* pool_qc = nullptr;
+    double* pool_macro = nullptr;
+    int32_t* pool_isfl = nullptr;
+    std::vector<long long> cell_off;  // first cell of each box in the pools
+    long long total_cells = 0;
+    bool any_bound = false;
+    bool dq_from_macro = false;
+    Tags fb3, fb1;       // FillBoundary over 3 ghost cells (f, g) and 1 (QCorr, macrodata)
+    Inter inter;         // this level as the FINE level of (lev - 1, lev)
+    int generation = 0, inter_coarse_generation = -1;
+};
+
+namespace {
+
+int sync_table(PatchLevel& L)
+{
+    CU(cudaMemcpy(L.set.d, L.set.h.data(), L.set.h.size() * sizeof(PBox), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+void build_fill_boundary(const PatchLevel& L, int ng, std::vector<CopyTag>& out)
+{
+    const auto shifts = periodic_shifts(L.G, ng);
+    const int nb = (int)L.boxes.size();
+    for (int i = 0; i < nb; ++i) {
+        const HBox gb = grow(L.boxes[i], ng);
+        for (const auto& s : shifts) {
+            const int sh[3] = {s[0], s[1], s[2]};
+            for (int j = 0; j < nb; ++j) {
+                if (i == j && !sh[0] && !sh[1] && !sh[2]) continue;
+                const HBox r = isect(gb, shifted(L.boxes[j], sh));
+                if (!r.ok()) continue;
+                // the ghost cells only: a periodic image may fall on valid cells of the box itself when the domain is
+                // narrower than the box is wide -- those keep their values
+                std::vector<HBox> pieces;
+                box_diff(r, L.boxes[i], pieces);
+                for (const HBox& p : pieces) out.push_back(make_tag(i, j, p, sh));
+            }
+        }
+    }
+}
+
+int alloc_aux(BoxSet& S, const std::vector<HBox>& valid, int ng)
+{
+    S.free_all();
+    long long total = 0;
+    for (const HBox& v : valid) {
+        PBox b = make_pbox(v, ng);
+        S.max_cells = std::max(S.max_cells, b.sq);
+        total += b.sq;
+        S.h.push_back(b);
+    }
+    CU(cudaMalloc(&S.pool_f, (size_t)total * NQ * sizeof(double)));
+    CU(cudaMalloc(&S.pool_g, (size_t)total * NQ * sizeof(double)));
+    CU(cudaMemset(S.pool_f, 0, (size_t)total * NQ * sizeof(double)));
+    CU(cudaMemset(S.pool_g, 0, (size_t)total * NQ * sizeof(double)));
+    long long off = 0;
+    for (PBox& b : S.h) {
+        b.f[0] = b.f[1] = S.pool_f + off * NQ;
+        b.g[0] = b.g[1] = S.pool_g + off * NQ;
+        off += b.sq;
+    }
+    CU(cudaMalloc(&S.d, S.h.size() * sizeof(PBox)));
+    CU(cudaMemcpy(S.d, S.h.data(), S.h.size() * sizeof(PBox), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// everything between level F.lev - 1 (coarse) and F.lev (fine), ratio 2
+int build_inter(PatchLevel& F, const PatchLevel& Cl)
+{
+    Inter& I = F.inter;
+    I.free_all();
+    const int nf = (int)F.boxes.size(), nc = (int)Cl.boxes.size();
+    for (const HBox& b : F.boxes)
+        for (int d = 0; d < 3; ++d)
+            if ((b.lo[d] & 1) || !(b.hi[d] & 1)) return fail("fine boxes must be aligned to the refinement ratio 2");
+    std::vector<HBox> cfine(nf);
+    for (int n = 0; n < nf; ++n) cfine[n] = coarsen2(F.boxes[n]);
+    const std::vector<int> order = hash_order(F.boxes);
+    for (int ng = 0; ng < 2; ++ng) {
+        if (alloc_aux(I.avg[ng], cfine, ng)) return 1;
+        // (1) cfine.ParallelCopy(crse, src ng 0, dst ng): the reference's copy is not periodic, and cells of the ring
+        // that lie outside the domain stay uninitialised there; here they take the periodic image, so that a ring cell
+        // whose eight fine cells are all masked hands the coarse cell its own value back (see oracle/amr_oracle.py)
+        std::vector<CopyTag> c2a;
+        const auto shifts_a = periodic_shifts(Cl.G, ng);
+        for (int n = 0; n < nf; ++n) {
+            const HBox gb = grow(cfine[n], ng);
+            for (const auto& s : shifts_a) {
+                const int sh[3] = {s[0], s[1], s[2]};
+                for (int j = 0; j < nc; ++j) {
+                    const HBox r = isect(gb, shifted(Cl.boxes[j], sh));
+                    if (r.ok()) c2a.push_back(make_tag(n, j, r, sh));
+                }
+            }
+        }
+        if (upload_tags(c2a, I.c2a[ng])) return 1;
+        // (2) crse.ParallelCopy(cfine, src ng, dst ng 0, periodicity): tags in CPC order; where the rings of two fine
+        // boxes overlap the LAST tag wins, so earlier tags are cut back to what later ones leave
+        std::vector<CopyTag> a2c;
+        const auto shifts_c = periodic_shifts(Cl.G, 0);
+        for (int j = 0; j < nc; ++j) {
+            std::vector<std::pair<HBox, CopyTag>> live;  // disjoint destination regions of box j
+            for (const auto& s : shifts_c) {
+                const int sh[3] = {s[0], s[1], s[2]};
+                for (int n : order) {
+                    const HBox r = isect(Cl.boxes[j], shifted(grow(cfine[n], ng), sh));
+                    if (!r.ok()) continue;
+                    std::vector<std::pair<HBox, CopyTag>> next;
+                    for (auto& e : live) {
+                        std::vector<HBox> pieces;
+                        box_diff(e.first, r, pieces);
+                        for (const HBox& p : pieces) {
+                            const int esh[3] = {e.second.d[0] - e.second.s[0], e.second.d[1] - e.second.s[1],
+                                                e.second.d[2] - e.second.s[2]};
+                            next.push_back({p, make_tag(e.second.dbox, e.second.sbox, p, esh)});
+                        }
+                    }
+                    next.push_back({r, make_tag(j, n, r, sh)});
+                    live.swap(next);
+                }
+            }
+            for (auto& e : live) a2c.push_back(e.second);
+        }
+        if (upload_tags(a2c, I.a2c[ng])) return 1;
+    }
+    // coarse patches for the interpolation: coarsen(grown fine box) grown by 1 (CellConservativeLinear::CoarseBox)
+    std::vector<HBox> cp(nf);
+    for (int n = 0; n < nf; ++n) cp[n] = grow(coarsen2(grow(F.boxes[n], PNG)), 1);
+    if (alloc_aux(I.cpatch, cp, 0)) return 1;
+    std::vector<CopyTag> c2p;
+    const auto shifts_p = periodic_shifts(Cl.G, PNG + 2);
+    for (int n = 0; n < nf; ++n)
+        for (const auto& s : shifts_p) {
+            const int sh[3] = {s[0], s[1], s[2]};
+            for (int j = 0; j < nc; ++j) {
+                const HBox r = isect(cp[n], shifted(Cl.boxes[j], sh));
+                if (r.ok()) c2p.push_back(make_tag(n, j, r, sh));
+            }
+        }
+    if (upload_tags(c2p, I.c2p)) return 1;
+    // fine ghost regions the interpolation fills: grown box inside dstdomain (the domain grown by the ghost width in
+    // periodic directions) minus the fine level's valid boxes, NOT periodically shifted (FPinfo: complementIn)
+    std::vector<RegionTag> regs;
+    for (int n = 0; n < nf; ++n) {
+        HBox r0 = grow(F.boxes[n], PNG);
+        for (int d = 0; d < 3; ++d)
+            if (!F.G.periodic[d]) {
+                r0.lo[d] = std::max(r0.lo[d], F.G.dlo[d]);
+                r0.hi[d] = std::min(r0.hi[d], F.G.dhi[d]);
+            }
+        std::vector<HBox> list{r0};
+        for (const HBox& v : F.boxes) {
+            std::vector<HBox> next;
+            for (const HBox& r : list) box_diff(r, v, next);
+            list.swap(next);
+        }
+        for (const HBox& r : list) {
+            for (int d = 0; d < 3; ++d) {
+                if (F.G.periodic[d]) continue;
+                // slopes of coarse cells on a non-periodic domain face are one-sided and depend on the extents of
+                // AMReX's internal coarse patch (AMReX_MFInterp_C.H:15-33): not reproduced
+                if (floor_div2(r.lo[d]) <= Cl.G.dlo[d] || floor_div2(r.hi[d]) >= Cl.G.dhi[d])
+                    return fail("level %d: a fine box lies within one coarse cell of a non-periodic domain face; the "
+                                "coarse-fine interpolation there is not supported", F.lev);
+            }
+            RegionTag t;
+            t.box = n;
+            for (int d = 0; d < 3; ++d) t.lo[d] = r.lo[d], t.n[d] = r.hi[d] - r.lo[d] + 1;
+            regs.push_back(t);
+            I.reg_max = std::max(I.reg_max, r.pts());
+        }
+    }
+    I.nregs = (int)regs.size();
+    if (I.nregs) {
+        CU(cudaMalloc(&I.d_regs, regs.size() * sizeof(RegionTag)));
+        CU(cudaMemcpy(I.d_regs, regs.data(), regs.size() * sizeof(RegionTag), cudaMemcpyHostToDevice));
+    }
+    I.valid = true;
+    F.inter_coarse_generation = Cl.generation;
+    return 0;
+}
+
+int ensure_inter(mbl_ctx* ctx, int fine_lev)
+{
+    if (fine_lev < 1 || !ctx->plev[fine_lev] || !ctx->plev[fine_lev - 1])
+        return fail("levels %d and %d must both be multi-box levels (mbl_level_define_boxes)", fine_lev - 1, fine_lev);
+    PatchLevel& F = *ctx->plev[fine_lev];
+    const PatchLevel& Cl = *ctx->plev[fine_lev - 1];
+    if (F.inter.valid && F.inter_coarse_generation == Cl.generation) return 0;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return build_inter(F, Cl);
+}
+
+int fill_boundary(mbl_ctx* ctx, PatchLevel& L, int arr, int ncomp, int ng)
+{
+    const Tags& t = ng == 1 ? L.fb1 : L.fb3;
+    ctx->launches += launch_patch_copy(L.set.d, L.cur, L.set.d, L.cur, t.d, t.n, arr, arr, ncomp, t.max_cells, ctx->stream);
+    return 0;
+}
+
+int ensure_macro(mbl_ctx* ctx, PatchLevel& L)
+{
+    if (L.pool_macro) return 0;
+    CU(cudaMalloc(&L.pool_macro, (size_t)L.total_cells * NMACRO_ALL * sizeof(double)));
+    CU(cudaMemsetAsync(L.pool_macro, 0, (size_t)L.total_cells * NMACRO_ALL * sizeof(double), ctx->stream));
+    for (size_t n = 0; n < L.set.h.size(); ++n) L.set.h[n].macro = L.pool_macro + L.cell_off[n] * NMACRO_ALL;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return sync_table(L);
+}
+
+PatchLevel* plevel(mbl_ctx* ctx, int lev)
+{
+    if (!ctx || lev < 0 || lev >= MAX_LEVELS || !ctx->plev[lev]) {
+        fail("level %d is not a multi-box level (mbl_level_define_boxes)", lev);
+        return nullptr;
+    }
+    return ctx->plev[lev];
+}
+
+// FAB <-> FAB copy of ncomp components between a caller's array (ghost width ng_fab) and a device box (ghost
+// width PNG): the cells both have, one pitched DMA per component
+int copy_fab(const PBox& b, double* dev, int ncomp, double* fab, int ng_fab, bool to_device, cudaStream_t st)
+{
+    const int g = std::min(ng_fab, PNG);
+    const int nx = b.hi[0] - b.lo[0] + 1, ny = b.hi[1] - b.lo[1] + 1, nz = b.hi[2] - b.lo[2] + 1;
+    const size_t fx = nx + 2 * ng_fab, fy = ny + 2 * ng_fab, fn = fx * fy * (nz + 2 * ng_fab);
+    for (int q = 0; q < ncomp; ++q) {
+        cudaMemcpy3DParms p;
+        memset(&p, 0, sizeof(p));
+        cudaPitchedPtr host = make_cudaPitchedPtr(fab + (size_t)q * fn, fx * sizeof(double), fx, fy);
+        cudaPitchedPtr devp = make_cudaPitchedPtr(dev + (size_t)q * b.sq, b.n[0] * sizeof(double), b.n[0], b.n[1]);
+        const cudaPos hpos = make_cudaPos((size_t)(ng_fab - g) * sizeof(double), ng_fab - g, ng_fab - g);
+        const cudaPos dpos = make_cudaPos((size_t)(PNG - g) * sizeof(double), PNG - g, PNG - g);
+        p.srcPtr = to_device ? host : devp;
+        p.srcPos = to_device ? hpos : dpos;
+        p.dstPtr = to_device ? devp : host;
+        p.dstPos = to_device ? dpos : hpos;
+        p.extent = make_cudaExtent((size_t)(nx + 2 * g) * sizeof(double), ny + 2 * g, nz + 2 * g);
+        p.kind = cudaMemcpyDefault;
+        CU(cudaMemcpy3DAsync(&p, st));
+    }
+    return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// patch-level counterparts of the per-level entry points (called from api.cu)
+// ---------------------------------------------------------------------------------------------------------
+int patch_clear(mbl_ctx* ctx, int lev)
+{
+    PatchLevel* L = ctx->plev[lev];
+    if (!L) return 0;
+    cudaStreamSynchronize(ctx->stream);
+    for (int n = 0; n < 2; ++n) {
+        if (L->pool_f[n]) cudaFree(L->pool_f[n]);
+        if (L->pool_g[n]) cudaFree(L->pool_g[n]);
+    }
+    if (L->pool_qc) cudaFree(L->pool_qc);
+    if (L->pool_macro) cudaFree(L->pool_macro);
+    if (L->pool_isfl) cudaFree(L->pool_isfl);
+    L->set.free_all();
+    L->fb3.free_all();
+    L->fb1.free_all();
+    L->inter.free_all();
+    delete L;
+    ctx->plev[lev] = nullptr;
+    return 0;
+}
+
+int patch_initialize(mbl_ctx* ctx, int lev, const IcInfo& I)
+{
+    PatchLevel* L = plevel(ctx, lev);
+    if (!L) return 1;
+    ctx->launches += launch_patch_initialize(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->cur, L->B, I, ctx->stream);
+    // initialize_f ends with FillBoundary of f and g (LBM.cpp:1209-1210)
+    fill_boundary(ctx, *L, PA_F, NQ, PNG);
+    fill_boundary(ctx, *L, PA_G, NQ, PNG);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int patch_physbc(mbl_ctx* ctx, int lev, double /*time*/)
+{
+    PatchLevel* L = plevel(ctx, lev);
+    if (!L) return 1;
+    ctx->launches += launch_patch_physbc(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->cur, L->G, L->B, ctx->stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// FillPatchOps::fillpatch(lev, time, m_f[lev]) and the same for g (FillPatchOps.H:75-132)
+int patch_fillpatch(mbl_ctx* ctx, int lev, double time)
+{
+    PatchLevel* L = plevel(ctx, lev);
+    if (!L) return 1;
+    const int nb = (int)L->boxes.size();
+    cudaStream_t st = ctx->stream;
+    const bool all_periodic = L->G.periodic[0] && L->G.periodic[1] && L->G.periodic[2];
+    ctx->launches += launch_patch_prepass(L->set.d, nb, L->set.max_cells, L->cur, L->G, st);  // K6
+    if (lev > 0) {
+        // FillPatchTwoLevels: coarse patch from the coarse level's valid cells, CellConservativeLinear into the fine
+        // ghost cells no fine valid cell covers
+        if (ensure_inter(ctx, lev)) return 1;
+        PatchLevel& Cl = *ctx->plev[lev - 1];
+        Inter& I = L->inter;
+        for (int arr = PA_F; arr <= PA_G; ++arr)
+            ctx->launches += launch_patch_copy(I.cpatch.d, 0, Cl.set.d, Cl.cur, I.c2p.d, I.c2p.n, arr, arr, NQ, I.c2p.max_cells, st);
+        ctx->launches += launch_patch_interp(L->set.d, L->cur, I.cpatch.d, I.d_regs, I.nregs, I.reg_max, st);
+    }
+    fill_boundary(ctx, *L, PA_F, NQ, PNG);
+    fill_boundary(ctx, *L, PA_G, NQ, PNG);
+    (void)all_periodic;
+    CU(cudaGetLastError());
+    return patch_physbc(ctx, lev, time);
+}
+
+// LBM::stream(lev, m_f); LBM::stream(lev, m_g) on the grown boxes (LBM.cpp:558-604)
+int patch_stream(mbl_ctx* ctx, int lev)
+{
+    PatchLevel* L = plevel(ctx, lev);
+    if (!L) return 1;
+    cudaStream_t st = ctx->stream;
+    ctx->launches += launch_patch_stream(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->cur, st);
+    if (L->any_bound) {
+        // bound FABs stay the current buffers: copy the streamed state back (MultiFab::Copy, LBM.cpp:601)
+        for (const PBox& b : L->set.h) {
+            CU(cudaMemcpyAsync(b.f[L->cur], b.f[1 - L->cur], (size_t)b.sq * NQ * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(b.g[L->cur], b.g[1 - L->cur], (size_t)b.sq * NQ * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        }
+    } else {
+        L->cur = 1 - L->cur;
+    }
+    fill_boundary(ctx, *L, PA_F, NQ, PNG);  // LBM.cpp:603
+    fill_boundary(ctx, *L, PA_G, NQ, PNG);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int patch_macro_pass(mbl_ctx* ctx, PatchLevel& L, int want_macro)
+{
+    const int nb = (int)L.boxes.size();
+    if (want_macro && ensure_macro(ctx, L)) return 1;
+    ctx->launches += launch_patch_qcorr(L.set.d, nb, L.set.max_cells, L.cur, L.P, want_macro, ctx->stream);
+    fill_boundary(ctx, L, PA_QC, 3, 1);                      // m_macrodata.FillBoundary, LBM.cpp:905 (the comps the
+    if (want_macro) fill_boundary(ctx, L, PA_MACRO, MBL_NMACRO, 1);  // gradient reads; all 19 when they are stored)
+    return 0;
+}
+
+// LBM::collide(lev) (LBM.cpp:607-618) on the streamed state, in place
+int patch_collide(mbl_ctx* ctx, int lev, int want_macro)
+{
+    PatchLevel* L = plevel(ctx, lev);
+    if (!L) return 1;
+    if (patch_macro_pass(ctx, *L, want_macro)) return 1;
+    if (want_macro) L->dq_from_macro = false;
+    ctx->launches += launch_patch_collide(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->cur, L->G, L->P, want_macro,
+                                          ctx->stream);
+    fill_boundary(ctx, *L, PA_F, NQ, PNG);  // LBM.cpp:805-806
+    fill_boundary(ctx, *L, PA_G, NQ, PNG);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int patch_f_to_macrodata(mbl_ctx* ctx, int lev)
+{
+    PatchLevel* L = plevel(ctx, lev);
+    if (!L) return 1;
+    if (patch_macro_pass(ctx, *L, 1)) return 1;
+    L->dq_from_macro = true;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int patch_compute_derived(mbl_ctx* ctx, int lev)
+{
+    PatchLevel* L = plevel(ctx, lev);
+    if (!L) return 1;
+    if (!L->pool_macro) return fail("mbl_compute_derived needs macrodata");
+    ctx->launches += launch_patch_derived(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->G, L->P, L->dq_from_macro ? 1 : 0,
+                                          ctx->stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace mbl
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int mbl_level_define_boxes(mbl_ctx* ctx, int lev, const mbl_level_geom* g, int nboxes, const int* lo, const int* hi)
+{
+    if (!ctx || !g || !lo || !hi) return fail("null argument");
+    if (lev < 0 || lev >= MAX_LEVELS) return fail("level %d out of range", lev);
+    if (nboxes < 1) return fail("a level needs at least one box");
+    CU(cudaSetDevice(ctx->device));
+    mbl_level_clear(ctx, lev);
+    PatchLevel* L = new PatchLevel();
+    L->lev = lev;
+    L->geom = *g;
+    for (int d = 0; d < 3; ++d) {
+        L->G.dlo[d] = g->dom_lo[d], L->G.dhi[d] = g->dom_hi[d];
+        L->G.periodic[d] = ctx->prm.periodic[d];
+    }
+    level_phys_bc(ctx->prm, *g, L->P, L->B);
+    for (int n = 0; n < nboxes; ++n) {
+        HBox b;
+        for (int d = 0; d < 3; ++d) b.lo[d] = lo[3 * n + d], b.hi[d] = hi[3 * n + d];
+        if (!b.ok()) {
+            delete L;
+            return fail("box %d is empty", n);
+        }
+        for (int d = 0; d < 3; ++d)
+            if (b.lo[d] < g->dom_lo[d] || b.hi[d] > g->dom_hi[d]) {
+                delete L;
+                return fail("box %d leaves the level domain in direction %d", n, d);
+            }
+        for (const HBox& o : L->boxes)
+            if (isect(o, b).ok()) {
+                delete L;
+                return fail("box %d overlaps another box of the level", n);
+            }
+        L->boxes.push_back(b);
+        PBox p = make_pbox(b, PNG);
+        L->cell_off.push_back(L->total_cells);
+        L->total_cells += p.sq;
+        L->set.max_cells = std::max(L->set.max_cells, p.sq);
+        L->set.h.push_back(p);
+    }
+    ctx->plev[lev] = L;
+    const size_t lat = (size_t)L->total_cells * NQ * sizeof(double);
+    for (int n = 0; n < 2; ++n) {
+        CU(cudaMalloc(&L->pool_f[n], lat));
+        CU(cudaMalloc(&L->pool_g[n], lat));
+        CU(cudaMemsetAsync(L->pool_f[n], 0, lat, ctx->stream));
+        CU(cudaMemsetAsync(L->pool_g[n], 0, lat, ctx->stream));
+    }
+    CU(cudaMalloc(&L->pool_qc, (size_t)L->total_cells * 3 * sizeof(double)));
+    CU(cudaMemsetAsync(L->pool_qc, 0, (size_t)L->total_cells * 3 * sizeof(double), ctx->stream));
+    CU(cudaMalloc(&L->pool_isfl, (size_t)L->total_cells * sizeof(int32_t)));
+    {
+        std::vector<int32_t> ones((size_t)L->total_cells, 1);  // all fluid until mbl_box_set_is_fluid says otherwise
+        CU(cudaMemcpy(L->pool_isfl, ones.data(), ones.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    for (size_t n = 0; n < L->set.h.size(); ++n) {
+        PBox& p = L->set.h[n];
+        const long long o = L->cell_off[n];
+        for (int c = 0; c < 2; ++c) p.f[c] = L->pool_f[c] + o * NQ, p.g[c] = L->pool_g[c] + o * NQ;
+        p.qc = L->pool_qc + o * 3;
+        p.isfl = L->pool_isfl + o;
+    }
+    CU(cudaMalloc(&L->set.d, L->set.h.size() * sizeof(PBox)));
+    if (sync_table(*L)) return 1;
+    std::vector<CopyTag> t3, t1;
+    build_fill_boundary(*L, PNG, t3);
+    build_fill_boundary(*L, 1, t1);
+    if (upload_tags(t3, L->fb3) || upload_tags(t1, L->fb1)) return 1;
+    static int generation = 0;
+    L->generation = ++generation;
+    patch_init_tables();
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbl_level_num_boxes(mbl_ctx* ctx, int lev)
+{
+    if (!ctx || lev < 0 || lev >= MAX_LEVELS) return -1;
+    if (ctx->plev[lev]) return (int)ctx->plev[lev]->boxes.size();
+    return ctx->lev[lev].defined ? 1 : 0;
+}
+
+int mbl_level_bind(mbl_ctx* ctx, int lev, int ibox, int which, double* device_fab)
+{
+    PatchLevel* L = plevel(ctx, lev);
+    if (!L) return 1;
+    if (ibox < 0 || ibox >= (int)L->boxes.size() || !device_fab) return fail("mbl_level_bind: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (L->cur != 0) {
+        // bring the library-owned state into buffer 0 before the table changes: bound FABs are always buffer 0
+        for (PBox& b : L->set.h) {
+            std::swap(b.f[0], b.f[1]);
+            std::swap(b.g[0], b.g[1]);
+        }
+        L->cur = 0;
+    }
+    PBox& b = L->set.h[ibox];
+    (which == MBL_G ? b.g[0] : b.f[0]) = device_fab;
+    L->any_bound = true;
+    return sync_table(*L);
+}
+
+int mbl_box_set_is_fluid(mbl_ctx* ctx, int lev, int ibox, const int32_t* fab, int ng)
+{
+    PatchLevel* L = plevel(ctx, lev);
+    if (!L) return 1;
+    if (ibox < 0 || ibox >= (int)L->boxes.size() || !fab) return fail("mbl_box_set_is_fluid: bad argument");
+    if (ng < PNG) return fail("is_fluid needs %d ghost cells (got %d): out-of-domain values come from the geometry", PNG, ng);
+    CU(cudaSetDevice(ctx->device));
+    const PBox& b = L->set.h[ibox];
+    const int nx = b.hi[0] - b.lo[0] + 1, ny = b.hi[1] - b.lo[1] + 1;
+    const size_t fx = nx + 2 * ng, fy = ny + 2 * ng;
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof(p));
+    p.srcPtr = make_cudaPitchedPtr(const_cast<int32_t*>(fab), fx * sizeof(int32_t), fx, fy);
+    p.srcPos = make_cudaPos((size_t)(ng - PNG) * sizeof(int32_t), ng - PNG, ng - PNG);
+    p.dstPtr = make_cudaPitchedPtr(b.isfl, b.n[0] * sizeof(int32_t), b.n[0], b.n[1]);
+    p.extent = make_cudaExtent((size_t)b.n[0] * sizeof(int32_t), b.n[1], b.n[2]);
+    p.kind = cudaMemcpyDefault;
+    CU(cudaMemcpy3DAsync(&p, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mbl_box_upload(mbl_ctx* ctx, int lev, int ibox, int which, const double* fab, int ng)
+{
+    PatchLevel* L = plevel(ctx, lev);
+    if (!L) return 1;
+    if (ibox < 0 || ibox >= (int)L->boxes.size() || !fab || ng < 0) return fail("mbl_box_upload: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    const PBox& b = L->set.h[ibox];
+    if (copy_fab(b, which == MBL_G ? b.g[L->cur] : b.f[L->cur], NQ, const_cast<double*>(fab), ng, true, ctx->stream)) return 1;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mbl_box_download(mbl_ctx* ctx, int lev, int ibox, int which, double* fab, int ng)
+{
+    PatchLevel* L = plevel(ctx, lev);
+    if (!L) return 1;
+    if (ibox < 0 || ibox >= (int)L->boxes.size() || !fab || ng < 0) return fail("mbl_box_download: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    const PBox& b = L->set.h[ibox];
+    if (copy_fab(b, which == MBL_G ? b.g[L->cur] : b.f[L->cur], NQ, fab, ng, false, ctx->stream)) return 1;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mbl_box_download_macrodata(mbl_ctx* ctx, int lev, int ibox, double* fab, int ng, int derived)
+{
+    PatchLevel* L = plevel(ctx, lev);
+    if (!L) return 1;
+    if (ibox < 0 || ibox >= (int)L->boxes.size() || !fab || ng < 0) return fail("mbl_box_download_macrodata: bad argument");
+    if (!L->pool_macro) return fail("no macrodata yet: call mbl_collide with want_macrodata or mbl_f_to_macrodata");
+    CU(cudaSetDevice(ctx->device));
+    const PBox& b = L->set.h[ibox];
+    double* src = derived ? b.macro + (size_t)MBL_NMACRO * b.sq : b.macro;
+    if (copy_fab(b, src, derived ? MBL_NDERIVED : MBL_NMACRO, fab, ng, false, ctx->stream)) return 1;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// LBM::average_down_to(crse_lev, ng) (LBM.cpp:1571-1584): f and g of level crse_lev + 1 onto level crse_lev
+int mbl_average_down(mbl_ctx* ctx, int crse_lev, int ng)
+{
+    if (!ctx) return fail("null context");
+    if (ng < 0 || ng > 1) return fail("mbl_average_down: ng must be 0 or 1");
+    CU(cudaSetDevice(ctx->device));
+    if (ensure_inter(ctx, crse_lev + 1)) return 1;
+    PatchLevel& F = *ctx->plev[crse_lev + 1];
+    PatchLevel& Cl = *ctx->plev[crse_lev];
+    Inter& I = F.inter;
+    cudaStream_t st = ctx->stream;
+    const int nf = (int)F.boxes.size();
+    for (int arr = PA_F; arr <= PA_G; ++arr)
+        ctx->launches += launch_patch_copy(I.avg[ng].d, 0, Cl.set.d, Cl.cur, I.c2a[ng].d, I.c2a[ng].n, arr, arr, NQ,
+                                           I.c2a[ng].max_cells, st);
+    ctx->launches += launch_patch_avgdown(F.set.d, F.cur, I.avg[ng].d, nf, I.avg[ng].max_cells, ng, st);
+    for (int arr = PA_F; arr <= PA_G; ++arr)
+        ctx->launches += launch_patch_copy(Cl.set.d, Cl.cur, I.avg[ng].d, 0, I.a2c[ng].d, I.a2c[ng].n, arr, arr, NQ,
+                                           I.a2c[ng].max_cells, st);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -2,21 +2,15 @@
 // device state ownership, host<->device transfer and the per-step sequencing that
 // replaces LBM::advance / FillPatchOps::fillpatch (Source/LBM.cpp:523-544,
 // Source/FillPatchOps.H:75-132).  No CPU fallback: every entry point needs a device.
-#include "../../include/marbles_b200.h"
-
-#include <cstdarg>
-#include <cstdio>
 #include <cstdlib>
 #include <algorithm>
 #include <cstring>
-#include <string>
-#include <vector>
 
-#include "kernels.cuh"
+#include "internal.cuh"
 
 using namespace mbl;
 
-namespace {
+namespace mbl {
 
 thread_local std::string g_err;
 
@@ -31,67 +25,7 @@ int fail(const char* fmt, ...)
     return 1;
 }
 
-#define CU(call)                                                                         \
-    do {                                                                                 \
-        cudaError_t e_ = (call);                                                         \
-        if (e_ != cudaSuccess) return fail("%s failed: %s", #call, cudaGetErrorString(e_)); \
-    } while (0)
-
-constexpr int MAX_LEVELS = 16;
-constexpr int NMACRO_ALL = MBL_NMACRO + MBL_NDERIVED;  // macro comps followed by derived comps
-
-struct Level {
-    bool defined = false;
-    Layout L;
-    Phys P;
-    BcInfo B;
-    mbl_level_geom geom;
-    char* base = nullptr;  // device state block
-    bool owned = false;
-    LevelPtrs p;
-    int cur = 0;  // index of the current lattice buffers
-    bool local_z = true;
-    int32_t* flag_stage = nullptr;
-    double* d_red = nullptr;  // 3 doubles for reductions
-    double* macro = nullptr;  // lazily allocated (26 comps)
-    int* counters = nullptr;  // fused kernel: ticket + per-slab completion counters
-    double* part = nullptr;   // carry step: 12 partial-sum words per cell (lazily allocated)
-    double* edge = nullptr;   // tile carry step: 18 words per CTA row
-    bool dq_from_macro = false;  // macrodata came from mbl_f_to_macrodata: compute_derived also differences QCorr
-    int part_pair = 0;        // `part` holds the 9-word plane-pair layout (variant 7)
-    int edge_rows = 0;        // rows per CTA the edge arrays were written with (0: written by the marching kernel)
-    // two consecutive steps (buffers a -> b -> a) captured as one CUDA graph: small boxes are launch-bound
-    // (a non-periodic level issues ~30 ghost-fill launches per step)
-    cudaGraphExec_t graph = nullptr;
-    int graph_cur = -1, graph_variant = -1;  // buffer parity and step variant the graph was captured for
-    int64_t graph_launches = 0;              // kernels per replay
-    bool carry_valid = false; // `part` holds the partial sums of the current lattice buffers' next post-stream state
-};
-
-}  // namespace
-
-struct mbl_ctx {
-    mbl_params prm;
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    Level lev[MAX_LEVELS];
-    int64_t launches = 0;
-    // implementation of mbl_step: 0 (default, fastest measured): two kernels, k_qcorr + k_collide;
-    // 1: persistent TMA-pipelined kernel with both job types; 2: the same kernel, one launch per job type;
-    // 3: persistent warp-autonomous kernel (plain loads) with both job types.  DESIGN.md has the numbers.
-    int variant = 5;
-    int uw = 128, band_rows = 16, lag_per_cta = 4;  // variants 1-3 tuning (MBL_UW / MBL_BAND / MBL_LAG)
-    int carry_own = 30, carry_ky = 32, carry_minb = 2, carry_rows = 6;  // variant 4 tuning (MBL_OWN / MBL_KY / MBL_MINB)
-    int march_rows = 6, march_zm = 64, march_pipe = 1;  // variant 8 tuning (MBL_MROWS / MBL_ZM / MBL_PIPE)
-    int sm_count = 148;
-    cudaStream_t s_up = nullptr, s_down = nullptr;  // copy streams of the pipelined mbl_step_host
-    cudaStream_t s_capture = nullptr;               // CUDA graph capture of step pairs
-    int host_chunk = 16;  // planes per upload chunk (MBL_HOST_CHUNK; negative: no pipelining)
-    bool use_graphs = true;  // MBL_GRAPH=0 disables
-    bool timing = false;
-    std::vector<cudaEvent_t> events;  // 4 per timed record: before ghost fill, q-corr, collide, after
-    int timed_steps = 0;              // steps covered by the records (a split step makes two records)
-};
+}  // namespace mbl
 
 namespace {
 
@@ -125,6 +59,8 @@ int check_level(mbl_ctx* ctx, int lev)
     if (lev < 0 || lev >= MAX_LEVELS || !ctx->lev[lev].defined) return fail("level %d is not defined", lev);
     return 0;
 }
+
+bool is_patch(mbl_ctx* ctx, int lev) { return ctx && lev >= 0 && lev < MAX_LEVELS && ctx->plev[lev] != nullptr; }
 
 int ensure_macro(Level& lv, cudaStream_t st, int64_t& launches)
 {
@@ -350,8 +286,9 @@ int mbl_level_clear(mbl_ctx* ctx, int lev)
 {
     if (!ctx || lev < 0 || lev >= MAX_LEVELS) return fail("bad level");
     Level& lv = ctx->lev[lev];
-    if (!lv.defined) return 0;
     cudaSetDevice(ctx->device);
+    if (ctx->plev[lev]) patch_clear(ctx, lev);
+    if (!lv.defined) return 0;
     cudaStreamSynchronize(ctx->stream);
     if (lv.owned && lv.base) cudaFree(lv.base);
     if (lv.flag_stage) cudaFree(lv.flag_stage);
@@ -385,31 +322,7 @@ int mbl_level_define(mbl_ctx* ctx, int lev, const mbl_level_geom* g, void* devic
     lv.L.wrap[0] = lv.L.wrap[1] = all_periodic;
     lv.L.wrap[2] = all_periodic && lv.local_z;
     if (!lv.local_z && lv.L.nz < GZ) return fail("a z-slab needs at least %d planes", GZ);
-    const mbl_params& pr = ctx->prm;
-    lv.P.nu = pr.nu;
-    lv.P.alpha = pr.alpha;
-    lv.P.R = pr.R;
-    lv.P.gamma = pr.gamma;
-    lv.P.cv = pr.R / (pr.gamma - 1.0);  // LBM.cpp:640
-    lv.P.dt = g->dt;
-    lv.P.mesh_speed = pr.mesh_speed;
-    for (int d = 0; d < 3; ++d) {
-        lv.P.idx[d] = g->inv_dx[d];
-        lv.B.periodic[d] = pr.periodic[d];
-        lv.B.prob_lo[d] = g->prob_lo[d];
-        lv.B.prob_hi[d] = g->prob_hi[d];
-        lv.B.dx[d] = g->dx[d];
-    }
-    for (int n = 0; n < 6; ++n) lv.B.bc[n] = pr.bc_type[n];
-    lv.B.vbc_kind = pr.vbc_kind;
-    lv.B.vbc_dir = pr.vbc_dir;
-    lv.B.vbc_normal_dir = pr.vbc_normal_dir;
-    lv.B.vbc_tangential_dir = pr.vbc_tangential_dir;
-    lv.B.vbc_u = pr.vbc_u;
-    lv.B.vbc_rho = pr.vbc_rho;
-    lv.B.vbc_T = pr.vbc_T;
-    lv.B.vbc_gamma = pr.vbc_gamma;
-    lv.B.vbc_R = pr.vbc_R;
+    level_phys_bc(ctx->prm, *g, lv.P, lv.B);
 
     const StateMap m = state_map(lv.L);
     if (device_state) {
@@ -559,11 +472,10 @@ int mbl_download_derived(mbl_ctx* ctx, int lev, double* fab)
 
 int mbl_initialize(mbl_ctx* ctx, int lev, int ic_kind, const double* v, int nv)
 {
-    if (check_level(ctx, lev)) return 1;
+    const bool patch = is_patch(ctx, lev);
+    if (!patch && check_level(ctx, lev)) return 1;
     if (nv < 16 || !v) return fail("mbl_initialize: need 16 parameters");
     if (ic_kind < 0 || ic_kind > 4) return fail("mbl_initialize: unknown initial condition %d", ic_kind);
-    Level& lv = ctx->lev[lev];
-    lv.carry_valid = false;
     CU(cudaSetDevice(ctx->device));
     IcInfo I;
     I.kind = ic_kind;
@@ -574,6 +486,9 @@ int mbl_initialize(mbl_ctx* ctx, int lev, int ic_kind, const double* v, int nv)
     I.wave_length = v[8];
     I.T0 = v[9], I.gamma = v[10], I.R = v[11], I.c_s = v[12];
     I.density_ratio = v[13], I.temperature_ratio = v[14], I.x_disc = v[15];
+    if (patch) return patch_initialize(ctx, lev, I);
+    Level& lv = ctx->lev[lev];
+    lv.carry_valid = false;
     ctx->launches += launch_initialize(lv.L, lv.B, I, lv.p.flag, curf(lv), curg(lv), ctx->stream);
     CU(cudaGetLastError());
     return 0;
@@ -581,6 +496,10 @@ int mbl_initialize(mbl_ctx* ctx, int lev, int ic_kind, const double* v, int nv)
 
 int mbl_fillpatch(mbl_ctx* ctx, int lev, double /*time*/)
 {
+    if (is_patch(ctx, lev)) {
+        CU(cudaSetDevice(ctx->device));
+        return patch_fillpatch(ctx, lev, 0.0);
+    }
     if (check_level(ctx, lev)) return 1;
     Level& lv = ctx->lev[lev];
     CU(cudaSetDevice(ctx->device));
@@ -591,6 +510,10 @@ int mbl_fillpatch(mbl_ctx* ctx, int lev, double /*time*/)
 
 int mbl_physbc(mbl_ctx* ctx, int lev, double /*time*/)
 {
+    if (is_patch(ctx, lev)) {
+        CU(cudaSetDevice(ctx->device));
+        return patch_physbc(ctx, lev, 0.0);
+    }
     if (check_level(ctx, lev)) return 1;
     Level& lv = ctx->lev[lev];
     CU(cudaSetDevice(ctx->device));
@@ -601,6 +524,10 @@ int mbl_physbc(mbl_ctx* ctx, int lev, double /*time*/)
 
 int mbl_stream(mbl_ctx* ctx, int lev)
 {
+    if (is_patch(ctx, lev)) {
+        CU(cudaSetDevice(ctx->device));
+        return patch_stream(ctx, lev);
+    }
     if (check_level(ctx, lev)) return 1;
     Level& lv = ctx->lev[lev];
     lv.carry_valid = false;
@@ -614,6 +541,10 @@ int mbl_stream(mbl_ctx* ctx, int lev)
 
 int mbl_collide(mbl_ctx* ctx, int lev, int want_macro)
 {
+    if (is_patch(ctx, lev)) {
+        CU(cudaSetDevice(ctx->device));
+        return patch_collide(ctx, lev, want_macro);
+    }
     if (check_level(ctx, lev)) return 1;
     Level& lv = ctx->lev[lev];
     lv.carry_valid = false;
@@ -631,6 +562,10 @@ int mbl_collide(mbl_ctx* ctx, int lev, int want_macro)
 
 int mbl_f_to_macrodata(mbl_ctx* ctx, int lev)
 {
+    if (is_patch(ctx, lev)) {
+        CU(cudaSetDevice(ctx->device));
+        return patch_f_to_macrodata(ctx, lev);
+    }
     if (check_level(ctx, lev)) return 1;
     Level& lv = ctx->lev[lev];
     CU(cudaSetDevice(ctx->device));
@@ -643,6 +578,10 @@ int mbl_f_to_macrodata(mbl_ctx* ctx, int lev)
 
 int mbl_compute_derived(mbl_ctx* ctx, int lev)
 {
+    if (is_patch(ctx, lev)) {
+        CU(cudaSetDevice(ctx->device));
+        return patch_compute_derived(ctx, lev);
+    }
     if (check_level(ctx, lev)) return 1;
     Level& lv = ctx->lev[lev];
     if (!lv.macro) return fail("mbl_compute_derived needs macrodata");

@@ -12,6 +12,7 @@
 // is the fastest index so every load/store of a component plane is coalesced; stores
 // and e_x = 0 loads are 128-byte aligned, e_x = +-1 loads are shifted by one element.
 #include "kernels.cuh"
+#include "bcic.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -1156,34 +1157,6 @@ __global__ void __launch_bounds__(128) k_xywrap(double* __restrict__ f, double* 
     }
 }
 
-// inlet functors (VelocityBC.H:44-190) at the literal (un-wrapped) global ghost index
-__device__ __forceinline__ void vel_bc_op(const BcInfo& B, const Layout& L, int gi, int gj, int gk, double& rho,
-                                          double vel[3], double& R, double& T, double& gamma)
-{
-    const int iv[3] = {gi, gj, gk};
-    if (B.vbc_kind == 1) {
-        rho = B.vbc_rho;
-        vel[B.vbc_dir] = B.vbc_u;
-    } else if (B.vbc_kind == 2) {
-        rho = B.vbc_rho;
-        const double c1 = (double)(iv[1] * (L.dhi[1] - iv[1]));
-        const double c2 = (double)(iv[2] * (L.dhi[2] - iv[2]));
-        const double d = (double)(L.dhi[1] + 1);
-        vel[0] = 16.0 * B.vbc_u * c1 * c2 / (d * d * d * d);
-    } else if (B.vbc_kind == 3) {
-        rho = B.vbc_rho;
-        const int nd = B.vbc_normal_dir;
-        const double height = B.prob_hi[nd] - B.prob_lo[nd];
-        const double x = B.prob_lo[nd] + (iv[nd] + 0.5) * B.dx[nd];
-        vel[B.vbc_tangential_dir] = 4.0 * B.vbc_u * x * (height - x) / (height * height);
-    } else {
-        return;
-    }
-    R = B.vbc_R;
-    T = B.vbc_T;
-    gamma = B.vbc_gamma;
-}
-
 struct Region {
     int lo[3], hi[3];     // cells of the region (local indices, inclusive)
     int in_lo[3], in_hi[3];  // the `inside` box of BC.H:374-380
@@ -1214,7 +1187,7 @@ __global__ void __launch_bounds__(64) k_bc_region(double* __restrict__ f, double
             // quantities that do not depend on q
             double vel[3] = {0.0, 0.0, 0.0}, R = 1.0, T = 1.0 / 3.0, gamma = 5.0 / 3.0;
             double rho_bc = (bc == 3) ? 1.0 : 0.0;
-            if (bc == 2 || bc == 3) vel_bc_op(B, L, i + L.lo[0], j + L.lo[1], k + L.lo[2], rho_bc, vel, R, T, gamma);
+            if (bc == 2 || bc == 3) vel_bc_op(B, L.dhi, i + L.lo[0], j + L.lo[1], k + L.lo[2], rho_bc, vel, R, T, gamma);
             for (int q = 0; q < NQ; ++q) {
                 const int e[3] = {c_dir.ex[q], c_dir.ey[q], c_dir.ez[q]};
                 const int in = i + e[0], jn = j + e[1], kn = k + e[2];
@@ -1334,45 +1307,8 @@ __global__ void __launch_bounds__(128) k_initialize(double* __restrict__ f, doub
     if (i > L.nx - 1 + GX) return;
     const long long c = L.cell(i, j, k);
     const int gi = i + L.lo[0], gj = j + L.lo[1], gk = k + L.lo[2];
-    double rho = 1.0, vel[3] = {0.0, 0.0, 0.0}, T = 1.0 / 3.0, R = 1.0, gamma = 1.667;
-    const double PI = 3.14159265358979323846;
-    if (I.kind == 0) {  // IC.H:42-57
-        rho = I.density;
-        vel[0] = I.vel[0], vel[1] = I.vel[1], vel[2] = I.vel[2];
-        T = I.T0, R = I.R, gamma = I.gamma;
-    } else if (I.kind == 1) {  // IC.H:119-153
-        const double x = B.prob_lo[0] + (gi + 0.5) * B.dx[0];
-        const double y = B.prob_lo[1] + (gj + 0.5) * B.dx[1];
-        const double z = B.prob_lo[2] + (gk + 0.5) * B.dx[2];
-        const double Lc = 1.0 / PI;
-        rho = I.density + I.density * I.v0 * I.v0 / 16.0 * (cos(2.0 * I.omega[0] * x / Lc) + cos(2.0 * I.omega[1] * y / Lc)) *
-                              (cos(2.0 * I.omega[2] * z / Lc) + 2.0);
-        vel[0] = I.v0 * sin(I.omega[0] * x / Lc) * cos(I.omega[1] * y / Lc) * cos(I.omega[2] * z / Lc);
-        vel[1] = -I.v0 * cos(I.omega[0] * x / Lc) * sin(I.omega[1] * y / Lc) * cos(I.omega[2] * z / Lc);
-        vel[2] = 0.0;
-        T = I.T0, R = I.R, gamma = 5.0 / 3.0;
-    } else if (I.kind == 2) {  // IC.H:213-240
-        const double y = B.prob_lo[1] + (gj + 0.5 * 0.0) * B.dx[1];
-        rho = I.density;
-        vel[0] = I.vel[0] + 0.010 * I.c_s * sin(2.0 * PI * y / I.wave_length);
-        vel[1] = I.vel[1], vel[2] = I.vel[2];
-        T = I.T0, R = I.R, gamma = I.gamma;
-    } else if (I.kind == 3) {  // IC.H:302-333
-        const double y = B.prob_lo[1] + (gj + 0.5 * 0.0) * B.dx[1];
-        R = I.R;
-        const double pressure = I.density * R * I.T0;
-        rho = I.density + 0.0010 * I.T0 * sin(2.0 * PI * y / I.wave_length);
-        vel[0] = I.vel[0], vel[1] = I.vel[1], vel[2] = I.vel[2];
-        gamma = I.gamma;
-        T = pressure / (rho * R);
-    } else if (I.kind == 4) {  // IC.H:394-428
-        const double x = B.prob_lo[0] + (gi + 0.5 * 0.0) * B.dx[0];
-        R = I.R, gamma = I.gamma;
-        vel[0] = I.vel[0], vel[1] = I.vel[1], vel[2] = I.vel[2];
-        const double s = 0.5 * (1.0 + tanh((x - I.x_disc) * 3.0));
-        rho = I.density + s * (I.density_ratio * I.density - I.density);
-        T = I.T0 + s * (I.temperature_ratio * I.T0 - I.T0);
-    }
+    double rho, vel[3], T, R, gamma;
+    ic_state(I, B, gi, gj, gk, rho, vel, T, R, gamma);
     const bool solid = !(flag[c] & FLAG_FLUID);
     for (int q = 0; q < NQ; ++q) {
         f[(long long)q * L.sq + c] = solid ? 0.0 : feq_std(rho, vel, R * T, q);

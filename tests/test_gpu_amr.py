@@ -1,0 +1,187 @@
+"""Multi-box / multi-level (AMR-exact) mode of the CUDA path through the C ABI (mbl_level_define_boxes, mbl_fillpatch
+with coarse-fine interpolation, grown-box mbl_stream, mbl_average_down, mbl_collide) against golden vectors written by
+the unmodified reference on 2- and 3-level decks (BASELINE configs 4-5 at reduced size) and against the multi-level
+oracle on seeded random states.  Sub-cycling order driven from Python (marbles_b200/amr.py) as LBM::time_step does.
+Tolerance: 1e-12 of the field scale per level step (tests/parity.py)."""
+import numpy as np
+import pytest
+
+from conftest import AMR_GOLDEN_CASES, load_amr_golden
+from parity import compare, scales
+
+pytestmark = pytest.mark.gpu
+
+
+def nan0(d):
+    return {k: np.where(np.isnan(v), 0.0, v) for k, v in d.items()}
+
+
+def golden_level(z, step, lev):
+    pre = f"s{step}_l{lev}_"
+    return {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
+
+
+def compare_levels(amr, ref_of_level, nsteps_coarse, inp, macro=True, keys=None):
+    worst_all = 0.0
+    for lev in range(amr.finest + 1):
+        ref = ref_of_level(lev)
+        got = amr.fields(lev, macro=macro)
+        cover = ~np.isnan(ref["f_00"])
+        assert (np.isnan(got["f_00"]) == ~cover).all(), f"level {lev}: box coverage differs"
+        r0 = nan0(ref)
+        if "rho" not in r0:  # step 0 goldens hold f, g and macrodata; oracle dicts always do
+            raise AssertionError("reference fields lack macrodata")
+        sc = scales(r0, inp.R, inp.gamma, 2 ** lev / inp.dx[0])
+        nsteps = nsteps_coarse * 2 ** lev
+        worst, key = compare(nan0(got), r0, sc, nsteps, keys=keys)
+        print(f"  level {lev}: worst {worst:.2e} ({key}) after {nsteps} level steps")
+        worst_all = max(worst_all, worst)
+    return worst_all
+
+
+def new_amr(case):
+    from marbles_b200.amr import AmrLBM
+    from marbles_b200.inputs import parse_deck
+    z, deck_text, steps, boxes, is_fluid = load_amr_golden(case)
+    amr = AmrLBM(parse_deck(text=deck_text), boxes, is_fluid)
+    amr.init_data()
+    return amr, z, deck_text, steps, boxes, is_fluid
+
+
+@pytest.mark.parametrize("case", AMR_GOLDEN_CASES)
+def test_amr_cuda_vs_reference_golden(case):
+    amr, z, deck_text, steps, boxes, is_fluid = new_amr(case)
+    fg = [f"f_{q:02d}" for q in range(27)] + [f"g_{q:02d}" for q in range(27)]
+    done = 0
+    for s in steps:
+        if s == 0:
+            compare_levels(amr, lambda lev: golden_level(z, 0, lev), 1, amr.inp, macro=False, keys=fg)
+            continue
+        amr.step(s - done, want_macrodata=True)
+        done = s
+        last = s == steps[-1]
+        print(f"{case} step {s}")
+        ref_of = lambda lev: golden_level(z, s, lev)
+        if last:
+            compare_levels(amr, ref_of, s, amr.inp)
+        else:  # mid steps store the 19 macrodata fields only
+            for lev in range(amr.finest + 1):
+                ref, got = nan0(ref_of(lev)), nan0(amr.fields(lev))
+                full = nan0(golden_level(z, steps[-1], lev))
+                sc = scales(full, amr.inp.R, amr.inp.gamma, 2 ** lev / amr.inp.dx[0])
+                compare(got, ref, sc, s * 2 ** lev, keys=list(ref.keys()))
+    amr.close()
+
+
+@pytest.mark.parametrize("case", ["amr2_tg", "amr3_chcyl"])
+def test_amr_random_state_vs_oracle(oracle_mod, case):
+    """seeded random perturbation of f, g on every level, two coarse steps against the multi-level oracle"""
+    from oracle import amr_oracle as A
+    O = oracle_mod
+    amr, z, deck_text, steps, boxes, is_fluid = new_amr(case)
+    o = A.AmrOracle(O.lbm_setup(O.parse_deck(None, deck_text.splitlines())), boxes, is_fluid)
+    o.initialize()
+    rng = np.random.default_rng(99)
+    for lev, L in enumerate(o.levels):
+        for ib, b in enumerate(L.boxes):
+            for name, which in (("f", 0), ("g", 1)):
+                a = getattr(b, name)
+                a[:] = np.where(a > 0, a * (1.0 + 0.03 * rng.standard_normal(a.shape)), a)
+        L.fill_boundary("f", 3)
+        L.fill_boundary("g", 3)
+        for ib, b in enumerate(L.boxes):
+            amr.set_box(lev, ib, 0, b.f, ng=3)
+            amr.set_box(lev, ib, 1, b.g, ng=3)
+    nsteps = 2
+    o.step(nsteps)
+    amr.step(nsteps, want_macrodata=True)
+    worst = compare_levels(amr, lambda lev: o.fields(lev), nsteps, amr.inp)
+    print(f"{case}: worst {worst:.2e}")
+    amr.close()
+
+
+def test_level_bind_is_zero_copy_and_bit_identical():
+    """mbl_level_bind: the fine level's boxes live in caller-owned device memory (torch tensors standing in for the
+    FABs of an AMReX device-arena MultiFab, 27 comps x 3 ghost cells); every operator leaves its result there"""
+    import ctypes as C
+    import torch
+    from marbles_b200._lib import check
+    a, z, deck_text, steps, boxes, is_fluid = new_amr("amr2_chcyl")
+    b, *_ = new_amr("amr2_chcyl")
+    lev = 1
+    fabs = []
+    for ib in range(len(boxes[lev])):
+        pair = []
+        for which in (0, 1):
+            host = b.get_box(lev, ib, which, ng=3)
+            t = torch.from_numpy(host).cuda()
+            check(b.lib.mbl_level_bind(b.ctx, lev, ib, which, C.c_void_p(t.data_ptr())))
+            pair.append(t)
+        fabs.append(pair)
+    a.step(3)
+    b.step(3)
+    a.sync(), b.sync()
+    for l in range(2):
+        assert np.array_equal(a.dense(l, "f"), b.dense(l, "f"), equal_nan=True)
+        assert np.array_equal(a.dense(l, "g"), b.dense(l, "g"), equal_nan=True)
+    for ib, (tf, tg) in enumerate(fabs):  # the caller's memory holds the state, ghost cells included
+        assert np.array_equal(tf.cpu().numpy(), a.get_box(lev, ib, 0, ng=3))
+        assert np.array_equal(tg.cpu().numpy(), a.get_box(lev, ib, 1, ng=3))
+    a.close()
+    b.close()
+
+
+def test_redefine_level_after_regrid(oracle_mod):
+    """the box list of the fine level changes between two coarse steps (what RemakeLevel hands over after a regrid:
+    same region, different boxes); the run continues and matches the oracle driven through the same change"""
+    from oracle import amr_oracle as A
+    O = oracle_mod
+    amr, z, deck_text, steps, boxes, is_fluid = new_amr("amr2_tg")
+    setup = O.lbm_setup(O.parse_deck(None, deck_text.splitlines()))
+    o = A.AmrOracle(setup, boxes, is_fluid)
+    o.initialize()
+    o.step(2)
+    amr.step(2)
+    # new fine box list: the same region cut differently (pairs of x-neighbours merged)
+    old = boxes[1]
+    merged, used = [], set()
+    for i, (lo, hi) in enumerate(old):
+        if i in used:
+            continue
+        mate = next((j for j, (l2, h2) in enumerate(old) if j not in used and j != i and l2[0] == hi[0] + 1 and
+                     l2[1:] == lo[1:] and h2[1:] == hi[1:]), None)
+        if mate is None:
+            merged.append((lo, hi))
+        else:
+            used.add(mate)
+            merged.append((lo, [old[mate][1][0], hi[1], hi[2]]))
+        used.add(i)
+    assert len(merged) < len(old)
+    new_boxes = [boxes[0], merged]
+    amr.redefine_level(1, merged, is_fluid[1])
+    o2 = A.AmrOracle(setup, new_boxes, is_fluid)
+    for lev in range(2):
+        for name in ("f", "g"):
+            G = o.levels[lev].gather(name, 27)
+            for b in o2.levels[lev].boxes:
+                getattr(b, name)[:, 3:-3, 3:-3, 3:-3] = G[:, b.lo[2]:b.hi[2] + 1, b.lo[1]:b.hi[1] + 1, b.lo[0]:b.hi[0] + 1]
+            o2.levels[lev].fill_boundary(name, 3)
+    o2.step(2)
+    amr.step(2, want_macrodata=True)
+    worst = compare_levels(amr, lambda lev: o2.fields(lev), 4, amr.inp)
+    print(f"regrid: worst {worst:.2e}")
+    amr.close()
+
+
+def test_fine_box_next_to_a_wall_is_refused():
+    """the documented restriction fails loudly instead of interpolating wrongly"""
+    from marbles_b200._lib import MarblesError
+    from marbles_b200.amr import AmrLBM
+    from marbles_b200.inputs import parse_deck
+    z, deck_text, steps, boxes, is_fluid = load_amr_golden("amr2_chcyl")
+    fine = [([16, 0, 0], [31, 15, 7])]  # touches the no-slip wall at y = 0
+    amr = AmrLBM(parse_deck(text=deck_text), [boxes[0], fine], None)
+    with pytest.raises(MarblesError, match="non-periodic domain face"):
+        amr.init_data()  # the first inter-level operator (average_down after initialisation) builds the tag lists
+        amr.step(1)
+    amr.close()
