@@ -222,10 +222,14 @@ int mbl_create(const mbl_params* params, int device, mbl_ctx** out)
         if (!params->periodic[d] && (params->bc_type[d] == 0 || params->bc_type[d + 3] == 0))
             return fail("BC is interior in direction %d but not periodic", d);
     }
-    mbl_ctx* c = new mbl_ctx();
+    int sm_count = 148;
+    CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    init_tables();
+    CU(cudaGetLastError());
+    mbl_ctx* c = new mbl_ctx();  // nothing below can fail: the context is never leaked
     c->prm = *params;
     c->device = device;
-    CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    c->sm_count = sm_count;
     if (const char* e = getenv("MBL_VARIANT")) c->variant = atoi(e);
     if (const char* e = getenv("MBL_UW")) c->uw = atoi(e) == 256 ? 256 : 128;
     if (const char* e = getenv("MBL_BAND")) c->band_rows = atoi(e) > 0 ? atoi(e) : 16;
@@ -239,8 +243,6 @@ int mbl_create(const mbl_params* params, int device, mbl_ctx** out)
     if (const char* e = getenv("MBL_OWN")) c->carry_own = atoi(e) == 28 ? 28 : 30;
     if (const char* e = getenv("MBL_KY")) c->carry_ky = atoi(e) > 0 ? atoi(e) : 32;
     if (const char* e = getenv("MBL_MINB")) c->carry_minb = atoi(e) >= 2 && atoi(e) <= 5 ? atoi(e) : 2;
-    init_tables();
-    CU(cudaGetLastError());
     *out = c;
     return 0;
 }
@@ -250,6 +252,10 @@ int mbl_destroy(mbl_ctx* ctx)
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     for (int l = 0; l < MAX_LEVELS; ++l) mbl_level_clear(ctx, l);
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    if (ctx->s_up) cudaStreamDestroy(ctx->s_up);
+    if (ctx->s_down) cudaStreamDestroy(ctx->s_down);
+    if (ctx->s_capture) cudaStreamDestroy(ctx->s_capture);
     delete ctx;
     return 0;
 }

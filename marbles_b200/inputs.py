@@ -102,6 +102,9 @@ def lbm_inputs(deck: dict) -> LbmInputs:
     periodic = tuple(_vector(deck, "geometry.is_periodic", [0, 0, 0], int))
     bc_lo = tuple(_vector(deck, "lbm.bc_lo", [0, 0, 0], int))
     bc_hi = tuple(_vector(deck, "lbm.bc_hi", [0, 0, 0], int))
+    for b in bc_lo + bc_hi:  # Source/LBM.cpp:109-150: anything else aborts with "Invalid bc_lo" / "Invalid bc_hi"
+        if b not in (0, 1, 2, 3, 5, 6, 7, 8):
+            raise DeckError(f"Invalid bc_lo / bc_hi code {b}")
     for d in range(3):  # Source/LBM.cpp:227-252
         if periodic[d]:
             if bc_lo[d] != BC_PERIODIC:

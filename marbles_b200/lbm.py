@@ -49,6 +49,27 @@ def slab_bounds(nz: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0) - 1
 
 
+def wrap_periodic(a: np.ndarray, ng: int, n, periodic) -> np.ndarray:
+    """m_is_fluid.FillBoundary(periodicity) on one box that spans the domain (n cells per direction): ghost cells in
+    periodic directions mirror the valid cells; a is [nz + 2 ng, ny + 2 ng, nx + 2 ng]."""
+    for axis, d in ((2, 0), (1, 1), (0, 2)):
+        if periodic[d]:
+            idx = (np.arange(-ng, n[d] + ng) % n[d]) + ng
+            a = np.take(a, idx, axis=axis)
+    return np.ascontiguousarray(a)
+
+
+def slab_is_fluid_from_deck(inp: LbmInputs, zlo: int, zhi: int, ng: int = F_NGHOST) -> np.ndarray:
+    """is_fluid (component 0) of the z-slab [zlo, zhi] grown by ng for the analytic body of the deck.  Ghost planes
+    that belong to a neighbouring rank, or to the periodic image at the domain ends, hold THOSE cells
+    (m_is_fluid.FillBoundary(periodicity), Source/LBM.cpp:1234); planes beyond a non-periodic domain end keep the
+    geometry evaluated beyond the domain (Source/LBM.cpp:1222-1232).  The body is analytic, so the whole domain is
+    evaluated once, wrapped, and the slab cut out."""
+    glob = is_fluid_from_deck(inp.deck, inp.n_cell, inp.prob_lo, inp.dx, (0, 0, 0), inp.n_cell, ng)
+    glob = wrap_periodic(glob, ng, inp.n_cell, inp.periodic)
+    return np.ascontiguousarray(glob[zlo:zhi + 1 + 2 * ng])
+
+
 class LBM:
     """Single-level lattice-Boltzmann state of one rank (one z-slab of the domain) on one B200."""
 
@@ -131,30 +152,32 @@ class LBM:
         nx, ny, nz = self.n_local
         full = (nz + 2 * ng, ny + 2 * ng, nx + 2 * ng)
         if is_fluid is None:
-            a = is_fluid_from_deck(self.inp.deck, self.inp.n_cell, self.inp.prob_lo, self.inp.dx, self.lo,
-                                   self.n_local, ng)
+            a = slab_is_fluid_from_deck(self.inp, self.lo[2], self.hi[2], ng)
             if a.min() == 1:
                 self._is_fluid = a
                 check(self.lib.mbl_set_all_fluid(self.ctx, self.lev))
                 return
-            a = self._wrap_periodic(a, ng, z_local=self.world == 1)
         else:
             is_fluid = np.asarray(is_fluid, dtype=np.int32)
             if is_fluid.shape == full:
                 a = np.ascontiguousarray(is_fluid)
             elif is_fluid.shape == (nz, ny, nx):
+                if self.world > 1:
+                    raise MarblesError(
+                        "on a z-slab (world > 1) is_fluid must cover the slab grown by 3 cells: the ghost planes are "
+                        "the neighbouring ranks' cells (m_is_fluid.FillBoundary), which a valid-box array cannot supply")
                 a = np.ones(full, dtype=np.int32)
                 a[ng:-ng, ng:-ng, ng:-ng] = is_fluid
-                a = self._wrap_periodic(a, ng, z_local=self.world == 1)
+                a = self._wrap_periodic(a, ng, z_local=True)
             else:
                 raise MarblesError(f"is_fluid has shape {is_fluid.shape}, expected {(nz, ny, nx)} or {full}")
         self._is_fluid = a
         check(self.lib.mbl_set_is_fluid(self.ctx, self.lev, a.ctypes.data_as(C.POINTER(C.c_int32)), ng))
 
-    def _wrap_periodic(self, a: np.ndarray, ng: int, z_local: bool) -> np.ndarray:
+    def _wrap_periodic(self, a: np.ndarray, ng: int, z_local: bool, n_local=None) -> np.ndarray:
         """m_is_fluid.FillBoundary(periodicity): ghost cells in periodic directions mirror the valid cells."""
         a = a.copy()
-        nloc = self.n_local
+        nloc = self.n_local if n_local is None else n_local
         for axis, d in ((2, 0), (1, 1), (0, 2)):
             if not self.inp.periodic[d] or (d == 2 and not z_local):
                 continue
@@ -352,11 +375,11 @@ class LBM:
         from .plotfile import write_lbm_plotfile
         return write_lbm_plotfile(self, directory, prefix)
 
-    def write_checkpoint_file(self, directory: str = ".", prefix: str = "chk") -> str:
+    def write_checkpoint_file(self, directory: str = ".", prefix: str = "chk", digits: int = 5) -> str:
         """LBM::write_checkpoint_file (Source/LBM.cpp:1692-1783): `<prefix><step:05d>` with Header, f_00 and g_00
         VisMF files (3 ghost cells); the unmodified reference restarts from it (amr.restart)."""
         from . import plotfile as P
-        path = os.path.join(directory, P.chk_file_name(prefix, self.isteps))
+        path = os.path.join(directory, P.chk_file_name(prefix, self.isteps, digits))
         deck = self.inp.deck
         mgs = deck.get("amr.max_grid_size", 32)
         mgs = int(str(mgs[0] if isinstance(mgs, (list, tuple)) else mgs).split()[0])

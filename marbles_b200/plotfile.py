@@ -143,13 +143,13 @@ def write_plotfile(path: str, names: list[str], data: np.ndarray, *, time: float
         fh.write("Level_0/Cell\n")
 
 
-def plot_file_name(prefix: str, step: int) -> str:
-    """amrex::Concatenate(plot_file, step, 5) (Source/LBM.cpp:1617-1621)"""
-    return f"{prefix}{step:05d}"
+def plot_file_name(prefix: str, step: int, digits: int = 5) -> str:
+    """amrex::Concatenate(plot_file, step, m_file_name_digits) (Source/LBM.cpp:1617-1621; amr.file_name_digits)"""
+    return f"{prefix}{step:0{digits}d}"
 
 
 def write_lbm_plotfile(lbm, directory: str = ".", prefix: str = "plt", max_grid_size: int | None = None,
-                       save_streaming: bool | None = None, save_derived: bool | None = None) -> str:
+                       save_streaming: bool | None = None, save_derived: bool | None = None, digits: int = 5) -> str:
     """LBM::write_plot_file: the macrodata must be current (last step taken with want_macrodata=True, as the
     reference's post_time_step leaves it).  On several ranks every rank writes the FABs of its z-slab and rank 0 the
     headers (collective call; compute_derived exchanges the neighbours' macrodata planes first)."""
@@ -178,7 +178,7 @@ def write_lbm_plotfile(lbm, directory: str = ".", prefix: str = "plt", max_grid_
     fl = lbm._is_fluid[ng:-ng, ng:-ng, ng:-ng] if ng else lbm._is_fluid
     parts.append(np.stack([fl.astype(np.float64), eb_boundary(lbm._is_fluid, ng).astype(np.float64)]))
     data = np.concatenate(parts, axis=0)
-    path = os.path.join(directory, plot_file_name(prefix, lbm.isteps))
+    path = os.path.join(directory, plot_file_name(prefix, lbm.isteps, digits))
     if lbm.world == 1:
         write_plotfile(path, names, data, time=lbm.time, step=lbm.isteps, prob_lo=lbm.inp.prob_lo,
                        prob_hi=lbm.inp.prob_hi, max_grid_size=max_grid_size)
@@ -315,8 +315,8 @@ def read_vismf(lev_dir: str, prefix: str, zrange=None):
     return data, ng, boxes
 
 
-def chk_file_name(prefix: str, step: int) -> str:
-    return f"{prefix}{step:05d}"
+def chk_file_name(prefix: str, step: int, digits: int = 5) -> str:
+    return f"{prefix}{step:0{digits}d}"
 
 
 def write_checkpoint(path: str, f: np.ndarray, g: np.ndarray, *, step: int, dt: float, time: float, periodic,

@@ -32,8 +32,13 @@ def evolve(lbm: LBM, out_dir: str = ".", log=print) -> list[str]:
     plot_file, plot_int = _get(deck, "amr.plot_file", "plt"), _get(deck, "amr.plot_int", -1, int)
     chk_file, chk_int = _get(deck, "amr.chk_file", "chk"), _get(deck, "amr.chk_int", -1, int)
     restart = _get(deck, "amr.restart", "")
+    digits = _get(deck, "amr.file_name_digits", 5, int)  # Source/LBM.cpp:215
     if _get(deck, "amr.max_level", 0, int) > 0:
         raise MarblesError("marbles_b200.run drives single-level decks (amr.max_level = 0)")
+    if stop_time < float("inf") and abs(stop_time - round(stop_time)) > 1.0e-9:
+        # the reference shortens the LAST lattice step to dt = stop_time - t (compute_dt, Source/LBM.cpp:1067-1071),
+        # which changes the relaxation of that step; the fused step runs whole steps only
+        raise MarblesError("stop_time must be a whole number of lattice time steps (dt = 1)")
     written = []
     # lbm.compute_forces: one line of EB forces per step (open_forces_file / output_forces_file,
     # Source/LBM.cpp:1925-1969: width 24, 16 significant digits); forces every step means stepping one at a time
@@ -49,11 +54,11 @@ def evolve(lbm: LBM, out_dir: str = ".", log=print) -> list[str]:
             fh.write("".join("%24s" % ("%.16g" % v) for v in (lbm.time, f3[0], f3[1], f3[2])) + "\n")
 
     def plot():
-        written.append(write_lbm_plotfile(lbm, out_dir, plot_file))
+        written.append(write_lbm_plotfile(lbm, out_dir, plot_file, digits=digits))
         log(f"Writing plot file {written[-1]} at time {lbm.time}")
 
     def chk():
-        written.append(lbm.write_checkpoint_file(out_dir, chk_file))
+        written.append(lbm.write_checkpoint_file(out_dir, chk_file, digits=digits))
         log(f"Writing checkpoint file {written[-1]} at time {lbm.time}")
 
     if restart:
@@ -82,11 +87,15 @@ def evolve(lbm: LBM, out_dir: str = ".", log=print) -> list[str]:
             nxt = min(nxt, lbm.isteps + max(1, int((stop_time - lbm.time) / lbm.dt + 1e-6)))
         n = nxt - lbm.isteps
         want_plot = plot_int > 0 and nxt % plot_int == 0
+        # the closing plotfile (below) is written whenever the run ends off the plot cadence, by max_step or by
+        # stop_time: its macrodata must belong to the last step (the reference recomputes macrodata every step)
+        ends_run = nxt >= max_step or lbm.time + n * lbm.dt >= stop_time - 1.0e-6 * lbm.dt
+        want_macro = want_plot or (plot_int > 0 and ends_run) or nxt >= max_step
         if forces_path is None:
-            lbm.step(n, want_macrodata=want_plot or nxt >= max_step)
+            lbm.step(n, want_macrodata=want_macro)
         else:
             for s in range(n):
-                lbm.step(1, want_macrodata=(s == n - 1) and (want_plot or nxt >= max_step))
+                lbm.step(1, want_macrodata=(s == n - 1) and want_macro)
                 forces_line()
         if want_plot:
             last_plot = lbm.isteps

@@ -30,3 +30,37 @@ def test_deck_quantities():
     ov = parse_deck(text=deck_text, overrides=["amr.n_cell = 64 24 8", "lbm.nu=0.02"])
     inp2 = lbm_inputs(ov)
     assert tuple(inp2.n_cell) == (64, 24, 8) and inp2.nu == pytest.approx(0.02)
+
+
+def test_slab_is_fluid_takes_neighbour_and_periodic_planes():
+    """multi-rank decks: the ghost planes of a z-slab hold the neighbouring ranks' cells and, at the domain ends of a
+    periodic direction, the periodic image -- not the body evaluated beyond the domain (m_is_fluid.FillBoundary)"""
+    import numpy as np
+    from conftest import load_golden
+    from marbles_b200.inputs import lbm_inputs, parse_deck
+    from marbles_b200.lbm import slab_bounds, slab_is_fluid_from_deck, wrap_periodic
+    _, deck_text, _ = load_golden("chcyl")  # cylinder along the periodic z direction: solid cells cross every slab cut
+    inp = lbm_inputs(parse_deck(text=deck_text))
+    ng, nz = 3, inp.n_cell[2]
+    whole = slab_is_fluid_from_deck(inp, 0, nz - 1, ng)
+    assert (whole == 0).any()
+    valid = whole[ng:-ng, ng:-ng, ng:-ng]
+    for world in (2, 4):
+        for rank in range(world):
+            lo, hi = slab_bounds(nz, rank, world)
+            a = slab_is_fluid_from_deck(inp, lo, hi, ng)
+            assert a.shape == (hi - lo + 1 + 2 * ng,) + whole.shape[1:]
+            for k in range(lo - ng, hi + ng + 1):  # every plane, ghost planes included, is the wrapped global plane
+                assert np.array_equal(a[k - lo + ng, ng:-ng, ng:-ng], valid[k % nz]), (world, rank, k)
+    # a non-periodic direction keeps the geometry beyond the domain
+    w = wrap_periodic(np.arange(5 * 5 * 5).reshape(5, 5, 5), 1, (3, 3, 3), (1, 0, 0))
+    assert w[2, 2, 0] == w[2, 2, 3] and w[0, 2, 2] == 2 + 2 * 5
+
+
+def test_invalid_bc_code_is_refused():
+    import pytest
+    from conftest import load_golden
+    from marbles_b200.inputs import DeckError, lbm_inputs, parse_deck
+    _, deck_text, _ = load_golden("chcyl")
+    with pytest.raises(DeckError, match="Invalid bc"):
+        lbm_inputs(parse_deck(text=deck_text, overrides=["lbm.bc_lo = 4 1 0"]))

@@ -95,6 +95,7 @@ def test_amr_random_state_vs_oracle(oracle_mod, case):
     nsteps = 2
     o.step(nsteps)
     amr.step(nsteps, want_macrodata=True)
+    amr.compute_derived()  # post_time_step: vorticity of every level
     worst = compare_levels(amr, lambda lev: o.fields(lev), nsteps, amr.inp)
     print(f"{case}: worst {worst:.2e}")
     amr.close()
@@ -168,6 +169,7 @@ def test_redefine_level_after_regrid(oracle_mod):
             o2.levels[lev].fill_boundary(name, 3)
     o2.step(2)
     amr.step(2, want_macrodata=True)
+    amr.compute_derived()
     worst = compare_levels(amr, lambda lev: o2.fields(lev), 4, amr.inp)
     print(f"regrid: worst {worst:.2e}")
     amr.close()
