@@ -61,6 +61,58 @@ amrex.the_arena_is_managed = 0
 """
 
 
+# Wall / EB workload (BASELINE config 4 at benchmark size, single level): channel inlet,
+# zeroth-order outflow, no-slip walls in y, periodic z, EB cylinder along z -- every boundary operator of the path
+CHANNEL_DECK = """
+max_step = 1000000
+geometry.prob_lo = 0.0 0.0 0.0
+geometry.prob_hi = {nx}.0 {ny}.0 {nz}.0
+geometry.is_periodic = 0 0 1
+amr.n_cell = {nx} {ny} {nz}
+amr.max_level = 0
+amr.max_grid_size = {mgs}
+amr.plot_int = -1
+amr.chk_int = -1
+lbm.bc_lo = 2 1 0
+lbm.bc_hi = 5 1 0
+lbm.dx_outer = 1.0
+lbm.dt_outer = 1.0
+lbm.nu = 0.0050
+lbm.save_streaming = 0
+lbm.velocity_bc_type = "channel"
+velocity_bc_channel.initial_density = 1.0
+velocity_bc_channel.Mach_ref = 0.01
+velocity_bc_channel.initial_temperature = 0.03
+lbm.ic_type = "constant"
+ic_constant.density = 1.0
+ic_constant.initial_temperature = 0.03
+ic_constant.mach_components = 0.0 0.0 0.0
+eb2.geom_type = "cylinder"
+eb2.cylinder_radius = {rad}.0
+eb2.cylinder_center = {cx}.0 {cy}.0 0.0
+eb2.cylinder_has_fluid_inside = 0
+eb2.cylinder_height = -1.0
+eb2.cylinder_direction = 2
+amrex.the_arena_is_managed = 0
+"""
+
+
+def workload_deck(args, world: int):
+    """-> (deck text, description, cells per rank are nx*ny*nz/world)"""
+    n = args.size
+    if args.workload == "channel":
+        nx, ny, nz = 2 * n, n // 2, (n // 2) * (world if args.scaling == "weak" else 1)
+        text = CHANNEL_DECK.format(nx=nx, ny=ny, nz=nz, mgs=nx, rad=max(2, ny // 8), cx=nx // 4, cy=ny // 2)
+        desc = (f"channel {nx}x{ny}x{nz} with an EB cylinder: channel-profile velocity inlet, outflow, no-slip walls, "
+                f"periodic z, halfway bounce-back (BASELINE config 4 geometry at benchmark size, single level)")
+    else:
+        nz = n * world if args.scaling == "weak" else n
+        text = TG_DECK.format(nx=n, ny=n, nz=nz, mgs=n)
+        per = f"{n}^3 per GPU" if args.scaling == "weak" else f"{n}^3 in total"
+        desc = (f"periodic Taylor-Green box {per}, single level, D3Q27 f+g fp64 (BASELINE config 3; domain {n}x{n}x{nz})")
+    return text, desc
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -154,33 +206,62 @@ def reference_mlups(size: int, steps: int, threads: int | None = None, exe: str 
     return size ** 3 / sec / 1e6, sec, threads, os.path.basename(exe)
 
 
+def host_memory_bytes():
+    try:
+        return next(int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
+    except Exception:
+        return 32 << 30
+
+
+def reference_sample_size(steps_total: int, cores: int, budget_s: float = 170.0) -> int:
+    """largest box of the reference CPU sample that fits the host memory (the reference keeps ~190 words per cell,
+    SURVEY section 8d) and lets `steps_total` steps finish in the time budget at ~0.22 MLUPS per core"""
+    mem = host_memory_bytes()
+    est = 0.22e6 * max(cores, 1)
+    for n in (512, 384, 256, 192, 128, 96, 64):
+        if 190 * 8 * n ** 3 * 1.25 < mem and n ** 3 * steps_total / est <= budget_s:
+            return n
+    return 64
+
+
 def run_reference_arm(args):
+    """The reference's own CPU implementation (unmodified sources, oracle/_ref OpenMP build) on this box's host
+    cores.  What runs is said in the line: W warm-up steps as one run, then the K timed steps as three runs of
+    about K/3 steps each (median and spread over the runs); each run is the TG deck at `sample` ^3 cells."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    size = args.ref_size
-    vals = []
-    for _ in range(args.warmup and 1 or 0):
-        reference_mlups(size, 1)
-    for _ in range(max(1, min(args.steps, 3))):
-        r = reference_mlups(size, args.ref_steps)
-        if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref executable missing or failed"}))
-            return
-        vals.append(r)
-    mlups = statistics.median(v[0] for v in vals)
+    cores = os.cpu_count() or 1
+    K, W = max(args.steps, 3), max(args.warmup, 1)
+    size = args.ref_size or reference_sample_size(K + W, cores)
+    t0 = time.time()
+    if reference_mlups(size, W) is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref executable missing or failed"}))
+        return
+    parts = [K // 3 + (1 if i < K % 3 else 0) for i in range(3)]
+    vals = [reference_mlups(size, n) for n in parts if n > 0]
+    if any(v is None for v in vals):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref executable failed"}))
+        return
+    ml = sorted(v[0] for v in vals)
+    mlups = statistics.median(ml)
     sec = statistics.median(v[1] for v in vals)
-    sample = f"TG deck {size}^3, {args.ref_steps} steps per run, LBM::evolve() inclusive time ({vals[0][3]})"
+    timed_s = sum(v[1] * n for v, n in zip(vals, parts))
+    sample = (f"TG deck at {size}^3 cells (not the {args.size}^3 of the GPU arm: ~190 words per cell and "
+              f"~{size ** 3 / (mlups * 1e6):.1f} s per step on {vals[0][2]} cores), {W} warm-up steps, then {K} timed steps as "
+              f"{len(vals)} runs of {'/'.join(str(n) for n in parts)} steps; per-step time = LBM::evolve() inclusive "
+              f"(TinyProfiler) / steps; median of the runs, spread {100 * (ml[-1] - ml[0]) / mlups:.0f} % ({vals[0][3]})")
     line = {
         "impl": "reference", "metric": "MLUPS (D3Q27 f+g, fp64)", "value": mlups, "unit": "MLUPS",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"periodic Taylor-Green box {args.size}^3 per GPU, single level, D3Q27 f+g fp64 "
-                               f"(BASELINE config 3; domain {args.size}x{args.size}x{args.size * args.gpus})",
-                   "sample": f"each step = the same deck at {size}^3 on the host cores (the reference's CPU build "
-                             f"needs ~190 words per cell; CPU MLUPS is size-independent to first order)"},
-        "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": vals[0][2], "kind": "reference", "sample": sample},
+        "config": {"workload": f"periodic Taylor-Green box, single level, D3Q27 f+g fp64 (BASELINE config 3), reference CPU "
+                               f"sample at {size}^3 cells per step (the GPU arm runs {args.size}^3 per GPU)",
+                   "sample_size": size, "gpu_arm_size": args.size},
+        "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": vals[0][2], "kind": "reference", "sample": sample,
+                         "runs_mlups": ml, "spread_pct": 100 * (ml[-1] - ml[0]) / mlups},
         "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "steps_executed": sum(parts), "warmup_executed": W, "timed_region_s": timed_s, "wall_s": time.time() - t0,
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -193,8 +274,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=512, help="cells per side per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-size", type=int, default=128)
-    ap.add_argument("--ref-steps", type=int, default=4)
+    ap.add_argument("--ref-size", type=int, default=None,
+                    help="box of the reference CPU sample (default: the largest that fits memory and a ~3 min run)")
+    ap.add_argument("--cpu-size", type=int, default=128, help="box of the cpu_baseline sample of the GPU arm (10-30 s)")
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--workload", default="tg", choices=["tg", "channel"],
+                    help="tg: periodic Taylor-Green box (BASELINE config 3, the headline); channel: inlet / outflow / "
+                         "no-slip walls / periodic z / EB cylinder at benchmark size")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: SIZE^3 per GPU; strong: SIZE^3 in total, cut into z-slabs")
     ap.add_argument("--ref-gpu-size", type=int, default=384, help="box of the reference-CUDA-build sample")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
@@ -231,12 +319,14 @@ def main():
             pass
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     n = args.size
-    deck = parse_deck(text=TG_DECK.format(nx=n, ny=n, nz=n * world, mgs=n))
+    deck_text, workload_desc = workload_deck(args, world)
+    deck = parse_deck(text=deck_text)
     comm = HaloComm(rank, world, True, dev) if world > 1 else None
     stream = torch.cuda.current_stream().cuda_stream
     lbm = LBM(deck, device=local, rank=rank, world=world, comm=comm, cuda_stream=stream, variant=args.variant)
     lbm.init_data()
     cells_total = lbm.ncells * world
+    cells_rank, lbm_shape, halo_lean = lbm.ncells, "x".join(str(v) for v in lbm.n_local), bool(getattr(lbm, "halo_lean", False))
 
     def barrier():
         torch.cuda.synchronize()
@@ -275,6 +365,10 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    if world > 1:
+        t = torch.tensor([float(lbm.ncells)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        cells_total = int(t.item())
     ms_per_step = ms / args.steps
     value = cells_total / (ms_per_step * 1e-3) / 1e6
 
@@ -299,11 +393,17 @@ def main():
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             tkey = {0: "k_collide_lean", 6: "k_collide_lean", 5: "k_collide_tile", 4: "k_collide_carry", 7: "k_collide_tile_pair", 8: "k_march"}.get(lbm.variant)
             traffic = json.load(fh).get("dram_bytes_per_launch_512", {}).get(tkey) if n == 512 else None
+            if args.workload != "tg" or world > 1 and args.scaling == "strong":
+                traffic = None
     except Exception:
         pass
     roofline = {
         "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic,
+        "traffic_source": ("ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 512^3, recorded in "
+                           "profiles/traffic.json from the capture under profiles/ (a run under ncu is never a bench "
+                           "value; regenerate when the kernel changes)") if traffic else None,
+        "peak_source": peak_src,
         "bytes_per_cell": BYTES_PER_CELL, "cells_per_launch": lbm.ncells,
         "kernel_ms": {"ghost_fill": kms[0] / max(nrec.value, 1), "qcorr": kms[1] / max(nrec.value, 1),
                       "collide": collide_ms},
@@ -313,7 +413,7 @@ def main():
 
     # ---- end to end through the host-buffer call -------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.workload == "tg" and args.scaling == "weak":
         from marbles_b200.lbm import _dptr
         from marbles_b200._lib import check
         # host FABs of f and g: 2 x 27 x 8 B per cell per rank, pinned.  Keep them within half of the free host
@@ -372,10 +472,11 @@ def main():
     # ---- CPU baseline: the unmodified reference on the host cores ---------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        r = reference_mlups(args.ref_size, args.ref_steps)
+        r = reference_mlups(args.cpu_size, args.cpu_steps)
         if r is not None:
             cpu = {"value": r[0], "unit": "MLUPS", "cores": r[2], "kind": "reference",
-                   "sample": f"TG deck {args.ref_size}^3, {args.ref_steps} steps, LBM::evolve() inclusive time, {r[3]}"}
+                   "sample": f"bounded sample: TG deck at {args.cpu_size}^3 cells, {args.cpu_steps} steps, "
+                             f"LBM::evolve() inclusive time, {r[3]} (the --impl reference arm runs the longer sample)"}
 
     # ---- the reference's own GPU path (unmodified sources, nvcc build of oracle/refbuild) on this GPU ------------
     ref_gpu = None
@@ -392,10 +493,10 @@ def main():
         line = {
             "metric": "MLUPS (D3Q27 f+g, fp64)", "value": value, "unit": "MLUPS", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"periodic Taylor-Green box {n}^3 per GPU, single level, D3Q27 f+g fp64 "
-                                   f"(BASELINE config 3; domain {n}x{n}x{n * world})",
-                       "decomposition": f"{world} z-slab(s)", "l2": "state (58 GB per GPU at 512^3) is far larger than L2",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_desc,
+                       "decomposition": f"{world} z-slab(s) of {lbm_shape}" + (", lean z-halo" if halo_lean else ""),
+                       "l2": f"state ({54 * 8 * cells_rank / 1e9:.1f} GB per GPU) is far larger than the 126 MB L2",
                        "variant": vname},
             "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "e2e": e2e,
             "gpu_launches": int(launches),

@@ -219,6 +219,10 @@ int mbl_step_local(mbl_ctx* ctx, int lev, double time, int want_macrodata);
  * (mbl_halo_doubles() doubles); unpack writes a neighbour's packed planes into
  * the ghost planes on that side.  Transport (NCCL over NVLink) is the caller's. */
 int64_t mbl_halo_doubles(mbl_ctx* ctx, int lev);
+/* lean halo: pack / unpack only the 27 of 54 plane-components per lattice a neighbour's pull can reach (the 18 with
+ * e_z towards it or 0 of the adjacent plane, the 9 with e_z towards it of the second plane): half the bytes.  Only
+ * for levels without bounce-back or boundary ghost values next to the slab cut (all-fluid, all-periodic). */
+int mbl_set_halo_lean(mbl_ctx* ctx, int on);
 int mbl_halo_pack(mbl_ctx* ctx, int lev, int side, double* device_buf);
 int mbl_halo_unpack(mbl_ctx* ctx, int lev, int side, const double* device_buf);
 

@@ -78,6 +78,7 @@ SYMBOLS = {
     "mbl_step": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_int]),
     "mbl_step_local": (C.c_int, [_P, C.c_int, C.c_double, C.c_int]),
     "mbl_halo_doubles": (C.c_int64, [_P, C.c_int]),
+    "mbl_set_halo_lean": (C.c_int, [_P, C.c_int]),
     "mbl_halo_pack": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "mbl_halo_unpack": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "mbl_step_split": (C.c_int, [_P, C.c_int, C.c_int]),

@@ -815,7 +815,7 @@ int mbl_halo_pack_next(mbl_ctx* ctx, int lev, int side, double* buf)
     if (check_level(ctx, lev)) return 1;
     Level& lv = ctx->lev[lev];
     CU(cudaSetDevice(ctx->device));
-    ctx->launches += launch_halo_pack(lv.L, lv.p.f[1 - lv.cur], lv.p.g[1 - lv.cur], side, buf, ctx->stream);
+    ctx->launches += launch_halo_pack(lv.L, lv.p.f[1 - lv.cur], lv.p.g[1 - lv.cur], side, buf, ctx->stream, ctx->halo_lean);
     CU(cudaGetLastError());
     return 0;
 }
@@ -825,7 +825,7 @@ int mbl_halo_unpack_next(mbl_ctx* ctx, int lev, int side, const double* buf)
     if (check_level(ctx, lev)) return 1;
     Level& lv = ctx->lev[lev];
     CU(cudaSetDevice(ctx->device));
-    ctx->launches += launch_halo_unpack(lv.L, lv.p.f[1 - lv.cur], lv.p.g[1 - lv.cur], side, buf, ctx->stream);
+    ctx->launches += launch_halo_unpack(lv.L, lv.p.f[1 - lv.cur], lv.p.g[1 - lv.cur], side, buf, ctx->stream, ctx->halo_lean);
     CU(cudaGetLastError());
     return 0;
 }
@@ -833,7 +833,14 @@ int mbl_halo_unpack_next(mbl_ctx* ctx, int lev, int side, const double* buf)
 int64_t mbl_halo_doubles(mbl_ctx* ctx, int lev)
 {
     if (check_level(ctx, lev)) return -1;
-    return 2LL * NQ * GZ * ctx->lev[lev].L.sz;
+    return (ctx->halo_lean ? 1LL : (long long)GZ) * 2LL * NQ * ctx->lev[lev].L.sz;
+}
+
+int mbl_set_halo_lean(mbl_ctx* ctx, int on)
+{
+    if (!ctx) return fail("null context");
+    ctx->halo_lean = on != 0;
+    return 0;
 }
 
 int mbl_halo_pack(mbl_ctx* ctx, int lev, int side, double* buf)
@@ -841,7 +848,7 @@ int mbl_halo_pack(mbl_ctx* ctx, int lev, int side, double* buf)
     if (check_level(ctx, lev)) return 1;
     Level& lv = ctx->lev[lev];
     CU(cudaSetDevice(ctx->device));
-    ctx->launches += launch_halo_pack(lv.L, curf(lv), curg(lv), side, buf, ctx->stream);
+    ctx->launches += launch_halo_pack(lv.L, curf(lv), curg(lv), side, buf, ctx->stream, ctx->halo_lean);
     CU(cudaGetLastError());
     return 0;
 }
@@ -851,7 +858,7 @@ int mbl_halo_unpack(mbl_ctx* ctx, int lev, int side, const double* buf)
     if (check_level(ctx, lev)) return 1;
     Level& lv = ctx->lev[lev];
     CU(cudaSetDevice(ctx->device));
-    ctx->launches += launch_halo_unpack(lv.L, curf(lv), curg(lv), side, buf, ctx->stream);
+    ctx->launches += launch_halo_unpack(lv.L, curf(lv), curg(lv), side, buf, ctx->stream, ctx->halo_lean);
     CU(cudaGetLastError());
     return 0;
 }

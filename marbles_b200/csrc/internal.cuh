@@ -104,6 +104,7 @@ struct mbl_ctx {
     cudaStream_t s_capture = nullptr;               // CUDA graph capture of step pairs
     int host_chunk = 16;  // planes per upload chunk (MBL_HOST_CHUNK; negative: no pipelining)
     bool use_graphs = true;  // MBL_GRAPH=0 disables
+    bool halo_lean = false;  // mbl_set_halo_lean: ghost planes carry only the populations a pull can reach
     bool timing = false;
     std::vector<cudaEvent_t> events;  // 4 per timed record: before ghost fill, q-corr, collide, after
     int timed_steps = 0;              // steps covered by the records (a split step makes two records)

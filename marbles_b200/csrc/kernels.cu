@@ -1678,22 +1678,68 @@ int launch_eb_forces(const Layout& L, const double* f, const uint8_t* flag, doub
     return 1;
 }
 
-int launch_halo_pack(const Layout& L, const double* f, const double* g, int side, double* buf, cudaStream_t st)
+// Lean z-halo: only the populations a neighbour's pull can reach.  Towards the neighbour on `side` (e_z = -1 for the
+// low side, +1 for the high side) the plane next to it sends the 18 populations with e_z in {towards, 0} (the pull of
+// its first owned plane and the q-correction of its first ghost plane), the second plane the 9 with e_z = towards
+// (q-correction of the first ghost plane): 27 instead of 54 plane-components per lattice.  Valid where no bounce-back
+// and no boundary ghost value can ask for the others (all-fluid, all-periodic levels); the caller decides.
+struct LeanList {
+    signed char q[NQ];      // component
+    signed char plane[NQ];  // 0: the plane next to the neighbour, 1: the second plane
+};
+static LeanList make_lean_list(int side)
 {
+    const int towards = side == 0 ? -1 : 1;
+    LeanList t;
+    int n = 0;
+    for (int q = 0; q < NQ; ++q)
+        if (ez(q) == towards || ez(q) == 0) t.q[n] = (signed char)q, t.plane[n++] = 0;
+    for (int q = 0; q < NQ; ++q)
+        if (ez(q) == towards) t.q[n] = (signed char)q, t.plane[n++] = 1;
+    return t;
+}
+__global__ void k_halo_copy_lean(double* __restrict__ f, double* __restrict__ g, double* __restrict__ buf, Layout L, int k_near,
+                                 int k_step, LeanList T, int to_buf)
+{
+    const long long total = 2LL * NQ * L.sz;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        const long long w = t % L.sz;
+        const int item = (int)((t / L.sz) % NQ);
+        const int lat = (int)(t / (L.sz * NQ));
+        const int k = k_near + k_step * T.plane[item];
+        double* p = (lat ? g : f) + (long long)T.q[item] * L.sq + (long long)(k + GZ) * L.sz + w;
+        if (to_buf)
+            buf[t] = *p;
+        else
+            *p = buf[t];
+    }
+}
+
+int launch_halo_pack(const Layout& L, const double* f, const double* g, int side, double* buf, cudaStream_t st, bool lean)
+{
+    if (lean) {
+        // side 0: my planes 0 (near the lower neighbour), 1; side 1: my planes nz-1, nz-2
+        k_halo_copy_lean<<<148 * 4, 256, 0, st>>>(const_cast<double*>(f), const_cast<double*>(g), buf, L,
+                                                  side == 0 ? 0 : L.nz - 1, side == 0 ? 1 : -1, make_lean_list(side), 1);
+        return 1;
+    }
     const int k0 = side == 0 ? 0 : L.nz - GZ;
     k_halo_copy<<<148 * 4, 256, 0, st>>>(const_cast<double*>(f), const_cast<double*>(g), buf, L, k0, 1);
     return 1;
 }
-int launch_halo_unpack(const Layout& L, double* f, double* g, int side, const double* buf, cudaStream_t st)
+int launch_halo_unpack(const Layout& L, double* f, double* g, int side, const double* buf, cudaStream_t st, bool lean)
 {
+    if (lean) {
+        // my low ghost planes -1 (near), -2 hold what the lower neighbour packed for ITS high side, and vice versa
+        k_halo_copy_lean<<<148 * 4, 256, 0, st>>>(f, g, const_cast<double*>(buf), L, side == 0 ? -1 : L.nz,
+                                                  side == 0 ? -1 : 1, make_lean_list(1 - side), 0);
+        return 1;
+    }
     const int k0 = side == 0 ? -GZ : L.nz;
     k_halo_copy<<<148 * 4, 256, 0, st>>>(f, g, const_cast<double*>(buf), L, k0, 0);
     return 1;
 }
-
-#ifdef MBL_EXPERIMENTS
-// negative-result kernels (variants 1-4), kept out of the shipped library: DESIGN.md section 3
-#include "experiments/experiments.cuh"
-#endif
 
 }  // namespace mbl

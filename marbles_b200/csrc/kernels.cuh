@@ -152,7 +152,10 @@ int launch_fused_plain(const Layout& L, const Phys& P, int band_rows, int lag_pe
                        const double* fin, const double* gin, double* fout, double* gout, const uint32_t* nbr,
                        const uint8_t* flag, double* qc, double* macro, int* counters, cudaStream_t st);
 
-int launch_halo_pack(const Layout& L, const double* f, const double* g, int side, double* buf, cudaStream_t st);
-int launch_halo_unpack(const Layout& L, double* f, double* g, int side, const double* buf, cudaStream_t st);
+// lean: only the 27 (of 54) plane-components per lattice a neighbour's pull can reach (kernels.cu: LeanList)
+int launch_halo_pack(const Layout& L, const double* f, const double* g, int side, double* buf, cudaStream_t st,
+                     bool lean = false);
+int launch_halo_unpack(const Layout& L, double* f, double* g, int side, const double* buf, cudaStream_t st,
+                       bool lean = false);
 
 }  // namespace mbl

@@ -132,6 +132,11 @@ class LBM:
         self._is_fluid = None
         self._halo = None
         self.set_is_fluid(is_fluid)
+        # lean z-halo (half the bytes per exchange): legal where no bounce-back and no boundary ghost value sits next
+        # to a slab cut -- all-periodic decks without solid cells
+        self.halo_lean = (world > 1 and all(self.inp.periodic) and int(self._is_fluid.min()) == 1
+                          and os.environ.get("MBL_HALO_LEAN", "1") != "0")
+        check(self.lib.mbl_set_halo_lean(self.ctx, int(self.halo_lean)))
 
     # ------------------------------------------------------------------ setup
     def close(self):

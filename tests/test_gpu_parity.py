@@ -557,3 +557,41 @@ def test_full_size_values_tiled_tg_vs_oracle(oracle_mod, n, variant):
     print(f"tiled TG {n}^3: worst {worst:.2e} of scale over {t ** 3} tiles")
     assert worst <= 1e-12 * nsteps, worst
     lbm.close()
+
+
+@pytest.mark.parametrize("variant", [0, 5], ids=["twopass", "tile"])
+def test_lean_halo_is_bit_identical(variant):
+    """the lean z-halo (27 of 54 plane-components per lattice: what a neighbour's pull can reach) against the full one
+    on an all-periodic all-fluid box cut into three slabs: plain and overlapped slab steps, same bits"""
+    import os
+    import torch
+    from marbles_b200.inputs import parse_deck
+    from marbles_b200.lbm import LBM
+    from marbles_b200.parallel import LocalSlabs
+    _, deck_text, _ = load_golden("tg12")
+    deck = parse_deck(text=deck_text, overrides=["amr.n_cell = 12 12 27"])
+
+    def run(lean):
+        os.environ["MBL_HALO_LEAN"] = "1" if lean else "0"
+        try:
+            def make(rank, w):
+                s = LBM(deck, rank=rank, world=w, comm=None, variant=variant)
+                assert s.halo_lean == lean
+                s.init_data()
+                return s
+            slabs = LocalSlabs(make, 3, True, torch.device("cuda", 0))
+        finally:
+            os.environ.pop("MBL_HALO_LEAN", None)
+        n = int(slabs.slabs[0].lib.mbl_halo_doubles(slabs.slabs[0].ctx, 0))
+        slabs.step(3)
+        slabs.step_overlapped(3)
+        slabs.step(1, want_macrodata=True)
+        out = [slabs.gather(lambda s: s.get_f()), slabs.gather(lambda s: s.get_g()), slabs.gather(lambda s: s.get_macrodata())]
+        slabs.close()
+        return n, out
+
+    n_full, full = run(False)
+    n_lean, lean = run(True)
+    assert 2 * n_lean == n_full
+    for a, b in zip(full, lean):
+        assert np.array_equal(a, b)
