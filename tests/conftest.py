@@ -8,7 +8,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["tg12", "sod48", "chcyl", "thermal", "pressure", "slip", "shear"]
+GOLDEN_CASES = ["tg12", "sod48", "chcyl", "thermal", "pressure", "slip", "shear", "slipyz", "touch"]
 
 
 AMR_GOLDEN_CASES = ["amr2_tg", "amr2_chcyl", "amr3_chcyl", "amr2_sod"]
@@ -39,3 +39,20 @@ def load_amr_golden(name):
     boxes = [[(list(map(int, b[0])), list(map(int, b[1]))) for b in z[f"boxes_l{l}"]] for l in range(nlev)]
     is_fluid = [z[f"is_fluid_l{l}"].astype(np.int32) for l in range(nlev)]
     return z, str(z["deck"]), [int(s) for s in z["steps"]], boxes, is_fluid
+
+
+def golden_is_fluid(name):
+    """is_fluid (component 0) for a single-level golden case: the reference's valid-cell field, except where the body
+    crosses a domain face (`touch`): there the 3 ghost layers carry the geometry evaluated beyond the domain, which a
+    plotfile does not hold -- taken from the analytic body of the deck (checked against the valid cells)."""
+    import numpy as np
+    z, deck_text, _ = load_golden(name)
+    fl = z["is_fluid"].astype(np.int32)
+    if name != "touch":
+        return fl
+    from marbles_b200.geometry import is_fluid_from_deck
+    from marbles_b200.inputs import lbm_inputs, parse_deck
+    inp = lbm_inputs(parse_deck(text=deck_text))
+    grown = is_fluid_from_deck(inp.deck, inp.n_cell, inp.prob_lo, inp.dx, ng=3)
+    assert np.array_equal(grown[3:-3, 3:-3, 3:-3], fl)
+    return grown

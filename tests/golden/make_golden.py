@@ -196,6 +196,49 @@ ic_viscosity_test.initial_temperature = 0.03333
 lbm.initial_temperature = 0.03333
 eb2.geom_type = "all_regular"
 """, [0, 1, 12]),
+    # slip walls with y and z normals (codes 7 and 8, BC.H:119, 138), constant-velocity inlet, outflow, EB sphere
+    "slipyz": ("""
+max_step = 6
+geometry.prob_lo = 0.0 0.0 0.0
+geometry.prob_hi = 20.0 10.0 8.0
+geometry.is_periodic = 0 0 0
+amr.n_cell = 20 10 8
+lbm.bc_lo = 2 7 8
+lbm.bc_hi = 5 7 8
+lbm.nu = 0.02
+lbm.velocity_bc_type = "constant"
+velocity_bc_constant.dir = 0
+velocity_bc_constant.Mach_ref = 0.02
+lbm.ic_type = "constant"
+ic_constant.density = 1.0
+ic_constant.mach_components = 0.005 0.0 0.0
+eb2.geom_type = "sphere"
+eb2.sphere_radius = 1.9
+eb2.sphere_center = 7.0 5.0 4.0
+eb2.sphere_has_fluid_inside = 0
+""", [0, 1, 6]),
+    # a body that crosses the pressure outlet and a no-slip wall: is_fluid of the out-of-domain ghost cells comes
+    # from the geometry evaluated beyond the domain (SURVEY A.4 last paragraph, the pine_box situation)
+    "touch": ("""
+max_step = 6
+geometry.prob_lo = 0.0 0.0 0.0
+geometry.prob_hi = 10.0 10.0 14.0
+geometry.is_periodic = 0 0 0
+amr.n_cell = 10 10 14
+lbm.bc_lo = 1 1 2
+lbm.bc_hi = 1 1 3
+lbm.nu = 0.01733333333333333
+lbm.velocity_bc_type = "constant"
+velocity_bc_constant.dir = 2
+velocity_bc_constant.Mach_ref = 0.01
+lbm.ic_type = "constant"
+ic_constant.density = 1.0
+ic_constant.mach_components = 0.0 0.0 0.002
+eb2.geom_type = "box"
+eb2.box_lo = 5.5 3.5 10.5
+eb2.box_hi = 12.5 6.5 17.5
+eb2.box_has_fluid_inside = 0
+""", [0, 1, 6]),
 }
 
 KEEP_STEP0 = ([f"f_{q:02d}" for q in range(27)] + [f"g_{q:02d}" for q in range(27)] + O.MACRO_NAMES)

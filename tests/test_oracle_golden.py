@@ -4,7 +4,7 @@ so the comparison is BIT-EXACT on every plotted field of every stored step."""
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, load_golden
+from conftest import GOLDEN_CASES, golden_is_fluid, load_golden
 
 
 def make_oracle(O, deck_text, is_fluid=None):
@@ -18,7 +18,7 @@ def make_oracle(O, deck_text, is_fluid=None):
 def test_oracle_bit_exact_vs_reference_golden(oracle_mod, case):
     O = oracle_mod
     z, deck_text, steps = load_golden(case)
-    o = make_oracle(O, deck_text, z["is_fluid"].astype(np.int32))
+    o = make_oracle(O, deck_text, golden_is_fluid(case))
     done = 0
     for s in steps:
         o.step(s - done)
