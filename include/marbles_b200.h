@@ -226,10 +226,11 @@ int mbl_set_halo_lean(mbl_ctx* ctx, int on);
 int mbl_halo_pack(mbl_ctx* ctx, int lev, int side, double* device_buf);
 int mbl_halo_unpack(mbl_ctx* ctx, int lev, int side, const double* device_buf);
 
-/* The slab step with the halo exchange overlapped with the interior planes (all-periodic levels: the
- * cross-rank part of FillBoundary, AMReX_FabArrayCommI.H:8-253, hidden behind the kernels).  Output plane k
+/* The slab step with the halo exchange overlapped with the interior planes (the cross-rank part of
+ * FillBoundary, AMReX_FabArrayCommI.H:8-253, hidden behind the kernels; any boundary conditions).  Output plane k
  * depends on input planes k-2..k+2, so:
- *   mbl_step_split(part 0): the 2 outermost planes at each z-end (needs the current ghost planes)
+ *   mbl_step_split(part 0): ghost fill of the current buffers (levels with non-periodic faces), then the 2 outermost
+ *     planes at each z-end (needs the current z ghost planes)
  *   mbl_halo_pack_next / exchange / mbl_halo_unpack_next on ANOTHER stream (mbl_set_stream): the boundary
  *     planes just written travel to the neighbours' ghost planes of the buffers being written
  *   mbl_step_split(part 1): the interior planes; the written buffers become current.

@@ -731,7 +731,6 @@ int mbl_step_split(mbl_ctx* ctx, int lev, int part)
     if (check_level(ctx, lev)) return 1;
     Level& lv = ctx->lev[lev];
     const Layout& L = lv.L;
-    if (!(L.wrap[0] && L.wrap[1])) return fail("mbl_step_split: only for all-periodic levels (no ghost fill between the parts)");
     if (L.nz < 8) return fail("mbl_step_split: a slab needs at least 8 planes");
     if (part != 0 && part != 1) return fail("mbl_step_split: part must be 0 or 1");
     CU(cudaSetDevice(ctx->device));
@@ -787,7 +786,13 @@ int mbl_step_split(mbl_ctx* ctx, int lev, int part)
         // a z-end that is a periodic image of the box itself (single rank in z) has no ghost planes to wait for,
         // but the split is still valid: the kernels wrap
         const int klo = L.wrap[2] ? 0 : -1, khi = L.wrap[2] ? nz : nz + 1;
-        mark(), mark();
+        mark();
+        // levels with walls / inlets / outlets: the ghost cells of the CURRENT buffers (whose z ghost planes the
+        // previous exchange delivered) are filled once, before either part reads them -- K6, periodic images in x, y,
+        // BCFill regions, exactly as mbl_step_local does
+        if (!(L.wrap[0] && L.wrap[1]))
+            ctx->launches += launch_ghost_fill(L, lv.B, lv.p.f[a], lv.p.g[a], lv.local_z, true, true, st);
+        mark();
         q(klo, 3);
         q(nz - 3, khi);
         mark();

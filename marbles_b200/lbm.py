@@ -254,9 +254,10 @@ class LBM:
         return f
 
     def can_overlap(self) -> bool:
-        """The overlapped slab step (mbl_step_split) applies to all-periodic decks (no ghost fill between its
-        parts), the two-kernel and the tile-carry variants and slabs of at least 8 planes."""
-        return (self.world > 1 and all(self.inp.periodic) and self.variant in (0, 5, 7, 8) and self.n_local[2] >= 8
+        """The overlapped slab step (mbl_step_split: boundary planes first, their exchange behind the interior planes)
+        applies to the two-kernel and the tile-carry variants and to slabs of at least 8 planes; levels with walls,
+        inlets or outlets fill their ghost cells at the start of part 0."""
+        return (self.world > 1 and self.variant in (0, 5, 7, 8) and self.n_local[2] >= 8
                 and self.comm is not None and hasattr(self.comm, "exchange_next") and self.overlap)
 
     def step(self, nsteps: int = 1, want_macrodata: bool = False):

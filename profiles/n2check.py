@@ -1,4 +1,6 @@
-"""2-rank check of the overlapped slab step against the plain slab step (run under torchrun)"""
+"""2-rank check (run under torchrun) of the overlapped slab step against the plain (blocking) slab step, and of the
+lean z-halo against the full one, on real NCCL transport: periodic Taylor-Green box and the channel + cylinder deck
+(inlet / outflow / no-slip walls / periodic z: ghost fill inside the split step).  Two-kernel step: bit-identical."""
 import os, sys, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.getcwd())
 from marbles_b200.inputs import parse_deck
@@ -9,20 +11,26 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 n = 64
-deck = parse_deck(text=bench.TG_DECK.format(nx=n, ny=n, nz=n * world, mgs=n))
-res = []
-for ov in ("1", "0"):
-    os.environ["MBL_OVERLAP"] = ov
-    comm = HaloComm(rank, world, True, dev)
-    lbm = LBM(deck, device=local, rank=rank, world=world, comm=comm, variant=0)
-    lbm.init_data()
-    lbm.step(7)
-    lbm.step(1)
-    lbm.step(3, want_macrodata=True)
-    torch.cuda.synchronize()
-    res.append((lbm.get_f(), lbm.get_g(), lbm.can_overlap()))
-    lbm.close()
-same = np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
-print(f"rank {rank}: overlap used {res[0][2]}/{res[1][2]}, overlapped == plain: {same}, sum f {res[0][0].sum():.12e}", flush=True)
+decks = {"tg": bench.TG_DECK.format(nx=n, ny=n, nz=n * world, mgs=n),
+         "channel": bench.CHANNEL_DECK.format(nx=2 * n, ny=n // 2, nz=(n // 2) * world, mgs=2 * n, rad=4, cx=n // 2, cy=n // 4)}
+ok = True
+for name, text in decks.items():
+    deck = parse_deck(text=text)
+    res = []
+    for ov, lean in (("1", "1"), ("0", "0")):
+        os.environ["MBL_OVERLAP"], os.environ["MBL_HALO_LEAN"] = ov, lean
+        comm = HaloComm(rank, world, True, dev)
+        lbm = LBM(deck, device=local, rank=rank, world=world, comm=comm, variant=0)
+        lbm.init_data()
+        lbm.step(7)
+        lbm.step(1)
+        lbm.step(3, want_macrodata=True)
+        torch.cuda.synchronize()
+        res.append((lbm.get_f(), lbm.get_g(), lbm.can_overlap(), lbm.halo_lean))
+        lbm.close()
+    same = np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    ok = ok and same
+    print(f"rank {rank} {name}: overlap {res[0][2]}/{res[1][2]} with MBL_OVERLAP 1/0, lean halo {res[0][3]}/{res[1][3]}, "
+          f"overlapped+lean == blocking+full: {same}, sum f {res[0][0].sum():.12e}", flush=True)
 dist.barrier(); dist.destroy_process_group()
-sys.exit(0 if same else 1)
+sys.exit(0 if ok else 1)

@@ -315,16 +315,24 @@ def test_step_host_matches_device_step(case, ov, chunk, ng):
 
 
 @pytest.mark.parametrize("variant", with_experiments([0, 5], [8]), ids=lambda v: {0: "twopass", 5: "tile", 8: "march"}[v])
-@pytest.mark.parametrize("nz,world", [(16, 2), (27, 3)])
-def test_overlapped_slab_step_matches_single_box(nz, world, variant):
-    """mbl_step_split (boundary planes first, exchange of the written buffers' boundary planes, interior planes)
-    in the order LBM._step_overlapped issues it, on one device: bit-identical to the single box"""
+@pytest.mark.parametrize("case,nxy,nz,world", [("tg12", "12 12", 16, 2), ("tg12", "12 12", 27, 3), ("chcyl", "32 12", 16, 2),
+                                               ("pressure", "10 10", 17, 2)])
+def test_overlapped_slab_step_matches_single_box(case, nxy, nz, world, variant):
+    """mbl_step_split (ghost fill where the level has walls, boundary planes first, exchange of the written buffers'
+    boundary planes, interior planes) in the order LBM._step_overlapped issues it, on one device: bit-identical to the
+    single box.  tg12: all periodic (lean halo); chcyl: inlet / outflow / no-slip / periodic z with a cylinder
+    through every slab cut; pressure: non-periodic z as well (slabs end at an inlet and a pressure outlet)"""
     import torch
     from marbles_b200.inputs import parse_deck
     from marbles_b200.lbm import LBM, slab_bounds
     from marbles_b200.parallel import LocalSlabs
-    z, deck_text, _ = load_golden("tg12")
-    deck = parse_deck(text=deck_text, overrides=[f"amr.n_cell = 12 12 {nz}"])
+    z, deck_text, _ = load_golden(case)
+    ov = [f"amr.n_cell = {nxy} {nz}"]
+    if case == "pressure":
+        ov.append(f"geometry.prob_hi = 10.0 10.0 {nz}.0")
+    elif case == "chcyl":
+        ov.append(f"geometry.prob_hi = 32.0 12.0 {nz}.0")
+    deck = parse_deck(text=deck_text, overrides=ov)
     single = LBM(deck, variant=0)
     single.init_data()
 
@@ -333,7 +341,7 @@ def test_overlapped_slab_step_matches_single_box(nz, world, variant):
         s.init_data()
         return s
 
-    slabs = LocalSlabs(make, world, True, torch.device("cuda", 0))
+    slabs = LocalSlabs(make, world, bool(single.inp.periodic[2]), torch.device("cuda", 0))
     single.step(7)
     slabs.step_overlapped(3)
     slabs.step(2)  # and back to the plain slab step
