@@ -121,6 +121,13 @@ int mbl_level_lattice_ptr(mbl_ctx* ctx, int lev, int which, void** out);
  * 27-bit pull mask on the device. */
 int mbl_set_is_fluid(mbl_ctx* ctx, int lev, const int32_t* is_fluid, int ng);
 int mbl_set_all_fluid(mbl_ctx* ctx, int lev);
+/* the same flag field for the analytic bodies of the shipped decks (eb2.geom_type, Source/EB.cpp:5-38), evaluated on
+ * the device with EB2's covered-cell rule (all 8 corners inside the body), ghost layers included (periodic images in
+ * periodic directions, the geometry beyond the domain elsewhere): no host field, no upload.
+ * kind 0 all_regular; 1 sphere {cx, cy, cz, r, fluid_inside}; 2 cylinder {cx, cy, cz, r, height (<= 0: unbounded),
+ * direction, fluid_inside}; 3 box {lox, loy, loz, hix, hiy, hiz, fluid_inside}.  STL / general EB2 bodies: pass
+ * m_is_fluid through mbl_set_is_fluid. */
+int mbl_set_body(mbl_ctx* ctx, int lev, int kind, const double* params, int nparams);
 
 /* state transfer between a FAB (27 comps, ghost width ng, x fastest, component slowest:
  * AMReX_Array4.H:60-94) and the library's padded SoA buffers: one pitched DMA per component.
@@ -203,6 +210,13 @@ int mbl_box_download(mbl_ctx* ctx, int lev, int ibox, int which, double* fab, in
 /* derived = 0: the 19 macrodata comps, 1: the 7 derived comps */
 int mbl_box_download_macrodata(mbl_ctx* ctx, int lev, int ibox, double* fab, int ng, int derived);
 int mbl_average_down(mbl_ctx* ctx, int crse_lev, int ng);
+/* LBM::RemakeLevel (Source/LBM.cpp:1302-1364) after AmrCore::regrid changed the box list of level lev >= 1: the new
+ * boxes take the old level's f, g where it covers them (periodic images included) and CellConservativeLinear values
+ * from level lev-1 elsewhere, then BCFill -- FillPatchOps::fillpatch into new MultiFabs.  The caller then passes the
+ * new is_fluid (mbl_box_set_is_fluid) and calls mbl_fill_f_inside_eb (zero in solid cells + FillBoundary,
+ * Source/LBM.cpp:1278-1298, 1347-1348). */
+int mbl_level_regrid(mbl_ctx* ctx, int lev, int nboxes, const int* lo, const int* hi);
+int mbl_fill_f_inside_eb(mbl_ctx* ctx, int lev);
 
 /* fused fast path: one coarse step of a single-level run =
  * fillpatch(f), fillpatch(g), stream(f), stream(g), collide

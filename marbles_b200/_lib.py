@@ -60,6 +60,7 @@ SYMBOLS = {
     "mbl_level_lattice_ptr": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     "mbl_set_is_fluid": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int32), C.c_int]),
     "mbl_set_all_fluid": (C.c_int, [_P, C.c_int]),
+    "mbl_set_body": (C.c_int, [_P, C.c_int, C.c_int, _D, C.c_int]),
     "mbl_upload": (C.c_int, [_P, C.c_int, C.c_int, _D, C.c_int]),
     "mbl_download": (C.c_int, [_P, C.c_int, C.c_int, _D, C.c_int]),
     "mbl_download_macrodata": (C.c_int, [_P, C.c_int, _D, C.c_int]),
@@ -95,6 +96,8 @@ SYMBOLS = {
     "mbl_box_download": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _D, C.c_int]),
     "mbl_box_download_macrodata": (C.c_int, [_P, C.c_int, C.c_int, _D, C.c_int, C.c_int]),
     "mbl_average_down": (C.c_int, [_P, C.c_int, C.c_int]),
+    "mbl_level_regrid": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mbl_fill_f_inside_eb": (C.c_int, [_P, C.c_int]),
     "mbl_launch_count": (C.c_int64, [_P]),
     "mbl_set_variant": (C.c_int, [_P, C.c_int]),
     "mbl_get_variant": (C.c_int, [_P]),

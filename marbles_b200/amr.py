@@ -10,8 +10,9 @@ reference-granular entry points in the reference's order:
     LBM::evolve (one step)    Source/LBM.cpp:416-422   -> fillpatch(0); time_step(0); post_time_step
     LBM::time_step            Source/LBM.cpp:452-521   -> fillpatch(lev+1); 2 x (physbc(lev+1); time_step(lev+1)); advance
     LBM::advance              Source/LBM.cpp:523-544   -> stream; average_down_to(lev, 1 ghost ring); collide
-    LBM::regrid callbacks     Source/LBM.cpp:1302-1379 -> `redefine_level` (re-define with a new box list, state
-                                                          carried over where the old and the new boxes overlap)
+    LBM::RemakeLevel          Source/LBM.cpp:1302-1364 -> `regrid_level`: mbl_level_regrid with the box list AmrCore::regrid
+                                                          produced (old level + coarse interpolation into new FABs),
+                                                          new is_fluid, mbl_fill_f_inside_eb
 
 No CPU fallback: every operator is a kernel of marbles_b200/csrc/patch.cu.
 """
@@ -111,6 +112,11 @@ class AmrLBM:
             self.boxes.append(boxes)
             self.n.append(n)
             self.dt.append(g.dt)
+        self._set_level_is_fluid(lev, is_fluid_dense)
+
+    def _set_level_is_fluid(self, lev: int, is_fluid_dense=None):
+        """initialize_is_fluid (Source/LBM.cpp:1213-1262) for every box of a level"""
+        boxes, n = self.boxes[lev], self.n[lev]
         ng = F_NGHOST
         dx = [self.inp.dx[d] / REF_RATIO ** lev for d in range(3)]
         for ib, (blo, bhi) in enumerate(boxes):
@@ -198,28 +204,18 @@ class AmrLBM:
     def sync(self):
         check(self.lib.mbl_sync(self.ctx))
 
-    def redefine_level(self, lev: int, boxes, is_fluid_dense=None):
-        """RemakeLevel (Source/LBM.cpp:1302-1364) for a level whose box list changed in a regrid: the new boxes take
-        the old level's data where they overlap it; the caller then calls fillpatch(lev) for the rest of the ghost
-        cells.  (New valid cells that no old box covers would be interpolated from the coarse level by the
-        reference; that case raises.)"""
-        old_boxes = self.boxes[lev]
-        old = [(self.get_box(lev, ib, 0, 0), self.get_box(lev, ib, 1, 0)) for ib in range(len(old_boxes))]
-        self.define_level(lev, boxes, is_fluid_dense)
-        n = self.n[lev]
-        dense_f = np.full((NQ, n[2], n[1], n[0]), np.nan)
-        dense_g = np.full((NQ, n[2], n[1], n[0]), np.nan)
-        for (lo, hi), (f, g) in zip(old_boxes, old):
-            s = (slice(None), slice(lo[2], hi[2] + 1), slice(lo[1], hi[1] + 1), slice(lo[0], hi[0] + 1))
-            dense_f[s], dense_g[s] = f, g
-        for ib, (lo, hi) in enumerate(self.boxes[lev]):
-            s = (slice(None), slice(lo[2], hi[2] + 1), slice(lo[1], hi[1] + 1), slice(lo[0], hi[0] + 1))
-            f, g = np.ascontiguousarray(dense_f[s]), np.ascontiguousarray(dense_g[s])
-            if np.isnan(f).any():
-                raise MarblesError("redefine_level: a new box has cells no old box covers (coarse interpolation of "
-                                   "new valid cells is not implemented)")
-            check(self.lib.mbl_box_upload(self.ctx, lev, ib, 0, _dptr(f), 0))
-            check(self.lib.mbl_box_upload(self.ctx, lev, ib, 1, _dptr(g), 0))
+    def regrid_level(self, lev: int, boxes, is_fluid_dense=None):
+        """LBM::RemakeLevel (Source/LBM.cpp:1302-1364) with the box list AmrCore::regrid produced for level lev >= 1:
+        mbl_level_regrid fills the new boxes from the old level and, where that does not cover them, from level lev-1
+        (FillPatchOps::fillpatch into new MultiFabs); then the new is_fluid and fill_f_inside_eb + FillBoundary."""
+        boxes = [(tuple(int(v) for v in lo), tuple(int(v) for v in hi)) for lo, hi in boxes]
+        nb = len(boxes)
+        lo = (C.c_int * (3 * nb))(*[v for b in boxes for v in b[0]])
+        hi = (C.c_int * (3 * nb))(*[v for b in boxes for v in b[1]])
+        check(self.lib.mbl_level_regrid(self.ctx, lev, nb, lo, hi))
+        self.boxes[lev] = boxes
+        self._set_level_is_fluid(lev, is_fluid_dense)
+        check(self.lib.mbl_fill_f_inside_eb(self.ctx, lev))
 
     # ------------------------------------------------------------------ access
     def box_shape(self, lev: int, ib: int, ncomp: int, ng: int):

@@ -279,6 +279,70 @@ int alloc_aux(BoxSet& S, const std::vector<HBox>& valid, int ng)
     return 0;
 }
 
+// coarse patches + fine regions of the coarse-fine interpolation into the boxes `fine` (grown by the ghost width):
+// every cell inside dstdomain that no box of `cover` contains.  cover = the level's own valid boxes for a ghost fill
+// (FillPatchTwoLevels, mf == fine level), the OLD level's boxes when a re-made level is filled (RemakeLevel).
+int build_interp(Inter& I, const std::vector<HBox>& fine, const PGeom& FG, int fine_lev, const PatchLevel& Cl,
+                 const std::vector<HBox>& cover)
+{
+    const int nf = (int)fine.size(), nc = (int)Cl.boxes.size();
+    // coarse patches for the interpolation: coarsen(grown fine box) grown by 1 (CellConservativeLinear::CoarseBox)
+    std::vector<HBox> cp(nf);
+    for (int n = 0; n < nf; ++n) cp[n] = grow(coarsen2(grow(fine[n], PNG)), 1);
+    if (alloc_aux(I.cpatch, cp, 0)) return 1;
+    std::vector<CopyTag> c2p;
+    const auto shifts_p = periodic_shifts(Cl.G, PNG + 2);
+    for (int n = 0; n < nf; ++n)
+        for (const auto& s : shifts_p) {
+            const int sh[3] = {s[0], s[1], s[2]};
+            for (int j = 0; j < nc; ++j) {
+                const HBox r = isect(cp[n], shifted(Cl.boxes[j], sh));
+                if (r.ok()) c2p.push_back(make_tag(n, j, r, sh));
+            }
+        }
+    if (upload_tags(c2p, I.c2p)) return 1;
+    // fine ghost regions the interpolation fills: grown box inside dstdomain (the domain grown by the ghost width in
+    // periodic directions) minus the fine level's valid boxes, NOT periodically shifted (FPinfo: complementIn)
+    std::vector<RegionTag> regs;
+    for (int n = 0; n < nf; ++n) {
+        HBox r0 = grow(fine[n], PNG);
+        for (int d = 0; d < 3; ++d)
+            if (!FG.periodic[d]) {
+                r0.lo[d] = std::max(r0.lo[d], FG.dlo[d]);
+                r0.hi[d] = std::min(r0.hi[d], FG.dhi[d]);
+            }
+        std::vector<HBox> list{r0};
+        for (const HBox& v : cover) {
+            std::vector<HBox> next;
+            for (const HBox& r : list) box_diff(r, v, next);
+            list.swap(next);
+        }
+        for (const HBox& r : list) {
+            for (int d = 0; d < 3; ++d) {
+                if (FG.periodic[d]) continue;
+                // slopes of coarse cells on a non-periodic domain face are one-sided and depend on the extents of
+                // AMReX's internal coarse patch (AMReX_MFInterp_C.H:15-33): not reproduced
+                if (floor_div2(r.lo[d]) <= Cl.G.dlo[d] || floor_div2(r.hi[d]) >= Cl.G.dhi[d])
+                    return fail("level %d: a fine box lies within one coarse cell of a non-periodic domain face; the "
+                                "coarse-fine interpolation there is not supported", fine_lev);
+            }
+            RegionTag t;
+            t.box = n;
+            for (int d = 0; d < 3; ++d) t.lo[d] = r.lo[d], t.n[d] = r.hi[d] - r.lo[d] + 1;
+            regs.push_back(t);
+            I.reg_max = std::max(I.reg_max, r.pts());
+        }
+    }
+    if (I.d_regs) cudaFree(I.d_regs);
+    I.d_regs = nullptr;
+    I.nregs = (int)regs.size();
+    if (I.nregs) {
+        CU(cudaMalloc(&I.d_regs, regs.size() * sizeof(RegionTag)));
+        CU(cudaMemcpy(I.d_regs, regs.data(), regs.size() * sizeof(RegionTag), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
 // everything between level F.lev - 1 (coarse) and F.lev (fine), ratio 2
 int build_inter(PatchLevel& F, const PatchLevel& Cl)
 {
@@ -338,58 +402,7 @@ int build_inter(PatchLevel& F, const PatchLevel& Cl)
         }
         if (upload_tags(a2c, I.a2c[ng])) return 1;
     }
-    // coarse patches for the interpolation: coarsen(grown fine box) grown by 1 (CellConservativeLinear::CoarseBox)
-    std::vector<HBox> cp(nf);
-    for (int n = 0; n < nf; ++n) cp[n] = grow(coarsen2(grow(F.boxes[n], PNG)), 1);
-    if (alloc_aux(I.cpatch, cp, 0)) return 1;
-    std::vector<CopyTag> c2p;
-    const auto shifts_p = periodic_shifts(Cl.G, PNG + 2);
-    for (int n = 0; n < nf; ++n)
-        for (const auto& s : shifts_p) {
-            const int sh[3] = {s[0], s[1], s[2]};
-            for (int j = 0; j < nc; ++j) {
-                const HBox r = isect(cp[n], shifted(Cl.boxes[j], sh));
-                if (r.ok()) c2p.push_back(make_tag(n, j, r, sh));
-            }
-        }
-    if (upload_tags(c2p, I.c2p)) return 1;
-    // fine ghost regions the interpolation fills: grown box inside dstdomain (the domain grown by the ghost width in
-    // periodic directions) minus the fine level's valid boxes, NOT periodically shifted (FPinfo: complementIn)
-    std::vector<RegionTag> regs;
-    for (int n = 0; n < nf; ++n) {
-        HBox r0 = grow(F.boxes[n], PNG);
-        for (int d = 0; d < 3; ++d)
-            if (!F.G.periodic[d]) {
-                r0.lo[d] = std::max(r0.lo[d], F.G.dlo[d]);
-                r0.hi[d] = std::min(r0.hi[d], F.G.dhi[d]);
-            }
-        std::vector<HBox> list{r0};
-        for (const HBox& v : F.boxes) {
-            std::vector<HBox> next;
-            for (const HBox& r : list) box_diff(r, v, next);
-            list.swap(next);
-        }
-        for (const HBox& r : list) {
-            for (int d = 0; d < 3; ++d) {
-                if (F.G.periodic[d]) continue;
-                // slopes of coarse cells on a non-periodic domain face are one-sided and depend on the extents of
-                // AMReX's internal coarse patch (AMReX_MFInterp_C.H:15-33): not reproduced
-                if (floor_div2(r.lo[d]) <= Cl.G.dlo[d] || floor_div2(r.hi[d]) >= Cl.G.dhi[d])
-                    return fail("level %d: a fine box lies within one coarse cell of a non-periodic domain face; the "
-                                "coarse-fine interpolation there is not supported", F.lev);
-            }
-            RegionTag t;
-            t.box = n;
-            for (int d = 0; d < 3; ++d) t.lo[d] = r.lo[d], t.n[d] = r.hi[d] - r.lo[d] + 1;
-            regs.push_back(t);
-            I.reg_max = std::max(I.reg_max, r.pts());
-        }
-    }
-    I.nregs = (int)regs.size();
-    if (I.nregs) {
-        CU(cudaMalloc(&I.d_regs, regs.size() * sizeof(RegionTag)));
-        CU(cudaMemcpy(I.d_regs, regs.data(), regs.size() * sizeof(RegionTag), cudaMemcpyHostToDevice));
-    }
+    if (build_interp(I, F.boxes, F.G, F.lev, Cl, F.boxes)) return 1;
     I.valid = true;
     F.inter_coarse_generation = Cl.generation;
     return 0;
@@ -765,6 +778,80 @@ int mbl_box_download_macrodata(mbl_ctx* ctx, int lev, int ibox, double* fab, int
     double* src = derived ? b.macro + (size_t)MBL_NMACRO * b.sq : b.macro;
     if (copy_fab(b, src, derived ? MBL_NDERIVED : MBL_NMACRO, fab, ng, false, ctx->stream)) return 1;
     CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// LBM::RemakeLevel (LBM.cpp:1302-1364) after AmrCore::regrid changed the box list of level lev >= 1: the new level's
+// f, g by FillPatchOps::fillpatch into NEW FABs -- K6 pre-pass on the old level, cells no OLD valid box covers by
+// CellConservativeLinear from level lev - 1, everything the old level covers copied from it (periodic images
+// included), BCFill.  The caller then hands over the new is_fluid (mbl_box_set_is_fluid) and calls
+// mbl_fill_f_inside_eb, as RemakeLevel does.
+int mbl_level_regrid(mbl_ctx* ctx, int lev, int nboxes, const int* lo, const int* hi)
+{
+    if (!ctx || !lo || !hi) return fail("null argument");
+    if (lev < 1 || lev >= MAX_LEVELS || !ctx->plev[lev] || !ctx->plev[lev - 1])
+        return fail("mbl_level_regrid: levels %d and %d must be multi-box levels", lev - 1, lev);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    PatchLevel* old = ctx->plev[lev];
+    ctx->launches += launch_patch_prepass(old->set.d, (int)old->boxes.size(), old->set.max_cells, old->cur, old->G, st);
+    CU(cudaStreamSynchronize(st));
+    ctx->plev[lev] = nullptr;  // keep the old level alive while the new one is filled from it
+    const mbl_level_geom geom = old->geom;
+    int rc = mbl_level_define_boxes(ctx, lev, &geom, nboxes, lo, hi);
+    PatchLevel* L = ctx->plev[lev];
+    if (!rc) {
+        PatchLevel& Cl = *ctx->plev[lev - 1];
+        Inter tmp;
+        rc = build_interp(tmp, L->boxes, L->G, lev, Cl, old->boxes);
+        if (!rc) {
+            for (int arr = PA_F; arr <= PA_G; ++arr)
+                ctx->launches += launch_patch_copy(tmp.cpatch.d, 0, Cl.set.d, Cl.cur, tmp.c2p.d, tmp.c2p.n, arr, arr, NQ,
+                                                   tmp.c2p.max_cells, st);
+            ctx->launches += launch_patch_interp(L->set.d, L->cur, tmp.cpatch.d, tmp.d_regs, tmp.nregs, tmp.reg_max, st);
+            // FillPatchSingleLevel(new, {old}): valid and ghost cells of the new boxes that lie on old valid cells
+            std::vector<CopyTag> tags;
+            const auto shifts = periodic_shifts(L->G, PNG);
+            for (int i = 0; i < (int)L->boxes.size(); ++i)
+                for (const auto& s : shifts) {
+                    const int sh[3] = {s[0], s[1], s[2]};
+                    for (int j = 0; j < (int)old->boxes.size(); ++j) {
+                        const HBox r = isect(grow(L->boxes[i], PNG), shifted(old->boxes[j], sh));
+                        if (r.ok()) tags.push_back(make_tag(i, j, r, sh));
+                    }
+                }
+            Tags t;
+            rc = upload_tags(tags, t);
+            if (!rc) {
+                for (int arr = PA_F; arr <= PA_G; ++arr)
+                    ctx->launches += launch_patch_copy(L->set.d, L->cur, old->set.d, old->cur, t.d, t.n, arr, arr, NQ, t.max_cells, st);
+                cudaStreamSynchronize(st);
+            }
+            t.free_all();
+        }
+        cudaStreamSynchronize(st);
+        tmp.free_all();
+    }
+    // release the old level
+    PatchLevel* keep = ctx->plev[lev];
+    ctx->plev[lev] = old;
+    patch_clear(ctx, lev);
+    ctx->plev[lev] = keep;
+    if (rc) return 1;
+    CU(cudaGetLastError());
+    return patch_physbc(ctx, lev, 0.0);
+}
+
+// fill_f_inside_eb (LBM.cpp:1278-1298) + the FillBoundary that follows it in RemakeLevel (LBM.cpp:1347-1348)
+int mbl_fill_f_inside_eb(mbl_ctx* ctx, int lev)
+{
+    PatchLevel* L = plevel(ctx, lev);
+    if (!L) return 1;
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches += launch_patch_zero_solid(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->cur, ctx->stream);
+    fill_boundary(ctx, *L, PA_F, NQ, PNG);
+    fill_boundary(ctx, *L, PA_G, NQ, PNG);
+    CU(cudaGetLastError());
     return 0;
 }
 

@@ -397,6 +397,42 @@ int mbl_set_is_fluid(mbl_ctx* ctx, int lev, const int32_t* is_fluid, int ng)
     return 0;
 }
 
+// LBM::initialize_is_fluid for the analytic bodies of the shipped decks, evaluated on the device (no host field, no
+// upload): kind 1 sphere {cx, cy, cz, r, fluid_inside}, 2 cylinder {cx, cy, cz, r, height, direction, fluid_inside},
+// 3 box {lox, loy, loz, hix, hiy, hiz, fluid_inside}; 0 = all_regular
+int mbl_set_body(mbl_ctx* ctx, int lev, int kind, const double* v, int nv)
+{
+    if (check_level(ctx, lev)) return 1;
+    if (kind == 0) return mbl_set_all_fluid(ctx, lev);
+    if (kind < 1 || kind > 3 || !v) return fail("mbl_set_body: unknown body kind %d", kind);
+    if (nv < (kind == 1 ? 5 : 7)) return fail("mbl_set_body: too few parameters for body kind %d", kind);
+    Level& lv = ctx->lev[lev];
+    lv.carry_valid = false;
+    CU(cudaSetDevice(ctx->device));
+    BodyInfo G;
+    memset(&G, 0, sizeof(G));
+    G.kind = kind;
+    if (kind == 1) {
+        G.a[0] = v[0], G.a[1] = v[1], G.a[2] = v[2], G.r = v[3], G.fluid_inside = v[4] != 0.0;
+    } else if (kind == 2) {
+        G.a[0] = v[0], G.a[1] = v[1], G.a[2] = v[2], G.r = v[3], G.h = v[4], G.axis = (int)v[5], G.fluid_inside = v[6] != 0.0;
+        if (G.axis < 0 || G.axis > 2) return fail("mbl_set_body: cylinder direction %d", G.axis);
+    } else {
+        for (int d = 0; d < 3; ++d) G.a[d] = v[d], G.b[d] = v[3 + d];
+        G.fluid_inside = v[6] != 0.0;
+    }
+    const int ng = 3;  // m_is_fluid's ghost width (Source/LBM.cpp:1166)
+    const size_t n = (size_t)(lv.L.nx + 2 * ng) * (lv.L.ny + 2 * ng) * (lv.L.nz + 2 * ng);
+    int32_t* stage = nullptr;
+    CU(cudaMalloc(&stage, n * sizeof(int32_t)));
+    ctx->launches += launch_body_is_fluid(lv.L, lv.B, G, stage, ng, ctx->stream);
+    ctx->launches += launch_flags(lv.L, lv.B, stage, ng, lv.p.nbr, lv.p.flag, ctx->stream);
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(stage);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 // planes [ka, kb) of the components of one lattice (or of the macrodata) between a host FAB (ghost width ng, interior only)
 // and the padded SoA buffer: one pitched DMA per component, no staging kernel
 // (with_ghosts: also the FAB's ghost cells the device layout has room for, as mbl_upload does)

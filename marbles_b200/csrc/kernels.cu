@@ -1288,6 +1288,55 @@ __global__ void __launch_bounds__(128) k_flags(const int32_t* __restrict__ fab, 
     flag[c] = (uint8_t)fb;
 }
 
+// ---------------------------------------------------------------------------
+// is_fluid of the analytic bodies of the shipped decks, evaluated on the device: a cell is
+// solid when all 8 of its corners lie inside the body (EB2's covered-cell rule for these implicit functions; the
+// same rule as the host mirror marbles_b200/geometry.py, which tests/ check against the reference's own is_fluid).
+// Written in FAB layout over the box grown by ng, so that k_flags consumes it like an uploaded m_is_fluid: ghost
+// cells of periodic directions take the periodic image (m_is_fluid.FillBoundary), ghost cells beyond a non-periodic
+// face the geometry evaluated beyond the domain (LBM.cpp:1222-1234).  Explicit roundings: no FMA, same bits as numpy.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool node_in_body(const BodyInfo& G, double x, double y, double z)
+{
+    const double p[3] = {__dsub_rn(x, G.a[0]), __dsub_rn(y, G.a[1]), __dsub_rn(z, G.a[2])};
+    bool inside;
+    if (G.kind == 1) {  // sphere: a = centre, r
+        inside = __dadd_rn(__dadd_rn(__dmul_rn(p[0], p[0]), __dmul_rn(p[1], p[1])), __dmul_rn(p[2], p[2])) < __dmul_rn(G.r, G.r);
+    } else if (G.kind == 2) {  // cylinder: a = centre, r, height h along `axis`
+        double rad2 = 0.0;
+        for (int d = 0; d < 3; ++d)
+            if (d != G.axis) rad2 = __dadd_rn(rad2, __dmul_rn(p[d], p[d]));
+        inside = rad2 < __dmul_rn(G.r, G.r);
+        if (G.h > 0.0) inside = inside && fabs(p[G.axis]) < __dmul_rn(0.5, G.h);
+    } else {  // box: a = lo, b = hi
+        inside = x > G.a[0] && x < G.b[0] && y > G.a[1] && y < G.b[1] && z > G.a[2] && z < G.b[2];
+    }
+    return G.fluid_inside ? !inside : inside;  // true: the node is solid
+}
+
+__global__ void __launch_bounds__(128) k_body_is_fluid(int32_t* __restrict__ fab, int ng, Layout L, BcInfo B, BodyInfo G)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - ng;
+    const int j = blockIdx.y - ng;
+    const int k = blockIdx.z - ng;
+    if (i >= L.nx + ng) return;
+    int gidx[3] = {i + L.lo[0], j + L.lo[1], k + L.lo[2]};
+    for (int d = 0; d < 3; ++d)
+        if (B.periodic[d]) {
+            const int n = L.dhi[d] - L.dlo[d] + 1;
+            gidx[d] = L.dlo[d] + (((gidx[d] - L.dlo[d]) % n) + n) % n;
+        }
+    bool all_solid = true;
+    for (int c = 0; c < 8; ++c) {
+        const double x = __dadd_rn(B.prob_lo[0], __dmul_rn((double)(gidx[0] + (c & 1)), B.dx[0]));
+        const double y = __dadd_rn(B.prob_lo[1], __dmul_rn((double)(gidx[1] + ((c >> 1) & 1)), B.dx[1]));
+        const double z = __dadd_rn(B.prob_lo[2], __dmul_rn((double)(gidx[2] + ((c >> 2) & 1)), B.dx[2]));
+        all_solid = all_solid && node_in_body(G, x, y, z);
+    }
+    const long long sx = L.nx + 2 * ng, sy = L.ny + 2 * ng;
+    fab[(i + ng) + (j + ng) * sx + (long long)(k + ng) * sx * sy] = all_solid ? 0 : 1;
+}
+
 __global__ void k_fill(double* __restrict__ p, long long n, double v)
 {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1358,6 +1407,13 @@ int launch_flags(const Layout& L, const BcInfo& B, const int32_t* fab, int ng, u
 int launch_flags_all_fluid(const Layout& L, const BcInfo& B, uint32_t* nbr, uint8_t* flag, cudaStream_t st)
 {
     return launch_flags(L, B, nullptr, 0, nbr, flag, st);
+}
+
+int launch_body_is_fluid(const Layout& L, const BcInfo& B, const BodyInfo& G, int32_t* fab, int ng, cudaStream_t st)
+{
+    const int bx = block_x(L);
+    k_body_is_fluid<<<dim3((L.nx + 2 * ng + bx - 1) / bx, L.ny + 2 * ng, L.nz + 2 * ng), bx, 0, st>>>(fab, ng, L, B, G);
+    return 1;
 }
 
 int launch_fill(double* p, long long n, double v, cudaStream_t st)

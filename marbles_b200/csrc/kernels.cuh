@@ -19,6 +19,15 @@ struct IcInfo {
     double density, vel[3], v0, omega[3], wave_length, T0, gamma, R, c_s, density_ratio, temperature_ratio, x_disc;
 };
 
+// analytic embedded-boundary body of a deck (eb2.geom_type = sphere | cylinder | box, Source/EB.cpp:5-38)
+struct BodyInfo {
+    int kind;          // 1 sphere, 2 cylinder, 3 box
+    int axis;          // cylinder direction
+    int fluid_inside;  // eb2.*_has_fluid_inside
+    double a[3], b[3]; // centre (sphere, cylinder) or box lo; box hi
+    double r, h;       // radius; cylinder height (<= 0: unbounded)
+};
+
 struct LevelPtrs {
     double* f[2];  // ping-pong lattice buffers
     double* g[2];
@@ -34,6 +43,9 @@ void init_tables();
 int launch_flags(const Layout& L, const BcInfo& B, const int32_t* d_isfluid_fab, int ng, uint32_t* nbr, uint8_t* flag,
                  cudaStream_t st);
 int launch_flags_all_fluid(const Layout& L, const BcInfo& B, uint32_t* nbr, uint8_t* flag, cudaStream_t st);
+
+// is_fluid (FAB layout, box grown by ng) of an analytic body, on the device
+int launch_body_is_fluid(const Layout& L, const BcInfo& B, const BodyInfo& G, int32_t* fab, int ng, cudaStream_t st);
 
 int launch_fill(double* p, long long n, double v, cudaStream_t st);
 

@@ -98,6 +98,19 @@ __global__ void __launch_bounds__(PT) k_patch_initialize(const PBox* __restrict_
     }
 }
 
+// fill_f_inside_eb (LBM.cpp:1278-1298): f = g = 0 in solid cells of the grown box
+__global__ void __launch_bounds__(PT) k_patch_zero_solid(const PBox* __restrict__ tab, int cur)
+{
+    const PBox B = tab[blockIdx.y];
+    for (long long t = (long long)blockIdx.x * PT + threadIdx.x; t < B.sq; t += (long long)gridDim.x * PT) {
+        if (B.isfl[t] != 0) continue;
+        for (int q = 0; q < NQ; ++q) {
+            B.f[cur][q * B.sq + t] = 0.0;
+            B.g[cur][q * B.sq + t] = 0.0;
+        }
+    }
+}
+
 // K6: every out-of-domain ghost takes the no-slip value of the in-domain cell it faces (FillPatchOps.H:92-108)
 __global__ void __launch_bounds__(PT) k_patch_prepass(const PBox* __restrict__ tab, int cur, PGeom G)
 {
@@ -492,6 +505,12 @@ int launch_patch_initialize(const PBox* tab, int nb, long long max_cells, int cu
                             cudaStream_t st)
 {
     k_patch_initialize<<<dim3(blocks_for(max_cells, PT), nb), PT, 0, st>>>(tab, cur, B, I);
+    return 1;
+}
+
+int launch_patch_zero_solid(const PBox* tab, int nb, long long max_cells, int cur, cudaStream_t st)
+{
+    k_patch_zero_solid<<<dim3(blocks_for(max_cells, PT), nb), PT, 0, st>>>(tab, cur);
     return 1;
 }
 

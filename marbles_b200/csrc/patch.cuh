@@ -62,6 +62,7 @@ int launch_patch_copy(const PBox* dtab, int dcur, const PBox* stab, int scur, co
 int launch_patch_fill(const PBox* tab, int nb, long long max_cells, int cur, int arr, int ncomp, double v, cudaStream_t st);
 int launch_patch_initialize(const PBox* tab, int nb, long long max_cells, int cur, const BcInfo& B, const IcInfo& I,
                             cudaStream_t st);
+int launch_patch_zero_solid(const PBox* tab, int nb, long long max_cells, int cur, cudaStream_t st);
 int launch_patch_prepass(const PBox* tab, int nb, long long max_cells, int cur, const PGeom& G, cudaStream_t st);
 // BCFill over faces, edges, corners of every box (26 launches at most; regions that are empty for every box are skipped
 // by the caller through `any_outside`)

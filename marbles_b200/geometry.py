@@ -19,6 +19,26 @@ def _vec(deck, key, default):
     return [float(v) for v in deck[key]] if key in deck else list(default)
 
 
+def body_from_deck(deck: dict):
+    """(kind, parameters) of the deck's analytic body for mbl_set_body, which evaluates the flag field on the device
+    (include/marbles_b200.h); None for a body the library does not know (the caller then supplies is_fluid)."""
+    gtype = deck.get("eb2.geom_type", ["all_regular"])[0]
+    if gtype == "all_regular":
+        return 0, []
+    if gtype == "sphere":
+        c = _vec(deck, "eb2.sphere_center", [0, 0, 0])
+        return 1, c + [float(deck["eb2.sphere_radius"][0]), float(int(deck.get("eb2.sphere_has_fluid_inside", ["0"])[0]))]
+    if gtype == "cylinder":
+        c = _vec(deck, "eb2.cylinder_center", [0, 0, 0])
+        return 2, c + [float(deck["eb2.cylinder_radius"][0]), float(deck.get("eb2.cylinder_height", ["-1"])[0]),
+                       float(int(deck.get("eb2.cylinder_direction", ["0"])[0])),
+                       float(int(deck.get("eb2.cylinder_has_fluid_inside", ["0"])[0]))]
+    if gtype == "box":
+        return 3, _vec(deck, "eb2.box_lo", [0, 0, 0]) + _vec(deck, "eb2.box_hi", [0, 0, 0]) + \
+            [float(int(deck.get("eb2.box_has_fluid_inside", ["0"])[0]))]
+    return None
+
+
 def _corner_coords(n, lo, prob_lo, dx, ng):
     """node coordinates of the grown box, per dimension (length n+2ng+1)"""
     return [prob_lo[d] + (np.arange(lo[d] - ng, lo[d] + n[d] + ng + 1)) * dx[d] for d in range(3)]

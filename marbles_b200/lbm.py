@@ -27,7 +27,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import LevelGeom, Layout, MarblesError, Params, check
-from .geometry import is_fluid_from_deck
+from .geometry import body_from_deck, is_fluid_from_deck
 from .inputs import LbmInputs, lbm_inputs, parse_deck
 
 NQ, NMACRO, NDERIVED = 27, 19, 7
@@ -129,12 +129,13 @@ class LBM:
         self.layout = Layout()
         check(self.lib.mbl_level_layout(C.byref(g), C.byref(self.layout)))
         check(self.lib.mbl_level_define(self.ctx, self.lev, C.byref(g), None))
-        self._is_fluid = None
+        self._is_fluid_cache = None
+        self._all_fluid = True
         self._halo = None
         self.set_is_fluid(is_fluid)
         # lean z-halo (half the bytes per exchange): legal where no bounce-back and no boundary ghost value sits next
         # to a slab cut -- all-periodic decks without solid cells
-        self.halo_lean = (world > 1 and all(self.inp.periodic) and int(self._is_fluid.min()) == 1
+        self.halo_lean = (world > 1 and all(self.inp.periodic) and self._all_fluid
                           and os.environ.get("MBL_HALO_LEAN", "1") != "0")
         check(self.lib.mbl_set_halo_lean(self.ctx, int(self.halo_lean)))
 
@@ -157,6 +158,15 @@ class LBM:
         nx, ny, nz = self.n_local
         full = (nz + 2 * ng, ny + 2 * ng, nx + 2 * ng)
         if is_fluid is None:
+            body = body_from_deck(self.inp.deck)
+            if body is not None and os.environ.get("MBL_HOST_GEOMETRY", "0") != "1":
+                # the analytic bodies of the shipped decks are evaluated on the device (mbl_set_body): no host field,
+                # no upload; the host copy (plotfiles) is made on demand
+                kind, par = body
+                self._is_fluid_cache, self._all_fluid = None, kind == 0
+                v = (C.c_double * max(len(par), 1))(*par)
+                check(self.lib.mbl_set_body(self.ctx, self.lev, kind, v, len(par)))
+                return
             a = slab_is_fluid_from_deck(self.inp, self.lo[2], self.hi[2], ng)
             if a.min() == 1:
                 self._is_fluid = a
@@ -178,6 +188,18 @@ class LBM:
                 raise MarblesError(f"is_fluid has shape {is_fluid.shape}, expected {(nz, ny, nx)} or {full}")
         self._is_fluid = a
         check(self.lib.mbl_set_is_fluid(self.ctx, self.lev, a.ctypes.data_as(C.POINTER(C.c_int32)), ng))
+
+    @property
+    def _is_fluid(self) -> np.ndarray:
+        """host copy of is_fluid (component 0, slab grown by 3); evaluated on demand when the device built the flags"""
+        if self._is_fluid_cache is None:
+            self._is_fluid_cache = slab_is_fluid_from_deck(self.inp, self.lo[2], self.hi[2], F_NGHOST)
+        return self._is_fluid_cache
+
+    @_is_fluid.setter
+    def _is_fluid(self, a: np.ndarray):
+        self._is_fluid_cache = a
+        self._all_fluid = bool(int(a.min()) == 1)
 
     def _wrap_periodic(self, a: np.ndarray, ng: int, z_local: bool, n_local=None) -> np.ndarray:
         """m_is_fluid.FillBoundary(periodicity): ghost cells in periodic directions mirror the valid cells."""

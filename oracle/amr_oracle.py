@@ -253,10 +253,14 @@ class AmrOracle:
         L.fill_boundary("g", L.params.ng)
         self.physbc(lev)
 
-    def _interp_from_coarse(self, lev, name, ratio=2):
-        """ghost cells of level lev inside the (periodically grown) domain that no valid cell of the level
-        covers (FPinfo: complementIn WITHOUT periodic shifts): CellConservativeLinear from level lev-1"""
-        Lf, Lc = self.levels[lev], self.levels[lev - 1]
+    def _interp_from_coarse(self, lev, name, ratio=2, target=None, cover=None):
+        """cells of the target boxes (default: level lev itself) grown by the ghost width, inside the (periodically
+        grown) domain, that no valid cell of `cover` (default: level lev's own boxes) lies on -- FPinfo: complementIn
+        WITHOUT periodic shifts: CellConservativeLinear from level lev-1.  With another `target` / `cover` this is
+        the fill of a re-made level from the old one (RemakeLevel)."""
+        Lf = self.levels[lev] if target is None else target
+        Lc = self.levels[lev - 1]
+        cover_mask = Lf.cover if cover is None else cover
         ng = Lf.params.ng
         Gc = Lc.gather(name, NQ)
         for b in Lf.boxes:
@@ -278,7 +282,7 @@ class AmrOracle:
                 sh = [1, 1, 1]
                 sh[ax] = -1
                 ins &= ok.reshape(sh)
-            m &= ~(ins & (Lf.cover[K, J, I] >= 0))
+            m &= ~(ins & (cover_mask[K, J, I] >= 0))
             if not m.any():
                 continue
             # coarse patch: coarsen(grown box) grown by 1, filled from the coarse level's valid cells (periodic)
@@ -390,6 +394,40 @@ class AmrOracle:
                         # direction, all eight fine cells masked: solid cells of a body that crosses the periodic face);
                         # the reference copies whatever its arena held there.  Only solid cells can receive it.
                         dst[(slice(None),) + d_s] = src
+
+    def regrid_level(self, lev, new_boxes, is_fluid_dense=None):
+        """LBM::RemakeLevel (Source/LBM.cpp:1302-1364) for a box list that AmrCore::regrid changed: the new level's f, g
+        by FillPatchOps::fillpatch into NEW MultiFabs -- K6 pre-pass on the old level, cells the OLD level's valid
+        boxes do not cover by interpolation from level lev-1, the rest copied from the old level (periodic images
+        included), BCFill -- then is_fluid, fill_f_inside_eb (zero in solid cells, LBM.cpp:1278-1298) and FillBoundary."""
+        assert lev >= 1
+        old = self.levels[lev]
+        for b in old.boxes:
+            self.lib.orc_prepass(C.byref(b.p), _ptr(b.f))
+            self.lib.orc_prepass(C.byref(b.p), _ptr(b.g))
+        new = Level(lev, self.setup, new_boxes)
+        new.time = old.time
+        ng = new.params.ng
+        for name in ("f", "g"):
+            self._interp_from_coarse(lev, name, target=new, cover=old.cover)
+            G = old.gather(name, NQ)  # FillPatchSingleLevel(mf, nghost, {old fine}): valid + ghost cells, periodic
+            for b in new.boxes:
+                a = getattr(b, name)
+                w, ok = new.wrapped(b.grown_index(ng))
+                K, J, I = np.meshgrid(*w, indexing="ij")
+                m = ok[0][:, None, None] & ok[1][None, :, None] & ok[2][None, None, :]
+                m &= old.cover[K, J, I] >= 0
+                a[:, m] = G[:, K[m], J[m], I[m]]
+        self.levels[lev] = new
+        self.physbc(lev)
+        self._set_is_fluid(new, is_fluid_dense)
+        for b in new.boxes:  # fill_f_inside_eb
+            solid = b.is_fluid[0] == 0
+            b.f[:, solid] = 0.0
+            b.g[:, solid] = 0.0
+        new.fill_boundary("f", ng)
+        new.fill_boundary("g", ng)
+        self._macrodata(new)
 
     # ------------------------------------------------------------ time stepping
     def advance(self, lev):

@@ -11,7 +11,7 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = ["tg12", "sod48", "chcyl", "thermal", "pressure", "slip", "shear", "slipyz", "touch"]
 
 
-AMR_GOLDEN_CASES = ["amr2_tg", "amr2_chcyl", "amr3_chcyl", "amr2_sod"]
+AMR_GOLDEN_CASES = ["amr2_tg", "amr2_chcyl", "amr3_chcyl", "amr2_sod", "amr2_sod_regrid"]
 
 
 def pytest_configure(config):
@@ -56,3 +56,11 @@ def golden_is_fluid(name):
     grown = is_fluid_from_deck(inp.deck, inp.n_cell, inp.prob_lo, inp.dx, ng=3)
     assert np.array_equal(grown[3:-3, 3:-3, 3:-3], fl)
     return grown
+
+
+def amr_boxes_at(z, step, lev):
+    """box list of level lev during coarse step `step` of a dynamically regridded golden case (None: unchanged)"""
+    key = f"boxes_s{step}_l{lev}"
+    if key not in z.files:
+        return None
+    return [(list(map(int, b[0])), list(map(int, b[1]))) for b in z[key]]

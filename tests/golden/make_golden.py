@@ -374,6 +374,17 @@ tagging.box.in_box_hi = 40.0 3.0 3.0
 """, 2, [0, 1, 4]),
 }
 
+# sod_amr.inp's dynamic refinement: regrid every coarse step (amr.regrid_int = 1), cells tagged where the density
+# differs from a neighbour's; the fine boxes grow, split and shrink as the waves travel.  The box list of level 1 is
+# stored for EVERY step (`boxes_s<N>_l1`): it is the input a regrid hands to RemakeLevel.
+AMR_CASES["amr2_sod_regrid"] = (AMR_CASES["amr2_sod"][0].replace("max_step = 4", "max_step = 16")
+                                .replace("amr.n_error_buf = 0", "amr.n_error_buf = 1")
+                                .split("tagging.refinement_indicators")[0] + """tagging.refinement_indicators = rho
+tagging.rho.adjacent_difference_greater = 0.02
+tagging.rho.field_name = rho
+""", 2, [0, 1, 8, 16])
+AMR_REGRID_INT = {"amr2_sod_regrid": 1}
+
 AMR_KEEP_LAST = KEEP_STEP0 + ["dQCorrX", "dQCorrY", "dQCorrZ"]
 AMR_KEEP_MID = O.MACRO_NAMES
 
@@ -384,11 +395,17 @@ def make_amr(out_dir, only):
             continue
         work = tempfile.mkdtemp(prefix=f"golden_{name}_")
         deck_text = deck.strip() + "\n" + AMR_COMMON
+        if name in AMR_REGRID_INT:
+            deck_text = deck_text.replace("amr.regrid_int = 1000000", f"amr.regrid_int = {AMR_REGRID_INT[name]}")
         deck_path = os.path.join(work, "case.inp")
         with open(deck_path, "w") as fh:
             fh.write(deck_text)
         O.run_reference(deck_path, work, [], omp=False)
         data = {"deck": np.array(deck_text), "steps": np.array(steps), "nlev": np.array(nlev)}
+        if name in AMR_REGRID_INT:
+            for st in range(1, steps[-1] + 1):
+                for lev in range(1, nlev):
+                    data[f"boxes_s{st}_l{lev}"] = np.array(O.read_plotfile_boxes(os.path.join(work, f"plt{st:05d}"), lev))
         for lev in range(nlev):
             data[f"boxes_l{lev}"] = np.array(O.read_plotfile_boxes(os.path.join(work, "plt00000"), lev))
             for s in steps:

@@ -6,7 +6,7 @@ Tolerance: 1e-12 of the field scale per level step (tests/parity.py)."""
 import numpy as np
 import pytest
 
-from conftest import AMR_GOLDEN_CASES, load_amr_golden
+from conftest import AMR_GOLDEN_CASES, amr_boxes_at, load_amr_golden
 from parity import compare, scales
 
 pytestmark = pytest.mark.gpu
@@ -57,8 +57,16 @@ def test_amr_cuda_vs_reference_golden(case):
         if s == 0:
             compare_levels(amr, lambda lev: golden_level(z, 0, lev), 1, amr.inp, macro=False, keys=fg)
             continue
-        amr.step(s - done, want_macrodata=True)
-        done = s
+        current = {lev: amr.boxes[lev] for lev in range(1, amr.finest + 1)}
+        while done < s:
+            # AmrCore::regrid at the start of a coarse step: levels whose box list changed are re-made on the device
+            for lev in range(1, amr.finest + 1):
+                nb = amr_boxes_at(z, done + 1, lev)
+                if nb is not None and [(tuple(a), tuple(b)) for a, b in nb] != list(current[lev]):
+                    amr.regrid_level(lev, nb, is_fluid[lev])
+                    current[lev] = amr.boxes[lev]
+            amr.step(1, want_macrodata=done + 1 == s)
+            done += 1
         last = s == steps[-1]
         print(f"{case} step {s}")
         ref_of = lambda lev: golden_level(z, s, lev)
@@ -132,9 +140,10 @@ def test_level_bind_is_zero_copy_and_bit_identical():
     b.close()
 
 
-def test_redefine_level_after_regrid(oracle_mod):
-    """the box list of the fine level changes between two coarse steps (what RemakeLevel hands over after a regrid:
-    same region, different boxes); the run continues and matches the oracle driven through the same change"""
+def test_regrid_moves_the_fine_level(oracle_mod):
+    """mbl_level_regrid (RemakeLevel) on the periodic Taylor-Green hierarchy: the fine region is shifted by two coarse
+    cells and cut differently between two coarse steps, so the new boxes take old fine data, coarse-fine interpolated
+    data (new valid cells) and periodic images; the run continues and matches the oracle driven through the same change"""
     from oracle import amr_oracle as A
     O = oracle_mod
     amr, z, deck_text, steps, boxes, is_fluid = new_amr("amr2_tg")
@@ -143,34 +152,17 @@ def test_redefine_level_after_regrid(oracle_mod):
     o.initialize()
     o.step(2)
     amr.step(2)
-    # new fine box list: the same region cut differently (pairs of x-neighbours merged)
-    old = boxes[1]
-    merged, used = [], set()
-    for i, (lo, hi) in enumerate(old):
-        if i in used:
-            continue
-        mate = next((j for j, (l2, h2) in enumerate(old) if j not in used and j != i and l2[0] == hi[0] + 1 and
-                     l2[1:] == lo[1:] and h2[1:] == hi[1:]), None)
-        if mate is None:
-            merged.append((lo, hi))
-        else:
-            used.add(mate)
-            merged.append((lo, [old[mate][1][0], hi[1], hi[2]]))
-        used.add(i)
-    assert len(merged) < len(old)
-    new_boxes = [boxes[0], merged]
-    amr.redefine_level(1, merged, is_fluid[1])
-    o2 = A.AmrOracle(setup, new_boxes, is_fluid)
-    for lev in range(2):
-        for name in ("f", "g"):
-            G = o.levels[lev].gather(name, 27)
-            for b in o2.levels[lev].boxes:
-                getattr(b, name)[:, 3:-3, 3:-3, 3:-3] = G[:, b.lo[2]:b.hi[2] + 1, b.lo[1]:b.hi[1] + 1, b.lo[0]:b.hi[0] + 1]
-            o2.levels[lev].fill_boundary(name, 3)
-    o2.step(2)
+    lo = [min(b[0][d] for b in boxes[1]) for d in range(3)]
+    hi = [max(b[1][d] for b in boxes[1]) for d in range(3)]
+    lo2, hi2 = [lo[0] + 4, lo[1] - 4, lo[2]], [hi[0] + 4, hi[1] - 4, hi[2]]
+    xm = (lo2[0] + hi2[0] + 1) // 2 // 2 * 2
+    new = [(lo2, [xm - 1, hi2[1], hi2[2]]), ([xm, lo2[1], lo2[2]], hi2)]
+    o.regrid_level(1, new, is_fluid[1])
+    amr.regrid_level(1, new, is_fluid[1])
+    o.step(2)
     amr.step(2, want_macrodata=True)
     amr.compute_derived()
-    worst = compare_levels(amr, lambda lev: o2.fields(lev), 4, amr.inp)
+    worst = compare_levels(amr, lambda lev: o.fields(lev), 4, amr.inp)
     print(f"regrid: worst {worst:.2e}")
     amr.close()
 

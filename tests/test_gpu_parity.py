@@ -617,3 +617,26 @@ def test_body_crossing_a_domain_face_from_the_deck():
     worst, key = compare(lbm.fields(), ref, sc, steps[-1])
     print(f"touch (deck geometry): worst {worst:.2e} ({key})")
     lbm.close()
+
+
+@pytest.mark.parametrize("case", ["chcyl", "pressure", "slip", "touch"])
+def test_device_geometry_matches_host_geometry(case):
+    """mbl_set_body (analytic body evaluated on the device, ghost layers and periodic images included) against the
+    host mirror's is_fluid uploaded through mbl_set_is_fluid: same flags, hence bit-identical runs"""
+    import os
+    z, deck_text, steps = load_golden(case)
+    a = new_lbm(deck_text, None, variant=0)           # device geometry
+    os.environ["MBL_HOST_GEOMETRY"] = "1"
+    try:
+        b = new_lbm(deck_text, None, variant=0)       # host geometry, uploaded
+    finally:
+        os.environ.pop("MBL_HOST_GEOMETRY", None)
+    assert a._is_fluid_cache is None and b._is_fluid_cache is not None
+    a.step(5, want_macrodata=True)
+    b.step(5, want_macrodata=True)
+    assert np.array_equal(a.get_f(), b.get_f()) and np.array_equal(a.get_g(), b.get_g())
+    assert np.array_equal(a.get_macrodata(), b.get_macrodata())
+    fa, fb = a.compute_eb_forces(), b.compute_eb_forces()
+    assert np.array_equal(fa, fb)
+    a.close()
+    b.close()
