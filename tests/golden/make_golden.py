@@ -217,16 +217,18 @@ eb2.sphere_radius = 1.9
 eb2.sphere_center = 7.0 5.0 4.0
 eb2.sphere_has_fluid_inside = 0
 """, [0, 1, 6]),
-    # a body that crosses the pressure outlet and a no-slip wall: is_fluid of the out-of-domain ghost cells comes
-    # from the geometry evaluated beyond the domain (SURVEY A.4 last paragraph, the pine_box situation)
+    # a body that crosses the outlet and a no-slip wall: is_fluid of the out-of-domain ghost cells comes from the
+    # geometry evaluated beyond the domain (SURVEY A.4 last paragraph, the pine_box situation).  The outlet is the
+    # zeroth-order outflow: with the pressure outlet of `pressure` the reference itself blows up within 8 steps when a
+    # body sits on the outlet face (FPE trap at step 8), which is no basis for a round-off comparison
     "touch": ("""
-max_step = 6
+max_step = 8
 geometry.prob_lo = 0.0 0.0 0.0
 geometry.prob_hi = 10.0 10.0 14.0
 geometry.is_periodic = 0 0 0
 amr.n_cell = 10 10 14
 lbm.bc_lo = 1 1 2
-lbm.bc_hi = 1 1 3
+lbm.bc_hi = 1 1 5
 lbm.nu = 0.01733333333333333
 lbm.velocity_bc_type = "constant"
 velocity_bc_constant.dir = 2
@@ -238,7 +240,7 @@ eb2.geom_type = "box"
 eb2.box_lo = 5.5 3.5 10.5
 eb2.box_hi = 12.5 6.5 17.5
 eb2.box_has_fluid_inside = 0
-""", [0, 1, 6]),
+""", [0, 1, 8]),
 }
 
 KEEP_STEP0 = ([f"f_{q:02d}" for q in range(27)] + [f"g_{q:02d}" for q in range(27)] + O.MACRO_NAMES)
