@@ -636,7 +636,7 @@ def test_device_geometry_matches_host_geometry(case):
     b.step(5, want_macrodata=True)
     assert np.array_equal(a.get_f(), b.get_f()) and np.array_equal(a.get_g(), b.get_g())
     assert np.array_equal(a.get_macrodata(), b.get_macrodata())
-    fa, fb = a.compute_eb_forces(), b.compute_eb_forces()
-    assert np.array_equal(fa, fb)
+    fa, fb = a.compute_eb_forces(), b.compute_eb_forces()  # block sums meet in atomicAdd: their order is not fixed
+    assert np.abs(fa - fb).max() <= 1e-13
     a.close()
     b.close()
