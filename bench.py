@@ -287,7 +287,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--variant", type=int, default=None, help="step implementation (default: the library's, 5 = tile carry step); " +"0 two kernels (default), 1 fused persistent TMA kernel, 2 same as two launches, 3 fused persistent plain-load kernel, 4 carry step")
+    ap.add_argument("--variant", type=int, default=None, help="step implementation (default: the library's, 9 = tile carry step marching through z-chunks); 0 two kernels, "
+                         "5 tile carry step, 7 with plane pairs; 1-4 and 8 only with MBL_EXPERIMENTS=1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -377,7 +378,8 @@ def main():
     collide_ms = kms[2] / max(nrec.value, 1)
     kname = {0: "k_collide_lean (pull + collide)", 1: "k_fused (q-correction + collide jobs)", 2: "k_fused (collide jobs)",
              3: "k_fused_plain (q-correction + collide jobs)", 4: "k_collide_carry", 5: "k_collide_tile", 6: "k_collide_lean", 7: "k_collide_tile_pair",
-             8: "k_march (pull + q-correction + collide, one kernel)"}[lbm.variant]
+             8: "k_march (pull + q-correction + collide, one kernel)",
+             9: "k_collide_tile_march"}[lbm.variant]
     vname = {0: "two kernels (k_qcorr, k_collide_lean)", 1: "one persistent TMA-pipelined kernel per step",
              2: "persistent TMA kernel, two launches (q-correction, collide)",
              3: "one persistent kernel per step, plain loads",
@@ -386,12 +388,14 @@ def main():
              5: "carry step without marching: k_qcorr_combine + k_collide_tile",
              6: "two kernels, collide with g staged through shared memory (k_qcorr, k_collide_lean)",
              7: "tile carry step with plane pairs: k_qcorr_combine_pair + k_collide_tile_pair",
-             8: "march step: one kernel per step, z-marching CTAs, q-corrections recomputed on a one-cell halo"}[lbm.variant]
+             8: "march step: one kernel per step, z-marching CTAs, q-corrections recomputed on a one-cell halo",
+             9: "tile carry step marching through z-chunks: k_qcorr_combine_march + k_collide_tile_march (z sums completed "
+                "on chip, QCorr of most cells finished by the collide kernel)"}[lbm.variant]
     achieved = BYTES_PER_CELL * lbm.ncells / (collide_ms * 1e-3) / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            tkey = {0: "k_collide_lean", 6: "k_collide_lean", 5: "k_collide_tile", 4: "k_collide_carry", 7: "k_collide_tile_pair", 8: "k_march"}.get(lbm.variant)
+            tkey = {0: "k_collide_lean", 6: "k_collide_lean", 5: "k_collide_tile", 4: "k_collide_carry", 7: "k_collide_tile_pair", 8: "k_march", 9: "k_collide_tile_march"}.get(lbm.variant)
             traffic = json.load(fh).get("dram_bytes_per_launch_512", {}).get(tkey) if n == 512 else None
             if args.workload != "tg" or world > 1 and args.scaling == "strong":
                 traffic = None

@@ -276,10 +276,12 @@ int mbl_get_timing(mbl_ctx* ctx, double ms[3], int* nsteps);
  * type; 3 = one persistent warp-autonomous kernel with plain loads; 4, 5 = "carry" steps whose collide kernel
  * also emits partial sums of the next step's conserved moments, so the q-correction pass does not read the
  * populations again (4: threads march through rows, 5: one cell per thread, rows exchanged inside the CTA).
- * 5 is the default (boxes whose components exceed 4 GB fall back to 0); 6 = 0 with a chosen number of CTAs per
- * SM; 7 = 5 with the z sum of plane pairs completed on chip (9 carried words instead of 12; even nz, else 5);
- * 8 = one z-marching kernel per step.  Variants 1-4 and 8 are measured negative results and are compiled only
- * with MBL_EXPERIMENTS=1.  All variants agree to round-off (the carried moments are summed in another order);
+ * 6 = 0 with a chosen number of CTAs per SM; 7 = 5 with the z sum of plane pairs completed on chip (9 carried words
+ * instead of 12; even nz, else 5); 8 = one z-marching kernel per step; 9 = 5 marching through z-chunks of 8 planes
+ * (MBL_ZMARCH): the z sums are completed on chip and the collide kernel itself stores the next step's QCorr for the
+ * cells that are complete (3 words instead of 12; needs a second QCorr array).  9 is the default (boxes whose
+ * components exceed 4 GB fall back to 0, boxes with fewer than 4 planes to 5).  Variants 1-4 and 8 are measured
+ * negative results and are compiled only with MBL_EXPERIMENTS=1.  All variants agree to round-off (the carried moments are summed in another order);
  * DESIGN.md has the measurements. */
 int mbl_set_variant(mbl_ctx* ctx, int variant);
 int mbl_get_variant(mbl_ctx* ctx);

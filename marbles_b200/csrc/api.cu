@@ -101,7 +101,8 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
     // the carry kernels address a component with 32-bit byte offsets: larger boxes take the two-kernel step
     int variant = ctx->variant;
     if (variant == 7 && ((lv.L.nz & 1) || carry_tile_rows(ctx->carry_rows) != 6)) variant = 5;  // pairs need an even nz
-    if ((variant == 4 || variant == 5 || variant == 7 || variant == 8) && lv.L.sq * 8 >= (1LL << 32)) variant = 0;
+    if (variant == 9 && (lv.L.nz < 4 || carry_tile_rows(ctx->carry_rows) != 6)) variant = 5;    // z-march needs chunks of >= 2 planes
+    if ((variant == 4 || variant == 5 || variant == 7 || variant == 8 || variant == 9) && lv.L.sq * 8 >= (1LL << 32)) variant = 0;
 #ifdef MBL_EXPERIMENTS
     if (variant == 8 && !macro) {
         // march step: ONE kernel, no q-correction pass and no carried sums (experiments/march.cu)
@@ -113,14 +114,24 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
         lv.carry_valid = false;
     } else
 #endif
-    if (variant == 5 || variant == 7 || variant == 4) {
+    if (variant == 5 || variant == 7 || variant == 4 || variant == 9) {
         // carry step: q-corrections from the partial sums the previous collide left behind (first step, or after
         // anything else wrote the lattice: the full q-correction pass)
         if (!lv.part) CU(cudaMalloc(&lv.part, (size_t)CARRY_WORDS * lv.L.sq * sizeof(double)));
         const int W = carry_tile_rows(ctx->carry_rows);
         if (variant != 4 && !lv.edge)
             CU(cudaMalloc(&lv.edge, (size_t)CARRY_EDGE_WORDS * carry_edge_plane(lv.L, 4) * (lv.L.nz + 2 * GZ) * sizeof(double)));
-        if (lv.carry_valid && lv.part_pair)
+        if (variant == 9) {
+            if (!lv.qc2) {
+                CU(cudaMalloc(&lv.qc2, (size_t)3 * lv.L.sq * sizeof(double)));
+                CU(cudaMemsetAsync(lv.qc2, 0, (size_t)3 * lv.L.sq * sizeof(double), st));
+            }
+            if (!lv.zpos) CU(cudaMalloc(&lv.zpos, (size_t)(lv.L.nz + 2 * GZ)));
+        }
+        if (lv.carry_valid && lv.part_pair == 2)
+            ctx->launches += launch_qcorr_combine_march(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.part, lv.edge, lv.zpos,
+                                                        lv.p.qc, st);
+        else if (lv.carry_valid && lv.part_pair)
             ctx->launches += launch_qcorr_combine_pair(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.part, lv.edge, lv.p.qc, st);
         else if (lv.carry_valid)
             ctx->launches += launch_qcorr_combine(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.part,
@@ -135,7 +146,24 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
         } else {
             const CarryPlan C = make_carry_plan(Lk, ctx->carry_own, ctx->carry_ky);
             int nl;
-            if (variant == 7) {
+            if (variant == 9) {
+                // chunks of zm planes, none of a single plane; zpos says where each plane sits in its chunk
+                int zm = ctx->zmarch > 1 ? ctx->zmarch : 8;
+                while (lv.L.nz % zm == 1) ++zm;
+                if (lv.zpos_zm != zm) {
+                    std::vector<signed char> zp((size_t)lv.L.nz + 2 * GZ, 0);
+                    for (int k = 0; k < lv.L.nz; ++k) {
+                        const int kk = k % zm, nk = std::min(zm, lv.L.nz - (k - kk));
+                        zp[k + GZ] = kk == 0 ? 1 : kk == nk - 1 ? 2 : 0;
+                    }
+                    CU(cudaMemcpyAsync(lv.zpos, zp.data(), zp.size(), cudaMemcpyHostToDevice, st));
+                    CU(cudaStreamSynchronize(st));
+                    lv.zpos_zm = zm;
+                }
+                nl = launch_collide_tile_march(Lk, lv.P, C, zm, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
+                                               lv.p.qc, lv.qc2, lv.part, lv.edge, st);
+                if (nl > 0) std::swap(lv.p.qc, lv.qc2);  // the cells the kernel finished are in what is now lv.p.qc
+            } else if (variant == 7) {
                 nl = launch_collide_tile_pair(Lk, lv.P, C, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
                                               lv.p.qc, lv.part, lv.edge, st);
             } else if (variant == 4) {
@@ -150,8 +178,8 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
                                          lv.p.qc, lv.part, lv.edge, st);
             }
             lv.edge_rows = variant == 4 ? 0 : W;
-            lv.part_pair = variant == 7;
-            if (nl < 0) return fail("carry step: a lattice component exceeds 4 GB (32-bit byte offsets)");
+            lv.part_pair = variant == 7 ? 1 : variant == 9 ? 2 : 0;
+            if (nl < 0) return fail("carry step: launch failed (%d)", nl);
             ctx->launches += nl;
             lv.carry_valid = true;
         }
@@ -242,6 +270,7 @@ int mbl_create(const mbl_params* params, int device, mbl_ctx** out)
     if (const char* e = getenv("MBL_GRAPH")) c->use_graphs = atoi(e) != 0;
     if (const char* e = getenv("MBL_OWN")) c->carry_own = atoi(e) == 28 ? 28 : 30;
     if (const char* e = getenv("MBL_KY")) c->carry_ky = atoi(e) > 0 ? atoi(e) : 32;
+    if (const char* e = getenv("MBL_ZMARCH")) c->zmarch = atoi(e) > 1 ? atoi(e) : 8;
     if (const char* e = getenv("MBL_MINB")) c->carry_minb = atoi(e) >= 2 && atoi(e) <= 5 ? atoi(e) : 2;
     *out = c;
     return 0;
@@ -304,6 +333,13 @@ int mbl_level_clear(mbl_ctx* ctx, int lev)
     if (lv.graph) cudaGraphExecDestroy(lv.graph);
     if (lv.part) cudaFree(lv.part);
     if (lv.edge) cudaFree(lv.edge);
+    if (lv.zpos) cudaFree(lv.zpos);
+    if (lv.qc2) {
+        // the two q-correction arrays may have changed places: free the one that is not part of the state block
+        char* q = (char*)lv.p.qc;
+        const bool qc_in_block = q >= lv.base && q < lv.base + state_map(lv.L).total;
+        cudaFree(qc_in_block ? lv.qc2 : lv.p.qc);
+    }
     lv = Level();
     return 0;
 }
@@ -711,7 +747,7 @@ int mbl_step(mbl_ctx* ctx, int lev, int nsteps, double time, int want_macro)
     if (graphable && nsteps - tail >= 5) {
         if (step_local(ctx, lv, time, 0)) return 1;
         s = 1;
-        if (lv.graph && (lv.graph_cur != lv.cur || lv.graph_variant != ctx->variant)) {
+        if (lv.graph && (lv.graph_cur != lv.cur || lv.graph_variant != ctx->variant || lv.graph_qc != lv.p.qc)) {
             cudaGraphExecDestroy(lv.graph);
             lv.graph = nullptr;
         }
@@ -744,6 +780,7 @@ int mbl_step(mbl_ctx* ctx, int lev, int nsteps, double time, int want_macro)
             } else {
                 lv.graph_cur = lv.cur;  // two steps: the parity is back where the capture started
                 lv.graph_variant = ctx->variant;
+                lv.graph_qc = lv.p.qc;
             }
         }
         for (; lv.graph && s + 2 <= nsteps - tail; s += 2) {
@@ -781,7 +818,7 @@ int mbl_step_split(mbl_ctx* ctx, int lev, int part)
     };
     // variant 5 keeps carrying through the split: q-corrections from the previous step's partial sums
     // (k_qcorr_combine; planes next to a ghost plane are pulled as before), collide by k_collide_tile
-    const bool tile = (ctx->variant == 5 || ctx->variant == 7) && L.sq * 8 < (1LL << 32);
+    const bool tile = (ctx->variant == 5 || ctx->variant == 7 || ctx->variant == 9) && L.sq * 8 < (1LL << 32);
     const int W = carry_tile_rows(ctx->carry_rows);
     if (tile) {
         if (!lv.part) CU(cudaMalloc(&lv.part, (size_t)CARRY_WORDS * L.sq * sizeof(double)));
@@ -1116,7 +1153,7 @@ int mbl_get_variant(mbl_ctx* ctx) { return ctx ? ctx->variant : -1; }
 int mbl_set_variant(mbl_ctx* ctx, int variant)
 {
     if (!ctx) return fail("null context");
-    if (variant < 0 || variant > 8) return fail("variant %d is not available", variant);
+    if (variant < 0 || variant > 9) return fail("variant %d is not available", variant);
 #ifndef MBL_EXPERIMENTS
     if ((variant >= 1 && variant <= 4) || variant == 8)
         return fail("step variant %d is an experiment: rebuild the library with MBL_EXPERIMENTS=1", variant);

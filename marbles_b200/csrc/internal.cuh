@@ -73,12 +73,16 @@ struct Level {
     double* part = nullptr;   // carry step: 12 partial-sum words per cell (lazily allocated)
     double* edge = nullptr;   // tile carry step: 18 words per CTA row
     bool dq_from_macro = false;  // macrodata came from mbl_f_to_macrodata: compute_derived also differences QCorr
-    int part_pair = 0;        // `part` holds the 9-word plane-pair layout (variant 7)
+    int part_pair = 0;        // layout of `part`: 0 twelve words per cell, 1 plane pairs (variant 7), 2 z-march chunks (variant 9)
+    double* qc2 = nullptr;    // variant 9: the q-correction array the collide kernel writes for the next step
+    signed char* zpos = nullptr;  // variant 9: position of each plane in its z-chunk (0 interior, 1 first, 2 last)
+    int zpos_zm = 0;          // chunk length zpos was written for
     int edge_rows = 0;        // rows per CTA the edge arrays were written with (0: written by the marching kernel)
     // two consecutive steps (buffers a -> b -> a) captured as one CUDA graph: small boxes are launch-bound
     // (a non-periodic level issues ~30 ghost-fill launches per step)
     cudaGraphExec_t graph = nullptr;
     int graph_cur = -1, graph_variant = -1;  // buffer parity and step variant the graph was captured for
+    const double* graph_qc = nullptr;        // ... and which of the two QCorr arrays was current (variant 9 swaps them)
     int64_t graph_launches = 0;              // kernels per replay
     bool carry_valid = false; // `part` holds the partial sums of the current lattice buffers' next post-stream state
 };
@@ -95,10 +99,11 @@ struct mbl_ctx {
     // implementation of mbl_step: 0 (default, fastest measured): two kernels, k_qcorr + k_collide;
     // 1: persistent TMA-pipelined kernel with both job types; 2: the same kernel, one launch per job type;
     // 3: persistent warp-autonomous kernel (plain loads) with both job types.  DESIGN.md has the numbers.
-    int variant = 5;
+    int variant = 9;
     int uw = 128, band_rows = 16, lag_per_cta = 4;  // variants 1-3 tuning (MBL_UW / MBL_BAND / MBL_LAG)
     int carry_own = 30, carry_ky = 32, carry_minb = 2, carry_rows = 6;  // variant 4 tuning (MBL_OWN / MBL_KY / MBL_MINB)
     int march_rows = 6, march_zm = 64, march_pipe = 1;  // variant 8 tuning (MBL_MROWS / MBL_ZM / MBL_PIPE)
+    int zmarch = 8;  // variant 9: planes per z-chunk (MBL_ZMARCH)
     int sm_count = 148;
     cudaStream_t s_up = nullptr, s_down = nullptr;  // copy streams of the pipelined mbl_step_host
     cudaStream_t s_capture = nullptr;               // CUDA graph capture of step pairs

@@ -824,6 +824,304 @@ __global__ void __launch_bounds__(128, 6) k_qcorr_combine_pair(const double* __r
     qc[2 * n + c] = s.qcz;
 }
 
+// ---------------------------------------------------------------------------
+// Carry step with the z sum completed ON CHIP (variant 9): k_collide_tile marching through the ZM planes of a z-chunk.
+// A thread keeps, for its cell column, the sums plane k-1 has received so far (own + from below) and what plane k-1
+// sends up, in a private shared-memory column; when plane k has been collided, plane k-1 is complete in z.  For a cell
+// whose row is not the first / last of the CTA (complete in y too) and whose 27 sources are all collided cells of the
+// box, the thread finishes the job the combine kernel did -- rho, j, 2rhoE -> QCorr -- and stores the THREE words
+// into the q-correction array of the next step (a second array: this step's is still being read).  Every other cell
+// stores its z-complete sums (5 words: rho, jx, jy, jz, 2rhoE); the first / last plane of a chunk additionally store
+// what they send down / up (4 words), exactly the layout of the plane-pair kernel (ZM = 2).  k_qcorr_combine_march
+// finishes those cells and skips the finished ones.  Carried words per cell at W = 6, ZM = 8: 8 written + 7.5 read
+// instead of 15 + 15.  zpos[k]: 0 interior plane of its chunk, 1 first, 2 last.
+// ---------------------------------------------------------------------------
+constexpr int MARCH_KEEP_SLOTS = 9;  // P: rho, jx, jy, jz, e2 of plane k-1 so far;  U: rho, jx, jy, e2 it sends up
+template <int W>
+__global__ void __launch_bounds__(32 * W, (W <= 4 ? 3 : W <= 8 ? 2 : 1))
+    k_collide_tile_march(const __grid_constant__ CarryPtrs A, const __grid_constant__ MarchOut Q,
+                         const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ flag,
+                         const __grid_constant__ Layout L, const __grid_constant__ Phys P,
+                         const __grid_constant__ CarryPlan C, int ka, int kb, int zm)
+{
+    constexpr int T = 32 * W;
+    extern __shared__ double smem[];
+    double* const sg = smem + threadIdx.x;  // sg[slot * T]
+    const unsigned sg_addr = (unsigned)__cvta_generic_to_shared(sg);
+    double* const sk = smem + NQ * T + threadIdx.x;  // sk[slot * T]: carried sums of plane k-1
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int xc = blockIdx.x;
+    const int y0 = blockIdx.y * W;
+    const int rows = min(W, L.ny - y0);
+    const int i = xc * C.own - C.halo + lane;
+    const bool own = lane >= C.halo && lane < C.halo + C.own && i < L.nx && w < rows;
+    int is = i, j = min(y0 + w, L.ny - 1);
+    if (is < 0) is = L.wrap[0] ? is + L.nx : 0;
+    if (is >= L.nx) is = (L.wrap[0] && is - L.nx < L.nx) ? is - L.nx : L.nx - 1;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned px8 = (unsigned)L.px * 8u, sz8 = (unsigned)L.sz * 8u;
+    unsigned xo[3], yo[3], zo[3];
+    xo[1] = yo[1] = zo[1] = 0u;
+    xo[2] = (L.wrap[0] && is == 0) ? (unsigned)(L.nx - 1) * 8u : 0u - 8u;
+    xo[0] = (L.wrap[0] && is == L.nx - 1) ? 0u - (unsigned)(L.nx - 1) * 8u : 8u;
+    yo[2] = (L.wrap[1] && j == 0) ? (unsigned)(L.ny - 1) * px8 : 0u - px8;
+    yo[0] = (L.wrap[1] && j == L.ny - 1) ? 0u - (unsigned)(L.ny - 1) * px8 : px8;
+    const bool first = w == 0, last = w == rows - 1;
+    // cells this thread may finish itself: complete in y inside the CTA, not on a non-wrapped x / y face of the box
+    const bool xy_inner = own && !first && !last && (L.wrap[0] || (i > 0 && i < L.nx - 1)) &&
+                          (L.wrap[1] || (j > 0 && j < L.ny - 1));
+    const int k0c = ka + (int)blockIdx.z * zm;
+    const int nk = min(zm, kb - k0c);
+    unsigned c_prev = 0u;
+    uint32_t m_prev = 0u;
+    auto ldb = [](const double* base, unsigned off) { return *(const double*)((const char*)base + off); };
+    auto stb = [](double* base, unsigned off, double v) { *(double*)((char*)base + off) = v; };
+#pragma unroll 1
+    for (int kk = 0; kk < nk; ++kk) {
+        const int k = k0c + kk;
+        zo[2] = (L.wrap[2] && k == 0) ? (unsigned)(L.nz - 1) * sz8 : 0u - sz8;
+        zo[0] = (L.wrap[2] && k == L.nz - 1) ? 0u - (unsigned)(L.nz - 1) * sz8 : sz8;
+        const unsigned c = (unsigned)(is + OX) * 8u + (unsigned)(j + GY) * px8 + (unsigned)(k + GZ) * sz8;
+        unsigned cyz[3][3];
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) cyz[b][d] = c + yo[b] + zo[d];
+        static_for<0, NQ>([&](auto qc_) {
+            constexpr int Qd = decltype(qc_)::value;
+            cp_async8(sg_addr + Qd * T * 8, (const char*)A.gin[Qd] + (cyz[ey(Qd) + 1][ez(Qd) + 1] + xo[ex(Qd) + 1]));
+        });
+        const uint32_t m = *(const uint32_t*)((const char*)nbr + (c >> 1));
+        const unsigned fb = flag[c >> 3];
+        const double qxp = ldb(A.qc[0], c + 8u), qxm = ldb(A.qc[0], c - 8u);
+        const double qyp = ldb(A.qc[1], c + px8), qym = ldb(A.qc[1], c - px8);
+        const double qzp = ldb(A.qc[2], c + sz8), qzm = ldb(A.qc[2], c - sz8);
+        double f[NQ];
+        static_for<0, NQ>([&](auto qc_) {
+            constexpr int Qd = decltype(qc_)::value;
+            f[Qd] = ldb(A.fin[Qd], cyz[ey(Qd) + 1][ez(Qd) + 1] + xo[ex(Qd) + 1]);
+        });
+        const bool fluid = m & 1u;
+        if (m != ALL_FLUID) {
+            if (fluid) {
+                static_for<1, NQ>([&](auto qc_) {
+                    constexpr int Qd = decltype(qc_)::value;
+                    if (!((m >> Qd) & 1u)) f[Qd] = ldb(A.fin[opp(Qd)], c);
+                });
+            } else {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) f[q] = -1.0;
+            }
+        }
+        MomF mf = moments_f([&](int q) { return f[q]; });
+        cp_async_wait_all_after(mf.rho);
+        if (m != ALL_FLUID) {
+            if (fluid) {
+                static_for<1, NQ>([&](auto qc_) {
+                    constexpr int Qd = decltype(qc_)::value;
+                    if (!((m >> Qd) & 1u)) sg[Qd * T] = ldb(A.gin[opp(Qd)], c);
+                });
+            } else {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) sg[q * T] = -1.0;
+            }
+        }
+        const MomG mg = moments_g([&](int q) { return sg[q * T]; });
+        const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
+        const double dqx = one_sided_gradient(fb & GRAD_PX, fb & GRAD_MX, (fb & GRAD_PX) ? qxp : 0.0, s.qcx,
+                                              (fb & GRAD_MX) ? qxm : 0.0, P.idx[0]);
+        const double dqy = one_sided_gradient(fb & GRAD_PY, fb & GRAD_MY, (fb & GRAD_PY) ? qyp : 0.0, s.qcy,
+                                              (fb & GRAD_MY) ? qym : 0.0, P.idx[1]);
+        const double dqz = one_sided_gradient(fb & GRAD_PZ, fb & GRAD_MZ, (fb & GRAD_PZ) ? qzp : 0.0, s.qcz,
+                                              (fb & GRAD_MZ) ? qzm : 0.0, P.idx[2]);
+        const Coll cc = collision_coefficients(s, mf, mg, dqx, dqy, dqz, P);
+        const double omega = fluid ? cc.omega : 0.0;
+        double TA[3][2] = {}, TB[3][2] = {}, TC[3][2] = {};
+        double EA[3] = {}, EB[3] = {}, EC[3] = {};
+        static_for<0, NQ>([&](auto qc_) {
+            constexpr int Qd = decltype(qc_)::value;
+            constexpr int d = ez(Qd) + 1;
+            const double v = f[Qd] + omega * (feq_q<Qd>(cc) - f[Qd]);
+            if (own) stb(A.fout[Qd], c, v);
+            double t = v;
+            if constexpr (ex(Qd) == 1) t = __shfl_up_sync(FULL, v, 1);
+            if constexpr (ex(Qd) == -1) t = __shfl_down_sync(FULL, v, 1);
+            double(&Tt)[3][2] = ey(Qd) == -1 ? TA : ey(Qd) == 0 ? TB : TC;
+            Tt[d][0] += t;
+            if constexpr (ex(Qd) == 1) Tt[d][1] += t;
+            if constexpr (ex(Qd) == -1) Tt[d][1] -= t;
+        });
+        static_for<0, NQ>([&](auto qc_) {
+            constexpr int Qd = decltype(qc_)::value;
+            constexpr int d = ez(Qd) + 1;
+            const double gq = sg[Qd * T];
+            const double v = gq + omega * (geq_q<Qd>(cc) - gq);
+            if (own) stb(A.gout[Qd], c, v);
+            double t = v;
+            if constexpr (ex(Qd) == 1) t = __shfl_up_sync(FULL, v, 1);
+            if constexpr (ex(Qd) == -1) t = __shfl_down_sync(FULL, v, 1);
+            double(&E)[3] = ey(Qd) == -1 ? EA : ey(Qd) == 0 ? EB : EC;
+            E[d] += t;
+        });
+        // y exchange through the g slots; the CTA's first / last row send through the edge arrays
+        const unsigned ce = (unsigned)(i + OX) * 8u + (unsigned)blockIdx.y * px8 + (unsigned)(k + GZ) * (unsigned)C.esz8;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (first) {
+                if (own) {
+                    stb(A.edge[3 * d + 0], ce, TA[d][0]);
+                    stb(A.edge[3 * d + 1], ce, TA[d][1]);
+                    stb(A.edge[3 * d + 2], ce, EA[d]);
+                }
+            } else {
+                sg[(3 * d + 0) * T] = TA[d][0];
+                sg[(3 * d + 1) * T] = TA[d][1];
+                sg[(3 * d + 2) * T] = EA[d];
+            }
+            if (last) {
+                if (own) {
+                    stb(A.edge[9 + 3 * d + 0], ce, TC[d][0]);
+                    stb(A.edge[9 + 3 * d + 1], ce, TC[d][1]);
+                    stb(A.edge[9 + 3 * d + 2], ce, EC[d]);
+                }
+            } else {
+                sg[(9 + 3 * d + 0) * T] = TC[d][0];
+                sg[(9 + 3 * d + 1) * T] = TC[d][1];
+                sg[(9 + 3 * d + 2) * T] = EC[d];
+            }
+        }
+        __syncthreads();
+        if (own) {
+            const double* up = sg + 32;   // row j+1: its e_y = -1 terms arrive here
+            const double* dn = sg - 32;   // row j-1: its e_y = +1 terms
+            double r[3], x[3], y[3], e[3];  // per destination plane k-1, k, k+1: rho, jx, jy, e2 (y-complete up to the CTA edges)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const double ua = last ? 0.0 : up[(3 * d + 0) * T], dc = first ? 0.0 : dn[(9 + 3 * d + 0) * T];
+                const double ux = last ? 0.0 : up[(3 * d + 1) * T], dx = first ? 0.0 : dn[(9 + 3 * d + 1) * T];
+                const double ue = last ? 0.0 : up[(3 * d + 2) * T], de = first ? 0.0 : dn[(9 + 3 * d + 2) * T];
+                r[d] = TB[d][0] + ua + dc;
+                x[d] = TB[d][1] + ux + dx;
+                y[d] = dc - ua;
+                e[d] = EB[d] + ue + de;
+            }
+            if (kk == 0) {
+                // first plane of the chunk: what it sends down leaves now (another chunk's last plane waits for it)
+                stb(A.part[5], c, r[0]);
+                stb(A.part[6], c, x[0]);
+                stb(A.part[7], c, y[0]);
+                stb(A.part[8], c, e[0]);
+                sk[0 * T] = r[1], sk[1 * T] = x[1], sk[2 * T] = y[1], sk[3 * T] = 0.0, sk[4 * T] = e[1];
+            } else {
+                // plane k-1 is complete in z: its sums so far + this plane's e_z = -1 terms
+                const double Sr = sk[0 * T] + r[0], Sx = sk[1 * T] + x[0], Sy = sk[2 * T] + y[0];
+                const double Sz = sk[3 * T] - r[0], Se = sk[4 * T] + e[0];
+                const int kp = k - 1;
+                const bool z_inner = kk >= 2 && (L.wrap[2] || (kp > 0 && kp < L.nz - 1));
+                if (xy_inner && z_inner && m_prev == ALL_FLUID) {
+                    const Prim sp = primitives(Sr, Sx, Sy, Sz, Se, P);
+                    stb(Q.qcn[0], c_prev, sp.qcx);
+                    stb(Q.qcn[1], c_prev, sp.qcy);
+                    stb(Q.qcn[2], c_prev, sp.qcz);
+                } else {
+                    stb(A.part[0], c_prev, Sr);
+                    stb(A.part[1], c_prev, Sx);
+                    stb(A.part[2], c_prev, Sy);
+                    stb(A.part[3], c_prev, Sz);
+                    stb(A.part[4], c_prev, Se);
+                }
+                // plane k so far: what plane k-1 sent up + its own e_z = 0 terms
+                const double ur = sk[5 * T];
+                sk[0 * T] = ur + r[1], sk[1 * T] = sk[6 * T] + x[1], sk[2 * T] = sk[7 * T] + y[1], sk[3 * T] = ur,
+                       sk[4 * T] = sk[8 * T] + e[1];
+            }
+            sk[5 * T] = r[2], sk[6 * T] = x[2], sk[7 * T] = y[2], sk[8 * T] = e[2];
+            if (kk == nk - 1) {
+                // last plane of the chunk: incomplete (the next chunk's first plane sends down); its sums so far and
+                // what it sends up leave
+                stb(A.part[0], c, sk[0 * T]);
+                stb(A.part[1], c, sk[1 * T]);
+                stb(A.part[2], c, sk[2 * T]);
+                stb(A.part[3], c, sk[3 * T]);
+                stb(A.part[4], c, sk[4 * T]);
+                if (kk > 0) {  // (a one-plane chunk keeps its send-down words; the launcher never makes one)
+                    stb(A.part[5], c, r[2]);
+                    stb(A.part[6], c, x[2]);
+                    stb(A.part[7], c, y[2]);
+                    stb(A.part[8], c, e[2]);
+                }
+            }
+        }
+        c_prev = c;
+        m_prev = m;
+        __syncthreads();  // the exchange slots are the next plane's g slots
+    }
+}
+
+// finishes what k_collide_tile_march left: cells on the first / last row of a CTA, on the first / last plane of a
+// chunk, next to a non-wrapped face, or with a solid source (those are pulled, as in k_qcorr)
+__global__ void __launch_bounds__(128, 6) k_qcorr_combine_march(const double* __restrict__ fin, const double* __restrict__ gin,
+                                                                const uint32_t* __restrict__ nbr, const double* __restrict__ part,
+                                                                const double* __restrict__ edge, const signed char* __restrict__ zpos,
+                                                                int W, long long esz, double* __restrict__ qc,
+                                                                const __grid_constant__ Layout L, const __grid_constant__ Phys P, int k0)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.nx) return;
+    const int j = blockIdx.y, k = blockIdx.z + k0;
+    const long long c = L.cell(i, j, k);
+    const long long n = L.sq;
+    const uint32_t m = nbr[c];
+    if (!(m & 1u)) return;
+    const bool inner = (L.wrap[0] || (i > 0 && i < L.nx - 1)) && (L.wrap[1] || (j > 0 && j < L.ny - 1)) &&
+                       (L.wrap[2] || (k > 0 && k < L.nz - 1)) && k >= 0 && k < L.nz;
+    if (!(inner && m == ALL_FLUID)) {
+        qcorr_cell<true>(fin, gin, nbr, qc, L, P, i, j, k);
+        return;
+    }
+    const int zp = zpos[k + GZ];
+    const int jr = j / W, w = j - jr * W, nyr = (L.ny + W - 1) / W;
+    const int rows = min(W, L.ny - jr * W);
+    const bool edge_row = w == 0 || w == rows - 1;
+    if (zp == 0 && !edge_row) return;  // finished by the collide kernel
+    const int km = k == 0 ? L.nz - 1 : k - 1, kp = k == L.nz - 1 ? 0 : k + 1;
+    double rho = part[0 * n + c], jx = part[1 * n + c], jy = part[2 * n + c], jz = part[3 * n + c], e2 = part[4 * n + c];
+    if (zp != 0) {
+        // first plane: the plane below (another chunk's last) sent up; last plane: the plane above sent down
+        const long long co = L.cell(i, j, zp == 1 ? km : kp);
+        const double ro = part[5 * n + co];
+        rho += ro;
+        jx += part[6 * n + co];
+        jy += part[7 * n + co];
+        jz += zp == 1 ? ro : -ro;
+        e2 += part[8 * n + co];
+    }
+    if (edge_row) {
+        const long long en = esz * (L.nz + 2 * GZ);
+        auto add_edge = [&](int side, int jrs, double sgn) {
+            const long long e0 = (long long)(i + OX) + (long long)jrs * L.px;
+            const double am = edge[(side * 9 + 6) * en + e0 + (long long)(km + GZ) * esz];
+            const double a0 = edge[(side * 9 + 3) * en + e0 + (long long)(k + GZ) * esz];
+            const double ap = edge[(side * 9 + 0) * en + e0 + (long long)(kp + GZ) * esz];
+            rho += am + a0 + ap;
+            jz += am - ap;
+            jy += sgn * (am + a0 + ap);
+            jx += edge[(side * 9 + 7) * en + e0 + (long long)(km + GZ) * esz] +
+                  edge[(side * 9 + 4) * en + e0 + (long long)(k + GZ) * esz] +
+                  edge[(side * 9 + 1) * en + e0 + (long long)(kp + GZ) * esz];
+            e2 += edge[(side * 9 + 8) * en + e0 + (long long)(km + GZ) * esz] +
+                  edge[(side * 9 + 5) * en + e0 + (long long)(k + GZ) * esz] +
+                  edge[(side * 9 + 2) * en + e0 + (long long)(kp + GZ) * esz];
+        };
+        if (w == 0) add_edge(1, jr == 0 ? nyr - 1 : jr - 1, 1.0);
+        if (w == rows - 1) add_edge(0, jr == nyr - 1 ? 0 : jr + 1, -1.0);
+    }
+    const Prim s = primitives(rho, jx, jy, jz, e2, P);
+    qc[c] = s.qcx;
+    qc[n + c] = s.qcy;
+    qc[2 * n + c] = s.qcz;
+}
+
 // q-corrections of the post-stream state from the carried plane sums (interior cells) or by pulling the
 // populations (everything k_collide_carry could not serve)
 __global__ void __launch_bounds__(128, 6) k_qcorr_combine(const double* __restrict__ fin, const double* __restrict__ gin,
@@ -1673,6 +1971,54 @@ int launch_collide_tile_pair(const Layout& L, const Phys& P, const CarryPlan& C,
     }
     const dim3 grid(C.nxc, (L.ny + W - 1) / W, (kb - ka) / 2);
     k_collide_tile_pair<6><<<grid, 32 * W, sm, st>>>(A, nbr, flag, L, P, Ce, ka);
+    return 1;
+}
+
+// variant 9.  Returns the number of kernels, -1 if a component exceeds 4 GB, -2 if a chunk would hold one plane
+int launch_collide_tile_march(const Layout& L, const Phys& P, const CarryPlan& C, int zm, const double* fin, const double* gin,
+                              double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag, const double* qc,
+                              double* qc_next, double* part, double* edge, cudaStream_t st, int ka, int kb)
+{
+    if (L.sq * 8 >= (1LL << 32)) return -1;
+    constexpr int W = 6;
+    if (kb <= ka) ka = 0, kb = L.nz;
+    if (zm < 2) zm = 2;
+    if ((kb - ka) % zm == 1 || kb - ka < 2) return -2;  // a one-plane chunk would need both send words
+    CarryPtrs A;
+    MarchOut Q;
+    for (int q = 0; q < NQ; ++q) {
+        A.fin[q] = fin + (long long)q * L.sq;
+        A.gin[q] = gin + (long long)q * L.sq;
+        A.fout[q] = fout + (long long)q * L.sq;
+        A.gout[q] = gout + (long long)q * L.sq;
+    }
+    for (int d = 0; d < 3; ++d) A.qc[d] = qc + (long long)d * L.sq, Q.qcn[d] = qc_next + (long long)d * L.sq;
+    for (int w = 0; w < CARRY_WORDS; ++w) A.part[w] = part + (long long)w * L.sq;
+    CarryPlan Ce = C;
+    const long long esz = carry_edge_plane(L, W);
+    Ce.esz8 = (unsigned)(esz * 8);
+    for (int e = 0; e < CARRY_EDGE_WORDS; ++e) A.edge[e] = edge + (long long)e * esz * (L.nz + 2 * GZ);
+    const size_t sm = (size_t)(NQ + MARCH_KEEP_SLOTS) * 32 * W * 8;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_collide_tile_march<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        attr_done = true;
+    }
+    const dim3 grid(C.nxc, (L.ny + W - 1) / W, (kb - ka + zm - 1) / zm);
+    k_collide_tile_march<6><<<grid, 32 * W, sm, st>>>(A, Q, nbr, flag, L, P, Ce, ka, kb, zm);
+    return 1;
+}
+
+int launch_qcorr_combine_march(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr,
+                               const double* part, const double* edge, const signed char* zpos, double* qc, cudaStream_t st,
+                               int ka, int kb)
+{
+    const int bx = block_x(L);
+    int k0 = (L.lo[2] > L.dlo[2]) ? -1 : 0;
+    int k1 = (L.lo[2] + L.nz - 1 < L.dhi[2]) ? L.nz : L.nz - 1;
+    if (kb > ka) k0 = ka, k1 = kb - 1;
+    dim3 grid((L.nx + bx - 1) / bx, L.ny, k1 - k0 + 1);
+    k_qcorr_combine_march<<<grid, bx, 0, st>>>(fin, gin, nbr, part, edge, zpos, 6, carry_edge_plane(L, 6), qc, L, P, k0);
     return 1;
 }
 

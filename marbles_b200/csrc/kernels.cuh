@@ -87,6 +87,10 @@ struct CarryPtrs {
     double* part[CARRY_WORDS];
     double* edge[CARRY_EDGE_WORDS];
 };
+// q-correction array of the NEXT step (k_collide_tile_march finishes most cells itself)
+struct MarchOut {
+    double* qcn[3];
+};
 CarryPlan make_carry_plan(const Layout& L, int own, int ky);
 int launch_collide_carry(const Layout& L, const Phys& P, const CarryPlan& C, int min_blocks, const double* fin,
                          const double* gin, double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag,
@@ -106,6 +110,15 @@ int launch_collide_tile_pair(const Layout& L, const Phys& P, const CarryPlan& C,
                              double* part, double* edge, cudaStream_t st, int ka = 0, int kb = 0);
 int launch_qcorr_combine_pair(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr,
                               const double* part, const double* edge, double* qc, cudaStream_t st, int ka = 0, int kb = 0);
+// variant 9: the tile carry step marching through z-chunks of zm planes, z sums completed on chip, QCorr of the next step
+// written by the collide kernel for the cells that are complete (kernels.cu); zpos[k + GZ]: 0 interior, 1 first, 2 last
+// plane of its chunk
+int launch_collide_tile_march(const Layout& L, const Phys& P, const CarryPlan& C, int zm, const double* fin, const double* gin,
+                              double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag, const double* qc,
+                              double* qc_next, double* part, double* edge, cudaStream_t st, int ka = 0, int kb = 0);
+int launch_qcorr_combine_march(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr,
+                               const double* part, const double* edge, const signed char* zpos, double* qc, cudaStream_t st,
+                               int ka = 0, int kb = 0);
 long long carry_edge_plane(const Layout& L, int rows);
 int carry_tile_rows(int rows);  // supported rows per CTA: 4, 6 (default), 8, 12
 // edge / edge_rows: the edge arrays k_collide_tile wrote (nullptr after k_collide_carry)

@@ -27,13 +27,17 @@ CARRY_ENV = {
     "tile-4rows": (5, {"MBL_ROWS": "4"}),
     "lean": (6, {"MBL_MINB": "4"}),
     "pair": (7, {}),
+    # variant 9: tile carry step marching through z-chunks (z sums completed on chip, QCorr finished by the collide kernel)
+    "zmarch": (9, {}),
+    "zmarch-zm3": (9, {"MBL_ZMARCH": "3"}),
+    "zmarch-zm2": (9, {"MBL_ZMARCH": "2"}),
     # variant 8: the one-kernel march step (march.cu): default tuning, small CTAs with short ragged marches, and
     # without the early pull of the next plane
     "march": (8, {}),
     "march-4rows-zm3": (8, {"MBL_MROWS": "4", "MBL_ZM": "3"}),
     "march-nopipe-zm5": (8, {"MBL_PIPE": "0", "MBL_ZM": "5"}),
 }
-TUNING_VARS = ("MBL_KY", "MBL_OWN", "MBL_MINB", "MBL_ROWS", "MBL_MROWS", "MBL_ZM", "MBL_PIPE")
+TUNING_VARS = ("MBL_KY", "MBL_OWN", "MBL_MINB", "MBL_ROWS", "MBL_MROWS", "MBL_ZM", "MBL_PIPE", "MBL_ZMARCH")
 # variants 1-4 are round-1 experiments, compiled only with MBL_EXPERIMENTS=1
 import os as _os
 EXPERIMENTS = _os.environ.get("MBL_EXPERIMENTS") == "1"
@@ -66,7 +70,7 @@ def new_lbm(deck_text, is_fluid=None, overrides=None, variant=None):
 
 # fused: mbl_step with the persistent TMA kernel (variant 1, the default), its two job types as two
 # launches (2), or the two plain kernels (0); unfused: the reference-granular operator sequence
-@pytest.mark.parametrize("fused", with_experiments([0, "tile", "tile-6rows-own28", "lean", "pair", None],
+@pytest.mark.parametrize("fused", with_experiments([0, "tile", "tile-6rows-own28", "lean", "pair", "zmarch", "zmarch-zm3", None],
                                                    [1, 2, 3, "carry", "carry-ky5-own28", "march", "march-4rows-zm3", "march-nopipe-zm5"]),
                          ids=lambda v: {0: "twopass-plain", 1: "fused-tma", 2: "twopass-tma", 3: "fused-plain",
                                         None: "unfused"}.get(v, str(v)))
@@ -123,7 +127,7 @@ def test_geometry_matches_reference_is_fluid():
         assert np.array_equal(a, z["is_fluid"].astype(np.int32)), case
 
 
-@pytest.mark.parametrize("variant", with_experiments([0, "tile", "tile-6rows-own28", "tile-12rows", "tile-4rows", "pair"],
+@pytest.mark.parametrize("variant", with_experiments([0, "tile", "tile-6rows-own28", "tile-12rows", "tile-4rows", "pair", "zmarch", "zmarch-zm3", "zmarch-zm2"],
                                                      [1, 3, "carry", "carry-ky5-own28", "carry-ky1", "march", "march-4rows-zm3",
                                                       "march-nopipe-zm5"]),
                          ids=lambda v: {0: "twopass-plain", 1: "fused-tma", 3: "fused-plain"}.get(v, str(v)))
@@ -176,7 +180,7 @@ def test_eb_forces_and_vorticity_vs_oracle(oracle_mod):
     lbm.close()
 
 
-@pytest.mark.parametrize("variant", with_experiments([0, "tile", "pair"], ["carry", "march"]),
+@pytest.mark.parametrize("variant", with_experiments([0, "tile", "pair", "zmarch"], ["carry", "march"]),
                          ids=lambda v: "twopass-plain" if v == 0 else str(v))
 def test_tg64_vs_oracle_and_conservation(oracle_mod, variant):
     """BASELINE config 1 (TG 64^3): 3 steps against the oracle, then size-independent properties"""
@@ -204,7 +208,7 @@ def test_tg64_vs_oracle_and_conservation(oracle_mod, variant):
     lbm.close()
 
 
-@pytest.mark.parametrize("variant", with_experiments([0, "tile"], ["carry", "march"]),
+@pytest.mark.parametrize("variant", with_experiments([0, "tile", "zmarch"], ["carry", "march"]),
                          ids=lambda v: "twopass-plain" if v == 0 else str(v))
 def test_full_size_conservation_256(variant):
     """periodic 256^3 (largest size the test box does in seconds): mass/energy conservation of
@@ -224,7 +228,7 @@ def test_full_size_conservation_256(variant):
 
 @pytest.mark.parametrize("case,nz,world", [("tg12", 12, 2), ("tg12", 13, 3), ("sod48", 8, 2), ("chcyl", None, 2),
                                            ("pressure", None, 2)])
-@pytest.mark.parametrize("variant", with_experiments([0, "tile-6rows-own28"], ["carry-ky5-own28", "march-4rows-zm3"]),
+@pytest.mark.parametrize("variant", with_experiments([0, "tile-6rows-own28", "zmarch-zm3"], ["carry-ky5-own28", "march-4rows-zm3"]),
                          ids=lambda v: "twopass-plain" if v == 0 else str(v))
 def test_two_slabs_match_single_box(case, nz, world, variant):
     """the multi-rank scheme (z-slabs, ONE exchange of two ghost planes per step, q-correction of the first
@@ -438,9 +442,11 @@ def test_full_size_conservation_512():
 
 
 @pytest.mark.parametrize("case", ["chcyl", "tg12", "sod48"])
-@pytest.mark.parametrize("variant", [None, 0], ids=["default", "twopass"])
+@pytest.mark.parametrize("variant", [None, 0, "tile"], ids=["default", "twopass", "tile"])
 def test_graph_replay_is_bit_identical(case, variant):
-    """mbl_step replays pairs of steps as one CUDA graph on small boxes: same kernels, same order"""
+    """mbl_step replays pairs of steps as one CUDA graph on small boxes: same kernels, same order.  A step with
+    macrodata between replays moves the buffer parity without swapping the two QCorr arrays of the default
+    (z-march) step, so the graph must be re-captured for the state it is replayed on."""
     import os
     z, deck_text, _ = load_golden(case)
     fl = z["is_fluid"].astype(np.int32)
@@ -459,12 +465,20 @@ def test_graph_replay_is_bit_identical(case, variant):
     assert np.array_equal(a.get_f(), b.get_f()) and np.array_equal(a.get_g(), b.get_g())
     assert np.array_equal(a.get_macrodata(), b.get_macrodata())
     assert a.launches == b.launches
+    for n in (7, 1, 6, 9):
+        a.step(n)
+        b.step(n)
+        a.step(1, want_macrodata=True)
+        b.step(1, want_macrodata=True)
+    assert np.array_equal(a.get_f(), b.get_f()) and np.array_equal(a.get_g(), b.get_g())
+    assert np.array_equal(a.get_macrodata(), b.get_macrodata())
+    assert a.launches == b.launches
     a.close()
     b.close()
 
 
 @pytest.mark.parametrize("case,n_cell", [("tg12", "67 45 13"), ("tg12", "31 7 9"), ("sod48", "75 3 5"), ("sod48", "130 2 2")])
-@pytest.mark.parametrize("variant", with_experiments([None, 0, "pair"], ["carry", "march", "march-4rows-zm3"]),
+@pytest.mark.parametrize("variant", with_experiments([None, 0, "tile", "pair", "zmarch-zm3"], ["carry", "march", "march-4rows-zm3"]),
                          ids=lambda v: {None: "default", 0: "twopass"}.get(v, str(v)))
 def test_odd_box_sizes_vs_oracle(oracle_mod, case, n_cell, variant):
     """box sizes that are no multiple of the warp strip (30 cells), the CTA height (6 rows) or the march length"""
@@ -526,7 +540,7 @@ def test_slab_vorticity_matches_single_box(case, nz, world):
     single.close()
 
 
-@pytest.mark.parametrize("variant", with_experiments([None], ["march"]), ids=lambda v: "default" if v is None else str(v))
+@pytest.mark.parametrize("variant", with_experiments([None, "tile"], ["march"]), ids=lambda v: "default" if v is None else str(v))
 @pytest.mark.parametrize("n", [256, 512])
 def test_full_size_values_tiled_tg_vs_oracle(oracle_mod, n, variant):
     """Value-level pin of the benchmarked size (BASELINE config 3, 512^3; and 256^3): the box is initialised with a
