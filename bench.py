@@ -379,7 +379,7 @@ def main():
     kname = {0: "k_collide_lean (pull + collide)", 1: "k_fused (q-correction + collide jobs)", 2: "k_fused (collide jobs)",
              3: "k_fused_plain (q-correction + collide jobs)", 4: "k_collide_carry", 5: "k_collide_tile", 6: "k_collide_lean", 7: "k_collide_tile_pair",
              8: "k_march (pull + q-correction + collide, one kernel)",
-             9: "k_collide_tile_march"}[lbm.variant]
+             9: "k_collide_tile_march", 10: "k_collide_tile_march (pipelined)"}[lbm.variant]
     vname = {0: "two kernels (k_qcorr, k_collide_lean)", 1: "one persistent TMA-pipelined kernel per step",
              2: "persistent TMA kernel, two launches (q-correction, collide)",
              3: "one persistent kernel per step, plain loads",
@@ -390,12 +390,13 @@ def main():
              7: "tile carry step with plane pairs: k_qcorr_combine_pair + k_collide_tile_pair",
              8: "march step: one kernel per step, z-marching CTAs, q-corrections recomputed on a one-cell halo",
              9: "tile carry step marching through z-chunks: k_qcorr_combine_march + k_collide_tile_march (z sums completed "
-                "on chip, QCorr of most cells finished by the collide kernel)"}[lbm.variant]
+                "on chip, QCorr of most cells finished by the collide kernel)",
+             10: "z-march tile carry step with plane k+1 pulled into shared memory while plane k is collided"}[lbm.variant]
     achieved = BYTES_PER_CELL * lbm.ncells / (collide_ms * 1e-3) / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            tkey = {0: "k_collide_lean", 6: "k_collide_lean", 5: "k_collide_tile", 4: "k_collide_carry", 7: "k_collide_tile_pair", 8: "k_march", 9: "k_collide_tile_march"}.get(lbm.variant)
+            tkey = {0: "k_collide_lean", 6: "k_collide_lean", 5: "k_collide_tile", 4: "k_collide_carry", 7: "k_collide_tile_pair", 8: "k_march", 9: "k_collide_tile_march", 10: "k_collide_tile_march_pipe"}.get(lbm.variant)
             traffic = json.load(fh).get("dram_bytes_per_launch_512", {}).get(tkey) if n == 512 else None
             if args.workload != "tg" or world > 1 and args.scaling == "strong":
                 traffic = None

@@ -216,6 +216,12 @@ int mbl_average_down(mbl_ctx* ctx, int crse_lev, int ng);
  * new is_fluid (mbl_box_set_is_fluid) and calls mbl_fill_f_inside_eb (zero in solid cells + FillBoundary,
  * Source/LBM.cpp:1278-1298, 1347-1348). */
 int mbl_level_regrid(mbl_ctx* ctx, int lev, int nboxes, const int* lo, const int* hi);
+/* LBM::MakeNewLevelFromCoarse (Source/LBM.cpp:1088-1144): a level lev >= 1 that did not exist appears in a regrid.
+ * Every cell of the new boxes (valid and ghost, inside the periodically grown domain) gets CellConservativeLinear
+ * values from level lev-1 (FillPatchOps::fillpatch_from_coarse, Source/FillPatchOps.H:164-181), then BCFill.  The
+ * caller passes is_fluid afterwards (no fill_f_inside_eb here: the reference does not call it for a new level).
+ * LBM::ClearLevel (Source/LBM.cpp:1367-1380), a level that vanishes, is mbl_level_clear. */
+int mbl_level_make_from_coarse(mbl_ctx* ctx, int lev, const mbl_level_geom* geom, int nboxes, const int* lo, const int* hi);
 int mbl_fill_f_inside_eb(mbl_ctx* ctx, int lev);
 
 /* fused fast path: one coarse step of a single-level run =

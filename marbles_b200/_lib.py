@@ -97,6 +97,7 @@ SYMBOLS = {
     "mbl_box_download_macrodata": (C.c_int, [_P, C.c_int, C.c_int, _D, C.c_int, C.c_int]),
     "mbl_average_down": (C.c_int, [_P, C.c_int, C.c_int]),
     "mbl_level_regrid": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mbl_level_make_from_coarse": (C.c_int, [_P, C.c_int, C.POINTER(LevelGeom), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mbl_fill_f_inside_eb": (C.c_int, [_P, C.c_int]),
     "mbl_launch_count": (C.c_int64, [_P]),
     "mbl_set_variant": (C.c_int, [_P, C.c_int]),

@@ -10,6 +10,7 @@ reference-granular entry points in the reference's order:
     LBM::evolve (one step)    Source/LBM.cpp:416-422   -> fillpatch(0); time_step(0); post_time_step
     LBM::time_step            Source/LBM.cpp:452-521   -> fillpatch(lev+1); 2 x (physbc(lev+1); time_step(lev+1)); advance
     LBM::advance              Source/LBM.cpp:523-544   -> stream; average_down_to(lev, 1 ghost ring); collide
+    LBM::MakeNewLevelFromCoarse / ClearLevel  Source/LBM.cpp:1088-1144, 1367-1380 -> `make_level_from_coarse`, `clear_level`
     LBM::RemakeLevel          Source/LBM.cpp:1302-1364 -> `regrid_level`: mbl_level_regrid with the box list AmrCore::regrid
                                                           produced (old level + coarse interpolation into new FABs),
                                                           new is_fluid, mbl_fill_f_inside_eb
@@ -216,6 +217,29 @@ class AmrLBM:
         self.boxes[lev] = boxes
         self._set_level_is_fluid(lev, is_fluid_dense)
         check(self.lib.mbl_fill_f_inside_eb(self.ctx, lev))
+
+    def make_level_from_coarse(self, lev: int, boxes, is_fluid_dense=None):
+        """LBM::MakeNewLevelFromCoarse (Source/LBM.cpp:1088-1144): level lev = finest + 1 appears in a regrid; every cell
+        of its grown boxes is interpolated from level lev-1 (mbl_level_make_from_coarse), then is_fluid is set."""
+        assert lev == self.finest + 1, "a new level appears above the finest one"
+        boxes = [(tuple(int(v) for v in lo), tuple(int(v) for v in hi)) for lo, hi in boxes]
+        g = self.level_geom(lev)
+        nb = len(boxes)
+        lo = (C.c_int * (3 * nb))(*[v for b in boxes for v in b[0]])
+        hi = (C.c_int * (3 * nb))(*[v for b in boxes for v in b[1]])
+        check(self.lib.mbl_level_make_from_coarse(self.ctx, lev, C.byref(g), nb, lo, hi))
+        self.boxes.append(boxes)
+        self.n.append([self.inp.n_cell[d] * REF_RATIO ** lev for d in range(3)])
+        self.dt.append(g.dt)
+        self._set_level_is_fluid(lev, is_fluid_dense)
+
+    def clear_level(self, lev: int):
+        """LBM::ClearLevel (Source/LBM.cpp:1367-1380): the finest level vanishes in a regrid"""
+        assert lev == self.finest and lev >= 1
+        check(self.lib.mbl_level_clear(self.ctx, lev))
+        self.boxes.pop()
+        self.n.pop()
+        self.dt.pop()
 
     # ------------------------------------------------------------------ access
     def box_shape(self, lev: int, ib: int, ncomp: int, ng: int):

@@ -842,6 +842,39 @@ int mbl_level_regrid(mbl_ctx* ctx, int lev, int nboxes, const int* lo, const int
     return patch_physbc(ctx, lev, 0.0);
 }
 
+// LBM::MakeNewLevelFromCoarse (LBM.cpp:1088-1144): f, g of a level that did not exist, every cell of the grown boxes
+// inside the periodically grown domain interpolated from level lev-1 (FillPatchOps::fillpatch_from_coarse =
+// InterpFromCoarseLevel), then the fine BCFill.  No K6 pre-pass, no zeroing of solid cells, no FillBoundary.
+int mbl_level_make_from_coarse(mbl_ctx* ctx, int lev, const mbl_level_geom* geom, int nboxes, const int* lo, const int* hi)
+{
+    if (!ctx || !geom || !lo || !hi) return fail("null argument");
+    if (lev < 1 || lev >= MAX_LEVELS || !ctx->plev[lev - 1])
+        return fail("mbl_level_make_from_coarse: level %d must be a multi-box level", lev - 1);
+    if (ctx->plev[lev] || ctx->lev[lev].defined)
+        return fail("mbl_level_make_from_coarse: level %d exists (mbl_level_regrid re-makes it)", lev);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (mbl_level_define_boxes(ctx, lev, geom, nboxes, lo, hi)) return 1;
+    PatchLevel* L = ctx->plev[lev];
+    PatchLevel& Cl = *ctx->plev[lev - 1];
+    Inter tmp;
+    int rc = build_interp(tmp, L->boxes, L->G, lev, Cl, std::vector<HBox>());
+    if (!rc) {
+        for (int arr = PA_F; arr <= PA_G; ++arr)
+            ctx->launches += launch_patch_copy(tmp.cpatch.d, 0, Cl.set.d, Cl.cur, tmp.c2p.d, tmp.c2p.n, arr, arr, NQ,
+                                               tmp.c2p.max_cells, st);
+        ctx->launches += launch_patch_interp(L->set.d, L->cur, tmp.cpatch.d, tmp.d_regs, tmp.nregs, tmp.reg_max, st);
+    }
+    cudaStreamSynchronize(st);
+    tmp.free_all();
+    if (rc) {
+        patch_clear(ctx, lev);
+        return 1;
+    }
+    CU(cudaGetLastError());
+    return patch_physbc(ctx, lev, 0.0);
+}
+
 // fill_f_inside_eb (LBM.cpp:1278-1298) + the FillBoundary that follows it in RemakeLevel (LBM.cpp:1347-1348)
 int mbl_fill_f_inside_eb(mbl_ctx* ctx, int lev)
 {

@@ -102,7 +102,9 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
     int variant = ctx->variant;
     if (variant == 7 && ((lv.L.nz & 1) || carry_tile_rows(ctx->carry_rows) != 6)) variant = 5;  // pairs need an even nz
     if (variant == 9 && (lv.L.nz < 4 || carry_tile_rows(ctx->carry_rows) != 6)) variant = 5;    // z-march needs chunks of >= 2 planes
-    if ((variant == 4 || variant == 5 || variant == 7 || variant == 8 || variant == 9) && lv.L.sq * 8 >= (1LL << 32)) variant = 0;
+    if (variant == 10 && lv.L.nz < 4) variant = 5;
+    const bool zmarch = variant == 9 || variant == 10;
+    if ((variant == 4 || variant == 5 || variant == 7 || variant == 8 || zmarch) && lv.L.sq * 8 >= (1LL << 32)) variant = 0;
 #ifdef MBL_EXPERIMENTS
     if (variant == 8 && !macro) {
         // march step: ONE kernel, no q-correction pass and no carried sums (experiments/march.cu)
@@ -114,14 +116,14 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
         lv.carry_valid = false;
     } else
 #endif
-    if (variant == 5 || variant == 7 || variant == 4 || variant == 9) {
+    if (variant == 5 || variant == 7 || variant == 4 || variant == 9 || variant == 10) {
         // carry step: q-corrections from the partial sums the previous collide left behind (first step, or after
         // anything else wrote the lattice: the full q-correction pass)
         if (!lv.part) CU(cudaMalloc(&lv.part, (size_t)CARRY_WORDS * lv.L.sq * sizeof(double)));
-        const int W = carry_tile_rows(ctx->carry_rows);
+        const int W = variant == 10 ? (ctx->carry_rows == 4 ? 4 : 8) : carry_tile_rows(ctx->carry_rows);
         if (variant != 4 && !lv.edge)
             CU(cudaMalloc(&lv.edge, (size_t)CARRY_EDGE_WORDS * carry_edge_plane(lv.L, 4) * (lv.L.nz + 2 * GZ) * sizeof(double)));
-        if (variant == 9) {
+        if (variant == 9 || variant == 10) {
             if (!lv.qc2) {
                 CU(cudaMalloc(&lv.qc2, (size_t)3 * lv.L.sq * sizeof(double)));
                 CU(cudaMemsetAsync(lv.qc2, 0, (size_t)3 * lv.L.sq * sizeof(double), st));
@@ -129,8 +131,8 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
             if (!lv.zpos) CU(cudaMalloc(&lv.zpos, (size_t)(lv.L.nz + 2 * GZ)));
         }
         if (lv.carry_valid && lv.part_pair == 2)
-            ctx->launches += launch_qcorr_combine_march(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.part, lv.edge, lv.zpos,
-                                                        lv.p.qc, st);
+            ctx->launches += launch_qcorr_combine_march(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.part, lv.edge, lv.edge_rows,
+                                                        lv.zpos, lv.p.qc, st);
         else if (lv.carry_valid && lv.part_pair)
             ctx->launches += launch_qcorr_combine_pair(Lk, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.part, lv.edge, lv.p.qc, st);
         else if (lv.carry_valid)
@@ -146,7 +148,7 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
         } else {
             const CarryPlan C = make_carry_plan(Lk, ctx->carry_own, ctx->carry_ky);
             int nl;
-            if (variant == 9) {
+            if (variant == 9 || variant == 10) {
                 // chunks of zm planes, none of a single plane; zpos says where each plane sits in its chunk
                 int zm = ctx->zmarch > 1 ? ctx->zmarch : 8;
                 while (lv.L.nz % zm == 1) ++zm;
@@ -160,8 +162,8 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
                     CU(cudaStreamSynchronize(st));
                     lv.zpos_zm = zm;
                 }
-                nl = launch_collide_tile_march(Lk, lv.P, C, zm, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
-                                               lv.p.qc, lv.qc2, lv.part, lv.edge, st);
+                nl = launch_collide_tile_march(Lk, lv.P, C, W, variant == 10, zm, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b],
+                                               lv.p.nbr, lv.p.flag, lv.p.qc, lv.qc2, lv.part, lv.edge, st);
                 if (nl > 0) std::swap(lv.p.qc, lv.qc2);  // the cells the kernel finished are in what is now lv.p.qc
             } else if (variant == 7) {
                 nl = launch_collide_tile_pair(Lk, lv.P, C, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr, lv.p.flag,
@@ -178,7 +180,7 @@ int step_local(mbl_ctx* ctx, Level& lv, double /*time*/, int want_macro)
                                          lv.p.qc, lv.part, lv.edge, st);
             }
             lv.edge_rows = variant == 4 ? 0 : W;
-            lv.part_pair = variant == 7 ? 1 : variant == 9 ? 2 : 0;
+            lv.part_pair = variant == 7 ? 1 : (variant == 9 || variant == 10) ? 2 : 0;
             if (nl < 0) return fail("carry step: launch failed (%d)", nl);
             ctx->launches += nl;
             lv.carry_valid = true;
@@ -818,7 +820,7 @@ int mbl_step_split(mbl_ctx* ctx, int lev, int part)
     };
     // variant 5 keeps carrying through the split: q-corrections from the previous step's partial sums
     // (k_qcorr_combine; planes next to a ghost plane are pulled as before), collide by k_collide_tile
-    const bool tile = (ctx->variant == 5 || ctx->variant == 7 || ctx->variant == 9) && L.sq * 8 < (1LL << 32);
+    const bool tile = (ctx->variant == 5 || ctx->variant == 7 || ctx->variant == 9 || ctx->variant == 10) && L.sq * 8 < (1LL << 32);
     const int W = carry_tile_rows(ctx->carry_rows);
     if (tile) {
         if (!lv.part) CU(cudaMalloc(&lv.part, (size_t)CARRY_WORDS * L.sq * sizeof(double)));
@@ -1153,9 +1155,9 @@ int mbl_get_variant(mbl_ctx* ctx) { return ctx ? ctx->variant : -1; }
 int mbl_set_variant(mbl_ctx* ctx, int variant)
 {
     if (!ctx) return fail("null context");
-    if (variant < 0 || variant > 9) return fail("variant %d is not available", variant);
+    if (variant < 0 || variant > 10) return fail("variant %d is not available", variant);
 #ifndef MBL_EXPERIMENTS
-    if ((variant >= 1 && variant <= 4) || variant == 8)
+    if ((variant >= 1 && variant <= 4) || variant == 8 || variant == 10)
         return fail("step variant %d is an experiment: rebuild the library with MBL_EXPERIMENTS=1", variant);
 #endif
     ctx->variant = variant;

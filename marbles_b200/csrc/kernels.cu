@@ -837,8 +837,12 @@ __global__ void __launch_bounds__(128, 6) k_qcorr_combine_pair(const double* __r
 // instead of 15 + 15.  zpos[k]: 0 interior plane of its chunk, 1 first, 2 last.
 // ---------------------------------------------------------------------------
 constexpr int MARCH_KEEP_SLOTS = 9;  // P: rho, jx, jy, jz, e2 of plane k-1 so far;  U: rho, jx, jy, e2 it sends up
-template <int W>
-__global__ void __launch_bounds__(32 * W, (W <= 4 ? 3 : W <= 8 ? 2 : 1))
+// PIPE: the populations of plane k+1 travel global -> shared (cp.async: f into 27 slots of its own, g into the second of
+// two g buffers) while plane k is collided, and the mask / flag / QCorr neighbours of plane k+1 wait in registers: the
+// loads of a CTA overlap its own arithmetic instead of relying on the other resident CTA.  90 slots per thread.
+constexpr int march_slots(bool pipe) { return pipe ? 3 * NQ + MARCH_KEEP_SLOTS : NQ + MARCH_KEEP_SLOTS; }
+template <int W, bool PIPE>
+__global__ void __launch_bounds__(32 * W, PIPE ? (W <= 4 ? 2 : 1) : (W <= 4 ? 3 : W <= 8 ? 2 : 1))
     k_collide_tile_march(const __grid_constant__ CarryPtrs A, const __grid_constant__ MarchOut Q,
                          const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ flag,
                          const __grid_constant__ Layout L, const __grid_constant__ Phys P,
@@ -846,9 +850,9 @@ __global__ void __launch_bounds__(32 * W, (W <= 4 ? 3 : W <= 8 ? 2 : 1))
 {
     constexpr int T = 32 * W;
     extern __shared__ double smem[];
-    double* const sg = smem + threadIdx.x;  // sg[slot * T]
-    const unsigned sg_addr = (unsigned)__cvta_generic_to_shared(sg);
-    double* const sk = smem + NQ * T + threadIdx.x;  // sk[slot * T]: carried sums of plane k-1
+    double* const sg0 = smem + threadIdx.x;  // sg0[slot * T]; PIPE: g buffers at slots 0 and NQ, f at 2 NQ
+    const unsigned sg0_addr = (unsigned)__cvta_generic_to_shared(sg0);
+    double* const sk = smem + (PIPE ? 3 * NQ : NQ) * T + threadIdx.x;  // sk[slot * T]: carried sums of plane k-1
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int xc = blockIdx.x;
     const int y0 = blockIdx.y * W;
@@ -876,12 +880,12 @@ __global__ void __launch_bounds__(32 * W, (W <= 4 ? 3 : W <= 8 ? 2 : 1))
     uint32_t m_prev = 0u;
     auto ldb = [](const double* base, unsigned off) { return *(const double*)((const char*)base + off); };
     auto stb = [](double* base, unsigned off, double v) { *(double*)((char*)base + off) = v; };
-#pragma unroll 1
-    for (int kk = 0; kk < nk; ++kk) {
-        const int k = k0c + kk;
+    const unsigned cxy = (unsigned)(is + OX) * 8u + (unsigned)(j + GY) * px8;
+    // populations of plane k: g -> g buffer `buf`, f -> registers (plain) or the f slots (PIPE)
+    auto pull = [&](int k, int buf, double* f) {
         zo[2] = (L.wrap[2] && k == 0) ? (unsigned)(L.nz - 1) * sz8 : 0u - sz8;
         zo[0] = (L.wrap[2] && k == L.nz - 1) ? 0u - (unsigned)(L.nz - 1) * sz8 : sz8;
-        const unsigned c = (unsigned)(is + OX) * 8u + (unsigned)(j + GY) * px8 + (unsigned)(k + GZ) * sz8;
+        const unsigned c = cxy + (unsigned)(k + GZ) * sz8;
         unsigned cyz[3][3];
 #pragma unroll
         for (int b = 0; b < 3; ++b)
@@ -889,18 +893,56 @@ __global__ void __launch_bounds__(32 * W, (W <= 4 ? 3 : W <= 8 ? 2 : 1))
             for (int d = 0; d < 3; ++d) cyz[b][d] = c + yo[b] + zo[d];
         static_for<0, NQ>([&](auto qc_) {
             constexpr int Qd = decltype(qc_)::value;
-            cp_async8(sg_addr + Qd * T * 8, (const char*)A.gin[Qd] + (cyz[ey(Qd) + 1][ez(Qd) + 1] + xo[ex(Qd) + 1]));
+            cp_async8(sg0_addr + (buf * NQ + Qd) * T * 8, (const char*)A.gin[Qd] + (cyz[ey(Qd) + 1][ez(Qd) + 1] + xo[ex(Qd) + 1]));
         });
-        const uint32_t m = *(const uint32_t*)((const char*)nbr + (c >> 1));
-        const unsigned fb = flag[c >> 3];
-        const double qxp = ldb(A.qc[0], c + 8u), qxm = ldb(A.qc[0], c - 8u);
-        const double qyp = ldb(A.qc[1], c + px8), qym = ldb(A.qc[1], c - px8);
-        const double qzp = ldb(A.qc[2], c + sz8), qzm = ldb(A.qc[2], c - sz8);
-        double f[NQ];
         static_for<0, NQ>([&](auto qc_) {
             constexpr int Qd = decltype(qc_)::value;
-            f[Qd] = ldb(A.fin[Qd], cyz[ey(Qd) + 1][ez(Qd) + 1] + xo[ex(Qd) + 1]);
+            if constexpr (PIPE)
+                cp_async8(sg0_addr + (2 * NQ + Qd) * T * 8, (const char*)A.fin[Qd] + (cyz[ey(Qd) + 1][ez(Qd) + 1] + xo[ex(Qd) + 1]));
+            else
+                f[Qd] = ldb(A.fin[Qd], cyz[ey(Qd) + 1][ez(Qd) + 1] + xo[ex(Qd) + 1]);
         });
+    };
+    // mask, gradient flags and the six QCorr neighbours of plane k
+    struct Small {
+        uint32_t m;
+        unsigned fb;
+        double qxp, qxm, qyp, qym, qzp, qzm;
+    };
+    auto pull_small = [&](int k) {
+        const unsigned c = cxy + (unsigned)(k + GZ) * sz8;
+        Small S;
+        S.m = *(const uint32_t*)((const char*)nbr + (c >> 1));
+        S.fb = flag[c >> 3];
+        S.qxp = ldb(A.qc[0], c + 8u), S.qxm = ldb(A.qc[0], c - 8u);
+        S.qyp = ldb(A.qc[1], c + px8), S.qym = ldb(A.qc[1], c - px8);
+        S.qzp = ldb(A.qc[2], c + sz8), S.qzm = ldb(A.qc[2], c - sz8);
+        return S;
+    };
+    Small Sn;
+    if constexpr (PIPE) {
+        pull(k0c, 0, nullptr);
+        Sn = pull_small(k0c);
+    }
+#pragma unroll 1
+    for (int kk = 0; kk < nk; ++kk) {
+        const int k = k0c + kk;
+        const unsigned c = cxy + (unsigned)(k + GZ) * sz8;
+        double* const sg = PIPE ? sg0 + (kk & 1) * NQ * T : sg0;  // this plane's g slots
+        double f[NQ];
+        Small S;
+        if constexpr (PIPE) {
+            S = Sn;
+            cp_async_wait_all();
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) f[q] = sg0[(2 * NQ + q) * T];
+        } else {
+            pull(k, 0, f);
+            S = pull_small(k);
+        }
+        const uint32_t m = S.m;
+        const unsigned fb = S.fb;
+        const double qxp = S.qxp, qxm = S.qxm, qyp = S.qyp, qym = S.qym, qzp = S.qzp, qzm = S.qzm;
         const bool fluid = m & 1u;
         if (m != ALL_FLUID) {
             if (fluid) {
@@ -914,7 +956,16 @@ __global__ void __launch_bounds__(32 * W, (W <= 4 ? 3 : W <= 8 ? 2 : 1))
             }
         }
         MomF mf = moments_f([&](int q) { return f[q]; });
-        cp_async_wait_all_after(mf.rho);
+        if constexpr (PIPE) {
+            // the f slots have been read (mf depends on all of them): plane k+1 may land there and in the other g buffer
+            if (kk + 1 < nk) {
+                asm volatile("" : "+d"(mf.rho)::"memory");
+                pull(k + 1, (kk + 1) & 1, nullptr);
+                Sn = pull_small(k + 1);
+            }
+        } else {
+            cp_async_wait_all_after(mf.rho);
+        }
         if (m != ALL_FLUID) {
             if (fluid) {
                 static_for<1, NQ>([&](auto qc_) {
@@ -1975,12 +2026,36 @@ int launch_collide_tile_pair(const Layout& L, const Phys& P, const CarryPlan& C,
 }
 
 // variant 9.  Returns the number of kernels, -1 if a component exceeds 4 GB, -2 if a chunk would hold one plane
-int launch_collide_tile_march(const Layout& L, const Phys& P, const CarryPlan& C, int zm, const double* fin, const double* gin,
-                              double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag, const double* qc,
-                              double* qc_next, double* part, double* edge, cudaStream_t st, int ka, int kb)
+template <int W, bool PIPE>
+static void run_collide_tile_march(dim3 grid, cudaStream_t st, const CarryPtrs& A, const MarchOut& Q, const uint32_t* nbr,
+                                   const uint8_t* flag, const Layout& L, const Phys& P, const CarryPlan& Ce, int ka, int kb, int zm)
+{
+    const size_t sm = (size_t)march_slots(PIPE) * 32 * W * 8;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_collide_tile_march<W, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        attr_done = true;
+    }
+    k_collide_tile_march<W, PIPE><<<grid, 32 * W, sm, st>>>(A, Q, nbr, flag, L, P, Ce, ka, kb, zm);
+}
+
+// rows per CTA the z-march kernels are built for: 6 (plain); 4 and 8 (pipelined: a measured negative result,
+// 30.5 / 29.1 ms against 25.8 ms at 512^3 with 8 instead of 12 warps per SM -- built only with MBL_EXPERIMENTS)
+bool march_rows_supported(int W, bool pipe)
+{
+#ifdef MBL_EXPERIMENTS
+    return pipe ? (W == 4 || W == 8) : W == 6;
+#else
+    return !pipe && W == 6;
+#endif
+}
+
+int launch_collide_tile_march(const Layout& L, const Phys& P, const CarryPlan& C, int W, bool pipe, int zm, const double* fin,
+                              const double* gin, double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag,
+                              const double* qc, double* qc_next, double* part, double* edge, cudaStream_t st, int ka, int kb)
 {
     if (L.sq * 8 >= (1LL << 32)) return -1;
-    constexpr int W = 6;
+    if (!march_rows_supported(W, pipe)) return -3;
     if (kb <= ka) ka = 0, kb = L.nz;
     if (zm < 2) zm = 2;
     if ((kb - ka) % zm == 1 || kb - ka < 2) return -2;  // a one-plane chunk would need both send words
@@ -1998,27 +2073,25 @@ int launch_collide_tile_march(const Layout& L, const Phys& P, const CarryPlan& C
     const long long esz = carry_edge_plane(L, W);
     Ce.esz8 = (unsigned)(esz * 8);
     for (int e = 0; e < CARRY_EDGE_WORDS; ++e) A.edge[e] = edge + (long long)e * esz * (L.nz + 2 * GZ);
-    const size_t sm = (size_t)(NQ + MARCH_KEEP_SLOTS) * 32 * W * 8;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_collide_tile_march<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        attr_done = true;
-    }
     const dim3 grid(C.nxc, (L.ny + W - 1) / W, (kb - ka + zm - 1) / zm);
-    k_collide_tile_march<6><<<grid, 32 * W, sm, st>>>(A, Q, nbr, flag, L, P, Ce, ka, kb, zm);
+    if (!pipe) run_collide_tile_march<6, false>(grid, st, A, Q, nbr, flag, L, P, Ce, ka, kb, zm);
+#ifdef MBL_EXPERIMENTS
+    else if (W == 4) run_collide_tile_march<4, true>(grid, st, A, Q, nbr, flag, L, P, Ce, ka, kb, zm);
+    else run_collide_tile_march<8, true>(grid, st, A, Q, nbr, flag, L, P, Ce, ka, kb, zm);
+#endif
     return 1;
 }
 
 int launch_qcorr_combine_march(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr,
-                               const double* part, const double* edge, const signed char* zpos, double* qc, cudaStream_t st,
-                               int ka, int kb)
+                               const double* part, const double* edge, int W, const signed char* zpos, double* qc,
+                               cudaStream_t st, int ka, int kb)
 {
     const int bx = block_x(L);
     int k0 = (L.lo[2] > L.dlo[2]) ? -1 : 0;
     int k1 = (L.lo[2] + L.nz - 1 < L.dhi[2]) ? L.nz : L.nz - 1;
     if (kb > ka) k0 = ka, k1 = kb - 1;
     dim3 grid((L.nx + bx - 1) / bx, L.ny, k1 - k0 + 1);
-    k_qcorr_combine_march<<<grid, bx, 0, st>>>(fin, gin, nbr, part, edge, zpos, 6, carry_edge_plane(L, 6), qc, L, P, k0);
+    k_qcorr_combine_march<<<grid, bx, 0, st>>>(fin, gin, nbr, part, edge, zpos, W, carry_edge_plane(L, W), qc, L, P, k0);
     return 1;
 }
 

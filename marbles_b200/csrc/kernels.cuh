@@ -113,12 +113,15 @@ int launch_qcorr_combine_pair(const Layout& L, const Phys& P, const double* fin,
 // variant 9: the tile carry step marching through z-chunks of zm planes, z sums completed on chip, QCorr of the next step
 // written by the collide kernel for the cells that are complete (kernels.cu); zpos[k + GZ]: 0 interior, 1 first, 2 last
 // plane of its chunk
-int launch_collide_tile_march(const Layout& L, const Phys& P, const CarryPlan& C, int zm, const double* fin, const double* gin,
-                              double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag, const double* qc,
-                              double* qc_next, double* part, double* edge, cudaStream_t st, int ka = 0, int kb = 0);
+// W rows per CTA; pipe: plane k+1 is pulled into shared memory while plane k is collided (variant 10; W = 4 or 8)
+bool march_rows_supported(int W, bool pipe);
+int launch_collide_tile_march(const Layout& L, const Phys& P, const CarryPlan& C, int W, bool pipe, int zm, const double* fin,
+                              const double* gin, double* fout, double* gout, const uint32_t* nbr, const uint8_t* flag,
+                              const double* qc, double* qc_next, double* part, double* edge, cudaStream_t st, int ka = 0,
+                              int kb = 0);
 int launch_qcorr_combine_march(const Layout& L, const Phys& P, const double* fin, const double* gin, const uint32_t* nbr,
-                               const double* part, const double* edge, const signed char* zpos, double* qc, cudaStream_t st,
-                               int ka = 0, int kb = 0);
+                               const double* part, const double* edge, int W, const signed char* zpos, double* qc,
+                               cudaStream_t st, int ka = 0, int kb = 0);
 long long carry_edge_plane(const Layout& L, int rows);
 int carry_tile_rows(int rows);  // supported rows per CTA: 4, 6 (default), 8, 12
 // edge / edge_rows: the edge arrays k_collide_tile wrote (nullptr after k_collide_carry)

@@ -279,7 +279,7 @@ class LBM:
         """The overlapped slab step (mbl_step_split: boundary planes first, their exchange behind the interior planes)
         applies to the two-kernel and the tile-carry variants and to slabs of at least 8 planes; levels with walls,
         inlets or outlets fill their ghost cells at the start of part 0."""
-        return (self.world > 1 and self.variant in (0, 5, 7, 8, 9) and self.n_local[2] >= 8
+        return (self.world > 1 and self.variant in (0, 5, 7, 8, 9, 10) and self.n_local[2] >= 8
                 and self.comm is not None and hasattr(self.comm, "exchange_next") and self.overlap)
 
     def step(self, nsteps: int = 1, want_macrodata: bool = False):

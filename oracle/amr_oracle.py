@@ -429,6 +429,29 @@ class AmrOracle:
         new.fill_boundary("g", ng)
         self._macrodata(new)
 
+    def make_level_from_coarse(self, lev, boxes, is_fluid_dense=None):
+        """LBM::MakeNewLevelFromCoarse (Source/LBM.cpp:1088-1144), a level AmrCore::regrid adds above the finest one:
+        is_fluid, then f and g of EVERY cell (valid and ghost, inside the periodically grown domain) by
+        FillPatchOps::fillpatch_from_coarse = InterpFromCoarseLevel (CellConservativeLinear from level lev-1) and the
+        fine BCFill -- no K6 pre-pass, no fill_f_inside_eb, no FillBoundary -- then the macrodata."""
+        assert lev == len(self.levels) and lev >= 1
+        new = Level(lev, self.setup, boxes)
+        new.time = self.levels[lev - 1].time
+        self._set_is_fluid(new, is_fluid_dense)
+        nothing = np.full_like(new.cover, -1)
+        for name in ("f", "g"):
+            self._interp_from_coarse(lev, name, target=new, cover=nothing)
+        self.levels.append(new)
+        self.finest = lev
+        self.physbc(lev)
+        self._macrodata(new)
+
+    def clear_level(self, lev):
+        """LBM::ClearLevel (Source/LBM.cpp:1367-1380): the finest level disappears in a regrid"""
+        assert lev == self.finest and lev >= 1
+        self.levels.pop()
+        self.finest = lev - 1
+
     # ------------------------------------------------------------ time stepping
     def advance(self, lev):
         """LBM::advance (Source/LBM.cpp:523-544)"""

@@ -11,7 +11,7 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = ["tg12", "sod48", "chcyl", "thermal", "pressure", "slip", "shear", "slipyz", "touch"]
 
 
-AMR_GOLDEN_CASES = ["amr2_tg", "amr2_chcyl", "amr3_chcyl", "amr2_sod", "amr2_sod_regrid"]
+AMR_GOLDEN_CASES = ["amr2_tg", "amr2_chcyl", "amr3_chcyl", "amr2_sod", "amr2_sod_regrid", "amr2_tg_appear", "amr2_chcyl_appear"]
 
 
 def pytest_configure(config):
@@ -64,3 +64,21 @@ def amr_boxes_at(z, step, lev):
     if key not in z.files:
         return None
     return [(list(map(int, b[0])), list(map(int, b[1]))) for b in z[key]]
+
+
+def amr_regrid_actions(z, step, current):
+    """What AmrCore::regrid did at the start of coarse step `step` of a dynamically regridded golden case, read off the
+    box lists the reference wrote: [(lev, "make" | "remake" | "clear", boxes)] -- levels made (MakeNewLevelFromCoarse)
+    or re-made (RemakeLevel) from the coarsest up, then cleared (ClearLevel) from the finest down.
+    `current` = {lev: box list now, [] if the level does not exist} is updated."""
+    acts, gone = [], []
+    for lev in sorted(current):
+        nb = amr_boxes_at(z, step, lev)
+        if nb is None or nb == current[lev]:
+            continue
+        if not nb:
+            gone.append((lev, "clear", nb))
+        else:
+            acts.append((lev, "remake" if current[lev] else "make", nb))
+        current[lev] = nb
+    return acts + gone[::-1]

@@ -385,7 +385,18 @@ AMR_CASES["amr2_sod_regrid"] = (AMR_CASES["amr2_sod"][0].replace("max_step = 4",
 tagging.rho.adjacent_difference_greater = 0.02
 tagging.rho.field_name = rho
 """, 2, [0, 1, 8, 16])
-AMR_REGRID_INT = {"amr2_sod_regrid": 1}
+# A level that appears and vanishes while the run goes on (MakeNewLevelFromCoarse, ClearLevel): tagging boxes with a
+# time window (tagging.*.start_time / end_time, Source/LBM.cpp:332-343), regrid every coarse step.  Level 1 does not
+# exist in plt00000; it is interpolated from level 0 when the window opens and dropped when it closes.
+AMR_CASES["amr2_tg_appear"] = (AMR_CASES["amr2_tg"][0].replace("max_step = 3", "max_step = 9") + """tagging.box.start_time = 2.5
+tagging.box.end_time = 6.5
+""", 2, [0, 2, 3, 4, 6, 7, 9])
+AMR_CASES["amr2_chcyl_appear"] = (AMR_CASES["amr2_chcyl"][0].replace("max_step = 4", "max_step = 8") + """tagging.box.start_time = 1.5
+tagging.box.end_time = 5.5
+""", 2, [0, 1, 2, 3, 5, 6, 8])
+AMR_REGRID_INT = {"amr2_sod_regrid": 1, "amr2_tg_appear": 1, "amr2_chcyl_appear": 1}
+# steps stored with f and g as well (besides the first and the last): the first step of the new level
+AMR_FULL_STEPS = {"amr2_tg_appear": [4], "amr2_chcyl_appear": [3]}
 
 AMR_KEEP_LAST = KEEP_STEP0 + ["dQCorrX", "dQCorrY", "dQCorrZ"]
 AMR_KEEP_MID = O.MACRO_NAMES
@@ -404,18 +415,26 @@ def make_amr(out_dir, only):
             fh.write(deck_text)
         O.run_reference(deck_path, work, [], omp=False)
         data = {"deck": np.array(deck_text), "steps": np.array(steps), "nlev": np.array(nlev)}
+        def boxes_of(st, lev):  # empty when the level does not exist in that plotfile
+            pdir = os.path.join(work, f"plt{st:05d}")
+            if not os.path.isdir(os.path.join(pdir, f"Level_{lev}")):
+                return np.zeros((0, 2, 3), dtype=np.int64)
+            return np.array(O.read_plotfile_boxes(pdir, lev))
         if name in AMR_REGRID_INT:
             for st in range(1, steps[-1] + 1):
                 for lev in range(1, nlev):
-                    data[f"boxes_s{st}_l{lev}"] = np.array(O.read_plotfile_boxes(os.path.join(work, f"plt{st:05d}"), lev))
+                    data[f"boxes_s{st}_l{lev}"] = boxes_of(st, lev)
         for lev in range(nlev):
-            data[f"boxes_l{lev}"] = np.array(O.read_plotfile_boxes(os.path.join(work, "plt00000"), lev))
+            data[f"boxes_l{lev}"] = boxes_of(0, lev)
             for s in steps:
+                if len(boxes_of(s, lev)) == 0:
+                    continue
                 pf = O.read_plotfile(os.path.join(work, f"plt{s:05d}"), lev)
-                if s == steps[0]:
+                if f"is_fluid_l{lev}" not in data:
                     fl = pf["is_fluid"]
                     data[f"is_fluid_l{lev}"] = np.where(np.isnan(fl), 1, fl).astype(np.int8)
-                keep = AMR_KEEP_LAST if s == steps[-1] else (KEEP_STEP0 if s == steps[0] else AMR_KEEP_MID)
+                keep = AMR_KEEP_LAST if s == steps[-1] else (
+                    KEEP_STEP0 if s == steps[0] or s in AMR_FULL_STEPS.get(name, []) else AMR_KEEP_MID)
                 for n in keep:
                     data[f"s{s}_l{lev}_{n}"] = pf[n]
         path = os.path.join(out_dir, f"{name}.npz")

@@ -31,6 +31,10 @@ CARRY_ENV = {
     "zmarch": (9, {}),
     "zmarch-zm3": (9, {"MBL_ZMARCH": "3"}),
     "zmarch-zm2": (9, {"MBL_ZMARCH": "2"}),
+    # variant 10 (MBL_EXPERIMENTS): the same with plane k+1 pulled into shared memory while plane k is collided
+    "zpipe": (10, {}),
+    "zpipe-4rows-zm3": (10, {"MBL_ROWS": "4", "MBL_ZMARCH": "3"}),
+    "zpipe-zm2": (10, {"MBL_ZMARCH": "2"}),
     # variant 8: the one-kernel march step (march.cu): default tuning, small CTAs with short ragged marches, and
     # without the early pull of the next plane
     "march": (8, {}),
@@ -71,7 +75,8 @@ def new_lbm(deck_text, is_fluid=None, overrides=None, variant=None):
 # fused: mbl_step with the persistent TMA kernel (variant 1, the default), its two job types as two
 # launches (2), or the two plain kernels (0); unfused: the reference-granular operator sequence
 @pytest.mark.parametrize("fused", with_experiments([0, "tile", "tile-6rows-own28", "lean", "pair", "zmarch", "zmarch-zm3", None],
-                                                   [1, 2, 3, "carry", "carry-ky5-own28", "march", "march-4rows-zm3", "march-nopipe-zm5"]),
+                                                   [1, 2, 3, "carry", "carry-ky5-own28", "march", "march-4rows-zm3", "march-nopipe-zm5", "zpipe",
+                                                    "zpipe-4rows-zm3"]),
                          ids=lambda v: {0: "twopass-plain", 1: "fused-tma", 2: "twopass-tma", 3: "fused-plain",
                                         None: "unfused"}.get(v, str(v)))
 @pytest.mark.parametrize("case", GOLDEN_CASES)
@@ -129,7 +134,7 @@ def test_geometry_matches_reference_is_fluid():
 
 @pytest.mark.parametrize("variant", with_experiments([0, "tile", "tile-6rows-own28", "tile-12rows", "tile-4rows", "pair", "zmarch", "zmarch-zm3", "zmarch-zm2"],
                                                      [1, 3, "carry", "carry-ky5-own28", "carry-ky1", "march", "march-4rows-zm3",
-                                                      "march-nopipe-zm5"]),
+                                                      "march-nopipe-zm5", "zpipe", "zpipe-4rows-zm3", "zpipe-zm2"]),
                          ids=lambda v: {0: "twopass-plain", 1: "fused-tma", 3: "fused-plain"}.get(v, str(v)))
 @pytest.mark.parametrize("case", ["chcyl", "pressure", "slip", "tg12"])
 def test_random_state_vs_oracle(oracle_mod, case, variant):
@@ -180,7 +185,7 @@ def test_eb_forces_and_vorticity_vs_oracle(oracle_mod):
     lbm.close()
 
 
-@pytest.mark.parametrize("variant", with_experiments([0, "tile", "pair", "zmarch"], ["carry", "march"]),
+@pytest.mark.parametrize("variant", with_experiments([0, "tile", "pair", "zmarch"], ["carry", "march", "zpipe"]),
                          ids=lambda v: "twopass-plain" if v == 0 else str(v))
 def test_tg64_vs_oracle_and_conservation(oracle_mod, variant):
     """BASELINE config 1 (TG 64^3): 3 steps against the oracle, then size-independent properties"""
@@ -208,7 +213,7 @@ def test_tg64_vs_oracle_and_conservation(oracle_mod, variant):
     lbm.close()
 
 
-@pytest.mark.parametrize("variant", with_experiments([0, "tile", "zmarch"], ["carry", "march"]),
+@pytest.mark.parametrize("variant", with_experiments([0, "tile", "zmarch"], ["carry", "march", "zpipe"]),
                          ids=lambda v: "twopass-plain" if v == 0 else str(v))
 def test_full_size_conservation_256(variant):
     """periodic 256^3 (largest size the test box does in seconds): mass/energy conservation of
@@ -228,7 +233,7 @@ def test_full_size_conservation_256(variant):
 
 @pytest.mark.parametrize("case,nz,world", [("tg12", 12, 2), ("tg12", 13, 3), ("sod48", 8, 2), ("chcyl", None, 2),
                                            ("pressure", None, 2)])
-@pytest.mark.parametrize("variant", with_experiments([0, "tile-6rows-own28", "zmarch-zm3"], ["carry-ky5-own28", "march-4rows-zm3"]),
+@pytest.mark.parametrize("variant", with_experiments([0, "tile-6rows-own28", "zmarch-zm3"], ["carry-ky5-own28", "march-4rows-zm3", "zpipe-4rows-zm3"]),
                          ids=lambda v: "twopass-plain" if v == 0 else str(v))
 def test_two_slabs_match_single_box(case, nz, world, variant):
     """the multi-rank scheme (z-slabs, ONE exchange of two ghost planes per step, q-correction of the first
@@ -478,7 +483,7 @@ def test_graph_replay_is_bit_identical(case, variant):
 
 
 @pytest.mark.parametrize("case,n_cell", [("tg12", "67 45 13"), ("tg12", "31 7 9"), ("sod48", "75 3 5"), ("sod48", "130 2 2")])
-@pytest.mark.parametrize("variant", with_experiments([None, 0, "tile", "pair", "zmarch-zm3"], ["carry", "march", "march-4rows-zm3"]),
+@pytest.mark.parametrize("variant", with_experiments([None, 0, "tile", "pair", "zmarch-zm3"], ["carry", "march", "march-4rows-zm3", "zpipe", "zpipe-4rows-zm3"]),
                          ids=lambda v: {None: "default", 0: "twopass"}.get(v, str(v)))
 def test_odd_box_sizes_vs_oracle(oracle_mod, case, n_cell, variant):
     """box sizes that are no multiple of the warp strip (30 cells), the CTA height (6 rows) or the march length"""
@@ -540,7 +545,7 @@ def test_slab_vorticity_matches_single_box(case, nz, world):
     single.close()
 
 
-@pytest.mark.parametrize("variant", with_experiments([None, "tile"], ["march"]), ids=lambda v: "default" if v is None else str(v))
+@pytest.mark.parametrize("variant", with_experiments([None, "tile"], ["march", "zpipe"]), ids=lambda v: "default" if v is None else str(v))
 @pytest.mark.parametrize("n", [256, 512])
 def test_full_size_values_tiled_tg_vs_oracle(oracle_mod, n, variant):
     """Value-level pin of the benchmarked size (BASELINE config 3, 512^3; and 256^3): the box is initialised with a
