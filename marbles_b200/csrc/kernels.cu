@@ -841,7 +841,9 @@ constexpr int MARCH_KEEP_SLOTS = 9;  // P: rho, jx, jy, jz, e2 of plane k-1 so f
 // two g buffers) while plane k is collided, and the mask / flag / QCorr neighbours of plane k+1 wait in registers: the
 // loads of a CTA overlap its own arithmetic instead of relying on the other resident CTA.  90 slots per thread.
 constexpr int march_slots(bool pipe) { return pipe ? 3 * NQ + MARCH_KEEP_SLOTS : NQ + MARCH_KEEP_SLOTS; }
-template <int W, bool PIPE>
+// ABL (MBL_EXPERIMENTS, timing only -- results are wrong): 1 no x shuffles, 2 no y exchange and no barriers, 4 no
+// carried stores (the sums become dead code)
+template <int W, bool PIPE, int ABL = 0>
 __global__ void __launch_bounds__(32 * W, PIPE ? (W <= 4 ? 2 : 1) : (W <= 4 ? 3 : W <= 8 ? 2 : 1))
     k_collide_tile_march(const __grid_constant__ CarryPtrs A, const __grid_constant__ MarchOut Q,
                          const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ flag,
@@ -880,6 +882,9 @@ __global__ void __launch_bounds__(32 * W, PIPE ? (W <= 4 ? 2 : 1) : (W <= 4 ? 3 
     uint32_t m_prev = 0u;
     auto ldb = [](const double* base, unsigned off) { return *(const double*)((const char*)base + off); };
     auto stb = [](double* base, unsigned off, double v) { *(double*)((char*)base + off) = v; };
+    auto stc = [&](double* base, unsigned off, double v) {  // carried words
+        if constexpr (!(ABL & 4)) *(double*)((char*)base + off) = v;
+    };
     const unsigned cxy = (unsigned)(is + OX) * 8u + (unsigned)(j + GY) * px8;
     // populations of plane k: g -> g buffer `buf`, f -> registers (plain) or the f slots (PIPE)
     auto pull = [&](int k, int buf, double* f) {
@@ -995,8 +1000,10 @@ __global__ void __launch_bounds__(32 * W, PIPE ? (W <= 4 ? 2 : 1) : (W <= 4 ? 3 
             const double v = f[Qd] + omega * (feq_q<Qd>(cc) - f[Qd]);
             if (own) stb(A.fout[Qd], c, v);
             double t = v;
-            if constexpr (ex(Qd) == 1) t = __shfl_up_sync(FULL, v, 1);
-            if constexpr (ex(Qd) == -1) t = __shfl_down_sync(FULL, v, 1);
+            if constexpr (!(ABL & 1)) {
+                if constexpr (ex(Qd) == 1) t = __shfl_up_sync(FULL, v, 1);
+                if constexpr (ex(Qd) == -1) t = __shfl_down_sync(FULL, v, 1);
+            }
             double(&Tt)[3][2] = ey(Qd) == -1 ? TA : ey(Qd) == 0 ? TB : TC;
             Tt[d][0] += t;
             if constexpr (ex(Qd) == 1) Tt[d][1] += t;
@@ -1009,8 +1016,10 @@ __global__ void __launch_bounds__(32 * W, PIPE ? (W <= 4 ? 2 : 1) : (W <= 4 ? 3 
             const double v = gq + omega * (geq_q<Qd>(cc) - gq);
             if (own) stb(A.gout[Qd], c, v);
             double t = v;
-            if constexpr (ex(Qd) == 1) t = __shfl_up_sync(FULL, v, 1);
-            if constexpr (ex(Qd) == -1) t = __shfl_down_sync(FULL, v, 1);
+            if constexpr (!(ABL & 1)) {
+                if constexpr (ex(Qd) == 1) t = __shfl_up_sync(FULL, v, 1);
+                if constexpr (ex(Qd) == -1) t = __shfl_down_sync(FULL, v, 1);
+            }
             double(&E)[3] = ey(Qd) == -1 ? EA : ey(Qd) == 0 ? EB : EC;
             E[d] += t;
         });
@@ -1019,38 +1028,39 @@ __global__ void __launch_bounds__(32 * W, PIPE ? (W <= 4 ? 2 : 1) : (W <= 4 ? 3 
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             if (first) {
-                if (own) {
+                if (own && !(ABL & 4)) {
                     stb(A.edge[3 * d + 0], ce, TA[d][0]);
                     stb(A.edge[3 * d + 1], ce, TA[d][1]);
                     stb(A.edge[3 * d + 2], ce, EA[d]);
                 }
-            } else {
+            } else if (!(ABL & 2)) {
                 sg[(3 * d + 0) * T] = TA[d][0];
                 sg[(3 * d + 1) * T] = TA[d][1];
                 sg[(3 * d + 2) * T] = EA[d];
             }
             if (last) {
-                if (own) {
+                if (own && !(ABL & 4)) {
                     stb(A.edge[9 + 3 * d + 0], ce, TC[d][0]);
                     stb(A.edge[9 + 3 * d + 1], ce, TC[d][1]);
                     stb(A.edge[9 + 3 * d + 2], ce, EC[d]);
                 }
-            } else {
+            } else if (!(ABL & 2)) {
                 sg[(9 + 3 * d + 0) * T] = TC[d][0];
                 sg[(9 + 3 * d + 1) * T] = TC[d][1];
                 sg[(9 + 3 * d + 2) * T] = EC[d];
             }
         }
-        __syncthreads();
+        if constexpr (!(ABL & 2)) __syncthreads();
         if (own) {
             const double* up = sg + 32;   // row j+1: its e_y = -1 terms arrive here
             const double* dn = sg - 32;   // row j-1: its e_y = +1 terms
             double r[3], x[3], y[3], e[3];  // per destination plane k-1, k, k+1: rho, jx, jy, e2 (y-complete up to the CTA edges)
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                const double ua = last ? 0.0 : up[(3 * d + 0) * T], dc = first ? 0.0 : dn[(9 + 3 * d + 0) * T];
-                const double ux = last ? 0.0 : up[(3 * d + 1) * T], dx = first ? 0.0 : dn[(9 + 3 * d + 1) * T];
-                const double ue = last ? 0.0 : up[(3 * d + 2) * T], de = first ? 0.0 : dn[(9 + 3 * d + 2) * T];
+                const bool nu = last || (ABL & 2), nd = first || (ABL & 2);
+                const double ua = nu ? 0.0 : up[(3 * d + 0) * T], dc = nd ? 0.0 : dn[(9 + 3 * d + 0) * T];
+                const double ux = nu ? 0.0 : up[(3 * d + 1) * T], dx = nd ? 0.0 : dn[(9 + 3 * d + 1) * T];
+                const double ue = nu ? 0.0 : up[(3 * d + 2) * T], de = nd ? 0.0 : dn[(9 + 3 * d + 2) * T];
                 r[d] = TB[d][0] + ua + dc;
                 x[d] = TB[d][1] + ux + dx;
                 y[d] = dc - ua;
@@ -1058,10 +1068,10 @@ __global__ void __launch_bounds__(32 * W, PIPE ? (W <= 4 ? 2 : 1) : (W <= 4 ? 3 
             }
             if (kk == 0) {
                 // first plane of the chunk: what it sends down leaves now (another chunk's last plane waits for it)
-                stb(A.part[5], c, r[0]);
-                stb(A.part[6], c, x[0]);
-                stb(A.part[7], c, y[0]);
-                stb(A.part[8], c, e[0]);
+                stc(A.part[5], c, r[0]);
+                stc(A.part[6], c, x[0]);
+                stc(A.part[7], c, y[0]);
+                stc(A.part[8], c, e[0]);
                 sk[0 * T] = r[1], sk[1 * T] = x[1], sk[2 * T] = y[1], sk[3 * T] = 0.0, sk[4 * T] = e[1];
             } else {
                 // plane k-1 is complete in z: its sums so far + this plane's e_z = -1 terms
@@ -1071,15 +1081,15 @@ __global__ void __launch_bounds__(32 * W, PIPE ? (W <= 4 ? 2 : 1) : (W <= 4 ? 3 
                 const bool z_inner = kk >= 2 && (L.wrap[2] || (kp > 0 && kp < L.nz - 1));
                 if (xy_inner && z_inner && m_prev == ALL_FLUID) {
                     const Prim sp = primitives(Sr, Sx, Sy, Sz, Se, P);
-                    stb(Q.qcn[0], c_prev, sp.qcx);
-                    stb(Q.qcn[1], c_prev, sp.qcy);
-                    stb(Q.qcn[2], c_prev, sp.qcz);
+                    stc(Q.qcn[0], c_prev, sp.qcx);
+                    stc(Q.qcn[1], c_prev, sp.qcy);
+                    stc(Q.qcn[2], c_prev, sp.qcz);
                 } else {
-                    stb(A.part[0], c_prev, Sr);
-                    stb(A.part[1], c_prev, Sx);
-                    stb(A.part[2], c_prev, Sy);
-                    stb(A.part[3], c_prev, Sz);
-                    stb(A.part[4], c_prev, Se);
+                    stc(A.part[0], c_prev, Sr);
+                    stc(A.part[1], c_prev, Sx);
+                    stc(A.part[2], c_prev, Sy);
+                    stc(A.part[3], c_prev, Sz);
+                    stc(A.part[4], c_prev, Se);
                 }
                 // plane k so far: what plane k-1 sent up + its own e_z = 0 terms
                 const double ur = sk[5 * T];
@@ -1090,22 +1100,22 @@ __global__ void __launch_bounds__(32 * W, PIPE ? (W <= 4 ? 2 : 1) : (W <= 4 ? 3 
             if (kk == nk - 1) {
                 // last plane of the chunk: incomplete (the next chunk's first plane sends down); its sums so far and
                 // what it sends up leave
-                stb(A.part[0], c, sk[0 * T]);
-                stb(A.part[1], c, sk[1 * T]);
-                stb(A.part[2], c, sk[2 * T]);
-                stb(A.part[3], c, sk[3 * T]);
-                stb(A.part[4], c, sk[4 * T]);
+                stc(A.part[0], c, sk[0 * T]);
+                stc(A.part[1], c, sk[1 * T]);
+                stc(A.part[2], c, sk[2 * T]);
+                stc(A.part[3], c, sk[3 * T]);
+                stc(A.part[4], c, sk[4 * T]);
                 if (kk > 0) {  // (a one-plane chunk keeps its send-down words; the launcher never makes one)
-                    stb(A.part[5], c, r[2]);
-                    stb(A.part[6], c, x[2]);
-                    stb(A.part[7], c, y[2]);
-                    stb(A.part[8], c, e[2]);
+                    stc(A.part[5], c, r[2]);
+                    stc(A.part[6], c, x[2]);
+                    stc(A.part[7], c, y[2]);
+                    stc(A.part[8], c, e[2]);
                 }
             }
         }
         c_prev = c;
         m_prev = m;
-        __syncthreads();  // the exchange slots are the next plane's g slots
+        if constexpr (!(ABL & 2)) __syncthreads();  // the exchange slots are the next plane's g slots
     }
 }
 
@@ -1911,6 +1921,9 @@ CarryPlan make_carry_plan(const Layout& L, int own, int ky)
 {
     CarryPlan C;
     C.own = (own == 28) ? 28 : 30;
+#ifdef MBL_EXPERIMENTS
+    if (own == 32) C.own = 32;  // no halo lanes: timing only, the x sums are wrong at the strip edges
+#endif
     C.halo = (32 - C.own) / 2;
     C.ky = ky < 1 ? 1 : (ky > L.ny ? L.ny : ky);
     C.nxc = (L.nx + C.own - 1) / C.own;
@@ -2026,17 +2039,17 @@ int launch_collide_tile_pair(const Layout& L, const Phys& P, const CarryPlan& C,
 }
 
 // variant 9.  Returns the number of kernels, -1 if a component exceeds 4 GB, -2 if a chunk would hold one plane
-template <int W, bool PIPE>
+template <int W, bool PIPE, int ABL = 0>
 static void run_collide_tile_march(dim3 grid, cudaStream_t st, const CarryPtrs& A, const MarchOut& Q, const uint32_t* nbr,
                                    const uint8_t* flag, const Layout& L, const Phys& P, const CarryPlan& Ce, int ka, int kb, int zm)
 {
     const size_t sm = (size_t)march_slots(PIPE) * 32 * W * 8;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_collide_tile_march<W, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaFuncSetAttribute(k_collide_tile_march<W, PIPE, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         attr_done = true;
     }
-    k_collide_tile_march<W, PIPE><<<grid, 32 * W, sm, st>>>(A, Q, nbr, flag, L, P, Ce, ka, kb, zm);
+    k_collide_tile_march<W, PIPE, ABL><<<grid, 32 * W, sm, st>>>(A, Q, nbr, flag, L, P, Ce, ka, kb, zm);
 }
 
 // rows per CTA the z-march kernels are built for: 6 (plain); 4 and 8 (pipelined: a measured negative result,
@@ -2074,6 +2087,13 @@ int launch_collide_tile_march(const Layout& L, const Phys& P, const CarryPlan& C
     Ce.esz8 = (unsigned)(esz * 8);
     for (int e = 0; e < CARRY_EDGE_WORDS; ++e) A.edge[e] = edge + (long long)e * esz * (L.nz + 2 * GZ);
     const dim3 grid(C.nxc, (L.ny + W - 1) / W, (kb - ka + zm - 1) / zm);
+#ifdef MBL_EXPERIMENTS
+    static const int abl = getenv("MBL_ABLATE") ? atoi(getenv("MBL_ABLATE")) : 0;  // timing only: wrong results
+    if (!pipe && abl == 1) { run_collide_tile_march<6, false, 1>(grid, st, A, Q, nbr, flag, L, P, Ce, ka, kb, zm); return 1; }
+    if (!pipe && abl == 2) { run_collide_tile_march<6, false, 2>(grid, st, A, Q, nbr, flag, L, P, Ce, ka, kb, zm); return 1; }
+    if (!pipe && abl == 4) { run_collide_tile_march<6, false, 4>(grid, st, A, Q, nbr, flag, L, P, Ce, ka, kb, zm); return 1; }
+    if (!pipe && abl == 6) { run_collide_tile_march<6, false, 6>(grid, st, A, Q, nbr, flag, L, P, Ce, ka, kb, zm); return 1; }
+#endif
     if (!pipe) run_collide_tile_march<6, false>(grid, st, A, Q, nbr, flag, L, P, Ce, ka, kb, zm);
 #ifdef MBL_EXPERIMENTS
     else if (W == 4) run_collide_tile_march<4, true>(grid, st, A, Q, nbr, flag, L, P, Ce, ka, kb, zm);
@@ -2216,5 +2236,10 @@ int launch_halo_unpack(const Layout& L, double* f, double* g, int side, const do
     k_halo_copy<<<148 * 4, 256, 0, st>>>(f, g, const_cast<double*>(buf), L, k0, 0);
     return 1;
 }
+
+#ifdef MBL_EXPERIMENTS
+// negative-result kernels (variants 3-4), kept out of the shipped library: DESIGN.md section 3
+#include "experiments/experiments.cuh"
+#endif
 
 }  // namespace mbl
