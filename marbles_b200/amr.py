@@ -120,19 +120,20 @@ class AmrLBM:
         boxes, n = self.boxes[lev], self.n[lev]
         ng = F_NGHOST
         dx = [self.inp.dx[d] / REF_RATIO ** lev for d in range(3)]
+        # the level's valid-cell field, once: ghost cells on cells of the level domain (periodic images included) take
+        # its value -- m_is_fluid.FillBoundary(periodicity), Source/LBM.cpp:1234
+        dense = is_fluid_dense
+        if dense is None:
+            dense = is_fluid_from_deck(self.inp.deck, n, self.inp.prob_lo, dx, (0, 0, 0), n, 0)
+        dense = np.asarray(dense)
+        all_fluid = bool(dense.min() == 1)
         for ib, (blo, bhi) in enumerate(boxes):
             nl = [bhi[d] - blo[d] + 1 for d in range(3)]
-            if is_fluid_dense is None:
+            if is_fluid_dense is None and not all_fluid:
+                # beyond non-periodic faces: the body evaluated there (EB2 covers the grown domain)
                 a = is_fluid_from_deck(self.inp.deck, n, self.inp.prob_lo, dx, blo, nl, ng)
-                if a.min() == 1:
-                    continue  # mbl_level_define_boxes starts all fluid
             else:
                 a = np.ones(tuple(nl[d] + 2 * ng for d in (2, 1, 0)), dtype=np.int32)
-            # ghost cells on cells of the level domain (periodic images included) take the dense field's value:
-            # m_is_fluid.FillBoundary(periodicity), Source/LBM.cpp:1234
-            dense = is_fluid_dense
-            if dense is None:
-                dense = is_fluid_from_deck(self.inp.deck, n, self.inp.prob_lo, dx, (0, 0, 0), n, 0)
             idx, ok = [], []
             for d in (2, 1, 0):
                 x = np.arange(blo[d] - ng, bhi[d] + ng + 1)
@@ -143,8 +144,10 @@ class AmrLBM:
                     idx.append(np.clip(x, 0, n[d] - 1))
                     ok.append((x >= 0) & (x < n[d]))
             m = ok[0][:, None, None] & ok[1][None, :, None] & ok[2][None, None, :]
-            v = np.asarray(dense)[idx[0][:, None, None], idx[1][None, :, None], idx[2][None, None, :]]
+            v = dense[idx[0][:, None, None], idx[1][None, :, None], idx[2][None, None, :]]
             a = np.ascontiguousarray(np.where(m, v, a).astype(np.int32))
+            if a.min() == 1:
+                continue  # freshly defined boxes (mbl_level_define_boxes, _regrid, _make_from_coarse) start all fluid
             check(self.lib.mbl_box_set_is_fluid(self.ctx, lev, ib, a.ctypes.data_as(C.POINTER(C.c_int32)), ng))
 
     def init_data(self):
