@@ -193,8 +193,9 @@ int mbl_eb_forces(mbl_ctx* ctx, int lev, double out[3]);
  *   mbl_average_down  average_down_with_ghosts / masked_avgdown of level crse_lev + 1 onto crse_lev
  *                   (Source/Utilities.cpp:5-28, Source/Utilities.H:315-350; ng = 1 inside advance, 0 after init)
  * The sub-cycling order (LBM::time_step, Source/LBM.cpp:452-521) stays in the caller.
- * Restrictions: refinement ratio 2; all boxes of a level on this rank; a fine box may not lie within one
- * coarse cell of a NON-periodic domain face (mbl_fillpatch reports it).
+ * Restrictions: refinement ratio 2; all boxes of a level on this rank; fine boxes may touch a NON-periodic domain
+ * face (sod_amr.inp refines its outflow face), but no coarse-fine INTERFACE cell may have its coarse parent on such a
+ * face (mbl_fillpatch reports it).
  * ------------------------------------------------------------------------------------------- */
 int mbl_level_define_boxes(mbl_ctx* ctx, int lev, const mbl_level_geom* geom, int nboxes, const int* lo, const int* hi);
 int mbl_level_num_boxes(mbl_ctx* ctx, int lev);

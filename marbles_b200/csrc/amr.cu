@@ -304,6 +304,7 @@ int build_interp(Inter& I, const std::vector<HBox>& fine, const PGeom& FG, int f
     // fine ghost regions the interpolation fills: grown box inside dstdomain (the domain grown by the ghost width in
     // periodic directions) minus the fine level's valid boxes, NOT periodically shifted (FPinfo: complementIn)
     std::vector<RegionTag> regs;
+    const auto shifts_f = periodic_shifts(FG, PNG);
     for (int n = 0; n < nf; ++n) {
         HBox r0 = grow(fine[n], PNG);
         for (int d = 0; d < 3; ++d)
@@ -318,13 +319,29 @@ int build_interp(Inter& I, const std::vector<HBox>& fine, const PGeom& FG, int f
             list.swap(next);
         }
         for (const HBox& r : list) {
-            for (int d = 0; d < 3; ++d) {
-                if (FG.periodic[d]) continue;
-                // slopes of coarse cells on a non-periodic domain face are one-sided and depend on the extents of
-                // AMReX's internal coarse patch (AMReX_MFInterp_C.H:15-33): not reproduced
-                if (floor_div2(r.lo[d]) <= Cl.G.dlo[d] || floor_div2(r.hi[d]) >= Cl.G.dhi[d])
-                    return fail("level %d: a fine box lies within one coarse cell of a non-periodic domain face; the "
-                                "coarse-fine interpolation there is not supported", fine_lev);
+            // Slopes of coarse cells on a non-periodic domain face are one-sided and depend on the extents of AMReX's
+            // internal coarse patch and on what its BCFill put beyond the face (AMReX_MFInterp_C.H:15-33): not
+            // reproduced.  Only cells that SURVIVE matter -- the copy from the fine level that follows the interpolation
+            // (FillPatchSingleLevel, periodic images included) overwrites every cell a box of `cover` lies on -- so a
+            // fine box may touch a non-periodic face as long as no coarse-fine interface cell has its parent there.
+            bool near_face = false;
+            for (int d = 0; d < 3; ++d)
+                if (!FG.periodic[d] && (floor_div2(r.lo[d]) <= Cl.G.dlo[d] || floor_div2(r.hi[d]) >= Cl.G.dhi[d])) near_face = true;
+            if (near_face) {
+                std::vector<HBox> surv{r};
+                for (const auto& s : shifts_f) {
+                    const int sh[3] = {s[0], s[1], s[2]};
+                    for (const HBox& v : cover) {
+                        std::vector<HBox> next;
+                        for (const HBox& p : surv) box_diff(p, shifted(v, sh), next);
+                        surv.swap(next);
+                    }
+                }
+                for (const HBox& p : surv)
+                    for (int d = 0; d < 3; ++d)
+                        if (!FG.periodic[d] && (floor_div2(p.lo[d]) <= Cl.G.dlo[d] || floor_div2(p.hi[d]) >= Cl.G.dhi[d]))
+                            return fail("level %d: a coarse-fine interface lies within one coarse cell of a non-periodic "
+                                        "domain face; the interpolation there is not supported", fine_lev);
             }
             RegionTag t;
             t.box = n;

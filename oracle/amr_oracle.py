@@ -327,12 +327,19 @@ class AmrOracle:
             OK_, OJ, OI = np.meshgrid(*off, indexing="ij")
             val = u0[:, PK, PJ, PI] + OI * sx[:, PK, PJ, PI] + OJ * sy[:, PK, PJ, PI] + OK_ * sz[:, PK, PJ, PI]
             # guard: slopes of coarse cells on a non-periodic domain face use one-sided formulas that depend on the
-            # extents of AMReX's internal coarse patch (AMReX_MFInterp_C.H:15-33): not restated
+            # extents of AMReX's internal coarse patch (AMReX_MFInterp_C.H:15-33) and on ghost values its BCFill put
+            # there: not restated.  Only cells that SURVIVE matter: the copy from the fine level that follows
+            # (FillPatchSingleLevel, periodic images included) overwrites every cell a box of `cover` lies on, so a fine
+            # box may touch a non-periodic face as long as no coarse-fine interface cell has its parent there.
+            wi, wok = Lf.wrapped(idx)
+            WK, WJ, WI = np.meshgrid(*wi, indexing="ij")
+            wm = wok[0][:, None, None] & wok[1][None, :, None] & wok[2][None, None, :]
+            surv = m & ~(wm & (cover_mask[WK, WJ, WI] >= 0))
             for ax, d in enumerate((2, 1, 0)):
                 if Lc.periodic[d]:
                     continue
                 pc = np.floor_divide(idx[ax], ratio)
-                sel = m.any(axis=tuple(x for x in range(3) if x != ax))
+                sel = surv.any(axis=tuple(x for x in range(3) if x != ax))
                 if ((pc[sel] <= 0) | (pc[sel] >= Lc.n[d] - 1)).any():
                     raise NotImplementedError("coarse-fine interpolation next to a non-periodic domain face is not restated")
             a[:, m] = val[:, m]  # NaN (see average_down_to) can only reach cells the FillBoundary below overwrites

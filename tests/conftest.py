@@ -11,7 +11,7 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = ["tg12", "sod48", "chcyl", "thermal", "pressure", "slip", "shear", "slipyz", "touch"]
 
 
-AMR_GOLDEN_CASES = ["amr2_tg", "amr2_chcyl", "amr3_chcyl", "amr2_sod", "amr2_sod_regrid", "amr2_tg_appear", "amr2_chcyl_appear"]
+AMR_GOLDEN_CASES = ["amr2_tg", "amr2_chcyl", "amr3_chcyl", "amr2_sod", "amr2_sod_regrid", "amr2_tg_appear", "amr2_chcyl_appear", "amr2_sod_bc"]
 
 
 def pytest_configure(config):

@@ -394,7 +394,16 @@ tagging.box.end_time = 6.5
 AMR_CASES["amr2_chcyl_appear"] = (AMR_CASES["amr2_chcyl"][0].replace("max_step = 4", "max_step = 8") + """tagging.box.start_time = 1.5
 tagging.box.end_time = 5.5
 """, 2, [0, 1, 2, 3, 5, 6, 8])
-AMR_REGRID_INT = {"amr2_sod_regrid": 1, "amr2_tg_appear": 1, "amr2_chcyl_appear": 1}
+# sod_amr.inp itself at reduced size: besides the density tagging, its `bc` box keeps the outflow face at x-lo refined
+# (Tests/test_files/sod_amr/sod_amr.inp:51-57) -- fine boxes TOUCH a non-periodic face; a second box does the same at
+# x-hi.  The coarse-fine interfaces stay x-normal planes away from the faces.
+AMR_CASES["amr2_sod_bc"] = (AMR_CASES["amr2_sod_regrid"][0].replace("max_step = 16", "max_step = 12")
+                            .replace("tagging.refinement_indicators = rho", "tagging.refinement_indicators = rho bc bchi") + """tagging.bc.in_box_lo = -10 -10 -10
+tagging.bc.in_box_hi = 6 10 10
+tagging.bchi.in_box_lo = 59 -10 -10
+tagging.bchi.in_box_hi = 80 10 10
+""", 2, [0, 1, 6, 12])
+AMR_REGRID_INT = {"amr2_sod_regrid": 1, "amr2_tg_appear": 1, "amr2_chcyl_appear": 1, "amr2_sod_bc": 1}
 # steps stored with f and g as well (besides the first and the last): the first step of the new level
 AMR_FULL_STEPS = {"amr2_tg_appear": [4], "amr2_chcyl_appear": [3]}
 
