@@ -818,15 +818,31 @@ int mbl_step_split(mbl_ctx* ctx, int lev, int part)
         cudaEventRecord(e, st);
         ctx->events.push_back(e);
     };
-    // variant 5 keeps carrying through the split: q-corrections from the previous step's partial sums
-    // (k_qcorr_combine; planes next to a ghost plane are pulled as before), collide by k_collide_tile
+    // the carry variants keep carrying through the split: q-corrections from the previous step's partial sums
+    // (k_qcorr_combine*; planes next to a ghost plane are pulled as before), collide by k_collide_tile*
     const bool tile = (ctx->variant == 5 || ctx->variant == 7 || ctx->variant == 9 || ctx->variant == 10) && L.sq * 8 < (1LL << 32);
     const int W = carry_tile_rows(ctx->carry_rows);
+    // variant 9: the z-march kernels; the three plane ranges of the split are chunked on their own -- [0, 2) and
+    // [nz-2, nz) are one chunk each, [2, nz-2) is cut into chunks of zm planes -- and zpos describes that layout
+    const bool zmarch = tile && ctx->variant == 9 && W == 6;
+    int zm = ctx->zmarch > 1 ? ctx->zmarch : 8;
+    while ((nz - 4) % zm == 1) ++zm;
+    const int zkey = -zm;  // layout key of the split (step_local's is +zm)
     if (tile) {
         if (!lv.part) CU(cudaMalloc(&lv.part, (size_t)CARRY_WORDS * L.sq * sizeof(double)));
         if (!lv.edge)
             CU(cudaMalloc(&lv.edge, (size_t)CARRY_EDGE_WORDS * carry_edge_plane(L, 4) * (L.nz + 2 * GZ) * sizeof(double)));
     }
+    if (zmarch) {
+        if (!lv.qc2) {
+            CU(cudaMalloc(&lv.qc2, (size_t)3 * L.sq * sizeof(double)));
+            CU(cudaMemsetAsync(lv.qc2, 0, (size_t)3 * L.sq * sizeof(double), st));
+        }
+        if (!lv.zpos) CU(cudaMalloc(&lv.zpos, (size_t)(nz + 2 * GZ)));
+    }
+    // sums of a z-march step can only be combined with the table of the layout that wrote them (lv.zpos_zm)
+    // (nothing part 0 does changes these, so part 1 decides the same)
+    const bool from_march = lv.carry_valid && lv.part_pair == 2 && lv.edge_rows == 6 && lv.zpos && lv.zpos_zm != 0;
     const bool from_sums = tile && lv.carry_valid && lv.edge_rows == W && !lv.part_pair;
     const CarryPlan C = make_carry_plan(L, ctx->carry_own, ctx->carry_ky);
 #ifdef MBL_EXPERIMENTS
@@ -836,7 +852,10 @@ int mbl_step_split(mbl_ctx* ctx, int lev, int part)
 #endif
     auto q = [&](int ka, int kb) {
         if (march) return;
-        if (from_sums)
+        if (from_march)
+            ctx->launches += launch_qcorr_combine_march(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.part, lv.edge, 6, lv.zpos,
+                                                        lv.p.qc, st, ka, kb);
+        else if (from_sums)
             ctx->launches += launch_qcorr_combine(L, lv.P, lv.p.f[a], lv.p.g[a], lv.p.nbr, lv.part, lv.edge, W, lv.p.qc, st,
                                                   ka, kb);
         else
@@ -850,7 +869,10 @@ int mbl_step_split(mbl_ctx* ctx, int lev, int part)
             return;
         }
 #endif
-        if (tile)
+        if (zmarch)
+            ctx->launches += launch_collide_tile_march(L, lv.P, C, 6, false, zm, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b],
+                                                       lv.p.nbr, lv.p.flag, lv.p.qc, lv.qc2, lv.part, lv.edge, st, ka, kb);
+        else if (tile)
             ctx->launches += launch_collide_tile(L, lv.P, C, W, lv.p.f[a], lv.p.g[a], lv.p.f[b], lv.p.g[b], lv.p.nbr,
                                                  lv.p.flag, lv.p.qc, lv.part, lv.edge, st, ka, kb);
         else
@@ -884,7 +906,22 @@ int mbl_step_split(mbl_ctx* ctx, int lev, int part)
         lv.cur = b;
         lv.carry_valid = tile;
         lv.edge_rows = tile ? W : 0;
-        lv.part_pair = 0;
+        lv.part_pair = zmarch ? 2 : 0;
+        if (zmarch) {
+            std::swap(lv.p.qc, lv.qc2);  // the cells the collide kernels finished are in what is now lv.p.qc
+            if (lv.zpos_zm != zkey) {
+                // the table of the layout the sums now have (the combine launches above used the previous one)
+                std::vector<signed char> zp((size_t)nz + 2 * GZ, 0);
+                zp[0 + GZ] = 1, zp[1 + GZ] = 2, zp[nz - 2 + GZ] = 1, zp[nz - 1 + GZ] = 2;
+                for (int k = 2; k < nz - 2; ++k) {
+                    const int kk = (k - 2) % zm, nk = std::min(zm, nz - 2 - (k - kk));
+                    zp[k + GZ] = kk == 0 ? 1 : kk == nk - 1 ? 2 : 0;
+                }
+                CU(cudaMemcpyAsync(lv.zpos, zp.data(), zp.size(), cudaMemcpyHostToDevice, st));
+                CU(cudaStreamSynchronize(st));
+                lv.zpos_zm = zkey;
+            }
+        }
     }
     CU(cudaGetLastError());
     return 0;
