@@ -161,6 +161,10 @@ int mbl_stream(mbl_ctx* ctx, int lev);
  * macrodata_to_equilibrium + relax_f_to_equilibrium (Source/LBM.cpp:607-618) on the
  * already streamed state */
 int mbl_collide(mbl_ctx* ctx, int lev, int want_macrodata);
+/* LBM::advance(lev) (Source/LBM.cpp:523-544): stream; average_down_to(lev, 1 ghost ring) if level lev+1 is defined;
+ * collide.  On the finest multi-box level the stream and the collide are ONE pass over the boxes (results bit-identical
+ * to the three calls; MBL_AMR_FUSED=0 keeps them apart). */
+int mbl_advance(mbl_ctx* ctx, int lev, int want_macrodata);
 /* LBM::f_to_macrodata(lev) (Source/LBM.cpp:810-906) on the current state */
 int mbl_f_to_macrodata(mbl_ctx* ctx, int lev);
 /* LBM::compute_derived(lev) (Source/LBM.cpp:909-955), needs macrodata */

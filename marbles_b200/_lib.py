@@ -70,6 +70,7 @@ SYMBOLS = {
     "mbl_physbc": (C.c_int, [_P, C.c_int, C.c_double]),
     "mbl_stream": (C.c_int, [_P, C.c_int]),
     "mbl_collide": (C.c_int, [_P, C.c_int, C.c_int]),
+    "mbl_advance": (C.c_int, [_P, C.c_int, C.c_int]),
     "mbl_f_to_macrodata": (C.c_int, [_P, C.c_int]),
     "mbl_compute_derived": (C.c_int, [_P, C.c_int]),
     "mbl_eb_forces": (C.c_int, [_P, C.c_int, _D]),

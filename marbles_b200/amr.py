@@ -176,7 +176,12 @@ class AmrLBM:
         check(self.lib.mbl_average_down(self.ctx, crse_lev, ng))
 
     def advance(self, lev: int, want_macrodata: bool = False):
-        """LBM::advance (Source/LBM.cpp:523-544)"""
+        """LBM::advance (Source/LBM.cpp:523-544): mbl_advance = stream; average_down_to(lev, 1) below a finer level;
+        collide -- one fused pass on the finest level"""
+        check(self.lib.mbl_advance(self.ctx, lev, int(want_macrodata)))
+
+    def advance_unfused(self, lev: int, want_macrodata: bool = False):
+        """the same through the three reference-granular entry points"""
         self.stream(lev)
         if lev < self.finest:
             self.average_down_to(lev, 1)

@@ -582,11 +582,11 @@ int patch_stream(mbl_ctx* ctx, int lev)
     return 0;
 }
 
-static int patch_macro_pass(mbl_ctx* ctx, PatchLevel& L, int want_macro)
+static int patch_macro_pass(mbl_ctx* ctx, PatchLevel& L, int want_macro, bool pull = false)
 {
     const int nb = (int)L.boxes.size();
     if (want_macro && ensure_macro(ctx, L)) return 1;
-    ctx->launches += launch_patch_qcorr(L.set.d, nb, L.set.max_cells, L.cur, L.P, want_macro, ctx->stream);
+    ctx->launches += launch_patch_qcorr(L.set.d, nb, L.set.max_cells, L.cur, L.P, want_macro, ctx->stream, pull);
     fill_boundary(ctx, L, PA_QC, 3, 1);                      // m_macrodata.FillBoundary, LBM.cpp:905 (the comps the
     if (want_macro) fill_boundary(ctx, L, PA_MACRO, MBL_NMACRO, 1);  // gradient reads; all 19 when they are stored)
     return 0;
@@ -601,6 +601,42 @@ int patch_collide(mbl_ctx* ctx, int lev, int want_macro)
     if (want_macro) L->dq_from_macro = false;
     ctx->launches += launch_patch_collide(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->cur, L->G, L->P, want_macro,
                                           ctx->stream);
+    fill_boundary(ctx, *L, PA_F, NQ, PNG);  // LBM.cpp:805-806
+    fill_boundary(ctx, *L, PA_G, NQ, PNG);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// LBM::advance(lev) (LBM.cpp:523-544): stream; average_down_to(lev, 1 ghost ring) when a finer level exists; collide.
+// On a finest level nothing happens between the stream and the collide, and the two are one pass: the q-corrections
+// of the streamed state are computed by pulling (k_patch_qcorr<., true>), then k_patch_advance pulls again and
+// collides.  The FillBoundary between the two passes of the reference (LBM.cpp:603) writes ghost cells that nothing
+// reads before the FillBoundary after the collide writes them again, so it is dropped.  Bit-identical to the un-fused
+// sequence (MBL_AMR_FUSED=0 selects it).
+int patch_advance(mbl_ctx* ctx, int lev, int want_macro)
+{
+    PatchLevel* L = plevel(ctx, lev);
+    if (!L) return 1;
+    const bool finest = lev + 1 >= MAX_LEVELS || !ctx->plev[lev + 1];
+    static const bool fused_ok = !(getenv("MBL_AMR_FUSED") && atoi(getenv("MBL_AMR_FUSED")) == 0);
+    if (!finest || !fused_ok) {
+        if (patch_stream(ctx, lev)) return 1;
+        if (!finest && mbl_average_down(ctx, lev, 1)) return 1;
+        return patch_collide(ctx, lev, want_macro);
+    }
+    cudaStream_t st = ctx->stream;
+    if (patch_macro_pass(ctx, *L, want_macro, true)) return 1;
+    if (want_macro) L->dq_from_macro = false;
+    ctx->launches += launch_patch_advance(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->cur, L->G, L->P, want_macro, st);
+    if (L->any_bound) {
+        // bound FABs stay the current buffers (MultiFab::Copy, LBM.cpp:601)
+        for (const PBox& b : L->set.h) {
+            CU(cudaMemcpyAsync(b.f[L->cur], b.f[1 - L->cur], (size_t)b.sq * NQ * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(b.g[L->cur], b.g[1 - L->cur], (size_t)b.sq * NQ * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        }
+    } else {
+        L->cur = 1 - L->cur;
+    }
     fill_boundary(ctx, *L, PA_F, NQ, PNG);  // LBM.cpp:805-806
     fill_boundary(ctx, *L, PA_G, NQ, PNG);
     CU(cudaGetLastError());

@@ -619,6 +619,16 @@ int mbl_stream(mbl_ctx* ctx, int lev)
     return 0;
 }
 
+// LBM::advance(lev) (LBM.cpp:523-544)
+int mbl_advance(mbl_ctx* ctx, int lev, int want_macro)
+{
+    if (is_patch(ctx, lev)) {
+        CU(cudaSetDevice(ctx->device));
+        return patch_advance(ctx, lev, want_macro);
+    }
+    return mbl_stream(ctx, lev) || mbl_collide(ctx, lev, want_macro);
+}
+
 int mbl_collide(mbl_ctx* ctx, int lev, int want_macro)
 {
     if (is_patch(ctx, lev)) {

@@ -230,7 +230,27 @@ __global__ void __launch_bounds__(64) k_patch_bc(const PBox* __restrict__ tab, i
     }
 }
 
-// LBM::stream on the grown box in pull form (SURVEY App. A.2): buffers [cur] -> [1 - cur]
+// one population of LBM::stream in pull form (LBM.cpp:565-599): -1 where the cell is not fluid or the
+// source lies outside the FAB, the cell's own opposite population where the source is solid (halfway bounce-back)
+__device__ __forceinline__ void patch_pull(const PBox& B, const double* __restrict__ fin, const double* __restrict__ gin,
+                                           long long t, int i, int j, int k, bool fluid, int q, double& vf, double& vg)
+{
+    vf = -1.0, vg = -1.0;  // f_star.setVal(-1), LBM.cpp:565
+    const int is = i - c_dir.ex[q], js = j - c_dir.ey[q], ks = k - c_dir.ez[q];
+    if (fluid && B.in_grown(is, js, ks)) {
+        const long long s = B.cell(is, js, ks);
+        const int fs = B.isfl[s];
+        if (fs == 1) {
+            vf = fin[q * B.sq + s];
+            vg = gin[q * B.sq + s];
+        } else if (fs == 0) {  // LBM.cpp:590-595
+            vf = fin[(long long)c_dir.opp[q] * B.sq + t];
+            vg = gin[(long long)c_dir.opp[q] * B.sq + t];
+        }
+    }
+}
+
+// LBM::stream on the grown box in pull form: buffers [cur] -> [1 - cur]
 __global__ void __launch_bounds__(PT) k_patch_stream(const PBox* __restrict__ tab, int cur)
 {
     const PBox B = tab[blockIdx.y];
@@ -243,19 +263,8 @@ __global__ void __launch_bounds__(PT) k_patch_stream(const PBox* __restrict__ ta
         decode(B, t, i, j, k);
         const bool fluid = B.isfl[t] == 1;
         for (int q = 0; q < NQ; ++q) {
-            double vf = -1.0, vg = -1.0;  // f_star.setVal(-1), LBM.cpp:565
-            const int is = i - c_dir.ex[q], js = j - c_dir.ey[q], ks = k - c_dir.ez[q];
-            if (fluid && B.in_grown(is, js, ks)) {
-                const long long s = B.cell(is, js, ks);
-                const int fs = B.isfl[s];
-                if (fs == 1) {
-                    vf = fin[q * B.sq + s];
-                    vg = gin[q * B.sq + s];
-                } else if (fs == 0) {  // halfway bounce-back: the cell's own opposite population (LBM.cpp:590-595)
-                    vf = fin[(long long)c_dir.opp[q] * B.sq + t];
-                    vg = gin[(long long)c_dir.opp[q] * B.sq + t];
-                }
-            }
+            double vf, vg;
+            patch_pull(B, fin, gin, t, i, j, k, fluid, q, vf, vg);
             fout[q * B.sq + t] = vf;
             gout[q * B.sq + t] = vg;
         }
@@ -263,7 +272,9 @@ __global__ void __launch_bounds__(PT) k_patch_stream(const PBox* __restrict__ ta
 }
 
 // f_to_macrodata on the valid box grown by 1 (LBM.cpp:823-903): QCorr always, all 19 fields on request
-template <bool MACRO>
+// PULL: from the state BEFORE the stream (the populations are pulled as LBM::stream would move them): the first half of
+// the fused advance of a finest level
+template <bool MACRO, bool PULL>
 __global__ void __launch_bounds__(PT) k_patch_qcorr(const PBox* __restrict__ tab, int cur, Phys P)
 {
     const PBox B = tab[blockIdx.y];
@@ -278,8 +289,18 @@ __global__ void __launch_bounds__(PT) k_patch_qcorr(const PBox* __restrict__ tab
         const long long c = B.cell(i, j, k);
         if (B.isfl[c] != 1) continue;
         const long long n = B.sq;
-        const MomF mf = moments_f([&](int q) { return f[q * n + c]; });
-        const MomG mg = moments_g([&](int q) { return g[q * n + c]; });
+        MomF mf;
+        MomG mg;
+        if constexpr (PULL) {
+            double fv[NQ], gv[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) patch_pull(B, f, g, c, i, j, k, true, q, fv[q], gv[q]);
+            mf = moments_f([&](int q) { return fv[q]; });
+            mg = moments_g([&](int q) { return gv[q]; });
+        } else {
+            mf = moments_f([&](int q) { return f[q * n + c]; });
+            mg = moments_g([&](int q) { return g[q * n + c]; });
+        }
         const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
         B.qc[c] = s.qcx;
         B.qc[n + c] = s.qcy;
@@ -357,6 +378,57 @@ __global__ void __launch_bounds__(128) k_patch_collide(const PBox* __restrict__ 
             constexpr int Q = decltype(qc_)::value;
             f[Q * n + c] = fv[Q] + cc.omega * (feq_q<Q>(cc) - fv[Q]);
             g[Q * n + c] = gv[Q] + cc.omega * (geq_q<Q>(cc) - gv[Q]);
+        });
+    }
+}
+
+// Fused LBM::advance of a FINEST level (stream + collide, LBM.cpp:523-544 without the average-down in between):
+// every cell of the grown box pulls its populations as LBM::stream would move them; a valid fluid cell collides them in
+// registers (q-corrections of the streamed state from k_patch_qcorr<., true>), every other cell stores the streamed
+// values -- the ghost cells a neighbour box does not cover keep them, as in the reference, the others are overwritten
+// by the FillBoundary that follows.  Buffers [cur] -> [1 - cur].  Same device functions, same order: bit-identical to
+// k_patch_stream + k_patch_collide.
+template <bool MACRO>
+__global__ void __launch_bounds__(128) k_patch_advance(const PBox* __restrict__ tab, int cur, PGeom G, Phys P)
+{
+    const PBox B = tab[blockIdx.y];
+    const double* __restrict__ fin = B.f[cur];
+    const double* __restrict__ gin = B.g[cur];
+    double* __restrict__ fout = B.f[1 - cur];
+    double* __restrict__ gout = B.g[1 - cur];
+    const long long n = B.sq;
+    for (long long t = (long long)blockIdx.x * 128 + threadIdx.x; t < n; t += (long long)gridDim.x * 128) {
+        int i, j, k;
+        decode(B, t, i, j, k);
+        const bool fluid = B.isfl[t] == 1;
+        double fv[NQ], gv[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) patch_pull(B, fin, gin, t, i, j, k, fluid, q, fv[q], gv[q]);
+        const bool valid = i >= B.lo[0] && i <= B.hi[0] && j >= B.lo[1] && j <= B.hi[1] && k >= B.lo[2] && k <= B.hi[2];
+        if (!(valid && fluid)) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                fout[q * n + t] = fv[q];
+                gout[q * n + t] = gv[q];
+            }
+            continue;
+        }
+        const MomF mf = moments_f([&](int q) { return fv[q]; });
+        const MomG mg = moments_g([&](int q) { return gv[q]; });
+        const Prim s = primitives(mf.rho, mf.jx, mf.jy, mf.jz, mg.e2, P);
+        const double dqx = patch_gradient(B, G, B.qc, t, i, j, k, 0, P.idx[0]);
+        const double dqy = patch_gradient(B, G, B.qc + n, t, i, j, k, 1, P.idx[1]);
+        const double dqz = patch_gradient(B, G, B.qc + 2 * n, t, i, j, k, 2, P.idx[2]);
+        if constexpr (MACRO) {
+            B.macro[23 * n + t] = dqx;
+            B.macro[24 * n + t] = dqy;
+            B.macro[25 * n + t] = dqz;
+        }
+        const Coll cc = collision_coefficients(s, mf, mg, dqx, dqy, dqz, P);
+        static_for<0, NQ>([&](auto qc_) {
+            constexpr int Q = decltype(qc_)::value;
+            fout[Q * n + t] = fv[Q] + cc.omega * (feq_q<Q>(cc) - fv[Q]);
+            gout[Q * n + t] = gv[Q] + cc.omega * (geq_q<Q>(cc) - gv[Q]);
         });
     }
 }
@@ -553,13 +625,30 @@ int launch_patch_stream(const PBox* tab, int nb, long long max_cells, int cur, c
     return 1;
 }
 
-int launch_patch_qcorr(const PBox* tab, int nb, long long max_cells, int cur, const Phys& P, int want_macro, cudaStream_t st)
+int launch_patch_qcorr(const PBox* tab, int nb, long long max_cells, int cur, const Phys& P, int want_macro, cudaStream_t st,
+                       bool pull)
 {
     const dim3 grid(blocks_for(max_cells, PT), nb);
-    if (want_macro)
-        k_patch_qcorr<true><<<grid, PT, 0, st>>>(tab, cur, P);
+    if (pull) {
+        if (want_macro)
+            k_patch_qcorr<true, true><<<grid, PT, 0, st>>>(tab, cur, P);
+        else
+            k_patch_qcorr<false, true><<<grid, PT, 0, st>>>(tab, cur, P);
+    } else if (want_macro)
+        k_patch_qcorr<true, false><<<grid, PT, 0, st>>>(tab, cur, P);
     else
-        k_patch_qcorr<false><<<grid, PT, 0, st>>>(tab, cur, P);
+        k_patch_qcorr<false, false><<<grid, PT, 0, st>>>(tab, cur, P);
+    return 1;
+}
+
+int launch_patch_advance(const PBox* tab, int nb, long long max_cells, int cur, const PGeom& G, const Phys& P, int want_macro,
+                         cudaStream_t st)
+{
+    const dim3 grid(blocks_for(max_cells, 128), nb);
+    if (want_macro)
+        k_patch_advance<true><<<grid, 128, 0, st>>>(tab, cur, G, P);
+    else
+        k_patch_advance<false><<<grid, 128, 0, st>>>(tab, cur, G, P);
     return 1;
 }
 

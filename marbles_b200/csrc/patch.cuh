@@ -69,7 +69,11 @@ int launch_patch_prepass(const PBox* tab, int nb, long long max_cells, int cur, 
 int launch_patch_physbc(const PBox* tab, int nb, long long max_cells, int cur, const PGeom& G, const BcInfo& B,
                         cudaStream_t st);
 int launch_patch_stream(const PBox* tab, int nb, long long max_cells, int cur, cudaStream_t st);
-int launch_patch_qcorr(const PBox* tab, int nb, long long max_cells, int cur, const Phys& P, int want_macro, cudaStream_t st);
+int launch_patch_qcorr(const PBox* tab, int nb, long long max_cells, int cur, const Phys& P, int want_macro, cudaStream_t st,
+                       bool pull = false);
+// fused stream + collide of a finest level: buffers [cur] -> [1 - cur]
+int launch_patch_advance(const PBox* tab, int nb, long long max_cells, int cur, const PGeom& G, const Phys& P, int want_macro,
+                         cudaStream_t st);
 int launch_patch_collide(const PBox* tab, int nb, long long max_cells, int cur, const PGeom& G, const Phys& P, int want_macro,
                          cudaStream_t st);
 int launch_patch_derived(const PBox* tab, int nb, long long max_cells, const PGeom& G, const Phys& P, int with_dq,

@@ -83,6 +83,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--reference", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="the three reference-granular calls instead of mbl_advance's fused pass")
     ap.add_argument("--ref-steps", type=int, default=3)
     args = ap.parse_args()
     nx, ny, nz, mgs = args.nx, args.ny, args.nz, args.mgs
@@ -121,6 +122,8 @@ def main():
         print(json.dumps(out))
         return
 
+    if args.unfused:
+        os.environ["MBL_AMR_FUSED"] = "0"
     import torch
     from marbles_b200.amr import AmrLBM
     from marbles_b200.inputs import parse_deck
@@ -146,7 +149,9 @@ def main():
         f = amr.dense(lev, "f")
         assert np.isfinite(f[~np.isnan(f)]).all()
     out.update({"ms_per_coarse_step": ms, "MLUPS": updates / ms / 1e3, "launches_per_coarse_step": (amr.launches - l0) / args.steps,
-                "setup_s": setup_s, "steps": args.steps})
+                "setup_s": setup_s, "steps": args.steps,
+                "advance": "un-fused (mbl_stream, mbl_average_down, mbl_collide)" if args.unfused else
+                           "mbl_advance (stream + collide fused on the finest level)"})
     print(json.dumps(out))
     amr.close()
 

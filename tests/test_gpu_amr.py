@@ -6,7 +6,7 @@ Tolerance: 1e-12 of the field scale per level step (tests/parity.py)."""
 import numpy as np
 import pytest
 
-from conftest import AMR_GOLDEN_CASES, amr_regrid_actions, load_amr_golden
+from conftest import AMR_GOLDEN_CASES, amr_regrid_actions, load_amr_golden, load_golden
 from parity import compare, scales
 
 pytestmark = pytest.mark.gpu
@@ -125,6 +125,59 @@ def test_amr_random_state_vs_oracle(oracle_mod, case):
     amr.compute_derived()  # post_time_step: vorticity of every level
     worst = compare_levels(amr, lambda lev: o.fields(lev), nsteps, amr.inp)
     print(f"{case}: worst {worst:.2e}")
+    amr.close()
+
+
+@pytest.mark.parametrize("case", ["amr2_chcyl", "amr3_chcyl", "amr2_sod_bc"])
+def test_fused_advance_is_bit_identical_to_the_operator_sequence(case):
+    """mbl_advance fuses the stream and the collide of the finest level into one pass (and drops the FillBoundary in
+    between, whose ghost values nothing reads): every cell of every FAB, ghost cells included, and the macrodata must
+    equal what mbl_stream; mbl_average_down; mbl_collide leave"""
+    a, z, deck_text, steps, boxes, is_fluid = new_amr(case)
+    b, *_ = new_amr(case)
+    b.advance = b.advance_unfused
+    l0 = (a.launches, b.launches)
+    a.step(3, want_macrodata=True)
+    b.step(3, want_macrodata=True)
+    a.compute_derived(), b.compute_derived()
+    assert a.launches - l0[0] < b.launches - l0[1]
+    for lev in range(a.finest + 1):
+        for ib in range(len(a.boxes[lev])):
+            for which in (0, 1):
+                assert np.array_equal(a.get_box(lev, ib, which, ng=3), b.get_box(lev, ib, which, ng=3)), (lev, ib, which)
+        for which in ("macro", "derived"):
+            assert np.array_equal(a.dense(lev, which), b.dense(lev, which), equal_nan=True), (lev, which)
+    a.close()
+    b.close()
+
+
+def test_single_level_many_boxes_matches_single_box(oracle_mod):
+    """a single level cut into many boxes (amr.max_grid_size < domain, as 10 of the 13 shipped decks do): the fused
+    multi-box advance against the single-level oracle on the channel + cylinder deck"""
+    from marbles_b200.amr import AmrLBM
+    from marbles_b200.inputs import parse_deck
+    from parity import compare, scales
+    O = oracle_mod
+    z, deck_text, _ = load_golden("chcyl")
+    fl = z["is_fluid"].astype(np.int32)
+    deck = parse_deck(text=deck_text)
+    n = [int(v) for v in deck["amr.n_cell"]]
+    cuts = [[(a, min(a + 7, n[d] - 1)) for a in range(0, n[d], 8)] for d in range(3)]
+    boxes = [((x[0], y[0], zz[0]), (x[1], y[1], zz[1])) for zz in cuts[2] for y in cuts[1] for x in cuts[0]]
+    amr = AmrLBM(deck, [boxes], [fl])
+    amr.init_data()
+    o = O.Oracle(O.lbm_setup(O.parse_deck(None, deck_text.splitlines())), fl)
+    o.initialize()
+    nsteps = 5
+    o.step(nsteps)
+    amr.step(nsteps, want_macrodata=True)
+    got = amr.fields(0, macro=False)
+    ref = {f"f_{q:02d}": o.f_valid[q] for q in range(27)} | {f"g_{q:02d}": o.g_valid[q] for q in range(27)}
+    worst = 0.0
+    for k, v in ref.items():
+        worst = max(worst, float(np.abs(got[k] - v).max()) / max(float(np.abs(v).max()), 1e-300))
+    print(f"{len(boxes)} boxes: worst {worst:.2e}")
+    assert worst <= 1e-12 * nsteps
     amr.close()
 
 
