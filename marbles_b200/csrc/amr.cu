@@ -619,7 +619,9 @@ int patch_advance(mbl_ctx* ctx, int lev, int want_macro)
     if (!L) return 1;
     const bool finest = lev + 1 >= MAX_LEVELS || !ctx->plev[lev + 1];
     static const bool fused_ok = !(getenv("MBL_AMR_FUSED") && atoi(getenv("MBL_AMR_FUSED")) == 0);
-    if (!finest || !fused_ok) {
+    bool fits = true;  // the fused kernels address a FAB with 32-bit element offsets (27 components)
+    for (const PBox& b : L->set.h) fits = fits && b.sq * NQ < (1LL << 31);
+    if (!finest || !fused_ok || !fits) {
         if (patch_stream(ctx, lev)) return 1;
         if (!finest && mbl_average_down(ctx, lev, 1)) return 1;
         return patch_collide(ctx, lev, want_macro);

@@ -250,6 +250,30 @@ __device__ __forceinline__ void patch_pull(const PBox& B, const double* __restri
     }
 }
 
+// The same for all 27 populations of a cell, in two phases so that no load waits for a branch: first the 27 source
+// flags -> element offsets (component included; -1 = sentinel), then the 54 values
+__device__ __forceinline__ void patch_pull_all(const PBox& B, const double* __restrict__ fin, const double* __restrict__ gin,
+                                               long long t, int i, int j, int k, bool fluid, double (&fv)[NQ], double (&gv)[NQ])
+{
+    int off[NQ];
+    const int n = (int)B.sq, tt = (int)t;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const int is = i - c_dir.ex[q], js = j - c_dir.ey[q], ks = k - c_dir.ez[q];
+        const bool ok = fluid && B.in_grown(is, js, ks);
+        const int s = ok ? (int)B.cell(is, js, ks) : tt;
+        const int fs = ok ? B.isfl[s] : -1;
+        off[q] = fs == 1 ? q * n + s : fs == 0 ? c_dir.opp[q] * n + tt : -1;
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const int o = off[q] < 0 ? tt : off[q];
+        const double a = fin[o], b = gin[o];
+        fv[q] = off[q] < 0 ? -1.0 : a;
+        gv[q] = off[q] < 0 ? -1.0 : b;
+    }
+}
+
 // LBM::stream on the grown box in pull form: buffers [cur] -> [1 - cur]
 __global__ void __launch_bounds__(PT) k_patch_stream(const PBox* __restrict__ tab, int cur)
 {
@@ -293,8 +317,7 @@ __global__ void __launch_bounds__(PT) k_patch_qcorr(const PBox* __restrict__ tab
         MomG mg;
         if constexpr (PULL) {
             double fv[NQ], gv[NQ];
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) patch_pull(B, f, g, c, i, j, k, true, q, fv[q], gv[q]);
+            patch_pull_all(B, f, g, c, i, j, k, true, fv, gv);
             mf = moments_f([&](int q) { return fv[q]; });
             mg = moments_g([&](int q) { return gv[q]; });
         } else {
@@ -402,8 +425,7 @@ __global__ void __launch_bounds__(128) k_patch_advance(const PBox* __restrict__ 
         decode(B, t, i, j, k);
         const bool fluid = B.isfl[t] == 1;
         double fv[NQ], gv[NQ];
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) patch_pull(B, fin, gin, t, i, j, k, fluid, q, fv[q], gv[q]);
+        patch_pull_all(B, fin, gin, t, i, j, k, fluid, fv, gv);
         const bool valid = i >= B.lo[0] && i <= B.hi[0] && j >= B.lo[1] && j <= B.hi[1] && k >= B.lo[2] && k <= B.hi[2];
         if (!(valid && fluid)) {
 #pragma unroll
