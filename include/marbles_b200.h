@@ -203,6 +203,22 @@ int mbl_eb_forces(mbl_ctx* ctx, int lev, double out[3]);
  * ------------------------------------------------------------------------------------------- */
 int mbl_level_define_boxes(mbl_ctx* ctx, int lev, const mbl_level_geom* geom, int nboxes, const int* lo, const int* hi);
 int mbl_level_num_boxes(mbl_ctx* ctx, int lev);
+/* Distributed levels (AMReX: DistributionMapping, one process per GPU).  Every rank passes the WHOLE box list of the
+ * level plus owner[ibox] = the rank that holds the box; only owned boxes get memory here.  The copy-tag lists are
+ * built from the global lists on every rank in the same order; a tag whose two boxes live on different ranks becomes a
+ * piece of one device message per peer and operator (FabArray::FillBoundary / ParallelCopy,
+ * AMReX_FabArrayCommI.H:8-253, AMReX_FabArrayBase.cpp:328-472).  The library packs and unpacks; the caller moves the
+ * messages: mbl_set_exchange registers a function that, for npeers peers, sends send[p] (nsend[p] doubles, device
+ * memory) to peers[p] and receives nrecv[p] doubles from it into recv[p], ordered after the work already queued on
+ * `stream` and complete (or stream-ordered) before it returns -- MPI_Isend/Irecv + Waitall on a CUDA-aware MPI, or
+ * ncclGroupStart / ncclSend / ncclRecv / ncclGroupEnd.  Every rank calls the same operators in the same order.
+ * The _on variants of define / regrid / make_from_coarse take the owner list; the plain ones put every box here. */
+typedef int (*mbl_exchange_fn)(void* user, int npeers, const int* peers, double* const* send, const int64_t* nsend,
+                               double* const* recv, const int64_t* nrecv, void* stream);
+int mbl_set_exchange(mbl_ctx* ctx, int rank, int world, mbl_exchange_fn fn, void* user);
+int mbl_level_define_boxes_on(mbl_ctx* ctx, int lev, const mbl_level_geom* geom, int nboxes, const int* lo, const int* hi,
+                              const int* owner);
+int mbl_level_box_owner(mbl_ctx* ctx, int lev, int ibox);
 /* zero-copy: use the DEVICE memory of an AMReX FAB (27 comps, 3 ghost cells: m_f[lev][mfi].dataPtr()) as box
  * `ibox`'s f (which = 0) or g (which = 1); no ownership transfer.  The library keeps the result of every operator
  * in that memory (a scratch copy is used inside mbl_stream, as the reference's f_star). */
@@ -221,12 +237,15 @@ int mbl_average_down(mbl_ctx* ctx, int crse_lev, int ng);
  * new is_fluid (mbl_box_set_is_fluid) and calls mbl_fill_f_inside_eb (zero in solid cells + FillBoundary,
  * Source/LBM.cpp:1278-1298, 1347-1348). */
 int mbl_level_regrid(mbl_ctx* ctx, int lev, int nboxes, const int* lo, const int* hi);
+int mbl_level_regrid_on(mbl_ctx* ctx, int lev, int nboxes, const int* lo, const int* hi, const int* owner);
 /* LBM::MakeNewLevelFromCoarse (Source/LBM.cpp:1088-1144): a level lev >= 1 that did not exist appears in a regrid.
  * Every cell of the new boxes (valid and ghost, inside the periodically grown domain) gets CellConservativeLinear
  * values from level lev-1 (FillPatchOps::fillpatch_from_coarse, Source/FillPatchOps.H:164-181), then BCFill.  The
  * caller passes is_fluid afterwards (no fill_f_inside_eb here: the reference does not call it for a new level).
  * LBM::ClearLevel (Source/LBM.cpp:1367-1380), a level that vanishes, is mbl_level_clear. */
 int mbl_level_make_from_coarse(mbl_ctx* ctx, int lev, const mbl_level_geom* geom, int nboxes, const int* lo, const int* hi);
+int mbl_level_make_from_coarse_on(mbl_ctx* ctx, int lev, const mbl_level_geom* geom, int nboxes, const int* lo, const int* hi,
+                                  const int* owner);
 int mbl_fill_f_inside_eb(mbl_ctx* ctx, int lev);
 
 /* fused fast path: one coarse step of a single-level run =

@@ -47,6 +47,10 @@ class Layout(C.Structure):
 # every symbol include/marbles_b200.h declares, with its argument types
 _P = C.c_void_p
 _D = C.POINTER(C.c_double)
+# mbl_exchange_fn: (user, npeers, peers[], send[], nsend[], recv[], nrecv[], stream) -> int
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                          C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p)
+
 SYMBOLS = {
     "mbl_last_error": (C.c_char_p, []),
     "mbl_version": (C.c_int, []),
@@ -99,6 +103,13 @@ SYMBOLS = {
     "mbl_average_down": (C.c_int, [_P, C.c_int, C.c_int]),
     "mbl_level_regrid": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mbl_level_make_from_coarse": (C.c_int, [_P, C.c_int, C.POINTER(LevelGeom), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mbl_level_make_from_coarse_on": (C.c_int, [_P, C.c_int, C.POINTER(LevelGeom), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                                C.POINTER(C.c_int)]),
+    "mbl_level_regrid_on": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mbl_level_define_boxes_on": (C.c_int, [_P, C.c_int, C.POINTER(LevelGeom), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                            C.POINTER(C.c_int)]),
+    "mbl_level_box_owner": (C.c_int, [_P, C.c_int, C.c_int]),
+    "mbl_set_exchange": (C.c_int, [_P, C.c_int, C.c_int, EXCHANGE_FN, C.c_void_p]),
     "mbl_fill_f_inside_eb": (C.c_int, [_P, C.c_int]),
     "mbl_launch_count": (C.c_int64, [_P]),
     "mbl_set_variant": (C.c_int, [_P, C.c_int]),

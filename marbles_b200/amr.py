@@ -36,11 +36,20 @@ class AmrLBM:
     """Multi-level lattice-Boltzmann state (all boxes of every level on this rank's B200)."""
 
     def __init__(self, deck, level_boxes, is_fluid=None, *, overrides=None, inputs: LbmInputs | None = None,
-                 device: int = 0, cuda_stream: int | None = None):
+                 device: int = 0, cuda_stream: int | None = None, rank: int = 0, world: int = 1, owners=None,
+                 exchange=None):
         """level_boxes[lev] = [(lo, hi), ...] valid boxes in the index space of level lev (AMReX BoxArray);
         is_fluid[lev] = dense int array over the level domain (component 0 of m_is_fluid on valid cells; ghost
         cells take the value of the cell they lie on, periodic images included, and 1 beyond non-periodic faces)
-        or None -> the analytic body of the deck evaluated at each level's resolution."""
+        or None -> the analytic body of the deck evaluated at each level's resolution.
+
+        Distributed levels (one process per GPU, AMReX's DistributionMapping): every rank passes the whole box lists,
+        `owners(lev, boxes) -> [rank per box]` (default: contiguous runs of the list, `default_owners`) says where each
+        box lives, `exchange(rank, parts, stream)` moves the device messages (marbles_b200/amr_comm.py)."""
+        self.rank, self.world = rank, world
+        self._owners_of = owners or (lambda lev, boxes: default_owners(boxes, world))
+        self._exchange = exchange
+        self.owner: list[list[int]] = []
         if inputs is None:
             d = deck if isinstance(deck, dict) else parse_deck(deck, overrides)
             inputs = lbm_inputs(d)
@@ -59,6 +68,11 @@ class AmrLBM:
         check(self.lib.mbl_create(C.byref(p), device, C.byref(self.ctx)))
         if cuda_stream is not None:
             check(self.lib.mbl_set_stream(self.ctx, C.c_void_p(cuda_stream)))
+        if world > 1:
+            if exchange is None:
+                raise ValueError("distributed levels need an exchange (marbles_b200.amr_comm)")
+            self._exchange_cb = _lib.EXCHANGE_FN(self._exchange_trampoline)  # kept alive with the object
+            check(self.lib.mbl_set_exchange(self.ctx, rank, world, self._exchange_cb, None))
         self.boxes: list[list[tuple]] = []
         self.n: list[list[int]] = []
         self.dt: list[float] = []
@@ -68,6 +82,25 @@ class AmrLBM:
         for lev, bxs in enumerate(level_boxes):
             dense = None if is_fluid is None else is_fluid[lev]
             self.define_level(lev, bxs, dense)
+
+    def _exchange_trampoline(self, user, npeers, peers, send, nsend, recv, nrecv, stream):
+        """mbl_exchange_fn: hands the library's per-peer device messages to the Python exchange object"""
+        try:
+            parts = [(int(peers[i]), int(send[i] or 0), int(nsend[i]), int(recv[i] or 0), int(nrecv[i])) for i in range(npeers)]
+            self._exchange(self.rank, parts, int(stream or 0))
+            return 0
+        except Exception:  # an exception must not unwind through the C frames
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    def _owner_array(self, lev: int, boxes):
+        own = [int(o) for o in self._owners_of(lev, boxes)]
+        assert len(own) == len(boxes) and all(0 <= o < self.world for o in own)
+        return own, (C.c_int * len(own))(*own)
+
+    def is_local(self, lev: int, ib: int) -> bool:
+        return self.owner[lev][ib] == self.rank
 
     # ------------------------------------------------------------------ setup
     def close(self):
@@ -104,15 +137,17 @@ class AmrLBM:
         nb = len(boxes)
         lo = (C.c_int * (3 * nb))(*[v for b in boxes for v in b[0]])
         hi = (C.c_int * (3 * nb))(*[v for b in boxes for v in b[1]])
-        check(self.lib.mbl_level_define_boxes(self.ctx, lev, C.byref(g), nb, lo, hi))
+        own, cown = self._owner_array(lev, boxes)
+        check(self.lib.mbl_level_define_boxes_on(self.ctx, lev, C.byref(g), nb, lo, hi, cown))
         n = [self.inp.n_cell[d] * REF_RATIO ** lev for d in range(3)]
         if lev < len(self.boxes):
-            self.boxes[lev], self.n[lev], self.dt[lev] = boxes, n, g.dt
+            self.boxes[lev], self.n[lev], self.dt[lev], self.owner[lev] = boxes, n, g.dt, own
         else:
             assert lev == len(self.boxes), "levels are defined in order"
             self.boxes.append(boxes)
             self.n.append(n)
             self.dt.append(g.dt)
+            self.owner.append(own)
         self._set_level_is_fluid(lev, is_fluid_dense)
 
     def _set_level_is_fluid(self, lev: int, is_fluid_dense=None):
@@ -128,6 +163,8 @@ class AmrLBM:
         dense = np.asarray(dense)
         all_fluid = bool(dense.min() == 1)
         for ib, (blo, bhi) in enumerate(boxes):
+            if not self.is_local(lev, ib):
+                continue
             nl = [bhi[d] - blo[d] + 1 for d in range(3)]
             if is_fluid_dense is None and not all_fluid:
                 # beyond non-periodic faces: the body evaluated there (EB2 covers the grown domain)
@@ -221,8 +258,9 @@ class AmrLBM:
         nb = len(boxes)
         lo = (C.c_int * (3 * nb))(*[v for b in boxes for v in b[0]])
         hi = (C.c_int * (3 * nb))(*[v for b in boxes for v in b[1]])
-        check(self.lib.mbl_level_regrid(self.ctx, lev, nb, lo, hi))
-        self.boxes[lev] = boxes
+        own, cown = self._owner_array(lev, boxes)
+        check(self.lib.mbl_level_regrid_on(self.ctx, lev, nb, lo, hi, cown))
+        self.boxes[lev], self.owner[lev] = boxes, own
         self._set_level_is_fluid(lev, is_fluid_dense)
         check(self.lib.mbl_fill_f_inside_eb(self.ctx, lev))
 
@@ -235,8 +273,10 @@ class AmrLBM:
         nb = len(boxes)
         lo = (C.c_int * (3 * nb))(*[v for b in boxes for v in b[0]])
         hi = (C.c_int * (3 * nb))(*[v for b in boxes for v in b[1]])
-        check(self.lib.mbl_level_make_from_coarse(self.ctx, lev, C.byref(g), nb, lo, hi))
+        own, cown = self._owner_array(lev, boxes)
+        check(self.lib.mbl_level_make_from_coarse_on(self.ctx, lev, C.byref(g), nb, lo, hi, cown))
         self.boxes.append(boxes)
+        self.owner.append(own)
         self.n.append([self.inp.n_cell[d] * REF_RATIO ** lev for d in range(3)])
         self.dt.append(g.dt)
         self._set_level_is_fluid(lev, is_fluid_dense)
@@ -248,6 +288,7 @@ class AmrLBM:
         self.boxes.pop()
         self.n.pop()
         self.dt.pop()
+        self.owner.pop()
 
     # ------------------------------------------------------------------ access
     def box_shape(self, lev: int, ib: int, ncomp: int, ng: int):
@@ -265,12 +306,14 @@ class AmrLBM:
         check(self.lib.mbl_box_upload(self.ctx, lev, ib, which, _dptr(a), ng))
 
     def dense(self, lev: int, which: str) -> np.ndarray:
-        """valid cells of every box of a level gathered over the level domain (NaN where the level has no box);
-        which = 'f' | 'g' | 'macro' | 'derived'"""
+        """valid cells of every box of a level THIS RANK holds, gathered over the level domain (NaN where the level has
+        no box here; `merge_dense` puts the ranks' arrays together); which = 'f' | 'g' | 'macro' | 'derived'"""
         ncomp = {"f": NQ, "g": NQ, "macro": NMACRO, "derived": NDERIVED}[which]
         n = self.n[lev]
         out = np.full((ncomp, n[2], n[1], n[0]), np.nan)
         for ib, (lo, hi) in enumerate(self.boxes[lev]):
+            if not self.is_local(lev, ib):
+                continue
             a = np.zeros(self.box_shape(lev, ib, ncomp, 0))
             if which in ("f", "g"):
                 check(self.lib.mbl_box_download(self.ctx, lev, ib, 0 if which == "f" else 1, _dptr(a), 0))
@@ -302,3 +345,25 @@ class AmrLBM:
     def ncells(self, lev: int | None = None) -> int:
         levs = range(self.finest + 1) if lev is None else [lev]
         return sum(int(np.prod([hi[d] - lo[d] + 1 for d in range(3)])) for l in levs for lo, hi in self.boxes[l])
+
+
+def default_owners(boxes, world: int):
+    """box -> rank: contiguous runs of the box list with about the same number of cells each (the lists AMReX makes
+    are ordered along a space-filling curve, so a run is a compact region)"""
+    if world <= 1:
+        return [0] * len(boxes)
+    cells = [int(np.prod([hi[d] - lo[d] + 1 for d in range(3)])) for lo, hi in boxes]
+    total, acc, own = float(sum(cells)), 0.0, []
+    for c in cells:
+        own.append(min(world - 1, int((acc + 0.5 * c) * world / total)))
+        acc += c
+    return own
+
+
+def merge_dense(parts):
+    """dense arrays of the ranks (NaN where a rank holds no box) -> one array"""
+    out = np.array(parts[0], copy=True)
+    for p in parts[1:]:
+        m = np.isnan(out)
+        out[m] = np.asarray(p)[m]
+    return out

@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <array>
 #include <cstring>
+#include <initializer_list>
+#include <map>
 
 #include "internal.cuh"
 #include "patch.cuh"
@@ -129,14 +131,28 @@ struct BoxSet {  // a table of FABs with its own memory (a level, or the auxilia
     }
 };
 
+// the tags of one peer's messages: what this rank sends (its boxes are the sources) and receives (destinations)
+struct PeerPart {
+    int peer = -1;
+    CopyTag* d_send = nullptr;
+    CopyTag* d_recv = nullptr;
+    int nsend = 0, nrecv = 0;
+    long long send_cells = 0, recv_cells = 0, send_max = 0, recv_max = 0;
+};
 struct Tags {
-    CopyTag* d = nullptr;
+    CopyTag* d = nullptr;  // tags whose two boxes live on this rank
     int n = 0;
     long long max_cells = 0;
+    std::vector<PeerPart> peers;
     void free_all()
     {
         if (d) cudaFree(d);
         d = nullptr, n = 0;
+        for (PeerPart& p : peers) {
+            if (p.d_send) cudaFree(p.d_send);
+            if (p.d_recv) cudaFree(p.d_recv);
+        }
+        peers.clear();
     }
 };
 
@@ -155,15 +171,56 @@ PBox make_pbox(const HBox& valid, int ng)
     return b;
 }
 
-int upload_tags(const std::vector<CopyTag>& v, Tags& t)
+int to_device(const std::vector<CopyTag>& v, CopyTag*& d)
+{
+    d = nullptr;
+    if (v.empty()) return 0;
+    CU(cudaMalloc(&d, v.size() * sizeof(CopyTag)));
+    CU(cudaMemcpy(d, v.data(), v.size() * sizeof(CopyTag), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// Splits a tag list (global box ids, the same list in the same order on every rank) by where the two boxes live:
+// both here -> local copies; source here -> a piece of the message to the destination's rank; destination here -> a
+// piece of the message from the source's rank.  Sender and receiver walk the same sub-sequence of the list, so the
+// offsets inside a message agree without any handshake.  downer / sowner == nullptr: every box lives here.
+int upload_tags(const std::vector<CopyTag>& v, Tags& t, const std::vector<int>* downer = nullptr,
+                const std::vector<int>* sowner = nullptr, int rank = 0)
 {
     t.free_all();
-    t.n = (int)v.size();
+    std::vector<CopyTag> local;
+    std::map<int, std::pair<std::vector<CopyTag>, std::vector<CopyTag>>> remote;
+    std::map<int, std::pair<long long, long long>> cells;
     t.max_cells = 0;
-    for (const CopyTag& c : v) t.max_cells = std::max(t.max_cells, (long long)c.n[0] * c.n[1] * c.n[2]);
-    if (t.n == 0) return 0;
-    CU(cudaMalloc(&t.d, v.size() * sizeof(CopyTag)));
-    CU(cudaMemcpy(t.d, v.data(), v.size() * sizeof(CopyTag), cudaMemcpyHostToDevice));
+    for (CopyTag c : v) {
+        const int od = downer ? (*downer)[c.dbox] : rank, os = sowner ? (*sowner)[c.sbox] : rank;
+        const long long nc = (long long)c.n[0] * c.n[1] * c.n[2];
+        c.boff = 0;
+        if (od == rank && os == rank) {
+            local.push_back(c);
+            t.max_cells = std::max(t.max_cells, nc);
+        } else if (os == rank) {
+            c.boff = cells[od].first;
+            cells[od].first += nc;
+            remote[od].first.push_back(c);
+        } else if (od == rank) {
+            c.boff = cells[os].second;
+            cells[os].second += nc;
+            remote[os].second.push_back(c);
+        }
+    }
+    t.n = (int)local.size();
+    if (to_device(local, t.d)) return 1;
+    for (auto& kv : remote) {
+        PeerPart p;
+        p.peer = kv.first;
+        p.nsend = (int)kv.second.first.size(), p.nrecv = (int)kv.second.second.size();
+        p.send_cells = cells[kv.first].first, p.recv_cells = cells[kv.first].second;
+        for (const CopyTag& c : kv.second.first) p.send_max = std::max(p.send_max, (long long)c.n[0] * c.n[1] * c.n[2]);
+        for (const CopyTag& c : kv.second.second) p.recv_max = std::max(p.recv_max, (long long)c.n[0] * c.n[1] * c.n[2]);
+        if (to_device(kv.second.first, p.d_send) || to_device(kv.second.second, p.d_recv)) return 1;
+        t.peers.push_back(p);
+    }
     return 0;
 }
 
@@ -207,8 +264,11 @@ struct PatchLevel {
     Phys P;
     BcInfo B;
     mbl_level_geom geom;
-    std::vector<HBox> boxes;
-    BoxSet set;          // the level's FABs (set.pool_* unused: separate pools below)
+    std::vector<HBox> boxes;  // ALL boxes of the level (every rank holds the list)
+    std::vector<int> owner;   // rank that holds each box (AMReX DistributionMapping)
+    int rank = 0;
+    bool local(int n) const { return owner[n] == rank; }
+    BoxSet set;          // the level's FABs (set.pool_* unused: separate pools below); boxes of other ranks have no memory
     int cur = 0;
     double* pool_f[2] = {nullptr, nullptr};
     double* pool_g[2] = {nullptr, nullptr};
@@ -226,11 +286,24 @@ struct PatchLevel {
 
 namespace {
 
-int sync_table(PatchLevel& L)
+// device copy of a box table: a box that lives on another rank has no memory and is EMPTY there (no cells to loop
+// over), so the kernels, which take the whole table, skip it without knowing about ranks
+PBox device_view(const PBox& b)
 {
-    CU(cudaMemcpy(L.set.d, L.set.h.data(), L.set.h.size() * sizeof(PBox), cudaMemcpyHostToDevice));
+    if (b.f[0]) return b;
+    PBox e = b;
+    for (int d = 0; d < 3; ++d) e.lo[d] = 0, e.hi[d] = -1, e.n[d] = 0;
+    e.sy = e.sz = e.sq = 0;
+    return e;
+}
+int upload_table(const std::vector<PBox>& h, PBox* d)
+{
+    std::vector<PBox> v(h.size());
+    for (size_t n = 0; n < h.size(); ++n) v[n] = device_view(h[n]);
+    CU(cudaMemcpy(d, v.data(), v.size() * sizeof(PBox), cudaMemcpyHostToDevice));
     return 0;
 }
+int sync_table(PatchLevel& L) { return upload_table(L.set.h, L.set.d); }
 
 void build_fill_boundary(const PatchLevel& L, int ng, std::vector<CopyTag>& out)
 {
@@ -254,42 +327,47 @@ void build_fill_boundary(const PatchLevel& L, int ng, std::vector<CopyTag>& out)
     }
 }
 
-int alloc_aux(BoxSet& S, const std::vector<HBox>& valid, int ng)
+// auxiliary boxes (one per fine box, living where the fine box lives)
+int alloc_aux(BoxSet& S, const std::vector<HBox>& valid, int ng, const std::vector<int>& owner, int rank)
 {
     S.free_all();
     long long total = 0;
-    for (const HBox& v : valid) {
-        PBox b = make_pbox(v, ng);
-        S.max_cells = std::max(S.max_cells, b.sq);
-        total += b.sq;
+    for (size_t n = 0; n < valid.size(); ++n) {
+        PBox b = make_pbox(valid[n], ng);
+        if (owner[n] == rank) {
+            S.max_cells = std::max(S.max_cells, b.sq);
+            total += b.sq;
+        }
         S.h.push_back(b);
     }
-    CU(cudaMalloc(&S.pool_f, (size_t)total * NQ * sizeof(double)));
-    CU(cudaMalloc(&S.pool_g, (size_t)total * NQ * sizeof(double)));
-    CU(cudaMemset(S.pool_f, 0, (size_t)total * NQ * sizeof(double)));
-    CU(cudaMemset(S.pool_g, 0, (size_t)total * NQ * sizeof(double)));
+    CU(cudaMalloc(&S.pool_f, (size_t)std::max(total, 1LL) * NQ * sizeof(double)));
+    CU(cudaMalloc(&S.pool_g, (size_t)std::max(total, 1LL) * NQ * sizeof(double)));
+    CU(cudaMemset(S.pool_f, 0, (size_t)std::max(total, 1LL) * NQ * sizeof(double)));
+    CU(cudaMemset(S.pool_g, 0, (size_t)std::max(total, 1LL) * NQ * sizeof(double)));
     long long off = 0;
-    for (PBox& b : S.h) {
+    for (size_t n = 0; n < S.h.size(); ++n) {
+        if (owner[n] != rank) continue;
+        PBox& b = S.h[n];
         b.f[0] = b.f[1] = S.pool_f + off * NQ;
         b.g[0] = b.g[1] = S.pool_g + off * NQ;
         off += b.sq;
     }
     CU(cudaMalloc(&S.d, S.h.size() * sizeof(PBox)));
-    CU(cudaMemcpy(S.d, S.h.data(), S.h.size() * sizeof(PBox), cudaMemcpyHostToDevice));
-    return 0;
+    return upload_table(S.h, S.d);
 }
 
 // coarse patches + fine regions of the coarse-fine interpolation into the boxes `fine` (grown by the ghost width):
 // every cell inside dstdomain that no box of `cover` contains.  cover = the level's own valid boxes for a ghost fill
 // (FillPatchTwoLevels, mf == fine level), the OLD level's boxes when a re-made level is filled (RemakeLevel).
-int build_interp(Inter& I, const std::vector<HBox>& fine, const PGeom& FG, int fine_lev, const PatchLevel& Cl,
-                 const std::vector<HBox>& cover)
+int build_interp(Inter& I, const std::vector<HBox>& fine, const std::vector<int>& fine_owner, const PGeom& FG, int fine_lev,
+                 const PatchLevel& Cl, const std::vector<HBox>& cover)
 {
     const int nf = (int)fine.size(), nc = (int)Cl.boxes.size();
+    const int rank = Cl.rank;
     // coarse patches for the interpolation: coarsen(grown fine box) grown by 1 (CellConservativeLinear::CoarseBox)
     std::vector<HBox> cp(nf);
     for (int n = 0; n < nf; ++n) cp[n] = grow(coarsen2(grow(fine[n], PNG)), 1);
-    if (alloc_aux(I.cpatch, cp, 0)) return 1;
+    if (alloc_aux(I.cpatch, cp, 0, fine_owner, rank)) return 1;
     std::vector<CopyTag> c2p;
     const auto shifts_p = periodic_shifts(Cl.G, PNG + 2);
     for (int n = 0; n < nf; ++n)
@@ -300,7 +378,7 @@ int build_interp(Inter& I, const std::vector<HBox>& fine, const PGeom& FG, int f
                 if (r.ok()) c2p.push_back(make_tag(n, j, r, sh));
             }
         }
-    if (upload_tags(c2p, I.c2p)) return 1;
+    if (upload_tags(c2p, I.c2p, &fine_owner, &Cl.owner, rank)) return 1;
     // fine ghost regions the interpolation fills: grown box inside dstdomain (the domain grown by the ghost width in
     // periodic directions) minus the fine level's valid boxes, NOT periodically shifted (FPinfo: complementIn)
     std::vector<RegionTag> regs;
@@ -343,6 +421,7 @@ int build_interp(Inter& I, const std::vector<HBox>& fine, const PGeom& FG, int f
                             return fail("level %d: a coarse-fine interface lies within one coarse cell of a non-periodic "
                                         "domain face; the interpolation there is not supported", fine_lev);
             }
+            if (fine_owner[n] != rank) continue;  // (the check above runs for every box on every rank: same verdict everywhere)
             RegionTag t;
             t.box = n;
             for (int d = 0; d < 3; ++d) t.lo[d] = r.lo[d], t.n[d] = r.hi[d] - r.lo[d] + 1;
@@ -373,7 +452,7 @@ int build_inter(PatchLevel& F, const PatchLevel& Cl)
     for (int n = 0; n < nf; ++n) cfine[n] = coarsen2(F.boxes[n]);
     const std::vector<int> order = hash_order(F.boxes);
     for (int ng = 0; ng < 2; ++ng) {
-        if (alloc_aux(I.avg[ng], cfine, ng)) return 1;
+        if (alloc_aux(I.avg[ng], cfine, ng, F.owner, F.rank)) return 1;
         // (1) cfine.ParallelCopy(crse, src ng 0, dst ng): the reference's copy is not periodic, and cells of the ring
         // that lie outside the domain stay uninitialised there; here they take the periodic image, so that a ring cell
         // whose eight fine cells are all masked hands the coarse cell its own value back (see oracle/amr_oracle.py)
@@ -389,7 +468,7 @@ int build_inter(PatchLevel& F, const PatchLevel& Cl)
                 }
             }
         }
-        if (upload_tags(c2a, I.c2a[ng])) return 1;
+        if (upload_tags(c2a, I.c2a[ng], &F.owner, &Cl.owner, F.rank)) return 1;
         // (2) crse.ParallelCopy(cfine, src ng, dst ng 0, periodicity): tags in CPC order; where the rings of two fine
         // boxes overlap the LAST tag wins, so earlier tags are cut back to what later ones leave
         std::vector<CopyTag> a2c;
@@ -417,9 +496,9 @@ int build_inter(PatchLevel& F, const PatchLevel& Cl)
             }
             for (auto& e : live) a2c.push_back(e.second);
         }
-        if (upload_tags(a2c, I.a2c[ng])) return 1;
+        if (upload_tags(a2c, I.a2c[ng], &Cl.owner, &F.owner, F.rank)) return 1;
     }
-    if (build_interp(I, F.boxes, F.G, F.lev, Cl, F.boxes)) return 1;
+    if (build_interp(I, F.boxes, F.owner, F.G, F.lev, Cl, F.boxes)) return 1;
     I.valid = true;
     F.inter_coarse_generation = Cl.generation;
     return 0;
@@ -436,19 +515,80 @@ int ensure_inter(mbl_ctx* ctx, int fine_lev)
     return build_inter(F, Cl);
 }
 
-int fill_boundary(mbl_ctx* ctx, PatchLevel& L, int arr, int ncomp, int ng)
+// One tag list applied to one or more arrays: the local tags as copies, the remote ones as one message per peer that
+// holds all the arrays (pack, the caller's exchange, unpack)
+struct ArrPair {
+    int darr, sarr, ncomp;
+};
+int run_copy(mbl_ctx* ctx, const PBox* dtab, int dcur, const PBox* stab, int scur, const Tags& t,
+             std::initializer_list<ArrPair> arrs)
 {
-    const Tags& t = ng == 1 ? L.fb1 : L.fb3;
-    ctx->launches += launch_patch_copy(L.set.d, L.cur, L.set.d, L.cur, t.d, t.n, arr, arr, ncomp, t.max_cells, ctx->stream);
+    cudaStream_t st = ctx->stream;
+    for (const ArrPair& a : arrs)
+        ctx->launches += launch_patch_copy(dtab, dcur, stab, scur, t.d, t.n, a.darr, a.sarr, a.ncomp, t.max_cells, st);
+    if (t.peers.empty()) return 0;
+    if (!ctx->exchange) return fail("a distributed level needs mbl_set_exchange");
+    int ncomp = 0;
+    for (const ArrPair& a : arrs) ncomp += a.ncomp;
+    if ((int)ctx->peer_buf.size() < ctx->world) ctx->peer_buf.resize(ctx->world);
+    std::vector<int> peers;
+    std::vector<double*> send, recv;
+    std::vector<int64_t> nsend, nrecv;
+    for (const PeerPart& p : t.peers) {
+        if (p.peer < 0 || p.peer >= ctx->world) return fail("owner rank %d outside the world of %d ranks", p.peer, ctx->world);
+        mbl_ctx::PeerBuf& b = ctx->peer_buf[p.peer];
+        const long long ns = p.send_cells * ncomp, nr = p.recv_cells * ncomp;
+        if (ns > b.cap_send) {
+            CU(cudaStreamSynchronize(st));
+            if (b.send) cudaFree(b.send);
+            CU(cudaMalloc(&b.send, (size_t)ns * sizeof(double)));
+            b.cap_send = ns;
+        }
+        if (nr > b.cap_recv) {
+            CU(cudaStreamSynchronize(st));
+            if (b.recv) cudaFree(b.recv);
+            CU(cudaMalloc(&b.recv, (size_t)nr * sizeof(double)));
+            b.cap_recv = nr;
+        }
+        long long base = 0;
+        for (const ArrPair& a : arrs) {
+            ctx->launches += launch_patch_pack(stab, scur, p.d_send, p.nsend, a.sarr, a.ncomp, p.send_max, b.send, base, true, st);
+            base += p.send_cells * a.ncomp;
+        }
+        peers.push_back(p.peer);
+        send.push_back(b.send), recv.push_back(b.recv);
+        nsend.push_back(ns), nrecv.push_back(nr);
+    }
+    if (ctx->exchange(ctx->exchange_user, (int)peers.size(), peers.data(), send.data(), nsend.data(), recv.data(), nrecv.data(),
+                      (void*)st))
+        return fail("the caller's exchange function failed");
+    for (const PeerPart& p : t.peers) {
+        long long base = 0;
+        for (const ArrPair& a : arrs) {
+            ctx->launches += launch_patch_pack(dtab, dcur, p.d_recv, p.nrecv, a.darr, a.ncomp, p.recv_max, ctx->peer_buf[p.peer].recv,
+                                               base, false, st);
+            base += p.recv_cells * a.ncomp;
+        }
+    }
     return 0;
 }
+
+// FabArray::FillBoundary(periodicity) of one or more arrays of a level over ng ghost cells
+int fill_boundary(mbl_ctx* ctx, PatchLevel& L, std::initializer_list<ArrPair> arrs, int ng)
+{
+    return run_copy(ctx, L.set.d, L.cur, L.set.d, L.cur, ng == 1 ? L.fb1 : L.fb3, arrs);
+}
+int fill_boundary(mbl_ctx* ctx, PatchLevel& L, int arr, int ncomp, int ng) { return fill_boundary(ctx, L, {{arr, arr, ncomp}}, ng); }
+int fill_boundary_fg(mbl_ctx* ctx, PatchLevel& L) { return fill_boundary(ctx, L, {{PA_F, PA_F, NQ}, {PA_G, PA_G, NQ}}, PNG); }
 
 int ensure_macro(mbl_ctx* ctx, PatchLevel& L)
 {
     if (L.pool_macro) return 0;
-    CU(cudaMalloc(&L.pool_macro, (size_t)L.total_cells * NMACRO_ALL * sizeof(double)));
-    CU(cudaMemsetAsync(L.pool_macro, 0, (size_t)L.total_cells * NMACRO_ALL * sizeof(double), ctx->stream));
-    for (size_t n = 0; n < L.set.h.size(); ++n) L.set.h[n].macro = L.pool_macro + L.cell_off[n] * NMACRO_ALL;
+    const size_t tc = (size_t)std::max(L.total_cells, 1LL);
+    CU(cudaMalloc(&L.pool_macro, tc * NMACRO_ALL * sizeof(double)));
+    CU(cudaMemsetAsync(L.pool_macro, 0, tc * NMACRO_ALL * sizeof(double), ctx->stream));
+    for (size_t n = 0; n < L.set.h.size(); ++n)
+        if (L.local((int)n)) L.set.h[n].macro = L.pool_macro + L.cell_off[n] * NMACRO_ALL;
     CU(cudaStreamSynchronize(ctx->stream));
     return sync_table(L);
 }
@@ -519,8 +659,7 @@ int patch_initialize(mbl_ctx* ctx, int lev, const IcInfo& I)
     if (!L) return 1;
     ctx->launches += launch_patch_initialize(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->cur, L->B, I, ctx->stream);
     // initialize_f ends with FillBoundary of f and g (LBM.cpp:1209-1210)
-    fill_boundary(ctx, *L, PA_F, NQ, PNG);
-    fill_boundary(ctx, *L, PA_G, NQ, PNG);
+    if (fill_boundary_fg(ctx, *L)) return 1;
     CU(cudaGetLastError());
     return 0;
 }
@@ -549,12 +688,10 @@ int patch_fillpatch(mbl_ctx* ctx, int lev, double time)
         if (ensure_inter(ctx, lev)) return 1;
         PatchLevel& Cl = *ctx->plev[lev - 1];
         Inter& I = L->inter;
-        for (int arr = PA_F; arr <= PA_G; ++arr)
-            ctx->launches += launch_patch_copy(I.cpatch.d, 0, Cl.set.d, Cl.cur, I.c2p.d, I.c2p.n, arr, arr, NQ, I.c2p.max_cells, st);
+        if (run_copy(ctx, I.cpatch.d, 0, Cl.set.d, Cl.cur, I.c2p, {{PA_F, PA_F, NQ}, {PA_G, PA_G, NQ}})) return 1;
         ctx->launches += launch_patch_interp(L->set.d, L->cur, I.cpatch.d, I.d_regs, I.nregs, I.reg_max, st);
     }
-    fill_boundary(ctx, *L, PA_F, NQ, PNG);
-    fill_boundary(ctx, *L, PA_G, NQ, PNG);
+    if (fill_boundary_fg(ctx, *L)) return 1;
     (void)all_periodic;
     CU(cudaGetLastError());
     return patch_physbc(ctx, lev, time);
@@ -570,14 +707,14 @@ int patch_stream(mbl_ctx* ctx, int lev)
     if (L->any_bound) {
         // bound FABs stay the current buffers: copy the streamed state back (MultiFab::Copy, LBM.cpp:601)
         for (const PBox& b : L->set.h) {
+            if (!b.f[0]) continue;
             CU(cudaMemcpyAsync(b.f[L->cur], b.f[1 - L->cur], (size_t)b.sq * NQ * sizeof(double), cudaMemcpyDeviceToDevice, st));
             CU(cudaMemcpyAsync(b.g[L->cur], b.g[1 - L->cur], (size_t)b.sq * NQ * sizeof(double), cudaMemcpyDeviceToDevice, st));
         }
     } else {
         L->cur = 1 - L->cur;
     }
-    fill_boundary(ctx, *L, PA_F, NQ, PNG);  // LBM.cpp:603
-    fill_boundary(ctx, *L, PA_G, NQ, PNG);
+    if (fill_boundary_fg(ctx, *L)) return 1;  // LBM.cpp:603
     CU(cudaGetLastError());
     return 0;
 }
@@ -587,9 +724,9 @@ static int patch_macro_pass(mbl_ctx* ctx, PatchLevel& L, int want_macro, bool pu
     const int nb = (int)L.boxes.size();
     if (want_macro && ensure_macro(ctx, L)) return 1;
     ctx->launches += launch_patch_qcorr(L.set.d, nb, L.set.max_cells, L.cur, L.P, want_macro, ctx->stream, pull);
-    fill_boundary(ctx, L, PA_QC, 3, 1);                      // m_macrodata.FillBoundary, LBM.cpp:905 (the comps the
-    if (want_macro) fill_boundary(ctx, L, PA_MACRO, MBL_NMACRO, 1);  // gradient reads; all 19 when they are stored)
-    return 0;
+    // m_macrodata.FillBoundary, LBM.cpp:905 (the comps the gradient reads; all 19 when they are stored)
+    if (want_macro) return fill_boundary(ctx, L, {{PA_QC, PA_QC, 3}, {PA_MACRO, PA_MACRO, MBL_NMACRO}}, 1);
+    return fill_boundary(ctx, L, PA_QC, 3, 1);
 }
 
 // LBM::collide(lev) (LBM.cpp:607-618) on the streamed state, in place
@@ -601,8 +738,7 @@ int patch_collide(mbl_ctx* ctx, int lev, int want_macro)
     if (want_macro) L->dq_from_macro = false;
     ctx->launches += launch_patch_collide(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->cur, L->G, L->P, want_macro,
                                           ctx->stream);
-    fill_boundary(ctx, *L, PA_F, NQ, PNG);  // LBM.cpp:805-806
-    fill_boundary(ctx, *L, PA_G, NQ, PNG);
+    if (fill_boundary_fg(ctx, *L)) return 1;  // LBM.cpp:805-806
     CU(cudaGetLastError());
     return 0;
 }
@@ -620,7 +756,7 @@ int patch_advance(mbl_ctx* ctx, int lev, int want_macro)
     const bool finest = lev + 1 >= MAX_LEVELS || !ctx->plev[lev + 1];
     static const bool fused_ok = !(getenv("MBL_AMR_FUSED") && atoi(getenv("MBL_AMR_FUSED")) == 0);
     bool fits = true;  // the fused kernels address a FAB with 32-bit element offsets (27 components)
-    for (const PBox& b : L->set.h) fits = fits && b.sq * NQ < (1LL << 31);
+    for (const PBox& b : L->set.h) fits = fits && b.sq * NQ < (1LL << 31);  // (every rank sees every box: same verdict)
     if (!finest || !fused_ok || !fits) {
         if (patch_stream(ctx, lev)) return 1;
         if (!finest && mbl_average_down(ctx, lev, 1)) return 1;
@@ -633,14 +769,14 @@ int patch_advance(mbl_ctx* ctx, int lev, int want_macro)
     if (L->any_bound) {
         // bound FABs stay the current buffers (MultiFab::Copy, LBM.cpp:601)
         for (const PBox& b : L->set.h) {
+            if (!b.f[0]) continue;
             CU(cudaMemcpyAsync(b.f[L->cur], b.f[1 - L->cur], (size_t)b.sq * NQ * sizeof(double), cudaMemcpyDeviceToDevice, st));
             CU(cudaMemcpyAsync(b.g[L->cur], b.g[1 - L->cur], (size_t)b.sq * NQ * sizeof(double), cudaMemcpyDeviceToDevice, st));
         }
     } else {
         L->cur = 1 - L->cur;
     }
-    fill_boundary(ctx, *L, PA_F, NQ, PNG);  // LBM.cpp:805-806
-    fill_boundary(ctx, *L, PA_G, NQ, PNG);
+    if (fill_boundary_fg(ctx, *L)) return 1;  // LBM.cpp:805-806
     CU(cudaGetLastError());
     return 0;
 }
@@ -673,7 +809,31 @@ int patch_compute_derived(mbl_ctx* ctx, int lev)
 // ---------------------------------------------------------------------------------------------------------
 extern "C" {
 
+int mbl_set_exchange(mbl_ctx* ctx, int rank, int world, mbl_exchange_fn fn, void* user)
+{
+    if (!ctx) return fail("null context");
+    if (world < 1 || rank < 0 || rank >= world) return fail("mbl_set_exchange: rank %d of %d", rank, world);
+    for (int l = 0; l < MAX_LEVELS; ++l)
+        if (ctx->plev[l]) return fail("mbl_set_exchange: call it before the levels are defined");
+    ctx->rank = rank, ctx->world = world;
+    ctx->exchange = fn, ctx->exchange_user = user;
+    return 0;
+}
+
 int mbl_level_define_boxes(mbl_ctx* ctx, int lev, const mbl_level_geom* g, int nboxes, const int* lo, const int* hi)
+{
+    return mbl_level_define_boxes_on(ctx, lev, g, nboxes, lo, hi, nullptr);
+}
+
+int mbl_level_box_owner(mbl_ctx* ctx, int lev, int ibox)
+{
+    PatchLevel* L = plevel(ctx, lev);
+    if (!L || ibox < 0 || ibox >= (int)L->boxes.size()) return -1;
+    return L->owner[ibox];
+}
+
+int mbl_level_define_boxes_on(mbl_ctx* ctx, int lev, const mbl_level_geom* g, int nboxes, const int* lo, const int* hi,
+                              const int* owner)
 {
     if (!ctx || !g || !lo || !hi) return fail("null argument");
     if (lev < 0 || lev >= MAX_LEVELS) return fail("level %d out of range", lev);
@@ -682,6 +842,7 @@ int mbl_level_define_boxes(mbl_ctx* ctx, int lev, const mbl_level_geom* g, int n
     mbl_level_clear(ctx, lev);
     PatchLevel* L = new PatchLevel();
     L->lev = lev;
+    L->rank = ctx->rank;
     L->geom = *g;
     for (int d = 0; d < 3; ++d) {
         L->G.dlo[d] = g->dom_lo[d], L->G.dhi[d] = g->dom_hi[d];
@@ -705,29 +866,39 @@ int mbl_level_define_boxes(mbl_ctx* ctx, int lev, const mbl_level_geom* g, int n
                 delete L;
                 return fail("box %d overlaps another box of the level", n);
             }
+        const int own = owner ? owner[n] : ctx->rank;
+        if (own < 0 || own >= ctx->world) {
+            delete L;
+            return fail("box %d: owner %d outside the world of %d ranks (mbl_set_exchange)", n, own, ctx->world);
+        }
         L->boxes.push_back(b);
+        L->owner.push_back(own);
         PBox p = make_pbox(b, PNG);
-        L->cell_off.push_back(L->total_cells);
-        L->total_cells += p.sq;
-        L->set.max_cells = std::max(L->set.max_cells, p.sq);
+        L->cell_off.push_back(own == ctx->rank ? L->total_cells : -1);
+        if (own == ctx->rank) {
+            L->total_cells += p.sq;
+            L->set.max_cells = std::max(L->set.max_cells, p.sq);
+        }
         L->set.h.push_back(p);
     }
     ctx->plev[lev] = L;
-    const size_t lat = (size_t)L->total_cells * NQ * sizeof(double);
+    const size_t lat = (size_t)std::max(L->total_cells, 1LL) * NQ * sizeof(double);
     for (int n = 0; n < 2; ++n) {
         CU(cudaMalloc(&L->pool_f[n], lat));
         CU(cudaMalloc(&L->pool_g[n], lat));
         CU(cudaMemsetAsync(L->pool_f[n], 0, lat, ctx->stream));
         CU(cudaMemsetAsync(L->pool_g[n], 0, lat, ctx->stream));
     }
-    CU(cudaMalloc(&L->pool_qc, (size_t)L->total_cells * 3 * sizeof(double)));
-    CU(cudaMemsetAsync(L->pool_qc, 0, (size_t)L->total_cells * 3 * sizeof(double), ctx->stream));
-    CU(cudaMalloc(&L->pool_isfl, (size_t)L->total_cells * sizeof(int32_t)));
+    const size_t tc = (size_t)std::max(L->total_cells, 1LL);
+    CU(cudaMalloc(&L->pool_qc, tc * 3 * sizeof(double)));
+    CU(cudaMemsetAsync(L->pool_qc, 0, tc * 3 * sizeof(double), ctx->stream));
+    CU(cudaMalloc(&L->pool_isfl, tc * sizeof(int32_t)));
     {
-        std::vector<int32_t> ones((size_t)L->total_cells, 1);  // all fluid until mbl_box_set_is_fluid says otherwise
+        std::vector<int32_t> ones(tc, 1);  // all fluid until mbl_box_set_is_fluid says otherwise
         CU(cudaMemcpy(L->pool_isfl, ones.data(), ones.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
     for (size_t n = 0; n < L->set.h.size(); ++n) {
+        if (!L->local((int)n)) continue;  // a box of another rank: no memory, empty on the device
         PBox& p = L->set.h[n];
         const long long o = L->cell_off[n];
         for (int c = 0; c < 2; ++c) p.f[c] = L->pool_f[c] + o * NQ, p.g[c] = L->pool_g[c] + o * NQ;
@@ -739,7 +910,7 @@ int mbl_level_define_boxes(mbl_ctx* ctx, int lev, const mbl_level_geom* g, int n
     std::vector<CopyTag> t3, t1;
     build_fill_boundary(*L, PNG, t3);
     build_fill_boundary(*L, 1, t1);
-    if (upload_tags(t3, L->fb3) || upload_tags(t1, L->fb1)) return 1;
+    if (upload_tags(t3, L->fb3, &L->owner, &L->owner, L->rank) || upload_tags(t1, L->fb1, &L->owner, &L->owner, L->rank)) return 1;
     static int generation = 0;
     L->generation = ++generation;
     patch_init_tables();
@@ -760,6 +931,7 @@ int mbl_level_bind(mbl_ctx* ctx, int lev, int ibox, int which, double* device_fa
     PatchLevel* L = plevel(ctx, lev);
     if (!L) return 1;
     if (ibox < 0 || ibox >= (int)L->boxes.size() || !device_fab) return fail("mbl_level_bind: bad argument");
+    if (!L->local(ibox)) return fail("mbl_level_bind: box %d lives on rank %d", ibox, L->owner[ibox]);
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     if (L->cur != 0) {
@@ -767,7 +939,7 @@ int mbl_level_bind(mbl_ctx* ctx, int lev, int ibox, int which, double* device_fa
         for (PBox& b : L->set.h) {
             std::swap(b.f[0], b.f[1]);
             std::swap(b.g[0], b.g[1]);
-        }
+        }  // (boxes of other ranks: null either way)
         L->cur = 0;
     }
     PBox& b = L->set.h[ibox];
@@ -781,6 +953,7 @@ int mbl_box_set_is_fluid(mbl_ctx* ctx, int lev, int ibox, const int32_t* fab, in
     PatchLevel* L = plevel(ctx, lev);
     if (!L) return 1;
     if (ibox < 0 || ibox >= (int)L->boxes.size() || !fab) return fail("mbl_box_set_is_fluid: bad argument");
+    if (!L->local(ibox)) return fail("mbl_box_set_is_fluid: box %d lives on rank %d", ibox, L->owner[ibox]);
     if (ng < PNG) return fail("is_fluid needs %d ghost cells (got %d): out-of-domain values come from the geometry", PNG, ng);
     CU(cudaSetDevice(ctx->device));
     const PBox& b = L->set.h[ibox];
@@ -803,6 +976,7 @@ int mbl_box_upload(mbl_ctx* ctx, int lev, int ibox, int which, const double* fab
     PatchLevel* L = plevel(ctx, lev);
     if (!L) return 1;
     if (ibox < 0 || ibox >= (int)L->boxes.size() || !fab || ng < 0) return fail("mbl_box_upload: bad argument");
+    if (!L->local(ibox)) return fail("mbl_box_upload: box %d lives on rank %d", ibox, L->owner[ibox]);
     CU(cudaSetDevice(ctx->device));
     const PBox& b = L->set.h[ibox];
     if (copy_fab(b, which == MBL_G ? b.g[L->cur] : b.f[L->cur], NQ, const_cast<double*>(fab), ng, true, ctx->stream)) return 1;
@@ -815,6 +989,7 @@ int mbl_box_download(mbl_ctx* ctx, int lev, int ibox, int which, double* fab, in
     PatchLevel* L = plevel(ctx, lev);
     if (!L) return 1;
     if (ibox < 0 || ibox >= (int)L->boxes.size() || !fab || ng < 0) return fail("mbl_box_download: bad argument");
+    if (!L->local(ibox)) return fail("mbl_box_download: box %d lives on rank %d", ibox, L->owner[ibox]);
     CU(cudaSetDevice(ctx->device));
     const PBox& b = L->set.h[ibox];
     if (copy_fab(b, which == MBL_G ? b.g[L->cur] : b.f[L->cur], NQ, fab, ng, false, ctx->stream)) return 1;
@@ -827,6 +1002,7 @@ int mbl_box_download_macrodata(mbl_ctx* ctx, int lev, int ibox, double* fab, int
     PatchLevel* L = plevel(ctx, lev);
     if (!L) return 1;
     if (ibox < 0 || ibox >= (int)L->boxes.size() || !fab || ng < 0) return fail("mbl_box_download_macrodata: bad argument");
+    if (!L->local(ibox)) return fail("mbl_box_download_macrodata: box %d lives on rank %d", ibox, L->owner[ibox]);
     if (!L->pool_macro) return fail("no macrodata yet: call mbl_collide with want_macrodata or mbl_f_to_macrodata");
     CU(cudaSetDevice(ctx->device));
     const PBox& b = L->set.h[ibox];
@@ -843,6 +1019,11 @@ int mbl_box_download_macrodata(mbl_ctx* ctx, int lev, int ibox, double* fab, int
 // mbl_fill_f_inside_eb, as RemakeLevel does.
 int mbl_level_regrid(mbl_ctx* ctx, int lev, int nboxes, const int* lo, const int* hi)
 {
+    return mbl_level_regrid_on(ctx, lev, nboxes, lo, hi, nullptr);
+}
+
+int mbl_level_regrid_on(mbl_ctx* ctx, int lev, int nboxes, const int* lo, const int* hi, const int* owner)
+{
     if (!ctx || !lo || !hi) return fail("null argument");
     if (lev < 1 || lev >= MAX_LEVELS || !ctx->plev[lev] || !ctx->plev[lev - 1])
         return fail("mbl_level_regrid: levels %d and %d must be multi-box levels", lev - 1, lev);
@@ -853,16 +1034,14 @@ int mbl_level_regrid(mbl_ctx* ctx, int lev, int nboxes, const int* lo, const int
     CU(cudaStreamSynchronize(st));
     ctx->plev[lev] = nullptr;  // keep the old level alive while the new one is filled from it
     const mbl_level_geom geom = old->geom;
-    int rc = mbl_level_define_boxes(ctx, lev, &geom, nboxes, lo, hi);
+    int rc = mbl_level_define_boxes_on(ctx, lev, &geom, nboxes, lo, hi, owner);
     PatchLevel* L = ctx->plev[lev];
     if (!rc) {
         PatchLevel& Cl = *ctx->plev[lev - 1];
         Inter tmp;
-        rc = build_interp(tmp, L->boxes, L->G, lev, Cl, old->boxes);
+        rc = build_interp(tmp, L->boxes, L->owner, L->G, lev, Cl, old->boxes);
         if (!rc) {
-            for (int arr = PA_F; arr <= PA_G; ++arr)
-                ctx->launches += launch_patch_copy(tmp.cpatch.d, 0, Cl.set.d, Cl.cur, tmp.c2p.d, tmp.c2p.n, arr, arr, NQ,
-                                                   tmp.c2p.max_cells, st);
+            rc = run_copy(ctx, tmp.cpatch.d, 0, Cl.set.d, Cl.cur, tmp.c2p, {{PA_F, PA_F, NQ}, {PA_G, PA_G, NQ}});
             ctx->launches += launch_patch_interp(L->set.d, L->cur, tmp.cpatch.d, tmp.d_regs, tmp.nregs, tmp.reg_max, st);
             // FillPatchSingleLevel(new, {old}): valid and ghost cells of the new boxes that lie on old valid cells
             std::vector<CopyTag> tags;
@@ -876,12 +1055,9 @@ int mbl_level_regrid(mbl_ctx* ctx, int lev, int nboxes, const int* lo, const int
                     }
                 }
             Tags t;
-            rc = upload_tags(tags, t);
-            if (!rc) {
-                for (int arr = PA_F; arr <= PA_G; ++arr)
-                    ctx->launches += launch_patch_copy(L->set.d, L->cur, old->set.d, old->cur, t.d, t.n, arr, arr, NQ, t.max_cells, st);
-                cudaStreamSynchronize(st);
-            }
+            if (!rc) rc = upload_tags(tags, t, &L->owner, &old->owner, L->rank);
+            if (!rc) rc = run_copy(ctx, L->set.d, L->cur, old->set.d, old->cur, t, {{PA_F, PA_F, NQ}, {PA_G, PA_G, NQ}});
+            cudaStreamSynchronize(st);
             t.free_all();
         }
         cudaStreamSynchronize(st);
@@ -902,6 +1078,12 @@ int mbl_level_regrid(mbl_ctx* ctx, int lev, int nboxes, const int* lo, const int
 // InterpFromCoarseLevel), then the fine BCFill.  No K6 pre-pass, no zeroing of solid cells, no FillBoundary.
 int mbl_level_make_from_coarse(mbl_ctx* ctx, int lev, const mbl_level_geom* geom, int nboxes, const int* lo, const int* hi)
 {
+    return mbl_level_make_from_coarse_on(ctx, lev, geom, nboxes, lo, hi, nullptr);
+}
+
+int mbl_level_make_from_coarse_on(mbl_ctx* ctx, int lev, const mbl_level_geom* geom, int nboxes, const int* lo, const int* hi,
+                                  const int* owner)
+{
     if (!ctx || !geom || !lo || !hi) return fail("null argument");
     if (lev < 1 || lev >= MAX_LEVELS || !ctx->plev[lev - 1])
         return fail("mbl_level_make_from_coarse: level %d must be a multi-box level", lev - 1);
@@ -909,15 +1091,13 @@ int mbl_level_make_from_coarse(mbl_ctx* ctx, int lev, const mbl_level_geom* geom
         return fail("mbl_level_make_from_coarse: level %d exists (mbl_level_regrid re-makes it)", lev);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    if (mbl_level_define_boxes(ctx, lev, geom, nboxes, lo, hi)) return 1;
+    if (mbl_level_define_boxes_on(ctx, lev, geom, nboxes, lo, hi, owner)) return 1;
     PatchLevel* L = ctx->plev[lev];
     PatchLevel& Cl = *ctx->plev[lev - 1];
     Inter tmp;
-    int rc = build_interp(tmp, L->boxes, L->G, lev, Cl, std::vector<HBox>());
+    int rc = build_interp(tmp, L->boxes, L->owner, L->G, lev, Cl, std::vector<HBox>());
     if (!rc) {
-        for (int arr = PA_F; arr <= PA_G; ++arr)
-            ctx->launches += launch_patch_copy(tmp.cpatch.d, 0, Cl.set.d, Cl.cur, tmp.c2p.d, tmp.c2p.n, arr, arr, NQ,
-                                               tmp.c2p.max_cells, st);
+        rc = run_copy(ctx, tmp.cpatch.d, 0, Cl.set.d, Cl.cur, tmp.c2p, {{PA_F, PA_F, NQ}, {PA_G, PA_G, NQ}});
         ctx->launches += launch_patch_interp(L->set.d, L->cur, tmp.cpatch.d, tmp.d_regs, tmp.nregs, tmp.reg_max, st);
     }
     cudaStreamSynchronize(st);
@@ -937,8 +1117,7 @@ int mbl_fill_f_inside_eb(mbl_ctx* ctx, int lev)
     if (!L) return 1;
     CU(cudaSetDevice(ctx->device));
     ctx->launches += launch_patch_zero_solid(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->cur, ctx->stream);
-    fill_boundary(ctx, *L, PA_F, NQ, PNG);
-    fill_boundary(ctx, *L, PA_G, NQ, PNG);
+    if (fill_boundary_fg(ctx, *L)) return 1;
     CU(cudaGetLastError());
     return 0;
 }
@@ -955,13 +1134,9 @@ int mbl_average_down(mbl_ctx* ctx, int crse_lev, int ng)
     Inter& I = F.inter;
     cudaStream_t st = ctx->stream;
     const int nf = (int)F.boxes.size();
-    for (int arr = PA_F; arr <= PA_G; ++arr)
-        ctx->launches += launch_patch_copy(I.avg[ng].d, 0, Cl.set.d, Cl.cur, I.c2a[ng].d, I.c2a[ng].n, arr, arr, NQ,
-                                           I.c2a[ng].max_cells, st);
+    if (run_copy(ctx, I.avg[ng].d, 0, Cl.set.d, Cl.cur, I.c2a[ng], {{PA_F, PA_F, NQ}, {PA_G, PA_G, NQ}})) return 1;
     ctx->launches += launch_patch_avgdown(F.set.d, F.cur, I.avg[ng].d, nf, I.avg[ng].max_cells, ng, st);
-    for (int arr = PA_F; arr <= PA_G; ++arr)
-        ctx->launches += launch_patch_copy(Cl.set.d, Cl.cur, I.avg[ng].d, 0, I.a2c[ng].d, I.a2c[ng].n, arr, arr, NQ,
-                                           I.a2c[ng].max_cells, st);
+    if (run_copy(ctx, Cl.set.d, Cl.cur, I.avg[ng].d, 0, I.a2c[ng], {{PA_F, PA_F, NQ}, {PA_G, PA_G, NQ}})) return 1;
     CU(cudaGetLastError());
     return 0;
 }

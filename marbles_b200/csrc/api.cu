@@ -280,6 +280,11 @@ int mbl_create(const mbl_params* params, int device, mbl_ctx** out)
 
 int mbl_destroy(mbl_ctx* ctx)
 {
+    if (ctx)
+        for (auto& b : ctx->peer_buf) {
+            if (b.send) cudaFree(b.send);
+            if (b.recv) cudaFree(b.recv);
+        }
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     for (int l = 0; l < MAX_LEVELS; ++l) mbl_level_clear(ctx, l);

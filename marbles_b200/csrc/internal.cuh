@@ -95,6 +95,17 @@ struct mbl_ctx {
     cudaStream_t stream = nullptr;
     mbl::Level lev[mbl::MAX_LEVELS];
     mbl::PatchLevel* plev[mbl::MAX_LEVELS] = {};  // multi-box levels (mbl_level_define_boxes), amr.cu
+    // distributed multi-box levels (mbl_set_exchange): this process' rank, the caller's pairwise exchange of device
+    // messages, one send and one receive message per peer (grown on demand)
+    int rank = 0, world = 1;
+    mbl_exchange_fn exchange = nullptr;
+    void* exchange_user = nullptr;
+    struct PeerBuf {
+        double* send = nullptr;
+        double* recv = nullptr;
+        long long cap_send = 0, cap_recv = 0;
+    };
+    std::vector<PeerBuf> peer_buf;
     int64_t launches = 0;
     // implementation of mbl_step: 0 (default, fastest measured): two kernels, k_qcorr + k_collide;
     // 1: persistent TMA-pipelined kernel with both job types; 2: the same kernel, one launch per job type;

@@ -73,6 +73,28 @@ __global__ void __launch_bounds__(PT) k_patch_copy(const PBox* __restrict__ dtab
     }
 }
 
+// pack (to_buf) the source region of every tag into the message, or unpack the message into the destination regions
+__global__ void __launch_bounds__(PT) k_patch_pack(const PBox* __restrict__ tab, int cur, const CopyTag* __restrict__ tags,
+                                                   int arr, int ncomp, double* __restrict__ buf, long long base, int to_buf)
+{
+    const CopyTag T = tags[blockIdx.y];
+    const PBox B = tab[to_buf ? T.sbox : T.dbox];
+    double* __restrict__ a = parr(B, arr, cur);
+    const long long cells = (long long)T.n[0] * T.n[1] * T.n[2];
+    double* __restrict__ m = buf + base + T.boff * ncomp;
+    const int* o = to_buf ? T.s : T.d;
+    for (long long t = (long long)blockIdx.x * PT + threadIdx.x; t < cells; t += (long long)gridDim.x * PT) {
+        const int x = (int)(t % T.n[0]);
+        long long r = t / T.n[0];
+        const int y = (int)(r % T.n[1]), z = (int)(r / T.n[1]);
+        const long long c = B.cell(o[0] + x, o[1] + y, o[2] + z);
+        if (to_buf)
+            for (int q = 0; q < ncomp; ++q) m[q * cells + t] = a[q * B.sq + c];
+        else
+            for (int q = 0; q < ncomp; ++q) a[q * B.sq + c] = m[q * cells + t];
+    }
+}
+
 __global__ void __launch_bounds__(PT) k_patch_fill(const PBox* __restrict__ tab, int cur, int arr, int ncomp, double v)
 {
     const PBox B = tab[blockIdx.y];
@@ -585,6 +607,17 @@ int launch_patch_copy(const PBox* dtab, int dcur, const PBox* stab, int scur, co
     for (int t0 = 0; t0 < ntags; t0 += 65535) {
         const int nt = ntags - t0 < 65535 ? ntags - t0 : 65535;
         k_patch_copy<<<dim3(blocks_for(max_cells, PT), nt), PT, 0, st>>>(dtab, dcur, stab, scur, tags + t0, darr, sarr, ncomp);
+    }
+    return (ntags + 65534) / 65535;
+}
+
+int launch_patch_pack(const PBox* tab, int cur, const CopyTag* tags, int ntags, int arr, int ncomp, long long max_cells,
+                      double* buf, long long base, bool to_buf, cudaStream_t st)
+{
+    if (ntags <= 0) return 0;
+    for (int t0 = 0; t0 < ntags; t0 += 65535) {
+        const int nt = ntags - t0 < 65535 ? ntags - t0 : 65535;
+        k_patch_pack<<<dim3(blocks_for(max_cells, PT), nt), PT, 0, st>>>(tab, cur, tags + t0, arr, ncomp, buf, base, to_buf ? 1 : 0);
     }
     return (ntags + 65534) / 65535;
 }

@@ -46,6 +46,7 @@ struct PGeom {
 struct CopyTag {
     int dbox, sbox;
     int d[3], s[3], n[3];
+    long long boff;  // remote tags: first cell of this tag in the peer's message (cells, not doubles)
 };
 // which array of a PBox a copy / fill touches
 enum PArray { PA_F = 0, PA_G = 1, PA_QC = 2, PA_MACRO = 3 };
@@ -59,6 +60,11 @@ void patch_init_tables();
 
 int launch_patch_copy(const PBox* dtab, int dcur, const PBox* stab, int scur, const CopyTag* tags, int ntags, int darr,
                       int sarr, int ncomp, long long max_cells, cudaStream_t st);
+// the remote half of a copy-tag list: regions of boxes <-> one contiguous message ([tag][comp][cell]); to_buf = pack
+// (source side of the tag), else unpack (destination side).  `base` = doubles already in the message (several arrays
+// share one message), `cells_total` = cells of all tags of the message
+int launch_patch_pack(const PBox* tab, int cur, const CopyTag* tags, int ntags, int arr, int ncomp, long long max_cells,
+                      double* buf, long long base, bool to_buf, cudaStream_t st);
 int launch_patch_fill(const PBox* tab, int nb, long long max_cells, int cur, int arr, int ncomp, double v, cudaStream_t st);
 int launch_patch_initialize(const PBox* tab, int nb, long long max_cells, int cur, const BcInfo& B, const IcInfo& I,
                             cudaStream_t st);

@@ -127,27 +127,54 @@ def main():
     import torch
     from marbles_b200.amr import AmrLBM
     from marbles_b200.inputs import parse_deck
+    # under torchrun: the boxes of both levels spread over the ranks (contiguous runs of the box lists), NCCL exchange
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    exchange = None
+    if world > 1:
+        import torch.distributed as dist
+        from marbles_b200.amr_comm import TorchExchange
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=dev)
+        exchange = TorchExchange(dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
     stream = torch.cuda.current_stream().cuda_stream
     t0 = time.time()
-    amr = AmrLBM(parse_deck(text=DECK.format(max_step=1000000, **deck)), [coarse, fine], cuda_stream=stream)
+    amr = AmrLBM(parse_deck(text=DECK.format(max_step=1000000, **deck)), [coarse, fine], device=local, cuda_stream=stream,
+                 rank=rank, world=world, exchange=exchange)
     amr.init_data()
-    torch.cuda.synchronize()
+    barrier()
     setup_s = time.time() - t0
     for _ in range(max(args.warmup, 1)):
         amr.step(1)
-    torch.cuda.synchronize()
+    barrier()
     l0 = amr.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     amr.step(args.steps)
     e1.record()
-    torch.cuda.synchronize()
+    barrier()
     ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     # sanity: the state is finite and the inlet drives a flow
     import numpy as np
     for lev in range(2):
         f = amr.dense(lev, "f")
         assert np.isfinite(f[~np.isnan(f)]).all()
+    out["n_gpus"] = world
+    if rank != 0:
+        amr.close()
+        return
     out.update({"ms_per_coarse_step": ms, "MLUPS": updates / ms / 1e3, "launches_per_coarse_step": (amr.launches - l0) / args.steps,
                 "setup_s": setup_s, "steps": args.steps,
                 "advance": "un-fused (mbl_stream, mbl_average_down, mbl_collide)" if args.unfused else

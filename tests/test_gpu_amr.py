@@ -181,6 +181,68 @@ def test_single_level_many_boxes_matches_single_box(oracle_mod):
     amr.close()
 
 
+def run_ranks(world, body):
+    """`world` ranks as threads of this process on one device (marbles_b200.amr_comm.ThreadExchange)"""
+    from concurrent.futures import ThreadPoolExecutor
+    from marbles_b200.amr_comm import ThreadExchange
+    ex = ThreadExchange(world, timeout=60.0)
+    with ThreadPoolExecutor(world) as pool:
+        futs = [pool.submit(body, r, ex) for r in range(world)]
+        return [f.result(timeout=600) for f in futs]
+
+
+@pytest.mark.parametrize("case,world", [("amr2_tg", 2), ("amr2_chcyl", 2), ("amr3_chcyl", 3), ("amr2_sod_regrid", 2),
+                                        ("amr2_tg_appear", 3), ("amr2_sod_bc", 2)])
+def test_distributed_levels_match_one_rank(case, world):
+    """Boxes of every level spread over `world` ranks (AMReX's DistributionMapping; here round-robin, the worst case for
+    the message count): FillBoundary, the coarse patches of the interpolation, both copies of the average-down and the
+    old -> new copies of a regrid cross ranks as packed device messages.  Same kernels on the same cells: every FAB of
+    every rank must equal the one-rank run bit for bit, through regrids and levels that appear and vanish."""
+    from marbles_b200.amr import AmrLBM, merge_dense
+    from marbles_b200.inputs import parse_deck
+    z, deck_text, steps, boxes, is_fluid = load_amr_golden(case)
+    existing = [b for b in boxes if b]
+    deck = parse_deck(text=deck_text)
+    nsteps = min(steps[-1], 8)
+    current = {lev: boxes[lev] for lev in range(1, len(boxes))}
+    actions = [amr_regrid_actions(z, done + 1, current) for done in range(nsteps)]  # (the npz reader is not thread-safe)
+
+    def drive(amr):
+        for done in range(nsteps):
+            for lev, what, nb in actions[done]:
+                if what == "make":
+                    amr.make_level_from_coarse(lev, nb, is_fluid[lev])
+                elif what == "remake":
+                    amr.regrid_level(lev, nb, is_fluid[lev])
+                else:
+                    amr.clear_level(lev)
+            amr.step(1, want_macrodata=done + 1 == nsteps)
+        amr.compute_derived()
+        amr.sync()
+        return [{w: amr.dense(lev, w) for w in ("f", "g", "macro", "derived")} for lev in range(amr.finest + 1)]
+
+    one = AmrLBM(deck, existing, is_fluid[:len(existing)])
+    one.init_data()
+    ref = drive(one)
+    one.close()
+
+    def body(rank, ex):
+        amr = AmrLBM(deck, existing, is_fluid[:len(existing)], rank=rank, world=world, exchange=ex,
+                     owners=lambda lev, bxs: [(i + lev) % world for i in range(len(bxs))])
+        amr.init_data()
+        out = drive(amr)
+        nloc = sum(amr.is_local(l, i) for l in range(amr.finest + 1) for i in range(len(amr.boxes[l])))
+        amr.close()
+        return out, nloc
+
+    res = run_ranks(world, body)
+    assert all(r[1] > 0 for r in res), "every rank must hold boxes"
+    for lev in range(len(ref)):
+        for w in ("f", "g", "macro", "derived"):
+            got = merge_dense([r[0][lev][w] for r in res])
+            assert np.array_equal(got, ref[lev][w], equal_nan=True), (case, lev, w)
+
+
 def test_level_bind_is_zero_copy_and_bit_identical():
     """mbl_level_bind: the fine level's boxes live in caller-owned device memory (torch tensors standing in for the
     FABs of an AMReX device-arena MultiFab, 27 comps x 3 ghost cells); every operator leaves its result there"""
