@@ -197,7 +197,7 @@ int mbl_eb_forces(mbl_ctx* ctx, int lev, double out[3]);
  *   mbl_average_down  average_down_with_ghosts / masked_avgdown of level crse_lev + 1 onto crse_lev
  *                   (Source/Utilities.cpp:5-28, Source/Utilities.H:315-350; ng = 1 inside advance, 0 after init)
  * The sub-cycling order (LBM::time_step, Source/LBM.cpp:452-521) stays in the caller.
- * Restrictions: refinement ratio 2; all boxes of a level on this rank; fine boxes may touch a NON-periodic domain
+ * Restrictions: refinement ratio 2; fine boxes may touch a NON-periodic domain
  * face (sod_amr.inp refines its outflow face), but no coarse-fine INTERFACE cell may have its coarse parent on such a
  * face (mbl_fillpatch reports it).
  * ------------------------------------------------------------------------------------------- */
@@ -219,6 +219,12 @@ int mbl_set_exchange(mbl_ctx* ctx, int rank, int world, mbl_exchange_fn fn, void
 int mbl_level_define_boxes_on(mbl_ctx* ctx, int lev, const mbl_level_geom* geom, int nboxes, const int* lo, const int* hi,
                               const int* owner);
 int mbl_level_box_owner(mbl_ctx* ctx, int lev, int ibox);
+/* Host only (no device, no context): the cells a FillBoundary over ng ghost cells of a distributed level moves between
+ * `rank` and every other rank (send_cells[world], recv_cells[world]) and inside the rank -- the split of the copy-tag
+ * list mbl_level_define_boxes_on makes.  What rank a sends to b is what b receives from a. */
+int mbl_fill_boundary_plan(int nboxes, const int* lo, const int* hi, const int* owner, const int dom_lo[3], const int dom_hi[3],
+                           const int periodic[3], int ng, int rank, int world, int64_t* send_cells, int64_t* recv_cells,
+                           int64_t* local_cells);
 /* zero-copy: use the DEVICE memory of an AMReX FAB (27 comps, 3 ghost cells: m_f[lev][mfi].dataPtr()) as box
  * `ibox`'s f (which = 0) or g (which = 1); no ownership transfer.  The library keeps the result of every operator
  * in that memory (a scratch copy is used inside mbl_stream, as the reference's f_star). */

@@ -109,6 +109,9 @@ SYMBOLS = {
     "mbl_level_define_boxes_on": (C.c_int, [_P, C.c_int, C.POINTER(LevelGeom), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                             C.POINTER(C.c_int)]),
     "mbl_level_box_owner": (C.c_int, [_P, C.c_int, C.c_int]),
+    "mbl_fill_boundary_plan": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                         C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mbl_set_exchange": (C.c_int, [_P, C.c_int, C.c_int, EXCHANGE_FN, C.c_void_p]),
     "mbl_fill_f_inside_eb": (C.c_int, [_P, C.c_int]),
     "mbl_launch_count": (C.c_int64, [_P]),

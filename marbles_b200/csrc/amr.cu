@@ -820,6 +820,36 @@ int mbl_set_exchange(mbl_ctx* ctx, int rank, int world, mbl_exchange_fn fn, void
     return 0;
 }
 
+// host only (no device, no context): how many cells the FillBoundary over ng ghost cells of a distributed level moves
+// between `rank` and every other rank -- the split of the tag list that mbl_level_define_boxes_on makes
+int mbl_fill_boundary_plan(int nboxes, const int* lo, const int* hi, const int* owner, const int dom_lo[3], const int dom_hi[3],
+                           const int periodic[3], int ng, int rank, int world, int64_t* send_cells, int64_t* recv_cells,
+                           int64_t* local_cells)
+{
+    if (!lo || !hi || !owner || !send_cells || !recv_cells || nboxes < 1 || world < 1) return fail("mbl_fill_boundary_plan: bad argument");
+    PatchLevel L;
+    for (int d = 0; d < 3; ++d) L.G.dlo[d] = dom_lo[d], L.G.dhi[d] = dom_hi[d], L.G.periodic[d] = periodic[d];
+    for (int n = 0; n < nboxes; ++n) {
+        HBox b;
+        for (int d = 0; d < 3; ++d) b.lo[d] = lo[3 * n + d], b.hi[d] = hi[3 * n + d];
+        if (owner[n] < 0 || owner[n] >= world) return fail("box %d: owner %d outside the world of %d ranks", n, owner[n], world);
+        L.boxes.push_back(b);
+    }
+    std::vector<CopyTag> tags;
+    build_fill_boundary(L, ng, tags);
+    for (int r = 0; r < world; ++r) send_cells[r] = recv_cells[r] = 0;
+    int64_t local = 0;
+    for (const CopyTag& c : tags) {
+        const int64_t nc = (int64_t)c.n[0] * c.n[1] * c.n[2];
+        const int od = owner[c.dbox], os = owner[c.sbox];
+        if (od == rank && os == rank) local += nc;
+        else if (os == rank) send_cells[od] += nc;
+        else if (od == rank) recv_cells[os] += nc;
+    }
+    if (local_cells) *local_cells = local;
+    return 0;
+}
+
 int mbl_level_define_boxes(mbl_ctx* ctx, int lev, const mbl_level_geom* g, int nboxes, const int* lo, const int* hi)
 {
     return mbl_level_define_boxes_on(ctx, lev, g, nboxes, lo, hi, nullptr);
