@@ -348,14 +348,26 @@ class AmrLBM:
 
 
 def default_owners(boxes, world: int):
-    """box -> rank: contiguous runs of the box list with about the same number of cells each (the lists AMReX makes
-    are ordered along a space-filling curve, so a run is a compact region)"""
+    """box -> rank as AMReX's space-filling-curve DistributionMapping does it (AMReX_DistributionMapping.cpp, SFC strategy):
+    the boxes sorted along a Morton curve through their positions, cut into `world` runs of about the same number of
+    cells -- every rank gets a compact region, so the cells that cross ranks are few"""
     if world <= 1:
         return [0] * len(boxes)
-    cells = [int(np.prod([hi[d] - lo[d] + 1 for d in range(3)])) for lo, hi in boxes]
-    total, acc, own = float(sum(cells)), 0.0, []
-    for c in cells:
-        own.append(min(world - 1, int((acc + 0.5 * c) * world / total)))
+    ext = [max(hi[d] - lo[d] + 1 for lo, hi in boxes) for d in range(3)]
+
+    def morton(lo):
+        c = [lo[d] // ext[d] for d in range(3)]
+        key = 0
+        for bit in range(21):
+            for d in range(3):
+                key |= ((c[d] >> bit) & 1) << (3 * bit + d)
+        return key
+
+    order = sorted(range(len(boxes)), key=lambda i: (morton(boxes[i][0]), i))
+    cells = [int(np.prod([boxes[i][1][d] - boxes[i][0][d] + 1 for d in range(3)])) for i in order]
+    total, acc, own = float(sum(cells)), 0.0, [0] * len(boxes)
+    for i, c in zip(order, cells):
+        own[i] = min(world - 1, int((acc + 0.5 * c) * world / total))
         acc += c
     return own
 

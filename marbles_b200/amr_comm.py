@@ -34,13 +34,21 @@ class TorchExchange:
 
     def __init__(self, device, group=None):
         self.device, self.group = device, group
+        self.calls, self.host_s, self.doubles = 0, 0.0, 0  # statistics: exchanges, host time inside them, doubles sent
+        self.timed, self._events = False, []               # timed: CUDA events around every exchange (gpu_ms())
 
     def __call__(self, rank: int, parts, stream: int):
+        import time
+
         import torch
         import torch.distributed as dist
+        t0 = time.perf_counter()
         lib_stream = torch.cuda.ExternalStream(stream, device=self.device) if stream else torch.cuda.default_stream(self.device)
         keep, ops = [], []
         with torch.cuda.stream(lib_stream):
+            if self.timed:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             for peer, sp, ns, rp, nr in parts:
                 if ns:
                     t = dev_tensor(sp, ns, self.device)
@@ -53,6 +61,21 @@ class TorchExchange:
             if ops:
                 for r in dist.batch_isend_irecv(ops):
                     r.wait()  # stream-ordered for NCCL: the unpack kernels queue behind the receives
+            if self.timed:
+                e1.record()
+                self._events.append((e0, e1))
+        self.calls += 1
+        self.host_s += time.perf_counter() - t0
+        self.doubles += sum(p[2] for p in parts)
+
+
+    def gpu_ms(self) -> float:
+        """device time between the start and the end of every timed exchange (waiting for the peer included)"""
+        import torch
+        torch.cuda.synchronize(self.device)
+        ms = sum(a.elapsed_time(b) for a, b in self._events)
+        self._events = []
+        return ms
 
 
 class ThreadExchange:

@@ -240,7 +240,7 @@ CopyTag make_tag(int dbox, int sbox, const HBox& dst_region, const int shift[3])
 struct Inter {
     bool valid = false;
     BoxSet avg[2];        // [ng]: coarsened fine boxes grown by ng (masked average-down, ng = 0 and 1)
-    Tags c2a[2], a2c[2];  // coarse valid -> aux; aux (grown) -> coarse valid, overlaps resolved to "last tag wins"
+    Tags a2c[2];          // aux (grown) -> coarse valid, overlaps resolved to "last tag wins"
     BoxSet cpatch;        // coarsen(grown fine box) grown by 1 (coarse-fine interpolation)
     Tags c2p;
     RegionTag* d_regs = nullptr;
@@ -248,7 +248,7 @@ struct Inter {
     long long reg_max = 0;
     void free_all()
     {
-        for (int n = 0; n < 2; ++n) avg[n].free_all(), c2a[n].free_all(), a2c[n].free_all();
+        for (int n = 0; n < 2; ++n) avg[n].free_all(), a2c[n].free_all();
         cpatch.free_all();
         c2p.free_all();
         if (d_regs) cudaFree(d_regs);
@@ -368,20 +368,10 @@ int build_interp(Inter& I, const std::vector<HBox>& fine, const std::vector<int>
     std::vector<HBox> cp(nf);
     for (int n = 0; n < nf; ++n) cp[n] = grow(coarsen2(grow(fine[n], PNG)), 1);
     if (alloc_aux(I.cpatch, cp, 0, fine_owner, rank)) return 1;
-    std::vector<CopyTag> c2p;
-    const auto shifts_p = periodic_shifts(Cl.G, PNG + 2);
-    for (int n = 0; n < nf; ++n)
-        for (const auto& s : shifts_p) {
-            const int sh[3] = {s[0], s[1], s[2]};
-            for (int j = 0; j < nc; ++j) {
-                const HBox r = isect(cp[n], shifted(Cl.boxes[j], sh));
-                if (r.ok()) c2p.push_back(make_tag(n, j, r, sh));
-            }
-        }
-    if (upload_tags(c2p, I.c2p, &fine_owner, &Cl.owner, rank)) return 1;
     // fine ghost regions the interpolation fills: grown box inside dstdomain (the domain grown by the ghost width in
     // periodic directions) minus the fine level's valid boxes, NOT periodically shifted (FPinfo: complementIn)
     std::vector<RegionTag> regs;
+    std::vector<std::vector<HBox>> needed(nf);  // coarse cells the interpolation of box n reads (disjoint pieces)
     const auto shifts_f = periodic_shifts(FG, PNG);
     for (int n = 0; n < nf; ++n) {
         HBox r0 = grow(fine[n], PNG);
@@ -421,6 +411,15 @@ int build_interp(Inter& I, const std::vector<HBox>& fine, const std::vector<int>
                             return fail("level %d: a coarse-fine interface lies within one coarse cell of a non-periodic "
                                         "domain face; the interpolation there is not supported", fine_lev);
             }
+            {   // parents of the region's cells and their 26 neighbours (slopes, min / max limiting)
+                std::vector<HBox> add{isect(grow(coarsen2(r), 1), cp[n])};
+                for (const HBox& have : needed[n]) {
+                    std::vector<HBox> next;
+                    for (const HBox& a : add) box_diff(a, have, next);
+                    add.swap(next);
+                }
+                for (const HBox& a : add) needed[n].push_back(a);
+            }
             if (fine_owner[n] != rank) continue;  // (the check above runs for every box on every rank: same verdict everywhere)
             RegionTag t;
             t.box = n;
@@ -429,6 +428,20 @@ int build_interp(Inter& I, const std::vector<HBox>& fine, const std::vector<int>
             I.reg_max = std::max(I.reg_max, r.pts());
         }
     }
+    // the coarse level's valid cells (periodic images included) -> the pieces of the coarse patches that are read; a
+    // fine box in the interior of its level has no region and gets nothing
+    std::vector<CopyTag> c2p;
+    const auto shifts_p = periodic_shifts(Cl.G, PNG + 2);
+    for (int n = 0; n < nf; ++n)
+        for (const HBox& piece : needed[n])
+            for (const auto& s : shifts_p) {
+                const int sh[3] = {s[0], s[1], s[2]};
+                for (int j = 0; j < nc; ++j) {
+                    const HBox r = isect(piece, shifted(Cl.boxes[j], sh));
+                    if (r.ok()) c2p.push_back(make_tag(n, j, r, sh));
+                }
+            }
+    if (upload_tags(c2p, I.c2p, &fine_owner, &Cl.owner, rank)) return 1;
     if (I.d_regs) cudaFree(I.d_regs);
     I.d_regs = nullptr;
     I.nregs = (int)regs.size();
@@ -453,22 +466,10 @@ int build_inter(PatchLevel& F, const PatchLevel& Cl)
     const std::vector<int> order = hash_order(F.boxes);
     for (int ng = 0; ng < 2; ++ng) {
         if (alloc_aux(I.avg[ng], cfine, ng, F.owner, F.rank)) return 1;
-        // (1) cfine.ParallelCopy(crse, src ng 0, dst ng): the reference's copy is not periodic, and cells of the ring
-        // that lie outside the domain stay uninitialised there; here they take the periodic image, so that a ring cell
-        // whose eight fine cells are all masked hands the coarse cell its own value back (see oracle/amr_oracle.py)
-        std::vector<CopyTag> c2a;
-        const auto shifts_a = periodic_shifts(Cl.G, ng);
-        for (int n = 0; n < nf; ++n) {
-            const HBox gb = grow(cfine[n], ng);
-            for (const auto& s : shifts_a) {
-                const int sh[3] = {s[0], s[1], s[2]};
-                for (int j = 0; j < nc; ++j) {
-                    const HBox r = isect(gb, shifted(Cl.boxes[j], sh));
-                    if (r.ok()) c2a.push_back(make_tag(n, j, r, sh));
-                }
-            }
-        }
-        if (upload_tags(c2a, I.c2a[ng], &F.owner, &Cl.owner, F.rank)) return 1;
+        // (1) cfine.ParallelCopy(crse, src ng 0, dst ng) is not made: its only effect is that a cell whose eight fine
+        // values are all masked hands the coarse cell its own value back (k_patch_avgdown's KEEP marker does that).  The
+        // reference's copy is not periodic, and ring cells outside the domain stay uninitialised there
+        // (oracle/amr_oracle.py); here they keep the coarse value as well
         // (2) crse.ParallelCopy(cfine, src ng, dst ng 0, periodicity): tags in CPC order; where the rings of two fine
         // boxes overlap the LAST tag wins, so earlier tags are cut back to what later ones leave
         std::vector<CopyTag> a2c;
@@ -521,11 +522,11 @@ struct ArrPair {
     int darr, sarr, ncomp;
 };
 int run_copy(mbl_ctx* ctx, const PBox* dtab, int dcur, const PBox* stab, int scur, const Tags& t,
-             std::initializer_list<ArrPair> arrs)
+             std::initializer_list<ArrPair> arrs, bool skip_keep = false)
 {
     cudaStream_t st = ctx->stream;
     for (const ArrPair& a : arrs)
-        ctx->launches += launch_patch_copy(dtab, dcur, stab, scur, t.d, t.n, a.darr, a.sarr, a.ncomp, t.max_cells, st);
+        ctx->launches += launch_patch_copy(dtab, dcur, stab, scur, t.d, t.n, a.darr, a.sarr, a.ncomp, t.max_cells, st, skip_keep);
     if (t.peers.empty()) return 0;
     if (!ctx->exchange) return fail("a distributed level needs mbl_set_exchange");
     int ncomp = 0;
@@ -566,7 +567,7 @@ int run_copy(mbl_ctx* ctx, const PBox* dtab, int dcur, const PBox* stab, int scu
         long long base = 0;
         for (const ArrPair& a : arrs) {
             ctx->launches += launch_patch_pack(dtab, dcur, p.d_recv, p.nrecv, a.darr, a.ncomp, p.recv_max, ctx->peer_buf[p.peer].recv,
-                                               base, false, st);
+                                               base, false, st, skip_keep);
             base += p.recv_cells * a.ncomp;
         }
     }
@@ -1164,9 +1165,10 @@ int mbl_average_down(mbl_ctx* ctx, int crse_lev, int ng)
     Inter& I = F.inter;
     cudaStream_t st = ctx->stream;
     const int nf = (int)F.boxes.size();
-    if (run_copy(ctx, I.avg[ng].d, 0, Cl.set.d, Cl.cur, I.c2a[ng], {{PA_F, PA_F, NQ}, {PA_G, PA_G, NQ}})) return 1;
+    // (the reference first copies the coarse level into the coarsened fine boxes so that a cell whose eight fine values
+    // are all masked keeps it; here such a cell carries a marker that the copy back does not store)
     ctx->launches += launch_patch_avgdown(F.set.d, F.cur, I.avg[ng].d, nf, I.avg[ng].max_cells, ng, st);
-    if (run_copy(ctx, Cl.set.d, Cl.cur, I.avg[ng].d, 0, I.a2c[ng], {{PA_F, PA_F, NQ}, {PA_G, PA_G, NQ}})) return 1;
+    if (run_copy(ctx, Cl.set.d, Cl.cur, I.avg[ng].d, 0, I.a2c[ng], {{PA_F, PA_F, NQ}, {PA_G, PA_G, NQ}}, true)) return 1;
     CU(cudaGetLastError());
     return 0;
 }

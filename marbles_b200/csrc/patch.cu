@@ -39,6 +39,10 @@ namespace {
 
 constexpr int PT = 256;  // threads per block
 
+// "keep what the destination has": what k_patch_avgdown writes where all eight fine values are masked, and what a copy
+// with skip_keep set does not store.  A quiet NaN with a payload no arithmetic produces.
+constexpr long long KEEP_BITS = 0x7ff84d424c4b4550LL;
+
 __device__ __forceinline__ double* parr(const PBox& b, int arr, int cur)
 {
     return arr == PA_F ? b.f[cur] : arr == PA_G ? b.g[cur] : arr == PA_QC ? b.qc : b.macro;
@@ -57,7 +61,8 @@ __device__ __forceinline__ void decode(const PBox& b, long long t, int& i, int& 
 }
 
 __global__ void __launch_bounds__(PT) k_patch_copy(const PBox* __restrict__ dtab, int dcur, const PBox* __restrict__ stab,
-                                                   int scur, const CopyTag* __restrict__ tags, int darr, int sarr, int ncomp)
+                                                   int scur, const CopyTag* __restrict__ tags, int darr, int sarr, int ncomp,
+                                                   int skip_keep)
 {
     const CopyTag T = tags[blockIdx.y];
     const PBox D = dtab[T.dbox], S = stab[T.sbox];
@@ -69,13 +74,17 @@ __global__ void __launch_bounds__(PT) k_patch_copy(const PBox* __restrict__ dtab
         long long r = t / T.n[0];
         const int b = (int)(r % T.n[1]), c = (int)(r / T.n[1]);
         const long long dc = D.cell(T.d[0] + a, T.d[1] + b, T.d[2] + c), sc = S.cell(T.s[0] + a, T.s[1] + b, T.s[2] + c);
-        for (int q = 0; q < ncomp; ++q) dst[q * D.sq + dc] = src[q * S.sq + sc];
+        for (int q = 0; q < ncomp; ++q) {
+            const double v = src[q * S.sq + sc];
+            if (!skip_keep || __double_as_longlong(v) != KEEP_BITS) dst[q * D.sq + dc] = v;
+        }
     }
 }
 
 // pack (to_buf) the source region of every tag into the message, or unpack the message into the destination regions
 __global__ void __launch_bounds__(PT) k_patch_pack(const PBox* __restrict__ tab, int cur, const CopyTag* __restrict__ tags,
-                                                   int arr, int ncomp, double* __restrict__ buf, long long base, int to_buf)
+                                                   int arr, int ncomp, double* __restrict__ buf, long long base, int to_buf,
+                                                   int skip_keep)
 {
     const CopyTag T = tags[blockIdx.y];
     const PBox B = tab[to_buf ? T.sbox : T.dbox];
@@ -91,7 +100,10 @@ __global__ void __launch_bounds__(PT) k_patch_pack(const PBox* __restrict__ tab,
         if (to_buf)
             for (int q = 0; q < ncomp; ++q) m[q * cells + t] = a[q * B.sq + c];
         else
-            for (int q = 0; q < ncomp; ++q) a[q * B.sq + c] = m[q * cells + t];
+            for (int q = 0; q < ncomp; ++q) {
+                const double v = m[q * cells + t];
+                if (!skip_keep || __double_as_longlong(v) != KEEP_BITS) a[q * B.sq + c] = v;
+            }
     }
 }
 
@@ -505,8 +517,10 @@ __global__ void __launch_bounds__(PT) k_patch_derived(const PBox* __restrict__ t
     }
 }
 
-// masked_avgdown (Utilities.H:315-350): ctab[b] is the coarsened fine box b grown by ng; its arrays f[0], g[0]
-// already hold the coarse level's values (they are kept where all eight fine cells carry the -1 sentinel)
+// masked_avgdown (Utilities.H:315-350): ctab[b] is the coarsened fine box b grown by ng.  Where all eight fine values
+// carry the -1 sentinel the reference keeps the coarse level's value (it copied the coarse level into these boxes
+// first): here the cell gets the KEEP marker and the copy back into the coarse level (skip_keep) leaves the
+// destination alone -- the same result without moving the coarse level into the boxes
 __global__ void __launch_bounds__(PT) k_patch_avgdown(const PBox* __restrict__ ftab, int fcur, const PBox* __restrict__ ctab)
 {
     const PBox F = ftab[blockIdx.y], Cb = ctab[blockIdx.y];
@@ -528,7 +542,7 @@ __global__ void __launch_bounds__(PT) k_patch_avgdown(const PBox* __restrict__ f
                                 vol += 1.0;
                             }
                         }
-                if (vol > 0.0) dst[q * Cb.sq + t] = c / vol;
+                dst[q * Cb.sq + t] = vol > 0.0 ? c / vol : __longlong_as_double(KEEP_BITS);
             }
         }
     }
@@ -601,23 +615,25 @@ inline unsigned blocks_for(long long cells, int threads)
 }  // namespace
 
 int launch_patch_copy(const PBox* dtab, int dcur, const PBox* stab, int scur, const CopyTag* tags, int ntags, int darr,
-                      int sarr, int ncomp, long long max_cells, cudaStream_t st)
+                      int sarr, int ncomp, long long max_cells, cudaStream_t st, bool skip_keep)
 {
     if (ntags <= 0) return 0;
     for (int t0 = 0; t0 < ntags; t0 += 65535) {
         const int nt = ntags - t0 < 65535 ? ntags - t0 : 65535;
-        k_patch_copy<<<dim3(blocks_for(max_cells, PT), nt), PT, 0, st>>>(dtab, dcur, stab, scur, tags + t0, darr, sarr, ncomp);
+        k_patch_copy<<<dim3(blocks_for(max_cells, PT), nt), PT, 0, st>>>(dtab, dcur, stab, scur, tags + t0, darr, sarr, ncomp,
+                                                                         skip_keep ? 1 : 0);
     }
     return (ntags + 65534) / 65535;
 }
 
 int launch_patch_pack(const PBox* tab, int cur, const CopyTag* tags, int ntags, int arr, int ncomp, long long max_cells,
-                      double* buf, long long base, bool to_buf, cudaStream_t st)
+                      double* buf, long long base, bool to_buf, cudaStream_t st, bool skip_keep)
 {
     if (ntags <= 0) return 0;
     for (int t0 = 0; t0 < ntags; t0 += 65535) {
         const int nt = ntags - t0 < 65535 ? ntags - t0 : 65535;
-        k_patch_pack<<<dim3(blocks_for(max_cells, PT), nt), PT, 0, st>>>(tab, cur, tags + t0, arr, ncomp, buf, base, to_buf ? 1 : 0);
+        k_patch_pack<<<dim3(blocks_for(max_cells, PT), nt), PT, 0, st>>>(tab, cur, tags + t0, arr, ncomp, buf, base, to_buf ? 1 : 0,
+                                                                         skip_keep ? 1 : 0);
     }
     return (ntags + 65534) / 65535;
 }

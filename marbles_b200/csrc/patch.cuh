@@ -59,12 +59,13 @@ struct RegionTag {
 void patch_init_tables();
 
 int launch_patch_copy(const PBox* dtab, int dcur, const PBox* stab, int scur, const CopyTag* tags, int ntags, int darr,
-                      int sarr, int ncomp, long long max_cells, cudaStream_t st);
+                      int sarr, int ncomp, long long max_cells, cudaStream_t st, bool skip_keep = false);
 // the remote half of a copy-tag list: regions of boxes <-> one contiguous message ([tag][comp][cell]); to_buf = pack
-// (source side of the tag), else unpack (destination side).  `base` = doubles already in the message (several arrays
+// (source side of the tag), else unpack (destination side); skip_keep: values carrying the KEEP marker of
+// k_patch_avgdown are not stored.  `base` = doubles already in the message (several arrays
 // share one message), `cells_total` = cells of all tags of the message
 int launch_patch_pack(const PBox* tab, int cur, const CopyTag* tags, int ntags, int arr, int ncomp, long long max_cells,
-                      double* buf, long long base, bool to_buf, cudaStream_t st);
+                      double* buf, long long base, bool to_buf, cudaStream_t st, bool skip_keep = false);
 int launch_patch_fill(const PBox* tab, int nb, long long max_cells, int cur, int arr, int ncomp, double v, cudaStream_t st);
 int launch_patch_initialize(const PBox* tab, int nb, long long max_cells, int cur, const BcInfo& B, const IcInfo& I,
                             cudaStream_t st);

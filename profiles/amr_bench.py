@@ -156,12 +156,23 @@ def main():
         amr.step(1)
     barrier()
     l0 = amr.launches
+    if exchange is not None:
+        exchange.calls, exchange.host_s, exchange.doubles = 0, 0.0, 0
+        exchange.timed = True
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw = time.perf_counter()
     e0.record()
     amr.step(args.steps)
     e1.record()
+    host_ms = (time.perf_counter() - tw) * 1e3 / args.steps  # host time to ISSUE a coarse step (launch-bound if ~ ms)
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
+    if exchange is not None:
+        out["exchange_rank0"] = {"calls_per_coarse_step": exchange.calls / args.steps,
+                                 "host_ms_per_coarse_step": exchange.host_s * 1e3 / args.steps,
+                                 "MB_sent_per_coarse_step": exchange.doubles * 8 / 1e6 / args.steps,
+                                 "gpu_ms_per_coarse_step": exchange.gpu_ms() / args.steps}
+    out["host_issue_ms_per_coarse_step"] = host_ms
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

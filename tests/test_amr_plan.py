@@ -74,9 +74,14 @@ def test_default_owners_balance_cells():
     boxes = tiles((64, 32, 16), (16, 16, 8))
     for world in (1, 2, 3, 4, 8):
         own = default_owners(boxes, world)
-        assert own == sorted(own) and set(own) == set(range(world))
+        assert set(own) == set(range(world))
         cells = np.bincount(own, weights=[np.prod([h[d] - l[d] + 1 for d in range(3)]) for l, h in boxes])
         assert cells.max() <= 1.5 * cells.min()
+    # compact regions: fewer cells cross ranks than with runs of the x-fastest box list
+    n, world = (64, 32, 16), 4
+    runs = [min(world - 1, i * world // len(boxes)) for i in range(len(boxes))]
+    cross = lambda own: sum(sum(plan(boxes, own, n, (1, 1, 1), 3, r, world)[0]) for r in range(world))
+    assert cross(default_owners(boxes, world)) < cross(runs)
 
 
 def _worker(rank, world, initfile, outdir):
