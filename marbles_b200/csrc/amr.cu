@@ -117,16 +117,20 @@ std::vector<int> hash_order(const std::vector<HBox>& b)
 
 struct BoxSet {  // a table of FABs with its own memory (a level, or the auxiliary coarse boxes between two levels)
     std::vector<PBox> h;
-    PBox* d = nullptr;
+    PBox* d = nullptr;   // every box of the level, indexed by box id (copy tags, regions); boxes of other ranks are empty
+    PBox* dl = nullptr;  // the boxes that live here, packed: what the one-launch-per-level kernels walk (blockIdx.y)
+    int nl = 0;
+    long long max_face = 0;  // cells of the largest 3-cell-thick face slab of a local box (grid size of the BC kernels)
     double* pool_f = nullptr;  // aux sets: one f and one g buffer per box
     double* pool_g = nullptr;
     long long max_cells = 0;
     void free_all()
     {
         if (d) cudaFree(d);
+        if (dl) cudaFree(dl);
         if (pool_f) cudaFree(pool_f);
         if (pool_g) cudaFree(pool_g);
-        d = nullptr, pool_f = pool_g = nullptr;
+        d = dl = nullptr, pool_f = pool_g = nullptr, nl = 0;
         h.clear();
     }
 };
@@ -296,14 +300,25 @@ PBox device_view(const PBox& b)
     e.sy = e.sz = e.sq = 0;
     return e;
 }
-int upload_table(const std::vector<PBox>& h, PBox* d)
+int upload_table(BoxSet& S)
 {
-    std::vector<PBox> v(h.size());
-    for (size_t n = 0; n < h.size(); ++n) v[n] = device_view(h[n]);
-    CU(cudaMemcpy(d, v.data(), v.size() * sizeof(PBox), cudaMemcpyHostToDevice));
+    std::vector<PBox> v(S.h.size()), loc;
+    for (size_t n = 0; n < S.h.size(); ++n) {
+        v[n] = device_view(S.h[n]);
+        if (S.h[n].f[0]) {
+            loc.push_back(S.h[n]);
+            const long long a = S.h[n].n[0], b = S.h[n].n[1], c = S.h[n].n[2];
+            S.max_face = std::max(S.max_face, PNG * std::max(a * b, std::max(a * c, b * c)));
+        }
+    }
+    if (!S.d) CU(cudaMalloc(&S.d, std::max<size_t>(v.size(), 1) * sizeof(PBox)));
+    if (!S.dl) CU(cudaMalloc(&S.dl, std::max<size_t>(v.size(), 1) * sizeof(PBox)));
+    CU(cudaMemcpy(S.d, v.data(), v.size() * sizeof(PBox), cudaMemcpyHostToDevice));
+    if (!loc.empty()) CU(cudaMemcpy(S.dl, loc.data(), loc.size() * sizeof(PBox), cudaMemcpyHostToDevice));
+    S.nl = (int)loc.size();
     return 0;
 }
-int sync_table(PatchLevel& L) { return upload_table(L.set.h, L.set.d); }
+int sync_table(PatchLevel& L) { return upload_table(L.set); }
 
 void build_fill_boundary(const PatchLevel& L, int ng, std::vector<CopyTag>& out)
 {
@@ -352,8 +367,7 @@ int alloc_aux(BoxSet& S, const std::vector<HBox>& valid, int ng, const std::vect
         b.g[0] = b.g[1] = S.pool_g + off * NQ;
         off += b.sq;
     }
-    CU(cudaMalloc(&S.d, S.h.size() * sizeof(PBox)));
-    return upload_table(S.h, S.d);
+    return upload_table(S);
 }
 
 // coarse patches + fine regions of the coarse-fine interpolation into the boxes `fine` (grown by the ghost width):
@@ -658,7 +672,7 @@ int patch_initialize(mbl_ctx* ctx, int lev, const IcInfo& I)
 {
     PatchLevel* L = plevel(ctx, lev);
     if (!L) return 1;
-    ctx->launches += launch_patch_initialize(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->cur, L->B, I, ctx->stream);
+    ctx->launches += launch_patch_initialize(L->set.dl, L->set.nl, L->set.max_cells, L->cur, L->B, I, ctx->stream);
     // initialize_f ends with FillBoundary of f and g (LBM.cpp:1209-1210)
     if (fill_boundary_fg(ctx, *L)) return 1;
     CU(cudaGetLastError());
@@ -669,7 +683,7 @@ int patch_physbc(mbl_ctx* ctx, int lev, double /*time*/)
 {
     PatchLevel* L = plevel(ctx, lev);
     if (!L) return 1;
-    ctx->launches += launch_patch_physbc(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->cur, L->G, L->B, ctx->stream);
+    ctx->launches += launch_patch_physbc(L->set.dl, L->set.nl, L->set.max_face, L->cur, L->G, L->B, ctx->stream);
     CU(cudaGetLastError());
     return 0;
 }
@@ -682,7 +696,7 @@ int patch_fillpatch(mbl_ctx* ctx, int lev, double time)
     const int nb = (int)L->boxes.size();
     cudaStream_t st = ctx->stream;
     const bool all_periodic = L->G.periodic[0] && L->G.periodic[1] && L->G.periodic[2];
-    ctx->launches += launch_patch_prepass(L->set.d, nb, L->set.max_cells, L->cur, L->G, st);  // K6
+    ctx->launches += launch_patch_prepass(L->set.dl, L->set.nl, L->set.max_cells, L->cur, L->G, st);  // K6
     if (lev > 0) {
         // FillPatchTwoLevels: coarse patch from the coarse level's valid cells, CellConservativeLinear into the fine
         // ghost cells no fine valid cell covers
@@ -704,7 +718,7 @@ int patch_stream(mbl_ctx* ctx, int lev)
     PatchLevel* L = plevel(ctx, lev);
     if (!L) return 1;
     cudaStream_t st = ctx->stream;
-    ctx->launches += launch_patch_stream(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->cur, st);
+    ctx->launches += launch_patch_stream(L->set.dl, L->set.nl, L->set.max_cells, L->cur, st);
     if (L->any_bound) {
         // bound FABs stay the current buffers: copy the streamed state back (MultiFab::Copy, LBM.cpp:601)
         for (const PBox& b : L->set.h) {
@@ -724,7 +738,7 @@ static int patch_macro_pass(mbl_ctx* ctx, PatchLevel& L, int want_macro, bool pu
 {
     const int nb = (int)L.boxes.size();
     if (want_macro && ensure_macro(ctx, L)) return 1;
-    ctx->launches += launch_patch_qcorr(L.set.d, nb, L.set.max_cells, L.cur, L.P, want_macro, ctx->stream, pull);
+    ctx->launches += launch_patch_qcorr(L.set.dl, L.set.nl, L.set.max_cells, L.cur, L.P, want_macro, ctx->stream, pull);
     // m_macrodata.FillBoundary, LBM.cpp:905 (the comps the gradient reads; all 19 when they are stored)
     if (want_macro) return fill_boundary(ctx, L, {{PA_QC, PA_QC, 3}, {PA_MACRO, PA_MACRO, MBL_NMACRO}}, 1);
     return fill_boundary(ctx, L, PA_QC, 3, 1);
@@ -737,7 +751,7 @@ int patch_collide(mbl_ctx* ctx, int lev, int want_macro)
     if (!L) return 1;
     if (patch_macro_pass(ctx, *L, want_macro)) return 1;
     if (want_macro) L->dq_from_macro = false;
-    ctx->launches += launch_patch_collide(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->cur, L->G, L->P, want_macro,
+    ctx->launches += launch_patch_collide(L->set.dl, L->set.nl, L->set.max_cells, L->cur, L->G, L->P, want_macro,
                                           ctx->stream);
     if (fill_boundary_fg(ctx, *L)) return 1;  // LBM.cpp:805-806
     CU(cudaGetLastError());
@@ -766,7 +780,7 @@ int patch_advance(mbl_ctx* ctx, int lev, int want_macro)
     cudaStream_t st = ctx->stream;
     if (patch_macro_pass(ctx, *L, want_macro, true)) return 1;
     if (want_macro) L->dq_from_macro = false;
-    ctx->launches += launch_patch_advance(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->cur, L->G, L->P, want_macro, st);
+    ctx->launches += launch_patch_advance(L->set.dl, L->set.nl, L->set.max_cells, L->cur, L->G, L->P, want_macro, st);
     if (L->any_bound) {
         // bound FABs stay the current buffers (MultiFab::Copy, LBM.cpp:601)
         for (const PBox& b : L->set.h) {
@@ -797,7 +811,7 @@ int patch_compute_derived(mbl_ctx* ctx, int lev)
     PatchLevel* L = plevel(ctx, lev);
     if (!L) return 1;
     if (!L->pool_macro) return fail("mbl_compute_derived needs macrodata");
-    ctx->launches += launch_patch_derived(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->G, L->P, L->dq_from_macro ? 1 : 0,
+    ctx->launches += launch_patch_derived(L->set.dl, L->set.nl, L->set.max_cells, L->G, L->P, L->dq_from_macro ? 1 : 0,
                                           ctx->stream);
     CU(cudaGetLastError());
     return 0;
@@ -936,7 +950,6 @@ int mbl_level_define_boxes_on(mbl_ctx* ctx, int lev, const mbl_level_geom* g, in
         p.qc = L->pool_qc + o * 3;
         p.isfl = L->pool_isfl + o;
     }
-    CU(cudaMalloc(&L->set.d, L->set.h.size() * sizeof(PBox)));
     if (sync_table(*L)) return 1;
     std::vector<CopyTag> t3, t1;
     build_fill_boundary(*L, PNG, t3);
@@ -1061,7 +1074,7 @@ int mbl_level_regrid_on(mbl_ctx* ctx, int lev, int nboxes, const int* lo, const 
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     PatchLevel* old = ctx->plev[lev];
-    ctx->launches += launch_patch_prepass(old->set.d, (int)old->boxes.size(), old->set.max_cells, old->cur, old->G, st);
+    ctx->launches += launch_patch_prepass(old->set.dl, old->set.nl, old->set.max_cells, old->cur, old->G, st);
     CU(cudaStreamSynchronize(st));
     ctx->plev[lev] = nullptr;  // keep the old level alive while the new one is filled from it
     const mbl_level_geom geom = old->geom;
@@ -1147,7 +1160,7 @@ int mbl_fill_f_inside_eb(mbl_ctx* ctx, int lev)
     PatchLevel* L = plevel(ctx, lev);
     if (!L) return 1;
     CU(cudaSetDevice(ctx->device));
-    ctx->launches += launch_patch_zero_solid(L->set.d, (int)L->boxes.size(), L->set.max_cells, L->cur, ctx->stream);
+    ctx->launches += launch_patch_zero_solid(L->set.dl, L->set.nl, L->set.max_cells, L->cur, ctx->stream);
     if (fill_boundary_fg(ctx, *L)) return 1;
     CU(cudaGetLastError());
     return 0;
@@ -1167,7 +1180,7 @@ int mbl_average_down(mbl_ctx* ctx, int crse_lev, int ng)
     const int nf = (int)F.boxes.size();
     // (the reference first copies the coarse level into the coarsened fine boxes so that a cell whose eight fine values
     // are all masked keeps it; here such a cell carries a marker that the copy back does not store)
-    ctx->launches += launch_patch_avgdown(F.set.d, F.cur, I.avg[ng].d, nf, I.avg[ng].max_cells, ng, st);
+    ctx->launches += launch_patch_avgdown(F.set.dl, F.cur, I.avg[ng].dl, F.set.nl, I.avg[ng].max_cells, ng, st);
     if (run_copy(ctx, Cl.set.d, Cl.cur, I.avg[ng].d, 0, I.a2c[ng], {{PA_F, PA_F, NQ}, {PA_G, PA_G, NQ}}, true)) return 1;
     CU(cudaGetLastError());
     return 0;

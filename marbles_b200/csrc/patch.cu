@@ -640,6 +640,7 @@ int launch_patch_pack(const PBox* tab, int cur, const CopyTag* tags, int ntags, 
 
 int launch_patch_fill(const PBox* tab, int nb, long long max_cells, int cur, int arr, int ncomp, double v, cudaStream_t st)
 {
+    if (nb <= 0) return 0;  // this rank holds no box of the level
     k_patch_fill<<<dim3(blocks_for(max_cells * ncomp, PT), nb), PT, 0, st>>>(tab, cur, arr, ncomp, v);
     return 1;
 }
@@ -647,29 +648,33 @@ int launch_patch_fill(const PBox* tab, int nb, long long max_cells, int cur, int
 int launch_patch_initialize(const PBox* tab, int nb, long long max_cells, int cur, const BcInfo& B, const IcInfo& I,
                             cudaStream_t st)
 {
+    if (nb <= 0) return 0;  // this rank holds no box of the level
     k_patch_initialize<<<dim3(blocks_for(max_cells, PT), nb), PT, 0, st>>>(tab, cur, B, I);
     return 1;
 }
 
 int launch_patch_zero_solid(const PBox* tab, int nb, long long max_cells, int cur, cudaStream_t st)
 {
+    if (nb <= 0) return 0;  // this rank holds no box of the level
     k_patch_zero_solid<<<dim3(blocks_for(max_cells, PT), nb), PT, 0, st>>>(tab, cur);
     return 1;
 }
 
 int launch_patch_prepass(const PBox* tab, int nb, long long max_cells, int cur, const PGeom& G, cudaStream_t st)
 {
+    if (nb <= 0) return 0;  // this rank holds no box of the level
     k_patch_prepass<<<dim3(blocks_for(max_cells, PT), nb), PT, 0, st>>>(tab, cur, G);
     return 1;
 }
 
-int launch_patch_physbc(const PBox* tab, int nb, long long max_cells, int cur, const PGeom& G, const BcInfo& B,
+int launch_patch_physbc(const PBox* tab, int nb, long long max_face, int cur, const PGeom& G, const BcInfo& B,
                         cudaStream_t st)
 {
+    if (nb <= 0) return 0;  // this rank holds no box of the level
     if (G.periodic[0] && G.periodic[1] && G.periodic[2]) return 0;  // PhysBCFunct::operator() returns early
     int nl = 0;
-    // a region has at most (grown face) cells; faces are the largest
-    const dim3 grid(blocks_for(max_cells / 4 + 64, 64), nb, 2);
+    // a region has at most the cells of a 3-cell-thick face slab of the grown box (the kernel strides if it has more)
+    const dim3 grid(blocks_for(max_face + 64, 64), nb, 2);
     auto region = [&](int sx, int sy, int sz) {
         // a region outside a periodic direction's grown domain is empty for every box: skip the launch
         if ((sx && G.periodic[0]) || (sy && G.periodic[1]) || (sz && G.periodic[2])) return;
@@ -692,6 +697,7 @@ int launch_patch_physbc(const PBox* tab, int nb, long long max_cells, int cur, c
 
 int launch_patch_stream(const PBox* tab, int nb, long long max_cells, int cur, cudaStream_t st)
 {
+    if (nb <= 0) return 0;  // this rank holds no box of the level
     k_patch_stream<<<dim3(blocks_for(max_cells, PT), nb), PT, 0, st>>>(tab, cur);
     return 1;
 }
@@ -699,6 +705,7 @@ int launch_patch_stream(const PBox* tab, int nb, long long max_cells, int cur, c
 int launch_patch_qcorr(const PBox* tab, int nb, long long max_cells, int cur, const Phys& P, int want_macro, cudaStream_t st,
                        bool pull)
 {
+    if (nb <= 0) return 0;  // this rank holds no box of the level
     const dim3 grid(blocks_for(max_cells, PT), nb);
     if (pull) {
         if (want_macro)
@@ -715,6 +722,7 @@ int launch_patch_qcorr(const PBox* tab, int nb, long long max_cells, int cur, co
 int launch_patch_advance(const PBox* tab, int nb, long long max_cells, int cur, const PGeom& G, const Phys& P, int want_macro,
                          cudaStream_t st)
 {
+    if (nb <= 0) return 0;  // this rank holds no box of the level
     const dim3 grid(blocks_for(max_cells, 128), nb);
     if (want_macro)
         k_patch_advance<true><<<grid, 128, 0, st>>>(tab, cur, G, P);
@@ -726,6 +734,7 @@ int launch_patch_advance(const PBox* tab, int nb, long long max_cells, int cur, 
 int launch_patch_collide(const PBox* tab, int nb, long long max_cells, int cur, const PGeom& G, const Phys& P, int want_macro,
                          cudaStream_t st)
 {
+    if (nb <= 0) return 0;  // this rank holds no box of the level
     const dim3 grid(blocks_for(max_cells, 128), nb);
     if (want_macro)
         k_patch_collide<true><<<grid, 128, 0, st>>>(tab, cur, G, P);
@@ -737,6 +746,7 @@ int launch_patch_collide(const PBox* tab, int nb, long long max_cells, int cur, 
 int launch_patch_derived(const PBox* tab, int nb, long long max_cells, const PGeom& G, const Phys& P, int with_dq,
                          cudaStream_t st)
 {
+    if (nb <= 0) return 0;  // this rank holds no box of the level
     k_patch_derived<<<dim3(blocks_for(max_cells, PT), nb), PT, 0, st>>>(tab, G, P, with_dq);
     return 1;
 }
@@ -744,6 +754,7 @@ int launch_patch_derived(const PBox* tab, int nb, long long max_cells, const PGe
 int launch_patch_avgdown(const PBox* ftab, int fcur, const PBox* ctab, int nb, long long max_cells, int /*ng*/,
                          cudaStream_t st)
 {
+    if (nb <= 0) return 0;  // this rank holds no box of the level
     k_patch_avgdown<<<dim3(blocks_for(max_cells, PT), nb), PT, 0, st>>>(ftab, fcur, ctab);
     return 1;
 }

@@ -73,7 +73,7 @@ int launch_patch_zero_solid(const PBox* tab, int nb, long long max_cells, int cu
 int launch_patch_prepass(const PBox* tab, int nb, long long max_cells, int cur, const PGeom& G, cudaStream_t st);
 // BCFill over faces, edges, corners of every box (26 launches at most; regions that are empty for every box are skipped
 // by the caller through `any_outside`)
-int launch_patch_physbc(const PBox* tab, int nb, long long max_cells, int cur, const PGeom& G, const BcInfo& B,
+int launch_patch_physbc(const PBox* tab, int nb, long long max_face, int cur, const PGeom& G, const BcInfo& B,
                         cudaStream_t st);
 int launch_patch_stream(const PBox* tab, int nb, long long max_cells, int cur, cudaStream_t st);
 int launch_patch_qcorr(const PBox* tab, int nb, long long max_cells, int cur, const Phys& P, int want_macro, cudaStream_t st,
