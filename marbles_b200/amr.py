@@ -50,6 +50,7 @@ class AmrLBM:
         self._owners_of = owners or (lambda lev, boxes: default_owners(boxes, world))
         self._exchange = exchange
         self.owner: list[list[int]] = []
+        self._isfl: dict = {}  # (lev, ib) -> is_fluid of the grown box as handed to the library (plotfiles)
         if inputs is None:
             d = deck if isinstance(deck, dict) else parse_deck(deck, overrides)
             inputs = lbm_inputs(d)
@@ -183,6 +184,7 @@ class AmrLBM:
             m = ok[0][:, None, None] & ok[1][None, :, None] & ok[2][None, None, :]
             v = dense[idx[0][:, None, None], idx[1][None, :, None], idx[2][None, None, :]]
             a = np.ascontiguousarray(np.where(m, v, a).astype(np.int32))
+            self._isfl[(lev, ib)] = a
             if a.min() == 1:
                 continue  # freshly defined boxes (mbl_level_define_boxes, _regrid, _make_from_coarse) start all fluid
             check(self.lib.mbl_box_set_is_fluid(self.ctx, lev, ib, a.ctypes.data_as(C.POINTER(C.c_int32)), ng))
@@ -299,6 +301,15 @@ class AmrLBM:
         a = np.zeros(self.box_shape(lev, ib, NQ, ng))
         check(self.lib.mbl_box_download(self.ctx, lev, ib, which, _dptr(a), ng))
         return a
+
+    def get_box_macrodata(self, lev: int, ib: int, derived: bool = False, ng: int = 0) -> np.ndarray:
+        a = np.zeros(self.box_shape(lev, ib, NDERIVED if derived else NMACRO, ng))
+        check(self.lib.mbl_box_download_macrodata(self.ctx, lev, ib, _dptr(a), ng, int(derived)))
+        return a
+
+    def box_is_fluid(self, lev: int, ib: int) -> np.ndarray:
+        """component 0 of m_is_fluid on the box grown by 3 ghost cells, as the library was given it"""
+        return self._isfl[(lev, ib)]
 
     def set_box(self, lev: int, ib: int, which: int, a: np.ndarray, ng: int = 0):
         a = np.ascontiguousarray(a, dtype=np.float64)

@@ -143,6 +143,109 @@ def write_plotfile(path: str, names: list[str], data: np.ndarray, *, time: float
         fh.write("Level_0/Cell\n")
 
 
+def write_plotfile_levels(path: str, names: list[str], levels, *, time: float, level_steps, prob_lo, prob_hi, n_cell,
+                          ref_ratio: int = 2) -> None:
+    """amrex::WriteMultiLevelPlotfile for a hierarchy (Source/LBM.cpp:1677-1690; AMReX_PlotFileUtil.cpp): levels[lev] =
+    (boxes, fabs) with boxes = [(lo, hi), ...] in the index space of level lev and fabs[i] = [ncomp, nz, ny, nx] float64 of
+    box i (the level's BoxArray order); level_steps[lev] = m_isteps[lev]; n_cell = cells of level 0.  One process:
+    every level's FABs go to Level_<lev>/Cell_D_00000."""
+    ncomp, nlev = len(names), len(levels)
+    dx0 = [(float(prob_hi[d]) - float(prob_lo[d])) / n_cell[d] for d in range(3)]
+    for lev, (boxes, fabs) in enumerate(levels):
+        assert len(boxes) == len(fabs)
+        lev_dir = os.path.join(path, f"Level_{lev}")
+        os.makedirs(lev_dir, exist_ok=True)
+        offsets, mins, maxs = [], [], []
+        with open(os.path.join(lev_dir, "Cell_D_00000"), "wb") as fh:
+            for (lo, hi), fab in zip(boxes, fabs):
+                fab = np.ascontiguousarray(fab, dtype="<f8")
+                assert fab.shape == (ncomp, hi[2] - lo[2] + 1, hi[1] - lo[1] + 1, hi[0] - lo[0] + 1), (fab.shape, lo, hi)
+                offsets.append(fh.tell())
+                fh.write(f"{FAB_HEADER}{_box(lo, hi)} {ncomp}\n".encode())
+                fh.write(fab.tobytes())
+                flat = fab.reshape(ncomp, -1)
+                mins.append(flat.min(axis=1))
+                maxs.append(flat.max(axis=1))
+        with open(os.path.join(lev_dir, "Cell_H"), "w") as fh:
+            fh.write(f"1\n1\n{ncomp}\n0\n")
+            fh.write(f"({len(boxes)} 0\n")
+            for lo, hi in boxes:
+                fh.write(_box(lo, hi) + "\n")
+            fh.write(")\n")
+            fh.write(f"{len(boxes)}\n")
+            for off in offsets:
+                fh.write(f"FabOnDisk: Cell_D_00000 {off}\n")
+            fh.write("\n")
+            for table in (mins, maxs):
+                fh.write(f"{len(boxes)},{ncomp}\n")
+                for row in table:
+                    fh.write("".join("%.17e," % v for v in row) + "\n")
+                fh.write("\n")
+    with open(os.path.join(path, "Header"), "w") as fh:
+        fh.write("HyperCLaw-V1.1\n")
+        fh.write(f"{ncomp}\n")
+        for nm in names:
+            fh.write(nm + "\n")
+        fh.write("3\n")
+        fh.write(_g17(time) + "\n")
+        fh.write(f"{nlev - 1}\n")
+        fh.write(" ".join(_g17(v) for v in prob_lo) + " \n")
+        fh.write(" ".join(_g17(v) for v in prob_hi) + " \n")
+        fh.write("".join(f"{ref_ratio} " for _ in range(nlev - 1)) + "\n")
+        fh.write("".join(_box((0, 0, 0), tuple(n_cell[d] * ref_ratio ** lev - 1 for d in range(3))) + " " for lev in range(nlev)) + "\n")
+        fh.write("".join(f"{int(st)} " for st in level_steps) + "\n")
+        for lev in range(nlev):
+            fh.write(" ".join(_g17(dx0[d] / ref_ratio ** lev) for d in range(3)) + " \n")
+        fh.write("0\n0\n")  # coordinate system, boundary width
+        for lev, (boxes, _) in enumerate(levels):
+            dx = [dx0[d] / ref_ratio ** lev for d in range(3)]
+            fh.write(f"{lev} {len(boxes)} {_g17(time)}\n")
+            fh.write(f"{int(level_steps[lev])}\n")
+            for lo, hi in boxes:
+                for d in range(3):
+                    fh.write(f"{_g17(prob_lo[d] + lo[d] * dx[d])} {_g17(prob_lo[d] + (hi[d] + 1) * dx[d])}\n")
+            fh.write(f"Level_{lev}/Cell\n")
+
+
+def write_amr_plotfile(amr, directory: str = ".", prefix: str = "plt", save_streaming: bool | None = None,
+                       save_derived: bool | None = None, digits: int = 5) -> str:
+    """LBM::write_plot_file for a multi-level state (marbles_b200.amr.AmrLBM, all boxes on this rank): the macrodata of
+    every level must be current (last step with want_macrodata=True) and compute_derived() called, as post_time_step
+    leaves them."""
+    deck = amr.inp.deck
+
+    def deck_int(key: str, default: int) -> int:
+        v = deck.get(key, default)
+        if isinstance(v, (list, tuple)):
+            v = v[0]
+        return int(str(v).split()[0])
+
+    if amr.world != 1:
+        raise NotImplementedError("write_amr_plotfile: distributed levels write their FABs per rank -- not implemented")
+    if save_streaming is None:
+        save_streaming = bool(deck_int("lbm.save_streaming", 1))
+    if save_derived is None:
+        save_derived = bool(deck_int("lbm.save_derived", 1))
+    names = plot_file_var_names(save_streaming, save_derived)
+    levels = []
+    for lev in range(amr.finest + 1):
+        fabs = []
+        for ib in range(len(amr.boxes[lev])):
+            parts = [amr.get_box_macrodata(lev, ib, derived=False)]
+            if save_streaming:
+                parts += [amr.get_box(lev, ib, 0), amr.get_box(lev, ib, 1)]
+            if save_derived:
+                parts.append(amr.get_box_macrodata(lev, ib, derived=True))
+            fl = amr.box_is_fluid(lev, ib)  # grown by 3
+            parts.append(np.stack([fl[3:-3, 3:-3, 3:-3].astype(np.float64), eb_boundary(fl, 3).astype(np.float64)]))
+            fabs.append(np.concatenate(parts, axis=0))
+        levels.append((amr.boxes[lev], fabs))
+    path = os.path.join(directory, plot_file_name(prefix, amr.isteps, digits))
+    write_plotfile_levels(path, names, levels, time=amr.time, level_steps=[amr.isteps * 2 ** l for l in range(amr.finest + 1)],
+                          prob_lo=amr.inp.prob_lo, prob_hi=amr.inp.prob_hi, n_cell=amr.inp.n_cell)
+    return path
+
+
 def plot_file_name(prefix: str, step: int, digits: int = 5) -> str:
     """amrex::Concatenate(plot_file, step, m_file_name_digits) (Source/LBM.cpp:1617-1621; amr.file_name_digits)"""
     return f"{prefix}{step:0{digits}d}"

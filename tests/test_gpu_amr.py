@@ -3,6 +3,8 @@ with coarse-fine interpolation, grown-box mbl_stream, mbl_average_down, mbl_coll
 the unmodified reference on 2- and 3-level decks (BASELINE configs 4-5 at reduced size) and against the multi-level
 oracle on seeded random states.  Sub-cycling order driven from Python (marbles_b200/amr.py) as LBM::time_step does.
 Tolerance: 1e-12 of the field scale per level step (tests/parity.py)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -241,6 +243,34 @@ def test_distributed_levels_match_one_rank(case, world):
         for w in ("f", "g", "macro", "derived"):
             got = merge_dense([r[0][lev][w] for r in res])
             assert np.array_equal(got, ref[lev][w], equal_nan=True), (case, lev, w)
+
+
+@pytest.mark.parametrize("case", ["amr2_chcyl", "amr3_chcyl"])
+def test_amr_plotfile_from_device_state(oracle_mod, case, tmp_path):
+    """LBM::write_plot_file for a hierarchy on the device (plotfile.write_amr_plotfile): read back with the oracle's
+    plotfile reader, every component of every level against the reference's plotfile of the same step (the golden),
+    is_fluid / eb_boundary and the box lists included"""
+    from marbles_b200 import plotfile as P
+    from parity import compare, scales
+    O = oracle_mod
+    amr, z, deck_text, steps, boxes, is_fluid = new_amr(case)
+    s = steps[-1]
+    amr.step(s, want_macrodata=True)
+    amr.compute_derived()
+    path = P.write_amr_plotfile(amr, str(tmp_path))
+    assert os.path.basename(path) == f"plt{s:05d}"
+    for lev in range(amr.finest + 1):
+        assert [(list(a), list(b)) for a, b in O.read_plotfile_boxes(path, lev)] == [(list(a), list(b)) for a, b in boxes[lev]]
+        pf = O.read_plotfile(path, lev)
+        ref = golden_level(z, s, lev)
+        sc = scales(nan0(ref), amr.inp.R, amr.inp.gamma, 2 ** lev / amr.inp.dx[0])
+        got = {k: pf[k] for k in ref}
+        worst, key = compare(nan0(got), nan0(ref), sc, s * 2 ** lev)
+        fl = z[f"is_fluid_l{lev}"]
+        m = ~np.isnan(pf["is_fluid"])
+        assert np.array_equal(pf["is_fluid"][m], fl[m].astype(np.float64))
+        print(f"{case} level {lev}: worst {worst:.2e} ({key}), {len(pf['__names__'])} components")
+    amr.close()
 
 
 def test_level_bind_is_zero_copy_and_bit_identical():

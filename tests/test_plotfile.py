@@ -30,6 +30,33 @@ def test_plotfile_bytes_match_reference(tmp_path):
     assert digest == str(z["cell_d_sha256"])
 
 
+def test_multilevel_plotfile_bytes_match_reference(tmp_path):
+    """amrex::WriteMultiLevelPlotfile of a 3-level hierarchy (tests/golden/plt_amr3.npz: written by the unmodified
+    reference, 8 boxes per level): Header, every Level_k/Cell_H and every Level_k/Cell_D_00000 byte for byte"""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "plt_amr3.npz"))
+    names = [str(n) for n in z["names"]]
+    nlev = int(z["nlev"])
+    levels = []
+    for lev in range(nlev):
+        boxes = [(tuple(int(v) for v in b[0]), tuple(int(v) for v in b[1])) for b in z[f"boxes_{lev}"]]
+        levels.append((boxes, [z[f"fab_{lev}_{ib}"] for ib in range(len(boxes))]))
+    out = str(tmp_path / "plt00002")
+    P.write_plotfile_levels(out, names, levels, time=float(z["time"]), level_steps=[2 * 2 ** l for l in range(nlev)],
+                            prob_lo=[-1, -1, -1], prob_hi=[1, 1, 1], n_cell=(8, 8, 8))
+    assert open(os.path.join(out, "Header")).read() == str(z["header"])
+    for lev in range(nlev):
+        assert open(os.path.join(out, f"Level_{lev}", "Cell_H")).read() == str(z[f"cell_h_{lev}"]), lev
+        digest = hashlib.sha256(open(os.path.join(out, f"Level_{lev}", "Cell_D_00000"), "rb").read()).hexdigest()
+        assert digest == str(z[f"cell_d_sha256_{lev}"]), lev
+    # and the oracle's reader gets the fields back, level by level
+    from oracle import oracle as O
+    for lev in range(nlev):
+        pf = O.read_plotfile(out, lev)
+        boxes, fabs = levels[lev]
+        for (lo, hi), fab in zip(boxes, fabs):
+            assert np.array_equal(pf["rho"][lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1], fab[0])
+
+
 @pytest.mark.parametrize("shape,mgs", [((5, 6, 7), 4), ((8, 8, 8), 8), ((3, 16, 4), 32)])
 def test_plotfile_round_trip_through_oracle_reader(tmp_path, shape, mgs):
     from oracle import oracle as O
