@@ -177,7 +177,8 @@ int mbl_compute_derived(mbl_ctx* ctx, int lev);
 int64_t mbl_macro_halo_doubles(mbl_ctx* ctx, int lev);
 int mbl_macro_halo(mbl_ctx* ctx, int lev, int side, double* device_buf, int pack);
 int mbl_compute_derived_slab(mbl_ctx* ctx, int lev, int has_lo, int has_hi);
-/* LBM::compute_eb_forces() for one level (Source/LBM.cpp:994-1044): local sum */
+/* LBM::compute_eb_forces() for one level (Source/LBM.cpp:994-1044): local sum; on a multi-box level over the boxes that
+ * live here.  The caller adds the levels (the reference adds them without weighting) and the ranks. */
 int mbl_eb_forces(mbl_ctx* ctx, int lev, double out[3]);
 
 /* ---------------------------------------------------------------------------------------------

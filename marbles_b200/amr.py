@@ -249,6 +249,17 @@ class AmrLBM:
         for lev in range(self.finest + 1):
             check(self.lib.mbl_compute_derived(self.ctx, lev))
 
+    def compute_eb_forces(self) -> np.ndarray:
+        """LBM::compute_eb_forces (Source/LBM.cpp:994-1044): the levels' sums added as the reference adds them (m_mask is
+        empty in every run the reference completes, so no cell is left out); this rank's boxes only -- the ranks of a
+        distributed hierarchy add theirs (ParallelDescriptor::ReduceRealSum)"""
+        total = np.zeros(3)
+        out = (C.c_double * 3)()
+        for lev in range(self.finest + 1):
+            check(self.lib.mbl_eb_forces(self.ctx, lev, out))
+            total += np.array(out[:])
+        return total
+
     def sync(self):
         check(self.lib.mbl_sync(self.ctx))
 

@@ -279,6 +279,7 @@ struct PatchLevel {
     double* pool_qc = nullptr;
     double* pool_macro = nullptr;
     int32_t* pool_isfl = nullptr;
+    double* d_red = nullptr;  // 3 doubles: reduction target of compute_eb_forces
     std::vector<long long> cell_off;  // first cell of each box in the pools
     long long total_cells = 0;
     bool any_bound = false;
@@ -659,6 +660,7 @@ int patch_clear(mbl_ctx* ctx, int lev)
     if (L->pool_qc) cudaFree(L->pool_qc);
     if (L->pool_macro) cudaFree(L->pool_macro);
     if (L->pool_isfl) cudaFree(L->pool_isfl);
+    if (L->d_red) cudaFree(L->d_red);
     L->set.free_all();
     L->fb3.free_all();
     L->fb1.free_all();
@@ -803,6 +805,19 @@ int patch_f_to_macrodata(mbl_ctx* ctx, int lev)
     if (patch_macro_pass(ctx, *L, 1)) return 1;
     L->dq_from_macro = true;
     CU(cudaGetLastError());
+    return 0;
+}
+
+// this level's part of LBM::compute_eb_forces (LBM.cpp:994-1044) over the boxes that live here.  m_mask is empty in
+// every run the reference completes (tests/golden/make_golden.py, amr3_chcyl_forces): no cell is excluded
+int patch_eb_forces(mbl_ctx* ctx, int lev, double out[3])
+{
+    PatchLevel* L = plevel(ctx, lev);
+    if (!L) return 1;
+    if (!L->d_red) CU(cudaMalloc(&L->d_red, 3 * sizeof(double)));
+    ctx->launches += launch_patch_eb_forces(L->set.dl, L->set.nl, L->set.max_cells, L->cur, L->d_red, ctx->stream);
+    CU(cudaMemcpyAsync(out, L->d_red, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 

@@ -729,6 +729,10 @@ int mbl_compute_derived_slab(mbl_ctx* ctx, int lev, int has_lo, int has_hi)
 
 int mbl_eb_forces(mbl_ctx* ctx, int lev, double out[3])
 {
+    if (is_patch(ctx, lev)) {
+        CU(cudaSetDevice(ctx->device));
+        return patch_eb_forces(ctx, lev, out);
+    }
     if (check_level(ctx, lev)) return 1;
     Level& lv = ctx->lev[lev];
     CU(cudaSetDevice(ctx->device));

@@ -135,6 +135,7 @@ int patch_physbc(mbl_ctx* ctx, int lev, double time);
 int patch_stream(mbl_ctx* ctx, int lev);
 int patch_collide(mbl_ctx* ctx, int lev, int want_macro);
 int patch_advance(mbl_ctx* ctx, int lev, int want_macro);
+int patch_eb_forces(mbl_ctx* ctx, int lev, double out[3]);
 int patch_f_to_macrodata(mbl_ctx* ctx, int lev);
 int patch_compute_derived(mbl_ctx* ctx, int lev);
 }  // namespace mbl

@@ -489,6 +489,48 @@ __global__ void __launch_bounds__(128) k_patch_advance(const PBox* __restrict__ 
     }
 }
 
+// compute_eb_forces (LBM.cpp:994-1044) on the valid cells of every local box: momentum exchange over the solid cells that
+// have a fluid face neighbour (is_fluid comp 1, LBM.cpp:1236-1259), reading the populations of the neighbour cells
+// (ghost cells included: FillBoundary'd after the collision).  One double atomicAdd per block and direction.
+__global__ void __launch_bounds__(128) k_patch_eb_forces(const PBox* __restrict__ tab, int cur, double* __restrict__ out3)
+{
+    const PBox B = tab[blockIdx.y];
+    const int m0 = B.hi[0] - B.lo[0] + 1, m1 = B.hi[1] - B.lo[1] + 1, m2 = B.hi[2] - B.lo[2] + 1;
+    const long long cells = (long long)m0 * m1 * m2;
+    const double* __restrict__ f = B.f[cur];
+    double fs[3] = {0.0, 0.0, 0.0};
+    for (long long t = (long long)blockIdx.x * 128 + threadIdx.x; t < cells; t += (long long)gridDim.x * 128) {
+        const int i = B.lo[0] + (int)(t % m0);
+        const long long r = t / m0;
+        const int j = B.lo[1] + (int)(r % m1), k = B.lo[2] + (int)(r / m1);
+        const long long c = B.cell(i, j, k);
+        if (B.isfl[c] == 1) continue;
+        const bool all_covered = B.isfl[c - 1] == 0 && B.isfl[c + 1] == 0 && B.isfl[c - B.sy] == 0 && B.isfl[c + B.sy] == 0 &&
+                                 B.isfl[c - B.sz] == 0 && B.isfl[c + B.sz] == 0;
+        if (all_covered) continue;
+        for (int q = 0; q < NQ; ++q) {
+            const int o = c_dir.opp[q];
+            const long long rr = c + c_dir.ex[o] + c_dir.ey[o] * B.sy + c_dir.ez[o] * B.sz;
+            const double v = 2.0 * f[(long long)q * B.sq + rr] * B.isfl[rr];
+            fs[0] += c_dir.ex[q] * v;
+            fs[1] += c_dir.ey[q] * v;
+            fs[2] += c_dir.ez[q] * v;
+        }
+    }
+    __shared__ double sh[3][4];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double v = fs[d];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) sh[d][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const double v = sh[threadIdx.x][0] + sh[threadIdx.x][1] + sh[threadIdx.x][2] + sh[threadIdx.x][3];
+        if (v != 0.0) atomicAdd(out3 + threadIdx.x, v);
+    }
+}
+
 // compute_derived (LBM.cpp:909-955): vorticity from the velocity macrodata (1 ghost cell, FillBoundary'd)
 __global__ void __launch_bounds__(PT) k_patch_derived(const PBox* __restrict__ tab, PGeom G, Phys P, int with_dq)
 {
@@ -740,6 +782,14 @@ int launch_patch_collide(const PBox* tab, int nb, long long max_cells, int cur, 
         k_patch_collide<true><<<grid, 128, 0, st>>>(tab, cur, G, P);
     else
         k_patch_collide<false><<<grid, 128, 0, st>>>(tab, cur, G, P);
+    return 1;
+}
+
+int launch_patch_eb_forces(const PBox* tab, int nb, long long max_cells, int cur, double* d_out3, cudaStream_t st)
+{
+    cudaMemsetAsync(d_out3, 0, 3 * sizeof(double), st);
+    if (nb <= 0) return 0;
+    k_patch_eb_forces<<<dim3(blocks_for(max_cells, 128), nb), 128, 0, st>>>(tab, cur, d_out3);
     return 1;
 }
 

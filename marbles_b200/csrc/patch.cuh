@@ -83,6 +83,8 @@ int launch_patch_advance(const PBox* tab, int nb, long long max_cells, int cur, 
                          cudaStream_t st);
 int launch_patch_collide(const PBox* tab, int nb, long long max_cells, int cur, const PGeom& G, const Phys& P, int want_macro,
                          cudaStream_t st);
+// compute_eb_forces over the local boxes of a level: d_out3[3] (device) = the level's sum
+int launch_patch_eb_forces(const PBox* tab, int nb, long long max_cells, int cur, double* d_out3, cudaStream_t st);
 int launch_patch_derived(const PBox* tab, int nb, long long max_cells, const PGeom& G, const Phys& P, int with_dq,
                          cudaStream_t st);
 // masked_avgdown (Utilities.H:315-350) of the fine boxes into the coarsened aux boxes (ng ghost cells), ratio 2

@@ -459,6 +459,18 @@ class AmrOracle:
         self.levels.pop()
         self.finest = lev - 1
 
+    def eb_forces(self):
+        """LBM::compute_eb_forces (Source/LBM.cpp:994-1044): momentum exchange over the eb_boundary cells of EVERY level,
+        summed without any weighting by the cell size.  m_mask[lev] is empty in every run the reference completes
+        (tests/golden/make_golden.py, amr3_chcyl_forces), so the coarse cells under a fine level count as well."""
+        total = np.zeros(3)
+        for L in self.levels:
+            for b in L.boxes:
+                out = (C.c_double * 3)()
+                self.lib.orc_eb_forces(C.byref(b.p), _ptr(b.is_fluid, C.c_int), _ptr(b.f), out)
+                total += np.array(out[:])
+        return total
+
     # ------------------------------------------------------------ time stepping
     def advance(self, lev):
         """LBM::advance (Source/LBM.cpp:523-544)"""

@@ -403,6 +403,16 @@ tagging.bc.in_box_hi = 6 10 10
 tagging.bchi.in_box_lo = 59 -10 -10
 tagging.bchi.in_box_hi = 80 10 10
 """, 2, [0, 1, 6, 12])
+# compute_eb_forces on a hierarchy (lbm.compute_forces = 1; the forces file is stored as `forces`): a uniform flow hits the
+# cylinder from the first step.  m_mask of every level is EMPTY in this and in every other run the reference completes:
+# LBM::initialize_mask only fills it when the level is (re)made while a finer one exists (Source/LBM.cpp:1264-1276), which
+# from scratch never happens (each level is made while it is the finest), and a RemakeLevel of level 1 under an existing
+# level 2 -- the one way to get there -- segfaults in the reference (tried: tagging box of level 1 widened at step 3).
+# So the coarse cells under a fine level are counted as well, and the levels' sums are added without any weighting.
+AMR_CASES["amr3_chcyl_forces"] = (AMR_CASES["amr3_chcyl"][0].replace("max_step = 3", "max_step = 6")
+                                  .replace("ic_constant.mach_components = 0.0 0.0 0.0", "ic_constant.mach_components = 0.05 0.0 0.0") + """lbm.compute_forces = 1
+lbm.forces_file = forces.txt
+""", 3, [0, 3, 6])
 AMR_REGRID_INT = {"amr2_sod_regrid": 1, "amr2_tg_appear": 1, "amr2_chcyl_appear": 1, "amr2_sod_bc": 1}
 # steps stored with f and g as well (besides the first and the last): the first step of the new level
 AMR_FULL_STEPS = {"amr2_tg_appear": [4], "amr2_chcyl_appear": [3]}
@@ -424,6 +434,8 @@ def make_amr(out_dir, only):
             fh.write(deck_text)
         O.run_reference(deck_path, work, [], omp=False)
         data = {"deck": np.array(deck_text), "steps": np.array(steps), "nlev": np.array(nlev)}
+        if os.path.exists(os.path.join(work, "forces.txt")):
+            data["forces"] = np.loadtxt(os.path.join(work, "forces.txt"), skiprows=1)
         def boxes_of(st, lev):  # empty when the level does not exist in that plotfile
             pdir = os.path.join(work, f"plt{st:05d}")
             if not os.path.isdir(os.path.join(pdir, f"Level_{lev}")):
@@ -446,6 +458,8 @@ def make_amr(out_dir, only):
                     KEEP_STEP0 if s == steps[0] or s in AMR_FULL_STEPS.get(name, []) else AMR_KEEP_MID)
                 for n in keep:
                     data[f"s{s}_l{lev}_{n}"] = pf[n]
+        if name.endswith("_forces"):  # the forces file is the golden; the fields of this deck's hierarchy are pinned elsewhere
+            data = {k: v for k, v in data.items() if not (k[0] == "s" and k[1].isdigit())}
         path = os.path.join(out_dir, f"{name}.npz")
         np.savez_compressed(path, **data)
         print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB, boxes per level "

@@ -273,6 +273,23 @@ def test_amr_plotfile_from_device_state(oracle_mod, case, tmp_path):
     amr.close()
 
 
+def test_amr_eb_forces_match_reference_forces_file():
+    """compute_eb_forces on a 3-level hierarchy on the device against the forces file the unmodified reference wrote
+    (tests/golden/amr3_chcyl_forces.npz: uniform flow onto the cylinder, one line per coarse step)"""
+    amr, z, deck_text, steps, boxes, is_fluid = new_amr("amr3_chcyl_forces")
+    ref = z["forces"]
+    scale = np.abs(ref[:, 1:]).max()
+    worst = 0.0
+    for s in range(len(ref)):
+        got = amr.compute_eb_forces()
+        worst = max(worst, float(np.abs(got - ref[s, 1:]).max()) / scale)
+        if s + 1 < len(ref):
+            amr.step(1)
+    print(f"forces: worst {worst:.2e} of {scale:.3f} over {len(ref)} lines")
+    assert worst <= 1e-12 * len(ref)
+    amr.close()
+
+
 def test_level_bind_is_zero_copy_and_bit_identical():
     """mbl_level_bind: the fine level's boxes live in caller-owned device memory (torch tensors standing in for the
     FABs of an AMReX device-arena MultiFab, 27 comps x 3 ghost cells); every operator leaves its result there"""
