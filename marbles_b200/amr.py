@@ -249,6 +249,30 @@ class AmrLBM:
         for lev in range(self.finest + 1):
             check(self.lib.mbl_compute_derived(self.ctx, lev))
 
+    def write_checkpoint_file(self, directory: str = ".", prefix: str = "chk", digits: int = 5) -> str:
+        """LBM::write_checkpoint_file (Source/LBM.cpp:1692-1783): Header + f and g of every box with their ghost cells;
+        the unmodified reference restarts from it (amr.restart)"""
+        from .plotfile import write_amr_checkpoint
+        max_level = int(self.inp.deck.get("amr.max_level", [self.finest])[0])
+        return write_amr_checkpoint(self, directory, prefix, digits, max_level=max(max_level, self.finest))
+
+    @classmethod
+    def from_checkpoint(cls, deck, path: str, is_fluid=None, **kw):
+        """LBM::read_checkpoint_file (Source/LBM.cpp:1785-1915): the box lists, step counters and times of the Header, f
+        and g of every FAB with their ghost cells, then is_fluid, fill_f_inside_eb and FillBoundary as the reference
+        populates "the other data".  Written by the reference or by write_checkpoint_file."""
+        from .plotfile import read_checkpoint_levels
+        c = read_checkpoint_levels(path)
+        amr = cls(deck, [lv[0] for lv in c["levels"]], is_fluid, **kw)
+        for lev, (boxes, ff, gg) in enumerate(c["levels"]):
+            for ib in range(len(boxes)):
+                if amr.is_local(lev, ib):
+                    amr.set_box(lev, ib, 0, ff[ib], ng=c["ng"])
+                    amr.set_box(lev, ib, 1, gg[ib], ng=c["ng"])
+            check(amr.lib.mbl_fill_f_inside_eb(amr.ctx, lev))
+        amr.isteps, amr.time = int(c["isteps"][0]), float(c["times"][0])
+        return amr
+
     def compute_eb_forces(self) -> np.ndarray:
         """LBM::compute_eb_forces (Source/LBM.cpp:994-1044): the levels' sums added as the reference adds them (m_mask is
         empty in every run the reference completes, so no cell is left out); this rank's boxes only -- the ranks of a

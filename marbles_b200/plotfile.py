@@ -464,6 +464,105 @@ def read_checkpoint(path: str) -> dict:
     return out
 
 
+def _write_vismf_fabs(lev_dir: str, prefix: str, fabs, ng: int, boxes) -> None:
+    """VisMF::Write of a MultiFab given FAB by FAB: fabs[i] = [ncomp, nz+2ng, ny+2ng, nx+2ng] of box i with its ghost
+    cells; minima / maxima over the valid box"""
+    os.makedirs(lev_dir, exist_ok=True)
+    ncomp = fabs[0].shape[0]
+    dname = f"{prefix}_D_00000"
+    part = {"file": dname, "boxes": [(tuple(lo), tuple(hi)) for lo, hi in boxes], "offsets": [], "mins": [], "maxs": []}
+    with open(os.path.join(lev_dir, dname), "wb") as fh:
+        for (lo, hi), fab in zip(boxes, fabs):
+            fab = np.ascontiguousarray(fab, dtype="<f8")
+            assert fab.shape == (ncomp,) + tuple(hi[d] - lo[d] + 1 + 2 * ng for d in (2, 1, 0))
+            part["offsets"].append(fh.tell())
+            glo, ghi = _grown(lo, hi, ng)
+            fh.write(f"{FAB_HEADER}{_box(glo, ghi)} {ncomp}\n".encode())
+            fh.write(fab.tobytes())
+            val = fab[:, ng:fab.shape[1] - ng, ng:fab.shape[2] - ng, ng:fab.shape[3] - ng] if ng else fab
+            flat = val.reshape(ncomp, -1)
+            part["mins"].append(flat.min(axis=1).tolist())
+            part["maxs"].append(flat.max(axis=1).tolist())
+    _write_vismf_header(lev_dir, prefix, ncomp, ng, [part])
+
+
+def _read_vismf_fabs(lev_dir: str, prefix: str):
+    """-> (fabs [ncomp, nz+2ng, ny+2ng, nx+2ng] per box, ng, boxes)"""
+    import re
+    with open(os.path.join(lev_dir, f"{prefix}_H")) as fh:
+        ch = fh.read().split("\n")
+    ncomp, ng = int(ch[2]), int(ch[3].split()[0].strip("(),"))
+    i = next(k for k, l in enumerate(ch) if l.startswith("(") and k >= 4)
+    nbox = int(ch[i].strip("(").split()[0])
+    boxes = []
+    for b in range(nbox):
+        m = [int(v) for v in re.findall(r"-?\d+", ch[i + 1 + b])]
+        boxes.append((tuple(m[0:3]), tuple(m[3:6])))
+    j = next(k for k, l in enumerate(ch) if l.startswith("FabOnDisk"))
+    fabs = []
+    for b, (lo, hi) in enumerate(boxes):
+        _, fname, off = ch[j + b].split()
+        bn = [hi[d] - lo[d] + 1 + 2 * ng for d in range(3)]
+        with open(os.path.join(lev_dir, fname), "rb") as fh:
+            fh.seek(int(off))
+            fh.readline()
+            fabs.append(np.frombuffer(fh.read(8 * ncomp * bn[0] * bn[1] * bn[2]), dtype="<f8")
+                        .reshape(ncomp, bn[2], bn[1], bn[0]).copy())
+    return fabs, ng, boxes
+
+
+def write_checkpoint_levels(path: str, levels, *, isteps, dts, times, ng: int = 3) -> None:
+    """LBM::write_checkpoint_file (Source/LBM.cpp:1692-1783) for a hierarchy: levels[lev] = (boxes, f_fabs, g_fabs) with
+    the FABs of every box INCLUDING their ng ghost cells (VisMF::Write stores them); isteps / dts / times are the
+    reference's m_isteps / m_dts / m_ts_new, one entry per level up to amr.max_level (levels that do not exist keep
+    their initial values there)."""
+    os.makedirs(path, exist_ok=True)
+    with open(os.path.join(path, "Header"), "w") as fh:
+        fh.write(f"Checkpoint file for LBM\n{len(levels) - 1}\n")
+        fh.write("".join(f"{int(v)} " for v in isteps) + "\n")
+        fh.write("".join(f"{_g17(v)} " for v in dts) + "\n")
+        fh.write("".join(f"{_g17(v)} " for v in times) + "\n")
+        for boxes, _, _ in levels:
+            fh.write(f"({len(boxes)} 0\n")
+            for lo, hi in boxes:
+                fh.write(_box(lo, hi) + "\n")
+            fh.write(")\n")
+    for lev, (boxes, ff, gg) in enumerate(levels):
+        lev_dir = os.path.join(path, f"Level_{lev}")
+        _write_vismf_fabs(lev_dir, "f_00", ff, ng, boxes)
+        _write_vismf_fabs(lev_dir, "g_00", gg, ng, boxes)
+
+
+def read_checkpoint_levels(path: str) -> dict:
+    """-> {"isteps", "dts", "times", "levels": [(boxes, f_fabs, g_fabs), ...], "ng"} (FABs with their ghost cells)"""
+    with open(os.path.join(path, "Header")) as fh:
+        lines = fh.read().split("\n")
+    finest = int(lines[1])
+    out = {"isteps": [int(v) for v in lines[2].split()], "dts": [float(v) for v in lines[3].split()],
+           "times": [float(v) for v in lines[4].split()], "levels": []}
+    for lev in range(finest + 1):
+        ff, ng, boxes = _read_vismf_fabs(os.path.join(path, f"Level_{lev}"), "f_00")
+        gg, _, _ = _read_vismf_fabs(os.path.join(path, f"Level_{lev}"), "g_00")
+        out["levels"].append((boxes, ff, gg))
+        out["ng"] = ng
+    return out
+
+
+def write_amr_checkpoint(amr, directory: str = ".", prefix: str = "chk", digits: int = 5, max_level: int | None = None) -> str:
+    """LBM::write_checkpoint_file for a hierarchy on the device (all boxes on this rank): f and g of every box with their
+    3 ghost cells.  The unmodified reference restarts from it (amr.restart)."""
+    if amr.world != 1:
+        raise NotImplementedError("write_amr_checkpoint: distributed levels write their FABs per rank -- not implemented")
+    nl = amr.finest + 1
+    nmax = (max_level if max_level is not None else amr.finest) + 1
+    levels = [(amr.boxes[lev], [amr.get_box(lev, ib, 0, ng=3) for ib in range(len(amr.boxes[lev]))],
+               [amr.get_box(lev, ib, 1, ng=3) for ib in range(len(amr.boxes[lev]))]) for lev in range(nl)]
+    path = os.path.join(directory, chk_file_name(prefix, amr.isteps, digits))
+    write_checkpoint_levels(path, levels, isteps=[amr.isteps * 2 ** l if l < nl else 0 for l in range(nmax)],
+                            dts=[1.0 / 2 ** l for l in range(nmax)], times=[amr.time if l < nl else 0.0 for l in range(nmax)])
+    return path
+
+
 # ---------------------------------------------------------------------------------------------------------
 # Multi-rank plotfiles: every rank writes the FABs of its own z-slab into Level_0/Cell_D_<rank>, rank 0 writes
 # Header and Cell_H from the gathered box lists, offsets and extrema -- the layout VisMF uses when every rank

@@ -100,3 +100,37 @@ def test_gpu_checkpoint_round_trip_with_reference(tmp_path):
     worst, key = compare(lbm.fields(), ref10, sc, 10)
     print(f"CUDA path continued from the reference checkpoint: worst {worst:.2e} ({key})")
     lbm.close()
+
+
+def _run_amr(O, work, deck_text, args):
+    os.makedirs(work, exist_ok=True)
+    with open(os.path.join(work, "case.inp"), "w") as fh:
+        fh.write(deck_text)
+    subprocess.run([O.REF_SERIAL, "case.inp"] + args, cwd=work, check=True, capture_output=True)
+
+
+def test_multilevel_checkpoint_round_trip_and_reference_restart(tmp_path):
+    """A 2-level checkpoint of the reference (channel + cylinder, 3 + 2 boxes) read FAB by FAB and written again is the
+    same bytes; the reference restarts from the rewritten one and arrives where its uninterrupted run does."""
+    from conftest import load_amr_golden
+    O = _ref()
+    z, deck_text, steps, boxes, is_fluid = load_amr_golden("amr2_chcyl")
+    ref = str(tmp_path / "ref")
+    _run_amr(O, ref, deck_text, ["max_step=4", "amr.chk_int=2", "amr.plot_int=4"])
+    c = P.read_checkpoint_levels(os.path.join(ref, "chk00002"))
+    assert c["isteps"] == [2, 4] and c["dts"] == [1.0, 0.5] and c["ng"] == 3
+    assert [[(list(a), list(b)) for a, b in lv[0]] for lv in c["levels"]] == [[(list(a), list(b)) for a, b in bx] for bx in boxes]
+    mine = str(tmp_path / "mine")
+    os.makedirs(mine)
+    out = os.path.join(mine, "chk00002")
+    P.write_checkpoint_levels(out, c["levels"], isteps=c["isteps"], dts=c["dts"], times=c["times"])
+    assert open(os.path.join(ref, "chk00002", "Header")).read() == open(os.path.join(out, "Header")).read()
+    for lev in range(2):
+        for name in ("f_00_H", "f_00_D_00000", "g_00_H", "g_00_D_00000"):
+            assert filecmp.cmp(os.path.join(ref, "chk00002", f"Level_{lev}", name), os.path.join(out, f"Level_{lev}", name),
+                               shallow=False), (lev, name)
+    _run_amr(O, mine, deck_text, ["max_step=4", "amr.chk_int=-1", "amr.plot_int=4", "amr.restart=chk00002"])
+    for lev in range(2):
+        a, b = O.read_plotfile(os.path.join(ref, "plt00004"), lev), O.read_plotfile(os.path.join(mine, "plt00004"), lev)
+        for k in ("rho", "vel_x", "two_rho_e", "f_05", "g_11"):
+            assert np.array_equal(a[k], b[k], equal_nan=True), (lev, k)

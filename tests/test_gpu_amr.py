@@ -290,6 +290,28 @@ def test_amr_eb_forces_match_reference_forces_file():
     amr.close()
 
 
+def test_amr_checkpoint_restart_on_the_device(tmp_path):
+    """LBM::write_checkpoint_file / read_checkpoint_file for a hierarchy: the state after 2 coarse steps written as a
+    checkpoint, loaded into a new object, both run on -- bit-identical -- and the golden of step 4 is met"""
+    from marbles_b200.amr import AmrLBM
+    from marbles_b200.inputs import parse_deck
+    a, z, deck_text, steps, boxes, is_fluid = new_amr("amr2_chcyl")
+    a.step(2)
+    path = a.write_checkpoint_file(str(tmp_path))
+    assert os.path.basename(path) == "chk00002" and os.path.exists(os.path.join(path, "Level_1", "g_00_D_00000"))
+    b = AmrLBM.from_checkpoint(parse_deck(text=deck_text), path, is_fluid)
+    assert b.isteps == 2 and b.time == 2.0 and b.boxes == a.boxes
+    a.step(2, want_macrodata=True)
+    b.step(2, want_macrodata=True)
+    a.compute_derived(), b.compute_derived()
+    for lev in range(2):
+        for w in ("f", "g", "macro"):
+            assert np.array_equal(a.dense(lev, w), b.dense(lev, w), equal_nan=True), (lev, w)
+    compare_levels(b, lambda lev: golden_level(z, 4, lev), 4, b.inp)
+    a.close()
+    b.close()
+
+
 def test_level_bind_is_zero_copy_and_bit_identical():
     """mbl_level_bind: the fine level's boxes live in caller-owned device memory (torch tensors standing in for the
     FABs of an AMReX device-arena MultiFab, 27 comps x 3 ghost cells); every operator leaves its result there"""
