@@ -843,7 +843,9 @@ constexpr int MARCH_KEEP_SLOTS = 9;  // P: rho, jx, jy, jz, e2 of plane k-1 so f
 constexpr int march_slots(bool pipe) { return pipe ? 3 * NQ + MARCH_KEEP_SLOTS : NQ + MARCH_KEEP_SLOTS; }
 // ABL (MBL_EXPERIMENTS, timing only -- results are wrong): 1 no x shuffles, 2 no y exchange and no barriers, 4 no
 // carried stores (the sums become dead code)
-template <int W, bool PIPE, int ABL = 0>
+// ORD (MBL_EXPERIMENTS, plain path): order in which a plane's loads are issued -- 0: g (cp.async), f, mask / QCorr;
+// 1: f, mask / QCorr, g;  2: mask / QCorr, f, g.  Results identical.
+template <int W, bool PIPE, int ABL = 0, int ORD = 0>
 __global__ void __launch_bounds__(32 * W, PIPE ? (W <= 4 ? 2 : 1) : (W <= 4 ? 3 : W <= 8 ? 2 : 1))
     k_collide_tile_march(const __grid_constant__ CarryPtrs A, const __grid_constant__ MarchOut Q,
                          const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ flag,
@@ -887,7 +889,7 @@ __global__ void __launch_bounds__(32 * W, PIPE ? (W <= 4 ? 2 : 1) : (W <= 4 ? 3 
     };
     const unsigned cxy = (unsigned)(is + OX) * 8u + (unsigned)(j + GY) * px8;
     // populations of plane k: g -> g buffer `buf`, f -> registers (plain) or the f slots (PIPE)
-    auto pull = [&](int k, int buf, double* f) {
+    auto pull = [&](int k, int buf, double* f, int which = 3) {  // which: 1 = g, 2 = f
         zo[2] = (L.wrap[2] && k == 0) ? (unsigned)(L.nz - 1) * sz8 : 0u - sz8;
         zo[0] = (L.wrap[2] && k == L.nz - 1) ? 0u - (unsigned)(L.nz - 1) * sz8 : sz8;
         const unsigned c = cxy + (unsigned)(k + GZ) * sz8;
@@ -896,17 +898,19 @@ __global__ void __launch_bounds__(32 * W, PIPE ? (W <= 4 ? 2 : 1) : (W <= 4 ? 3 
         for (int b = 0; b < 3; ++b)
 #pragma unroll
             for (int d = 0; d < 3; ++d) cyz[b][d] = c + yo[b] + zo[d];
-        static_for<0, NQ>([&](auto qc_) {
-            constexpr int Qd = decltype(qc_)::value;
-            cp_async8(sg0_addr + (buf * NQ + Qd) * T * 8, (const char*)A.gin[Qd] + (cyz[ey(Qd) + 1][ez(Qd) + 1] + xo[ex(Qd) + 1]));
-        });
-        static_for<0, NQ>([&](auto qc_) {
-            constexpr int Qd = decltype(qc_)::value;
-            if constexpr (PIPE)
-                cp_async8(sg0_addr + (2 * NQ + Qd) * T * 8, (const char*)A.fin[Qd] + (cyz[ey(Qd) + 1][ez(Qd) + 1] + xo[ex(Qd) + 1]));
-            else
-                f[Qd] = ldb(A.fin[Qd], cyz[ey(Qd) + 1][ez(Qd) + 1] + xo[ex(Qd) + 1]);
-        });
+        if (which & 1)
+            static_for<0, NQ>([&](auto qc_) {
+                constexpr int Qd = decltype(qc_)::value;
+                cp_async8(sg0_addr + (buf * NQ + Qd) * T * 8, (const char*)A.gin[Qd] + (cyz[ey(Qd) + 1][ez(Qd) + 1] + xo[ex(Qd) + 1]));
+            });
+        if (which & 2)
+            static_for<0, NQ>([&](auto qc_) {
+                constexpr int Qd = decltype(qc_)::value;
+                if constexpr (PIPE)
+                    cp_async8(sg0_addr + (2 * NQ + Qd) * T * 8, (const char*)A.fin[Qd] + (cyz[ey(Qd) + 1][ez(Qd) + 1] + xo[ex(Qd) + 1]));
+                else
+                    f[Qd] = ldb(A.fin[Qd], cyz[ey(Qd) + 1][ez(Qd) + 1] + xo[ex(Qd) + 1]);
+            });
     };
     // mask, gradient flags and the six QCorr neighbours of plane k
     struct Small {
@@ -941,6 +945,14 @@ __global__ void __launch_bounds__(32 * W, PIPE ? (W <= 4 ? 2 : 1) : (W <= 4 ? 3 
             cp_async_wait_all();
 #pragma unroll
             for (int q = 0; q < NQ; ++q) f[q] = sg0[(2 * NQ + q) * T];
+        } else if constexpr (ORD == 1) {
+            pull(k, 0, f, 2);
+            S = pull_small(k);
+            pull(k, 0, f, 1);
+        } else if constexpr (ORD == 2) {
+            S = pull_small(k);
+            pull(k, 0, f, 2);
+            pull(k, 0, f, 1);
         } else {
             pull(k, 0, f);
             S = pull_small(k);
@@ -2039,17 +2051,17 @@ int launch_collide_tile_pair(const Layout& L, const Phys& P, const CarryPlan& C,
 }
 
 // variant 9.  Returns the number of kernels, -1 if a component exceeds 4 GB, -2 if a chunk would hold one plane
-template <int W, bool PIPE, int ABL = 0>
+template <int W, bool PIPE, int ABL = 0, int ORD = 0>
 static void run_collide_tile_march(dim3 grid, cudaStream_t st, const CarryPtrs& A, const MarchOut& Q, const uint32_t* nbr,
                                    const uint8_t* flag, const Layout& L, const Phys& P, const CarryPlan& Ce, int ka, int kb, int zm)
 {
     const size_t sm = (size_t)march_slots(PIPE) * 32 * W * 8;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_collide_tile_march<W, PIPE, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaFuncSetAttribute(k_collide_tile_march<W, PIPE, ABL, ORD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         attr_done = true;
     }
-    k_collide_tile_march<W, PIPE, ABL><<<grid, 32 * W, sm, st>>>(A, Q, nbr, flag, L, P, Ce, ka, kb, zm);
+    k_collide_tile_march<W, PIPE, ABL, ORD><<<grid, 32 * W, sm, st>>>(A, Q, nbr, flag, L, P, Ce, ka, kb, zm);
 }
 
 // rows per CTA the z-march kernels are built for: 6 (plain); 4 and 8 (pipelined: a measured negative result,
@@ -2093,6 +2105,9 @@ int launch_collide_tile_march(const Layout& L, const Phys& P, const CarryPlan& C
     if (!pipe && abl == 2) { run_collide_tile_march<6, false, 2>(grid, st, A, Q, nbr, flag, L, P, Ce, ka, kb, zm); return 1; }
     if (!pipe && abl == 4) { run_collide_tile_march<6, false, 4>(grid, st, A, Q, nbr, flag, L, P, Ce, ka, kb, zm); return 1; }
     if (!pipe && abl == 6) { run_collide_tile_march<6, false, 6>(grid, st, A, Q, nbr, flag, L, P, Ce, ka, kb, zm); return 1; }
+    static const int ord = getenv("MBL_LOADORDER") ? atoi(getenv("MBL_LOADORDER")) : 0;  // results identical
+    if (!pipe && ord == 1) { run_collide_tile_march<6, false, 0, 1>(grid, st, A, Q, nbr, flag, L, P, Ce, ka, kb, zm); return 1; }
+    if (!pipe && ord == 2) { run_collide_tile_march<6, false, 0, 2>(grid, st, A, Q, nbr, flag, L, P, Ce, ka, kb, zm); return 1; }
 #endif
     if (!pipe) run_collide_tile_march<6, false>(grid, st, A, Q, nbr, flag, L, P, Ce, ka, kb, zm);
 #ifdef MBL_EXPERIMENTS
