@@ -144,28 +144,42 @@ def write_plotfile(path: str, names: list[str], data: np.ndarray, *, time: float
 
 
 def write_plotfile_levels(path: str, names: list[str], levels, *, time: float, level_steps, prob_lo, prob_hi, n_cell,
-                          ref_ratio: int = 2) -> None:
+                          ref_ratio: int = 2, rank: int = 0, owners=None, gather=None) -> None:
     """amrex::WriteMultiLevelPlotfile for a hierarchy (Source/LBM.cpp:1677-1690; AMReX_PlotFileUtil.cpp): levels[lev] =
     (boxes, fabs) with boxes = [(lo, hi), ...] in the index space of level lev and fabs[i] = [ncomp, nz, ny, nx] float64 of
     box i (the level's BoxArray order); level_steps[lev] = m_isteps[lev]; n_cell = cells of level 0.  One process:
-    every level's FABs go to Level_<lev>/Cell_D_00000."""
+    every level's FABs go to Level_<lev>/Cell_D_00000.  Distributed levels (owners[lev][i] = rank of box i, fabs[i] only
+    for this rank's boxes, `gather(obj) -> [obj of rank 0, obj of rank 1, ...]` the only communication): every rank writes
+    its FABs into Level_<lev>/Cell_D_<rank> and rank 0 the headers, the layout VisMF uses when every rank owns a file."""
     ncomp, nlev = len(names), len(levels)
     dx0 = [(float(prob_hi[d]) - float(prob_lo[d])) / n_cell[d] for d in range(3)]
+    mine_all = []
     for lev, (boxes, fabs) in enumerate(levels):
         assert len(boxes) == len(fabs)
         lev_dir = os.path.join(path, f"Level_{lev}")
         os.makedirs(lev_dir, exist_ok=True)
-        offsets, mins, maxs = [], [], []
-        with open(os.path.join(lev_dir, "Cell_D_00000"), "wb") as fh:
-            for (lo, hi), fab in zip(boxes, fabs):
-                fab = np.ascontiguousarray(fab, dtype="<f8")
-                assert fab.shape == (ncomp, hi[2] - lo[2] + 1, hi[1] - lo[1] + 1, hi[0] - lo[0] + 1), (fab.shape, lo, hi)
-                offsets.append(fh.tell())
-                fh.write(f"{FAB_HEADER}{_box(lo, hi)} {ncomp}\n".encode())
-                fh.write(fab.tobytes())
-                flat = fab.reshape(ncomp, -1)
-                mins.append(flat.min(axis=1))
-                maxs.append(flat.max(axis=1))
+        own = owners[lev] if owners is not None else [rank] * len(boxes)
+        mine = {}
+        if any(o == rank for o in own):
+            with open(os.path.join(lev_dir, f"Cell_D_{rank:05d}"), "wb") as fh:
+                for ib, ((lo, hi), fab) in enumerate(zip(boxes, fabs)):
+                    if own[ib] != rank:
+                        continue
+                    fab = np.ascontiguousarray(fab, dtype="<f8")
+                    assert fab.shape == (ncomp, hi[2] - lo[2] + 1, hi[1] - lo[1] + 1, hi[0] - lo[0] + 1), (fab.shape, lo, hi)
+                    off = fh.tell()
+                    fh.write(f"{FAB_HEADER}{_box(lo, hi)} {ncomp}\n".encode())
+                    fh.write(fab.tobytes())
+                    flat = fab.reshape(ncomp, -1)
+                    mine[ib] = (off, flat.min(axis=1).tolist(), flat.max(axis=1).tolist())
+        mine_all.append(mine)
+    parts = gather(mine_all) if gather is not None else [mine_all]
+    if rank != 0:
+        return
+    for lev, (boxes, _) in enumerate(levels):
+        lev_dir = os.path.join(path, f"Level_{lev}")
+        own = owners[lev] if owners is not None else [0] * len(boxes)
+        rec = [parts[own[ib]][lev][ib] for ib in range(len(boxes))]
         with open(os.path.join(lev_dir, "Cell_H"), "w") as fh:
             fh.write(f"1\n1\n{ncomp}\n0\n")
             fh.write(f"({len(boxes)} 0\n")
@@ -173,13 +187,13 @@ def write_plotfile_levels(path: str, names: list[str], levels, *, time: float, l
                 fh.write(_box(lo, hi) + "\n")
             fh.write(")\n")
             fh.write(f"{len(boxes)}\n")
-            for off in offsets:
-                fh.write(f"FabOnDisk: Cell_D_00000 {off}\n")
+            for ib, r in enumerate(rec):
+                fh.write(f"FabOnDisk: Cell_D_{own[ib]:05d} {r[0]}\n")
             fh.write("\n")
-            for table in (mins, maxs):
+            for col in (1, 2):
                 fh.write(f"{len(boxes)},{ncomp}\n")
-                for row in table:
-                    fh.write("".join("%.17e," % v for v in row) + "\n")
+                for r in rec:
+                    fh.write("".join("%.17e," % v for v in r[col]) + "\n")
                 fh.write("\n")
     with open(os.path.join(path, "Header"), "w") as fh:
         fh.write("HyperCLaw-V1.1\n")
@@ -211,7 +225,7 @@ def write_amr_plotfile(amr, directory: str = ".", prefix: str = "plt", save_stre
                        save_derived: bool | None = None, digits: int = 5) -> str:
     """LBM::write_plot_file for a multi-level state (marbles_b200.amr.AmrLBM, all boxes on this rank): the macrodata of
     every level must be current (last step with want_macrodata=True) and compute_derived() called, as post_time_step
-    leaves them."""
+    leaves them.  With distributed levels a collective call: every rank writes the FABs it holds."""
     deck = amr.inp.deck
 
     def deck_int(key: str, default: int) -> int:
@@ -220,8 +234,6 @@ def write_amr_plotfile(amr, directory: str = ".", prefix: str = "plt", save_stre
             v = v[0]
         return int(str(v).split()[0])
 
-    if amr.world != 1:
-        raise NotImplementedError("write_amr_plotfile: distributed levels write their FABs per rank -- not implemented")
     if save_streaming is None:
         save_streaming = bool(deck_int("lbm.save_streaming", 1))
     if save_derived is None:
@@ -231,6 +243,9 @@ def write_amr_plotfile(amr, directory: str = ".", prefix: str = "plt", save_stre
     for lev in range(amr.finest + 1):
         fabs = []
         for ib in range(len(amr.boxes[lev])):
+            if not amr.is_local(lev, ib):
+                fabs.append(None)  # another rank writes it
+                continue
             parts = [amr.get_box_macrodata(lev, ib, derived=False)]
             if save_streaming:
                 parts += [amr.get_box(lev, ib, 0), amr.get_box(lev, ib, 1)]
@@ -241,8 +256,18 @@ def write_amr_plotfile(amr, directory: str = ".", prefix: str = "plt", save_stre
             fabs.append(np.concatenate(parts, axis=0))
         levels.append((amr.boxes[lev], fabs))
     path = os.path.join(directory, plot_file_name(prefix, amr.isteps, digits))
+    gather = None
+    if amr.world > 1:  # collective call: every rank writes its FABs, rank 0 the headers
+        import torch.distributed as dist
+
+        def gather(obj):
+            out = [None] * amr.world
+            dist.all_gather_object(out, obj)
+            return out
+
     write_plotfile_levels(path, names, levels, time=amr.time, level_steps=[amr.isteps * 2 ** l for l in range(amr.finest + 1)],
-                          prob_lo=amr.inp.prob_lo, prob_hi=amr.inp.prob_hi, n_cell=amr.inp.n_cell)
+                          prob_lo=amr.inp.prob_lo, prob_hi=amr.inp.prob_hi, n_cell=amr.inp.n_cell, rank=amr.rank,
+                          owners=amr.owner if amr.world > 1 else None, gather=gather)
     return path
 
 

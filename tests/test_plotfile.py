@@ -57,6 +57,43 @@ def test_multilevel_plotfile_bytes_match_reference(tmp_path):
             assert np.array_equal(pf["rho"][lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1], fab[0])
 
 
+def test_multilevel_plotfile_written_by_several_ranks(tmp_path):
+    """distributed levels: every rank writes the FABs it holds into Level_k/Cell_D_<rank>, rank 0 the headers (boxes in
+    the level's order, FabOnDisk pointing into the owners' files).  Same Header as the reference's, and the oracle's
+    reader gets every box back."""
+    from oracle import oracle as O
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "plt_amr3.npz"))
+    names = [str(n) for n in z["names"]]
+    nlev, world = int(z["nlev"]), 3
+    boxes = [[(tuple(int(v) for v in b[0]), tuple(int(v) for v in b[1])) for b in z[f"boxes_{lev}"]] for lev in range(nlev)]
+    owners = [[(ib + lev) % world for ib in range(len(boxes[lev]))] for lev in range(nlev)]
+    out = str(tmp_path / "plt00002")
+    contributions = {}
+
+    def write(rank):
+        levels = [(boxes[lev], [z[f"fab_{lev}_{ib}"] if owners[lev][ib] == rank else None for ib in range(len(boxes[lev]))])
+                  for lev in range(nlev)]
+
+        def gather(obj):
+            contributions[rank] = obj
+            return [contributions.get(r) for r in range(world)]
+
+        P.write_plotfile_levels(out, names, levels, time=float(z["time"]), level_steps=[2 * 2 ** l for l in range(nlev)],
+                                prob_lo=[-1, -1, -1], prob_hi=[1, 1, 1], n_cell=(8, 8, 8), rank=rank, owners=owners,
+                                gather=gather)
+
+    for rank in (2, 1, 0):  # rank 0 last: it writes the headers from everybody's offsets and extrema
+        write(rank)
+    assert open(os.path.join(out, "Header")).read() == str(z["header"])
+    assert sorted(os.listdir(os.path.join(out, "Level_1"))) == ["Cell_D_00000", "Cell_D_00001", "Cell_D_00002", "Cell_H"]
+    for lev in range(nlev):
+        pf = O.read_plotfile(out, lev)
+        assert [(tuple(a), tuple(b)) for a, b in O.read_plotfile_boxes(out, lev)] == boxes[lev]
+        for ib, (lo, hi) in enumerate(boxes[lev]):
+            for c, nm in enumerate(names):
+                assert np.array_equal(pf[nm][lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1], z[f"fab_{lev}_{ib}"][c])
+
+
 @pytest.mark.parametrize("shape,mgs", [((5, 6, 7), 4), ((8, 8, 8), 8), ((3, 16, 4), 32)])
 def test_plotfile_round_trip_through_oracle_reader(tmp_path, shape, mgs):
     from oracle import oracle as O
