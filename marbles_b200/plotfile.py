@@ -489,26 +489,48 @@ def read_checkpoint(path: str) -> dict:
     return out
 
 
-def _write_vismf_fabs(lev_dir: str, prefix: str, fabs, ng: int, boxes) -> None:
+def _write_vismf_fabs(lev_dir: str, prefix: str, fabs, ng: int, boxes, rank: int = 0, own=None, gather=None) -> None:
     """VisMF::Write of a MultiFab given FAB by FAB: fabs[i] = [ncomp, nz+2ng, ny+2ng, nx+2ng] of box i with its ghost
-    cells; minima / maxima over the valid box"""
+    cells; minima / maxima over the valid box.  Distributed (own[i] = rank of box i, fabs[i] only for this rank's boxes):
+    every rank writes `<prefix>_D_<rank>`, rank 0 the header from the gathered offsets and extrema."""
     os.makedirs(lev_dir, exist_ok=True)
-    ncomp = fabs[0].shape[0]
-    dname = f"{prefix}_D_00000"
-    part = {"file": dname, "boxes": [(tuple(lo), tuple(hi)) for lo, hi in boxes], "offsets": [], "mins": [], "maxs": []}
-    with open(os.path.join(lev_dir, dname), "wb") as fh:
-        for (lo, hi), fab in zip(boxes, fabs):
-            fab = np.ascontiguousarray(fab, dtype="<f8")
-            assert fab.shape == (ncomp,) + tuple(hi[d] - lo[d] + 1 + 2 * ng for d in (2, 1, 0))
-            part["offsets"].append(fh.tell())
-            glo, ghi = _grown(lo, hi, ng)
-            fh.write(f"{FAB_HEADER}{_box(glo, ghi)} {ncomp}\n".encode())
-            fh.write(fab.tobytes())
-            val = fab[:, ng:fab.shape[1] - ng, ng:fab.shape[2] - ng, ng:fab.shape[3] - ng] if ng else fab
-            flat = val.reshape(ncomp, -1)
-            part["mins"].append(flat.min(axis=1).tolist())
-            part["maxs"].append(flat.max(axis=1).tolist())
-    _write_vismf_header(lev_dir, prefix, ncomp, ng, [part])
+    own = own if own is not None else [rank] * len(boxes)
+    mine, ncomp = {}, None
+    if any(o == rank for o in own):
+        with open(os.path.join(lev_dir, f"{prefix}_D_{rank:05d}"), "wb") as fh:
+            for ib, ((lo, hi), fab) in enumerate(zip(boxes, fabs)):
+                if own[ib] != rank:
+                    continue
+                fab = np.ascontiguousarray(fab, dtype="<f8")
+                ncomp = fab.shape[0]
+                assert fab.shape == (ncomp,) + tuple(hi[d] - lo[d] + 1 + 2 * ng for d in (2, 1, 0))
+                off = fh.tell()
+                glo, ghi = _grown(lo, hi, ng)
+                fh.write(f"{FAB_HEADER}{_box(glo, ghi)} {ncomp}\n".encode())
+                fh.write(fab.tobytes())
+                val = fab[:, ng:fab.shape[1] - ng, ng:fab.shape[2] - ng, ng:fab.shape[3] - ng] if ng else fab
+                flat = val.reshape(ncomp, -1)
+                mine[ib] = (off, flat.min(axis=1).tolist(), flat.max(axis=1).tolist(), ncomp)
+    parts = gather(mine) if gather is not None else [mine]
+    if rank != 0:
+        return
+    rec = [parts[own[ib]][ib] for ib in range(len(boxes))]
+    ncomp = rec[0][3]
+    with open(os.path.join(lev_dir, f"{prefix}_H"), "w") as fh:
+        fh.write(f"1\n1\n{ncomp}\n{ng}\n")
+        fh.write(f"({len(boxes)} 0\n")
+        for lo, hi in boxes:
+            fh.write(_box(lo, hi) + "\n")
+        fh.write(")\n")
+        fh.write(f"{len(boxes)}\n")
+        for ib, r in enumerate(rec):
+            fh.write(f"FabOnDisk: {prefix}_D_{own[ib]:05d} {r[0]}\n")
+        fh.write("\n")
+        for col in (1, 2):
+            fh.write(f"{len(boxes)},{ncomp}\n")
+            for r in rec:
+                fh.write("".join("%.17e," % v for v in r[col]) + "\n")
+            fh.write("\n")
 
 
 def _read_vismf_fabs(lev_dir: str, prefix: str):
@@ -536,13 +558,16 @@ def _read_vismf_fabs(lev_dir: str, prefix: str):
     return fabs, ng, boxes
 
 
-def write_checkpoint_levels(path: str, levels, *, isteps, dts, times, ng: int = 3) -> None:
+def write_checkpoint_levels(path: str, levels, *, isteps, dts, times, ng: int = 3, rank: int = 0, owners=None,
+                            gather=None) -> None:
     """LBM::write_checkpoint_file (Source/LBM.cpp:1692-1783) for a hierarchy: levels[lev] = (boxes, f_fabs, g_fabs) with
     the FABs of every box INCLUDING their ng ghost cells (VisMF::Write stores them); isteps / dts / times are the
     reference's m_isteps / m_dts / m_ts_new, one entry per level up to amr.max_level (levels that do not exist keep
-    their initial values there)."""
+    their initial values there).  Distributed levels: owners[lev][i] = rank of box i, FABs only for this rank's boxes,
+    `gather` as in write_plotfile_levels; every rank writes its data files, rank 0 the headers."""
     os.makedirs(path, exist_ok=True)
-    with open(os.path.join(path, "Header"), "w") as fh:
+    if rank == 0:
+      with open(os.path.join(path, "Header"), "w") as fh:
         fh.write(f"Checkpoint file for LBM\n{len(levels) - 1}\n")
         fh.write("".join(f"{int(v)} " for v in isteps) + "\n")
         fh.write("".join(f"{_g17(v)} " for v in dts) + "\n")
@@ -554,8 +579,9 @@ def write_checkpoint_levels(path: str, levels, *, isteps, dts, times, ng: int = 
             fh.write(")\n")
     for lev, (boxes, ff, gg) in enumerate(levels):
         lev_dir = os.path.join(path, f"Level_{lev}")
-        _write_vismf_fabs(lev_dir, "f_00", ff, ng, boxes)
-        _write_vismf_fabs(lev_dir, "g_00", gg, ng, boxes)
+        own = owners[lev] if owners is not None else None
+        _write_vismf_fabs(lev_dir, "f_00", ff, ng, boxes, rank, own, gather)
+        _write_vismf_fabs(lev_dir, "g_00", gg, ng, boxes, rank, own, gather)
 
 
 def read_checkpoint_levels(path: str) -> dict:
@@ -574,17 +600,26 @@ def read_checkpoint_levels(path: str) -> dict:
 
 
 def write_amr_checkpoint(amr, directory: str = ".", prefix: str = "chk", digits: int = 5, max_level: int | None = None) -> str:
-    """LBM::write_checkpoint_file for a hierarchy on the device (all boxes on this rank): f and g of every box with their
-    3 ghost cells.  The unmodified reference restarts from it (amr.restart)."""
-    if amr.world != 1:
-        raise NotImplementedError("write_amr_checkpoint: distributed levels write their FABs per rank -- not implemented")
+    """LBM::write_checkpoint_file for a hierarchy on the device: f and g of every box with their 3 ghost cells.  The
+    unmodified reference restarts from it (amr.restart).  With distributed levels a collective call."""
     nl = amr.finest + 1
     nmax = (max_level if max_level is not None else amr.finest) + 1
-    levels = [(amr.boxes[lev], [amr.get_box(lev, ib, 0, ng=3) for ib in range(len(amr.boxes[lev]))],
-               [amr.get_box(lev, ib, 1, ng=3) for ib in range(len(amr.boxes[lev]))]) for lev in range(nl)]
+    fab = lambda lev, ib, which: amr.get_box(lev, ib, which, ng=3) if amr.is_local(lev, ib) else None
+    levels = [(amr.boxes[lev], [fab(lev, ib, 0) for ib in range(len(amr.boxes[lev]))],
+               [fab(lev, ib, 1) for ib in range(len(amr.boxes[lev]))]) for lev in range(nl)]
     path = os.path.join(directory, chk_file_name(prefix, amr.isteps, digits))
+    gather = None
+    if amr.world > 1:  # collective call: every rank writes the FABs it holds, rank 0 the headers
+        import torch.distributed as dist
+
+        def gather(obj):
+            out = [None] * amr.world
+            dist.all_gather_object(out, obj)
+            return out
+
     write_checkpoint_levels(path, levels, isteps=[amr.isteps * 2 ** l if l < nl else 0 for l in range(nmax)],
-                            dts=[1.0 / 2 ** l for l in range(nmax)], times=[amr.time if l < nl else 0.0 for l in range(nmax)])
+                            dts=[1.0 / 2 ** l for l in range(nmax)], times=[amr.time if l < nl else 0.0 for l in range(nmax)],
+                            rank=amr.rank, owners=amr.owner if amr.world > 1 else None, gather=gather)
     return path
 
 

@@ -134,3 +134,50 @@ def test_multilevel_checkpoint_round_trip_and_reference_restart(tmp_path):
         a, b = O.read_plotfile(os.path.join(ref, "plt00004"), lev), O.read_plotfile(os.path.join(mine, "plt00004"), lev)
         for k in ("rho", "vel_x", "two_rho_e", "f_05", "g_11"):
             assert np.array_equal(a[k], b[k], equal_nan=True), (lev, k)
+
+
+def test_multilevel_checkpoint_written_by_two_ranks_restarts_the_reference(tmp_path):
+    """distributed hierarchies: every rank writes the FABs it holds (f_00_D_<rank>, g_00_D_<rank>), rank 0 the headers.
+    Read back FAB by FAB it is the original data, and the unmodified reference restarts from it."""
+    from conftest import load_amr_golden
+    O = _ref()
+    z, deck_text, steps, boxes, is_fluid = load_amr_golden("amr2_chcyl")
+    ref = str(tmp_path / "ref")
+    _run_amr(O, ref, deck_text, ["max_step=4", "amr.chk_int=2", "amr.plot_int=4"])
+    c = P.read_checkpoint_levels(os.path.join(ref, "chk00002"))
+    world = 2
+    owners = [[(ib + lev) % world for ib in range(len(lv[0]))] for lev, lv in enumerate(c["levels"])]
+    mine = str(tmp_path / "mine")
+    os.makedirs(mine)
+    out = os.path.join(mine, "chk00002")
+    store, calls = {}, {}
+
+    def write(rank):
+        calls[rank] = 0
+
+        def gather(obj):  # the n-th collective of every rank meets the n-th of the others
+            store[(calls[rank], rank)] = obj
+            parts = [store.get((calls[rank], r)) for r in range(world)]
+            calls[rank] += 1
+            return parts
+
+        levels = [(bx, [f if owners[lev][ib] == rank else None for ib, f in enumerate(ff)],
+                   [g if owners[lev][ib] == rank else None for ib, g in enumerate(gg)])
+                  for lev, (bx, ff, gg) in enumerate(c["levels"])]
+        P.write_checkpoint_levels(out, levels, isteps=c["isteps"], dts=c["dts"], times=c["times"], rank=rank, owners=owners,
+                                  gather=gather)
+
+    write(1)
+    write(0)
+    assert open(os.path.join(ref, "chk00002", "Header")).read() == open(os.path.join(out, "Header")).read()
+    assert sorted(os.listdir(os.path.join(out, "Level_0"))) == ["f_00_D_00000", "f_00_D_00001", "f_00_H", "g_00_D_00000",
+                                                                "g_00_D_00001", "g_00_H"]
+    back = P.read_checkpoint_levels(out)
+    for (bx, ff, gg), (bx2, ff2, gg2) in zip(c["levels"], back["levels"]):
+        assert bx == bx2
+        assert all(np.array_equal(a, b) for a, b in zip(ff, ff2)) and all(np.array_equal(a, b) for a, b in zip(gg, gg2))
+    _run_amr(O, mine, deck_text, ["max_step=4", "amr.chk_int=-1", "amr.plot_int=4", "amr.restart=chk00002"])
+    for lev in range(2):
+        a, b = O.read_plotfile(os.path.join(ref, "plt00004"), lev), O.read_plotfile(os.path.join(mine, "plt00004"), lev)
+        for k in ("rho", "two_rho_e", "f_05", "g_11"):
+            assert np.array_equal(a[k], b[k], equal_nan=True), (lev, k)
