@@ -48,6 +48,25 @@ if rank == 0:
         files = sorted(f for f in os.listdir(os.path.join(path, f"Level_{lev}")) if f.startswith("Cell_D"))
         print(f"level {lev}: {len(ref)} components, worst {worst:.2e} ({key}), data files {files}", flush=True)
     print("eb forces summed over ranks:", forces.cpu().numpy(), flush=True)
+# the checkpoint of the distributed hierarchy (collective), loaded by ONE rank into an undistributed object
+chk = amr.write_checkpoint_file(tmp[0])
+mine = [{w: amr.dense(lev, w) for w in ("f", "g")} for lev in range(amr.finest + 1)]
+parts = [None] * world
+dist.all_gather_object(parts, mine)
+if rank == 0:
+    from marbles_b200.amr import merge_dense
+    one = AmrLBM.from_checkpoint(parse_deck(text=deck_text), chk, is_fluid, device=local)
+    # (solid cells differ by design: the restart zeroes them, fill_f_inside_eb, where the running state holds the -1 sentinel)
+    same = True
+    for lev in range(one.finest + 1):
+        fluid = np.asarray(is_fluid[lev]) == 1
+        for w in ("f", "g"):
+            a, b = merge_dense([p[lev][w] for p in parts]), one.dense(lev, w)
+            same = same and np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[:, fluid], b[:, fluid], equal_nan=True)
+    files = sorted(os.listdir(os.path.join(chk, "Level_1")))
+    print(f"checkpoint {os.path.basename(chk)}: {files}; restored on one rank == distributed state: {same}", flush=True)
+    ok = ok and same
+    one.close()
 dist.barrier()
 dist.destroy_process_group()
 amr.close()
