@@ -113,3 +113,14 @@ def test_plain_c_caller_on_device(tmp_path):
     """the same C program on the GPU box: defines a level, initialises a periodic box, steps it 8 times through
     mbl_step and checks mass conservation -- the C ABI driven from plain C on a device"""
     assert _run_c_caller(tmp_path).startswith("DEVICE")
+
+
+def test_every_entry_point_is_documented_in_integration_md():
+    """INTEGRATION.md names, for every function the header declares, the reference interface it stands for"""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "marbles_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    syms = sorted(set(re.findall(r"\b(mbl_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(syms) >= 60
+    assert [s for s in syms if s not in doc] == []
